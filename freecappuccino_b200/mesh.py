@@ -1,0 +1,464 @@
+"""Mesh arrays in the layout of the reference's ``module geometry``.
+
+This is the *input contract* of the pressure-correction path: the arrays the
+Fortran host owns after ``mesh_geometry`` has run
+(``src/mesh_geometry_and_topology.f90:13-98``; parallel additions
+``src-parallel/mesh_geometry_and_topology.f90:497-515, 637-660, 879-881``).
+Index arrays are 1-based int32, reals are float64, exactly as Fortran keeps
+them, so they can be handed to the C-ABI unchanged.
+
+Contents
+  * :class:`Mesh`            -- the array bundle
+  * :func:`hex_mesh`         -- synthetic structured-hex generator (configs 3/4)
+  * :func:`geometry_from_polymesh` / :func:`read_polymesh` -- OpenFOAM polyMesh
+    reader restating ``mesh_geometry`` (:859-1081) for the shipped cases
+  * :func:`partition`        -- cell partitioner emitting per-rank meshes with
+    processor faces + halo slots like an OpenFOAM ``decomposePar`` +
+    the reference's ``process`` file
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+import re
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# boundary kinds in the order their slots follow the cells in every field array
+# (mesh_geometry_and_topology.f90:597-609)
+KINDS = ("inlet", "outlet", "symmetry", "wall", "prOutlet")
+
+
+@dataclasses.dataclass
+class Mesh:
+    numCells: int
+    numInnerFaces: int
+    numFaces: int
+    owner: np.ndarray       # int32 [numFaces], 1-based
+    neighbour: np.ndarray   # int32 [numInnerFaces], 1-based
+    xc: np.ndarray
+    yc: np.ndarray
+    zc: np.ndarray
+    vol: np.ndarray         # [numCells (+npro in a partitioned mesh)]
+    arx: np.ndarray
+    ary: np.ndarray
+    arz: np.ndarray
+    xf: np.ndarray
+    yf: np.ndarray
+    zf: np.ndarray          # [numFaces]
+    facint: np.ndarray      # [numInnerFaces]
+    # boundary kinds: count and 0-based "FacesStart" (face = start + i, i = 1..count)
+    counts: Dict[str, int] = dataclasses.field(default_factory=dict)
+    starts: Dict[str, int] = dataclasses.field(default_factory=dict)
+    # processor boundary (partitioned meshes only)
+    npro: int = 0
+    iProcFacesStart: int = 0
+    fpro: Optional[np.ndarray] = None
+    neighbProcNo: Optional[np.ndarray] = None      # [numConnections], 0-based ranks
+    neighbProcOffset: Optional[np.ndarray] = None  # [numConnections+1], 1-based like the reference
+    gloCells: int = 0
+    cell_global: Optional[np.ndarray] = None       # local cell -> global cell (0-based), partitioned only
+    # O-C cuts (none of the BASELINE configs has them; carried for the oracle)
+    noc: int = 0
+    iOCFacesStart: int = 0
+    ijl: Optional[np.ndarray] = None
+    ijr: Optional[np.ndarray] = None
+    ijlFace: Optional[np.ndarray] = None
+    foc: Optional[np.ndarray] = None
+
+    # ---- derived sizes (mesh_geometry_and_topology.f90:580-609) ----
+    @property
+    def numBoundaryFaces(self) -> int:
+        return self.numFaces - self.numInnerFaces
+
+    @property
+    def numTotal(self) -> int:
+        return self.numCells + self.numBoundaryFaces
+
+    @property
+    def numPCells(self) -> int:
+        return self.numCells + self.npro
+
+    @property
+    def nnz(self) -> int:
+        return self.numCells + 2 * self.numInnerFaces
+
+    def count(self, kind: str) -> int:
+        return int(self.counts.get(kind, 0))
+
+    def faces_start(self, kind: str) -> int:
+        return int(self.starts.get(kind, 0))
+
+    def slot_start(self, kind: str) -> int:
+        """0-based start of the boundary slots of ``kind`` (``iWallStart`` etc.)."""
+        s = self.numCells + self.npro
+        for k in KINDS:
+            if k == kind:
+                return s
+            s += self.count(k)
+        if kind == "oc":
+            return s
+        raise KeyError(kind)
+
+    def boundary_slots(self, kind: str) -> np.ndarray:
+        """0-based indices into a numTotal-sized field for the slots of ``kind``."""
+        s = self.slot_start(kind)
+        return np.arange(s, s + self.count(kind))
+
+    def boundary_faces(self, kind: str) -> np.ndarray:
+        """0-based face indices of ``kind``."""
+        s = self.faces_start(kind)
+        return np.arange(s, s + self.count(kind))
+
+
+# --------------------------------------------------------------------------
+# synthetic structured hex mesh
+# --------------------------------------------------------------------------
+def _group_patches(patch_kinds: Sequence[str]) -> List[int]:
+    """Order patches so faces of one kind are contiguous (the reference only
+    records the first ``startFace`` of each kind, :414-470)."""
+    seen: List[str] = []
+    for k in patch_kinds:
+        if k not in seen:
+            seen.append(k)
+    order: List[int] = []
+    for k in seen:
+        order += [i for i, pk in enumerate(patch_kinds) if pk == k]
+    return order
+
+
+def hex_mesh(nx: int, ny: int, nz: int, lengths: Tuple[float, float, float] = (1.0, 1.0, 1.0),
+             kinds: Sequence[str] = ("wall",) * 6) -> Mesh:
+    """Uniform hex mesh of a box, OpenFOAM (blockMesh) numbering.
+
+    Cell id ``i + nx*(j + ny*k)`` (+1).  Inner faces are ordered by owner then
+    neighbour ascending (upper-triangular order); boundary patches follow in the
+    order x-, x+, y-, y+, z-, z+ (regrouped so equal kinds are contiguous),
+    each ordered by owner.  ``kinds[p]`` in {inlet, outlet, symmetry, wall, prOutlet}.
+    """
+    lx, ly, lz = lengths
+    dx, dy, dz = lx / nx, ly / ny, lz / nz
+    n = nx * ny * nz
+    ii, jj, kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    # flatten in cell-id order: i fastest
+    order = np.argsort((ii + nx * (jj + ny * kk)).ravel(), kind="stable")
+    ci = ii.ravel()[order].astype(np.int64)
+    cj = jj.ravel()[order].astype(np.int64)
+    ck = kk.ravel()[order].astype(np.int64)
+    cid = np.arange(n, dtype=np.int64)
+    xc = (ci + 0.5) * dx
+    yc = (cj + 0.5) * dy
+    zc = (ck + 0.5) * dz
+    vol = np.full(n, dx * dy * dz)
+
+    # inner faces: per cell, candidates (+x, +y, +z) in that order
+    valid = np.stack([ci < nx - 1, cj < ny - 1, ck < nz - 1], axis=1)            # [n,3]
+    nb = np.stack([cid + 1, cid + nx, cid + nx * ny], axis=1)
+    own = np.repeat(cid[:, None], 3, axis=1)
+    dirn = np.tile(np.arange(3), (n, 1))
+    m = valid.ravel()
+    f_own = own.ravel()[m]
+    f_nb = nb.ravel()[m]
+    f_dir = dirn.ravel()[m]
+    nin = f_own.size
+    area = np.array([dy * dz, dx * dz, dx * dy])
+    half = np.array([0.5 * dx, 0.5 * dy, 0.5 * dz])
+    arx = np.where(f_dir == 0, area[0], 0.0)
+    ary = np.where(f_dir == 1, area[1], 0.0)
+    arz = np.where(f_dir == 2, area[2], 0.0)
+    xf = xc[f_own] + np.where(f_dir == 0, half[0], 0.0)
+    yf = yc[f_own] + np.where(f_dir == 1, half[1], 0.0)
+    zf = zc[f_own] + np.where(f_dir == 2, half[2], 0.0)
+    # facint = |x_j' - x_P| / |x_N - x_P| (:1040-1062)
+    dpn = np.sqrt((xc[f_nb] - xc[f_own]) ** 2 + (yc[f_nb] - yc[f_own]) ** 2 + (zc[f_nb] - zc[f_own]) ** 2)
+    djn = np.sqrt((xf - xc[f_own]) ** 2 + (yf - yc[f_own]) ** 2 + (zf - zc[f_own]) ** 2)
+    facint = djn / dpn
+
+    # boundary patches
+    patch_cells = [cid[ci == 0], cid[ci == nx - 1], cid[cj == 0], cid[cj == ny - 1], cid[ck == 0], cid[ck == nz - 1]]
+    patch_axis = [0, 0, 1, 1, 2, 2]
+    patch_sign = [-1.0, 1.0, -1.0, 1.0, -1.0, 1.0]
+    porder = _group_patches(list(kinds))
+    b_own, b_ar, b_xf = [], [], []
+    counts: Dict[str, int] = {}
+    starts: Dict[str, int] = {}
+    pos = nin
+    for p in porder:
+        cells = patch_cells[p]
+        ax, sg = patch_axis[p], patch_sign[p]
+        ar = np.zeros((cells.size, 3))
+        ar[:, ax] = sg * area[ax]
+        cf = np.stack([xc[cells], yc[cells], zc[cells]], axis=1)
+        cf[:, ax] += sg * half[ax]
+        b_own.append(cells)
+        b_ar.append(ar)
+        b_xf.append(cf)
+        k = kinds[p]
+        if k not in counts:
+            counts[k] = 0
+            starts[k] = pos
+        counts[k] += cells.size
+        pos += cells.size
+    b_own_a = np.concatenate(b_own)
+    b_ar_a = np.concatenate(b_ar)
+    b_xf_a = np.concatenate(b_xf)
+    owner = np.concatenate([f_own, b_own_a]) + 1
+    return Mesh(
+        numCells=n, numInnerFaces=nin, numFaces=owner.size,
+        owner=owner.astype(np.int32), neighbour=(f_nb + 1).astype(np.int32),
+        xc=xc, yc=yc, zc=zc, vol=vol,
+        arx=np.concatenate([arx, b_ar_a[:, 0]]), ary=np.concatenate([ary, b_ar_a[:, 1]]),
+        arz=np.concatenate([arz, b_ar_a[:, 2]]),
+        xf=np.concatenate([xf, b_xf_a[:, 0]]), yf=np.concatenate([yf, b_xf_a[:, 1]]),
+        zf=np.concatenate([zf, b_xf_a[:, 2]]),
+        facint=facint, counts=counts, starts=starts, gloCells=n)
+
+
+def hex_polymesh_arrays(nx: int, ny: int, nz: int, lengths=(1.0, 1.0, 1.0), kinds=("wall",) * 6,
+                        jitter: float = 0.0, seed: int = 12345):
+    """Points + quad faces of the same hex box (optionally with jittered interior
+    points => non-orthogonal, skewed cells).  Returns the inputs of
+    :func:`geometry_from_polymesh`."""
+    lx, ly, lz = lengths
+    px, py, pz = nx + 1, ny + 1, nz + 1
+    gi, gj, gk = np.meshgrid(np.arange(px), np.arange(py), np.arange(pz), indexing="ij")
+    pid = gi + px * (gj + py * gk)
+    pts = np.zeros((px * py * pz, 3))
+    pts[pid.ravel(), 0] = (gi * (lx / nx)).ravel()
+    pts[pid.ravel(), 1] = (gj * (ly / ny)).ravel()
+    pts[pid.ravel(), 2] = (gk * (lz / nz)).ravel()
+    if jitter > 0.0:
+        rng = np.random.default_rng(seed)
+        interior = ((gi > 0) & (gi < nx) & (gj > 0) & (gj < ny) & (gk > 0) & (gk < nz)).ravel()
+        d = rng.uniform(-1.0, 1.0, size=(px * py * pz, 3)) * jitter * np.array([lx / nx, ly / ny, lz / nz])
+        pts[pid.ravel()[interior]] += d[pid.ravel()[interior]]
+
+    def P(i, j, k):
+        return i + px * (j + py * k)
+
+    m = hex_mesh(nx, ny, nz, lengths, kinds)
+    own0 = m.owner.astype(np.int64) - 1
+    ci, cj, ck = own0 % nx, (own0 // nx) % ny, own0 // (nx * ny)
+    # direction / side of every face from its area vector
+    axis = np.argmax(np.abs(np.stack([m.arx, m.ary, m.arz], axis=1)), axis=1)
+    sign = np.sign(np.stack([m.arx, m.ary, m.arz], axis=1)[np.arange(m.numFaces), axis])
+    faces = np.zeros((m.numFaces, 4), dtype=np.int64)
+    for ax in range(3):
+        for sg in (-1.0, 1.0):
+            sel = (axis == ax) & (sign == sg)
+            i, j, k = ci[sel], cj[sel], ck[sel]
+            if ax == 0:
+                i0 = i + (1 if sg > 0 else 0)
+                quad = [P(i0, j, k), P(i0, j + 1, k), P(i0, j + 1, k + 1), P(i0, j, k + 1)]
+            elif ax == 1:
+                j0 = j + (1 if sg > 0 else 0)
+                quad = [P(i, j0, k), P(i, j0, k + 1), P(i + 1, j0, k + 1), P(i + 1, j0, k)]
+            else:
+                k0 = k + (1 if sg > 0 else 0)
+                quad = [P(i, j, k0), P(i + 1, j, k0), P(i + 1, j + 1, k0), P(i, j + 1, k0)]
+            q = np.stack(quad, axis=1)
+            if sg < 0:
+                q = q[:, ::-1]  # outward normal for the low-side patches
+            faces[sel] = q
+    return pts, faces, m.owner.copy(), m.neighbour.copy(), dict(m.counts), dict(m.starts)
+
+
+# --------------------------------------------------------------------------
+# geometry from points/faces: restates mesh_geometry (:859-1081)
+# --------------------------------------------------------------------------
+def geometry_from_polymesh(points: np.ndarray, faces, owner: np.ndarray, neighbour: np.ndarray,
+                           counts: Dict[str, int], starts: Dict[str, int]) -> Mesh:
+    """Face area vectors by fan triangulation about node 1, face centre = node
+    average, cell volume / centroid by the pyramid sums of the reference, and
+    ``facint`` from the intersection of the P-N line with the plane of the first
+    three face nodes.  ``faces`` is an [nFaces, k] array or a list of node arrays
+    (0-based nodes); ``owner``/``neighbour`` are 1-based."""
+    nF = len(owner)
+    nI = len(neighbour)
+    own = owner.astype(np.int64) - 1
+    nb = neighbour.astype(np.int64) - 1
+    n = int(own.max()) + 1
+    if isinstance(faces, np.ndarray) and faces.ndim == 2:
+        groups = [(np.arange(nF), faces)]
+    else:
+        lens = np.array([len(f) for f in faces])
+        groups = []
+        for k in np.unique(lens):
+            idx = np.nonzero(lens == k)[0]
+            groups.append((idx, np.array([faces[i] for i in idx], dtype=np.int64)))
+    ar = np.zeros((nF, 3))
+    cf = np.zeros((nF, 3))
+    vol = np.zeros(n)
+    cen = np.zeros((n, 3))
+    first3 = np.zeros((nF, 3), dtype=np.int64)
+    tri_store = []
+    for idx, fa in groups:
+        k = fa.shape[1]
+        p1 = points[fa[:, 0]]
+        first3[idx] = fa[:, :3]
+        cf[idx] = points[fa].sum(axis=1) / float(k)
+        for t in range(k - 2):
+            a = points[fa[:, t + 1]] - p1
+            b = points[fa[:, t + 2]] - p1
+            nrm = np.cross(a, b)                      # triangular_face_area_components_polymesh
+            ar[idx] += 0.5 * nrm
+            c = (points[fa[:, t + 2]] + points[fa[:, t + 1]] + p1) / 3.0
+            dv = (c * nrm).sum(axis=1) / 6.0          # cell_volume_part_polymesh
+            np.add.at(vol, own[idx], dv)
+            inner = idx < nI
+            np.add.at(vol, nb[idx[inner]], -dv[inner])
+            tri_store.append((idx, fa[:, 0], fa[:, t + 1], fa[:, t + 2], nrm))
+    for idx, n1, n2, n3, nrm in tri_store:
+        # centroid_component_part_polymesh: 1/(2*vol) * 1/24 * n_c * ((a+b)^2+(b+c)^2+(c+a)^2)
+        pa, pb, pc = points[n1], points[n2], points[n3]
+        s = (pa + pb) ** 2 + (pb + pc) ** 2 + (pc + pa) ** 2
+        contrib = nrm * s / 48.0
+        np.add.at(cen, own[idx], contrib / vol[own[idx], None])
+        inner = idx < nI
+        np.add.at(cen, nb[idx[inner]], -contrib[inner] / vol[nb[idx[inner]], None])
+    # interpolation factor (:1040-1062)
+    io, inn = own[:nI], nb[:nI]
+    a0 = points[first3[:nI, 0]]
+    pn = np.cross(points[first3[:nI, 1]] - a0, points[first3[:nI, 2]] - a0)
+    d = cen[inn] - cen[io]
+    t = ((a0 - cen[io]) * pn).sum(axis=1) / (d * pn).sum(axis=1)
+    xj = cen[io] + t[:, None] * d
+    djn = np.sqrt(((xj - cen[io]) ** 2).sum(axis=1))
+    dpn = np.sqrt((d ** 2).sum(axis=1))
+    facint = djn / dpn
+    return Mesh(numCells=n, numInnerFaces=nI, numFaces=nF, owner=owner.astype(np.int32),
+                neighbour=neighbour.astype(np.int32),
+                xc=cen[:, 0].copy(), yc=cen[:, 1].copy(), zc=cen[:, 2].copy(), vol=vol,
+                arx=ar[:, 0].copy(), ary=ar[:, 1].copy(), arz=ar[:, 2].copy(),
+                xf=cf[:, 0].copy(), yf=cf[:, 1].copy(), zf=cf[:, 2].copy(),
+                facint=facint, counts=dict(counts), starts=dict(starts), gloCells=n)
+
+
+def _foam_body(text: str) -> str:
+    """Strip the FoamFile header; return from the entry count on."""
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//.*", "", text)
+    i = text.find("}")
+    return text[i + 1:] if "FoamFile" in text[:i + 1] else text
+
+
+def read_polymesh(polymesh_dir: str) -> Mesh:
+    """Read OpenFOAM ASCII ``points/faces/owner/neighbour`` plus the reference's
+    simplified ``boundary`` file (``#type nFaces startFace``, :414-470)."""
+    def body(name):
+        with open(os.path.join(polymesh_dir, name)) as fh:
+            return _foam_body(fh.read())
+    b = body("points")
+    npts = int(re.search(r"(\d+)\s*\(", b).group(1))
+    nums = re.findall(r"\(\s*([-+0-9.eE]+)\s+([-+0-9.eE]+)\s+([-+0-9.eE]+)\s*\)", b)
+    points = np.array(nums, dtype=np.float64)
+    assert points.shape[0] == npts
+    b = body("faces")
+    faces = [np.array(m.split(), dtype=np.int64) for m in re.findall(r"\d+\(([\d\s]+)\)", b)]
+    def labels(name):
+        b = body(name)
+        m = re.search(r"(\d+)\s*\(([\d\s]*)\)", b)
+        arr = np.array(m.group(2).split(), dtype=np.int64)
+        assert arr.size == int(m.group(1))
+        return arr
+    owner = labels("owner") + 1
+    neighbour = labels("neighbour") + 1
+    counts: Dict[str, int] = {}
+    starts: Dict[str, int] = {}
+    with open(os.path.join(polymesh_dir, "boundary")) as fh:
+        for line in fh:
+            if line.startswith("#") or not line.strip():
+                continue
+            kind, nf, st = line.split()[:3]
+            kind = {"wallIsoth": "wall", "wallAdiab": "wall", "wallQFlux": "wall"}.get(kind, kind)
+            if kind not in KINDS:
+                raise ValueError(f"boundary type {kind!r} is outside the supported path")
+            if kind not in counts:
+                counts[kind] = 0
+                starts[kind] = int(st)
+            counts[kind] += int(nf)
+    if len({len(f) for f in faces}) == 1:
+        faces = np.array(faces)
+    return geometry_from_polymesh(points, faces, owner, neighbour, counts, starts)
+
+
+# --------------------------------------------------------------------------
+# cell partitioner: per-rank meshes in the src-parallel layout
+# --------------------------------------------------------------------------
+def slab_ranks(mesh_n: int, nranks: int) -> np.ndarray:
+    """Contiguous blocks of cell ids (z-slabs for the hex numbering)."""
+    return (np.arange(mesh_n, dtype=np.int64) * nranks) // mesh_n
+
+
+def partition(g: Mesh, cell_rank: np.ndarray, nranks: int) -> List[Mesh]:
+    """Split ``g`` by ``cell_rank`` into per-rank meshes laid out like an
+    OpenFOAM decomposition read by src-parallel: faces = [inner | boundary
+    patches in the global order | processor faces grouped by neighbour rank
+    ascending], slots = [cells | npro halo | inlet | outlet | symmetry | wall |
+    prOutlet] (:637-660).  Processor faces keep the global face order on both
+    sides, so buffer position i of a connection pairs with position i of the
+    mirrored connection (exchange.f90:49-90).  ``fpro`` as in :1183-1250."""
+    own = g.owner.astype(np.int64) - 1
+    nb = g.neighbour.astype(np.int64) - 1
+    nI = g.numInnerFaces
+    r_own = cell_rank[own]
+    r_nb = cell_rank[nb]
+    out: List[Mesh] = []
+    for r in range(nranks):
+        cells = np.nonzero(cell_rank == r)[0]
+        g2l = np.full(g.numCells, -1, dtype=np.int64)
+        g2l[cells] = np.arange(cells.size)
+        fin = np.nonzero((r_own[:nI] == r) & (r_nb == r))[0]
+        cut_o = np.nonzero((r_own[:nI] == r) & (r_nb != r))[0]   # we own, other side remote
+        cut_n = np.nonzero((r_own[:nI] != r) & (r_nb == r))[0]   # we are neighbour: flip
+        # boundary faces of this rank, kept in global face order inside each kind
+        bfaces, counts, starts = [], {}, {}
+        pos = fin.size
+        # kinds must be traversed in global *face* order of their first patch
+        for kind in sorted(g.counts, key=lambda k: g.starts[k]):
+            fr = np.arange(g.starts[kind], g.starts[kind] + g.counts[kind])
+            fr = fr[r_own[fr] == r]
+            counts[kind] = fr.size
+            starts[kind] = pos
+            pos += fr.size
+            bfaces.append(fr)
+        bfaces = np.concatenate(bfaces) if bfaces else np.zeros(0, dtype=np.int64)
+        # processor faces grouped by neighbour rank
+        cut = np.concatenate([cut_o, cut_n])
+        flip = np.concatenate([np.zeros(cut_o.size, bool), np.ones(cut_n.size, bool)])
+        other = np.where(flip, r_own[cut], r_nb[cut])
+        o = np.lexsort((cut, other))
+        cut, flip, other = cut[o], flip[o], other[o]
+        nbr_ranks = np.unique(other)
+        offs = [1]
+        for q in nbr_ranks:
+            offs.append(offs[-1] + int((other == q).sum()))
+        npro = cut.size
+        sgn = np.where(flip, -1.0, 1.0)
+        loc_cell = np.where(flip, nb[cut], own[cut])
+        rem_cell = np.where(flip, own[cut], nb[cut])
+        allf = np.concatenate([fin, bfaces, cut])
+        fsign = np.concatenate([np.ones(fin.size + bfaces.size), sgn])
+        owner_l = np.concatenate([g2l[own[fin]], g2l[own[bfaces]], g2l[loc_cell]]) + 1
+        neigh_l = g2l[nb[fin]] + 1
+        nloc = cells.size
+        # geometry; halo copies of xc,yc,zc,vol sit in [nloc, nloc+npro) (:1112-1115)
+        xc = np.concatenate([g.xc[cells], g.xc[rem_cell]])
+        yc = np.concatenate([g.yc[cells], g.yc[rem_cell]])
+        zc = np.concatenate([g.zc[cells], g.zc[rem_cell]])
+        vol = np.concatenate([g.vol[cells], g.vol[rem_cell]])
+        # fpro: distance-weighted factor towards the remote cell; for a face we own it
+        # equals the global facint, for a flipped face 1 - facint
+        fpro = np.where(flip, 1.0 - g.facint[cut], g.facint[cut])
+        out.append(Mesh(
+            numCells=nloc, numInnerFaces=fin.size, numFaces=allf.size,
+            owner=owner_l.astype(np.int32), neighbour=neigh_l.astype(np.int32),
+            xc=xc, yc=yc, zc=zc, vol=vol,
+            arx=g.arx[allf] * fsign, ary=g.ary[allf] * fsign, arz=g.arz[allf] * fsign,
+            xf=g.xf[allf].copy(), yf=g.yf[allf].copy(), zf=g.zf[allf].copy(),
+            facint=g.facint[fin].copy(), counts=counts, starts=starts,
+            npro=npro, iProcFacesStart=fin.size + bfaces.size, fpro=fpro,
+            neighbProcNo=nbr_ranks.astype(np.int32), neighbProcOffset=np.array(offs, dtype=np.int32),
+            gloCells=g.numCells, cell_global=cells))
+    return out

@@ -1,0 +1,133 @@
+/*
+ * fc_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C, sequential sums, no FMA contraction) of the
+ * pressure-correction hot path of nikola-m/freeCappuccino.  It is the checker
+ * the CUDA path is compared against; only tests/, __graft_entry__.smoke() and
+ * the cpu_baseline / --impl reference legs of bench.py may load it.  The
+ * product library (freecappuccino_b200/csrc) never links or calls it.
+ *
+ * Parity status: PINNED for the three Krylov solvers by the reference's own
+ * golden file tests/output.txt (every printed digit, see
+ * tests/test_oracle_golden.py); the assembly / gradient routines have no
+ * stored outputs in the reference -- they are pinned analytically (Poisson
+ * second-order convergence, poisson.f90) and by exact-arithmetic identities.
+ *
+ * All index arrays are 1-based INTEGER(4) exactly as the Fortran code keeps
+ * them; all reals are REAL(8).  Citations are relative to /root/reference.
+ */
+#ifndef FC_ORACLE_H
+#define FC_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mesh description = the arrays of `module geometry`
+ * (src/mesh_geometry_and_topology.f90:13-98; src-parallel twin adds npro). */
+typedef struct {
+  int numCells, numInnerFaces, numFaces, numTotal;
+  int npro;  /* processor-boundary faces (src-parallel only, else 0) */
+  int ninl, nout, nsym, nwal, npru, noc;
+  /* 0-based "start" offsets exactly like the reference: face = start + i, i=1.. */
+  int iProcFacesStart, iInletFacesStart, iOutletFacesStart, iSymmetryFacesStart,
+      iWallFacesStart, iPressOutletFacesStart, iOCFacesStart;
+  const int *owner;      /* [numFaces]      */
+  const int *neighbour;  /* [numInnerFaces] */
+  const double *xc, *yc, *zc, *vol;             /* [numCells (+npro)] */
+  const double *arx, *ary, *arz, *xf, *yf, *zf; /* [numFaces]         */
+  const double *facint;                         /* [numInnerFaces]    */
+  const double *fpro;                           /* [npro]             */
+  const int *ijl, *ijr, *ijlFace;               /* [noc]              */
+  const double *foc;                            /* [noc]              */
+} fco_mesh;
+
+/* CSR container = `module sparse_matrix` (src/sparse_matrix.f90:8-22). */
+typedef struct {
+  int n, nnz;
+  const int *ioffset, *ja, *diag;       /* 1-based */
+  const int *icell_jcell, *jcell_icell; /* [numInnerFaces], may be NULL for solvers */
+} fco_csr;
+
+typedef struct {
+  double sor;    /* resmax = sor(ifi)                       */
+  int nsw;       /* max sweeps = nsw(ifi)                   */
+  double small;  /* (double)1e-20f in src, (double)1e-30f in tests/ */
+  double tol;    /* early-return threshold, (double)1e-13f; <0 disables (tests/) */
+  int parallel;  /* 1 = src-parallel arithmetic (+small in preconditioners)   */
+} fco_solver_opts;
+
+typedef struct {
+  double res0, resl;
+  int iters;
+} fco_report;
+
+int fco_create_csr(int numCells, int numInnerFaces, const int *owner, const int *neighbour,
+                   int *ioffset, int *ja, int *diag, int *icell_jcell, int *jcell_icell);
+
+void fco_spmv(const fco_csr *m, const double *a, const double *x, double *y);
+
+/* O-C strips (al, ar, ijl, ijr, noc) and processor strips (apr, npro, owner of
+ * proc faces `pown`, halo values live in fi[iProcStart + i]) may be empty.   */
+typedef struct {
+  int noc;  const int *ijl, *ijr;  const double *al, *ar;
+  int npro; const int *pown;       const double *apr;  int iProcStart;
+} fco_strips;
+
+int fco_dpcg(const fco_csr *m, const double *a, const double *su, double *fi, double *res,
+             const fco_strips *s, const fco_solver_opts *o, fco_report *rep, double *hist);
+int fco_iccg(const fco_csr *m, const double *a, const double *su, double *fi, double *res,
+             const fco_strips *s, const fco_solver_opts *o, fco_report *rep, double *hist);
+int fco_bicgstab(const fco_csr *m, const double *a, const double *su, double *fi, double *res,
+                 const fco_strips *s, const fco_solver_opts *o, fco_report *rep, double *hist);
+
+void fco_laplacian(const fco_mesh *g, const fco_csr *m, const double *mu, const double *phi,
+                   double *a, double *su, double *al, double *ar);
+
+void fco_grad_gauss(const fco_mesh *g, const double *u, int nigrad, double *dudxi /* (3,numCells) */);
+void fco_grad_gauss_corrected(const fco_mesh *g, const double *u, double *dudxi);
+void fco_bpres(const fco_mesh *g, double *p, const double *dPdxi, int istage);
+
+/* Fields of `module variables` + `sparse_matrix` touched by calcp. */
+typedef struct {
+  double *u, *v, *w, *p, *pp;           /* [numTotal] */
+  const double *den;                    /* [numTotal] */
+  double *flmass;                       /* [numInnerFaces] */
+  double *fmi, *fmo, *fmoc;             /* [ninl],[nout],[noc] */
+  double *dUdxi, *dVdxi, *dWdxi, *dPdxi;/* (3,numCells) */
+  const double *apu, *apv, *apw;        /* [numCells] */
+  double *a, *su, *res, *al, *ar;       /* CSR values, rhs, residual, O-C coefs */
+} fco_fields;
+
+typedef struct {
+  int npcor, nigrad, nipgrad;   /* parameters :114-117 (nipgrad = 2)         */
+  int pRefCell;                 /* 1-based                                    */
+  double urf_p;                 /* urf(ip)                                    */
+  int solver;                   /* 0 dpcg, 1 iccg (shipped), 2 bicgstab       */
+  int const_mflux;              /* .true. skips adjustMassFlow                */
+  double flomas;
+  int lsq_flag;                 /* lstsq_qr.or.lstsq_dm: extra gauss_corrected*/
+  int flux_variant;             /* 0 facefluxmass, 1 facefluxmass2, 2 _piso   */
+  fco_solver_opts sol;
+} fco_calcp_opts;
+
+typedef struct {
+  fco_report rep[8];            /* one per pressure corrector                 */
+  double sumLocalContErr, globalContErr;
+} fco_calcp_report;
+
+void fco_calcp_assemble(const fco_mesh *g, const fco_csr *m, fco_fields *f, const fco_calcp_opts *o);
+int  fco_calcp(const fco_mesh *g, const fco_csr *m, fco_fields *f, const fco_calcp_opts *o,
+               fco_calcp_report *rep);
+
+void fco_facefluxmass(const fco_mesh *g, const fco_fields *f, int variant, int ijp, int ijn,
+                      double xf, double yf, double zf, double arx, double ary, double arz,
+                      double lambda, double *cap, double *can, double *fluxmass);
+void fco_fluxmc(const fco_mesh *g, const fco_fields *f, int ijp, int ijn,
+                double xf, double yf, double zf, double arx, double ary, double arz,
+                double lambda, double *fmcor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

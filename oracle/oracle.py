@@ -1,0 +1,253 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE ONLY, see fc_oracle.h).
+
+Only tests/, __graft_entry__.smoke() and the cpu_baseline / --impl reference
+legs of bench.py may import this module.  The product package
+``freecappuccino_b200`` never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB: Optional[C.CDLL] = None
+
+SMALL = float(np.float32(1e-20))      # parameters: small = 1e-20 (single literal), modules_allocatable.f90:27
+SMALL_TEST = float(np.float32(1e-30)) # tests/test_sparse_solvers.f90:36
+TOL = float(np.float32(1e-13))        # dpcg.f90:37
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libfc_oracle.so")
+    src = [os.path.join(_HERE, f) for f in ("fc_oracle.c", "fc_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libfc_oracle.so"])
+    return so
+
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+class FcoMesh(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "numCells", "numInnerFaces", "numFaces", "numTotal", "npro",
+        "ninl", "nout", "nsym", "nwal", "npru", "noc",
+        "iProcFacesStart", "iInletFacesStart", "iOutletFacesStart", "iSymmetryFacesStart",
+        "iWallFacesStart", "iPressOutletFacesStart", "iOCFacesStart")] + [
+        ("owner", ip), ("neighbour", ip),
+        ("xc", dp), ("yc", dp), ("zc", dp), ("vol", dp),
+        ("arx", dp), ("ary", dp), ("arz", dp), ("xf", dp), ("yf", dp), ("zf", dp),
+        ("facint", dp), ("fpro", dp),
+        ("ijl", ip), ("ijr", ip), ("ijlFace", ip), ("foc", dp)]
+
+
+class FcoCsr(C.Structure):
+    _fields_ = [("n", C.c_int), ("nnz", C.c_int), ("ioffset", ip), ("ja", ip), ("diag", ip),
+                ("icell_jcell", ip), ("jcell_icell", ip)]
+
+
+class FcoSolverOpts(C.Structure):
+    _fields_ = [("sor", C.c_double), ("nsw", C.c_int), ("small", C.c_double), ("tol", C.c_double),
+                ("parallel", C.c_int)]
+
+
+class FcoReport(C.Structure):
+    _fields_ = [("res0", C.c_double), ("resl", C.c_double), ("iters", C.c_int)]
+
+
+class FcoStrips(C.Structure):
+    _fields_ = [("noc", C.c_int), ("ijl", ip), ("ijr", ip), ("al", dp), ("ar", dp),
+                ("npro", C.c_int), ("pown", ip), ("apr", dp), ("iProcStart", C.c_int)]
+
+
+class FcoFields(C.Structure):
+    _fields_ = [(n, dp) for n in (
+        "u", "v", "w", "p", "pp", "den", "flmass", "fmi", "fmo", "fmoc",
+        "dUdxi", "dVdxi", "dWdxi", "dPdxi", "apu", "apv", "apw", "a", "su", "res", "al", "ar")]
+
+
+class FcoCalcpOpts(C.Structure):
+    _fields_ = [("npcor", C.c_int), ("nigrad", C.c_int), ("nipgrad", C.c_int), ("pRefCell", C.c_int),
+                ("urf_p", C.c_double), ("solver", C.c_int), ("const_mflux", C.c_int), ("flomas", C.c_double),
+                ("lsq_flag", C.c_int), ("flux_variant", C.c_int), ("sol", FcoSolverOpts)]
+
+
+class FcoCalcpReport(C.Structure):
+    _fields_ = [("rep", FcoReport * 8), ("sumLocalContErr", C.c_double), ("globalContErr", C.c_double)]
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.fco_create_csr.restype = C.c_int
+        for f in ("fco_dpcg", "fco_iccg", "fco_bicgstab", "fco_calcp"):
+            getattr(_LIB, f).restype = C.c_int
+    return _LIB
+
+
+def _d(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(dp)
+
+
+def _i(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(ip)
+
+
+SOLVERS = {"dpcg": 0, "iccg": 1, "bicgstab": 2}
+
+
+class Csr:
+    """Integer arrays of ``create_CSR_matrix_from_mesh_data`` (1-based)."""
+
+    def __init__(self, ioffset, ja, diag, icell_jcell=None, jcell_icell=None):
+        self.ioffset, self.ja, self.diag = ioffset, ja, diag
+        self.icell_jcell, self.jcell_icell = icell_jcell, jcell_icell
+        self.n = ioffset.size - 1
+        self.nnz = ja.size
+
+    def c(self) -> FcoCsr:
+        return FcoCsr(self.n, self.nnz, _i(self.ioffset), _i(self.ja), _i(self.diag),
+                      _i(self.icell_jcell), _i(self.jcell_icell))
+
+
+def create_csr(mesh) -> Csr:
+    n, F = mesh.numCells, mesh.numInnerFaces
+    nnz = n + 2 * F
+    ioffset = np.zeros(n + 1, np.int32)
+    ja = np.zeros(nnz, np.int32)
+    diag = np.zeros(n, np.int32)
+    ij = np.zeros(F, np.int32)
+    ji = np.zeros(F, np.int32)
+    rc = lib().fco_create_csr(n, F, _i(mesh.owner), _i(mesh.neighbour), _i(ioffset), _i(ja), _i(diag), _i(ij), _i(ji))
+    assert rc == 0
+    return Csr(ioffset, ja, diag, ij, ji)
+
+
+def mesh_struct(m) -> FcoMesh:
+    keep = []
+    def d(a):
+        a = np.ascontiguousarray(a, dtype=np.float64) if a is not None else None
+        keep.append(a)
+        return _d(a)
+    s = FcoMesh()
+    s.numCells, s.numInnerFaces, s.numFaces, s.numTotal, s.npro = m.numCells, m.numInnerFaces, m.numFaces, m.numTotal, m.npro
+    s.ninl, s.nout, s.nsym, s.nwal, s.npru, s.noc = (m.count("inlet"), m.count("outlet"), m.count("symmetry"),
+                                                   m.count("wall"), m.count("prOutlet"), m.noc)
+    s.iProcFacesStart = m.iProcFacesStart
+    s.iInletFacesStart, s.iOutletFacesStart = m.faces_start("inlet"), m.faces_start("outlet")
+    s.iSymmetryFacesStart, s.iWallFacesStart = m.faces_start("symmetry"), m.faces_start("wall")
+    s.iPressOutletFacesStart, s.iOCFacesStart = m.faces_start("prOutlet"), m.iOCFacesStart
+    s.owner, s.neighbour = _i(m.owner), _i(m.neighbour)
+    s.xc, s.yc, s.zc, s.vol = d(m.xc), d(m.yc), d(m.zc), d(m.vol)
+    s.arx, s.ary, s.arz, s.xf, s.yf, s.zf = d(m.arx), d(m.ary), d(m.arz), d(m.xf), d(m.yf), d(m.zf)
+    s.facint, s.fpro = d(m.facint), d(m.fpro)
+    s.ijl, s.ijr, s.ijlFace, s.foc = _i(m.ijl), _i(m.ijr), _i(m.ijlFace), d(m.foc)
+    s._keep = keep
+    return s
+
+
+def spmv(csr: Csr, a: np.ndarray, x: np.ndarray) -> np.ndarray:
+    y = np.zeros(csr.n)
+    cs = csr.c()
+    lib().fco_spmv(C.byref(cs), _d(a), _d(x), _d(y))
+    return y
+
+
+def solve(name: str, csr: Csr, a: np.ndarray, su: np.ndarray, fi: np.ndarray, sor: float, nsw: int,
+          small: float = SMALL, tol: float = TOL, parallel: bool = False, history: bool = False):
+    """Run dpcg / iccg / bicgstab in place on ``fi``.  Returns (res0, resl, iters, res[, hist])."""
+    res = np.zeros(csr.n)
+    hist = np.zeros(nsw) if history else None
+    o = FcoSolverOpts(sor, nsw, small, tol, int(parallel))
+    rep = FcoReport()
+    cs = csr.c()
+    fn = getattr(lib(), "fco_" + name)
+    rc = fn(C.byref(cs), _d(a), _d(su), _d(fi), _d(res), None, C.byref(o), C.byref(rep), _d(hist))
+    assert rc == 0
+    out = (rep.res0, rep.resl, rep.iters, res)
+    return out + (hist[:rep.iters],) if history else out
+
+
+def laplacian(mesh, csr: Csr, mu: np.ndarray, phi: np.ndarray, su: np.ndarray) -> np.ndarray:
+    """``call laplacian(mu,phi)``: returns ``a``; updates ``su`` in place (wall BC)."""
+    a = np.zeros(csr.nnz)
+    ms, cs = mesh_struct(mesh), csr.c()
+    lib().fco_laplacian(C.byref(ms), C.byref(cs), _d(mu), _d(phi), _d(a), _d(su), None, None)
+    return a
+
+
+def grad_gauss(mesh, u: np.ndarray, nigrad: int = 1) -> np.ndarray:
+    """Returns dPhidxi as an [numCells, 3] C array == Fortran (3,numCells)."""
+    g = np.zeros((mesh.numCells, 3))
+    ms = mesh_struct(mesh)
+    lib().fco_grad_gauss(C.byref(ms), _d(u), nigrad, _d(g))
+    return g
+
+
+def grad_gauss_corrected(mesh, u: np.ndarray, seed: np.ndarray) -> np.ndarray:
+    g = np.ascontiguousarray(seed, dtype=np.float64).copy()
+    ms = mesh_struct(mesh)
+    lib().fco_grad_gauss_corrected(C.byref(ms), _d(u), _d(g))
+    return g
+
+
+def bpres(mesh, p: np.ndarray, dPdxi: np.ndarray, istage: int) -> None:
+    ms = mesh_struct(mesh)
+    lib().fco_bpres(C.byref(ms), _d(p), _d(dPdxi), istage)
+
+
+class Fields:
+    """The arrays of ``module variables`` / ``sparse_matrix`` calcp touches."""
+
+    NAMES = ("u", "v", "w", "p", "pp", "den", "flmass", "fmi", "fmo", "fmoc",
+             "dUdxi", "dVdxi", "dWdxi", "dPdxi", "apu", "apv", "apw", "a", "su", "res", "al", "ar")
+
+    def __init__(self, mesh, nnz: int):
+        nt, n = mesh.numTotal, mesh.numCells
+        z = np.zeros
+        self.u, self.v, self.w, self.p, self.pp = z(nt), z(nt), z(nt), z(nt), z(nt)
+        self.den = np.ones(nt)
+        self.flmass = z(mesh.numInnerFaces)
+        self.fmi, self.fmo, self.fmoc = z(max(mesh.count("inlet"), 1)), z(max(mesh.count("outlet"), 1)), z(max(mesh.noc, 1))
+        self.dUdxi, self.dVdxi, self.dWdxi, self.dPdxi = z((n, 3)), z((n, 3)), z((n, 3)), z((n, 3))
+        self.apu, self.apv, self.apw = z(n + mesh.npro), z(n + mesh.npro), z(n + mesh.npro)
+        self.a, self.su, self.res = z(nnz), z(n), z(n)
+        self.al, self.ar = z(max(mesh.noc, 1)), z(max(mesh.noc, 1))
+
+    def c(self) -> FcoFields:
+        return FcoFields(*[_d(getattr(self, k)) for k in self.NAMES])
+
+    def copy(self) -> "Fields":
+        import copy
+        return copy.deepcopy(self)
+
+
+def calcp_opts(npcor=1, nigrad=1, pRefCell=1, urf_p=0.3, solver="iccg", const_mflux=False, flomas=0.0,
+               lsq_flag=False, flux_variant=0, sor=1e-2, nsw=100, small=SMALL, tol=TOL) -> FcoCalcpOpts:
+    return FcoCalcpOpts(npcor, nigrad, 2, pRefCell, urf_p, SOLVERS[solver], int(const_mflux), flomas,
+                        int(lsq_flag), flux_variant, FcoSolverOpts(sor, nsw, small, tol, 0))
+
+
+def calcp_assemble(mesh, csr: Csr, f: Fields, opts: FcoCalcpOpts) -> None:
+    ms, cs, fs = mesh_struct(mesh), csr.c(), f.c()
+    lib().fco_calcp_assemble(C.byref(ms), C.byref(cs), C.byref(fs), C.byref(opts))
+
+
+def calcp(mesh, csr: Csr, f: Fields, opts: FcoCalcpOpts) -> FcoCalcpReport:
+    ms, cs, fs = mesh_struct(mesh), csr.c(), f.c()
+    rep = FcoCalcpReport()
+    rc = lib().fco_calcp(C.byref(ms), C.byref(cs), C.byref(fs), C.byref(opts), C.byref(rep))
+    assert rc == 0
+    return rep
