@@ -1,0 +1,61 @@
+// Communication of the cell-partitioned build: the NCCL equivalents of src-parallel's
+// exchange (exchange.f90:3-92) and global_sum (global_sum_mpi.f90:4-37).
+//
+// One rank per GPU.  A halo exchange is a device pack (buffer(i) = phi(bufind(i)),
+// exchange.f90:48-50) followed by ONE ncclGroup holding a send/recv pair per neighbouring
+// rank; the receive lands directly in the halo slots phi(iProcStart+i) (:86-90), so there
+// is no unpack kernel.  Scalar sums are an in-place ncclAllReduce on the device-resident
+// reduction block; everything is enqueued on the context's stream.
+#include "fc_internal.cuh"
+
+namespace {
+__global__ void k_pack(int npro, const int *__restrict__ bufind, const double *__restrict__ phi,
+                       double *__restrict__ buf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npro) buf[i] = phi[bufind[i]];
+}
+}  // namespace
+
+int fc_halo_exchange(fc_context *ctx, double *phi) {
+  if (ctx->npro == 0) return FC_OK;
+  if (!ctx->comm) FC_FAIL(FC_ERR_ARG, "halo exchange on a partitioned mesh needs fc_comm_init");
+  k_pack<<<fc_blocks(ctx->npro, 256), 256, 0, ctx->stream>>>(ctx->npro, ctx->bufind, phi, ctx->sendbuf);
+  FC_LAUNCH_CHECK();
+  FC_NCCL(ncclGroupStart());
+  for (size_t c = 0; c < ctx->nbr_rank.size(); ++c) {
+    const int off = ctx->nbr_off[c], len = ctx->nbr_off[c + 1] - off;
+    FC_NCCL(ncclSend(ctx->sendbuf + off, (size_t)len, ncclDouble, ctx->nbr_rank[c], ctx->comm, ctx->stream));
+    FC_NCCL(ncclRecv(phi + ctx->n + off, (size_t)len, ncclDouble, ctx->nbr_rank[c], ctx->comm, ctx->stream));
+  }
+  FC_NCCL(ncclGroupEnd());
+  return FC_OK;
+}
+
+int fc_allreduce_scalars(fc_context *ctx, double *dev, int count) {
+  if (ctx->nranks == 1) return FC_OK;
+  if (!ctx->comm) FC_FAIL(FC_ERR_ARG, "all-reduce needs fc_comm_init");
+  FC_NCCL(ncclAllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  return FC_OK;
+}
+
+extern "C" int fc_comm_unique_id(char id128[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return FC_ERR_NCCL;
+  memcpy(id128, &id, 128);
+  return FC_OK;
+}
+
+extern "C" int fc_comm_init(fc_context *ctx, int rank, int nranks, const char id128[128]) {
+  if (!ctx) return FC_ERR_ARG;
+  if (nranks < 1 || rank < 0 || rank >= nranks) FC_FAIL(FC_ERR_ARG, "fc_comm_init: bad rank / nranks");
+  FC_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->comm) { ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  if (nranks == 1) return FC_OK;
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  FC_NCCL(ncclCommInitRank(&ctx->comm, nranks, id, rank));
+  return FC_OK;
+}

@@ -1,0 +1,172 @@
+// Internal declarations of libfcapp_cuda (not installed; the public ABI is include/fcapp.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fcapp.h"
+
+// Number of SMs the persistent / grid-stride kernels are sized for (B200).
+constexpr int FC_SMS = 148;
+constexpr int FC_RED_BLOCK = 512;               // threads of the streaming vector kernels
+constexpr int FC_RED_GRID = FC_SMS * 4;         // 4 resident CTAs of 512 threads per SM
+constexpr int FC_MAX_RED = 4;                   // scalars reduced by one kernel
+
+// Scalars of a Krylov solve, resident on the device so that no iteration
+// needs a host round trip (dpcg.f90:33, bicgstab.f90:26-28).
+struct fc_scalars {
+  double res0, resl;
+  double sk, s0, pkapk;                 // dpcg / iccg
+  double bet, beto, alf, gam, om;       // bicgstab (bicgstab.f90:105-113)
+  double ukreso, svkres, svkvk;
+  double sor, small;
+  double red[FC_MAX_RED];               // raw (rank-local, then all-reduced) sums of the last reduction
+  double aux[4];
+  int iters, nsw, done, pad;
+  unsigned int ticket[4];               // "last block finalises" counters
+};
+
+struct fc_levels {                      // level schedule of the strict lower / upper triangle
+  int nlev = 0;
+  int nslots = 0;                       // rows padded so that a block never straddles two levels
+  int *rows = nullptr;                  // [nslots] row id or -1 (padding), level-major, ascending inside a level
+  int *blk_level = nullptr;             // [nslots / TRI_BLOCK] level of every block
+  int *lev_blocks_before = nullptr;     // [nlev+1] number of blocks in levels < L
+  unsigned int *done = nullptr;         // [nlev] blocks finished per level (monotone over sweeps)
+  unsigned int *ticket = nullptr;       // dynamic block id
+  unsigned long long epoch = 0;         // sweeps run so far
+};
+
+struct fc_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+
+  // ---- mesh (0-based on the device) ----
+  bool has_mesh = false;
+  fc_mesh_desc m{};                     // scalar members only are meaningful
+  int n = 0, F = 0, NF = 0, NT = 0, npro = 0, nnz = 0, NP = 0;
+  int *owner = nullptr, *neigh = nullptr;
+  double *xc = nullptr, *yc = nullptr, *zc = nullptr, *vol = nullptr;
+  double *arx = nullptr, *ary = nullptr, *arz = nullptr, *xf = nullptr, *yf = nullptr, *zf = nullptr;
+  double *facint = nullptr, *fpro = nullptr;
+  // cell -> face map in the reference's loop order (inner faces ascending, processor
+  // faces, then inlet, outlet, symmetry, wall, prOutlet): grad_gauss.f90:53-103
+  int *c2f_off = nullptr;               // [n+1]
+  int *c2f_face = nullptr;              // face id | (cell is the neighbour side) << 31
+  int *c2f_other = nullptr;             // other cell (inner), halo / boundary slot otherwise
+  int *c2f_pos = nullptr;               // CSR position of a(cell,other) for inner faces, else -1
+  int c2f_len = 0;
+
+  // ---- CSR pattern (0-based on the device) ----
+  bool has_csr = false;
+  bool csr_external = false;            // adopted through fc_solve_csr (no mesh)
+  bool csr_dup = false;                 // duplicate cell pairs: `a` must be zeroed before assembly
+  int *ioffset = nullptr, *ja = nullptr, *diag = nullptr, *icj = nullptr, *jci = nullptr;
+  int *tpos = nullptr;                  // position of a(j,i) for every lower a(i,j) (bicgstab.f90:72-75)
+  int spmv_max_chunk = 0;               // max nnz of a 256-row block
+
+  // ---- fields ----
+  double *field[FC_NUM_FIELDS] = {};
+  size_t field_n[FC_NUM_FIELDS] = {};
+
+  // ---- solver scratch ----
+  double *pk = nullptr, *zk = nullptr, *dd = nullptr, *reso = nullptr, *uk = nullptr, *vk = nullptr;
+  double *adiag = nullptr;              // a(diag(i)) compacted once per solve
+  double *tt = nullptr;                 // forward-sweep result of the preconditioner
+  double *coef = nullptr;               // per-face coefficient cap = can [F + npro]
+  double *facev = nullptr;              // per-face scratch [NF]
+  double *gtmp = nullptr;               // previous-pass gradient (3,numCells)
+  double *partials = nullptr;           // [FC_MAX_RED * FC_RED_GRID]
+  fc_scalars *sc = nullptr;             // device
+  fc_scalars *sc_host = nullptr;        // pinned
+  size_t scratch_n = 0;
+  fc_levels lower, upper;
+  bool has_levels = false;
+
+  // ---- communication ----
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  std::vector<int> nbr_rank, nbr_off;   // neighbProcNo, neighbProcOffset (0-based offsets)
+  int *bufind = nullptr;                // owner cell of every processor face (exchange.f90:48-50)
+  double *sendbuf = nullptr;
+  int *strip_off = nullptr, *strip_idx = nullptr;  // per-row processor faces (apr strip of the SpMV)
+
+  // ---- timing ----
+  cudaEvent_t ev[4] = {};
+  fc_timings tm{};
+};
+
+#define FC_CUDA(call)                                                                           \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" +   \
+                 std::to_string(__LINE__) + ")";                                                \
+      return FC_ERR_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+#define FC_NCCL(call)                                                                           \
+  do {                                                                                          \
+    ncclResult_t r_ = (call);                                                                   \
+    if (r_ != ncclSuccess) {                                                                    \
+      ctx->err = std::string(#call) + ": " + ncclGetErrorString(r_);                            \
+      return FC_ERR_NCCL;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+#define FC_CHECK(expr)                                                                          \
+  do {                                                                                          \
+    int s_ = (expr);                                                                            \
+    if (s_ != FC_OK) return s_;                                                                 \
+  } while (0)
+
+#define FC_FAIL(code, msg)                                                                      \
+  do {                                                                                          \
+    ctx->err = (msg);                                                                           \
+    return (code);                                                                              \
+  } while (0)
+
+#define FC_LAUNCH_CHECK()                                                                       \
+  do {                                                                                          \
+    ctx->launches++;                                                                            \
+    FC_CUDA(cudaGetLastError());                                                                \
+  } while (0)
+
+template <class T>
+static inline int fc_dev_alloc(fc_context *ctx, T **p, size_t count) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (count == 0) count = 1;
+  FC_CUDA(cudaMalloc((void **)p, count * sizeof(T)));
+  return FC_OK;
+}
+
+static inline int fc_blocks(size_t n, int bs) { return (int)((n + bs - 1) / bs); }
+
+// ---- cross-file entry points ----
+int fc_csr_build(fc_context *ctx);                                   // fc_csr.cu
+int fc_csr_post(fc_context *ctx);                                    // transposed positions, spmv chunking
+int fc_c2f_build(fc_context *ctx);                                   // fc_csr.cu
+int fc_levels_build(fc_context *ctx);                                // fc_trisolve.cu
+void fc_levels_free(fc_levels &L);
+int fc_levels_reset(fc_context *ctx);
+int fc_precond_factor(fc_context *ctx, int kind, const double *a, double *d, double padd);
+int fc_precond_apply(fc_context *ctx, const double *a, const double *d, const double *r, double *t, double *z,
+                     double small);
+int fc_alloc_solver_scratch(fc_context *ctx);                        // fc_krylov.cu
+int fc_launch_spmv(fc_context *ctx, const double *a, const double *x, double *y);       // fc_spmv.cu
+int fc_launch_spmv_dots(fc_context *ctx, const double *a, const double *x, double *y, const double *w, int two,
+                        int step);
+int fc_launch_residual(fc_context *ctx, const double *a, const double *su, const double *x, double *res,
+                       double *adiag);
+int fc_halo_exchange(fc_context *ctx, double *phi);                  // fc_comm.cu
+int fc_allreduce_scalars(fc_context *ctx, double *dev, int count);
+int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opts *o, fc_solver_report *rep,
+                    double *hist);

@@ -1,0 +1,134 @@
+// Deterministic grid reduction ("last block finalises") and the scalar steps of the
+// Krylov recurrences.  No floating-point atomics: every block writes its partial sum,
+// the block that draws the last ticket adds the partials in a fixed order, so a given
+// (grid, block) configuration always produces the same bits.
+#pragma once
+#include "fc_internal.cuh"
+
+// Scalar recurrences executed once per reduction, either by the finalising thread
+// (single GPU) or by k_scalar_step after the NCCL all-reduce (src-parallel: every
+// sum is followed by global_sum, dpcg.f90:75,102,141,154 of src-parallel).
+enum fc_step {
+  STEP_NONE = 0,
+  STEP_RES0,        // red[0] = sum|res|            -> res0, resl; reset recurrences (dpcg.f90:64-79)
+  STEP_RES0_SK,     // + red[1] = sum res*z          -> sk (first Jacobi inner product fused in)
+  STEP_SK,          // red[0] = sum res*z            -> sk (dpcg.f90:90)
+  STEP_PKAPK,       // red[0] = sum pk*A pk          -> pkapk (dpcg.f90:119)
+  STEP_CG_UPDATE,   // red[0] = sum|res|             -> resl, s0 = sk, ++iters, convergence (dpcg.f90:130-142)
+  STEP_CG_UPDATE_SK,// + red[1] = next sum res*z     -> sk
+  STEP_BET,         // red[0] = res.reso             -> bet, om, beto (bicgstab.f90:105-113)
+  STEP_UKRESO,      // red[0] = uk.reso              -> gam (bicgstab.f90:152-157)
+  STEP_VK,          // red[0] = vk.res, red[1]=vk.vk -> alf (bicgstab.f90:200-206)
+  STEP_BI_UPDATE    // red[0] = sum|res|             -> resl, ++iters, convergence (bicgstab.f90:217-225)
+};
+
+__device__ __forceinline__ void fc_scalar_step(fc_scalars *sc, int step, double *hist) {
+  switch (step) {
+    case STEP_RES0:
+    case STEP_RES0_SK:
+      sc->res0 = sc->red[0];
+      sc->resl = sc->red[0];
+      sc->s0 = (double)1.e20f;  // s0=1.e20 is a default-real literal (dpcg.f90:79)
+      sc->iters = 0;
+      sc->done = 0;
+      sc->alf = 1.0; sc->beto = 1.0; sc->gam = 1.0;  // bicgstab.f90:84-86
+      if (step == STEP_RES0_SK) sc->sk = sc->red[1];
+      break;
+    case STEP_SK:
+      sc->sk = sc->red[0];
+      break;
+    case STEP_PKAPK:
+      sc->pkapk = sc->red[0];
+      break;
+    case STEP_CG_UPDATE:
+    case STEP_CG_UPDATE_SK: {
+      sc->resl = sc->red[0];
+      sc->s0 = sc->sk;
+      if (step == STEP_CG_UPDATE_SK) sc->sk = sc->red[1];
+      int it = ++sc->iters;
+      if (hist) hist[it - 1] = sc->resl;
+      double rsm = sc->resl / (sc->res0 + sc->small);
+      if (rsm < sc->sor || it >= sc->nsw) sc->done = 1;
+    } break;
+    case STEP_BET:
+      sc->bet = sc->red[0];
+      sc->om = sc->bet * sc->gam / (sc->alf * sc->beto + sc->small);
+      sc->beto = sc->bet;
+      break;
+    case STEP_UKRESO:
+      sc->ukreso = sc->red[0];
+      sc->gam = sc->bet / sc->ukreso;
+      break;
+    case STEP_VK:
+      sc->svkres = sc->red[0];
+      sc->svkvk = sc->red[1];
+      sc->alf = sc->svkres / (sc->svkvk + sc->small);
+      break;
+    case STEP_BI_UPDATE: {
+      sc->resl = sc->red[0];
+      int it = ++sc->iters;
+      if (hist) hist[it - 1] = sc->resl;
+      double rsm = sc->resl / (sc->res0 + sc->small);
+      if (rsm < sc->sor || it >= sc->nsw) sc->done = 1;
+    } break;
+    default:
+      break;
+  }
+}
+
+__device__ __forceinline__ double fc_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of NR values; result valid in thread 0.  blockDim.x must be a multiple of 32, <= 1024.
+template <int NR>
+__device__ __forceinline__ void fc_block_sum(double (&v)[NR], double *smem /* [NR*32] */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    double w = fc_warp_sum(v[r]);
+    if (lane == 0) smem[r * 32 + wid] = w;
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double w = lane < nw ? smem[r * 32 + lane] : 0.0;
+      v[r] = fc_warp_sum(w);
+    }
+  }
+  __syncthreads();
+}
+
+// Grid-wide deterministic sum.  Every thread passes its private partial sums; after the
+// call, thread 0 of exactly one block (the last to arrive) gets `true` with the totals
+// in v[].  `partials` holds NR * gridDim.x doubles; `ticket` must be zero on entry and is
+// reset on exit.
+template <int NR>
+__device__ __forceinline__ bool fc_grid_sum(double (&v)[NR], double *partials, unsigned int *ticket,
+                                            double *smem /* [NR*32] */) {
+  __shared__ bool s_last;
+  fc_block_sum<NR>(v, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) partials[r * gridDim.x + blockIdx.x] = v[r];
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    double w = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+      w += ((volatile double *)partials)[r * gridDim.x + b];
+    v[r] = w;
+  }
+  fc_block_sum<NR>(v, smem);
+  if (threadIdx.x == 0) *ticket = 0u;
+  return threadIdx.x == 0;
+}

@@ -1,0 +1,251 @@
+// Level-scheduled triangular sweeps for the DIC / DILU preconditioners.
+//
+// Reference: iccg.f90:77-83 (d_i = 1/(a_ii - sum_{k<i} a_ik^2 d_k)), :94-111 (forward sweep,
+// z = z/(d+small), backward sweep); bicgstab.f90:68-79 (DILU diagonal), :117-136, :167-185.
+// L and U are A's own strict triangles in NATURAL ordering -- reordering would change the
+// preconditioner and with it the iteration counts, so the rows are only *scheduled* by
+// dependency level, never renumbered.  One launch runs a whole sweep: CTAs draw a ticket,
+// take the next TRI_BLOCK rows of the level-major row list, wait until every CTA of the
+// previous level has published its rows (one counter per level, no grid-wide barrier) and
+// then add their row left to right exactly like the Fortran loop, so z is bit-identical.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "fc_internal.cuh"
+
+constexpr int TRI_BLOCK = 128;
+
+namespace {
+
+__global__ void k_level_relax(const int *__restrict__ ioffset, const int *__restrict__ ja,
+                              const int *__restrict__ diag, int n, int lower, int *level, int *changed) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lv = level[i], nl = lv;
+  int s = lower ? ioffset[i] : diag[i] + 1;
+  int e = lower ? diag[i] : ioffset[i + 1];
+  for (int k = s; k < e; ++k) {
+    int j = ja[k];
+    if (j < n) nl = max(nl, level[j] + 1);
+  }
+  if (nl != lv) {
+    level[i] = nl;
+    *changed = 1;
+  }
+}
+
+__global__ void k_iota(int *p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+__global__ void k_level_hist(const int *__restrict__ level, int n, int *hist) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&hist[level[i]], 1);
+}
+
+// scatter the level-sorted rows into the padded slot list
+__global__ void k_level_place(const int *__restrict__ sorted_level, const int *__restrict__ sorted_row, int n,
+                              const int *__restrict__ lev_start, const int *__restrict__ lev_slot, int *rows) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lv = sorted_level[i];
+  rows[lev_slot[lv] + (i - lev_start[lv])] = sorted_row[i];
+}
+
+__global__ void k_fill(int *p, int v, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int build_one(fc_context *ctx, fc_levels &L, int lower) {
+  const int n = ctx->n, B = 256;
+  int *level = nullptr, *changed = nullptr;
+  FC_CHECK(fc_dev_alloc(ctx, &level, (size_t)n));
+  FC_CHECK(fc_dev_alloc(ctx, &changed, 1));
+  FC_CUDA(cudaMemsetAsync(level, 0, sizeof(int) * (size_t)n, ctx->stream));
+  // Jacobi relaxation of level(i) = 1 + max level(dependencies): converges in nlev passes
+  for (int pass = 0;; ++pass) {
+    FC_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), ctx->stream));
+    for (int rep = 0; rep < 16; ++rep) {
+      k_level_relax<<<fc_blocks(n, B), B, 0, ctx->stream>>>(ctx->ioffset, ctx->ja, ctx->diag, n, lower, level, changed);
+      FC_LAUNCH_CHECK();
+    }
+    int h = 0;
+    FC_CUDA(cudaMemcpyAsync(&h, changed, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!h) break;
+    if (pass > (n / 16) + 2) FC_FAIL(FC_ERR_ARG, "level schedule did not converge");
+  }
+  // stable sort of the row ids by level -> ascending rows inside a level
+  int *rowid = nullptr, *slevel = nullptr, *srow = nullptr;
+  FC_CHECK(fc_dev_alloc(ctx, &rowid, (size_t)n));
+  FC_CHECK(fc_dev_alloc(ctx, &slevel, (size_t)n));
+  FC_CHECK(fc_dev_alloc(ctx, &srow, (size_t)n));
+  k_iota<<<fc_blocks(n, B), B, 0, ctx->stream>>>(rowid, n);
+  FC_LAUNCH_CHECK();
+  void *tmp = nullptr;
+  size_t bytes = 0;
+  FC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, level, slevel, rowid, srow, n, 0, 32, ctx->stream));
+  FC_CUDA(cudaMalloc(&tmp, bytes ? bytes : 1));
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, bytes, level, slevel, rowid, srow, n, 0, 32, ctx->stream);
+  int nlev = 0;
+  cudaMemcpyAsync(&nlev, slevel + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(tmp);
+  FC_CUDA(e);
+  ctx->launches++;
+  nlev += 1;
+  int *hist = nullptr;
+  FC_CHECK(fc_dev_alloc(ctx, &hist, (size_t)nlev));
+  FC_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)nlev, ctx->stream));
+  k_level_hist<<<fc_blocks(n, B), B, 0, ctx->stream>>>(level, n, hist);
+  FC_LAUNCH_CHECK();
+  std::vector<int> h(nlev), start(nlev + 1), slot(nlev + 1), blkb(nlev + 1);
+  FC_CUDA(cudaMemcpyAsync(h.data(), hist, sizeof(int) * (size_t)nlev, cudaMemcpyDeviceToHost, ctx->stream));
+  FC_CUDA(cudaStreamSynchronize(ctx->stream));
+  start[0] = slot[0] = blkb[0] = 0;
+  for (int l = 0; l < nlev; ++l) {
+    int nb = (h[l] + TRI_BLOCK - 1) / TRI_BLOCK;
+    start[l + 1] = start[l] + h[l];
+    blkb[l + 1] = blkb[l] + nb;
+    slot[l + 1] = slot[l] + nb * TRI_BLOCK;
+  }
+  const int nblocks = blkb[nlev];
+  std::vector<int> blev(nblocks);
+  for (int l = 0; l < nlev; ++l)
+    for (int b = blkb[l]; b < blkb[l + 1]; ++b) blev[b] = l;
+  fc_levels_free(L);
+  L.nlev = nlev;
+  L.nslots = slot[nlev];
+  int *dstart = nullptr, *dslot = nullptr;
+  FC_CHECK(fc_dev_alloc(ctx, &dstart, (size_t)nlev + 1));
+  FC_CHECK(fc_dev_alloc(ctx, &dslot, (size_t)nlev + 1));
+  FC_CHECK(fc_dev_alloc(ctx, &L.rows, (size_t)L.nslots));
+  FC_CHECK(fc_dev_alloc(ctx, &L.blk_level, (size_t)nblocks));
+  FC_CHECK(fc_dev_alloc(ctx, &L.lev_blocks_before, (size_t)nlev + 1));
+  FC_CHECK(fc_dev_alloc(ctx, &L.done, (size_t)nlev));
+  FC_CHECK(fc_dev_alloc(ctx, &L.ticket, 1));
+  FC_CUDA(cudaMemcpyAsync(dstart, start.data(), sizeof(int) * (nlev + 1), cudaMemcpyHostToDevice, ctx->stream));
+  FC_CUDA(cudaMemcpyAsync(dslot, slot.data(), sizeof(int) * (nlev + 1), cudaMemcpyHostToDevice, ctx->stream));
+  FC_CUDA(cudaMemcpyAsync(L.blk_level, blev.data(), sizeof(int) * (size_t)nblocks, cudaMemcpyHostToDevice, ctx->stream));
+  FC_CUDA(cudaMemcpyAsync(L.lev_blocks_before, blkb.data(), sizeof(int) * (nlev + 1), cudaMemcpyHostToDevice,
+                          ctx->stream));
+  k_fill<<<fc_blocks(L.nslots, B), B, 0, ctx->stream>>>(L.rows, -1, L.nslots);
+  FC_LAUNCH_CHECK();
+  k_level_place<<<fc_blocks(n, B), B, 0, ctx->stream>>>(slevel, srow, n, dstart, dslot, L.rows);
+  FC_LAUNCH_CHECK();
+  FC_CUDA(cudaMemsetAsync(L.done, 0, sizeof(unsigned int) * (size_t)nlev, ctx->stream));
+  FC_CUDA(cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), ctx->stream));
+  L.epoch = 0;
+  FC_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(level); cudaFree(changed); cudaFree(rowid); cudaFree(slevel); cudaFree(srow); cudaFree(hist);
+  cudaFree(dstart); cudaFree(dslot);
+  return FC_OK;
+}
+
+enum { TRI_FWD = 0, TRI_BWD = 1, TRI_DIC = 2, TRI_DIC_PAR = 3, TRI_DILU = 4 };
+
+// One sweep.  `in`: r (FWD) or the forward result t (BWD); `out`: t (FWD), z (BWD), d (factor modes).
+template <int MODE>
+__global__ void __launch_bounds__(TRI_BLOCK)
+k_tri_sweep(const int *__restrict__ rows, const int *__restrict__ blk_level,
+            const int *__restrict__ lev_blocks_before, unsigned int *done, unsigned int *ticket,
+            unsigned int ticket_base, unsigned int sweep_no, const int *__restrict__ ioffset,
+            const int *__restrict__ ja, const int *__restrict__ diag, const int *__restrict__ tpos,
+            const double *__restrict__ a, const double *__restrict__ d, const double *__restrict__ in,
+            double *out, double small, double padd, int n, const fc_scalars *sc) {
+  __shared__ unsigned int s_b;
+  if (sc && sc->done) return;
+  if (threadIdx.x == 0) s_b = atomicAdd(ticket, 1u) - ticket_base;
+  __syncthreads();
+  const unsigned int b = s_b;
+  const int lev = blk_level[b];
+  const int row = rows[b * TRI_BLOCK + threadIdx.x];
+  int s = 0, e = 0;
+  double v = 0.0, di = 0.0;
+  if (row >= 0) {  // everything that does not depend on other rows is fetched before the wait
+    if (MODE == TRI_BWD) { s = diag[row] + 1; e = ioffset[row + 1]; }
+    else { s = ioffset[row]; e = diag[row]; }
+    if (MODE == TRI_FWD) { v = in[row]; di = d[row]; }
+    else if (MODE == TRI_BWD) { di = d[row]; v = in[row] / (di + small); }   // z = z/(d+small), iccg.f90:102
+    else v = a[diag[row]];
+  }
+  if (lev > 0) {
+    if (threadIdx.x == 0) {
+      const unsigned int need = sweep_no * (unsigned int)(lev_blocks_before[lev] - lev_blocks_before[lev - 1]);
+      volatile unsigned int *c = done + (lev - 1);
+      while (*c < need) { __nanosleep(20); }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  if (row >= 0) {
+    for (int k = s; k < e; ++k) {
+      const int j = ja[k];
+      if (MODE == TRI_BWD && j >= n) break;            // halo columns never enter the preconditioner
+      const double zj = __ldcg(out + j);               // written by another CTA during this launch: bypass L1
+      const double ak = a[k];
+      if (MODE == TRI_FWD || MODE == TRI_BWD) v = v - ak * zj;
+      else if (MODE == TRI_DIC) v = v - (ak * ak) * zj;            // iccg.f90:80
+      else if (MODE == TRI_DIC_PAR) v = v - ak * zj * ak;          // src-parallel/iccg.f90:97
+      else v = v - ak * zj * a[tpos[k]];                           // bicgstab.f90:76
+    }
+    if (MODE == TRI_FWD || MODE == TRI_BWD) out[row] = v * di;
+    else out[row] = 1.0 / (v + padd);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(done + lev, 1u);
+}
+
+template <int MODE>
+int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const double *in, double *out,
+          double small, double padd, bool guarded) {
+  const int nblocks = L.nslots / TRI_BLOCK;
+  const unsigned int base = (unsigned int)(L.epoch * (unsigned long long)nblocks);
+  L.epoch++;
+  k_tri_sweep<MODE><<<nblocks, TRI_BLOCK, 0, ctx->stream>>>(
+      L.rows, L.blk_level, L.lev_blocks_before, L.done, L.ticket, base, (unsigned int)L.epoch, ctx->ioffset, ctx->ja,
+      ctx->diag, ctx->tpos, a, d, in, out, small, padd, ctx->n, guarded ? ctx->sc : nullptr);
+  FC_LAUNCH_CHECK();
+  return FC_OK;
+}
+
+}  // namespace
+
+void fc_levels_free(fc_levels &L) {
+  cudaFree(L.rows); cudaFree(L.blk_level); cudaFree(L.lev_blocks_before); cudaFree(L.done); cudaFree(L.ticket);
+  L = fc_levels{};
+}
+
+int fc_levels_build(fc_context *ctx) {
+  if (ctx->has_levels) return FC_OK;
+  FC_CHECK(build_one(ctx, ctx->lower, 1));
+  FC_CHECK(build_one(ctx, ctx->upper, 0));
+  ctx->has_levels = true;
+  return FC_OK;
+}
+
+// counters are monotone over the sweeps of one solve; restart them so that they never wrap
+int fc_levels_reset(fc_context *ctx) {
+  for (fc_levels *L : {&ctx->lower, &ctx->upper}) {
+    FC_CUDA(cudaMemsetAsync(L->done, 0, sizeof(unsigned int) * (size_t)L->nlev, ctx->stream));
+    FC_CUDA(cudaMemsetAsync(L->ticket, 0, sizeof(unsigned int), ctx->stream));
+    L->epoch = 0;
+  }
+  return FC_OK;
+}
+
+// kind: 0 DIC serial, 1 DIC src-parallel, 2 DILU
+int fc_precond_factor(fc_context *ctx, int kind, const double *a, double *d, double padd) {
+  if (kind == 0) return sweep<TRI_DIC>(ctx, ctx->lower, a, nullptr, nullptr, d, 0.0, padd, false);
+  if (kind == 1) return sweep<TRI_DIC_PAR>(ctx, ctx->lower, a, nullptr, nullptr, d, 0.0, padd, false);
+  return sweep<TRI_DILU>(ctx, ctx->lower, a, nullptr, nullptr, d, 0.0, padd, false);
+}
+
+// z = (D+U)^-1 D (D+L)^-1 r with the reference's intermediate z/(d+small); t is scratch
+int fc_precond_apply(fc_context *ctx, const double *a, const double *d, const double *r, double *t, double *z,
+                     double small) {
+  FC_CHECK(sweep<TRI_FWD>(ctx, ctx->lower, a, d, r, t, small, 0.0, true));
+  return sweep<TRI_BWD>(ctx, ctx->upper, a, d, t, z, small, 0.0, true);
+}

@@ -1,0 +1,313 @@
+"""ctypes binding of ``libfcapp_cuda.so`` (C ABI: ``include/fcapp.h``).
+
+This is the Python stand-in for the Fortran ISO_C_BINDING shim (``fortran/fcapp_shim.f90``):
+it passes exactly what gfortran would pass -- 1-based int32 index arrays, float64 arrays,
+plain pointers -- and nothing else.  There is no CPU path: if the shared library has not
+been built (``python -c "import __graft_entry__ as g; g.build()"``) loading fails loudly,
+and without a CUDA device ``fc_create`` returns ``FC_ERR_NODEVICE``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfcapp_cuda.so")
+
+FC_OK, FC_ERR_ARG, FC_ERR_CUDA, FC_ERR_NCCL, FC_ERR_UNSUPPORTED, FC_ERR_NODEVICE = range(6)
+DPCG, ICCG, BICGSTAB = 0, 1, 2
+SOLVERS = {"dpcg": DPCG, "iccg": ICCG, "bicgstab": BICGSTAB}
+
+FIELDS = ("U", "V", "W", "P", "PP", "DEN", "FLMASS", "APU", "APV", "APW", "DUDXI", "DVDXI", "DWDXI", "DPDXI",
+          "A", "SU", "RES", "FMI", "FMO", "APR", "FMPRO", "SCRATCH_T")
+F = {name: i for i, name in enumerate(FIELDS)}
+
+SMALL = float(np.float32(1e-20))   # `small` of module parameters is a default-real literal (modules_allocatable.f90:27)
+TOL = float(np.float32(1e-13))     # dpcg.f90:37
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+# every symbol include/fcapp.h declares (checked by tests/test_abi.py)
+SYMBOLS = (
+    "fc_create", "fc_destroy", "fc_last_error", "fc_version", "fc_comm_unique_id", "fc_comm_init", "fc_set_mesh",
+    "fc_create_csr", "fc_field_size", "fc_upload", "fc_download", "fc_fill", "fc_synchronize", "fc_spmv",
+    "fc_grad_gauss", "fc_grad_gauss_corrected", "fc_bpres", "fc_laplacian", "fc_solve", "fc_solve_host",
+    "fc_solve_csr", "fc_calcp_assemble", "fc_calcp", "fc_calcp_host", "fc_exchange", "fc_global_sum",
+    "fc_get_timings", "fc_time_spmv", "fc_stream",
+)
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "numCells", "numInnerFaces", "numFaces", "numTotal", "npro",
+        "ninl", "nout", "nsym", "nwal", "npru", "noc",
+        "iProcFacesStart", "iInletFacesStart", "iOutletFacesStart", "iSymmetryFacesStart",
+        "iWallFacesStart", "iPressOutletFacesStart", "iOCFacesStart")] + [
+        ("owner", ip), ("neighbour", ip),
+        ("xc", dp), ("yc", dp), ("zc", dp), ("vol", dp),
+        ("arx", dp), ("ary", dp), ("arz", dp), ("xf", dp), ("yf", dp), ("zf", dp),
+        ("facint", dp), ("fpro", dp),
+        ("numConnections", C.c_int), ("neighbProcNo", ip), ("neighbProcOffset", ip), ("gloCells", C.c_int)]
+
+
+class SolverOpts(C.Structure):
+    _fields_ = [("sor", C.c_double), ("nsw", C.c_int), ("small", C.c_double), ("tol", C.c_double),
+                ("parallel", C.c_int)]
+
+
+class SolverReport(C.Structure):
+    _fields_ = [("res0", C.c_double), ("resl", C.c_double), ("iters", C.c_int)]
+
+
+class CalcpOpts(C.Structure):
+    _fields_ = [("npcor", C.c_int), ("nigrad", C.c_int), ("nipgrad", C.c_int), ("pRefCell", C.c_int),
+                ("urf_p", C.c_double), ("solver", C.c_int), ("const_mflux", C.c_int), ("flomas", C.c_double),
+                ("lsq_flag", C.c_int), ("flux_variant", C.c_int), ("sol", SolverOpts)]
+
+
+class CalcpReport(C.Structure):
+    _fields_ = [("rep", SolverReport * 8), ("sumLocalContErr", C.c_double), ("globalContErr", C.c_double)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("solve_ms", C.c_double), ("assemble_ms", C.c_double), ("correct_ms", C.c_double),
+                ("spmv_ms", C.c_double), ("launches", C.c_longlong)]
+
+
+class FcError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libfcapp_cuda error {code}: {msg}")
+        self.code = code
+
+
+_LIB: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library.  Raises if it has not been built -- never falls back."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} is missing: build it with `make -C freecappuccino_b200/csrc` "
+                "(or __graft_entry__.build()).  freecappuccino_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        lib.fc_last_error.restype = C.c_char_p
+        lib.fc_last_error.argtypes = [C.c_void_p]
+        lib.fc_stream.restype = C.c_void_p
+        lib.fc_stream.argtypes = [C.c_void_p]
+        for name in SYMBOLS:
+            fn = getattr(lib, name)
+            if name not in ("fc_last_error", "fc_stream"):
+                fn.restype = C.c_int
+        _LIB = lib
+    return _LIB
+
+
+def _d(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags.c_contiguous, "float64 C-contiguous array expected"
+    return a.ctypes.data_as(dp)
+
+
+def _i(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags.c_contiguous, "int32 C-contiguous array expected"
+    return a.ctypes.data_as(ip)
+
+
+def solver_opts(sor: float, nsw: int, small: float = SMALL, tol: float = TOL, parallel: bool = False) -> SolverOpts:
+    return SolverOpts(sor, nsw, small, tol, int(parallel))
+
+
+def calcp_opts(npcor=1, nigrad=1, pRefCell=1, urf_p=0.3, solver="iccg", const_mflux=False, flomas=0.0,
+               lsq_flag=False, flux_variant=0, sor=1e-2, nsw=100, small=SMALL, tol=TOL, parallel=False) -> CalcpOpts:
+    return CalcpOpts(npcor, nigrad, 2, pRefCell, urf_p, SOLVERS[solver], int(const_mflux), flomas,
+                     int(lsq_flag), flux_variant, SolverOpts(sor, nsw, small, tol, int(parallel)))
+
+
+class Context:
+    """One ``fc_context`` = one rank / one GPU."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        rc = self.lib.fc_create(device, C.byref(self.h))
+        if rc != FC_OK:
+            raise FcError(rc, (self.lib.fc_last_error(None) or b"").decode())
+        self.mesh = None
+        self._keep = []
+
+    # -- plumbing ---------------------------------------------------------
+    def _ck(self, rc: int):
+        if rc != FC_OK:
+            raise FcError(rc, (self.lib.fc_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if self.h:
+            self.lib.fc_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def comm_init(self, rank: int, nranks: int, uid: bytes):
+        self._ck(self.lib.fc_comm_init(self.h, rank, nranks, C.c_char_p(uid)))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = load().fc_comm_unique_id(buf)
+        if rc != FC_OK:
+            raise FcError(rc, "ncclGetUniqueId failed")
+        return buf.raw
+
+    # -- mesh / pattern ---------------------------------------------------
+    def set_mesh(self, m):
+        """``m``: :class:`freecappuccino_b200.mesh.Mesh` (arrays exactly as the Fortran host holds them)."""
+        s = MeshDesc()
+        s.numCells, s.numInnerFaces, s.numFaces, s.numTotal, s.npro = (m.numCells, m.numInnerFaces, m.numFaces,
+                                                                       m.numTotal, m.npro)
+        s.ninl, s.nout, s.nsym, s.nwal, s.npru, s.noc = (m.count("inlet"), m.count("outlet"), m.count("symmetry"),
+                                                         m.count("wall"), m.count("prOutlet"), m.noc)
+        s.iProcFacesStart = m.iProcFacesStart
+        s.iInletFacesStart, s.iOutletFacesStart = m.faces_start("inlet"), m.faces_start("outlet")
+        s.iSymmetryFacesStart, s.iWallFacesStart = m.faces_start("symmetry"), m.faces_start("wall")
+        s.iPressOutletFacesStart, s.iOCFacesStart = m.faces_start("prOutlet"), m.iOCFacesStart
+        keep = []
+
+        def d(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            keep.append(a)
+            return _d(a)
+
+        def i(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.int32)
+            keep.append(a)
+            return _i(a)
+
+        s.owner, s.neighbour = i(m.owner), i(m.neighbour)
+        s.xc, s.yc, s.zc, s.vol = d(m.xc), d(m.yc), d(m.zc), d(m.vol)
+        s.arx, s.ary, s.arz, s.xf, s.yf, s.zf = d(m.arx), d(m.ary), d(m.arz), d(m.xf), d(m.yf), d(m.zf)
+        s.facint, s.fpro = d(m.facint), d(m.fpro)
+        s.numConnections = 0 if m.neighbProcNo is None else int(len(m.neighbProcNo))
+        s.neighbProcNo, s.neighbProcOffset = i(m.neighbProcNo), i(m.neighbProcOffset)
+        s.gloCells = m.gloCells or m.numCells
+        self._ck(self.lib.fc_set_mesh(self.h, C.byref(s)))
+        self.mesh = m
+
+    def create_csr(self, download: bool = True):
+        """``create_CSR_matrix_from_mesh_data``: returns the 1-based (ioffset, ja, diag, icell_jcell, jcell_icell)."""
+        m = self.mesh
+        if not download:
+            self._ck(self.lib.fc_create_csr(self.h, None, None, None, None, None))
+            return None
+        ioffset = np.zeros(m.numCells + 1, np.int32)
+        ja = np.zeros(m.nnz, np.int32)
+        diag = np.zeros(m.numCells, np.int32)
+        ij = np.zeros(m.numInnerFaces, np.int32)
+        ji = np.zeros(m.numInnerFaces, np.int32)
+        self._ck(self.lib.fc_create_csr(self.h, _i(ioffset), _i(ja), _i(diag), _i(ij), _i(ji)))
+        return ioffset, ja, diag, ij, ji
+
+    # -- fields -----------------------------------------------------------
+    def field_size(self, name: str) -> int:
+        n = C.c_size_t()
+        self._ck(self.lib.fc_field_size(self.h, F[name], C.byref(n)))
+        return n.value
+
+    def upload(self, name: str, a: np.ndarray):
+        a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        self._ck(self.lib.fc_upload(self.h, F[name], _d(a), C.c_size_t(a.size)))
+
+    def download(self, name: str, n: Optional[int] = None) -> np.ndarray:
+        n = self.field_size(name) if n is None else n
+        out = np.zeros(n)
+        self._ck(self.lib.fc_download(self.h, F[name], _d(out), C.c_size_t(n)))
+        return out
+
+    def fill(self, name: str, value: float):
+        self._ck(self.lib.fc_fill(self.h, F[name], C.c_double(value)))
+
+    def synchronize(self):
+        self._ck(self.lib.fc_synchronize(self.h))
+
+    # -- operators --------------------------------------------------------
+    def spmv(self, x: str, y: str):
+        self._ck(self.lib.fc_spmv(self.h, F[x], F[y]))
+
+    def time_spmv(self, x: str, y: str, reps: int) -> float:
+        ms = C.c_double()
+        self._ck(self.lib.fc_time_spmv(self.h, F[x], F[y], reps, C.byref(ms)))
+        return ms.value
+
+    def grad_gauss(self, phi: str, grad: str, nigrad: int = 1):
+        self._ck(self.lib.fc_grad_gauss(self.h, F[phi], F[grad], nigrad))
+
+    def grad_gauss_corrected(self, phi: str, grad: str, zero_seed: bool = False):
+        self._ck(self.lib.fc_grad_gauss_corrected(self.h, F[phi], F[grad], int(zero_seed)))
+
+    def bpres(self, p: str, istage: int):
+        self._ck(self.lib.fc_bpres(self.h, F[p], istage))
+
+    def laplacian(self, mu: str, phi: str):
+        self._ck(self.lib.fc_laplacian(self.h, F[mu], F[phi]))
+
+    def solve(self, solver: str, fi: str, opts: SolverOpts) -> SolverReport:
+        rep = SolverReport()
+        self._ck(self.lib.fc_solve(self.h, SOLVERS[solver], F[fi], C.byref(opts), C.byref(rep)))
+        return rep
+
+    def solve_host(self, solver: str, a: np.ndarray, su: np.ndarray, fi: np.ndarray, opts: SolverOpts,
+                   res: Optional[np.ndarray] = None) -> SolverReport:
+        rep = SolverReport()
+        self._ck(self.lib.fc_solve_host(self.h, SOLVERS[solver], _d(a), _d(su), _d(fi), _d(res), C.byref(opts),
+                                        C.byref(rep)))
+        return rep
+
+    def solve_csr(self, solver: str, ioffset, ja, diag, a, su, fi, opts: SolverOpts, history: bool = False):
+        rep = SolverReport()
+        hist = np.zeros(max(opts.nsw, 1)) if history else None
+        self._ck(self.lib.fc_solve_csr(self.h, SOLVERS[solver], int(diag.size), int(ja.size), _i(ioffset), _i(ja),
+                                       _i(diag), _d(a), _d(su), _d(fi), C.byref(opts), C.byref(rep), _d(hist)))
+        return (rep, hist[:rep.iters]) if history else rep
+
+    def calcp_assemble(self, opts: CalcpOpts):
+        self._ck(self.lib.fc_calcp_assemble(self.h, C.byref(opts)))
+
+    def calcp(self, opts: CalcpOpts) -> CalcpReport:
+        rep = CalcpReport()
+        self._ck(self.lib.fc_calcp(self.h, C.byref(opts), C.byref(rep)))
+        return rep
+
+    def calcp_host(self, opts: CalcpOpts, u, v, w, p, pp, apu, apv, apw, flmass) -> CalcpReport:
+        rep = CalcpReport()
+        self._ck(self.lib.fc_calcp_host(self.h, C.byref(opts), _d(u), _d(v), _d(w), _d(p), _d(pp), _d(apu), _d(apv),
+                                        _d(apw), _d(flmass), C.byref(rep)))
+        return rep
+
+    def exchange(self, field: str):
+        self._ck(self.lib.fc_exchange(self.h, F[field]))
+
+    def global_sum(self, value: float) -> float:
+        v = C.c_double(value)
+        self._ck(self.lib.fc_global_sum(self.h, C.byref(v)))
+        return v.value
+
+    def timings(self) -> Timings:
+        t = Timings()
+        self._ck(self.lib.fc_get_timings(self.h, C.byref(t)))
+        return t

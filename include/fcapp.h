@@ -1,0 +1,225 @@
+/*
+ * fcapp.h -- C ABI of libfcapp_cuda.so: the B200 (sm_100a) implementation of
+ * freeCappuccino's pressure-correction path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes and returns
+ * an int status (FC_OK = 0).  This is exactly what a Fortran ISO_C_BINDING
+ * interface block binds (see fortran/fcapp_shim.f90 and INTEGRATION.md): the
+ * reference keeps its subroutine signatures (`call calcp`, `call dpcg(fi,ifi)`,
+ * `call laplacian(mu,phi)`, `call grad(phi,dPhidxi)`, ...) and their bodies
+ * become calls into this library.
+ *
+ * Conventions (the reference's own): INTEGER(4) / REAL(8);
+ * index arrays are 1-BASED as Fortran keeps them (`owner`, `neighbour`,
+ * `ioffset`, `ja`, `diag`, ...); gradient arrays are dPhidxi(3,numCells), i.e.
+ * xyz interleaved per cell; host arrays stay owned by the caller, the library
+ * owns device mirrors.  There is no CPU fallback anywhere behind this header.
+ *
+ * Citations are relative to the reference tree (nikola-m/freeCappuccino).
+ */
+#ifndef FCAPP_H
+#define FCAPP_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fc_context fc_context; /* opaque; one per rank / GPU */
+
+enum {
+  FC_OK = 0,
+  FC_ERR_ARG = 1,         /* bad argument / call order                    */
+  FC_ERR_CUDA = 2,        /* CUDA runtime failure (see fc_last_error)     */
+  FC_ERR_NCCL = 3,        /* NCCL failure                                 */
+  FC_ERR_UNSUPPORTED = 4, /* feature of the reference not on the GPU path */
+  FC_ERR_NODEVICE = 5     /* no CUDA device: the library never falls back */
+};
+
+/* Krylov solvers of the path: src/dpcg.f90, src/iccg.f90, src/bicgstab.f90 */
+enum { FC_DPCG = 0, FC_ICCG = 1, FC_BICGSTAB = 2 };
+
+/* Device-resident fields (`module variables`, `module sparse_matrix`).
+ * Sizes: *_T = numTotal, *_C = numCells, *_P = numCells+npro, G = 3*numCells. */
+enum {
+  FC_U = 0, FC_V, FC_W, FC_P, FC_PP, FC_DEN,          /* numTotal           */
+  FC_FLMASS,                                          /* numInnerFaces      */
+  FC_APU, FC_APV, FC_APW,                             /* numCells + npro    */
+  FC_DUDXI, FC_DVDXI, FC_DWDXI, FC_DPDXI,             /* (3,numCells)       */
+  FC_A,                                               /* nnz                */
+  FC_SU, FC_RES,                                      /* numCells           */
+  FC_FMI, FC_FMO,                                     /* ninl, nout         */
+  FC_APR, FC_FMPRO,                                   /* npro               */
+  FC_SCRATCH_T,                                       /* numTotal (user vec)*/
+  FC_NUM_FIELDS
+};
+
+/* `module geometry` (src/mesh_geometry_and_topology.f90:13-98; the parallel
+ * twin adds the processor-boundary block, src-parallel/...:497-515,637-660).
+ * "FacesStart" values are 0-based offsets exactly like the reference:
+ * face = start + i, i = 1..count.  Field slots follow the cells in the order
+ * [numCells | npro halo | inlet | outlet | symmetry | wall | prOutlet].     */
+typedef struct {
+  int numCells, numInnerFaces, numFaces, numTotal;
+  int npro;
+  int ninl, nout, nsym, nwal, npru, noc;
+  int iProcFacesStart, iInletFacesStart, iOutletFacesStart, iSymmetryFacesStart,
+      iWallFacesStart, iPressOutletFacesStart, iOCFacesStart;
+  const int *owner;      /* [numFaces]      */
+  const int *neighbour;  /* [numInnerFaces] */
+  const double *xc, *yc, *zc, *vol;             /* [numCells + npro]  */
+  const double *arx, *ary, *arz, *xf, *yf, *zf; /* [numFaces]         */
+  const double *facint;                         /* [numInnerFaces]    */
+  const double *fpro;                           /* [npro] or NULL     */
+  /* processor connectivity (`process` file; my_mpi_module): */
+  int numConnections;
+  const int *neighbProcNo;     /* [numConnections] ranks, 0-based          */
+  const int *neighbProcOffset; /* [numConnections+1], 1-based into 1..npro */
+  int gloCells;                /* global cell count (ppref = mean in MPI)  */
+} fc_mesh_desc;
+
+/* ---- life cycle ------------------------------------------------------- */
+int fc_create(int device, fc_context **out);
+int fc_destroy(fc_context *ctx);
+const char *fc_last_error(const fc_context *ctx);
+int fc_version(void);
+
+/* ---- multi-GPU plumbing: replaces MPI_COMM_WORLD of src-parallel -------
+ * One rank per GPU.  Rank 0 calls fc_comm_unique_id and broadcasts the 128
+ * bytes with whatever the host program has (MPI_Bcast in the Fortran MPI
+ * build, torch.distributed in the Python harness).                        */
+int fc_comm_unique_id(char id128[128]);
+int fc_comm_init(fc_context *ctx, int rank, int nranks, const char id128[128]);
+
+/* ---- mesh + CSR pattern ----------------------------------------------- */
+/* Copies the geometry arrays to the device and builds the cell-to-face map. */
+int fc_set_mesh(fc_context *ctx, const fc_mesh_desc *mesh);
+
+/* create_CSR_matrix_from_mesh_data (src/sparse_matrix.f90:42-172): builds the
+ * pattern on the device and, for every non-NULL pointer, returns the 1-based
+ * arrays bit-identical to the reference's.  Sizes: ioffset[numCells+1],
+ * ja[nnz], diag[numCells], icell_jcell/jcell_icell[numInnerFaces].          */
+int fc_create_csr(fc_context *ctx, int *ioffset, int *ja, int *diag, int *icell_jcell,
+                  int *jcell_icell);
+
+/* ---- field transfer ---------------------------------------------------- */
+int fc_field_size(const fc_context *ctx, int field, size_t *n);
+int fc_upload(fc_context *ctx, int field, const double *host, size_t n);
+int fc_download(fc_context *ctx, int field, double *host, size_t n);
+int fc_fill(fc_context *ctx, int field, double value);
+int fc_synchronize(fc_context *ctx);
+
+/* ---- operators (device-resident fields) -------------------------------- */
+/* y = A x over the resident CSR; x, y are field ids of size >= numCells.
+ * One launch of the SpMV kernel of the Krylov loop (dpcg.f90:105-110).      */
+int fc_spmv(fc_context *ctx, int x_field, int y_field);
+
+/* grad(phi,dPhidxi) with the Gauss option (gradients.f90:95-151 ->
+ * grad_gauss.f90:1-124): nigrad fixed-point passes.                         */
+int fc_grad_gauss(fc_context *ctx, int phi_field, int grad_field, int nigrad);
+/* grad(phi,dPhidxi,'gauss_corrected') (gradients.f90:197-259 ->
+ * grad_gauss_corrected.f90): one pass seeded by the current grad_field.
+ * `zero_seed` != 0 reproduces the option wrapper, which zeroes dPhidxi first
+ * (gradients.f90:222).                                                      */
+int fc_grad_gauss_corrected(fc_context *ctx, int phi_field, int grad_field, int zero_seed);
+/* bpres(p,istage) (bpres.f90:37-150), gradient taken from FC_DPDXI.         */
+int fc_bpres(fc_context *ctx, int p_field, int istage);
+
+/* laplacian(mu,phi) (fvm_laplacian.f90:1-163): fills FC_A and updates FC_SU
+ * (wall Dirichlet part).  mu_field has >= numCells (+npro) entries.          */
+int fc_laplacian(fc_context *ctx, int mu_field, int phi_field);
+
+typedef struct {
+  double sor;    /* sor(ifi): relative L1 tolerance                         */
+  int nsw;       /* nsw(ifi): iteration cap                                 */
+  double small;  /* `small` of module parameters: (double)1e-20f            */
+  double tol;    /* early-return threshold on res0, (double)1e-13f; <0 off  */
+  int parallel;  /* 1 = src-parallel arithmetic (+small in preconditioners) */
+} fc_solver_opts;
+
+typedef struct {
+  double res0, resl; /* initial / final L1 residual (resor(ifi) = res0)     */
+  int iters;
+} fc_solver_report;
+
+/* dpcg / iccg / bicgstab (fi, ifi): solves A fi = su with the resident FC_A,
+ * FC_SU; fi is a numTotal field id (only 1..numCells is updated); FC_RES
+ * holds the final residual afterwards.                                      */
+int fc_solve(fc_context *ctx, int solver, int fi_field, const fc_solver_opts *o,
+             fc_solver_report *rep);
+
+/* Host-buffer form, the drop-in body of `subroutine dpcg(fi,ifi)` when the
+ * matrix lives in the Fortran module arrays: uploads a(nnz), su(numCells),
+ * fi(numTotal), solves, downloads fi(1:numCells) and res(numCells).  All
+ * copies are inside the call.                                               */
+int fc_solve_host(fc_context *ctx, int solver, const double *a, const double *su, double *fi,
+                  double *res, const fc_solver_opts *o, fc_solver_report *rep);
+
+/* Explicit-array form shaped like the reference's only explicit interfaces:
+ * LIS solve_csr(numCells,nnz,ioffset,ja,aval,su,phi)
+ * (LIS_linear_solver_library.f95:106-119) and the test copies
+ * X(a,ja,ioffset,diag,nnz,numCells,numTotal,su,fi)
+ * (tests/test_sparse_solvers.f90:8,233,398).  Needs no mesh: the context
+ * adopts the given 1-based pattern.  `hist` (nsw doubles or NULL) receives
+ * resl of every iteration, the numbers tests/output.txt prints.            */
+int fc_solve_csr(fc_context *ctx, int solver, int numCells, int nnz, const int *ioffset,
+                 const int *ja, const int *diag, const double *a, const double *su, double *fi,
+                 const fc_solver_opts *o, fc_solver_report *rep, double *hist);
+
+typedef struct {
+  int npcor, nigrad, nipgrad; /* parameters: npcor, nigrad, nipgrad(=2)      */
+  int pRefCell;               /* 1-based                                      */
+  double urf_p;               /* urf(ip)                                      */
+  int solver;                 /* FC_DPCG / FC_ICCG (shipped) / FC_BICGSTAB    */
+  int const_mflux;            /* .true. skips adjustMassFlow                  */
+  double flomas;
+  int lsq_flag;               /* lstsq_qr.or.lstsq_dm: extra gauss_corrected  */
+  int flux_variant;           /* 0 facefluxmass, 1 facefluxmass2, 2 _piso     */
+  fc_solver_opts sol;
+} fc_calcp_opts;
+
+typedef struct {
+  fc_solver_report rep[8];    /* one per pressure corrector                   */
+  double sumLocalContErr, globalContErr; /* continuityErrors.h               */
+} fc_calcp_report;
+
+/* The assembly half of calcp (calcp-multiple_correction_SIMPLE.f90:34-107):
+ * gradients of U,V,W, face fluxes, FC_A / FC_SU / FC_FLMASS.                */
+int fc_calcp_assemble(fc_context *ctx, const fc_calcp_opts *o);
+/* `call calcp`: assemble + npcor x (solve, bpres/grad, flux / velocity /
+ * pressure correction) + continuity report, all on device-resident fields. */
+int fc_calcp(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep);
+
+/* Host-buffer form of `call calcp`: uploads u,v,w,p (numTotal), apu,apv,apw
+ * (numCells+npro), runs fc_calcp, downloads u,v,w,p,pp (numTotal) and flmass
+ * (numInnerFaces).  den, fmi are uploaded separately (they do not change per
+ * SIMPLE iteration).                                                        */
+int fc_calcp_host(fc_context *ctx, const fc_calcp_opts *o, double *u, double *v, double *w,
+                  double *p, double *pp, const double *apu, const double *apv, const double *apw,
+                  double *flmass, fc_calcp_report *rep);
+
+/* ---- src-parallel communication (exchange.f90, global_sum_mpi.f90) ------ */
+int fc_exchange(fc_context *ctx, int field);          /* halo of a numTotal / numPCells field */
+int fc_global_sum(fc_context *ctx, double *value);    /* in-place sum over ranks (host scalar) */
+
+/* ---- measurement helpers (bench.py): device time of the last fc_solve /
+ * fc_calcp phases in milliseconds, measured with CUDA events on the library's
+ * own stream.                                                               */
+typedef struct {
+  double solve_ms;     /* Krylov loop of the last solve                       */
+  double assemble_ms;  /* gradients + face loop + row gather of last calcp    */
+  double correct_ms;   /* post-solve corrections of last calcp                */
+  double spmv_ms;      /* mean SpMV launch duration if spmv timing was on     */
+  long long launches;  /* kernels launched by the library since creation      */
+} fc_timings;
+int fc_get_timings(const fc_context *ctx, fc_timings *t);
+/* Times `reps` back-to-back launches of the SpMV kernel (y = A x) with CUDA
+ * events on the library stream; returns the mean in ms.                     */
+int fc_time_spmv(fc_context *ctx, int x_field, int y_field, int reps, double *mean_ms);
+void *fc_stream(fc_context *ctx); /* cudaStream_t of the context */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCAPP_H */

@@ -1,0 +1,257 @@
+"""GPU parity tests: every call goes through the C ABI of libfcapp_cuda.so (ctypes) and is
+compared with the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): CSR integers bit-exact; assembled coefficients / fields
+within 1e-10 relative L2 (the kernels keep the reference's summation order and are built
+without FMA, so most comparisons are in fact exact and are asserted as such); Krylov
+iteration counts within +-1.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from freecappuccino_b200 import cases
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def fc():
+    from freecappuccino_b200 import lib
+    return lib
+
+
+def make_ctx(fc, mesh):
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    csr = ctx.create_csr()
+    return ctx, csr
+
+
+MESHES = {
+    "hex": lambda: cases.hex_case(12, 10, 8),
+    "hex_mixed_bc": lambda: cases.hex_case(9, 7, 11, kinds=("inlet", "outlet", "wall", "symmetry", "wall", "prOutlet")),
+    "skew": lambda: cases.skew_case(),
+    "slab_1cell_thick": lambda: cases.hex_case(20, 20, 1, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry")),
+    "single_cell": lambda: cases.hex_case(1, 1, 1),
+}
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+def test_csr_pattern_bit_exact(fc, name):
+    mesh = MESHES[name]()
+    ctx, (ioffset, ja, diag, ij, ji) = make_ctx(fc, mesh)
+    ref = oracle.create_csr(mesh)
+    assert np.array_equal(ioffset, ref.ioffset)
+    assert np.array_equal(ja, ref.ja)
+    assert np.array_equal(diag, ref.diag)
+    assert np.array_equal(ij, ref.icell_jcell)
+    assert np.array_equal(ji, ref.jcell_icell)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["hex", "skew", "slab_1cell_thick"])
+def test_spmv_bit_exact(fc, name):
+    mesh = MESHES[name]()
+    ctx, _ = make_ctx(fc, mesh)
+    ref = oracle.create_csr(mesh)
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal(mesh.nnz)
+    x = rng.standard_normal(mesh.numTotal)
+    ctx.upload("A", a)
+    ctx.upload("PP", x)
+    ctx.spmv("PP", "SCRATCH_T")
+    y = ctx.download("SCRATCH_T")[:mesh.numCells]
+    assert np.array_equal(y, oracle.spmv(ref, a, x))
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["hex_mixed_bc", "skew"])
+@pytest.mark.parametrize("nigrad", [1, 2, 3])
+def test_grad_gauss_bit_exact(fc, name, nigrad):
+    mesh = MESHES[name]()
+    ctx, _ = make_ctx(fc, mesh)
+    f = cases.flow_fields(mesh)
+    ctx.upload("P", f["p"])
+    ctx.grad_gauss("P", "DPDXI", nigrad)
+    g = ctx.download("DPDXI").reshape(-1, 3)
+    ref = oracle.grad_gauss(mesh, f["p"], nigrad)
+    assert np.array_equal(g, ref)
+    # 'gauss_corrected' seeded with that gradient, and with the zero seed of the option wrapper
+    ctx.grad_gauss_corrected("P", "DPDXI", zero_seed=False)
+    g2 = ctx.download("DPDXI").reshape(-1, 3)
+    assert np.array_equal(g2, oracle.grad_gauss_corrected(mesh, f["p"], ref))
+    ctx.grad_gauss_corrected("P", "DPDXI", zero_seed=True)
+    g3 = ctx.download("DPDXI").reshape(-1, 3)
+    assert np.array_equal(g3, oracle.grad_gauss_corrected(mesh, f["p"], np.zeros_like(ref)))
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["hex", "hex_mixed_bc", "skew"])
+def test_laplacian_bit_exact(fc, name):
+    mesh = MESHES[name]()
+    ctx, _ = make_ctx(fc, mesh)
+    ref = oracle.create_csr(mesh)
+    rng = np.random.default_rng(11)
+    n = mesh.numCells
+    mu = -1.0 - 0.3 * rng.random(n)
+    phi = rng.standard_normal(mesh.numTotal)
+    su = cases.poisson_rhs(mesh)
+    su_ref = su.copy()
+    a_ref = oracle.laplacian(mesh, ref, mu, phi, su_ref)
+    ctx.upload("APU", mu)       # any numCells-sized field can carry mu
+    ctx.upload("PP", phi)
+    ctx.upload("SU", su)
+    ctx.laplacian("APU", "PP")
+    assert np.array_equal(ctx.download("A"), a_ref)
+    assert np.array_equal(ctx.download("SU"), su_ref)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["hex_mixed_bc", "skew"])
+@pytest.mark.parametrize("istage", [1, 2])
+def test_bpres_bit_exact(fc, name, istage):
+    mesh = MESHES[name]()
+    ctx, _ = make_ctx(fc, mesh)
+    f = cases.flow_fields(mesh)
+    g = oracle.grad_gauss(mesh, f["p"], 1)
+    p_ref = f["p"].copy()
+    oracle.bpres(mesh, p_ref, g, istage)
+    ctx.upload("P", f["p"])
+    ctx.upload("DPDXI", g)
+    ctx.bpres("P", istage)
+    assert np.array_equal(ctx.download("P"), p_ref)
+    ctx.close()
+
+
+def upload_flow(ctx, mesh, f, fmi):
+    for k, name in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("apu", "APU"), ("apv", "APV"),
+                    ("apw", "APW")):
+        ctx.upload(name, f[k])
+    if fmi.size:
+        ctx.upload("FMI", fmi)
+
+
+def oracle_fields(mesh, csr, f, fmi):
+    of = oracle.Fields(mesh, csr.nnz)
+    for k in ("u", "v", "w", "p", "den", "apu", "apv", "apw"):
+        getattr(of, k)[:] = f[k]
+    if fmi.size:
+        of.fmi[:] = fmi
+    # the incoming dPdxi of a SIMPLE iteration is the gradient of the current pressure
+    of.dPdxi[:] = oracle.grad_gauss(mesh, of.p, 1)
+    return of
+
+
+@pytest.mark.parametrize("name", ["hex_mixed_bc", "skew"])
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_calcp_assembly_bit_exact(fc, name, variant):
+    mesh = MESHES[name]()
+    ctx, _ = make_ctx(fc, mesh)
+    csr = oracle.create_csr(mesh)
+    f = cases.flow_fields(mesh)
+    fmi, flomas = cases.inlet_fluxes(mesh, f)
+    of = oracle_fields(mesh, csr, f, fmi)
+    oo = oracle.calcp_opts(solver="dpcg", flomas=flomas, flux_variant=variant)
+    oracle.calcp_assemble(mesh, csr, of, oo)
+    upload_flow(ctx, mesh, f, fmi)
+    ctx.upload("DPDXI", oracle.grad_gauss(mesh, f["p"], 1))
+    go = fc.calcp_opts(solver="dpcg", flomas=flomas, flux_variant=variant)
+    ctx.calcp_assemble(go)
+    assert np.array_equal(ctx.download("DUDXI").reshape(-1, 3), of.dUdxi)
+    assert np.array_equal(ctx.download("FLMASS"), of.flmass)
+    assert np.array_equal(ctx.download("A"), of.a)
+    assert np.array_equal(ctx.download("SU"), of.su)
+    # adjustMassFlow also rewrites the outlet slots of u, v, w
+    assert np.array_equal(ctx.download("U"), of.u)
+    ctx.close()
+
+
+@pytest.mark.parametrize("solver", ["dpcg", "iccg", "bicgstab"])
+@pytest.mark.parametrize("name,npcor,lsq", [("hex_mixed_bc", 1, False), ("skew", 2, True)])
+def test_calcp_full_parity(fc, solver, name, npcor, lsq):
+    mesh = MESHES[name]()
+    ctx, _ = make_ctx(fc, mesh)
+    csr = oracle.create_csr(mesh)
+    f = cases.flow_fields(mesh)
+    fmi, flomas = cases.inlet_fluxes(mesh, f)
+    of = oracle_fields(mesh, csr, f, fmi)
+    kw = dict(solver=solver, flomas=flomas, npcor=npcor, lsq_flag=lsq, sor=1e-8, nsw=500, pRefCell=3)
+    rep_ref = oracle.calcp(mesh, csr, of, oracle.calcp_opts(**kw))
+    upload_flow(ctx, mesh, f, fmi)
+    ctx.upload("DPDXI", oracle.grad_gauss(mesh, f["p"], 1))
+    rep = ctx.calcp(fc.calcp_opts(**kw))
+    for k in range(npcor):
+        assert abs(rep.rep[k].iters - rep_ref.rep[k].iters) <= 1, (k, rep.rep[k].iters, rep_ref.rep[k].iters)
+        assert rep.rep[k].res0 == pytest.approx(rep_ref.rep[k].res0, rel=1e-10)
+    for name_g, ref in (("U", of.u), ("V", of.v), ("W", of.w), ("P", of.p), ("FLMASS", of.flmass)):
+        assert cases.rel_l2(ctx.download(name_g), ref) < 1e-7, name_g  # solve stopped at rsm<1e-8: fields agree to solver tolerance
+    assert rep.sumLocalContErr == pytest.approx(rep_ref.sumLocalContErr, rel=1e-6, abs=1e-14)
+    ctx.close()
+
+
+@pytest.mark.parametrize("solver", ["dpcg", "iccg", "bicgstab"])
+def test_poisson_solvers_iteration_parity(fc, solver):
+    """poisson.f90 on a hex box: laplacian(mu=-1) + solve to 1e-8, iteration counts within +-1,
+    solution within 1e-10 relative L2 after a tight solve."""
+    mesh = cases.hex_case(24, 24, 6, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry"))
+    ctx, _ = make_ctx(fc, mesh)
+    csr = oracle.create_csr(mesh)
+    n = mesh.numCells
+    mu = -np.ones(n)
+    su = cases.poisson_rhs(mesh)
+    su_ref = su.copy()
+    a = oracle.laplacian(mesh, csr, mu, np.zeros(mesh.numTotal), su_ref)
+    fi_ref = np.zeros(mesh.numTotal)
+    res0, resl, iters, res = oracle.solve(solver, csr, a, su_ref, fi_ref, sor=1e-8, nsw=2000)
+    ctx.upload("APU", mu)
+    ctx.upload("SU", su)
+    ctx.fill("PP", 0.0)
+    ctx.laplacian("APU", "PP")
+    rep = ctx.solve(solver, "PP", fc.solver_opts(1e-8, 2000))
+    assert abs(rep.iters - iters) <= 1, (rep.iters, iters)
+    assert rep.res0 == pytest.approx(res0, rel=1e-12)
+    assert cases.rel_l2(ctx.download("PP")[:n], fi_ref[:n]) < 1e-7
+    # tight solve: both converge to the same discrete solution
+    fi_ref[:] = 0.0
+    oracle.solve(solver, csr, a, su_ref, fi_ref, sor=1e-14, nsw=5000)
+    ctx.fill("PP", 0.0)
+    ctx.solve(solver, "PP", fc.solver_opts(1e-14, 5000))
+    assert cases.rel_l2(ctx.download("PP")[:n], fi_ref[:n]) < TOL
+    # and it is the analytic solution to second order (poisson.f90:104)
+    exact = np.sin(2 * np.pi * mesh.xc[:n]) * np.sin(2 * np.pi * mesh.yc[:n])
+    assert np.max(np.abs(ctx.download("PP")[:n] - exact)) < 2e-2
+    ctx.close()
+
+
+# ---- the reference's own golden vector, through the explicit-array entry point ----------
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "reference_tests_output.txt")
+
+
+def test_reference_golden_5x5_through_fc_solve_csr(fc):
+    from test_oracle_golden import A1, B1, A2, B2, dense5_csr, parse_golden
+    gold = parse_golden()
+    csr = dense5_csr()
+    ctx = fc.Context(0)
+    x = np.zeros(5)
+    xo = np.zeros(5)
+    opts = fc.solver_opts(float(np.float32(1e-13)), 100, small=float(np.float32(1e-30)), tol=-1.0)
+    for g, (name, a, b) in zip(gold, (("bicgstab", A1, B1), ("iccg", A2, B2), ("dpcg", A2, B2))):
+        rep, hist = ctx.solve_csr(name, csr.ioffset, csr.ja, csr.diag, a, b, x, opts, history=True)
+        res0_o, _, iters_o, _, hist_o = oracle.solve(name, csr, a, b, xo, sor=float(np.float32(1e-13)), nsw=100,
+                                                     small=oracle.SMALL_TEST, tol=-1.0, history=True)
+        # residuals that are far above round-off must agree with the printed golden digits
+        if float(g["res0"]) > 1e-10:
+            assert f"{rep.res0:10.3E}".strip() == g["res0"]
+            assert abs(rep.iters - len(g["iters"])) <= 1
+            for (it, resl_s, _), resl in zip(g["iters"], hist):
+                if float(resl_s) > 1e-9:
+                    assert resl == pytest.approx(float(resl_s), rel=2e-3), (name, it)
+        assert [f"{v:5.2f}".strip() for v in x] == g["sol"], name
+        assert np.allclose(x, xo, rtol=1e-12, atol=1e-13)
+    ctx.close()
