@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the pressure-correction hot path (BASELINE.json: "pCorr solve: DPCG iter/s &
+SpMV HBM GB/s at 10M cells; SIMPLE iter time").
+
+A *step* is one `calcp` call -- assembly of the p' system, DPCG solve to rsm < 1e-8 and the
+flux / velocity / pressure correction -- on the synthetic 216^3 hex pressure-correction case
+(SURVEY.md 8d config 4, 10 077 696 cells).  `value` = DPCG iterations per second of whole
+steps with all inputs resident in HBM; `e2e` = the same through fc_calcp_host with pinned HOST
+buffers (H2D of u,v,w,p,apu,apv,apw and D2H of u,v,w,p,pp,flmass inside the timed region);
+`roofline` is the SpMV(+p.Ap) kernel of the Krylov loop, timed with CUDA events on the
+library's stream inside the timed steps.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 216]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SOR, NSW = 1e-8, 100000
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            d = json.load(fh)
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.f:
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def build_case(n: int):
+    from freecappuccino_b200 import cases, mesh as M
+    m = M.hex_mesh(n, n, n)
+    return m, cases.config4_fields(m)
+
+
+def algorithmic_bytes(mesh):
+    n, nnz = mesh.numCells, mesh.nnz
+    return {"spmv": 12 * nnz + 20 * n, "dpcg_iter": 12 * nnz + 116 * n}
+
+
+def cpu_port_sample(mesh, a, su, iters: int):
+    """Oracle DPCG (serial src semantics, 1 core) on the same system: `iters` iterations."""
+    from oracle import oracle
+    csr = oracle.create_csr(mesh)
+    fi = np.zeros(mesh.numTotal)
+    t0 = time.perf_counter()
+    res0, resl, used, _ = oracle.solve("dpcg", csr, a, su, fi, sor=1e-30, nsw=iters)
+    dt = time.perf_counter() - t0
+    return used / dt, dt, used
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU algorithm for the path.  The reference is
+    Fortran-only and cannot be compiled in this image (no Fortran compiler), so this is the
+    oracle port (kind "port"), serial src/ semantics on one host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    mesh, f = build_case(args.n)
+    csr = oracle.create_csr(mesh)
+    of = oracle.Fields(mesh, csr.nnz)
+    for k in ("u", "v", "w", "p", "den", "apu", "apv", "apw"):
+        getattr(of, k)[:] = f[k]
+    of.dPdxi[:] = oracle.grad_gauss(mesh, of.p, 1)
+    oo = oracle.calcp_opts(solver="dpcg", const_mflux=True, sor=SOR, nsw=NSW)
+    t0 = time.perf_counter()
+    oracle.calcp_assemble(mesh, csr, of, oo)
+    asm_s = time.perf_counter() - t0
+    per_step = args.ref_iters
+    fi = np.zeros(mesh.numTotal)
+    for _ in range(args.warmup):
+        oracle.solve("dpcg", csr, of.a, of.su, fi, sor=1e-30, nsw=2)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        fi[:] = 0.0
+        _, _, used, _ = oracle.solve("dpcg", csr, of.a, of.su, fi, sor=1e-30, nsw=per_step)
+        done += used
+    dt = time.perf_counter() - t0
+    v = done / dt
+    sample = f"{per_step} DPCG iterations per step on the {args.n}^3 p' system (oracle assembly {asm_s:.1f} s, untimed)"
+    print(json.dumps({
+        "impl": "reference", "metric": "pcorr_dpcg_iterations_per_second", "value": v, "unit": "iter/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak" if False else "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"synthetic {args.n}^3 hex pressure-correction (config 4), DPCG", "cells": mesh.numCells,
+                   "nnz": mesh.nnz},
+        "cpu_baseline": {"value": v, "unit": "iter/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_assemble_s": asm_s,
+    }))
+
+
+def run_ours(args):
+    import torch
+    from freecappuccino_b200 import lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    mesh, f = build_case(args.n)
+    ctx = lib.Context(local)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    for k, name in (("u", "USER0"), ("v", "USER1"), ("w", "USER2"), ("p", "USER3"), ("den", "DEN"), ("apu", "APU"),
+                    ("apv", "APV"), ("apw", "APW")):
+        ctx.upload(name, f[k])
+    ctx.upload("P", f["p"])
+    ctx.grad_gauss("P", "DPDXI", 1)          # incoming pressure gradient of the SIMPLE iteration
+    opts = lib.calcp_opts(solver="dpcg", const_mflux=True, sor=SOR, nsw=NSW, pRefCell=1, urf_p=0.3)
+    ctx.set_spmv_sampling(512)
+    stream = torch.cuda.ExternalStream(ctx.lib.fc_stream(ctx.h), device=torch.device("cuda", local))
+
+    def restore():  # device-to-device: the step always starts from the same fields
+        for s, d in (("USER0", "U"), ("USER1", "V"), ("USER2", "W"), ("USER3", "P")):
+            ctx.copy(s, d)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        ctx.synchronize()
+        torch.cuda.synchronize()
+
+    def step():
+        restore()
+        return ctx.calcp(opts)
+
+    for _ in range(args.warmup):
+        rep = step()
+    barrier()
+    clocks = ClockSampler(local)
+    l0 = ctx.timings().launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 0
+    spmv_ms, spmv_n, asm_ms, corr_ms, solve_ms = 0.0, 0, 0.0, 0.0, 0.0
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rep = step()
+        iters += rep.rep[0].iters
+        t = ctx.timings()
+        spmv_ms += t.spmv_ms * t.spmv_samples
+        spmv_n += t.spmv_samples
+        asm_ms += t.assemble_ms; corr_ms += t.correct_ms; solve_ms += t.solve_ms
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    launches = ctx.timings().launches - l0
+    clk = clocks.stop()
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms = float(tt.item())
+    value = iters / (dev_ms * 1e-3)
+
+    # ---- e2e: host buffers through fc_calcp_host, copies inside the timed region ----
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hb = {k: pin(f[k]) for k in ("u", "v", "w", "p", "apu", "apv", "apw")}
+    hpp = torch.zeros(mesh.numTotal, dtype=torch.float64).pin_memory()
+    hfl = torch.zeros(mesh.numInnerFaces, dtype=torch.float64).pin_memory()
+    src = {k: torch.from_numpy(np.ascontiguousarray(f[k])) for k in ("u", "v", "w", "p")}
+    e2e_steps = max(1, min(args.steps, 3))
+    h2d = 8 * (4 * mesh.numTotal + 3 * (mesh.numCells + mesh.npro))
+    d2h = 8 * (5 * mesh.numTotal + mesh.numInnerFaces)
+
+    def e2e_step():
+        for k in ("u", "v", "w", "p"):
+            hb[k].copy_(src[k])     # fresh host inputs (what calcuvw would have produced); untimed? no: timed
+        return ctx.calcp_host(opts, hb["u"].numpy(), hb["v"].numpy(), hb["w"].numpy(), hb["p"].numpy(), hpp.numpy(),
+                              hb["apu"].numpy(), hb["apv"].numpy(), hb["apw"].numpy(), hfl.numpy())
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_iters = 0
+    for _ in range(e2e_steps):
+        e2e_iters += e2e_step().rep[0].iters
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = e2e_iters / e2e_s
+
+    # ---- roofline of the dominant kernel: SpMV fused with p.Ap ----
+    ab = algorithmic_bytes(mesh)
+    peak, peak_src = measured_peak()
+    spmv_mean_ms = spmv_ms / max(spmv_n, 1)
+    achieved = ab["spmv"] / (spmv_mean_ms * 1e-3) / 1e9 if spmv_n else None
+    alone_ms = ctx.time_spmv("PP", "SCRATCH_T", 50)
+    roof = {"bound": "hbm", "kernel": "k_spmv<256,2304,DOT> (SpMV + p.Ap)", "achieved": achieved, "peak": peak,
+            "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+            "frac_of_nominal_8000": (achieved / 8000.0) if achieved else None, "traffic": None,
+            "algorithmic_bytes_per_launch": ab["spmv"], "mean_launch_ms": spmv_mean_ms, "launches_sampled": spmv_n,
+            "standalone_spmv_ms": alone_ms, "standalone_spmv_gbs": ab["spmv"] / (alone_ms * 1e-3) / 1e9}
+    iter_ms = solve_ms / max(iters, 1)
+    out = {
+        "metric": "pcorr_dpcg_iterations_per_second", "value": value, "unit": "iter/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic {args.n}^3 hex pressure-correction (config 4): calcp = assemble + DPCG to "
+                               f"rsm<1e-8 + correct", "cells": mesh.numCells, "nnz": mesh.nnz,
+                   "l2": "inputs_exceed_l2 (SpMV working set %.0f MB)" % (ab["spmv"] / 1e6), "solver": "dpcg",
+                   "sor": SOR},
+        "dpcg_iterations_per_step": iters / args.steps,
+        "simple_iter_ms": {"assemble": asm_ms / args.steps, "solve": solve_ms / args.steps,
+                           "correct": corr_ms / args.steps},
+        "dpcg_iter_ms": iter_ms,
+        "dpcg_iter_gbs": ab["dpcg_iter"] / (iter_ms * 1e-3) / 1e9 if iters else None,
+        "wall_s": wall,
+        "e2e": {"value": e2e_value, "unit": "iter/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roof,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        a = ctx.download("A")
+        su = ctx.download("SU")
+        v, dt, used = cpu_port_sample(mesh, a, su, args.cpu_iters)
+        out["cpu_baseline"] = {"value": v, "unit": "iter/s", "cores": 1, "kind": "port",
+                               "sample": f"{used} DPCG iterations of the same {args.n}^3 system (oracle, serial src "
+                                         f"semantics, {dt:.1f} s)"}
+    if rank == 0:
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=216, help="cells per edge of the synthetic hex box")
+    ap.add_argument("--cpu-iters", type=int, default=60, help="DPCG iterations of the cpu_baseline sample")
+    ap.add_argument("--ref-iters", type=int, default=20, help="DPCG iterations per step of the reference arm")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

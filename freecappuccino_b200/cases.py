@@ -65,3 +65,24 @@ def rel_l2(a, b):
     b = np.asarray(b, dtype=np.float64).ravel()
     den = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / den) if den > 0 else float(np.linalg.norm(a - b))
+
+
+def config4_fields(mesh):
+    """Synthetic pressure-correction case of SURVEY 8(d) config 4 (deterministic, no RNG):
+    u = sin cos cos, v = -cos sin cos, w = 0.1 sin sin sin (not divergence free, so su is non-trivial),
+    p = cos cos, den = 1, ap* = 1/(6 h (1 + 0.1 sin 2pi(x+y+z))), no-slip walls.  Works on a
+    partitioned mesh too: halo / boundary slots are filled from their own coordinates."""
+    n, nt, npc = mesh.numCells, mesh.numTotal, mesh.numCells + mesh.npro
+    two_pi = 2.0 * np.pi
+    x = np.zeros(nt); y = np.zeros(nt); z = np.zeros(nt)
+    x[:npc], y[:npc], z[:npc] = mesh.xc[:npc], mesh.yc[:npc], mesh.zc[:npc]
+    u = np.sin(two_pi * x) * np.cos(two_pi * y) * np.cos(two_pi * z)
+    v = -np.cos(two_pi * x) * np.sin(two_pi * y) * np.cos(two_pi * z)
+    w = 0.1 * np.sin(two_pi * x) * np.sin(two_pi * y) * np.sin(two_pi * z)
+    p = np.cos(two_pi * x) * np.cos(two_pi * y)
+    u[npc:] = v[npc:] = w[npc:] = 0.0
+    p[npc:] = 0.0
+    den = np.ones(nt)
+    h = 1.0 / round((mesh.gloCells or n) ** (1.0 / 3.0))
+    ap = 1.0 / (6.0 * h * (1.0 + 0.1 * np.sin(two_pi * (x[:npc] + y[:npc] + z[:npc]))))
+    return dict(u=u, v=v, w=w, p=p, den=den, apu=ap.copy(), apv=ap.copy(), apw=ap.copy())

@@ -64,7 +64,7 @@ int alloc_field(fc_context *ctx, int f, size_t count) {
 
 int alloc_fields(fc_context *ctx) {
   const size_t n = ctx->n, NT = ctx->NT, NP = (size_t)ctx->n + ctx->npro, F = ctx->F;
-  for (int f : {FC_U, FC_V, FC_W, FC_P, FC_PP, FC_DEN, FC_SCRATCH_T}) FC_CHECK(alloc_field(ctx, f, NT > NP ? NT : NP));
+  for (int f : {FC_U, FC_V, FC_W, FC_P, FC_PP, FC_DEN, FC_SCRATCH_T, FC_USER0, FC_USER1, FC_USER2, FC_USER3}) FC_CHECK(alloc_field(ctx, f, NT > NP ? NT : NP));
   FC_CHECK(alloc_field(ctx, FC_FLMASS, F));
   for (int f : {FC_APU, FC_APV, FC_APW}) FC_CHECK(alloc_field(ctx, f, NP));
   for (int f : {FC_DUDXI, FC_DVDXI, FC_DWDXI, FC_DPDXI}) FC_CHECK(alloc_field(ctx, f, 3 * n));
@@ -161,6 +161,7 @@ int fc_destroy(fc_context *ctx) {
   if (!ctx) return FC_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto &e : ctx->spmv_ev) cudaEventDestroy(e);
   if (ctx->comm) ncclCommDestroy(ctx->comm);
   free_all(ctx);
   for (auto &ev : ctx->ev)
@@ -286,6 +287,25 @@ int fc_fill(fc_context *ctx, int field, double value) {
   if (n == 0) return FC_OK;
   k_fill_double<<<fc_blocks(n, 256), 256, 0, ctx->stream>>>(ctx->field[field], value, n);
   FC_LAUNCH_CHECK();
+  return FC_OK;
+}
+
+int fc_copy(fc_context *ctx, int src_field, int dst_field) {
+  if (!ctx) return FC_ERR_ARG;
+  FC_CHECK(check_field(ctx, src_field, 0, "fc_copy"));
+  FC_CHECK(check_field(ctx, dst_field, 0, "fc_copy"));
+  const size_t n = ctx->field_n[src_field] < ctx->field_n[dst_field] ? ctx->field_n[src_field] : ctx->field_n[dst_field];
+  FC_CUDA(cudaMemcpyAsync(ctx->field[dst_field], ctx->field[src_field], sizeof(double) * n, cudaMemcpyDeviceToDevice,
+                          ctx->stream));
+  return FC_OK;
+}
+
+int fc_set_spmv_sampling(fc_context *ctx, int max_samples) {
+  if (!ctx || max_samples < 0 || max_samples > 4096) return FC_ERR_ARG;
+  for (auto &e : ctx->spmv_ev) cudaEventDestroy(e);
+  ctx->spmv_ev.assign((size_t)2 * max_samples, nullptr);
+  for (auto &e : ctx->spmv_ev) FC_CUDA(cudaEventCreate(&e));
+  ctx->spmv_sampled = 0;
   return FC_OK;
 }
 

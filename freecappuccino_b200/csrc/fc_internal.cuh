@@ -100,6 +100,8 @@ struct fc_context {
 
   // ---- timing ----
   cudaEvent_t ev[4] = {};
+  std::vector<cudaEvent_t> spmv_ev;     // 2 * max_samples events bracketing SpMV launches of a solve
+  int spmv_sampled = 0;
   fc_timings tm{};
 };
 

@@ -214,6 +214,7 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
   double *hist = nullptr;
   if (hist_host && o->nsw > 0) FC_CUDA(cudaMalloc((void **)&hist, sizeof(double) * (size_t)o->nsw));
 
+  ctx->spmv_sampled = 0;
   FC_CUDA(cudaEventRecord(ctx->ev[0], st));
   k_init_scalars<<<1, 1, 0, st>>>(ctx->sc, o->sor, o->small, o->nsw);
   FC_LAUNCH_CHECK();
@@ -312,5 +313,19 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
   float ms = 0.f;
   FC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   ctx->tm.solve_ms = ms;
+  // SpMV launches that ran after convergence returned immediately: only the first `iters`
+  // (x2 for bicgstab) samples are real work
+  int real = rep->iters * (solver == FC_BICGSTAB ? 2 : 1);
+  if (real > ctx->spmv_sampled) real = ctx->spmv_sampled;
+  if (real > 0) {
+    double sum = 0.0;
+    for (int i = 0; i < real; ++i) {
+      float t = 0.f;
+      FC_CUDA(cudaEventElapsedTime(&t, ctx->spmv_ev[2 * i], ctx->spmv_ev[2 * i + 1]));
+      sum += t;
+    }
+    ctx->tm.spmv_ms = sum / real;
+    ctx->tm.spmv_samples = real;
+  }
   return FC_OK;
 }

@@ -124,8 +124,15 @@ int fc_launch_spmv(fc_context *ctx, const double *a, const double *x, double *y)
 // y = A x fused with red[0] = w.y (and red[1] = y.y when `two`)
 int fc_launch_spmv_dots(fc_context *ctx, const double *a, const double *x, double *y, const double *w, int two,
                         int step) {
-  return two ? launch<MODE_DOT2>(ctx, a, x, y, nullptr, w, nullptr, step)
-             : launch<MODE_DOT>(ctx, a, x, y, nullptr, w, nullptr, step);
+  const bool sample = (size_t)(2 * ctx->spmv_sampled + 1) < ctx->spmv_ev.size();
+  if (sample) FC_CUDA(cudaEventRecord(ctx->spmv_ev[2 * ctx->spmv_sampled], ctx->stream));
+  FC_CHECK(two ? launch<MODE_DOT2>(ctx, a, x, y, nullptr, w, nullptr, step)
+               : launch<MODE_DOT>(ctx, a, x, y, nullptr, w, nullptr, step));
+  if (sample) {
+    FC_CUDA(cudaEventRecord(ctx->spmv_ev[2 * ctx->spmv_sampled + 1], ctx->stream));
+    ctx->spmv_sampled++;
+  }
+  return FC_OK;
 }
 
 int fc_launch_residual(fc_context *ctx, const double *a, const double *su, const double *x, double *res,

@@ -22,7 +22,7 @@ DPCG, ICCG, BICGSTAB = 0, 1, 2
 SOLVERS = {"dpcg": DPCG, "iccg": ICCG, "bicgstab": BICGSTAB}
 
 FIELDS = ("U", "V", "W", "P", "PP", "DEN", "FLMASS", "APU", "APV", "APW", "DUDXI", "DVDXI", "DWDXI", "DPDXI",
-          "A", "SU", "RES", "FMI", "FMO", "APR", "FMPRO", "SCRATCH_T")
+          "A", "SU", "RES", "FMI", "FMO", "APR", "FMPRO", "SCRATCH_T", "USER0", "USER1", "USER2", "USER3")
 F = {name: i for i, name in enumerate(FIELDS)}
 
 SMALL = float(np.float32(1e-20))   # `small` of module parameters is a default-real literal (modules_allocatable.f90:27)
@@ -37,7 +37,7 @@ SYMBOLS = (
     "fc_create_csr", "fc_field_size", "fc_upload", "fc_download", "fc_fill", "fc_synchronize", "fc_spmv",
     "fc_grad_gauss", "fc_grad_gauss_corrected", "fc_bpres", "fc_laplacian", "fc_solve", "fc_solve_host",
     "fc_solve_csr", "fc_calcp_assemble", "fc_calcp", "fc_calcp_host", "fc_exchange", "fc_global_sum",
-    "fc_get_timings", "fc_time_spmv", "fc_stream",
+    "fc_get_timings", "fc_time_spmv", "fc_stream", "fc_copy", "fc_set_spmv_sampling",
 )
 
 
@@ -75,7 +75,7 @@ class CalcpReport(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("solve_ms", C.c_double), ("assemble_ms", C.c_double), ("correct_ms", C.c_double),
-                ("spmv_ms", C.c_double), ("launches", C.c_longlong)]
+                ("spmv_ms", C.c_double), ("spmv_samples", C.c_int), ("pad_", C.c_int), ("launches", C.c_longlong)]
 
 
 class FcError(RuntimeError):
@@ -241,6 +241,12 @@ class Context:
 
     def fill(self, name: str, value: float):
         self._ck(self.lib.fc_fill(self.h, F[name], C.c_double(value)))
+
+    def copy(self, src: str, dst: str):
+        self._ck(self.lib.fc_copy(self.h, F[src], F[dst]))
+
+    def set_spmv_sampling(self, max_samples: int):
+        self._ck(self.lib.fc_set_spmv_sampling(self.h, max_samples))
 
     def synchronize(self):
         self._ck(self.lib.fc_synchronize(self.h))

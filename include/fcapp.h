@@ -52,6 +52,7 @@ enum {
   FC_FMI, FC_FMO,                                     /* ninl, nout         */
   FC_APR, FC_FMPRO,                                   /* npro               */
   FC_SCRATCH_T,                                       /* numTotal (user vec)*/
+  FC_USER0, FC_USER1, FC_USER2, FC_USER3,             /* numTotal, caller's */
   FC_NUM_FIELDS
 };
 
@@ -108,6 +109,7 @@ int fc_field_size(const fc_context *ctx, int field, size_t *n);
 int fc_upload(fc_context *ctx, int field, const double *host, size_t n);
 int fc_download(fc_context *ctx, int field, double *host, size_t n);
 int fc_fill(fc_context *ctx, int field, double value);
+int fc_copy(fc_context *ctx, int src_field, int dst_field); /* device-to-device, min of the two sizes */
 int fc_synchronize(fc_context *ctx);
 
 /* ---- operators (device-resident fields) -------------------------------- */
@@ -210,9 +212,15 @@ typedef struct {
   double solve_ms;     /* Krylov loop of the last solve                       */
   double assemble_ms;  /* gradients + face loop + row gather of last calcp    */
   double correct_ms;   /* post-solve corrections of last calcp                */
-  double spmv_ms;      /* mean SpMV launch duration if spmv timing was on     */
+  double spmv_ms;      /* mean duration of the SpMV(+dot) launches sampled    */
+                       /* inside the last solve (fc_set_spmv_sampling)        */
+  int spmv_samples;    /* how many launches that mean is over                 */
+  int pad_;
   long long launches;  /* kernels launched by the library since creation      */
 } fc_timings;
+/* Bracket up to `max_samples` SpMV launches of every following solve with CUDA
+ * events on the library stream (0 switches it off).                          */
+int fc_set_spmv_sampling(fc_context *ctx, int max_samples);
 int fc_get_timings(const fc_context *ctx, fc_timings *t);
 /* Times `reps` back-to-back launches of the SpMV kernel (y = A x) with CUDA
  * events on the library stream; returns the mean in ms.                     */

@@ -250,7 +250,7 @@ def test_reference_golden_5x5_through_fc_solve_csr(fc):
             assert f"{rep.res0:10.3E}".strip() == g["res0"]
             assert abs(rep.iters - len(g["iters"])) <= 1
             for (it, resl_s, _), resl in zip(g["iters"], hist):
-                if float(resl_s) > 1e-9:
+                if float(resl_s) > 1e-6 * float(g["res0"]):  # below that the printed history is round-off
                     assert resl == pytest.approx(float(resl_s), rel=2e-3), (name, it)
         assert [f"{v:5.2f}".strip() for v in x] == g["sol"], name
         assert np.allclose(x, xo, rtol=1e-12, atol=1e-13)
