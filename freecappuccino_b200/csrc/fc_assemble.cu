@@ -23,6 +23,8 @@ struct geom_t {
   const double *xc, *yc, *zc, *vol;
   const double *arx, *ary, *arz, *xf, *yf, *zf, *facint;
   int n, F;
+  int npro, pface0;       // processor faces: face = pface0 + i, halo cell = n + i (src-parallel)
+  const double *fpro;
 };
 
 struct c2f_t {
@@ -37,7 +39,7 @@ struct slots_t {  // 0-based first slot / first face / count per boundary kind: 
 
 inline geom_t geom_of(const fc_context *ctx) {
   return geom_t{ctx->owner, ctx->neigh, ctx->xc, ctx->yc, ctx->zc, ctx->vol, ctx->arx, ctx->ary, ctx->arz,
-                ctx->xf, ctx->yf, ctx->zf, ctx->facint, ctx->n, ctx->F};
+                ctx->xf, ctx->yf, ctx->zf, ctx->facint, ctx->n, ctx->F, ctx->npro, ctx->m.iProcFacesStart, ctx->fpro};
 }
 inline c2f_t c2f_of(const fc_context *ctx) { return c2f_t{ctx->c2f_off, ctx->c2f_face, ctx->c2f_other, ctx->c2f_pos}; }
 inline slots_t slots_of(const fc_context *ctx) {
@@ -67,10 +69,10 @@ k_grad_pass(geom_t g, c2f_t m, const double *__restrict__ phi, const double *__r
     const int f = fe & 0x7fffffff;
     const int o = m.other[q];
     const double sx = g.arx[f], sy = g.ary[f], sz = g.arz[f];
-    if (f < g.F) {
+    if (f < g.F || o < g.n + g.npro) {  // inner face, or processor face (src-parallel/grad_gauss.f90:68-75)
       const bool nb = fe < 0;
       const int ijp = nb ? o : c, ijn = nb ? c : o;
-      const double fxn = g.facint[f], fxp = 1.0 - fxn;
+      const double fxn = (f < g.F) ? g.facint[f] : g.fpro[o - g.n], fxp = 1.0 - fxn;
       double fie = phi[ijp] * fxp + phi[ijn] * fxn;
       if (HAS_OLD) {
         const double xi = g.xc[ijp] * fxp + g.xc[ijn] * fxn;
@@ -190,13 +192,37 @@ k_calcp_faces(geom_t g, flow_t f, double *__restrict__ coef, double *__restrict_
 }
 
 // fluxmc (facefluxmass.f90:520-607): non-orthogonal corrector flux; flmass += fmcor (calcp :195-205)
+// facefluxlaplacian (fvm_laplacian.f90:171-221)
 __global__ void __launch_bounds__(256)
-k_fluxmc_faces(geom_t g, flow_t f, double *__restrict__ fmcor_out, double *__restrict__ flmass) {
+k_laplacian_faces(geom_t g, const double *__restrict__ mu, double *__restrict__ coef) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.F) return;
   const int ijp = g.owner[i], ijn = g.neigh[i];
-  const double xf = g.xf[i], yf = g.yf[i], zf = g.zf[i], arx = g.arx[i], ary = g.ary[i], arz = g.arz[i];
+  const double arx = g.arx[i], ary = g.ary[i], arz = g.arz[i];
   const double fxn = g.facint[i], fxp = 1.0 - fxn;
+  const double xpn = g.xc[ijn] - g.xc[ijp];
+  const double ypn = g.yc[ijn] - g.yc[ijp];
+  const double zpn = g.zc[ijn] - g.zc[ijp];
+  const double smdpn = (arx * arx + ary * ary + arz * arz) / (arx * xpn + ary * ypn + arz * zpn);
+  coef[i] = (fxp * mu[ijp] + fxn * mu[ijn]) * smdpn;
+}
+
+// processor-boundary faces (src-parallel/calcp :107-128): facefluxmass2 with the halo cell as neighbour
+__global__ void __launch_bounds__(256)
+k_calcp_proc_faces(geom_t g, flow_t f, double *__restrict__ apr, double *__restrict__ fmpro) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.npro) return;
+  const int fc = g.pface0 + i;
+  double cap, fl;
+  facefluxmass<1>(g, f, g.owner[fc], g.n + i, g.xf[fc], g.yf[fc], g.zf[fc], g.arx[fc], g.ary[fc], g.arz[fc], g.fpro[i],
+                  cap, fl);
+  apr[i] = cap;
+  fmpro[i] = fl;
+}
+
+__device__ __forceinline__ double fluxmc(const geom_t &g, const flow_t &f, int ijp, int ijn, int fc, double lambda) {
+  const double xf = g.xf[fc], yf = g.yf[fc], zf = g.zf[fc], arx = g.arx[fc], ary = g.ary[fc], arz = g.arz[fc];
+  const double fxn = lambda, fxp = 1.0 - fxn;
   const double xpn = g.xc[ijn] - g.xc[ijp];
   const double ypn = g.yc[ijn] - g.yc[ijp];
   const double zpn = g.zc[ijn] - g.zc[ijp];
@@ -213,27 +239,48 @@ k_fluxmc_faces(geom_t g, flow_t f, double *__restrict__ fmcor_out, double *__res
   xep = xep - g.xc[ijn]; yep = yep - g.yc[ijn]; zep = zep - g.zc[ijn];
   const double rapr = (f.apu[ijp] * f.den[ijp] * g.vol[ijp] * fxp + f.apu[ijn] * f.den[ijn] * g.vol[ijn] * fxn);
   const double *dP = f.dP;
-  const double fmcor = rapr * are *
-                       ((G3(dP, 0, ijn) * xep - G3(dP, 0, ijp) * xpp) + (G3(dP, 1, ijn) * yep - G3(dP, 1, ijp) * ypp) +
-                        (G3(dP, 2, ijn) * zep - G3(dP, 2, ijp) * zpp)) *
-                       dppnnr;
+  return rapr * are *
+         ((G3(dP, 0, ijn) * xep - G3(dP, 0, ijp) * xpp) + (G3(dP, 1, ijn) * yep - G3(dP, 1, ijp) * ypp) +
+          (G3(dP, 2, ijn) * zep - G3(dP, 2, ijp) * zpp)) *
+         dppnnr;
+}
+
+__global__ void __launch_bounds__(256)
+k_fluxmc_faces(geom_t g, flow_t f, double *__restrict__ fmcor_out, double *__restrict__ flmass) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.F) return;
+  const double fmcor = fluxmc(g, f, g.owner[i], g.neigh[i], i, g.facint[i]);
   fmcor_out[i] = fmcor;
   flmass[i] = flmass[i] + fmcor;
 }
 
-// facefluxlaplacian (fvm_laplacian.f90:171-221)
-__global__ void __launch_bounds__(256)
-k_laplacian_faces(geom_t g, const double *__restrict__ mu, double *__restrict__ coef) {
+__global__ void k_fluxmc_proc_faces(geom_t g, flow_t f, double *__restrict__ fmcor_out, double *__restrict__ fmpro) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.F) return;
-  const int ijp = g.owner[i], ijn = g.neigh[i];
-  const double arx = g.arx[i], ary = g.ary[i], arz = g.arz[i];
-  const double fxn = g.facint[i], fxp = 1.0 - fxn;
+  if (i >= g.npro) return;
+  const int fc = g.pface0 + i;
+  const double fmcor = fluxmc(g, f, g.owner[fc], g.n + i, fc, g.fpro[i]);
+  fmcor_out[i] = fmcor;
+  fmpro[i] = fmpro[i] + fmcor;
+}
+
+__global__ void k_laplacian_proc_faces(geom_t g, const double *__restrict__ mu, double *__restrict__ apr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.npro) return;
+  const int fc = g.pface0 + i, ijp = g.owner[fc], ijn = g.n + i;
+  const double arx = g.arx[fc], ary = g.ary[fc], arz = g.arz[fc];
+  const double fxn = g.fpro[i], fxp = 1.0 - fxn;
   const double xpn = g.xc[ijn] - g.xc[ijp];
   const double ypn = g.yc[ijn] - g.yc[ijp];
   const double zpn = g.zc[ijn] - g.zc[ijp];
   const double smdpn = (arx * arx + ary * ary + arz * arz) / (arx * xpn + ary * ypn + arz * zpn);
-  coef[i] = (fxp * mu[ijp] + fxn * mu[ijn]) * smdpn;
+  apr[i] = (fxp * mu[ijp] + fxn * mu[ijn]) * smdpn;
+}
+
+// fmpro(i) += apr(i) * (pp(halo) - pp(owner))   (src-parallel/calcp :200-208)
+__global__ void k_fmpro_correct(geom_t g, const double *__restrict__ apr, const double *__restrict__ pp, double *fmpro) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.npro) return;
+  fmpro[i] = fmpro[i] + apr[i] * (pp[g.n + i] - pp[g.owner[g.pface0 + i]]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -245,7 +292,8 @@ enum { ROWS_CALCP = 0, ROWS_LAPLACIAN = 1, ROWS_SU_ONLY = 2 };
 template <int KIND>
 __global__ void __launch_bounds__(256)
 k_rows_gather(geom_t g, c2f_t m, slots_t sl, const int *__restrict__ diag, const double *__restrict__ coef,
-              const double *__restrict__ flux, const double *__restrict__ fmi, const double *__restrict__ fmo,
+              const double *__restrict__ flux, const double *__restrict__ apr, const double *__restrict__ fpr,
+              const double *__restrict__ fmi, const double *__restrict__ fmo,
               int mass_bc, const double *__restrict__ mu, const double *__restrict__ phi, double *__restrict__ a,
               double *__restrict__ su) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,6 +314,10 @@ k_rows_gather(geom_t g, c2f_t m, slots_t sl, const int *__restrict__ diag, const
         const double fl = flux[f];
         s = (fe < 0) ? s + fl : s - fl;   // su(owner) -= flux ; su(neighbour) += flux
       }
+    } else if (m.other[q] < g.n + g.npro) {   // processor face: coupling stays outside the CSR (apr)
+      const int i = m.other[q] - g.n;
+      if (KIND != ROWS_SU_ONLY) d = d - apr[i];
+      if (KIND != ROWS_LAPLACIAN) s = s - fpr[i];
     } else if (KIND == ROWS_CALCP) {
       const int o = m.other[q];
       if (mass_bc) {
@@ -302,10 +354,13 @@ __global__ void k_outlet_extrapolate(geom_t g, slots_t sl, double *u, double *v,
 }
 
 // flowo = sum(fmo) in the reference's sequential order (one thread; outlet patches are O(boundary))
-__global__ void k_outlet_factor(int nout, const double *__restrict__ fmo, double flomas, double small, double *fac) {
+__global__ void k_outlet_sum(int nout, const double *__restrict__ fmo, fc_scalars *sc) {
   double flowo = 0.0;
   for (int i = 0; i < nout; ++i) flowo = flowo + fmo[i];
-  *fac = flomas / (flowo + small);
+  sc->red[0] = flowo;
+}
+__global__ void k_outlet_factor(const fc_scalars *sc, double flomas, double small, double *fac) {
+  *fac = flomas / (sc->red[0] + small);
 }
 
 __global__ void k_outlet_scale(slots_t sl, double *u, double *v, double *w, double *fmo,
@@ -376,8 +431,9 @@ __global__ void k_mean(fc_scalars *sc, double gloCells, double *dst) { *dst = sc
 // continuityErrors.h: res = net flux per cell -- including its flmass(ijp) (owner CELL id used
 // as a face index, :18-19) -- then sum|res| and sum res.  Report only.
 __global__ void __launch_bounds__(FC_RED_BLOCK)
-k_continuity(geom_t g, c2f_t m, slots_t sl, const double *__restrict__ flmass, const double *__restrict__ fmi,
-             const double *__restrict__ fmo, double *res, double *partials, fc_scalars *sc) {
+k_continuity(geom_t g, c2f_t m, slots_t sl, const double *__restrict__ flmass, const double *__restrict__ fmpro,
+             const double *__restrict__ fmi, const double *__restrict__ fmo, double *res, double *partials,
+             fc_scalars *sc) {
   __shared__ double s_red[64];
   double a0 = 0.0, a1 = 0.0;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.n; c += gridDim.x * blockDim.x) {
@@ -390,7 +446,8 @@ k_continuity(geom_t g, c2f_t m, slots_t sl, const double *__restrict__ flmass, c
         const int own = (fe < 0) ? o : c;
         const double fl = flmass[own < g.F ? own : g.F - 1];
         r = (fe < 0) ? r + fl : r - fl;
-      } else if (o >= sl.slot[0] && o < sl.slot[0] + sl.count[0]) r = r - fmi[o - sl.slot[0]];
+      } else if (o < g.n + g.npro) r = r - fmpro[o - g.n];
+      else if (o >= sl.slot[0] && o < sl.slot[0] + sl.count[0]) r = r - fmi[o - sl.slot[0]];
       else if (o >= sl.slot[1] && o < sl.slot[1] + sl.count[1]) r = r - fmo[o - sl.slot[1]];
     }
     res[c] = r;
@@ -399,8 +456,8 @@ k_continuity(geom_t g, c2f_t m, slots_t sl, const double *__restrict__ flmass, c
   }
   double v[2] = {a0, a1};
   if (fc_grid_sum<2>(v, partials, &sc->ticket[2], s_red)) {
-    sc->aux[0] = v[0];
-    sc->aux[1] = v[1];
+    sc->red[0] = v[0];
+    sc->red[1] = v[1];
   }
 }
 
@@ -427,16 +484,25 @@ flow_t flow_of(fc_context *ctx) {
                 ctx->field[FC_APU], ctx->field[FC_APV], ctx->field[FC_APW]};
 }
 
-int outlet_extrapolate_and_scale(fc_context *ctx, double flomas, double small) {
+// `global`: adjustMassFlow sums flowo over the ranks (src-parallel/adjustMassFlow.f90:49),
+// correctBoundaryConditionsVelocity does not
+int outlet_extrapolate_and_scale(fc_context *ctx, double flomas, double small, bool global) {
   const slots_t sl = slots_of(ctx);
   const int nout = sl.count[1];
-  if (nout == 0) return FC_OK;
-  const int B = 256, G = fc_blocks(nout, B);
+  const bool comm = global && ctx->nranks > 1;
+  if (nout == 0 && !comm) return FC_OK;
+  const int B = 256, G = fc_blocks(nout > 0 ? nout : 1, B);
   double *fac = &ctx->sc->aux[2];
-  k_outlet_extrapolate<<<G, B, 0, ctx->stream>>>(geom_of(ctx), sl, ctx->field[FC_U], ctx->field[FC_V],
-                                                 ctx->field[FC_W], ctx->field[FC_DEN], ctx->field[FC_FMO]);
+  if (nout > 0) {
+    k_outlet_extrapolate<<<G, B, 0, ctx->stream>>>(geom_of(ctx), sl, ctx->field[FC_U], ctx->field[FC_V],
+                                                   ctx->field[FC_W], ctx->field[FC_DEN], ctx->field[FC_FMO]);
+    FC_LAUNCH_CHECK();
+  }
+  k_outlet_sum<<<1, 1, 0, ctx->stream>>>(nout, ctx->field[FC_FMO], ctx->sc);
   FC_LAUNCH_CHECK();
-  k_outlet_factor<<<1, 1, 0, ctx->stream>>>(nout, ctx->field[FC_FMO], flomas, small, fac);
+  if (comm) FC_CHECK(fc_allreduce_scalars(ctx, ctx->sc->red, 1));
+  if (nout == 0) return FC_OK;
+  k_outlet_factor<<<1, 1, 0, ctx->stream>>>(ctx->sc, flomas, small, fac);
   FC_LAUNCH_CHECK();
   k_outlet_scale<<<G, B, 0, ctx->stream>>>(sl, ctx->field[FC_U], ctx->field[FC_V], ctx->field[FC_W],
                                            ctx->field[FC_FMO], fac);
@@ -452,25 +518,38 @@ static int need_mesh(fc_context *ctx, const char *who) {
   return FC_OK;
 }
 
-int fc_grad_gauss_dev(fc_context *ctx, const double *phi, double *grad, int nigrad) {
+// grad(phi,dPhidxi): src-parallel/gradients.f90:95-160 brackets the Gauss passes with exchange(phi)
+// and the exchange of the three gradient components (one packed NCCL exchange here).  For
+// nigrad > 1 the previous-pass gradient is exchanged too (the reference indexes a numCells-sized
+// copy with halo cells there, i.e. out of bounds).
+int fc_grad_gauss_dev(fc_context *ctx, double *phi, double *grad, int nigrad) {
   FC_CHECK(need_mesh(ctx, "fc_grad_gauss"));
   if (nigrad < 1) FC_FAIL(FC_ERR_ARG, "fc_grad_gauss: nigrad < 1");
+  if (ctx->npro > 0) FC_CHECK(fc_halo_exchange(ctx, phi));
   for (int lc = 1; lc <= nigrad; ++lc) {
     if (lc == 1) FC_CHECK(grad_pass(ctx, phi, nullptr, grad));
     else {
-      FC_CUDA(cudaMemcpyAsync(ctx->gtmp, grad, sizeof(double) * 3 * (size_t)ctx->n, cudaMemcpyDeviceToDevice,
+      if (ctx->npro > 0) FC_CHECK(fc_halo_exchange3(ctx, grad));
+      FC_CUDA(cudaMemcpyAsync(ctx->gtmp, grad, sizeof(double) * 3 * (size_t)ctx->NP, cudaMemcpyDeviceToDevice,
                               ctx->stream));
       FC_CHECK(grad_pass(ctx, phi, ctx->gtmp, grad));
     }
   }
+  if (ctx->npro > 0) FC_CHECK(fc_halo_exchange3(ctx, grad));
   return FC_OK;
 }
 
-int fc_grad_gauss_corrected_dev(fc_context *ctx, const double *phi, double *grad, int zero_seed) {
+int fc_grad_gauss_corrected_dev(fc_context *ctx, double *phi, double *grad, int zero_seed) {
   FC_CHECK(need_mesh(ctx, "fc_grad_gauss_corrected"));
-  if (zero_seed) return grad_pass(ctx, phi, nullptr, grad);  // seed 0: the correction terms vanish identically
-  FC_CUDA(cudaMemcpyAsync(ctx->gtmp, grad, sizeof(double) * 3 * (size_t)ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
-  return grad_pass(ctx, phi, ctx->gtmp, grad);
+  if (ctx->npro > 0) FC_CHECK(fc_halo_exchange(ctx, phi));
+  if (zero_seed) FC_CHECK(grad_pass(ctx, phi, nullptr, grad));  // seed 0: the correction terms vanish identically
+  else {
+    FC_CUDA(cudaMemcpyAsync(ctx->gtmp, grad, sizeof(double) * 3 * (size_t)ctx->NP, cudaMemcpyDeviceToDevice,
+                            ctx->stream));
+    FC_CHECK(grad_pass(ctx, phi, ctx->gtmp, grad));
+  }
+  if (ctx->npro > 0) FC_CHECK(fc_halo_exchange3(ctx, grad));
+  return FC_OK;
 }
 
 int fc_bpres_dev(fc_context *ctx, double *p, const double *dPdxi, int istage) {
@@ -484,17 +563,22 @@ int fc_bpres_dev(fc_context *ctx, double *p, const double *dPdxi, int istage) {
   return FC_OK;
 }
 
-int fc_laplacian_dev(fc_context *ctx, const double *mu, const double *phi) {
+int fc_laplacian_dev(fc_context *ctx, double *mu, const double *phi) {
   FC_CHECK(need_mesh(ctx, "fc_laplacian"));
   const int B = 256;
+  if (ctx->npro > 0) {  // src-parallel/fvm_laplacian.f90:36, :93-114
+    FC_CHECK(fc_halo_exchange(ctx, mu));
+    k_laplacian_proc_faces<<<fc_blocks(ctx->npro, B), B, 0, ctx->stream>>>(geom_of(ctx), mu, ctx->field[FC_APR]);
+    FC_LAUNCH_CHECK();
+  }
   if (ctx->csr_dup) FC_CUDA(cudaMemsetAsync(ctx->field[FC_A], 0, sizeof(double) * (size_t)ctx->nnz, ctx->stream));
   if (ctx->F > 0) {
     k_laplacian_faces<<<fc_blocks(ctx->F, B), B, 0, ctx->stream>>>(geom_of(ctx), mu, ctx->coef);
     FC_LAUNCH_CHECK();
   }
   k_rows_gather<ROWS_LAPLACIAN><<<fc_blocks(ctx->n, B), B, 0, ctx->stream>>>(
-      geom_of(ctx), c2f_of(ctx), slots_of(ctx), ctx->diag, ctx->coef, nullptr, nullptr, nullptr, 0, mu, phi,
-      ctx->field[FC_A], ctx->field[FC_SU]);
+      geom_of(ctx), c2f_of(ctx), slots_of(ctx), ctx->diag, ctx->coef, nullptr, ctx->field[FC_APR], nullptr, nullptr,
+      nullptr, 0, mu, phi, ctx->field[FC_A], ctx->field[FC_SU]);
   FC_LAUNCH_CHECK();
   return FC_OK;
 }
@@ -518,10 +602,16 @@ int fc_calcp_assemble_dev(fc_context *ctx, const fc_calcp_opts *o) {
       k_calcp_faces<2><<<G, B, 0, ctx->stream>>>(geom_of(ctx), flow_of(ctx), ctx->coef, ctx->field[FC_FLMASS]);
     FC_LAUNCH_CHECK();
   }
-  if (!o->const_mflux) FC_CHECK(outlet_extrapolate_and_scale(ctx, o->flomas, o->sol.small));  // adjustMassFlow
+  if (ctx->npro > 0) {
+    k_calcp_proc_faces<<<fc_blocks(ctx->npro, B), B, 0, ctx->stream>>>(geom_of(ctx), flow_of(ctx), ctx->field[FC_APR],
+                                                                       ctx->field[FC_FMPRO]);
+    FC_LAUNCH_CHECK();
+  }
+  if (!o->const_mflux) FC_CHECK(outlet_extrapolate_and_scale(ctx, o->flomas, o->sol.small, true));  // adjustMassFlow
   k_rows_gather<ROWS_CALCP><<<fc_blocks(ctx->n, B), B, 0, ctx->stream>>>(
-      geom_of(ctx), c2f_of(ctx), slots_of(ctx), ctx->diag, ctx->coef, ctx->field[FC_FLMASS], ctx->field[FC_FMI],
-      ctx->field[FC_FMO], o->const_mflux ? 0 : 1, nullptr, nullptr, ctx->field[FC_A], ctx->field[FC_SU]);
+      geom_of(ctx), c2f_of(ctx), slots_of(ctx), ctx->diag, ctx->coef, ctx->field[FC_FLMASS], ctx->field[FC_APR],
+      ctx->field[FC_FMPRO], ctx->field[FC_FMI], ctx->field[FC_FMO], o->const_mflux ? 0 : 1, nullptr, nullptr,
+      ctx->field[FC_A], ctx->field[FC_SU]);
   FC_LAUNCH_CHECK();
   FC_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
   return FC_OK;
@@ -565,12 +655,17 @@ int fc_calcp_dev(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep) 
       k_flux_correct<<<fc_blocks(ctx->F, B), B, 0, st>>>(geom_of(ctx), ctx->coef, pp, ctx->field[FC_FLMASS]);
       FC_LAUNCH_CHECK();
     }
+    if (ctx->npro > 0) {
+      k_fmpro_correct<<<fc_blocks(ctx->npro, B), B, 0, st>>>(geom_of(ctx), ctx->field[FC_APR], pp,
+                                                             ctx->field[FC_FMPRO]);
+      FC_LAUNCH_CHECK();
+    }
     k_cell_correct<<<fc_blocks(n, B), B, 0, st>>>(geom_of(ctx), ctx->field[FC_U], ctx->field[FC_V], ctx->field[FC_W],
                                                   ctx->field[FC_P], pp, dP, ctx->field[FC_APU], ctx->field[FC_APV],
                                                   ctx->field[FC_APW], o->urf_p, ppref);
     FC_LAUNCH_CHECK();
     // correctBoundaryConditionsVelocity (:184)
-    FC_CHECK(outlet_extrapolate_and_scale(ctx, o->flomas, o->sol.small));
+    FC_CHECK(outlet_extrapolate_and_scale(ctx, o->flomas, o->sol.small, false));
     const slots_t sl = slots_of(ctx);
     if (sl.count[2] > 0) {
       k_symmetry_project<<<fc_blocks(sl.count[2], B), B, 0, st>>>(geom_of(ctx), sl, ctx->field[FC_U],
@@ -583,9 +678,14 @@ int fc_calcp_dev(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep) 
                                                            ctx->field[FC_FLMASS]);
         FC_LAUNCH_CHECK();
       }
+      if (ctx->npro > 0) {
+        k_fluxmc_proc_faces<<<fc_blocks(ctx->npro, B), B, 0, st>>>(geom_of(ctx), flow_of(ctx), ctx->facev + ctx->F,
+                                                                   ctx->field[FC_FMPRO]);
+        FC_LAUNCH_CHECK();
+      }
       k_rows_gather<ROWS_SU_ONLY><<<fc_blocks(n, B), B, 0, st>>>(
-          geom_of(ctx), c2f_of(ctx), sl, ctx->diag, ctx->coef, ctx->facev, nullptr, nullptr, 0, nullptr, nullptr,
-          ctx->field[FC_A], ctx->field[FC_SU]);
+          geom_of(ctx), c2f_of(ctx), sl, ctx->diag, ctx->coef, ctx->facev, nullptr, ctx->facev + ctx->F, nullptr,
+          nullptr, 0, nullptr, nullptr, ctx->field[FC_A], ctx->field[FC_SU]);
       FC_LAUNCH_CHECK();
     }
     FC_CUDA(cudaEventRecord(c1, st));
@@ -594,14 +694,17 @@ int fc_calcp_dev(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep) 
     FC_CUDA(cudaEventElapsedTime(&ms, c0, c1));
     corr_ms += ms;
   }
+  if (ctx->npro > 0)  // src-parallel/calcp :289-292
+    for (int fld : {FC_U, FC_V, FC_W, FC_P}) FC_CHECK(fc_halo_exchange(ctx, ctx->field[fld]));
   k_continuity<<<FC_RED_GRID, FC_RED_BLOCK, 0, st>>>(geom_of(ctx), c2f_of(ctx), slots_of(ctx), ctx->field[FC_FLMASS],
-                                                     ctx->field[FC_FMI], ctx->field[FC_FMO], ctx->field[FC_RES],
-                                                     ctx->partials, ctx->sc);
+                                                     ctx->field[FC_FMPRO], ctx->field[FC_FMI], ctx->field[FC_FMO],
+                                                     ctx->field[FC_RES], ctx->partials, ctx->sc);
   FC_LAUNCH_CHECK();
+  FC_CHECK(fc_allreduce_scalars(ctx, ctx->sc->red, 2));
   FC_CUDA(cudaMemcpyAsync(ctx->sc_host, ctx->sc, sizeof(fc_scalars), cudaMemcpyDeviceToHost, st));
   FC_CUDA(cudaStreamSynchronize(st));
-  rep->sumLocalContErr = ctx->sc_host->aux[0];
-  rep->globalContErr = ctx->sc_host->aux[1];
+  rep->sumLocalContErr = ctx->sc_host->red[0];
+  rep->globalContErr = ctx->sc_host->red[1];
   float ams = 0.f;
   FC_CUDA(cudaEventElapsedTime(&ams, ctx->ev[2], ctx->ev[3]));
   ctx->tm.assemble_ms = ams;

@@ -4,10 +4,10 @@
 // fc_create fails with FC_ERR_NODEVICE and nothing else can be called.
 #include "fc_internal.cuh"
 
-int fc_grad_gauss_dev(fc_context *ctx, const double *phi, double *grad, int nigrad);
-int fc_grad_gauss_corrected_dev(fc_context *ctx, const double *phi, double *grad, int zero_seed);
+int fc_grad_gauss_dev(fc_context *ctx, double *phi, double *grad, int nigrad);
+int fc_grad_gauss_corrected_dev(fc_context *ctx, double *phi, double *grad, int zero_seed);
 int fc_bpres_dev(fc_context *ctx, double *p, const double *dPdxi, int istage);
-int fc_laplacian_dev(fc_context *ctx, const double *mu, const double *phi);
+int fc_laplacian_dev(fc_context *ctx, double *mu, const double *phi);
 int fc_calcp_assemble_dev(fc_context *ctx, const fc_calcp_opts *o);
 int fc_calcp_dev(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep);
 
@@ -67,7 +67,7 @@ int alloc_fields(fc_context *ctx) {
   for (int f : {FC_U, FC_V, FC_W, FC_P, FC_PP, FC_DEN, FC_SCRATCH_T, FC_USER0, FC_USER1, FC_USER2, FC_USER3}) FC_CHECK(alloc_field(ctx, f, NT > NP ? NT : NP));
   FC_CHECK(alloc_field(ctx, FC_FLMASS, F));
   for (int f : {FC_APU, FC_APV, FC_APW}) FC_CHECK(alloc_field(ctx, f, NP));
-  for (int f : {FC_DUDXI, FC_DVDXI, FC_DWDXI, FC_DPDXI}) FC_CHECK(alloc_field(ctx, f, 3 * n));
+  for (int f : {FC_DUDXI, FC_DVDXI, FC_DWDXI, FC_DPDXI}) FC_CHECK(alloc_field(ctx, f, 3 * NP));  // (3,numPCells)
   FC_CHECK(alloc_field(ctx, FC_A, (size_t)ctx->nnz + 2));
   ctx->field_n[FC_A] = ctx->nnz;
   FC_CHECK(alloc_field(ctx, FC_SU, n));
@@ -81,7 +81,7 @@ int alloc_fields(fc_context *ctx) {
   FC_LAUNCH_CHECK();
   FC_CHECK(fc_dev_alloc(ctx, &ctx->coef, F + ctx->npro));
   FC_CHECK(fc_dev_alloc(ctx, &ctx->facev, (size_t)ctx->NF));
-  FC_CHECK(fc_dev_alloc(ctx, &ctx->gtmp, 3 * n));
+  FC_CHECK(fc_dev_alloc(ctx, &ctx->gtmp, 3 * NP));
   return FC_OK;
 }
 
@@ -222,7 +222,7 @@ int fc_set_mesh(fc_context *ctx, const fc_mesh_desc *m) {
     FC_CHECK(fc_dev_alloc(ctx, &ctx->bufind, (size_t)m->npro));
     FC_CUDA(cudaMemcpyAsync(ctx->bufind, ctx->owner + m->iProcFacesStart, sizeof(int) * (size_t)m->npro,
                             cudaMemcpyDeviceToDevice, ctx->stream));
-    FC_CHECK(fc_dev_alloc(ctx, &ctx->sendbuf, (size_t)m->npro));
+    FC_CHECK(fc_dev_alloc(ctx, &ctx->sendbuf, 3 * (size_t)m->npro));
   }
   // the descriptor's pointers are the caller's; keep only the scalars
   ctx->m.owner = ctx->m.neighbour = nullptr;
@@ -356,7 +356,7 @@ int fc_bpres(fc_context *ctx, int p_field, int istage) {
 
 int fc_laplacian(fc_context *ctx, int mu_field, int phi_field) {
   if (!ctx) return FC_ERR_ARG;
-  FC_CHECK(check_field(ctx, mu_field, (size_t)ctx->n, "fc_laplacian"));
+  FC_CHECK(check_field(ctx, mu_field, (size_t)ctx->NP, "fc_laplacian"));
   FC_CHECK(check_field(ctx, phi_field, (size_t)ctx->NT, "fc_laplacian"));
   return fc_laplacian_dev(ctx, ctx->field[mu_field], ctx->field[phi_field]);
 }

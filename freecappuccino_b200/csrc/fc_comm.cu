@@ -14,7 +14,31 @@ __global__ void k_pack(int npro, const int *__restrict__ bufind, const double *_
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < npro) buf[i] = phi[bufind[i]];
 }
+__global__ void k_pack3(int npro, const int *__restrict__ bufind, const double *__restrict__ g,
+                        double *__restrict__ buf) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 3 * npro) buf[t] = g[3 * (size_t)bufind[t / 3] + (t % 3)];
+}
 }  // namespace
+
+// exchange( dPhidxi(1,:) ), (2,:), (3,:) of src-parallel/gradients.f90:157-159 as ONE exchange: the
+// halo part of the interleaved (3,numPCells) array is contiguous, so the receive needs no unpack
+int fc_halo_exchange3(fc_context *ctx, double *grad) {
+  if (ctx->npro == 0) return FC_OK;
+  if (!ctx->comm) FC_FAIL(FC_ERR_ARG, "halo exchange on a partitioned mesh needs fc_comm_init");
+  k_pack3<<<fc_blocks(3 * (size_t)ctx->npro, 256), 256, 0, ctx->stream>>>(ctx->npro, ctx->bufind, grad, ctx->sendbuf);
+  FC_LAUNCH_CHECK();
+  FC_NCCL(ncclGroupStart());
+  for (size_t c = 0; c < ctx->nbr_rank.size(); ++c) {
+    const int off = ctx->nbr_off[c], len = ctx->nbr_off[c + 1] - off;
+    FC_NCCL(ncclSend(ctx->sendbuf + 3 * (size_t)off, 3 * (size_t)len, ncclDouble, ctx->nbr_rank[c], ctx->comm,
+                     ctx->stream));
+    FC_NCCL(ncclRecv(grad + 3 * ((size_t)ctx->n + off), 3 * (size_t)len, ncclDouble, ctx->nbr_rank[c], ctx->comm,
+                     ctx->stream));
+  }
+  FC_NCCL(ncclGroupEnd());
+  return FC_OK;
+}
 
 int fc_halo_exchange(fc_context *ctx, double *phi) {
   if (ctx->npro == 0) return FC_OK;

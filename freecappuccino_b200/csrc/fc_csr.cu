@@ -166,6 +166,26 @@ __global__ void k_c2f_sort(const int *__restrict__ off, int n, int F, int *face,
   }
 }
 
+// per-row list of processor faces (ascending i): the `apr` strip the SpMV adds after the CSR part
+// of a row (src-parallel/dpcg.f90:132-136)
+__global__ void k_strip_count(const int *__restrict__ off, const int *__restrict__ other, int n, int npro, int F,
+                              const int *__restrict__ face, int *cnt) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  int k = 0;
+  for (int q = off[c]; q < off[c + 1]; ++q)
+    if ((face[q] & 0x7fffffff) >= F && other[q] < n + npro) ++k;
+  cnt[c] = k;
+}
+__global__ void k_strip_fill(const int *__restrict__ off, const int *__restrict__ other, int n, int npro, int F,
+                             const int *__restrict__ face, const int *__restrict__ soff, int *sidx) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  int k = soff[c];
+  for (int q = off[c]; q < off[c + 1]; ++q)
+    if ((face[q] & 0x7fffffff) >= F && other[q] < n + npro) sidx[k++] = other[q] - n;
+}
+
 int exclusive_scan(fc_context *ctx, int *in, int *out, int count) {
   void *tmp = nullptr;
   size_t bytes = 0;
@@ -290,6 +310,18 @@ int fc_c2f_build(fc_context *ctx) {
   k_c2f_sort<<<fc_blocks(n, B), B, 0, ctx->stream>>>(ctx->c2f_off, n, F, ctx->c2f_face, ctx->c2f_other,
                                                      ctx->c2f_pos, ctx->has_csr ? ctx->ioffset : nullptr, ctx->ja);
   FC_LAUNCH_CHECK();
+  if (ctx->npro > 0) {
+    FC_CHECK(fc_dev_alloc(ctx, &ctx->strip_off, (size_t)n + 1));
+    FC_CHECK(fc_dev_alloc(ctx, &ctx->strip_idx, (size_t)ctx->npro));
+    FC_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)n + 1), ctx->stream));
+    k_strip_count<<<fc_blocks(n, B), B, 0, ctx->stream>>>(ctx->c2f_off, ctx->c2f_other, n, ctx->npro, F, ctx->c2f_face,
+                                                          cnt);
+    FC_LAUNCH_CHECK();
+    FC_CHECK(exclusive_scan(ctx, cnt, ctx->strip_off, n + 1));
+    k_strip_fill<<<fc_blocks(n, B), B, 0, ctx->stream>>>(ctx->c2f_off, ctx->c2f_other, n, ctx->npro, F, ctx->c2f_face,
+                                                         ctx->strip_off, ctx->strip_idx);
+    FC_LAUNCH_CHECK();
+  }
   FC_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(cnt);
   cudaFree(fill);

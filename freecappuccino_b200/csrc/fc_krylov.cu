@@ -218,8 +218,7 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
   FC_CUDA(cudaEventRecord(ctx->ev[0], st));
   k_init_scalars<<<1, 1, 0, st>>>(ctx->sc, o->sor, o->small, o->nsw);
   FC_LAUNCH_CHECK();
-  if (ctx->npro > 0) FC_CHECK(fc_halo_exchange(ctx, fi));
-  // res = su - A fi, res0 = sum|res|   (dpcg.f90:51-64)
+  // res = su - A fi, res0 = sum|res|   (dpcg.f90:51-64; the parallel twin uses fi's halo as it is)
   FC_CHECK(fc_launch_residual(ctx, a, su, fi, res, ctx->adiag));
   FC_CHECK(global_step(ctx, 1, STEP_RES0, nullptr));
   FC_CHECK(poll(ctx));

@@ -98,19 +98,20 @@ template <int MODE>
 int launch(fc_context *ctx, const double *a, const double *x, double *y, const double *su, const double *w,
            double *adiag, int step) {
   const int n = ctx->n;
-  strip_t st{nullptr, nullptr, nullptr, 0};
+  strip_t st{ctx->strip_off, ctx->strip_idx, ctx->field[FC_APR], n};
   const int nchunks = (n + 255) / 256;
   int grid = nchunks < FC_SMS * 8 ? nchunks : FC_SMS * 8;
   if (grid < 1) grid = 1;
   const int local = ctx->nranks == 1;
-  if (ctx->spmv_max_chunk <= 2304) {
-    k_spmv<256, 2304, MODE, false><<<grid, 256, 0, ctx->stream>>>(n, ctx->ioffset, ctx->ja, a, x, y, su, w, ctx->diag,
-                                                                  adiag, st, ctx->partials, ctx->sc, step, local);
-  } else {
-    if (grid > FC_SMS * 4) grid = FC_SMS * 4;
-    k_spmv<256, 5632, MODE, false><<<grid, 256, 0, ctx->stream>>>(n, ctx->ioffset, ctx->ja, a, x, y, su, w, ctx->diag,
-                                                                  adiag, st, ctx->partials, ctx->sc, step, local);
-  }
+  const bool strip = ctx->npro > 0;
+  const bool small_rows = ctx->spmv_max_chunk <= 2304;
+  if (!small_rows && grid > FC_SMS * 4) grid = FC_SMS * 4;
+#define FC_SPMV_LAUNCH(CAP, STRIP)                                                                              \
+  k_spmv<256, CAP, MODE, STRIP><<<grid, 256, 0, ctx->stream>>>(n, ctx->ioffset, ctx->ja, a, x, y, su, w, ctx->diag, \
+                                                               adiag, st, ctx->partials, ctx->sc, step, local)
+  if (small_rows) { if (strip) FC_SPMV_LAUNCH(2304, true); else FC_SPMV_LAUNCH(2304, false); }
+  else            { if (strip) FC_SPMV_LAUNCH(5632, true); else FC_SPMV_LAUNCH(5632, false); }
+#undef FC_SPMV_LAUNCH
   FC_LAUNCH_CHECK();
   return FC_OK;
 }

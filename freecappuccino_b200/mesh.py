@@ -59,6 +59,8 @@ class Mesh:
     neighbProcOffset: Optional[np.ndarray] = None  # [numConnections+1], 1-based like the reference
     gloCells: int = 0
     cell_global: Optional[np.ndarray] = None       # local cell -> global cell (0-based), partitioned only
+    halo_global: Optional[np.ndarray] = None       # processor face i -> global id of the remote cell
+    face_global: Optional[np.ndarray] = None       # local face -> global face (0-based)
     # O-C cuts (none of the BASELINE configs has them; carried for the oracle)
     noc: int = 0
     iOCFacesStart: int = 0
@@ -391,7 +393,7 @@ def slab_ranks(mesh_n: int, nranks: int) -> np.ndarray:
     return (np.arange(mesh_n, dtype=np.int64) * nranks) // mesh_n
 
 
-def partition(g: Mesh, cell_rank: np.ndarray, nranks: int) -> List[Mesh]:
+def partition(g: Mesh, cell_rank: np.ndarray, nranks: int, only: Optional[int] = None) -> List[Mesh]:
     """Split ``g`` by ``cell_rank`` into per-rank meshes laid out like an
     OpenFOAM decomposition read by src-parallel: faces = [inner | boundary
     patches in the global order | processor faces grouped by neighbour rank
@@ -405,7 +407,7 @@ def partition(g: Mesh, cell_rank: np.ndarray, nranks: int) -> List[Mesh]:
     r_own = cell_rank[own]
     r_nb = cell_rank[nb]
     out: List[Mesh] = []
-    for r in range(nranks):
+    for r in (range(nranks) if only is None else [only]):   # `only`: build just that rank's mesh
         cells = np.nonzero(cell_rank == r)[0]
         g2l = np.full(g.numCells, -1, dtype=np.int64)
         g2l[cells] = np.arange(cells.size)
@@ -460,5 +462,41 @@ def partition(g: Mesh, cell_rank: np.ndarray, nranks: int) -> List[Mesh]:
             facint=g.facint[fin].copy(), counts=counts, starts=starts,
             npro=npro, iProcFacesStart=fin.size + bfaces.size, fpro=fpro,
             neighbProcNo=nbr_ranks.astype(np.int32), neighbProcOffset=np.array(offs, dtype=np.int32),
-            gloCells=g.numCells, cell_global=cells))
+            gloCells=g.numCells, cell_global=cells, halo_global=rem_cell, face_global=allf))
     return out
+
+
+def scatter_total(g: Mesh, part: Mesh, arr: np.ndarray) -> np.ndarray:
+    """Global numTotal-sized field -> the rank's numTotal-sized field: own cells, halo slots
+    (value of the remote cell) and boundary slots."""
+    out = np.zeros(part.numTotal)
+    n = part.numCells
+    out[:n] = arr[part.cell_global]
+    out[n:n + part.npro] = arr[part.halo_global]
+    for kind in KINDS:
+        c = part.count(kind)
+        if c == 0:
+            continue
+        gf = part.face_global[part.faces_start(kind):part.faces_start(kind) + c]
+        out[part.slot_start(kind):part.slot_start(kind) + c] = arr[g.slot_start(kind) + (gf - g.faces_start(kind))]
+    return out
+
+
+def scatter_cells(g: Mesh, part: Mesh, arr: np.ndarray, width: int = 1) -> np.ndarray:
+    """Global per-cell field (numCells[, width]) -> the rank's numCells+npro field incl. halo copies."""
+    idx = np.concatenate([part.cell_global, part.halo_global]) if part.npro else part.cell_global
+    return np.ascontiguousarray(arr[idx])
+
+
+def gather_cells(g: Mesh, parts: List[Mesh], arrs: List[np.ndarray]) -> np.ndarray:
+    """Per-rank cell fields -> global cell field."""
+    first = np.asarray(arrs[0])
+    out = np.zeros((g.numCells,) + first.shape[1:])
+    for m, a in zip(parts, arrs):
+        out[m.cell_global] = np.asarray(a)[:m.numCells]
+    return out
+
+
+def scatter_faces(part: Mesh, arr: np.ndarray) -> np.ndarray:
+    """Global per-boundary-kind face list helper: values of a global per-face array at the rank's faces."""
+    return np.ascontiguousarray(arr[part.face_global])

@@ -376,7 +376,7 @@ static void gradco(const fco_mesh *g, int ijp, int ijn, double xfc, double yfc, 
 
 static void grad_pass(const fco_mesh *g, const double *u, const double *dfo, double *df) {
   const int n = g->numCells;
-  memset(df, 0, sizeof(double) * 3 * (size_t)n);
+  memset(df, 0, sizeof(double) * 3 * (size_t)(n + g->npro)); /* dudx(numPCells) in src-parallel */
   for (int i = 1; i <= g->numInnerFaces; ++i)
     gradco(g, A1(g->owner, i), A1(g->neighbour, i), A1(g->xf, i), A1(g->yf, i), A1(g->zf, i), A1(g->arx, i),
            A1(g->ary, i), A1(g->arz, i), A1(g->facint, i), u, dfo, df);
@@ -384,6 +384,12 @@ static void grad_pass(const fco_mesh *g, const double *u, const double *dfo, dou
     int iface = A1(g->ijlFace, i);
     gradco(g, A1(g->ijl, i), A1(g->ijr, i), A1(g->xf, iface), A1(g->yf, iface), A1(g->zf, iface),
            A1(g->arx, iface), A1(g->ary, iface), A1(g->arz, iface), A1(g->foc, i), u, dfo, df);
+  }
+  /* processor boundaries: src-parallel/grad_gauss.f90:68-75 (halo cell = iProcStart + i) */
+  for (int i = 1; i <= g->npro; ++i) {
+    int iface = g->iProcFacesStart + i;
+    gradco(g, A1(g->owner, iface), g->numCells + i, A1(g->xf, iface), A1(g->yf, iface), A1(g->zf, iface),
+           A1(g->arx, iface), A1(g->ary, iface), A1(g->arz, iface), A1(g->fpro, i), u, dfo, df);
   }
   /* boundary faces in the order inlet, outlet, symmetry, wall, prOutlet (:70-103) */
   const int cnt[5] = {g->ninl, g->nout, g->nsym, g->nwal, g->npru};
@@ -409,7 +415,7 @@ static void grad_pass(const fco_mesh *g, const double *u, const double *dfo, dou
 }
 
 void fco_grad_gauss(const fco_mesh *g, const double *u, int nigrad, double *dudxi) {
-  const size_t n3 = 3 * (size_t)g->numCells;
+  const size_t n3 = 3 * (size_t)(g->numCells + g->npro);
   double *dfo = (double *)calloc(n3, sizeof(double));
   for (int lc = 1; lc <= nigrad; ++lc) {
     grad_pass(g, u, dfo, dudxi);
@@ -419,7 +425,7 @@ void fco_grad_gauss(const fco_mesh *g, const double *u, int nigrad, double *dudx
 }
 
 void fco_grad_gauss_corrected(const fco_mesh *g, const double *u, double *dudxi) {
-  const size_t n3 = 3 * (size_t)g->numCells;
+  const size_t n3 = 3 * (size_t)(g->numCells + g->npro);
   double *dfo = (double *)malloc(sizeof(double) * n3);
   memcpy(dfo, dudxi, sizeof(double) * n3);
   grad_pass(g, u, dfo, dudxi);

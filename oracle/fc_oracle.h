@@ -127,6 +127,26 @@ void fco_fluxmc(const fco_mesh *g, const fco_fields *f, int ijp, int ijn,
                 double xf, double yf, double zf, double arx, double ary, double arz,
                 double lambda, double *fmcor);
 
+/* ---- src-parallel semantics: R ranks in lock step inside one process (fc_oracle_par.c) ---- */
+typedef struct {
+  fco_mesh g;
+  fco_csr m;
+  fco_fields f;                 /* gradients (3,numCells+npro), apu.. numCells+npro, u.. numTotal */
+  double *apr, *fmpro;          /* [npro] */
+  int numConnections;
+  const int *neighbProcNo;      /* 0-based ranks */
+  const int *neighbProcOffset;  /* 1-based, numConnections+1 entries */
+} fco_rank;
+
+void fco_par_exchange(fco_rank *R, int nr, double **phi, int stride);
+void fco_par_grad_gauss(fco_rank *R, int nr, double **phi, int nigrad, double **grad);
+void fco_par_grad_gauss_corrected(fco_rank *R, int nr, double **phi, double **grad);
+void fco_par_laplacian(fco_rank *R, int nr, double **mu, double **phi);
+int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver_opts *o, fco_report *rep,
+                  double *hist);
+void fco_par_calcp_assemble(fco_rank *R, int nr, const fco_calcp_opts *o);
+int fco_par_calcp(fco_rank *R, int nr, const fco_calcp_opts *o, fco_calcp_report *rep);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ TOL = float(np.float32(1e-13))        # dpcg.f90:37
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libfc_oracle.so")
-    src = [os.path.join(_HERE, f) for f in ("fc_oracle.c", "fc_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("fc_oracle.c", "fc_oracle_par.c", "fc_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libfc_oracle.so"])
     return so
@@ -189,8 +189,8 @@ def laplacian(mesh, csr: Csr, mu: np.ndarray, phi: np.ndarray, su: np.ndarray) -
 
 
 def grad_gauss(mesh, u: np.ndarray, nigrad: int = 1) -> np.ndarray:
-    """Returns dPhidxi as an [numCells, 3] C array == Fortran (3,numCells)."""
-    g = np.zeros((mesh.numCells, 3))
+    """Returns dPhidxi as an [numCells(+npro), 3] C array == Fortran (3,numPCells)."""
+    g = np.zeros((mesh.numCells + mesh.npro, 3))
     ms = mesh_struct(mesh)
     lib().fco_grad_gauss(C.byref(ms), _d(u), nigrad, _d(g))
     return g
@@ -221,7 +221,8 @@ class Fields:
         self.den = np.ones(nt)
         self.flmass = z(mesh.numInnerFaces)
         self.fmi, self.fmo, self.fmoc = z(max(mesh.count("inlet"), 1)), z(max(mesh.count("outlet"), 1)), z(max(mesh.noc, 1))
-        self.dUdxi, self.dVdxi, self.dWdxi, self.dPdxi = z((n, 3)), z((n, 3)), z((n, 3)), z((n, 3))
+        npc = n + mesh.npro   # dPhidxi(3,numPCells) in src-parallel
+        self.dUdxi, self.dVdxi, self.dWdxi, self.dPdxi = z((npc, 3)), z((npc, 3)), z((npc, 3)), z((npc, 3))
         self.apu, self.apv, self.apw = z(n + mesh.npro), z(n + mesh.npro), z(n + mesh.npro)
         self.a, self.su, self.res = z(nnz), z(n), z(n)
         self.al, self.ar = z(max(mesh.noc, 1)), z(max(mesh.noc, 1))

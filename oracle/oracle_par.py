@@ -1,0 +1,86 @@
+"""ctypes front-end of the lock-step multi-rank oracle (TEST INFRASTRUCTURE ONLY).
+
+src-parallel semantics (exchange.f90, global_sum_mpi.f90, the parallel twins of calcp / dpcg /
+iccg / bicgstab / grad_gauss / laplacian) with the R ranks advanced inside one process; used to
+check the NCCL path and the gloo tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import numpy as np
+
+from . import oracle as O
+
+
+class FcoRank(C.Structure):
+    _fields_ = [("g", O.FcoMesh), ("m", O.FcoCsr), ("f", O.FcoFields), ("apr", O.dp), ("fmpro", O.dp),
+                ("numConnections", C.c_int), ("neighbProcNo", O.ip), ("neighbProcOffset", O.ip)]
+
+
+class ParCase:
+    """Per-rank meshes (from freecappuccino_b200.mesh.partition) + CSR + fields."""
+
+    def __init__(self, meshes):
+        self.meshes = list(meshes)
+        self.nr = len(self.meshes)
+        self.csr = [O.create_csr(m) for m in self.meshes]
+        self.fields = [O.Fields(m, c.nnz) for m, c in zip(self.meshes, self.csr)]
+        self.apr = [np.zeros(max(m.npro, 1)) for m in self.meshes]
+        self.fmpro = [np.zeros(max(m.npro, 1)) for m in self.meshes]
+        self._keep = []
+        self.R = (FcoRank * self.nr)()
+        for r, m in enumerate(self.meshes):
+            ms = O.mesh_struct(m)
+            self._keep.append(ms)
+            nb = np.ascontiguousarray(m.neighbProcNo if m.neighbProcNo is not None else np.zeros(0), dtype=np.int32)
+            off = np.ascontiguousarray(m.neighbProcOffset if m.neighbProcOffset is not None else np.ones(1),
+                                       dtype=np.int32)
+            self._keep += [nb, off]
+            self.R[r].g = ms
+            self.R[r].m = self.csr[r].c()
+            self.R[r].f = self.fields[r].c()
+            self.R[r].apr = O._d(self.apr[r])
+            self.R[r].fmpro = O._d(self.fmpro[r])
+            self.R[r].numConnections = nb.size
+            self.R[r].neighbProcNo = O._i(nb)
+            self.R[r].neighbProcOffset = O._i(off)
+
+    def _ptrs(self, arrays: List[np.ndarray]):
+        p = (O.dp * self.nr)()
+        for r, a in enumerate(arrays):
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+            p[r] = a.ctypes.data_as(O.dp)
+        return p
+
+    def exchange(self, arrays: List[np.ndarray], stride: int = 1):
+        O.lib().fco_par_exchange(self.R, self.nr, self._ptrs(arrays), stride)
+
+    def grad_gauss(self, phis: List[np.ndarray], nigrad: int = 1) -> List[np.ndarray]:
+        out = [np.zeros((m.numCells + m.npro, 3)) for m in self.meshes]
+        O.lib().fco_par_grad_gauss(self.R, self.nr, self._ptrs(phis), nigrad, self._ptrs(out))
+        return out
+
+    def laplacian(self, mus: List[np.ndarray], phis: List[np.ndarray]):
+        """fills fields[r].a, apr[r]; updates fields[r].su."""
+        O.lib().fco_par_laplacian(self.R, self.nr, self._ptrs(mus), self._ptrs(phis))
+
+    def solve(self, name: str, fis: List[np.ndarray], sor: float, nsw: int, small: float = O.SMALL,
+              tol: float = O.TOL, history: bool = False):
+        o = O.FcoSolverOpts(sor, nsw, small, tol, 1)
+        rep = O.FcoReport()
+        hist = np.zeros(nsw) if history else None
+        rc = O.lib().fco_par_solve(self.R, self.nr, O.SOLVERS[name], self._ptrs(fis), C.byref(o), C.byref(rep),
+                                   O._d(hist))
+        assert rc == 0
+        return (rep, hist[:rep.iters]) if history else rep
+
+    def calcp_assemble(self, opts: O.FcoCalcpOpts):
+        O.lib().fco_par_calcp_assemble(self.R, self.nr, C.byref(opts))
+
+    def calcp(self, opts: O.FcoCalcpOpts) -> O.FcoCalcpReport:
+        rep = O.FcoCalcpReport()
+        rc = O.lib().fco_par_calcp(self.R, self.nr, C.byref(opts), C.byref(rep))
+        assert rc == 0
+        return rep

@@ -1,0 +1,119 @@
+"""Multi-GPU parity check, one process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/mgpu_check.py
+
+Every rank partitions the same seeded mesh, runs the pressure-correction path through the C ABI
+with NCCL halo exchange / all-reduce, and rank 0 compares the gathered fields with the lock-step
+multi-rank oracle (src-parallel semantics) on the same partition.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from freecappuccino_b200 import cases, lib, mesh as M, parallel  # noqa: E402
+
+
+def scatter_case(g, part, f, fmi, gp):
+    out = {k: M.scatter_total(g, part, f[k]) for k in ("u", "v", "w", "p", "den")}
+    out.update({k: M.scatter_cells(g, part, f[k]) for k in ("apu", "apv", "apw")})
+    out["dPdxi"] = M.scatter_cells(g, part, gp)
+    c = part.count("inlet")
+    out["fmi"] = np.zeros(0)
+    if c:
+        gf = part.face_global[part.faces_start("inlet"):part.faces_start("inlet") + c]
+        out["fmi"] = np.ascontiguousarray(fmi[gf - g.faces_start("inlet")])
+    return out
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from oracle import oracle as O, oracle_par as OP
+
+    failures = []
+    for mesh_name, g in (("hex_mixed", cases.hex_case(12, 9, 4 * world, kinds=("inlet", "outlet", "wall", "symmetry", "wall", "wall"))),
+                         ("skew", cases.skew_case(9, 8, 3 * world + 2))):
+        f = cases.flow_fields(g)
+        fmi, flomas = cases.inlet_fluxes(g, f)
+        gp = O.grad_gauss(g, f["p"], 1)
+        cell_rank = M.slab_ranks(g.numCells, world)
+        parts = M.partition(g, cell_rank, world)
+        part = parts[rank]
+        mine = scatter_case(g, part, f, fmi, gp)
+        for solver, npcor, lsq, nigrad in (("dpcg", 1, False, 1), ("iccg", 2, True, 2), ("bicgstab", 1, False, 1)):
+            kw = dict(solver=solver, flomas=flomas, npcor=npcor, lsq_flag=lsq, nigrad=nigrad, sor=1e-9, nsw=800)
+            ctx = lib.Context(local)
+            parallel.init_comm(ctx)
+            ctx.set_mesh(part)
+            ctx.create_csr()
+            for k, name in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("apu", "APU"),
+                            ("apv", "APV"), ("apw", "APW"), ("dPdxi", "DPDXI")):
+                ctx.upload(name, mine[k])
+            if mine["fmi"].size:
+                ctx.upload("FMI", mine["fmi"])
+            rep = ctx.calcp(lib.calcp_opts(parallel=True, **kw))
+            got = {k: ctx.download(k.upper()) for k in ("u", "v", "w", "p", "pp")}
+            got["a"] = ctx.download("A")
+            got["apr"] = ctx.download("APR")
+            got["flmass"] = ctx.download("FLMASS")
+            got["iters"] = [rep.rep[k].iters for k in range(npcor)]
+            got["res0"] = [rep.rep[k].res0 for k in range(npcor)]
+            got["cont"] = (rep.sumLocalContErr, rep.globalContErr)
+            ctx.close()
+            box = [None] * world
+            dist.all_gather_object(box, got)
+            if rank == 0:
+                pc = OP.ParCase(parts)
+                for m, fl in zip(parts, pc.fields):
+                    sc = scatter_case(g, m, f, fmi, gp)
+                    for k in ("u", "v", "w", "p", "den", "apu", "apv", "apw", "dPdxi"):
+                        getattr(fl, k)[:] = sc[k]
+                    fl.fmi[:sc["fmi"].size] = sc["fmi"]
+                oo = O.calcp_opts(**kw)
+                oo.sol.parallel = 1
+                rep_o = pc.calcp(oo)
+                tag = f"{mesh_name}/{solver}/npcor{npcor}"
+                for k in range(npcor):
+                    it, ito = box[0]["iters"][k], rep_o.rep[k].iters
+                    if abs(it - ito) > 1:
+                        failures.append(f"{tag}: iterations {it} vs oracle {ito}")
+                    if abs(box[0]["res0"][k] - rep_o.rep[k].res0) > 1e-9 * abs(rep_o.rep[k].res0):
+                        failures.append(f"{tag}: res0 {box[0]['res0'][k]} vs {rep_o.rep[k].res0}")
+                worst = 0.0
+                for r in range(world):
+                    for k in ("u", "v", "w", "p", "pp", "flmass"):
+                        ref = getattr(pc.fields[r], k)
+                        e = cases.rel_l2(box[r][k][:ref.size], ref)
+                        worst = max(worst, e)
+                        if e > 1e-6:
+                            failures.append(f"{tag}: rank {r} field {k} rel L2 {e:.2e}")
+                    if npcor == 1:   # the matrix is bit-exact (for npcor > 1 it is unchanged too, su differs)
+                        if not np.array_equal(box[r]["a"], pc.fields[r].a):
+                            failures.append(f"{tag}: rank {r} matrix not bit-exact")
+                        if parts[r].npro and not np.array_equal(box[r]["apr"][:parts[r].npro], pc.apr[r][:parts[r].npro]):
+                            failures.append(f"{tag}: rank {r} apr not bit-exact")
+                c0, c1 = box[0]["cont"]
+                if abs(c0 - rep_o.sumLocalContErr) > 1e-6 * abs(rep_o.sumLocalContErr) + 1e-13:
+                    failures.append(f"{tag}: sumLocalContErr {c0} vs {rep_o.sumLocalContErr}")
+                print(f"[mgpu] {tag}: iters {box[0]['iters']} (oracle {[rep_o.rep[k].iters for k in range(npcor)]}) "
+                      f"worst field rel L2 {worst:.2e}", flush=True)
+    ok = [not failures]
+    dist.broadcast_object_list(ok, src=0)
+    if rank == 0:
+        for m in failures:
+            print("[mgpu] FAIL", m, flush=True)
+        print("[mgpu] " + ("ALL OK" if not failures else f"{len(failures)} FAILURES"), flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if ok[0] else 1)
+
+
+if __name__ == "__main__":
+    main()

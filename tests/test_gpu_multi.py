@@ -1,0 +1,22 @@
+"""Launches the multi-GPU parity check (tests/mgpu_check.py) when the box has >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_rank_nccl_parity():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "mgpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(out.stdout[-4000:])
+    sys.stderr.write(out.stderr[-4000:])
+    assert out.returncode == 0
+    assert "ALL OK" in out.stdout
