@@ -15,7 +15,11 @@ namespace {
 
 #define GRID_STRIDE(i, n) for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)(n); i += (size_t)gridDim.x * blockDim.x)
 
-__global__ void k_scalar_step(fc_scalars *sc, int step, double *hist) { fc_scalar_step(sc, step, hist); }
+// after convergence the remaining launches of a batch are no-ops, the scalar step included
+__global__ void k_scalar_step(fc_scalars *sc, int step, double *hist) {
+  if (sc->done && step != STEP_RES0 && step != STEP_RES0_SK) return;
+  fc_scalar_step(sc, step, hist);
+}
 
 __global__ void k_init_scalars(fc_scalars *sc, double sor, double small, int nsw) {
   sc->sor = sor; sc->small = small; sc->nsw = nsw;

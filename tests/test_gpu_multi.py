@@ -16,7 +16,11 @@ def test_two_rank_nccl_parity():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "mgpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    sys.stdout.write(out.stdout[-4000:])
-    sys.stderr.write(out.stderr[-4000:])
-    assert out.returncode == 0
-    assert "ALL OK" in out.stdout
+    lines = [l for l in out.stdout.splitlines() if l.startswith("[mgpu]")]
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "mgpu_pytest.log"), "w") as fh:
+            fh.write(out.stdout + "\n--- stderr ---\n" + out.stderr)
+    except OSError:
+        pass
+    assert out.returncode == 0 and "[mgpu] ALL OK" in lines, "\n".join(lines[-30:]) + out.stderr[-1500:]
