@@ -86,3 +86,18 @@ def config4_fields(mesh):
     h = 1.0 / round((mesh.gloCells or n) ** (1.0 / 3.0))
     ap = 1.0 / (6.0 * h * (1.0 + 0.1 * np.sin(two_pi * (x[:npc] + y[:npc] + z[:npc]))))
     return dict(u=u, v=v, w=w, p=p, den=den, apu=ap.copy(), apv=ap.copy(), apw=ap.copy())
+
+
+def golden_mesh(npz_path, prefix=""):
+    """Mesh of a stored polyMesh fixture (tests/golden/*.npz, written by make_fixtures.py)."""
+    d = np.load(npz_path)
+    g = lambda k: d[prefix + k]
+    counts, starts = {}, {}
+    for kind, nf, st in zip(g("bkind"), g("bn"), g("bstart")):
+        kind = {"wallIsoth": "wall", "wallAdiab": "wall", "wallQFlux": "wall"}.get(str(kind), str(kind))
+        if kind not in counts:
+            counts[kind] = 0
+            starts[kind] = int(st)
+        counts[kind] += int(nf)
+    return M.geometry_from_polymesh(g("points"), g("faces").astype(np.int64), g("owner").astype(np.int32) + 1,
+                                    g("neighbour").astype(np.int32) + 1, counts, starts)

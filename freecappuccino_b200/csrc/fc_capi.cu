@@ -162,7 +162,7 @@ int fc_destroy(fc_context *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto &e : ctx->spmv_ev) cudaEventDestroy(e);
-  if (ctx->comm) ncclCommDestroy(ctx->comm);
+  fc_comm_destroy(ctx);
   free_all(ctx);
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);

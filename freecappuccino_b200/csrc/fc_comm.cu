@@ -6,7 +6,49 @@
 // rank; the receive lands directly in the halo slots phi(iProcStart+i) (:86-90), so there
 // is no unpack kernel.  Scalar sums are an in-place ncclAllReduce on the device-resident
 // reduction block; everything is enqueued on the context's stream.
+#include <dlfcn.h>
+
 #include "fc_internal.cuh"
+
+// NCCL is bound at run time, on the first communicator call, and never at library load: a host
+// process may already hold a libnccl (torch bundles its own 2.28 next to the system 2.27) and two
+// copies with one soname must not race for the symbol namespace.  An already-loaded libnccl.so.2 is
+// reused (RTLD_NOLOAD); otherwise the system library is opened.
+namespace fcnccl {
+#define FC_NCCL_FUNCS(X)                                                                         \
+  X(ncclGetUniqueId) X(ncclCommInitRank) X(ncclCommDestroy) X(ncclSend) X(ncclRecv) X(ncclAllReduce) \
+  X(ncclGroupStart) X(ncclGroupEnd) X(ncclGetErrorString)
+#define X(f) static decltype(&::f) f = nullptr;
+FC_NCCL_FUNCS(X)
+#undef X
+static bool bind() {
+  static int state = 0;  // 0 untried, 1 ok, -1 failed
+  if (state) return state > 0;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  bool ok = h != nullptr;
+#define X(f) if (ok) { f = (decltype(f))dlsym(h, #f); ok = f != nullptr; }
+  FC_NCCL_FUNCS(X)
+#undef X
+  state = ok ? 1 : -1;
+  return ok;
+}
+}  // namespace fcnccl
+#define ncclGetUniqueId fcnccl::ncclGetUniqueId
+#define ncclCommInitRank fcnccl::ncclCommInitRank
+#define ncclCommDestroy fcnccl::ncclCommDestroy
+#define ncclSend fcnccl::ncclSend
+#define ncclRecv fcnccl::ncclRecv
+#define ncclAllReduce fcnccl::ncclAllReduce
+#define ncclGroupStart fcnccl::ncclGroupStart
+#define ncclGroupEnd fcnccl::ncclGroupEnd
+#define ncclGetErrorString fcnccl::ncclGetErrorString
+
+void fc_comm_destroy(fc_context *ctx) {
+  if (ctx->comm && fcnccl::bind()) ncclCommDestroy(ctx->comm);
+  ctx->comm = nullptr;
+}
 
 namespace {
 __global__ void k_pack(int npro, const int *__restrict__ bufind, const double *__restrict__ phi,
@@ -65,6 +107,7 @@ int fc_allreduce_scalars(fc_context *ctx, double *dev, int count) {
 extern "C" int fc_comm_unique_id(char id128[128]) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
   ncclUniqueId id;
+  if (!fcnccl::bind()) return FC_ERR_NCCL;
   if (ncclGetUniqueId(&id) != ncclSuccess) return FC_ERR_NCCL;
   memcpy(id128, &id, 128);
   return FC_OK;
@@ -74,10 +117,11 @@ extern "C" int fc_comm_init(fc_context *ctx, int rank, int nranks, const char id
   if (!ctx) return FC_ERR_ARG;
   if (nranks < 1 || rank < 0 || rank >= nranks) FC_FAIL(FC_ERR_ARG, "fc_comm_init: bad rank / nranks");
   FC_CUDA(cudaSetDevice(ctx->device));
-  if (ctx->comm) { ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
+  fc_comm_destroy(ctx);
   ctx->rank = rank;
   ctx->nranks = nranks;
   if (nranks == 1) return FC_OK;
+  if (!fcnccl::bind()) FC_FAIL(FC_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : ""));
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   FC_NCCL(ncclCommInitRank(&ctx->comm, nranks, id, rank));

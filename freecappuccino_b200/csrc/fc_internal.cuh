@@ -168,7 +168,8 @@ int fc_launch_spmv_dots(fc_context *ctx, const double *a, const double *x, doubl
                         int step);
 int fc_launch_residual(fc_context *ctx, const double *a, const double *su, const double *x, double *res,
                        double *adiag);
-int fc_halo_exchange(fc_context *ctx, double *phi);                  // fc_comm.cu
+void fc_comm_destroy(fc_context *ctx);                               // fc_comm.cu
+int fc_halo_exchange(fc_context *ctx, double *phi);
 int fc_halo_exchange3(fc_context *ctx, double *grad);                // interleaved (3,numPCells) field
 int fc_strip_build(fc_context *ctx);                                 // fc_csr.cu: per-row processor faces
 int fc_allreduce_scalars(fc_context *ctx, double *dev, int count);

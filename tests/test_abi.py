@@ -1,0 +1,66 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/fcapp.h declares,
+and refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "fcapp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from freecappuccino_b200 import lib
+    h = lib.load()
+    names = header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(h, n), f"{n} declared in include/fcapp.h but not exported"
+    assert set(lib.SYMBOLS) == set(names)
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """ctypes mirrors of the ABI structs have the sizes / field offsets the C compiler gives the header."""
+    import subprocess
+    from freecappuccino_b200 import lib
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "fcapp.h"\n'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %d\\n", sizeof(fc_mesh_desc), sizeof(fc_solver_opts),'
+        ' sizeof(fc_solver_report), sizeof(fc_calcp_opts), sizeof(fc_calcp_report), sizeof(fc_timings),'
+        ' offsetof(fc_mesh_desc, gloCells), offsetof(fc_calcp_opts, sol), offsetof(fc_timings, launches),'
+        ' (int)FC_NUM_FIELDS);return 0;}\n')
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    want = [C.sizeof(lib.MeshDesc), C.sizeof(lib.SolverOpts), C.sizeof(lib.SolverReport), C.sizeof(lib.CalcpOpts),
+            C.sizeof(lib.CalcpReport), C.sizeof(lib.Timings), lib.MeshDesc.gloCells.offset, lib.CalcpOpts.sol.offset,
+            lib.Timings.launches.offset, len(lib.FIELDS)]
+    assert got == want
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from freecappuccino_b200 import lib
+    with pytest.raises(lib.FcError) as e:
+        lib.Context(0)
+    assert e.value.code == lib.FC_ERR_NODEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under freecappuccino_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "freecappuccino_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "fc_oracle" not in src, f

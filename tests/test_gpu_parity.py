@@ -39,6 +39,9 @@ MESHES = {
     "skew": lambda: cases.skew_case(),
     "slab_1cell_thick": lambda: cases.hex_case(20, 20, 1, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry")),
     "single_cell": lambda: cases.hex_case(1, 1, 1),
+    # the reference's shipped example meshes (BASELINE configs 1 and 2), stored under tests/golden
+    "cavity": lambda: cases.golden_mesh(os.path.join(os.path.dirname(__file__), "golden", "cavity.npz")),
+    "pitzDaily": lambda: cases.golden_mesh(os.path.join(os.path.dirname(__file__), "golden", "pitzDaily.npz")),
 }
 
 
@@ -148,7 +151,7 @@ def oracle_fields(mesh, csr, f, fmi):
     return of
 
 
-@pytest.mark.parametrize("name", ["hex_mixed_bc", "skew"])
+@pytest.mark.parametrize("name", ["hex_mixed_bc", "skew", "cavity", "pitzDaily"])
 @pytest.mark.parametrize("variant", [0, 1, 2])
 def test_calcp_assembly_bit_exact(fc, name, variant):
     mesh = MESHES[name]()
@@ -192,6 +195,30 @@ def test_calcp_full_parity(fc, solver, name, npcor, lsq):
     for name_g, ref in (("U", of.u), ("V", of.v), ("W", of.w), ("P", of.p), ("FLMASS", of.flmass)):
         assert cases.rel_l2(ctx.download(name_g), ref) < 1e-7, name_g  # solve stopped at rsm<1e-8: fields agree to solver tolerance
     assert rep.sumLocalContErr == pytest.approx(rep_ref.sumLocalContErr, rel=1e-6, abs=1e-14)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,sor,nsw", [("cavity", 1e-2, 100), ("pitzDaily", 1e-2, 200)])
+def test_example_cases_repeated_simple_steps(fc, name, sor, nsw):
+    """Configs 1/2 with the shipped settings of the pressure path (iccg, sor(ip)=1e-2, nsw(ip) of the
+    `input` files, urf(ip)=0.3, npcor=1): five consecutive calcp calls, each implementation evolving its
+    own state; iteration counts within +-1 and fields within 1e-10 relative L2 at every step."""
+    mesh = MESHES[name]()
+    ctx, _ = make_ctx(fc, mesh)
+    csr = oracle.create_csr(mesh)
+    f = cases.flow_fields(mesh)
+    fmi, flomas = cases.inlet_fluxes(mesh, f)
+    of = oracle_fields(mesh, csr, f, fmi)
+    kw = dict(solver="iccg", flomas=flomas, sor=sor, nsw=nsw, urf_p=0.3, pRefCell=1)
+    upload_flow(ctx, mesh, f, fmi)
+    ctx.upload("DPDXI", oracle.grad_gauss(mesh, f["p"], 1))
+    for step in range(5):
+        rep_ref = oracle.calcp(mesh, csr, of, oracle.calcp_opts(**kw))
+        rep = ctx.calcp(fc.calcp_opts(**kw))
+        assert abs(rep.rep[0].iters - rep_ref.rep[0].iters) <= 1, (step, rep.rep[0].iters, rep_ref.rep[0].iters)
+        if rep.rep[0].iters == rep_ref.rep[0].iters:
+            for name_g, ref in (("U", of.u), ("V", of.v), ("W", of.w), ("P", of.p), ("FLMASS", of.flmass), ("PP", of.pp)):
+                assert cases.rel_l2(ctx.download(name_g), ref) < TOL, (step, name_g)
     ctx.close()
 
 
