@@ -101,3 +101,22 @@ def golden_mesh(npz_path, prefix=""):
         counts[kind] += int(nf)
     return M.geometry_from_polymesh(g("points"), g("faces").astype(np.int64), g("owner").astype(np.int32) + 1,
                                     g("neighbour").astype(np.int32) + 1, counts, starts)
+
+
+def channel_fields(mesh, seed=11):
+    """Through-flow in +x (inlet left, outlet right, as in pitzDaily) with smooth perturbations: the outlet
+    mass-flow scaling of adjustMassFlow / correctBoundaryConditionsVelocity is then well conditioned."""
+    f = flow_fields(mesh, seed)
+    n, nt = mesh.numCells, mesh.numTotal
+    x = np.zeros(nt); y = np.zeros(nt)
+    x[:n], y[:n] = mesh.xc[:n], mesh.yc[:n]
+    for kind in M.KINDS:
+        fs, sl = mesh.boundary_faces(kind), mesh.boundary_slots(kind)
+        x[sl], y[sl] = mesh.xf[fs], mesh.yf[fs]
+    lx = max(float(np.ptp(mesh.xf)), 1e-30)
+    f["u"] = 1.0 + 0.1 * np.sin(2 * np.pi * x / lx) * np.cos(2 * np.pi * y / lx) + 0.05 * f["u"]
+    f["v"] = 0.05 * f["v"]
+    f["w"] = 0.05 * f["w"]
+    sl = mesh.boundary_slots("wall")
+    f["u"][sl] = f["v"][sl] = f["w"][sl] = 0.0
+    return f
