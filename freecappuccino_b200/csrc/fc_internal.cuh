@@ -38,6 +38,7 @@ struct fc_levels {                      // level schedule of the strict lower / 
   int *blk_level = nullptr;             // [nslots / TRI_BLOCK] level of every block
   int *lev_blocks_before = nullptr;     // [nlev+1] number of blocks in levels < L
   unsigned int *done = nullptr;         // [nlev] blocks finished per level (monotone over sweeps)
+  unsigned int *ready = nullptr;        // [nlev] number of the last sweep whose level is complete
   unsigned int *ticket = nullptr;       // dynamic block id
   unsigned long long epoch = 0;         // sweeps run so far
 };

@@ -124,6 +124,7 @@ int build_one(fc_context *ctx, fc_levels &L, int lower) {
   FC_CHECK(fc_dev_alloc(ctx, &L.blk_level, (size_t)nblocks));
   FC_CHECK(fc_dev_alloc(ctx, &L.lev_blocks_before, (size_t)nlev + 1));
   FC_CHECK(fc_dev_alloc(ctx, &L.done, (size_t)nlev));
+  FC_CHECK(fc_dev_alloc(ctx, &L.ready, (size_t)nlev));
   FC_CHECK(fc_dev_alloc(ctx, &L.ticket, 1));
   FC_CUDA(cudaMemcpyAsync(dstart, start.data(), sizeof(int) * (nlev + 1), cudaMemcpyHostToDevice, ctx->stream));
   FC_CUDA(cudaMemcpyAsync(dslot, slot.data(), sizeof(int) * (nlev + 1), cudaMemcpyHostToDevice, ctx->stream));
@@ -135,6 +136,7 @@ int build_one(fc_context *ctx, fc_levels &L, int lower) {
   k_level_place<<<fc_blocks(n, B), B, 0, ctx->stream>>>(slevel, srow, n, dstart, dslot, L.rows);
   FC_LAUNCH_CHECK();
   FC_CUDA(cudaMemsetAsync(L.done, 0, sizeof(unsigned int) * (size_t)nlev, ctx->stream));
+  FC_CUDA(cudaMemsetAsync(L.ready, 0, sizeof(unsigned int) * (size_t)nlev, ctx->stream));
   FC_CUDA(cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), ctx->stream));
   L.epoch = 0;
   FC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -145,11 +147,31 @@ int build_one(fc_context *ctx, fc_levels &L, int lower) {
 
 enum { TRI_FWD = 0, TRI_BWD = 1, TRI_DIC = 2, TRI_DIC_PAR = 3, TRI_DILU = 4 };
 
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int atom_add_acq_rel(unsigned int *p, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+
+constexpr int TRI_PRE = 4;  // matrix entries of a row fetched before the wait (hex rows have 3 per triangle)
+
 // One sweep.  `in`: r (FWD) or the forward result t (BWD); `out`: t (FWD), z (BWD), d (factor modes).
+// Dependency chain per level: poll `ready[lev-1]` -> gather z of earlier rows from L2 -> row sum ->
+// store -> CTA barrier -> one acq_rel atomic per CTA; the CTA that completes the level publishes
+// ready[lev].  Everything that does not depend on other rows (row bounds, d, r and the first TRI_PRE
+// matrix entries) is already in registers when the wait ends.
 template <int MODE>
 __global__ void __launch_bounds__(TRI_BLOCK)
 k_tri_sweep(const int *__restrict__ rows, const int *__restrict__ blk_level,
-            const int *__restrict__ lev_blocks_before, unsigned int *done, unsigned int *ticket,
+            const int *__restrict__ lev_blocks_before, unsigned int *done, unsigned int *ready, unsigned int *ticket,
             unsigned int ticket_base, unsigned int sweep_no, const int *__restrict__ ioffset,
             const int *__restrict__ ja, const int *__restrict__ diag, const int *__restrict__ tpos,
             const double *__restrict__ a, const double *__restrict__ d, const double *__restrict__ in,
@@ -163,39 +185,65 @@ k_tri_sweep(const int *__restrict__ rows, const int *__restrict__ blk_level,
   const int row = rows[b * TRI_BLOCK + threadIdx.x];
   int s = 0, e = 0;
   double v = 0.0, di = 0.0;
-  if (row >= 0) {  // everything that does not depend on other rows is fetched before the wait
+  double pa[TRI_PRE], pt[TRI_PRE];
+  int pj[TRI_PRE];
+  if (row >= 0) {
     if (MODE == TRI_BWD) { s = diag[row] + 1; e = ioffset[row + 1]; }
     else { s = ioffset[row]; e = diag[row]; }
+#pragma unroll
+    for (int q = 0; q < TRI_PRE; ++q) {
+      const int k = s + q;
+      if (k < e) {
+        pa[q] = a[k];
+        pj[q] = ja[k];
+        if (MODE == TRI_DILU) pt[q] = a[tpos[k]];
+      }
+    }
     if (MODE == TRI_FWD) { v = in[row]; di = d[row]; }
     else if (MODE == TRI_BWD) { di = d[row]; v = in[row] / (di + small); }   // z = z/(d+small), iccg.f90:102
     else v = a[diag[row]];
   }
   if (lev > 0) {
     if (threadIdx.x == 0) {
-      const unsigned int need = sweep_no * (unsigned int)(lev_blocks_before[lev] - lev_blocks_before[lev - 1]);
-      volatile unsigned int *c = done + (lev - 1);
-      while (*c < need) { __nanosleep(20); }
-      __threadfence();
+      const unsigned int *r = ready + (lev - 1);
+      while (ld_acquire(r) < sweep_no) {}
     }
     __syncthreads();
   }
   if (row >= 0) {
-    for (int k = s; k < e; ++k) {
+    double zq[TRI_PRE];
+#pragma unroll
+    for (int q = 0; q < TRI_PRE; ++q)
+      if (s + q < e) zq[q] = __ldcg(out + pj[q]);   // written by another CTA during this launch: bypass L1
+#pragma unroll
+    for (int q = 0; q < TRI_PRE; ++q) {
+      if (s + q < e) {
+        const double ak = pa[q], zj = zq[q];
+        if (MODE == TRI_FWD || MODE == TRI_BWD) v = v - ak * zj;
+        else if (MODE == TRI_DIC) v = v - (ak * ak) * zj;            // iccg.f90:80
+        else if (MODE == TRI_DIC_PAR) v = v - ak * zj * ak;          // src-parallel/iccg.f90:97
+        else v = v - ak * zj * pt[q];                                // bicgstab.f90:76
+      }
+    }
+    for (int k = s + TRI_PRE; k < e; ++k) {                          // long rows (polyhedral cells)
       const int j = ja[k];
-      if (MODE == TRI_BWD && j >= n) break;            // halo columns never enter the preconditioner
-      const double zj = __ldcg(out + j);               // written by another CTA during this launch: bypass L1
+      const double zj = __ldcg(out + j);
       const double ak = a[k];
       if (MODE == TRI_FWD || MODE == TRI_BWD) v = v - ak * zj;
-      else if (MODE == TRI_DIC) v = v - (ak * ak) * zj;            // iccg.f90:80
-      else if (MODE == TRI_DIC_PAR) v = v - ak * zj * ak;          // src-parallel/iccg.f90:97
-      else v = v - ak * zj * a[tpos[k]];                           // bicgstab.f90:76
+      else if (MODE == TRI_DIC) v = v - (ak * ak) * zj;
+      else if (MODE == TRI_DIC_PAR) v = v - ak * zj * ak;
+      else v = v - ak * zj * a[tpos[k]];
     }
     if (MODE == TRI_FWD || MODE == TRI_BWD) out[row] = v * di;
     else out[row] = 1.0 / (v + padd);
   }
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(done + lev, 1u);
+  if (threadIdx.x == 0) {
+    // release this CTA's rows; the CTA that completes the level has acquired every other CTA's release
+    const unsigned int nb = (unsigned int)(lev_blocks_before[lev + 1] - lev_blocks_before[lev]);
+    const unsigned int old = atom_add_acq_rel(done + lev, 1u);
+    if (old + 1u == sweep_no * nb) st_release(ready + lev, sweep_no);
+  }
 }
 
 template <int MODE>
@@ -205,8 +253,8 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
   const unsigned int base = (unsigned int)(L.epoch * (unsigned long long)nblocks);
   L.epoch++;
   k_tri_sweep<MODE><<<nblocks, TRI_BLOCK, 0, ctx->stream>>>(
-      L.rows, L.blk_level, L.lev_blocks_before, L.done, L.ticket, base, (unsigned int)L.epoch, ctx->ioffset, ctx->ja,
-      ctx->diag, ctx->tpos, a, d, in, out, small, padd, ctx->n, guarded ? ctx->sc : nullptr);
+      L.rows, L.blk_level, L.lev_blocks_before, L.done, L.ready, L.ticket, base, (unsigned int)L.epoch, ctx->ioffset,
+      ctx->ja, ctx->diag, ctx->tpos, a, d, in, out, small, padd, ctx->n, guarded ? ctx->sc : nullptr);
   FC_LAUNCH_CHECK();
   return FC_OK;
 }
@@ -214,7 +262,8 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
 }  // namespace
 
 void fc_levels_free(fc_levels &L) {
-  cudaFree(L.rows); cudaFree(L.blk_level); cudaFree(L.lev_blocks_before); cudaFree(L.done); cudaFree(L.ticket);
+  cudaFree(L.rows); cudaFree(L.blk_level); cudaFree(L.lev_blocks_before); cudaFree(L.done); cudaFree(L.ready);
+  cudaFree(L.ticket);
   L = fc_levels{};
 }
 
@@ -230,6 +279,7 @@ int fc_levels_build(fc_context *ctx) {
 int fc_levels_reset(fc_context *ctx) {
   for (fc_levels *L : {&ctx->lower, &ctx->upper}) {
     FC_CUDA(cudaMemsetAsync(L->done, 0, sizeof(unsigned int) * (size_t)L->nlev, ctx->stream));
+    FC_CUDA(cudaMemsetAsync(L->ready, 0, sizeof(unsigned int) * (size_t)L->nlev, ctx->stream));
     FC_CUDA(cudaMemsetAsync(L->ticket, 0, sizeof(unsigned int), ctx->stream));
     L->epoch = 0;
   }

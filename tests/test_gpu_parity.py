@@ -198,11 +198,15 @@ def test_calcp_full_parity(fc, solver, name, npcor, lsq):
     ctx.close()
 
 
-@pytest.mark.parametrize("name,sor,nsw", [("cavity", 1e-2, 100), ("pitzDaily", 1e-2, 200)])
-def test_example_cases_repeated_simple_steps(fc, name, sor, nsw):
+@pytest.mark.parametrize("name,sor,nsw,ftol", [("cavity", 1e-2, 100, 1e-10), ("pitzDaily", 1e-2, 200, 2e-3),
+                                               ("pitzDaily", 1e-9, 3000, 1e-6)])
+def test_example_cases_repeated_simple_steps(fc, name, sor, nsw, ftol):
     """Configs 1/2 with the shipped settings of the pressure path (iccg, sor(ip)=1e-2, nsw(ip) of the
     `input` files, urf(ip)=0.3, npcor=1): five consecutive calcp calls, each implementation evolving its
-    own state; iteration counts within +-1 and fields within 1e-10 relative L2 at every step."""
+    own state; iteration counts within +-1 at every step.  Fields: 1e-10 relative L2 on the well-conditioned
+    cavity; on pitzDaily (stretched 2-D mesh, ~140 ICCG iterations for two digits) a solve stopped at
+    rsm < sor fixes the fields only to about that tolerance, so the bar scales with sor there and a second
+    run with a tight solve shows the agreement improving accordingly."""
     mesh = MESHES[name]()
     ctx, _ = make_ctx(fc, mesh)
     csr = oracle.create_csr(mesh)
@@ -218,7 +222,7 @@ def test_example_cases_repeated_simple_steps(fc, name, sor, nsw):
         assert abs(rep.rep[0].iters - rep_ref.rep[0].iters) <= 1, (step, rep.rep[0].iters, rep_ref.rep[0].iters)
         if rep.rep[0].iters == rep_ref.rep[0].iters:
             for name_g, ref in (("U", of.u), ("V", of.v), ("W", of.w), ("P", of.p), ("FLMASS", of.flmass), ("PP", of.pp)):
-                assert cases.rel_l2(ctx.download(name_g), ref) < TOL, (step, name_g)
+                assert cases.rel_l2(ctx.download(name_g), ref) < ftol, (step, name_g)
     ctx.close()
 
 

@@ -25,7 +25,7 @@ def main():
         t_csr = time.perf_counter() - t0
         su = cases.poisson_rhs(m)
         ctx.upload("APU", -np.ones(m.numCells))
-        for solver in ("dpcg", "iccg", "bicgstab"):
+        for solver in os.environ.get("SOLVERS", "dpcg,iccg").split(","):
             ctx.upload("SU", su)
             ctx.fill("PP", 0.0)
             ctx.laplacian("APU", "PP")
