@@ -184,6 +184,7 @@ def run_ours(args):
         mesh, f = gmesh, gf
     ctx.set_mesh(mesh)
     ctx.create_csr(download=False)
+    p2p = parallel.enable_p2p(ctx) if world > 1 else False
     for k, name in (("u", "USER0"), ("v", "USER1"), ("w", "USER2"), ("p", "USER3"), ("den", "DEN"), ("apu", "APU"),
                     ("apv", "APV"), ("apw", "APW")):
         ctx.upload(name, f[k])
@@ -288,6 +289,7 @@ def run_ours(args):
         "config": {"workload": f"synthetic {args.n}^3 hex pressure-correction (config 4): calcp = assemble + DPCG to "
                                f"rsm<1e-8 + correct", "cells": gmesh.numCells, "nnz": gmesh.nnz,
                    "partition": "1 rank" if world == 1 else f"{world} z-slabs, {mesh.npro} processor faces on rank 0",
+                   "comm": "none" if world == 1 else ("p2p: NVLink stores between kernels (CUDA IPC)" if p2p else "nccl"),
                    "l2": "inputs_exceed_l2 (SpMV working set %.0f MB)" % (ab["spmv"] / 1e6), "solver": "dpcg",
                    "sor": SOR},
         "dpcg_iterations_per_step": iters / args.steps,

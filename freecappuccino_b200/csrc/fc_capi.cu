@@ -162,6 +162,7 @@ int fc_destroy(fc_context *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto &e : ctx->spmv_ev) cudaEventDestroy(e);
+  fc_p2p_close(ctx);
   fc_comm_destroy(ctx);
   free_all(ctx);
   for (auto &ev : ctx->ev)
@@ -183,6 +184,7 @@ int fc_set_mesh(fc_context *ctx, const fc_mesh_desc *m) {
   if (!ctx || !m) return FC_ERR_ARG;
   FC_CUDA(cudaSetDevice(ctx->device));
   if (ctx->csr_external) FC_FAIL(FC_ERR_ARG, "fc_set_mesh: context already adopted an explicit CSR pattern");
+  fc_p2p_close(ctx);
   if (m->noc > 0)
     FC_FAIL(FC_ERR_UNSUPPORTED, "O-C grid cuts (noc > 0) are not on the GPU path (none of the target cases has them)");
   if (m->numCells < 1 || m->numInnerFaces < 0 || m->numFaces < m->numInnerFaces ||

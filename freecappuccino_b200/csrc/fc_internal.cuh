@@ -29,6 +29,32 @@ struct fc_scalars {
   double aux[4];
   int iters, nsw, done, pad;
   unsigned int ticket[4];               // "last block finalises" counters
+  unsigned long long applied;           // P2P mode: sequence number of the last reduction folded into the scalars
+};
+
+// ---- peer-to-peer (NVLink) communication state, see fc_p2p.cu ----
+constexpr int FC_MAX_RANKS = 16, FC_MAX_CONN = 16, FC_MAIL_SLOTS = 4;
+struct fc_mail {                        // one rank's contribution to one reduction, written by that rank
+  double v[4];
+  unsigned long long seq;
+  unsigned long long pad[3];
+};
+struct fc_p2p_dev {                     // device-resident tables read by the kernels
+  int rank, nranks, nconn, pad;
+  fc_mail *mail;                                   // my mailboxes [FC_MAIL_SLOTS][FC_MAX_RANKS]
+  fc_mail *peer_mail[FC_MAX_RANKS];                // every rank's mailbox array (peer-mapped; [rank] = mine)
+  unsigned long long *hflag;                       // my halo-arrival flags, one per connection
+  unsigned long long *peer_hflag[FC_MAX_CONN];     // the flag in neighbour c's arena that I raise
+  double *peer_pk[FC_MAX_CONN], *peer_zk[FC_MAX_CONN];  // halo slots of neighbour c's pk / zk that I fill
+  int conn_off[FC_MAX_CONN + 1];                   // my processor faces [conn_off[c], conn_off[c+1]) go to c
+};
+struct fc_sync {                        // per-launch synchronisation descriptor of a Krylov kernel
+  fc_p2p_dev *p2p;                      // nullptr: single rank, or NCCL mode
+  unsigned long long wait_seq;          // reduction to fold into the scalars before the kernel body (0: none)
+  int wait_step, wait_count;
+  unsigned long long post_seq;          // sequence number of the reduction this kernel produces
+  int local, pad;                       // 1: single rank, the finalising thread runs the scalar step itself
+  double *hist;
 };
 
 struct fc_levels {                      // level schedule of the strict lower / upper triangle
@@ -98,6 +124,14 @@ struct fc_context {
   int *bufind = nullptr;                // owner cell of every processor face (exchange.f90:48-50)
   double *sendbuf = nullptr;
   int *strip_off = nullptr, *strip_idx = nullptr;  // per-row processor faces (apr strip of the SpMV)
+  // peer-to-peer mode (fc_p2p.cu): reductions and the Krylov halo go over mapped peer memory
+  bool p2p = false;
+  void *arena = nullptr;                // IPC-shared allocation: mailboxes, flags, pk, zk
+  size_t arena_bytes = 0, arena_hflag_off = 0;
+  fc_p2p_dev *p2p_dev = nullptr;
+  std::vector<void *> peer_base;        // opened peer arenas
+  unsigned long long red_seq = 0, halo_seq = 0, halo_wait = 0;
+  struct { unsigned long long seq; int step, count; } pending = {0, 0, 0};
 
   // ---- timing ----
   cudaEvent_t ev[4] = {};
@@ -166,13 +200,15 @@ int fc_precond_apply(fc_context *ctx, const double *a, const double *d, const do
 int fc_alloc_solver_scratch(fc_context *ctx);                        // fc_krylov.cu
 int fc_launch_spmv(fc_context *ctx, const double *a, const double *x, double *y);       // fc_spmv.cu
 int fc_launch_spmv_dots(fc_context *ctx, const double *a, const double *x, double *y, const double *w, int two,
-                        int step);
+                        int step, const fc_sync &sy);
 int fc_launch_residual(fc_context *ctx, const double *a, const double *su, const double *x, double *res,
-                       double *adiag);
+                       double *adiag, const fc_sync &sy);
 void fc_comm_destroy(fc_context *ctx);                               // fc_comm.cu
 int fc_halo_exchange(fc_context *ctx, double *phi);
 int fc_halo_exchange3(fc_context *ctx, double *grad);                // interleaved (3,numPCells) field
-int fc_strip_build(fc_context *ctx);                                 // fc_csr.cu: per-row processor faces
+int fc_strip_build(fc_context *ctx);
+int fc_p2p_pack(fc_context *ctx, double *x);                          // fc_p2p.cu: halo of pk / zk by peer stores
+void fc_p2p_close(fc_context *ctx);                                 // fc_csr.cu: per-row processor faces
 int fc_allreduce_scalars(fc_context *ctx, double *dev, int count);
 int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opts *o, fc_solver_report *rep,
                     double *hist);

@@ -21,6 +21,9 @@ __global__ void k_scalar_step(fc_scalars *sc, int step, double *hist) {
   fc_scalar_step(sc, step, hist);
 }
 
+// P2P mode: fold a pending reduction into the scalars when no Krylov kernel follows that would do it
+__global__ void k_apply(fc_scalars *sc, fc_sync sy) { fc_kernel_begin(sc, sy); }
+
 __global__ void k_init_scalars(fc_scalars *sc, double sor, double small, int nsw) {
   sc->sor = sor; sc->small = small; sc->nsw = nsw;
   sc->done = 0; sc->iters = 0;
@@ -30,25 +33,23 @@ __global__ void k_init_scalars(fc_scalars *sc, double sor, double small, int nsw
 // sk = sum res * (res / (a_ii [+small]))  -- first Jacobi inner product (dpcg.f90:85-90)
 __global__ void __launch_bounds__(FC_RED_BLOCK)
 k_jacobi_sk(int n, const double *__restrict__ res, const double *__restrict__ adiag, double padd, double *partials,
-            fc_scalars *sc, int local) {
+            fc_scalars *sc, fc_sync sy) {
   __shared__ double s_red[32];
+  if (!fc_kernel_begin(sc, sy)) return;
   double acc = 0.0;
   GRID_STRIDE(i, n) {
     double r = res[i];
     acc += r * (r / (adiag[i] + padd));
   }
   double v[1] = {acc};
-  if (fc_grid_sum<1>(v, partials, &sc->ticket[1], s_red)) {
-    sc->red[0] = v[0];
-    if (local) fc_scalar_step(sc, STEP_SK, nullptr);
-  }
+  if (fc_grid_sum<1>(v, partials, &sc->ticket[1], s_red)) fc_reduction_done<1>(sc, sy, v, STEP_SK);
 }
 
 // pk = res/(a_ii[+small]) + bet*pk   (dpcg.f90:85-87, 95-100)
 __global__ void __launch_bounds__(FC_RED_BLOCK)
 k_dpcg_pupdate(int n, const double *__restrict__ res, const double *__restrict__ adiag, double padd,
-               double *__restrict__ pk, const fc_scalars *sc) {
-  if (sc->done) return;
+               double *__restrict__ pk, fc_scalars *sc, fc_sync sy) {
+  if (!fc_kernel_begin(sc, sy)) return;
   const double bet = sc->sk / sc->s0;
   GRID_STRIDE(i, n) pk[i] = res[i] / (adiag[i] + padd) + bet * pk[i];
 }
@@ -57,9 +58,9 @@ k_dpcg_pupdate(int n, const double *__restrict__ res, const double *__restrict__
 __global__ void __launch_bounds__(FC_RED_BLOCK)
 k_dpcg_update(int n, double *__restrict__ fi, const double *__restrict__ pk, double *__restrict__ res,
               const double *__restrict__ zk, const double *__restrict__ adiag, double padd, double *partials,
-              fc_scalars *sc, double *hist, int local) {
+              fc_scalars *sc, fc_sync sy) {
   __shared__ double s_red[64];
-  if (sc->done) return;
+  if (!fc_kernel_begin(sc, sy)) return;
   const double alf = sc->sk / sc->pkapk;
   double a0 = 0.0, a1 = 0.0;
   GRID_STRIDE(i, n) {
@@ -70,32 +71,25 @@ k_dpcg_update(int n, double *__restrict__ fi, const double *__restrict__ pk, dou
     a1 += r * (r / (adiag[i] + padd));
   }
   double v[2] = {a0, a1};
-  if (fc_grid_sum<2>(v, partials, &sc->ticket[1], s_red)) {
-    sc->red[0] = v[0];
-    sc->red[1] = v[1];
-    if (local) fc_scalar_step(sc, STEP_CG_UPDATE_SK, hist);
-  }
+  if (fc_grid_sum<2>(v, partials, &sc->ticket[1], s_red)) fc_reduction_done<2>(sc, sy, v, STEP_CG_UPDATE_SK);
 }
 
 // generic dot products: red[0] = sum x*y (and red[1] = sum x*z if z)
 __global__ void __launch_bounds__(FC_RED_BLOCK)
 k_dot(int n, const double *__restrict__ x, const double *__restrict__ y, double *partials, fc_scalars *sc, int step,
-      int local, int guarded) {
+      fc_sync sy) {
   __shared__ double s_red[32];
-  if (guarded && sc->done) return;
+  if (!fc_kernel_begin(sc, sy)) return;
   double acc = 0.0;
   GRID_STRIDE(i, n) acc += x[i] * y[i];
   double v[1] = {acc};
-  if (fc_grid_sum<1>(v, partials, &sc->ticket[1], s_red)) {
-    sc->red[0] = v[0];
-    if (local) fc_scalar_step(sc, step, nullptr);
-  }
+  if (fc_grid_sum<1>(v, partials, &sc->ticket[1], s_red)) fc_reduction_done<1>(sc, sy, v, step);
 }
 
 // pk = zk + bet*pk   (iccg.f90:121-126)
 __global__ void __launch_bounds__(FC_RED_BLOCK)
-k_cg_pupdate(int n, const double *__restrict__ zk, double *__restrict__ pk, const fc_scalars *sc) {
-  if (sc->done) return;
+k_cg_pupdate(int n, const double *__restrict__ zk, double *__restrict__ pk, fc_scalars *sc, fc_sync sy) {
+  if (!fc_kernel_begin(sc, sy)) return;
   const double bet = sc->sk / sc->s0;
   GRID_STRIDE(i, n) pk[i] = zk[i] + bet * pk[i];
 }
@@ -103,9 +97,9 @@ k_cg_pupdate(int n, const double *__restrict__ zk, double *__restrict__ pk, cons
 // fi += alf*pk ; res -= alf*zk ; resl = sum|res|   (iccg.f90:156-165)
 __global__ void __launch_bounds__(FC_RED_BLOCK)
 k_cg_update(int n, double *__restrict__ fi, const double *__restrict__ pk, double *__restrict__ res,
-            const double *__restrict__ zk, double *partials, fc_scalars *sc, double *hist, int local) {
+            const double *__restrict__ zk, double *partials, fc_scalars *sc, fc_sync sy) {
   __shared__ double s_red[32];
-  if (sc->done) return;
+  if (!fc_kernel_begin(sc, sy)) return;
   const double alf = sc->sk / sc->pkapk;
   double a0 = 0.0;
   GRID_STRIDE(i, n) {
@@ -115,17 +109,14 @@ k_cg_update(int n, double *__restrict__ fi, const double *__restrict__ pk, doubl
     a0 += fabs(r);
   }
   double v[1] = {a0};
-  if (fc_grid_sum<1>(v, partials, &sc->ticket[1], s_red)) {
-    sc->red[0] = v[0];
-    if (local) fc_scalar_step(sc, STEP_CG_UPDATE, hist);
-  }
+  if (fc_grid_sum<1>(v, partials, &sc->ticket[1], s_red)) fc_reduction_done<1>(sc, sy, v, STEP_CG_UPDATE);
 }
 
 // pk = res + om*(pk - alf*uk)   (bicgstab.f90:113-115)
 __global__ void __launch_bounds__(FC_RED_BLOCK)
 k_bi_pupdate(int n, const double *__restrict__ res, double *__restrict__ pk, const double *__restrict__ uk,
-             const fc_scalars *sc) {
-  if (sc->done) return;
+             fc_scalars *sc, fc_sync sy) {
+  if (!fc_kernel_begin(sc, sy)) return;
   const double om = sc->om, alf = sc->alf;
   GRID_STRIDE(i, n) pk[i] = res[i] + om * (pk[i] - alf * uk[i]);
 }
@@ -133,8 +124,8 @@ k_bi_pupdate(int n, const double *__restrict__ res, double *__restrict__ pk, con
 // fi += gam*zk ; res -= gam*uk   (bicgstab.f90:159-162)
 __global__ void __launch_bounds__(FC_RED_BLOCK)
 k_bi_half(int n, double *__restrict__ fi, const double *__restrict__ zk, double *__restrict__ res,
-          const double *__restrict__ uk, const fc_scalars *sc) {
-  if (sc->done) return;
+          const double *__restrict__ uk, fc_scalars *sc, fc_sync sy) {
+  if (!fc_kernel_begin(sc, sy)) return;
   const double gam = sc->gam;
   GRID_STRIDE(i, n) {
     fi[i] = fi[i] + gam * zk[i];
@@ -145,9 +136,9 @@ k_bi_half(int n, double *__restrict__ fi, const double *__restrict__ zk, double 
 // fi += alf*zk ; res -= alf*vk ; resl = sum|res|   (bicgstab.f90:208-217)
 __global__ void __launch_bounds__(FC_RED_BLOCK)
 k_bi_update(int n, double *__restrict__ fi, const double *__restrict__ zk, double *__restrict__ res,
-            const double *__restrict__ vk, double *partials, fc_scalars *sc, double *hist, int local) {
+            const double *__restrict__ vk, double *partials, fc_scalars *sc, fc_sync sy) {
   __shared__ double s_red[32];
-  if (sc->done) return;
+  if (!fc_kernel_begin(sc, sy)) return;
   const double alf = sc->alf;
   double a0 = 0.0;
   GRID_STRIDE(i, n) {
@@ -157,10 +148,7 @@ k_bi_update(int n, double *__restrict__ fi, const double *__restrict__ zk, doubl
     a0 += fabs(r);
   }
   double v[1] = {a0};
-  if (fc_grid_sum<1>(v, partials, &sc->ticket[1], s_red)) {
-    sc->red[0] = v[0];
-    if (local) fc_scalar_step(sc, STEP_BI_UPDATE, hist);
-  }
+  if (fc_grid_sum<1>(v, partials, &sc->ticket[1], s_red)) fc_reduction_done<1>(sc, sy, v, STEP_BI_UPDATE);
 }
 
 inline int vec_grid(int n) {
@@ -169,14 +157,54 @@ inline int vec_grid(int n) {
   return g < 1 ? 1 : g;
 }
 
-// all-reduce of red[0..count) over the ranks + the scalar step (src-parallel: global_sum after every sum)
-int global_step(fc_context *ctx, int count, int step, double *hist) {
-  if (ctx->nranks == 1) return FC_OK;  // the finalising thread already ran the step
-  FC_CHECK(fc_allreduce_scalars(ctx, ctx->sc->red, count));
-  k_scalar_step<<<1, 1, 0, ctx->stream>>>(ctx->sc, step, hist);
-  FC_LAUNCH_CHECK();
-  return FC_OK;
-}
+// Host side of the reduction hand-over.  Three modes:
+//   single rank  the finishing thread of the producing kernel runs the scalar step itself;
+//   NCCL         producing kernel -> ncclAllReduce(red) -> k_scalar_step   (global_sum of src-parallel);
+//   P2P          producing kernel posts to the peers' mailboxes, the NEXT kernel folds them in
+//                (`pending`); flush() does it with a 1-CTA kernel when no Krylov kernel follows.
+struct flow_t {
+  fc_context *ctx;
+  double *hist;
+
+  // descriptor for the next launch; `step`/`count` describe the reduction it produces (0: none)
+  fc_sync next(int step = 0, int count = 0) {
+    fc_sync s{};
+    s.hist = hist;
+    s.local = ctx->nranks == 1;
+    if (ctx->p2p) {
+      s.p2p = ctx->p2p_dev;
+      if (ctx->pending.seq) {
+        s.wait_seq = ctx->pending.seq; s.wait_step = ctx->pending.step; s.wait_count = ctx->pending.count;
+        ctx->pending = {0, 0, 0};
+      }
+      if (step) {
+        s.post_seq = ++ctx->red_seq;
+        ctx->pending = {s.post_seq, step, count};
+      }
+    }
+    return s;
+  }
+  // after a producing launch
+  int reduced(int step, int count) {
+    if (ctx->nranks == 1 || ctx->p2p) return FC_OK;
+    FC_CHECK(fc_allreduce_scalars(ctx, ctx->sc->red, count));
+    k_scalar_step<<<1, 1, 0, ctx->stream>>>(ctx->sc, step, hist);
+    FC_LAUNCH_CHECK();
+    return FC_OK;
+  }
+  int flush() {
+    if (!ctx->p2p || !ctx->pending.seq) return FC_OK;
+    k_apply<<<1, 32, 0, ctx->stream>>>(ctx->sc, next());
+    FC_LAUNCH_CHECK();
+    return FC_OK;
+  }
+  // halo of a Krylov vector before the SpMV (call exchange(pk), src-parallel/dpcg.f90:114)
+  int exchange(double *x) {
+    if (ctx->npro == 0) return FC_OK;
+    if (ctx->p2p) return fc_p2p_pack(ctx, x);
+    return fc_halo_exchange(ctx, x);
+  }
+};
 
 int poll(fc_context *ctx) {
   FC_CUDA(cudaMemcpyAsync(ctx->sc_host, ctx->sc, sizeof(fc_scalars), cudaMemcpyDeviceToHost, ctx->stream));
@@ -208,7 +236,6 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
   if (solver < FC_DPCG || solver > FC_BICGSTAB) FC_FAIL(FC_ERR_ARG, "fc_solve: unknown solver");
   FC_CHECK(fc_alloc_solver_scratch(ctx));
   const int n = ctx->n;
-  const int local = ctx->nranks == 1;
   const int g = vec_grid(n);
   const double *a = ctx->field[FC_A], *su = ctx->field[FC_SU];
   double *res = ctx->field[FC_RES];
@@ -222,9 +249,13 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
   FC_CUDA(cudaEventRecord(ctx->ev[0], st));
   k_init_scalars<<<1, 1, 0, st>>>(ctx->sc, o->sor, o->small, o->nsw);
   FC_LAUNCH_CHECK();
+  flow_t fl{ctx, hist};
+  ctx->pending = {0, 0, 0};
+  ctx->halo_wait = 0;
   // res = su - A fi, res0 = sum|res|   (dpcg.f90:51-64; the parallel twin uses fi's halo as it is)
-  FC_CHECK(fc_launch_residual(ctx, a, su, fi, res, ctx->adiag));
-  FC_CHECK(global_step(ctx, 1, STEP_RES0, nullptr));
+  FC_CHECK(fc_launch_residual(ctx, a, su, fi, res, ctx->adiag, fl.next(STEP_RES0, 1)));
+  FC_CHECK(fl.reduced(STEP_RES0, 1));
+  FC_CHECK(fl.flush());
   FC_CHECK(poll(ctx));
   rep->res0 = ctx->sc_host->res0;
   rep->resl = ctx->sc_host->res0;
@@ -240,9 +271,9 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
     FC_CHECK(fc_precond_factor(ctx, solver == FC_BICGSTAB ? 2 : (o->parallel ? 1 : 0), a, d, padd));
   }
   if (solver == FC_DPCG) {
-    k_jacobi_sk<<<g, FC_RED_BLOCK, 0, st>>>(n, res, ctx->adiag, padd, ctx->partials, ctx->sc, local);
+    k_jacobi_sk<<<g, FC_RED_BLOCK, 0, st>>>(n, res, ctx->adiag, padd, ctx->partials, ctx->sc, fl.next(STEP_SK, 1));
     FC_LAUNCH_CHECK();
-    FC_CHECK(global_step(ctx, 1, STEP_SK, nullptr));
+    FC_CHECK(fl.reduced(STEP_SK, 1));
   } else if (solver == FC_BICGSTAB) {
     FC_CUDA(cudaMemcpyAsync(ctx->reso, res, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
     FC_CUDA(cudaMemsetAsync(ctx->uk, 0, sizeof(double) * (size_t)n, st));
@@ -254,51 +285,53 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
     const int todo = (o->nsw - launched) < batch ? (o->nsw - launched) : batch;
     for (int it = 0; it < todo; ++it) {
       if (solver == FC_DPCG) {
-        k_dpcg_pupdate<<<g, FC_RED_BLOCK, 0, st>>>(n, res, ctx->adiag, padd, pk, ctx->sc);
+        k_dpcg_pupdate<<<g, FC_RED_BLOCK, 0, st>>>(n, res, ctx->adiag, padd, pk, ctx->sc, fl.next());
         FC_LAUNCH_CHECK();
-        if (ctx->npro > 0) FC_CHECK(fc_halo_exchange(ctx, pk));
-        FC_CHECK(fc_launch_spmv_dots(ctx, a, pk, zk, pk, 0, STEP_PKAPK));
-        FC_CHECK(global_step(ctx, 1, STEP_PKAPK, nullptr));
-        k_dpcg_update<<<g, FC_RED_BLOCK, 0, st>>>(n, fi, pk, res, zk, ctx->adiag, padd, ctx->partials, ctx->sc, hist,
-                                                  local);
+        FC_CHECK(fl.exchange(pk));
+        FC_CHECK(fc_launch_spmv_dots(ctx, a, pk, zk, pk, 0, STEP_PKAPK, fl.next(STEP_PKAPK, 1)));
+        FC_CHECK(fl.reduced(STEP_PKAPK, 1));
+        k_dpcg_update<<<g, FC_RED_BLOCK, 0, st>>>(n, fi, pk, res, zk, ctx->adiag, padd, ctx->partials, ctx->sc,
+                                                  fl.next(STEP_CG_UPDATE_SK, 2));
         FC_LAUNCH_CHECK();
-        FC_CHECK(global_step(ctx, 2, STEP_CG_UPDATE_SK, hist));
+        FC_CHECK(fl.reduced(STEP_CG_UPDATE_SK, 2));
       } else if (solver == FC_ICCG) {
+        FC_CHECK(fl.flush());   // the sweeps read `done`: the end-of-iteration reduction must be folded in first
         FC_CHECK(fc_precond_apply(ctx, a, d, res, ctx->tt, zk, o->small));
-        k_dot<<<g, FC_RED_BLOCK, 0, st>>>(n, res, zk, ctx->partials, ctx->sc, STEP_SK, local, 1);
+        k_dot<<<g, FC_RED_BLOCK, 0, st>>>(n, res, zk, ctx->partials, ctx->sc, STEP_SK, fl.next(STEP_SK, 1));
         FC_LAUNCH_CHECK();
-        FC_CHECK(global_step(ctx, 1, STEP_SK, nullptr));
-        k_cg_pupdate<<<g, FC_RED_BLOCK, 0, st>>>(n, zk, pk, ctx->sc);
+        FC_CHECK(fl.reduced(STEP_SK, 1));
+        k_cg_pupdate<<<g, FC_RED_BLOCK, 0, st>>>(n, zk, pk, ctx->sc, fl.next());
         FC_LAUNCH_CHECK();
-        if (ctx->npro > 0) FC_CHECK(fc_halo_exchange(ctx, pk));
-        FC_CHECK(fc_launch_spmv_dots(ctx, a, pk, zk, pk, 0, STEP_PKAPK));
-        FC_CHECK(global_step(ctx, 1, STEP_PKAPK, nullptr));
-        k_cg_update<<<g, FC_RED_BLOCK, 0, st>>>(n, fi, pk, res, zk, ctx->partials, ctx->sc, hist, local);
+        FC_CHECK(fl.exchange(pk));
+        FC_CHECK(fc_launch_spmv_dots(ctx, a, pk, zk, pk, 0, STEP_PKAPK, fl.next(STEP_PKAPK, 1)));
+        FC_CHECK(fl.reduced(STEP_PKAPK, 1));
+        k_cg_update<<<g, FC_RED_BLOCK, 0, st>>>(n, fi, pk, res, zk, ctx->partials, ctx->sc, fl.next(STEP_CG_UPDATE, 1));
         FC_LAUNCH_CHECK();
-        FC_CHECK(global_step(ctx, 1, STEP_CG_UPDATE, hist));
+        FC_CHECK(fl.reduced(STEP_CG_UPDATE, 1));
       } else {
         double *uk = ctx->uk, *vk = ctx->vk, *reso = ctx->reso, *t = ctx->tt;
-        k_dot<<<g, FC_RED_BLOCK, 0, st>>>(n, res, reso, ctx->partials, ctx->sc, STEP_BET, local, 1);
+        k_dot<<<g, FC_RED_BLOCK, 0, st>>>(n, res, reso, ctx->partials, ctx->sc, STEP_BET, fl.next(STEP_BET, 1));
         FC_LAUNCH_CHECK();
-        FC_CHECK(global_step(ctx, 1, STEP_BET, nullptr));
-        k_bi_pupdate<<<g, FC_RED_BLOCK, 0, st>>>(n, res, pk, uk, ctx->sc);
+        FC_CHECK(fl.reduced(STEP_BET, 1));
+        k_bi_pupdate<<<g, FC_RED_BLOCK, 0, st>>>(n, res, pk, uk, ctx->sc, fl.next());
         FC_LAUNCH_CHECK();
         FC_CHECK(fc_precond_apply(ctx, a, d, pk, t, zk, o->small));
-        if (ctx->npro > 0) FC_CHECK(fc_halo_exchange(ctx, zk));
-        FC_CHECK(fc_launch_spmv_dots(ctx, a, zk, uk, reso, 0, STEP_UKRESO));
-        FC_CHECK(global_step(ctx, 1, STEP_UKRESO, nullptr));
-        k_bi_half<<<g, FC_RED_BLOCK, 0, st>>>(n, fi, zk, res, uk, ctx->sc);
+        FC_CHECK(fl.exchange(zk));
+        FC_CHECK(fc_launch_spmv_dots(ctx, a, zk, uk, reso, 0, STEP_UKRESO, fl.next(STEP_UKRESO, 1)));
+        FC_CHECK(fl.reduced(STEP_UKRESO, 1));
+        k_bi_half<<<g, FC_RED_BLOCK, 0, st>>>(n, fi, zk, res, uk, ctx->sc, fl.next());
         FC_LAUNCH_CHECK();
         FC_CHECK(fc_precond_apply(ctx, a, d, res, t, zk, o->small));
-        if (ctx->npro > 0) FC_CHECK(fc_halo_exchange(ctx, zk));
-        FC_CHECK(fc_launch_spmv_dots(ctx, a, zk, vk, res, 1, STEP_VK));
-        FC_CHECK(global_step(ctx, 2, STEP_VK, nullptr));
-        k_bi_update<<<g, FC_RED_BLOCK, 0, st>>>(n, fi, zk, res, vk, ctx->partials, ctx->sc, hist, local);
+        FC_CHECK(fl.exchange(zk));
+        FC_CHECK(fc_launch_spmv_dots(ctx, a, zk, vk, res, 1, STEP_VK, fl.next(STEP_VK, 2)));
+        FC_CHECK(fl.reduced(STEP_VK, 2));
+        k_bi_update<<<g, FC_RED_BLOCK, 0, st>>>(n, fi, zk, res, vk, ctx->partials, ctx->sc, fl.next(STEP_BI_UPDATE, 1));
         FC_LAUNCH_CHECK();
-        FC_CHECK(global_step(ctx, 1, STEP_BI_UPDATE, hist));
+        FC_CHECK(fl.reduced(STEP_BI_UPDATE, 1));
       }
     }
     launched += todo;
+    FC_CHECK(fl.flush());
     FC_CHECK(poll(ctx));
     if (ctx->sc_host->done) break;
     if (batch < 32) batch *= 2;

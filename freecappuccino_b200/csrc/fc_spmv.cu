@@ -21,18 +21,24 @@ struct strip_t {               // processor-boundary coupling kept outside the C
   const int *idx;              // processor-face index i (0-based, ascending per row)
   const double *apr;           // [npro]
   int halo0;                   // x[halo0 + i] = value on the other rank
+  // P2P mode: the neighbours store the halo of x themselves (fc_p2p.cu) and raise hflag[c] to hseq
+  const unsigned long long *hflag;
+  unsigned long long hseq;
+  int nconn;
 };
 
 template <int ROWS, int CAP, int MODE, bool STRIP>
 __global__ void __launch_bounds__(ROWS)
 k_spmv(int n, const int *__restrict__ ioffset, const int *__restrict__ ja, const double *__restrict__ a,
        const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ su,
-       const double *__restrict__ w, const int *__restrict__ diag, double *__restrict__ adiag, strip_t st, double *partials, fc_scalars *sc,
-       int step, int local_step) {
+       const double *__restrict__ w, const int *__restrict__ diag, double *__restrict__ adiag, strip_t st,
+       double *partials, fc_scalars *sc, int step, fc_sync sy) {
   __shared__ double prod[CAP];
   __shared__ int s_off[ROWS + 1];
   __shared__ double s_red[64];
-  if ((MODE == MODE_DOT || MODE == MODE_DOT2) && sc->done) return;
+  if (MODE == MODE_DOT || MODE == MODE_DOT2) {
+    if (!fc_kernel_begin(sc, sy)) return;
+  }
   const int tid = threadIdx.x;
   const int nchunks = (n + ROWS - 1) / ROWS;
   double acc = 0.0, acc2 = 0.0;
@@ -62,9 +68,14 @@ k_spmv(int n, const int *__restrict__ ioffset, const int *__restrict__ ja, const
         }
       }
       if (STRIP) {
-        for (int q = st.off[r]; q < st.off[r + 1]; ++q) {
+        const int q0 = st.off[r], q1 = st.off[r + 1];
+        if (q1 > q0 && st.hseq) {   // rows with processor faces wait for the neighbours' stores; the rest overlap them
+          for (int c = 0; c < st.nconn; ++c)
+            while (fc_ld_acquire_sys(st.hflag + c) < st.hseq) {}
+        }
+        for (int q = q0; q < q1; ++q) {
           const int i = st.idx[q];
-          double t = st.apr[i] * x[st.halo0 + i];
+          double t = st.apr[i] * __ldcg(x + st.halo0 + i);
           v = (MODE == MODE_RESID) ? v - t : v + t;
         }
       }
@@ -80,35 +91,33 @@ k_spmv(int n, const int *__restrict__ ioffset, const int *__restrict__ ja, const
   }
   if (MODE == MODE_DOT2) {
     double v[2] = {acc, acc2};
-    if (fc_grid_sum<2>(v, partials, &sc->ticket[0], s_red)) {
-      sc->red[0] = v[0];
-      sc->red[1] = v[1];
-      if (local_step) fc_scalar_step(sc, step, nullptr);
-    }
+    if (fc_grid_sum<2>(v, partials, &sc->ticket[0], s_red)) fc_reduction_done<2>(sc, sy, v, step);
   } else if (MODE != MODE_SPMV) {
     double v[1] = {acc};
-    if (fc_grid_sum<1>(v, partials, &sc->ticket[0], s_red)) {
-      sc->red[0] = v[0];
-      if (local_step) fc_scalar_step(sc, step, nullptr);
-    }
+    if (fc_grid_sum<1>(v, partials, &sc->ticket[0], s_red)) fc_reduction_done<1>(sc, sy, v, step);
   }
 }
 
 template <int MODE>
 int launch(fc_context *ctx, const double *a, const double *x, double *y, const double *su, const double *w,
-           double *adiag, int step) {
+           double *adiag, int step, const fc_sync &sy) {
   const int n = ctx->n;
-  strip_t st{ctx->strip_off, ctx->strip_idx, ctx->field[FC_APR], n};
+  strip_t st{ctx->strip_off, ctx->strip_idx, ctx->field[FC_APR], n, nullptr, 0ull, 0};
+  if (ctx->p2p && ctx->halo_wait && (x == ctx->pk || x == ctx->zk)) {
+    st.hflag = (const unsigned long long *)((const char *)ctx->arena + ctx->arena_hflag_off);
+    st.hseq = ctx->halo_wait;
+    st.nconn = (int)ctx->nbr_rank.size();
+    ctx->halo_wait = 0;
+  }
   const int nchunks = (n + 255) / 256;
   int grid = nchunks < FC_SMS * 8 ? nchunks : FC_SMS * 8;
   if (grid < 1) grid = 1;
-  const int local = ctx->nranks == 1;
   const bool strip = ctx->npro > 0;
   const bool small_rows = ctx->spmv_max_chunk <= 2304;
   if (!small_rows && grid > FC_SMS * 4) grid = FC_SMS * 4;
 #define FC_SPMV_LAUNCH(CAP, STRIP)                                                                              \
   k_spmv<256, CAP, MODE, STRIP><<<grid, 256, 0, ctx->stream>>>(n, ctx->ioffset, ctx->ja, a, x, y, su, w, ctx->diag, \
-                                                               adiag, st, ctx->partials, ctx->sc, step, local)
+                                                               adiag, st, ctx->partials, ctx->sc, step, sy)
   if (small_rows) { if (strip) FC_SPMV_LAUNCH(2304, true); else FC_SPMV_LAUNCH(2304, false); }
   else            { if (strip) FC_SPMV_LAUNCH(5632, true); else FC_SPMV_LAUNCH(5632, false); }
 #undef FC_SPMV_LAUNCH
@@ -119,16 +128,17 @@ int launch(fc_context *ctx, const double *a, const double *x, double *y, const d
 }  // namespace
 
 int fc_launch_spmv(fc_context *ctx, const double *a, const double *x, double *y) {
-  return launch<MODE_SPMV>(ctx, a, x, y, nullptr, nullptr, nullptr, STEP_NONE);
+  fc_sync sy{};
+  return launch<MODE_SPMV>(ctx, a, x, y, nullptr, nullptr, nullptr, STEP_NONE, sy);
 }
 
 // y = A x fused with red[0] = w.y (and red[1] = y.y when `two`)
 int fc_launch_spmv_dots(fc_context *ctx, const double *a, const double *x, double *y, const double *w, int two,
-                        int step) {
+                        int step, const fc_sync &sy) {
   const bool sample = (size_t)(2 * ctx->spmv_sampled + 1) < ctx->spmv_ev.size();
   if (sample) FC_CUDA(cudaEventRecord(ctx->spmv_ev[2 * ctx->spmv_sampled], ctx->stream));
-  FC_CHECK(two ? launch<MODE_DOT2>(ctx, a, x, y, nullptr, w, nullptr, step)
-               : launch<MODE_DOT>(ctx, a, x, y, nullptr, w, nullptr, step));
+  FC_CHECK(two ? launch<MODE_DOT2>(ctx, a, x, y, nullptr, w, nullptr, step, sy)
+               : launch<MODE_DOT>(ctx, a, x, y, nullptr, w, nullptr, step, sy));
   if (sample) {
     FC_CUDA(cudaEventRecord(ctx->spmv_ev[2 * ctx->spmv_sampled + 1], ctx->stream));
     ctx->spmv_sampled++;
@@ -137,6 +147,6 @@ int fc_launch_spmv_dots(fc_context *ctx, const double *a, const double *x, doubl
 }
 
 int fc_launch_residual(fc_context *ctx, const double *a, const double *su, const double *x, double *res,
-                       double *adiag) {
-  return launch<MODE_RESID>(ctx, a, x, res, su, nullptr, adiag, STEP_RES0);
+                       double *adiag, const fc_sync &sy) {
+  return launch<MODE_RESID>(ctx, a, x, res, su, nullptr, adiag, STEP_RES0, sy);
 }

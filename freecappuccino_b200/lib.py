@@ -37,7 +37,8 @@ SYMBOLS = (
     "fc_create_csr", "fc_field_size", "fc_upload", "fc_download", "fc_fill", "fc_synchronize", "fc_spmv",
     "fc_grad_gauss", "fc_grad_gauss_corrected", "fc_bpres", "fc_laplacian", "fc_solve", "fc_solve_host",
     "fc_solve_csr", "fc_calcp_assemble", "fc_calcp", "fc_calcp_host", "fc_exchange", "fc_global_sum",
-    "fc_get_timings", "fc_time_spmv", "fc_stream", "fc_copy", "fc_set_spmv_sampling",
+    "fc_get_timings", "fc_time_spmv", "fc_stream", "fc_copy", "fc_set_spmv_sampling", "fc_comm_p2p_blob",
+    "fc_comm_p2p_open",
 )
 
 
@@ -162,6 +163,17 @@ class Context:
 
     def comm_init(self, rank: int, nranks: int, uid: bytes):
         self._ck(self.lib.fc_comm_init(self.h, rank, nranks, C.c_char_p(uid)))
+
+    P2P_BLOB_BYTES = 512
+
+    def p2p_blob(self) -> bytes:
+        buf = C.create_string_buffer(self.P2P_BLOB_BYTES)
+        self._ck(self.lib.fc_comm_p2p_blob(self.h, buf))
+        return buf.raw
+
+    def p2p_open(self, blobs):
+        raw = b"".join(blobs)
+        self._ck(self.lib.fc_comm_p2p_open(self.h, C.c_char_p(raw), len(blobs)))
 
     @staticmethod
     def comm_unique_id() -> bytes:

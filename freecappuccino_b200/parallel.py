@@ -27,6 +27,20 @@ def init_comm(ctx):
     return rank, world
 
 
+def enable_p2p(ctx) -> bool:
+    """Switch the Krylov loop's halo exchange and reductions to direct NVLink stores between the ranks'
+    kernels (csrc/fc_p2p.cu).  Call after ``create_csr``.  The blobs (CUDA IPC handle + connection table)
+    are all-gathered in rank order -- MPI_Allgather in a Fortran MPI host.  Set FC_NO_P2P=1 to stay on NCCL."""
+    import os
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1 or os.environ.get("FC_NO_P2P") == "1":
+        return False
+    blobs = [None] * dist.get_world_size()
+    dist.all_gather_object(blobs, ctx.p2p_blob())
+    ctx.p2p_open(blobs)
+    return True
+
+
 def bufind(mesh) -> np.ndarray:
     """0-based owner cell of every processor face (``bufind(i) = owner(iProcFacesStart+i)``,
     src-parallel/mesh_geometry_and_topology.f90:879-881)."""

@@ -92,6 +92,15 @@ int fc_version(void);
  * build, torch.distributed in the Python harness).                        */
 int fc_comm_unique_id(char id128[128]);
 int fc_comm_init(fc_context *ctx, int rank, int nranks, const char id128[128]);
+/* Optional peer-to-peer mode for the GPUs of one box (after fc_create_csr): every
+ * rank publishes a blob (CUDA IPC handle of its communication arena + its
+ * connection table), the host all-gathers them in rank order (MPI_Allgather /
+ * torch.distributed) and hands the table back.  Afterwards the Krylov loop's halo
+ * exchange and scalar reductions run as direct NVLink stores between the kernels
+ * instead of NCCL calls.  Without it everything goes through NCCL.            */
+#define FC_P2P_BLOB_BYTES 512
+int fc_comm_p2p_blob(fc_context *ctx, char *blob /* FC_P2P_BLOB_BYTES */);
+int fc_comm_p2p_open(fc_context *ctx, const char *blobs /* nranks * FC_P2P_BLOB_BYTES */, int nranks);
 
 /* ---- mesh + CSR pattern ----------------------------------------------- */
 /* Copies the geometry arrays to the device and builds the cell-to-face map. */

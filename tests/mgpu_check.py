@@ -62,6 +62,7 @@ def main():
             parallel.init_comm(ctx)
             ctx.set_mesh(part)
             ctx.create_csr()
+            p2p = parallel.enable_p2p(ctx)      # direct NVLink stores unless FC_NO_P2P=1
             for k, name in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("apu", "APU"),
                             ("apv", "APV"), ("apw", "APW"), ("dPdxi", "DPDXI")):
                 ctx.upload(name, mine[k])
@@ -111,7 +112,7 @@ def main():
                 c0, c1 = box[0]["cont"]
                 if abs(c0 - rep_o.sumLocalContErr) > 1e-6 * abs(rep_o.sumLocalContErr) + 1e-13:
                     failures.append(f"{tag}: sumLocalContErr {c0} vs {rep_o.sumLocalContErr}")
-                print(f"[mgpu] {tag}: iters {box[0]['iters']} (oracle {[rep_o.rep[k].iters for k in range(npcor)]}) "
+                print(f"[mgpu] {'p2p' if p2p else 'nccl'} {tag}: iters {box[0]['iters']} (oracle {[rep_o.rep[k].iters for k in range(npcor)]}) "
                       f"worst field rel L2 {worst:.2e}", flush=True)
     ok = [not failures]
     dist.broadcast_object_list(ok, src=0)

@@ -9,18 +9,22 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_rank_nccl_parity():
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_two_rank_parity(mode):
+    """2 ranks, halo + reductions over direct NVLink stores (p2p) or NCCL collectives (nccl)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "mgpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "127.0.0.1", "--master-port", "29517" if mode == "p2p" else "29518", os.path.join(ROOT, "tests", "mgpu_check.py")]
+    env = dict(os.environ, FC_NO_P2P="0" if mode == "p2p" else "1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     lines = [l for l in out.stdout.splitlines() if l.startswith("[mgpu]")]
     try:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", "mgpu_pytest.log"), "w") as fh:
+        with open(os.path.join(ROOT, "gpurun_out", f"mgpu_pytest_{mode}.log"), "w") as fh:
             fh.write(out.stdout + "\n--- stderr ---\n" + out.stderr)
     except OSError:
         pass
+    assert any(l.startswith(f"[mgpu] {mode} ") for l in lines), "the requested communication mode did not run"
     assert out.returncode == 0 and "[mgpu] ALL OK" in lines, "\n".join(lines[-30:]) + out.stderr[-1500:]
