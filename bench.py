@@ -43,6 +43,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic():
+    """DRAM bytes of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -193,6 +203,8 @@ def run_ours(args):
     opts = lib.calcp_opts(solver="dpcg", const_mflux=True, sor=SOR, nsw=NSW, pRefCell=1, urf_p=0.3,
                           parallel=world > 1)
     ctx.set_spmv_sampling(512)
+    if args.no_persist:
+        ctx.set_tuning(lib.TUNE_DPCG_PERSISTENT, 0)
     stream = torch.cuda.ExternalStream(ctx.lib.fc_stream(ctx.h), device=torch.device("cuda", local))
 
     def restore():  # device-to-device: the step always starts from the same fields
@@ -218,6 +230,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = 0
     spmv_ms, spmv_n, asm_ms, corr_ms, solve_ms = 0.0, 0, 0.0, 0.0, 0.0
+    persist = dict(ms=0.0, pupdate_ms=0.0, spmv_ms=0.0, update_ms=0.0, mail_ms=0.0, iters=0, grid=0)
     e0.record(stream)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -227,6 +240,11 @@ def run_ours(args):
         spmv_ms += t.spmv_ms * t.spmv_samples
         spmv_n += t.spmv_samples
         asm_ms += t.assemble_ms; corr_ms += t.correct_ms; solve_ms += t.solve_ms
+        if t.persist_iters:
+            persist["ms"] += t.persist_ms; persist["pupdate_ms"] += t.persist_pupdate_ms
+            persist["spmv_ms"] += t.persist_spmv_ms; persist["update_ms"] += t.persist_update_ms
+            persist["mail_ms"] += t.persist_mail_ms; persist["iters"] += t.persist_iters
+            persist["grid"] = t.persist_grid
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
@@ -270,17 +288,51 @@ def run_ours(args):
         e2e_s = float(tt.item())
     e2e_value = e2e_iters / e2e_s
 
-    # ---- roofline of the dominant kernel: SpMV fused with p.Ap ----
+    # ---- roofline of the dominant kernel ----
+    # Default path: the whole Krylov loop of a step is ONE launch of the persistent kernel k_dpcg_persist, so the
+    # launch duration is the solve bracket (CUDA events on the library's stream) and the launch processes
+    # `iterations` units of SURVEY 8(d)'s per-iteration figure 12 nnz + 116 n.  Its SpMV phase is timed inside the
+    # kernel on the GPU's global timer (grid barrier release -> arrival of the last CTA at the next barrier).
+    # With FC_TUNE persistent=0 (or NCCL mode) the SpMV(+p.Ap) launches are bracketed with events instead.
     ab = algorithmic_bytes(mesh)   # this rank's share
     peak, peak_src = measured_peak()
-    spmv_mean_ms = spmv_ms / max(spmv_n, 1)
-    achieved = ab["spmv"] / (spmv_mean_ms * 1e-3) / 1e9 if spmv_n else None
+    iters_per_step = iters / args.steps
     alone_ms = ctx.time_spmv("PP", "SCRATCH_T", 50)
-    roof = {"bound": "hbm", "kernel": "k_spmv<256,2304,DOT> (SpMV + p.Ap)", "achieved": achieved, "peak": peak,
-            "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-            "frac_of_nominal_8000": (achieved / 8000.0) if achieved else None, "traffic": None,
-            "algorithmic_bytes_per_launch": ab["spmv"], "mean_launch_ms": spmv_mean_ms, "launches_sampled": spmv_n,
-            "standalone_spmv_ms": alone_ms, "standalone_spmv_gbs": ab["spmv"] / (alone_ms * 1e-3) / 1e9}
+    traffic = measured_traffic()
+    if persist["iters"]:
+        launch_ms = solve_ms / args.steps
+        achieved = ab["dpcg_iter"] * iters_per_step / (launch_ms * 1e-3) / 1e9
+        it = persist["iters"]
+        spmv_us = 1e3 * persist["spmv_ms"] / it
+        roof = {"bound": "hbm", "kernel": "k_dpcg_persist<256,2304,2> (whole DPCG solve, one cooperative launch per step)",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_nominal_8000": achieved / 8000.0,
+                "traffic": (traffic["dram_bytes_per_iteration"] * iters_per_step) if traffic and world == 1 else None,
+                "traffic_source": traffic["source"] if traffic and world == 1 else None,
+                "algorithmic_bytes_per_launch": ab["dpcg_iter"] * iters_per_step,
+                "algorithmic_bytes_per_iteration": ab["dpcg_iter"], "iterations_per_launch": iters_per_step,
+                "mean_launch_ms": launch_ms, "launches_timed": args.steps, "grid": persist["grid"],
+                "phases_us_per_iteration": {
+                    "p_update": 1e3 * persist["pupdate_ms"] / it, "spmv_dot": spmv_us,
+                    "x_r_update": 1e3 * persist["update_ms"] / it,
+                    "barriers_reductions_halo": 1e3 * (persist["ms"] - persist["pupdate_ms"] - persist["spmv_ms"]
+                                                       - persist["update_ms"]) / it,
+                    "of_which_waiting_for_other_ranks": 1e3 * persist["mail_ms"] / it},
+                "spmv_phase": {"algorithmic_bytes": ab["spmv"], "us": spmv_us,
+                               "achieved": ab["spmv"] / (spmv_us * 1e-6) / 1e9,
+                               "frac": ab["spmv"] / (spmv_us * 1e-6) / 1e9 / peak,
+                               "frac_of_nominal_8000": ab["spmv"] / (spmv_us * 1e-6) / 1e9 / 8000.0,
+                               "clock": "in-kernel %globaltimer, barrier release -> last CTA arrival"},
+                "standalone_spmv_ms": alone_ms, "standalone_spmv_gbs": ab["spmv"] / (alone_ms * 1e-3) / 1e9}
+    else:
+        spmv_mean_ms = spmv_ms / max(spmv_n, 1)
+        achieved = ab["spmv"] / (spmv_mean_ms * 1e-3) / 1e9 if spmv_n else None
+        roof = {"bound": "hbm", "kernel": "k_spmv<256,2304,DOT> (SpMV + p.Ap)", "achieved": achieved, "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "frac_of_nominal_8000": (achieved / 8000.0) if achieved else None, "traffic": None,
+                "algorithmic_bytes_per_launch": ab["spmv"], "mean_launch_ms": spmv_mean_ms,
+                "launches_sampled": spmv_n, "standalone_spmv_ms": alone_ms,
+                "standalone_spmv_gbs": ab["spmv"] / (alone_ms * 1e-3) / 1e9}
     iter_ms = solve_ms / max(iters, 1)
     out = {
         "metric": "pcorr_dpcg_iterations_per_second", "value": value, "unit": "iter/s", "n_gpus": world,
@@ -289,7 +341,8 @@ def run_ours(args):
         "config": {"workload": f"synthetic {args.n}^3 hex pressure-correction (config 4): calcp = assemble + DPCG to "
                                f"rsm<1e-8 + correct", "cells": gmesh.numCells, "nnz": gmesh.nnz,
                    "partition": "1 rank" if world == 1 else f"{world} z-slabs, {mesh.npro} processor faces on rank 0",
-                   "comm": "none" if world == 1 else ("p2p: NVLink stores between kernels (CUDA IPC)" if p2p else "nccl"),
+                   "comm": "none" if world == 1 else ("p2p: NVLink stores + flags inside the persistent kernel (CUDA IPC)"
+                                                      if p2p else "nccl"),
                    "l2": "inputs_exceed_l2 (SpMV working set %.0f MB)" % (ab["spmv"] / 1e6), "solver": "dpcg",
                    "sor": SOR},
         "dpcg_iterations_per_step": iters / args.steps,
@@ -329,6 +382,8 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=60, help="DPCG iterations of the cpu_baseline sample")
     ap.add_argument("--ref-iters", type=int, default=20, help="DPCG iterations per step of the reference arm")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-persist", action="store_true", help="one launch per vector operation instead of the "
+                    "persistent DPCG kernel (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

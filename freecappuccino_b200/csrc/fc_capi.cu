@@ -102,13 +102,15 @@ void free_all(fc_context *ctx) {
                   (void *)ctx->pk, (void *)ctx->zk, (void *)ctx->dd, (void *)ctx->reso, (void *)ctx->uk,
                   (void *)ctx->vk, (void *)ctx->adiag, (void *)ctx->tt, (void *)ctx->coef, (void *)ctx->facev,
                   (void *)ctx->gtmp, (void *)ctx->partials, (void *)ctx->sc, (void *)ctx->bufind,
-                  (void *)ctx->sendbuf, (void *)ctx->strip_off, (void *)ctx->strip_idx})
+                  (void *)ctx->sendbuf, (void *)ctx->strip_off, (void *)ctx->strip_idx,
+                  (void *)ctx->strip_any32, (void *)ctx->persist})
     if (p) cudaFree(p);
   for (int f = 0; f < FC_NUM_FIELDS; ++f)
     if (ctx->field[f]) cudaFree(ctx->field[f]);
   fc_levels_free(ctx->lower);
   fc_levels_free(ctx->upper);
   if (ctx->sc_host) cudaFreeHost(ctx->sc_host);
+  if (ctx->persist_host) cudaFreeHost(ctx->persist_host);
 }
 
 }  // namespace
@@ -149,6 +151,10 @@ int fc_create(int device, fc_context **out) {
     FC_CUDA(cudaMallocHost((void **)&ctx->sc_host, sizeof(fc_scalars)));
     memset(ctx->sc_host, 0, sizeof(fc_scalars));
     FC_CHECK(fc_dev_alloc(ctx, &ctx->partials, (size_t)FC_MAX_RED * 2048));
+    FC_CHECK(fc_dev_alloc(ctx, &ctx->persist, 1));
+    FC_CUDA(cudaMemset(ctx->persist, 0, sizeof(fc_persist_state)));
+    FC_CUDA(cudaMallocHost((void **)&ctx->persist_host, sizeof(fc_persist_state)));
+    memset(ctx->persist_host, 0, sizeof(fc_persist_state));
     return FC_OK;
   };
   int s = init();
@@ -462,6 +468,18 @@ int fc_global_sum(fc_context *ctx, double *value) {
   FC_CHECK(fc_allreduce_scalars(ctx, &ctx->sc->aux[0], 1));
   FC_CUDA(cudaMemcpyAsync(value, &ctx->sc->aux[0], sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   FC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FC_OK;
+}
+
+int fc_set_tuning(fc_context *ctx, int key, int value) {
+  if (!ctx) return FC_ERR_ARG;
+  switch (key) {
+    case FC_TUNE_SPMV_KERNEL: if (value < 0 || value > 2) return FC_ERR_ARG; ctx->tune_spmv = value; break;
+    case FC_TUNE_DPCG_PERSISTENT: if (value < 0 || value > 1) return FC_ERR_ARG; ctx->tune_persist = value; break;
+    case FC_TUNE_PIPE_GEOMETRY: if (value < 0 || value > 3) return FC_ERR_ARG; ctx->tune_pipe = value; break;
+    case FC_TUNE_CTAS_PER_SM: if (value < 0 || value > 8) return FC_ERR_ARG; ctx->tune_ctas_per_sm = value; break;
+    default: FC_FAIL(FC_ERR_ARG, "fc_set_tuning: unknown key");
+  }
   return FC_OK;
 }
 

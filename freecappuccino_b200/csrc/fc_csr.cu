@@ -186,6 +186,13 @@ __global__ void k_strip_fill(const int *__restrict__ off, const int *__restrict_
     if ((face[q] & 0x7fffffff) >= F && other[q] < n + npro) sidx[k++] = other[q] - n;
 }
 
+__global__ void k_strip_any32(const int *__restrict__ soff, int n, unsigned char *any32) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g * 32 >= n) return;
+  int r1 = min(n, (g + 1) * 32);
+  any32[g] = soff[r1] > soff[g * 32] ? 1 : 0;
+}
+
 int exclusive_scan(fc_context *ctx, int *in, int *out, int count) {
   void *tmp = nullptr;
   size_t bytes = 0;
@@ -320,6 +327,9 @@ int fc_c2f_build(fc_context *ctx) {
     FC_CHECK(exclusive_scan(ctx, cnt, ctx->strip_off, n + 1));
     k_strip_fill<<<fc_blocks(n, B), B, 0, ctx->stream>>>(ctx->c2f_off, ctx->c2f_other, n, ctx->npro, F, ctx->c2f_face,
                                                          ctx->strip_off, ctx->strip_idx);
+    FC_LAUNCH_CHECK();
+    FC_CHECK(fc_dev_alloc(ctx, &ctx->strip_any32, (size_t)(n + 31) / 32));
+    k_strip_any32<<<fc_blocks((size_t)(n + 31) / 32, B), B, 0, ctx->stream>>>(ctx->strip_off, n, ctx->strip_any32);
     FC_LAUNCH_CHECK();
   }
   FC_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -1,0 +1,415 @@
+// dpcg(fi,ifi) (src/dpcg.f90:3-154, src-parallel/dpcg.f90) as ONE persistent cooperative kernel.
+//
+// The multi-kernel path (fc_krylov.cu) pays a kernel boundary per vector operation: three launches
+// per iteration plus, on several GPUs, a pack kernel and waits in the prologues.  On 8 GPUs an
+// iteration of the 216^3 case is ~50 us of memory traffic per GPU, so those boundaries -- not the
+// traffic -- set the time.  Here the whole solve is one launch of 148 x k co-resident CTAs:
+//
+//   * every CTA owns a fixed, contiguous range of rows for ALL phases (residual, p-update, SpMV, x/r
+//     update): a row is only ever touched by one SM, consecutive chunks share their x neighbours in
+//     L1, and when the partition is small enough the vectors stay in L2 while the matrix streams past
+//     them (evict-first).  Ranges are equal shares of a cost that counts a row with processor faces
+//     twice (fc_row_range), so the CTAs on a partition boundary finish with the others;
+//   * the SpMV is the TMA pipeline of fc_spmv_pipe.cuh; the first chunks of the next product are
+//     requested before the reductions, so the copy engine works through the barriers;
+//   * three grid barriers per iteration (dpcg.f90:85-142): after the p-update (the product gathers
+//     other CTAs' rows), and one per inner product.  The CTA that arrives last adds the per-CTA
+//     partial sums in a fixed order (deterministic, no float atomics), runs the scalar recurrence
+//     (alpha, beta, convergence test) and releases the others;
+//   * several GPUs (P2P mode, fc_p2p.cu): the p-update stores the boundary values of p straight
+//     into the neighbours' halo slots over NVLink and the barrier's last CTA raises their arrival
+//     flags; only rows with processor faces wait for a flag.  An inner product's last CTA posts the
+//     rank's partial sums to every rank's mailbox and adds all mailboxes in rank order (global_sum
+//     of src-parallel, bit-identical on all ranks) before it releases its own grid.
+// Every wait is bounded (fc_spin_guard): a lost peer surfaces as a CUDA error, not as a hung GPU.
+#include <cooperative_groups.h>
+
+#include "fc_spmv_pipe.cuh"
+
+namespace {
+
+struct persist_args {
+  fc_spmv_mat M;
+  const double *su;
+  double *fi, *pk, *zk, *res, *adiag;
+  const int *diag;
+  double padd, tol;
+  fc_strip st;
+  const int *bufind;
+  fc_scalars *sc;
+  fc_persist_state *ps;
+  double *partials;
+  fc_p2p_dev *p2p;
+  unsigned long long red_seq0, halo_seq0;
+  double *hist;
+};
+
+enum { PH_PUPDATE = 0, PH_SPMV = 1, PH_UPDATE = 2, PH_SETUP = 3 };
+
+struct sync_ctx {
+  unsigned long long my_gen;
+  bool *s_last;
+  double *s_red;
+};
+
+// thread 0 of a CTA that is not the last: wait for the release of barrier `my_gen`
+__device__ __forceinline__ void wait_release(fc_persist_state *ps, unsigned long long my_gen) {
+  fc_spin_guard g;
+  while (fc_ld_acquire_gpu(&ps->gen) <= my_gen) g.tick();
+}
+
+// last CTA, thread 0: book-keeping of the phase clocks, then open the barrier
+__device__ __forceinline__ void release_barrier(fc_persist_state *ps, unsigned long long my_gen, int phase,
+                                                unsigned long long t_arrive) {
+  ps->t_phase[phase] += t_arrive - ps->t_mark;
+  const unsigned long long now = fc_globaltimer();
+  ps->t_mark = now;
+  ps->t_total = now - ps->t_start;
+  ps->count = 0u;
+  __threadfence();
+  fc_st_release_gpu(&ps->gen, my_gen + 1ull);
+}
+
+// plain grid barrier; `hseq` != 0: the last CTA raises the neighbours' halo-arrival flags first
+__device__ __forceinline__ void grid_barrier(const persist_args &A, sync_ctx &S, int phase, unsigned long long hseq,
+                                             bool sent_remote) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // one fence per CTA covers the block's stores (ordered before it by the block barrier); CTAs that stored
+    // halo values into a neighbour's memory fence at system scope
+    if (sent_remote) __threadfence_system();
+    else __threadfence();
+    const unsigned t = atomicAdd(&A.ps->count, 1u);
+    if (t == gridDim.x - 1) {
+      const unsigned long long t_arrive = fc_globaltimer();
+      if (hseq && A.p2p) {   // every CTA's halo stores are ordered before its arrival: one fence, then the flags
+        __threadfence_system();
+        for (int c = 0; c < A.p2p->nconn; ++c) fc_st_relaxed_sys(A.p2p->peer_hflag[c], hseq);
+      } else {
+        __threadfence();
+      }
+      release_barrier(A.ps, S.my_gen, phase, t_arrive);
+    } else {
+      wait_release(A.ps, S.my_gen);
+    }
+    __threadfence();
+  }
+  S.my_gen++;
+  __syncthreads();
+}
+
+// grid barrier that carries a reduction: v[] = per-thread partial sums on entry.  The last CTA
+// finishes the sum, exchanges it with the other ranks and runs the scalar step `step`.
+template <int NR>
+__device__ __forceinline__ void grid_reduce(const persist_args &A, sync_ctx &S, double (&v)[NR], int step, int phase,
+                                            unsigned long long seq) {
+  const int G = gridDim.x;
+  __shared__ unsigned long long s_tarr;
+  fc_block_sum<NR>(v, S.s_red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) A.partials[r * G + blockIdx.x] = v[r];
+    __threadfence();
+    const unsigned t = atomicAdd(&A.ps->count, 1u);
+    *S.s_last = (t == (unsigned)G - 1u);
+    if (*S.s_last) s_tarr = fc_globaltimer();
+  }
+  __syncthreads();
+  if (*S.s_last) {
+    __threadfence();
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double w = 0.0;
+      for (int b = threadIdx.x; b < G; b += blockDim.x) w += __ldcg(A.partials + r * G + b);
+      v[r] = w;
+    }
+    fc_block_sum<NR>(v, S.s_red);
+    if (threadIdx.x == 0) {
+      fc_scalars *sc = A.sc;
+      if (A.p2p) {
+        const fc_p2p_dev *P = A.p2p;
+        const unsigned long long t_post = fc_globaltimer();
+        fc_mail_post(P, seq, v, NR);
+        double t[NR];
+        fc_mail_collect<NR>(P, seq, NR, t);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) v[i] = t[i];
+        A.ps->t_mail += fc_globaltimer() - t_post;
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) sc->red[r] = v[r];
+      fc_scalar_step(sc, step, A.hist);
+      if (step == STEP_RES0_SK && A.tol >= 0.0 && sc->res0 < A.tol) sc->done = 1;   // dpcg.f90:66-70
+      release_barrier(A.ps, S.my_gen, phase, s_tarr);
+    }
+  } else if (threadIdx.x == 0) {
+    wait_release(A.ps, S.my_gen);
+  }
+  if (threadIdx.x == 0) __threadfence();
+  S.my_gen++;
+  __syncthreads();
+}
+
+template <int T, int CAP, int S, bool STRIP>
+__global__ void __launch_bounds__(T)
+k_dpcg_persist(persist_args A) {
+  extern __shared__ __align__(128) unsigned char fc_smem_raw[];
+  __shared__ double s_red[64];
+  __shared__ bool s_last;
+  // connection table of the halo stores (P2P mode)
+  __shared__ int s_conn_off[FC_MAX_CONN + 1];
+  __shared__ double *s_peer_pk[FC_MAX_CONN];
+  const int tid = threadIdx.x;
+  const int n = A.M.n;
+  fc_scalars *sc = A.sc;
+  sync_ctx SY{fc_ld_acquire_gpu(&A.ps->gen), &s_last, s_red};
+
+  fc_spmv_pipe<T, CAP, S> pipe;
+  auto *sm = reinterpret_cast<fc_spmv_smem<T, CAP, S> *>(fc_smem_raw);
+  int rbeg, rend;
+  fc_row_range(n, STRIP ? A.st.off : nullptr, &rbeg, &rend);
+  pipe.init(sm, A.M.ioffset, rbeg, rend, STRIP ? A.st.off : nullptr);
+  pipe.prefetch(A.M);
+  const bool p2p = STRIP && A.p2p != nullptr;
+  if (p2p) {
+    if (tid <= A.p2p->nconn) s_conn_off[tid] = A.p2p->conn_off[tid];
+    if (tid < A.p2p->nconn) s_peer_pk[tid] = A.p2p->peer_pk[tid];
+    __syncthreads();
+  }
+  const int nch = pipe.nch;
+  fc_strip st = A.st;
+  st.hseq = 0ull;   // the residual uses fi's halo as it is (src-parallel/dpcg.f90:58-66)
+  unsigned long long red_seq = A.red_seq0, halo_seq = A.halo_seq0;
+
+  // ---- res = su - A fi ; res0 = sum|res| ; sk = sum res*res/(a_ii[+small])   (dpcg.f90:51-90) ----
+  {
+    fc_spmv_vec V{A.fi, A.res, A.su, nullptr, A.diag, A.adiag, A.padd};
+    double v[2] = {0.0, 0.0};
+    pipe.template sweep<FC_MODE_RESID_SK, STRIP>(A.M, V, st, v[0], v[1]);
+    pipe.prefetch(A.M);
+    grid_reduce<2>(A, SY, v, STEP_RES0_SK, PH_SETUP, ++red_seq);
+  }
+
+  while (!__ldcg(&sc->done)) {
+    // ---- pk = res/(a_ii[+small]) + bet*pk   (dpcg.f90:95-100); exchange(pk) (src-parallel/dpcg.f90:114): the
+    //      owner of a cell on a processor boundary stores its new value straight into the neighbour's halo ----
+    {
+      const double bet = __ldcg(&sc->sk) / __ldcg(&sc->s0);
+      int i = rbeg + tid, j = 0;
+      for (; i + 3 * T < rend; i += 4 * T, j += 4) {
+        const double r0 = A.res[i], r1 = A.res[i + T], r2 = A.res[i + 2 * T], r3 = A.res[i + 3 * T];
+        const double d0 = A.adiag[i], d1 = A.adiag[i + T], d2 = A.adiag[i + 2 * T], d3 = A.adiag[i + 3 * T];
+        const double p0 = A.pk[i], p1 = A.pk[i + T], p2 = A.pk[i + 2 * T], p3 = A.pk[i + 3 * T];
+        A.pk[i] = r0 / (d0 + A.padd) + bet * p0;
+        A.pk[i + T] = r1 / (d1 + A.padd) + bet * p1;
+        A.pk[i + 2 * T] = r2 / (d2 + A.padd) + bet * p2;
+        A.pk[i + 3 * T] = r3 / (d3 + A.padd) + bet * p3;
+      }
+      for (; i < rend; i += T) A.pk[i] = A.res[i] / (A.adiag[i] + A.padd) + bet * A.pk[i];
+      if (p2p && pipe.cta_strip) {
+        // my cells on a processor boundary: their new values go straight into the neighbours' halo slots
+        __syncthreads();
+        for (j = 0; j < nch; j += 2) {   // two chunks at a time: the load chains of the two rows overlap
+          int row[2], q0[2], q1[2], f[2];
+          double v[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            row[u] = rbeg + (j + u) * T + tid;
+            const bool act = j + u < nch && sm->cs[j + u] && row[u] < rend;
+            q0[u] = act ? A.st.off[row[u]] : 0;
+            q1[u] = act ? A.st.off[row[u] + 1] : 0;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (q1[u] > q0[u]) {
+              f[u] = A.st.idx[q0[u]];
+              v[u] = A.pk[row[u]];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            for (int q = q0[u]; q < q1[u]; ++q) {
+              const int ff = q == q0[u] ? f[u] : A.st.idx[q];
+              int c = 0;
+              while (ff >= s_conn_off[c + 1]) ++c;
+              s_peer_pk[c][ff - s_conn_off[c]] = v[u];
+            }
+          }
+        }
+      }
+    }
+    ++halo_seq;
+    grid_barrier(A, SY, PH_PUPDATE, p2p ? halo_seq : 0ull, p2p && pipe.cta_strip);
+
+    // ---- zk = A pk ; pkapk = pk.zk   (dpcg.f90:105-119) ----
+    {
+      if (p2p) {
+        st.hseq = halo_seq;
+        pipe.halo_pending = pipe.cta_strip;   // only CTAs that own rows with processor faces wait
+      }
+      fc_spmv_vec V{A.pk, A.zk, nullptr, A.pk, nullptr, nullptr, 0.0};
+      double v[1] = {0.0};
+      double unused = 0.0;
+      pipe.template sweep<FC_MODE_DOT, STRIP>(A.M, V, st, v[0], unused);
+      pipe.prefetch(A.M);   // the next product's first chunks load behind the two reductions
+      grid_reduce<1>(A, SY, v, STEP_PKAPK, PH_SPMV, ++red_seq);
+    }
+
+    // ---- fi += alf*pk ; res -= alf*zk ; resl = sum|res| ; next sk   (dpcg.f90:121-142) ----
+    {
+      const double alf = __ldcg(&sc->sk) / __ldcg(&sc->pkapk);
+      double a0 = 0.0, a1 = 0.0;
+      int i = rbeg + tid;
+      for (; i + T < rend; i += 2 * T) {
+        const double f0 = A.fi[i], f1 = A.fi[i + T];
+        const double p0 = A.pk[i], p1 = A.pk[i + T];
+        const double r0 = A.res[i], r1 = A.res[i + T];
+        const double z0 = A.zk[i], z1 = A.zk[i + T];
+        const double d0 = A.adiag[i], d1 = A.adiag[i + T];
+        A.fi[i] = f0 + alf * p0;
+        A.fi[i + T] = f1 + alf * p1;
+        const double n0 = r0 - alf * z0, n1 = r1 - alf * z1;
+        A.res[i] = n0;
+        A.res[i + T] = n1;
+        a0 += fabs(n0);
+        a1 += n0 * (n0 / (d0 + A.padd));
+        a0 += fabs(n1);
+        a1 += n1 * (n1 / (d1 + A.padd));
+      }
+      for (; i < rend; i += T) {
+        A.fi[i] = A.fi[i] + alf * A.pk[i];
+        const double r = A.res[i] - alf * A.zk[i];
+        A.res[i] = r;
+        a0 += fabs(r);
+        a1 += r * (r / (A.adiag[i] + A.padd));
+      }
+      double v[2] = {a0, a1};
+      grid_reduce<2>(A, SY, v, STEP_CG_UPDATE_SK, PH_UPDATE, ++red_seq);
+    }
+  }
+  pipe.drain();   // no CTA may exit with bulk copies in flight
+}
+
+template <int T, int CAP, int S, bool STRIP>
+int launch_persist(fc_context *ctx, persist_args &A, bool *ok) {
+  auto kern = k_dpcg_persist<T, CAP, S, STRIP>;
+  const size_t smem = sizeof(fc_spmv_smem<T, CAP, S>);
+  static int per_sm = -1;
+  if (per_sm < 0) {
+    FC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
+    if (per_sm < 1) per_sm = 0;
+  }
+  int use = per_sm;
+  if (ctx->tune_ctas_per_sm > 0 && ctx->tune_ctas_per_sm < use) use = ctx->tune_ctas_per_sm;
+  if (use == 0) { *ok = false; return FC_OK; }
+  int sms = FC_SMS;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const long long groups = ((long long)A.M.n + 31) / 32;
+  long long grid = (long long)sms * use;
+  if (grid > groups) grid = groups;
+  if (grid < 1) grid = 1;
+  // largest row range of a CTA (one without processor faces) must fit the chunk table
+  const long long rows_per_cta = (((long long)A.M.n + ctx->npro + grid - 1) / grid / 32 + 2) * 32;
+  if ((rows_per_cta + T - 1) / T > FC_KB_MAX || grid * FC_MAX_RED > (long long)FC_MAX_RED * 2048) {
+    *ok = false;
+    return FC_OK;
+  }
+  void *args[] = {(void *)&A};
+  FC_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(T), args, smem, ctx->stream));
+  ctx->launches++;
+  ctx->tm.persist_grid = (int)grid;
+  *ok = true;
+  return FC_OK;
+}
+
+__global__ void k_persist_begin(fc_persist_state *ps) {
+  ps->count = 0u;
+  for (int i = 0; i < 4; ++i) ps->t_phase[i] = 0ull;
+  const unsigned long long now = fc_globaltimer();
+  ps->t_start = now;
+  ps->t_mark = now;
+  ps->t_total = 0ull;
+  ps->t_mail = 0ull;
+}
+
+}  // namespace
+
+// `handled` = false: the caller must run the multi-kernel path (NCCL mode, a CSR pattern whose rows
+// do not fit the staging buffers, no cooperative launch).
+int fc_dpcg_persistent(fc_context *ctx, double *fi, const fc_solver_opts *o, fc_solver_report *rep, double *hist,
+                       bool *handled) {
+  *handled = false;
+  if (!ctx->tune_persist) return FC_OK;
+  if (ctx->nranks > 1 && !ctx->p2p) return FC_OK;
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+  if (!coop) return FC_OK;
+  const int n = ctx->n;
+  cudaStream_t st = ctx->stream;
+  persist_args A{};
+  A.M = fc_spmv_mat{n, ctx->ioffset, ctx->ja, ctx->field[FC_A]};
+  A.su = ctx->field[FC_SU];
+  A.fi = fi; A.pk = ctx->pk; A.zk = ctx->zk; A.res = ctx->field[FC_RES]; A.adiag = ctx->adiag;
+  A.diag = ctx->diag;
+  A.padd = o->parallel ? o->small : 0.0;
+  A.tol = o->tol;
+  A.st = fc_strip{ctx->strip_off, ctx->strip_idx, ctx->field[FC_APR], ctx->strip_any32, n, nullptr, 0ull, 0};
+  if (ctx->p2p) {
+    A.st.hflag = (const unsigned long long *)((const char *)ctx->arena + ctx->arena_hflag_off);
+    A.st.nconn = (int)ctx->nbr_rank.size();
+  }
+  A.bufind = ctx->bufind;
+  A.sc = ctx->sc;
+  A.ps = ctx->persist;
+  A.partials = ctx->partials;
+  A.p2p = ctx->p2p ? ctx->p2p_dev : nullptr;
+  A.red_seq0 = ctx->red_seq;
+  A.halo_seq0 = ctx->halo_seq;
+  A.hist = hist;
+
+  FC_CUDA(cudaMemsetAsync(ctx->pk, 0, sizeof(double) * ((size_t)n + ctx->npro), st));
+  k_persist_begin<<<1, 1, 0, st>>>(ctx->persist);
+  FC_LAUNCH_CHECK();
+  const bool strip = ctx->npro > 0;
+  bool ok = false;
+#define FC_PERSIST(T, CAP, S)                                                     \
+  do {                                                                            \
+    if (strip) FC_CHECK((launch_persist<T, CAP, S, true>(ctx, A, &ok)));          \
+    else       FC_CHECK((launch_persist<T, CAP, S, false>(ctx, A, &ok)));         \
+  } while (0)
+  if (ctx->spmv_max_chunk <= 2000) {
+    switch (ctx->tune_pipe) {
+      case 1: FC_PERSIST(256, 2304, 2); break;
+      case 2: FC_PERSIST(256, 2048, 2); break;
+      case 3: FC_PERSIST(128, 1024, 2); break;
+      default: FC_PERSIST(256, 2304, 3); break;
+    }
+  } else {
+    FC_PERSIST(256, 4096, 2);
+  }
+#undef FC_PERSIST
+  if (!ok) return FC_OK;
+  FC_CUDA(cudaMemcpyAsync(ctx->sc_host, ctx->sc, sizeof(fc_scalars), cudaMemcpyDeviceToHost, st));
+  FC_CUDA(cudaMemcpyAsync(ctx->persist_host, ctx->persist, sizeof(fc_persist_state), cudaMemcpyDeviceToHost, st));
+  FC_CUDA(cudaStreamSynchronize(st));
+  rep->res0 = ctx->sc_host->res0;
+  rep->resl = ctx->sc_host->resl;
+  rep->iters = ctx->sc_host->iters;
+  // the sequence numbers the kernel consumed (identical on every rank)
+  ctx->red_seq += 1ull + 2ull * (unsigned long long)rep->iters;
+  ctx->halo_seq += (unsigned long long)rep->iters;
+  const fc_persist_state &ps = *ctx->persist_host;
+  ctx->tm.persist_ms = 1e-6 * (double)ps.t_total;
+  ctx->tm.persist_pupdate_ms = 1e-6 * (double)ps.t_phase[PH_PUPDATE];
+  ctx->tm.persist_spmv_ms = 1e-6 * (double)ps.t_phase[PH_SPMV];
+  ctx->tm.persist_update_ms = 1e-6 * (double)ps.t_phase[PH_UPDATE];
+  ctx->tm.persist_mail_ms = 1e-6 * (double)ps.t_mail;
+  ctx->tm.persist_iters = rep->iters;
+  if (rep->iters > 0) {
+    ctx->tm.spmv_ms = ctx->tm.persist_spmv_ms / rep->iters;
+    ctx->tm.spmv_samples = rep->iters;
+  }
+  *handled = true;
+  return FC_OK;
+}

@@ -34,10 +34,12 @@ struct fc_scalars {
 
 // ---- peer-to-peer (NVLink) communication state, see fc_p2p.cu ----
 constexpr int FC_MAX_RANKS = 16, FC_MAX_CONN = 16, FC_MAIL_SLOTS = 4;
-struct fc_mail {                        // one rank's contribution to one reduction, written by that rank
-  double v[4];
-  unsigned long long seq;
-  unsigned long long pad[3];
+// One rank's contribution to one reduction, written by that rank straight into every rank's copy.  Every FP64
+// value travels as two 8-byte words {32 bits of the value | 32-bit sequence number}: an 8-byte store is atomic,
+// so a word whose sequence half matches is complete and no fence or separate flag is needed between data and
+// "ready" (one NVLink flight per reduction instead of store - fence - flag).
+struct fc_mail {
+  unsigned long long w[2 * FC_MAX_RED];
 };
 struct fc_p2p_dev {                     // device-resident tables read by the kernels
   int rank, nranks, nconn, pad;
@@ -55,6 +57,19 @@ struct fc_sync {                        // per-launch synchronisation descriptor
   unsigned long long post_seq;          // sequence number of the reduction this kernel produces
   int local, pad;                       // 1: single rank, the finalising thread runs the scalar step itself
   double *hist;
+};
+
+// grid barrier and phase clocks of the persistent DPCG kernel (fc_dpcg_persist.cu)
+struct fc_persist_state {
+  unsigned int count;                   // arrivals at the current barrier
+  unsigned int pad0;
+  unsigned long long gen;               // barriers completed so far
+  unsigned long long t_mark;            // globaltimer at the last barrier release
+  unsigned long long t_phase[4];        // accumulated ns: p-update, SpMV, x/r update, (spare)
+  unsigned long long t_total;           // ns from kernel start to the last release
+  unsigned long long t_start;
+  unsigned long long t_mail;            // ns the reducing CTA waited for the other ranks' partial sums
+  unsigned long long pad1[5];
 };
 
 struct fc_levels {                      // level schedule of the strict lower / upper triangle
@@ -124,6 +139,7 @@ struct fc_context {
   int *bufind = nullptr;                // owner cell of every processor face (exchange.f90:48-50)
   double *sendbuf = nullptr;
   int *strip_off = nullptr, *strip_idx = nullptr;  // per-row processor faces (apr strip of the SpMV)
+  unsigned char *strip_any32 = nullptr;            // [ceil(n/32)] 1 when one of the 32 rows has processor faces
   // peer-to-peer mode (fc_p2p.cu): reductions and the Krylov halo go over mapped peer memory
   bool p2p = false;
   void *arena = nullptr;                // IPC-shared allocation: mailboxes, flags, pk, zk
@@ -132,6 +148,14 @@ struct fc_context {
   std::vector<void *> peer_base;        // opened peer arenas
   unsigned long long red_seq = 0, halo_seq = 0, halo_wait = 0;
   struct { unsigned long long seq; int step, count; } pending = {0, 0, 0};
+
+  // ---- tuning (fc_set_tuning) ----
+  int tune_spmv = 2;                    // 0: CSR-stream kernel, 1: TMA-staged pipeline, 2: by size (measured cross-over)
+  int tune_persist = 1;                 // 1: DPCG as one persistent cooperative kernel
+  int tune_pipe = 1;                    // staging geometry of the TMA pipeline (threads, capacity, stages)
+  int tune_ctas_per_sm = 0;             // persistent kernel: CTAs per SM (0 = as many as fit)
+  fc_persist_state *persist = nullptr;  // device: grid barrier + phase clocks of the persistent kernel
+  fc_persist_state *persist_host = nullptr;
 
   // ---- timing ----
   cudaEvent_t ev[4] = {};
@@ -181,7 +205,8 @@ template <class T>
 static inline int fc_dev_alloc(fc_context *ctx, T **p, size_t count) {
   if (*p) { cudaFree(*p); *p = nullptr; }
   if (count == 0) count = 1;
-  FC_CUDA(cudaMalloc((void **)p, count * sizeof(T)));
+  // 64 spare bytes: the bulk copies of the SpMV pipeline read whole 16-byte groups
+  FC_CUDA(cudaMalloc((void **)p, count * sizeof(T) + 64));
   return FC_OK;
 }
 
@@ -210,5 +235,7 @@ int fc_strip_build(fc_context *ctx);
 int fc_p2p_pack(fc_context *ctx, double *x);                          // fc_p2p.cu: halo of pk / zk by peer stores
 void fc_p2p_close(fc_context *ctx);                                 // fc_csr.cu: per-row processor faces
 int fc_allreduce_scalars(fc_context *ctx, double *dev, int count);
+int fc_dpcg_persistent(fc_context *ctx, double *fi, const fc_solver_opts *o, fc_solver_report *rep, double *hist,
+                       bool *handled);                                                   // fc_dpcg_persist.cu
 int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opts *o, fc_solver_report *rep,
                     double *hist);

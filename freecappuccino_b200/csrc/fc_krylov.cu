@@ -252,6 +252,28 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
   flow_t fl{ctx, hist};
   ctx->pending = {0, 0, 0};
   ctx->halo_wait = 0;
+  ctx->tm.persist_ms = ctx->tm.persist_pupdate_ms = ctx->tm.persist_spmv_ms = ctx->tm.persist_update_ms = 0.0;
+  ctx->tm.persist_iters = ctx->tm.persist_grid = 0;
+  ctx->tm.persist_mail_ms = 0.0;
+  if (solver == FC_DPCG) {   // the whole solve as one persistent kernel (fc_dpcg_persist.cu)
+    bool handled = false;
+    FC_CHECK(fc_dpcg_persistent(ctx, fi, o, rep, hist, &handled));
+    if (handled) {
+      FC_CUDA(cudaEventRecord(ctx->ev[1], st));
+      if (ctx->npro > 0 && !(o->tol >= 0.0 && rep->res0 < o->tol))
+        FC_CHECK(fc_halo_exchange(ctx, fi));  // src-parallel/dpcg.f90:173
+      FC_CUDA(cudaStreamSynchronize(st));
+      if (hist) {
+        if (rep->iters > 0)
+          FC_CUDA(cudaMemcpy(hist_host, hist, sizeof(double) * (size_t)rep->iters, cudaMemcpyDeviceToHost));
+        cudaFree(hist);
+      }
+      float ms = 0.f;
+      FC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+      ctx->tm.solve_ms = ms;
+      return FC_OK;
+    }
+  }
   // res = su - A fi, res0 = sum|res|   (dpcg.f90:51-64; the parallel twin uses fi's halo as it is)
   FC_CHECK(fc_launch_residual(ctx, a, su, fi, res, ctx->adiag, fl.next(STEP_RES0, 1)));
   FC_CHECK(fl.reduced(STEP_RES0, 1));

@@ -4,6 +4,7 @@
 // (grid, block) configuration always produces the same bits.
 #pragma once
 #include "fc_internal.cuh"
+#include "fc_tma.cuh"
 
 // Scalar recurrences executed once per reduction, either by the finalising thread
 // (single GPU) or by k_scalar_step after the NCCL all-reduce (src-parallel: every
@@ -158,14 +159,50 @@ __device__ __forceinline__ void fc_st_release_gpu(unsigned long long *p, unsigne
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ void fc_st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long fc_ld_relaxed_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// post `count` partial sums of reduction `seq` to every rank (my own copy included)
 __device__ __forceinline__ void fc_mail_post(const fc_p2p_dev *P, unsigned long long seq, const double *v, int count) {
   const int slot = (int)(seq % FC_MAIL_SLOTS);
-  for (int q = 0; q < P->nranks; ++q) {
-    volatile double *dst = P->peer_mail[q][slot * FC_MAX_RANKS + P->rank].v;
-    for (int i = 0; i < count; ++i) dst[i] = v[i];
+  const unsigned long long tag = (seq & 0xffffffffull) << 32;
+  for (int i = 0; i < count; ++i) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v[i]);
+    const unsigned long long lo = (bits & 0xffffffffull) | tag, hi = (bits >> 32) | tag;
+    for (int q = 0; q < P->nranks; ++q) {
+      unsigned long long *dst = P->peer_mail[q][slot * FC_MAX_RANKS + P->rank].w;
+      fc_st_relaxed_sys(dst + 2 * i, lo);
+      fc_st_relaxed_sys(dst + 2 * i + 1, hi);
+    }
   }
-  __threadfence_system();
-  for (int q = 0; q < P->nranks; ++q) fc_st_release_sys(&P->peer_mail[q][slot * FC_MAX_RANKS + P->rank].seq, seq);
+}
+
+// wait for every rank's partial sums of reduction `seq` and add them in rank order (global_sum of src-parallel;
+// the same order on every rank, so all ranks hold bit-identical totals)
+template <int NMAX>
+__device__ __forceinline__ void fc_mail_collect(const fc_p2p_dev *P, unsigned long long seq, int count, double (&t)[NMAX]) {
+  const fc_mail *box = P->mail + (seq % FC_MAIL_SLOTS) * FC_MAX_RANKS;
+  const unsigned long long tag = seq & 0xffffffffull;
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) t[i] = 0.0;
+  fc_spin_guard g;
+  for (int r = 0; r < P->nranks; ++r) {
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) {
+      if (i < count) {
+        unsigned long long lo, hi;
+        while (((lo = fc_ld_relaxed_sys(box[r].w + 2 * i)) >> 32) != tag) g.tick();
+        while (((hi = fc_ld_relaxed_sys(box[r].w + 2 * i + 1)) >> 32) != tag) g.tick();
+        t[i] = t[i] + __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+      }
+    }
+  }
 }
 
 // Kernel prologue.  Returns false when the solve has converged (the kernel must return at once).
@@ -175,19 +212,15 @@ __device__ __forceinline__ bool fc_kernel_begin(fc_scalars *sc, const fc_sync &s
     if (threadIdx.x == 0) {
       if (blockIdx.x == 0) {
         if (!((volatile fc_scalars *)sc)->done) {
-          const fc_p2p_dev *P = sy.p2p;
-          const fc_mail *box = P->mail + (sy.wait_seq % FC_MAIL_SLOTS) * FC_MAX_RANKS;
-          double t[FC_MAX_RED] = {0.0, 0.0, 0.0, 0.0};
-          for (int r = 0; r < P->nranks; ++r) {      // rank order: identical sums on every rank
-            while (fc_ld_acquire_sys(&box[r].seq) < sy.wait_seq) {}
-            for (int i = 0; i < sy.wait_count; ++i) t[i] = t[i] + ((volatile const double *)box[r].v)[i];
-          }
+          double t[FC_MAX_RED];
+          fc_mail_collect<FC_MAX_RED>(sy.p2p, sy.wait_seq, sy.wait_count, t);
           for (int i = 0; i < sy.wait_count; ++i) sc->red[i] = t[i];
           fc_scalar_step(sc, sy.wait_step, sy.hist);
         }
         fc_st_release_gpu(&sc->applied, sy.wait_seq);
       } else {
-        while (fc_ld_acquire_gpu(&sc->applied) < sy.wait_seq) {}
+        fc_spin_guard g;
+        while (fc_ld_acquire_gpu(&sc->applied) < sy.wait_seq) g.tick();
       }
     }
     __syncthreads();

@@ -10,22 +10,13 @@
 //            summation order, so y is bit-identical to the Fortran loop.
 // Algorithmic traffic: 12 B per non-zero + 20 B per row (ioffset 4, x 8, y 8); x is
 // gathered through L1/L2, every x element is used by its ~7 neighbouring rows.
-#include "fc_reduce.cuh"
+#include "fc_spmv_pipe.cuh"
 
 namespace {
 
-enum { MODE_SPMV = 0, MODE_DOT = 1, MODE_RESID = 2, MODE_DOT2 = 3 };  // DOT: w.y ; DOT2: w.y and y.y
+enum { MODE_SPMV = FC_MODE_SPMV, MODE_DOT = FC_MODE_DOT, MODE_RESID = FC_MODE_RESID, MODE_DOT2 = FC_MODE_DOT2 };
 
-struct strip_t {               // processor-boundary coupling kept outside the CSR (src-parallel `apr`)
-  const int *off;              // [n+1] per-row range into idx, or nullptr on a single rank
-  const int *idx;              // processor-face index i (0-based, ascending per row)
-  const double *apr;           // [npro]
-  int halo0;                   // x[halo0 + i] = value on the other rank
-  // P2P mode: the neighbours store the halo of x themselves (fc_p2p.cu) and raise hflag[c] to hseq
-  const unsigned long long *hflag;
-  unsigned long long hseq;
-  int nconn;
-};
+using strip_t = fc_strip;
 
 template <int ROWS, int CAP, int MODE, bool STRIP>
 __global__ void __launch_bounds__(ROWS)
@@ -68,15 +59,18 @@ k_spmv(int n, const int *__restrict__ ioffset, const int *__restrict__ ja, const
         }
       }
       if (STRIP) {
-        const int q0 = st.off[r], q1 = st.off[r + 1];
-        if (q1 > q0 && st.hseq) {   // rows with processor faces wait for the neighbours' stores; the rest overlap them
-          for (int c = 0; c < st.nconn; ++c)
-            while (fc_ld_acquire_sys(st.hflag + c) < st.hseq) {}
-        }
-        for (int q = q0; q < q1; ++q) {
-          const int i = st.idx[q];
-          double t = st.apr[i] * __ldcg(x + st.halo0 + i);
-          v = (MODE == MODE_RESID) ? v - t : v + t;
+        if (st.any32[r >> 5]) {
+          const int q0 = st.off[r], q1 = st.off[r + 1];
+          if (q1 > q0 && st.hseq) {   // rows with processor faces wait for the neighbours' stores; the rest overlap them
+            fc_spin_guard g;
+            for (int c = 0; c < st.nconn; ++c)
+              while (fc_ld_acquire_sys(st.hflag + c) < st.hseq) g.tick();
+          }
+          for (int q = q0; q < q1; ++q) {
+            const int i = st.idx[q];
+            double t = st.apr[i] * __ldcg(x + st.halo0 + i);
+            v = (MODE == MODE_RESID) ? v - t : v + t;
+          }
         }
       }
       y[r] = v;
@@ -98,21 +92,98 @@ k_spmv(int n, const int *__restrict__ ioffset, const int *__restrict__ ja, const
   }
 }
 
+// The same product as a TMA-fed pipeline (fc_spmv_pipe.cuh): every CTA owns an equal-cost contiguous share of
+// the rows, so the grid has no tail wave.
+template <int T, int CAP, int S, int MODE, bool STRIP>
+__global__ void __launch_bounds__(T)
+k_spmv_tma(fc_spmv_mat M, fc_spmv_vec V, strip_t st, double *partials, fc_scalars *sc, int step, fc_sync sy) {
+  extern __shared__ __align__(128) unsigned char fc_smem_raw[];
+  __shared__ double s_red[64];
+  if (MODE == MODE_DOT || MODE == MODE_DOT2) {
+    if (!fc_kernel_begin(sc, sy)) return;
+  }
+  fc_spmv_pipe<T, CAP, S> pipe;
+  int rbeg, rend;
+  fc_row_range(M.n, STRIP ? st.off : nullptr, &rbeg, &rend);
+  pipe.init(reinterpret_cast<fc_spmv_smem<T, CAP, S> *>(fc_smem_raw), M.ioffset, rbeg, rend, STRIP ? st.off : nullptr);
+  pipe.prefetch(M);
+  pipe.halo_pending = STRIP && pipe.cta_strip && st.hseq != 0ull;
+  double acc = 0.0, acc2 = 0.0;
+  pipe.template sweep<MODE, STRIP>(M, V, st, acc, acc2);
+  if (MODE == MODE_DOT2) {
+    double v[2] = {acc, acc2};
+    if (fc_grid_sum<2>(v, partials, &sc->ticket[0], s_red)) fc_reduction_done<2>(sc, sy, v, step);
+  } else if (MODE != MODE_SPMV) {
+    double v[1] = {acc};
+    if (fc_grid_sum<1>(v, partials, &sc->ticket[0], s_red)) fc_reduction_done<1>(sc, sy, v, step);
+  }
+}
+
+template <int T, int CAP, int S, int MODE, bool STRIP>
+int launch_tma(fc_context *ctx, const fc_spmv_mat &M, const fc_spmv_vec &V, const strip_t &st, int step,
+               const fc_sync &sy, bool *ok) {
+  auto kern = k_spmv_tma<T, CAP, S, MODE, STRIP>;
+  const size_t smem = sizeof(fc_spmv_smem<T, CAP, S>);
+  static int per_sm = -1;   // per instantiation
+  if (per_sm < 0) {
+    FC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
+    if (per_sm < 1) per_sm = 0;
+  }
+  if (per_sm == 0) { *ok = false; return FC_OK; }
+  const long long groups = ((long long)M.n + 31) / 32;
+  long long grid = (long long)FC_SMS * per_sm;
+  if (grid > groups) grid = groups;
+  if (grid < 1) grid = 1;
+  // the chunk boundaries of a CTA must fit its shared-memory table (an unweighted share is the largest)
+  const long long rows_per_cta = (((long long)M.n + ctx->npro + grid - 1) / grid / 32 + 2) * 32;
+  if ((rows_per_cta + T - 1) / T > FC_KB_MAX) { *ok = false; return FC_OK; }
+  kern<<<(int)grid, T, smem, ctx->stream>>>(M, V, st, ctx->partials, ctx->sc, step, sy);
+  FC_LAUNCH_CHECK();
+  *ok = true;
+  return FC_OK;
+}
+
 template <int MODE>
 int launch(fc_context *ctx, const double *a, const double *x, double *y, const double *su, const double *w,
            double *adiag, int step, const fc_sync &sy) {
   const int n = ctx->n;
-  strip_t st{ctx->strip_off, ctx->strip_idx, ctx->field[FC_APR], n, nullptr, 0ull, 0};
+  strip_t st{ctx->strip_off, ctx->strip_idx, ctx->field[FC_APR], ctx->strip_any32, n, nullptr, 0ull, 0};
   if (ctx->p2p && ctx->halo_wait && (x == ctx->pk || x == ctx->zk)) {
     st.hflag = (const unsigned long long *)((const char *)ctx->arena + ctx->arena_hflag_off);
     st.hseq = ctx->halo_wait;
     st.nconn = (int)ctx->nbr_rank.size();
     ctx->halo_wait = 0;
   }
+  const bool strip = ctx->npro > 0;
+  // stand-alone launches: the pipeline wins while a launch is short (its CTAs own equal row ranges: no tail
+  // wave), the stream kernel on long launches (profiles/r01_variants.txt); inside the persistent DPCG kernel
+  // the pipeline is always used
+  if (ctx->tune_spmv == 1 || (ctx->tune_spmv == 2 && n < 4000000)) {
+    fc_spmv_mat M{n, ctx->ioffset, ctx->ja, a};
+    fc_spmv_vec V{x, y, su, w, ctx->diag, adiag};
+    bool ok = false;
+#define FC_TMA(T, CAP, S)                                                                         \
+  do {                                                                                            \
+    if (strip) FC_CHECK((launch_tma<T, CAP, S, MODE, true>(ctx, M, V, st, step, sy, &ok)));       \
+    else       FC_CHECK((launch_tma<T, CAP, S, MODE, false>(ctx, M, V, st, step, sy, &ok)));      \
+  } while (0)
+    if (ctx->spmv_max_chunk <= 2000) {   // <= 8.75 non-zeros per row: hexahedra
+      switch (ctx->tune_pipe) {
+        case 1: FC_TMA(256, 2304, 2); break;
+        case 2: FC_TMA(256, 2048, 2); break;
+        case 3: FC_TMA(128, 1024, 2); break;
+        default: FC_TMA(256, 2304, 3); break;
+      }
+    } else {                             // polyhedra (~15 per row); longer chunks fall back to global loads
+      FC_TMA(256, 4096, 2);
+    }
+#undef FC_TMA
+    if (ok) return FC_OK;
+  }
   const int nchunks = (n + 255) / 256;
   int grid = nchunks < FC_SMS * 8 ? nchunks : FC_SMS * 8;
   if (grid < 1) grid = 1;
-  const bool strip = ctx->npro > 0;
   const bool small_rows = ctx->spmv_max_chunk <= 2304;
   if (!small_rows && grid > FC_SMS * 4) grid = FC_SMS * 4;
 #define FC_SPMV_LAUNCH(CAP, STRIP)                                                                              \

@@ -1,0 +1,281 @@
+// CSR SpMV as a TMA-fed shared-memory pipeline (sm_100a), shared by the stand-alone SpMV kernels
+// (fc_spmv.cu) and the persistent DPCG kernel (fc_dpcg_persist.cu).
+//
+// A CTA owns a contiguous range of rows (fc_row_range: equal shares, rows with processor faces
+// weighted up so that the CTAs on a partition boundary get fewer of them) and walks it in chunks
+// of T rows; consecutive chunks of a CTA share most of their x neighbours, which keeps the gathers
+// in the SM's L1.  For every chunk one thread asks the copy engine for three 1-D bulk copies (cp.async.bulk): the chunk's T+1 row
+// offsets and its contiguous slices of `a` (FP64) and `ja` (int32), 12 B per non-zero, marked
+// L2 evict-first because the matrix is streamed once per product.  The copies complete on an
+// mbarrier per stage; S stages keep S-1 chunks in flight while the CTA works on one, so the HBM
+// stream never drains at the block-level synchronisation that frees a stage.  The arithmetic is
+// thread = row: thread t reads its row's a / ja from shared memory (stride = row length: odd on
+// hexahedra, conflict-free), gathers x through L1/L2 -- the 32 lanes of a warp ask for the c-th
+// neighbours of 32 consecutive cells, which a finite-volume numbering keeps (nearly) contiguous, so a
+// warp gather costs one or two L1 lines instead of the ~8 of a non-zero-per-thread mapping -- and adds
+// the products left to right: the order of the reference's loop (dpcg.f90:105-110), so y is
+// bit-identical to the Fortran result.  No thread ever loads the matrix from global memory.
+// Algorithmic HBM traffic: 12 B per non-zero + 20 B per row (ioffset 4, x 8, y 8).
+#pragma once
+#include "fc_reduce.cuh"
+#include "fc_tma.cuh"
+
+constexpr int FC_KB_MAX = 512;   // chunks per CTA whose boundaries are cached in shared memory
+
+// DOT: w.y ; DOT2: w.y and y.y ; RESID: y = su - A x, sum|y| ; RESID_SK: + sum y*y/(a_ii + padd)
+enum { FC_MODE_SPMV = 0, FC_MODE_DOT = 1, FC_MODE_RESID = 2, FC_MODE_DOT2 = 3, FC_MODE_RESID_SK = 4 };
+
+struct fc_strip {              // processor-boundary coupling kept outside the CSR (src-parallel `apr`)
+  const int *off;              // [n+1] per-row range into idx, or nullptr on a single rank
+  const int *idx;              // processor-face index i (0-based, ascending per row)
+  const double *apr;           // [npro]
+  const unsigned char *any32;  // [ceil(n/32)] 1 when one of the 32 rows has processor faces
+  int halo0;                   // x[halo0 + i] = value on the other rank
+  // P2P mode: the neighbours store the halo of x themselves and raise hflag[c] to hseq
+  const unsigned long long *hflag;
+  unsigned long long hseq;
+  int nconn;
+};
+
+struct fc_spmv_mat {
+  int n;
+  const int *ioffset, *ja;
+  const double *a;
+};
+
+struct fc_spmv_vec {
+  const double *x;
+  double *y;
+  const double *su;      // RESID: y = su - A x
+  const double *w;       // DOT / DOT2: red[0] = w.y
+  const int *diag;       // RESID: adiag[r] = a[diag[r]]
+  double *adiag;
+  double padd;           // RESID_SK: `small` of the parallel preconditioner (src-parallel/dpcg.f90:96)
+};
+
+// Rows [rbeg, rend) of CTA b out of G: equal shares of cost(r) = r + FC_STRIP_WEIGHT * (processor faces of
+// rows < r), cut at multiples of 32 rows.  A row with a processor face costs about twice an interior one
+// (strip chain in the product, remote store in the p-update), so the CTAs on a partition boundary get
+// about half as many rows and finish with the others.  Every CTA computes the same cuts.
+constexpr long long FC_STRIP_WEIGHT = 1;
+__device__ __forceinline__ int fc_row_cut(int n, const int *soff, long long b, long long G) {
+  const long long groups = ((long long)n + 31) / 32;
+  if (!soff) {
+    const long long r = (groups * b / G) * 32;
+    return (int)(r < n ? r : n);
+  }
+  const long long total = (long long)n + FC_STRIP_WEIGHT * soff[n];
+  const long long target = total / G * b + (total % G) * b / G;
+  long long lo = 0, hi = groups;   // smallest group g with cost(32 g) >= target
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    const long long r = mid * 32 < n ? mid * 32 : n;
+    if (r + FC_STRIP_WEIGHT * soff[r] >= target) hi = mid;
+    else lo = mid + 1;
+  }
+  const long long r = lo * 32;
+  return (int)(r < n ? r : n);
+}
+__device__ __forceinline__ void fc_row_range(int n, const int *soff, int *rbeg, int *rend) {
+  *rbeg = fc_row_cut(n, soff, blockIdx.x, gridDim.x);
+  *rend = blockIdx.x + 1 == gridDim.x ? n : fc_row_cut(n, soff, blockIdx.x + 1, gridDim.x);
+}
+
+template <int T, int CAP, int S>
+struct fc_spmv_smem {
+  double a[S][CAP];
+  int ja[S][CAP];
+  int off[S][T + 4];
+  unsigned long long full[S];
+  int kb0[FC_KB_MAX], kb1[FC_KB_MAX];   // first / one-past-last non-zero of every chunk this CTA owns
+  unsigned char cs[FC_KB_MAX];          // chunk contains rows with processor faces
+};
+
+template <int T, int CAP, int S>
+struct fc_spmv_pipe {
+  static_assert(CAP % 4 == 0 && T % 32 == 0, "staging sizes must keep the bulk copies 16-byte aligned");
+  using smem_t = fc_spmv_smem<T, CAP, S>;
+  smem_t *sm;
+  int rbeg, rend, nch;           // rows owned by this CTA, number of chunks
+  unsigned issued, consumed;     // running chunk counters over the kernel's life (uniform over the CTA)
+  int next;                      // next chunk of the current sweep to hand to the copy engine
+  bool halo_pending;             // set by the caller before a sweep whose halo arrives by peer stores
+  bool cta_strip;                // this CTA owns rows with processor faces
+  unsigned long long pol;
+
+  __device__ __forceinline__ int row0(int j) const { return rbeg + j * T; }
+
+  // Once per kernel.  [rbeg_, rend_) starts on a multiple of 4 rows; `soff` = per-row processor-face
+  // offsets (fc_strip::off) or nullptr.  Ends with a block barrier.
+  __device__ __forceinline__ void init(smem_t *s, const int *ioffset, int rbeg_, int rend_, const int *soff) {
+    sm = s;
+    rbeg = rbeg_;
+    rend = rend_ > rbeg_ ? rend_ : rbeg_;
+    nch = (rend - rbeg + T - 1) / T;
+    issued = consumed = 0u;
+    next = 0;
+    halo_pending = false;
+    pol = fc_policy_evict_first();
+    int any = 0;
+    for (int j = threadIdx.x; j < nch; j += blockDim.x) {
+      const int r0 = row0(j);
+      const int r1 = min(rend, r0 + T);
+      sm->kb0[j] = ioffset[r0];
+      sm->kb1[j] = ioffset[r1];
+      const unsigned char c = (soff && soff[r1] > soff[r0]) ? 1 : 0;
+      sm->cs[j] = c;
+      any |= c;
+    }
+    if (threadIdx.x == 0) {
+      for (int s2 = 0; s2 < S; ++s2) fc_mbar_init(&sm->full[s2], 1u);
+      fc_mbar_init_fence();
+    }
+    cta_strip = __syncthreads_or(any) != 0;
+  }
+
+  // all threads call; thread 0 talks to the copy engine
+  __device__ __forceinline__ void issue_one(const fc_spmv_mat &M) {
+    const int j = next++;
+    const unsigned st = issued % S;
+    issued++;
+    if (threadIdx.x == 0) {
+      const int r0 = row0(j);
+      const int nr = min(T, rend - r0);
+      const int k0 = sm->kb0[j], k1 = sm->kb1[j];
+      const int ka = k0 & ~3, cnt = ((k1 + 3) & ~3) - ka;
+      const unsigned off_bytes = ((unsigned)(nr + 1) * 4u + 15u) & ~15u;
+      const bool staged = cnt <= CAP && cnt > 0;
+      fc_mbar_expect_tx(&sm->full[st], off_bytes + (staged ? (unsigned)cnt * 12u : 0u));
+      fc_bulk_g2s(sm->off[st], M.ioffset + r0, off_bytes, &sm->full[st]);
+      if (staged) {
+        fc_bulk_g2s(sm->a[st], M.a + ka, (unsigned)cnt * 8u, &sm->full[st], pol);
+        fc_bulk_g2s(sm->ja[st], M.ja + ka, (unsigned)cnt * 4u, &sm->full[st], pol);
+      }
+    }
+  }
+
+  // start of a sweep: fill the pipeline (may be called long before sweep(); the matrix does not
+  // depend on x, so a Krylov loop prefetches the next product's first chunks behind its barriers)
+  __device__ __forceinline__ void prefetch(const fc_spmv_mat &M) {
+    while (next < nch && next < S) issue_one(M);
+  }
+
+  // wait for copies that will never be consumed (a CTA must not exit with copies in flight)
+  __device__ __forceinline__ void drain() {
+    while (consumed < issued) {
+      fc_mbar_wait(&sm->full[consumed % S], (consumed / S) & 1u);
+      consumed++;
+    }
+    next = 0;
+  }
+
+  // y = A x over the CTA's rows (prefetch() must have been called for this sweep)
+  template <int MODE, bool STRIP>
+  __device__ __forceinline__ void sweep(const fc_spmv_mat &M, const fc_spmv_vec &V, const fc_strip &st, double &acc,
+                                        double &acc2) {
+    const int tid = threadIdx.x;
+    constexpr bool RES = (MODE == FC_MODE_RESID || MODE == FC_MODE_RESID_SK);
+    for (int j = 0; j < nch; ++j) {
+      const unsigned sg = consumed % S, par = (consumed / S) & 1u;
+      consumed++;
+      const int r0 = row0(j);
+      const int nr = min(T, rend - r0);
+      const int r = r0 + tid;
+      // ---- processor-boundary strip of the row, requested BEFORE the wait for the matrix chunk: the chain
+      //      strip_off -> strip_idx -> (apr, halo of x) then overlaps the chunk's own loads.  Only chunks that
+      //      contain rows with processor faces pay for it. ----
+      int sq0 = 0, sq1 = 0;
+      double sap = 0.0, sxh = 0.0;
+      if (STRIP && sm->cs[j]) {
+        if (halo_pending) {
+          // P2P mode: the neighbours store the halo of x themselves.  The CTA waits for their flags once per
+          // sweep, at its first chunk with processor faces; everything before overlaps the transfer.  One
+          // thread polls (an acquire at system scope is expensive), the others follow through the barrier.
+          if (tid == 0) {
+            fc_spin_guard gd;
+            for (int c = 0; c < st.nconn; ++c)
+              while (fc_ld_relaxed_sys(st.hflag + c) < st.hseq) gd.tick();
+            __threadfence_system();   // acquire: the halo values precede the flags
+          }
+          __syncthreads();
+          halo_pending = false;
+        }
+        if (tid < nr) {
+          sq0 = st.off[r];
+          sq1 = st.off[r + 1];
+          if (sq1 > sq0) {
+            const int i = st.idx[sq0];
+            sap = st.apr[i];
+            sxh = __ldcg(V.x + st.halo0 + i);
+          }
+        }
+      }
+      fc_mbar_wait(&sm->full[sg], par);
+      const int k0 = sm->kb0[j], k1 = sm->kb1[j];
+      const int ka = k0 & ~3;
+      const bool staged = (((k1 + 3) & ~3) - ka) <= CAP;
+      const double *pa = sm->a[sg];
+      const int *pj = sm->ja[sg];
+      const int *po = sm->off[sg];
+      if (tid < nr) {
+        const int s = po[tid], e = po[tid + 1];
+        double v = RES ? V.su[r] : 0.0;
+        if (staged) {
+          // thread = row: the 32 lanes of a warp read x at 32 consecutive rows' c-th neighbours, which on a
+          // finite-volume numbering are (nearly) contiguous -- one or two L1 lines per warp gather
+          constexpr int U = 8;
+          for (int c = s - ka; c < e - ka; c += U) {
+            int id[U];
+            double av[U], xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const bool in = c + u < e - ka;
+              id[u] = in ? pj[c + u] : r;
+              av[u] = in ? pa[c + u] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = V.x[id[u]];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (c + u < e - ka) {
+                const double t = av[u] * xv[u];
+                v = RES ? v - t : v + t;
+              }
+            }
+          }
+        } else {  // a chunk too long for the staging buffers: straight from global memory
+          for (int k = s; k < e; ++k) {
+            double t = M.a[k] * V.x[M.ja[k]];
+            v = RES ? v - t : v + t;
+          }
+        }
+        if (STRIP) {
+          if (sq1 > sq0) {   // `apr` strip after the CSR part of the row (src-parallel/dpcg.f90:132-136)
+            double t = sap * sxh;
+            v = RES ? v - t : v + t;
+            for (int q = sq0 + 1; q < sq1; ++q) {
+              const int i = st.idx[q];
+              t = st.apr[i] * __ldcg(V.x + st.halo0 + i);
+              v = RES ? v - t : v + t;
+            }
+          }
+        }
+        V.y[r] = v;
+        if (MODE == FC_MODE_DOT || MODE == FC_MODE_DOT2) acc += V.w[r] * v;
+        if (MODE == FC_MODE_DOT2) acc2 += v * v;
+        if (RES) {
+          acc += fabs(v);
+          const double ad = staged ? pa[V.diag[r] - ka] : M.a[V.diag[r]];
+          V.adiag[r] = ad;
+          if (MODE == FC_MODE_RESID_SK) acc2 += v * (v / (ad + V.padd));
+        }
+      }
+      __syncthreads();
+      if (next < nch) {
+        if (tid == 0) fc_fence_proxy_async();
+        issue_one(M);
+      }
+    }
+    next = 0;
+  }
+};

@@ -38,8 +38,9 @@ SYMBOLS = (
     "fc_grad_gauss", "fc_grad_gauss_corrected", "fc_bpres", "fc_laplacian", "fc_solve", "fc_solve_host",
     "fc_solve_csr", "fc_calcp_assemble", "fc_calcp", "fc_calcp_host", "fc_exchange", "fc_global_sum",
     "fc_get_timings", "fc_time_spmv", "fc_stream", "fc_copy", "fc_set_spmv_sampling", "fc_comm_p2p_blob",
-    "fc_comm_p2p_open",
+    "fc_comm_p2p_open", "fc_set_tuning",
 )
+TUNE_SPMV_KERNEL, TUNE_DPCG_PERSISTENT, TUNE_CTAS_PER_SM, TUNE_PIPE_GEOMETRY = 0, 1, 2, 3
 
 
 class MeshDesc(C.Structure):
@@ -76,7 +77,10 @@ class CalcpReport(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("solve_ms", C.c_double), ("assemble_ms", C.c_double), ("correct_ms", C.c_double),
-                ("spmv_ms", C.c_double), ("spmv_samples", C.c_int), ("pad_", C.c_int), ("launches", C.c_longlong)]
+                ("spmv_ms", C.c_double), ("spmv_samples", C.c_int), ("pad_", C.c_int), ("launches", C.c_longlong),
+                ("persist_ms", C.c_double), ("persist_pupdate_ms", C.c_double), ("persist_spmv_ms", C.c_double),
+                ("persist_update_ms", C.c_double), ("persist_iters", C.c_int), ("persist_grid", C.c_int),
+                ("persist_mail_ms", C.c_double)]
 
 
 class FcError(RuntimeError):
@@ -256,6 +260,10 @@ class Context:
 
     def copy(self, src: str, dst: str):
         self._ck(self.lib.fc_copy(self.h, F[src], F[dst]))
+
+    def set_tuning(self, key: int, value: int):
+        """Kernel selection for A/B measurements (TUNE_* keys, include/fcapp.h)."""
+        self._ck(self.lib.fc_set_tuning(self.h, int(key), int(value)))
 
     def set_spmv_sampling(self, max_samples: int):
         self._ck(self.lib.fc_set_spmv_sampling(self.h, max_samples))

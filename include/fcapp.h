@@ -226,7 +226,27 @@ typedef struct {
   int spmv_samples;    /* how many launches that mean is over                 */
   int pad_;
   long long launches;  /* kernels launched by the library since creation      */
+  /* persistent DPCG kernel of the last solve (zero when the multi-kernel path ran):
+   * device time of the whole kernel and of its three phases summed over the
+   * iterations, each phase measured on the GPU's global timer from the grid
+   * barrier that starts it to the arrival of the last CTA at the barrier that
+   * ends it; persist_ms - the three = barriers, reductions, halo waits.          */
+  double persist_ms, persist_pupdate_ms, persist_spmv_ms, persist_update_ms;
+  int persist_iters;   /* iterations the phase sums cover                      */
+  int persist_grid;    /* CTAs of the persistent kernel                        */
+  double persist_mail_ms; /* of the remainder: waiting for the other ranks' partial sums */
 } fc_timings;
+/* Kernel selection, for measurements and A/B tests (defaults in brackets).     */
+enum {
+  FC_TUNE_SPMV_KERNEL = 0,     /* stand-alone SpMV launches: 0 CSR-stream kernel,
+                                  1 TMA-staged pipeline, [2] chosen by size        */
+  FC_TUNE_DPCG_PERSISTENT = 1, /* 0 one launch per vector op, [1] whole DPCG loop
+                                  as one persistent cooperative kernel            */
+  FC_TUNE_CTAS_PER_SM = 2,     /* persistent kernel: CTAs per SM, [0] = all that fit */
+  FC_TUNE_PIPE_GEOMETRY = 3    /* TMA pipeline (threads, non-zeros staged, stages):
+                                  0 256/2304/3, [1] 256/2304/2, 2 256/2048/2, 3 128/1024/2 */
+};
+int fc_set_tuning(fc_context *ctx, int key, int value);
 /* Bracket up to `max_samples` SpMV launches of every following solve with CUDA
  * events on the library stream (0 switches it off).                          */
 int fc_set_spmv_sampling(fc_context *ctx, int max_samples);
