@@ -124,18 +124,50 @@ __device__ __forceinline__ void grid_reduce(const persist_args &A, sync_ctx &S, 
       v[r] = w;
     }
     fc_block_sum<NR>(v, S.s_red);
+    if (A.p2p) {
+      // all-reduce over the ranks through the mailboxes, one thread per 8-byte word: thread t posts word
+      // t % (2 NR) of my sums to rank t / (2 NR) and polls the same word of that rank's contribution to me,
+      // so the exchange costs one NVLink flight, not one per word
+      __shared__ double s_v[NR];
+      __shared__ unsigned long long s_mail[FC_MAX_RANKS * 2 * NR];
+      __shared__ unsigned long long s_tpost;
+      const fc_p2p_dev *P = A.p2p;
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) s_v[r] = v[r];
+        s_tpost = fc_globaltimer();
+      }
+      __syncthreads();
+      const int nw = P->nranks * 2 * NR;
+      for (int t = threadIdx.x; t < nw; t += blockDim.x) {
+        const int q = t / (2 * NR), w = t % (2 * NR);
+        const int slot = (int)(seq % FC_MAIL_SLOTS);
+        const unsigned long long tag = seq & 0xffffffffull;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(s_v[w >> 1]);
+        const unsigned long long word = ((w & 1) ? (bits >> 32) : (bits & 0xffffffffull)) | (tag << 32);
+        fc_st_relaxed_sys(P->peer_mail[q][slot * FC_MAX_RANKS + P->rank].w + w, word);
+        const unsigned long long *src = P->mail[slot * FC_MAX_RANKS + q].w + w;
+        unsigned long long x;
+        fc_spin_guard g;
+        while (((x = fc_ld_relaxed_sys(src)) >> 32) != tag) g.tick();
+        s_mail[t] = x;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) v[i] = 0.0;
+        for (int r = 0; r < P->nranks; ++r) {   // rank order: identical sums on every rank (global_sum)
+#pragma unroll
+          for (int i = 0; i < NR; ++i) {
+            const unsigned long long lo = s_mail[r * 2 * NR + 2 * i], hi = s_mail[r * 2 * NR + 2 * i + 1];
+            v[i] = v[i] + __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+          }
+        }
+        A.ps->t_mail += fc_globaltimer() - s_tpost;
+      }
+    }
     if (threadIdx.x == 0) {
       fc_scalars *sc = A.sc;
-      if (A.p2p) {
-        const fc_p2p_dev *P = A.p2p;
-        const unsigned long long t_post = fc_globaltimer();
-        fc_mail_post(P, seq, v, NR);
-        double t[NR];
-        fc_mail_collect<NR>(P, seq, NR, t);
-#pragma unroll
-        for (int i = 0; i < NR; ++i) v[i] = t[i];
-        A.ps->t_mail += fc_globaltimer() - t_post;
-      }
 #pragma unroll
       for (int r = 0; r < NR; ++r) sc->red[r] = v[r];
       fc_scalar_step(sc, step, A.hist);
