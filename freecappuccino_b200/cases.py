@@ -17,6 +17,11 @@ def skew_case(nx=10, ny=9, nz=8, kinds=("inlet", "outlet", "wall", "wall", "symm
     return M.geometry_from_polymesh(pts, faces, owner, neigh, counts, starts)
 
 
+def poly_case(N=6, jitter=0.15):
+    """Non-orthogonal polyhedral mesh of BASELINE config 5 at test size (2 N^3 truncated octahedra)."""
+    return M.bcc_poly_mesh(N, jitter)
+
+
 def flow_fields(mesh, seed=7):
     """Deterministic smooth velocity / pressure + momentum-diagonal fields (config 4 of SURVEY 8d,
     plus a small seeded perturbation so that no two values coincide)."""

@@ -183,7 +183,7 @@ __device__ __forceinline__ void grid_reduce(const persist_args &A, sync_ctx &S, 
 }
 
 template <int T, int CAP, int S, bool STRIP>
-__global__ void __launch_bounds__(T)
+__global__ void __launch_bounds__(T, 768 / T)   // <= 85 registers: three 256-thread CTAs per SM
 k_dpcg_persist(persist_args A) {
   extern __shared__ __align__(128) unsigned char fc_smem_raw[];
   __shared__ double s_red[64];
@@ -222,22 +222,50 @@ k_dpcg_persist(persist_args A) {
     grid_reduce<2>(A, SY, v, STEP_RES0_SK, PH_SETUP, ++red_seq);
   }
 
+  bool first = true;
   while (!__ldcg(&sc->done)) {
     // ---- pk = res/(a_ii[+small]) + bet*pk   (dpcg.f90:95-100); exchange(pk) (src-parallel/dpcg.f90:114): the
     //      owner of a cell on a processor boundary stores its new value straight into the neighbour's halo ----
     {
+      // The x update of the PREVIOUS iteration, fi += alf*pk (dpcg.f90:121-124), rides along: this phase reads
+      // pk anyway, so deferring it saves one pass over pk per iteration.  alf = sk_prev / pkapk, and the last
+      // reduction left sk_prev in s0 (dpcg.f90:139), so the value -- and fi -- are bit-identical.
       const double bet = __ldcg(&sc->sk) / __ldcg(&sc->s0);
+      const double alfp = first ? 0.0 : __ldcg(&sc->s0) / __ldcg(&sc->pkapk);
+      first = false;
       int i = rbeg + tid, j = 0;
-      for (; i + 3 * T < rend; i += 4 * T, j += 4) {
+      for (; i + 3 * T < rend; i += 4 * T) {
         const double r0 = A.res[i], r1 = A.res[i + T], r2 = A.res[i + 2 * T], r3 = A.res[i + 3 * T];
         const double d0 = A.adiag[i], d1 = A.adiag[i + T], d2 = A.adiag[i + 2 * T], d3 = A.adiag[i + 3 * T];
         const double p0 = A.pk[i], p1 = A.pk[i + T], p2 = A.pk[i + 2 * T], p3 = A.pk[i + 3 * T];
+        const double f0 = A.fi[i], f1 = A.fi[i + T], f2 = A.fi[i + 2 * T], f3 = A.fi[i + 3 * T];
+        A.fi[i] = f0 + alfp * p0;
+        A.fi[i + T] = f1 + alfp * p1;
+        A.fi[i + 2 * T] = f2 + alfp * p2;
+        A.fi[i + 3 * T] = f3 + alfp * p3;
         A.pk[i] = r0 / (d0 + A.padd) + bet * p0;
         A.pk[i + T] = r1 / (d1 + A.padd) + bet * p1;
         A.pk[i + 2 * T] = r2 / (d2 + A.padd) + bet * p2;
         A.pk[i + 3 * T] = r3 / (d3 + A.padd) + bet * p3;
       }
-      for (; i < rend; i += T) A.pk[i] = A.res[i] / (A.adiag[i] + A.padd) + bet * A.pk[i];
+      if (i < rend) {   // up to three rows left: one predicated batch instead of three dependent round trips
+        const bool b1 = i + T < rend, b2 = i + 2 * T < rend;
+        const double r0 = A.res[i], d0 = A.adiag[i], p0 = A.pk[i], f0 = A.fi[i];
+        const double r1 = b1 ? A.res[i + T] : 0.0, d1 = b1 ? A.adiag[i + T] : 1.0, p1 = b1 ? A.pk[i + T] : 0.0;
+        const double f1 = b1 ? A.fi[i + T] : 0.0;
+        const double r2 = b2 ? A.res[i + 2 * T] : 0.0, d2 = b2 ? A.adiag[i + 2 * T] : 1.0;
+        const double p2 = b2 ? A.pk[i + 2 * T] : 0.0, f2 = b2 ? A.fi[i + 2 * T] : 0.0;
+        A.fi[i] = f0 + alfp * p0;
+        A.pk[i] = r0 / (d0 + A.padd) + bet * p0;
+        if (b1) {
+          A.fi[i + T] = f1 + alfp * p1;
+          A.pk[i + T] = r1 / (d1 + A.padd) + bet * p1;
+        }
+        if (b2) {
+          A.fi[i + 2 * T] = f2 + alfp * p2;
+          A.pk[i + 2 * T] = r2 / (d2 + A.padd) + bet * p2;
+        }
+      }
       if (p2p && pipe.cta_strip) {
         // my cells on a processor boundary: their new values go straight into the neighbours' halo slots
         __syncthreads();
@@ -287,37 +315,52 @@ k_dpcg_persist(persist_args A) {
       grid_reduce<1>(A, SY, v, STEP_PKAPK, PH_SPMV, ++red_seq);
     }
 
-    // ---- fi += alf*pk ; res -= alf*zk ; resl = sum|res| ; next sk   (dpcg.f90:121-142) ----
+    // ---- res -= alf*zk ; resl = sum|res| ; next sk   (dpcg.f90:125-142; fi += alf*pk is deferred, see above) ----
     {
       const double alf = __ldcg(&sc->sk) / __ldcg(&sc->pkapk);
       double a0 = 0.0, a1 = 0.0;
       int i = rbeg + tid;
-      for (; i + T < rend; i += 2 * T) {
-        const double f0 = A.fi[i], f1 = A.fi[i + T];
-        const double p0 = A.pk[i], p1 = A.pk[i + T];
-        const double r0 = A.res[i], r1 = A.res[i + T];
-        const double z0 = A.zk[i], z1 = A.zk[i + T];
-        const double d0 = A.adiag[i], d1 = A.adiag[i + T];
-        A.fi[i] = f0 + alf * p0;
-        A.fi[i + T] = f1 + alf * p1;
-        const double n0 = r0 - alf * z0, n1 = r1 - alf * z1;
+      for (; i + 3 * T < rend; i += 4 * T) {
+        const double r0 = A.res[i], r1 = A.res[i + T], r2 = A.res[i + 2 * T], r3 = A.res[i + 3 * T];
+        const double z0 = A.zk[i], z1 = A.zk[i + T], z2 = A.zk[i + 2 * T], z3 = A.zk[i + 3 * T];
+        const double d0 = A.adiag[i], d1 = A.adiag[i + T], d2 = A.adiag[i + 2 * T], d3 = A.adiag[i + 3 * T];
+        const double n0 = r0 - alf * z0, n1 = r1 - alf * z1, n2 = r2 - alf * z2, n3 = r3 - alf * z3;
         A.res[i] = n0;
         A.res[i + T] = n1;
-        a0 += fabs(n0);
-        a1 += n0 * (n0 / (d0 + A.padd));
-        a0 += fabs(n1);
-        a1 += n1 * (n1 / (d1 + A.padd));
+        A.res[i + 2 * T] = n2;
+        A.res[i + 3 * T] = n3;
+        a0 += fabs(n0); a1 += n0 * (n0 / (d0 + A.padd));
+        a0 += fabs(n1); a1 += n1 * (n1 / (d1 + A.padd));
+        a0 += fabs(n2); a1 += n2 * (n2 / (d2 + A.padd));
+        a0 += fabs(n3); a1 += n3 * (n3 / (d3 + A.padd));
       }
-      for (; i < rend; i += T) {
-        A.fi[i] = A.fi[i] + alf * A.pk[i];
-        const double r = A.res[i] - alf * A.zk[i];
-        A.res[i] = r;
-        a0 += fabs(r);
-        a1 += r * (r / (A.adiag[i] + A.padd));
+      if (i < rend) {
+        const bool b1 = i + T < rend, b2 = i + 2 * T < rend;
+        const double r0 = A.res[i], z0 = A.zk[i], d0 = A.adiag[i];
+        const double r1 = b1 ? A.res[i + T] : 0.0, z1 = b1 ? A.zk[i + T] : 0.0, d1 = b1 ? A.adiag[i + T] : 1.0;
+        const double r2 = b2 ? A.res[i + 2 * T] : 0.0, z2 = b2 ? A.zk[i + 2 * T] : 0.0;
+        const double d2 = b2 ? A.adiag[i + 2 * T] : 1.0;
+        const double n0 = r0 - alf * z0;
+        A.res[i] = n0;
+        a0 += fabs(n0); a1 += n0 * (n0 / (d0 + A.padd));
+        if (b1) {
+          const double n1 = r1 - alf * z1;
+          A.res[i + T] = n1;
+          a0 += fabs(n1); a1 += n1 * (n1 / (d1 + A.padd));
+        }
+        if (b2) {
+          const double n2 = r2 - alf * z2;
+          A.res[i + 2 * T] = n2;
+          a0 += fabs(n2); a1 += n2 * (n2 / (d2 + A.padd));
+        }
       }
       double v[2] = {a0, a1};
       grid_reduce<2>(A, SY, v, STEP_CG_UPDATE_SK, PH_UPDATE, ++red_seq);
     }
+  }
+  if (!first) {   // the x update of the last iteration (dpcg.f90:121-124)
+    const double alf = __ldcg(&sc->s0) / __ldcg(&sc->pkapk);
+    for (int i = rbeg + tid; i < rend; i += T) A.fi[i] = A.fi[i] + alf * A.pk[i];
   }
   pipe.drain();   // no CTA may exit with bulk copies in flight
 }

@@ -10,6 +10,7 @@ them, so they can be handed to the C-ABI unchanged.
 Contents
   * :class:`Mesh`            -- the array bundle
   * :func:`hex_mesh`         -- synthetic structured-hex generator (configs 3/4)
+  * :func:`bcc_poly_mesh`    -- synthetic non-orthogonal polyhedral generator (config 5)
   * :func:`geometry_from_polymesh` / :func:`read_polymesh` -- OpenFOAM polyMesh
     reader restating ``mesh_geometry`` (:859-1081) for the shipped cases
   * :func:`partition`        -- cell partitioner emitting per-rank meshes with
@@ -383,6 +384,127 @@ def read_polymesh(polymesh_dir: str) -> Mesh:
     if len({len(f) for f in faces}) == 1:
         faces = np.array(faces)
     return geometry_from_polymesh(points, faces, owner, neighbour, counts, starts)
+
+
+# --------------------------------------------------------------------------
+# synthetic non-orthogonal polyhedral mesh
+# --------------------------------------------------------------------------
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    """Counter-based RNG keyed by cell id (values do not depend on how the mesh is partitioned)."""
+    with np.errstate(over="ignore"):
+        z = (x.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def bcc_poly_mesh(N: int, jitter: float = 0.15, seed: int = 2024, length: float = 1.0) -> Mesh:
+    """Voronoi tessellation of a body-centred cubic lattice over N^3 cubic unit cells: 2 N^3 truncated
+    octahedra, each with 8 hexagonal faces towards the (+-1/2,+-1/2,+-1/2) neighbours and 6 square faces
+    towards the (+-1,0,0) neighbours = 14 faces per cell (nnz/row = 15).  The geometry arrays are emitted
+    directly (no points / faces files): face area vectors and face centres are those of the regular
+    tessellation, cell centres are displaced by up to ``jitter`` x the nearest-neighbour spacing
+    (splitmix64 keyed by cell id), which makes every face non-orthogonal; ``facint`` follows from the
+    displaced centres (intersection of the P-N line with the face plane, mesh_geometry...:1040-1062).
+    A cell on the hull of the lattice is closed by ONE wall face carrying the sum of its missing faces'
+    area vectors, so that sum(S) = 0 holds for every cell.  Cells are numbered unit cell by unit cell
+    (corner site, then body centre; i fastest), faces in OpenFOAM's upper-triangular order."""
+    a = length / N
+    n = 2 * N ** 3
+    ii, jj, kk = np.meshgrid(np.arange(N), np.arange(N), np.arange(N), indexing="ij")
+    order = np.argsort((ii + N * (jj + N * kk)).ravel(), kind="stable")
+    ci, cj, ck = (v.ravel()[order].astype(np.int64) for v in (ii, jj, kk))
+    ucell = ci + N * (cj + N * ck)                                   # unit-cell id
+    # site positions in units of a/2: corner sites (type 0) at even, body centres (type 1) at odd coordinates
+    P = np.empty((n, 3), dtype=np.int64)
+    P[0::2] = np.stack([2 * ci, 2 * cj, 2 * ck], axis=1)
+    P[1::2] = P[0::2] + 1
+    cid = np.arange(n, dtype=np.int64)
+
+    def site_id(q):
+        """cell id of the site at half-lattice coordinates q [m,3], or -1 outside the lattice"""
+        t = q[:, 0] & 1
+        same = ((q[:, 1] & 1) == t) & ((q[:, 2] & 1) == t)
+        u = (q - t[:, None]) >> 1
+        inside = same & np.all((u >= 0) & (u < N), axis=1)
+        out = np.full(q.shape[0], -1, dtype=np.int64)
+        uu = u[inside]
+        out[inside] = 2 * (uu[:, 0] + N * (uu[:, 1] + N * uu[:, 2])) + t[inside]
+        return out
+
+    hexd = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.int64)
+    sqd = np.array([[2, 0, 0], [-2, 0, 0], [0, 2, 0], [0, -2, 0], [0, 0, 2], [0, 0, -2]], dtype=np.int64)
+    dirs = np.concatenate([hexd, sqd])                               # in units of a/2
+    a_hex, a_sq = 3.0 * a * a / 16.0, a * a / 8.0                    # |S_hex| / sqrt(3) per component, |S_sq|
+    Sdir = np.concatenate([hexd * a_hex, (sqd // 2) * a_sq]).astype(np.float64)
+
+    f_own, f_nb, f_S, f_c = [], [], [], []
+    bS = np.zeros((n, 3)); bC = np.zeros((n, 3)); bW = np.zeros(n)
+    for d, S in zip(dirs, Sdir):
+        q = P + d
+        nb = site_id(q)
+        ctr = (P + 0.5 * d) * (0.5 * a)                              # face centre = midpoint of the two sites
+        keep = nb > cid                                              # every inner face once, owner < neighbour
+        f_own.append(cid[keep]); f_nb.append(nb[keep])
+        f_S.append(np.broadcast_to(S, (int(keep.sum()), 3))); f_c.append(ctr[keep])
+        miss = nb < 0
+        w = float(np.sqrt((S * S).sum()))
+        bS[miss] += S; bC[miss] += w * ctr[miss]; bW[miss] += w
+    f_own = np.concatenate(f_own); f_nb = np.concatenate(f_nb)
+    f_S = np.concatenate(f_S); f_c = np.concatenate(f_c)
+    o = np.lexsort((f_nb, f_own))
+    f_own, f_nb, f_S, f_c = f_own[o], f_nb[o], f_S[o], f_c[o]
+    nin = f_own.size
+    # displaced cell centres
+    spacing = a * np.sqrt(3.0) / 2.0
+    cen = P * (0.5 * a)
+    if jitter > 0.0:
+        u = np.stack([_splitmix64(np.uint64(seed) * np.uint64(0x100000001B3) + (cid * 3 + c).astype(np.uint64))
+                      for c in range(3)], axis=1)
+        u = (u >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)     # [0,1)
+        cen = cen + (2.0 * u - 1.0) * (jitter * spacing / np.sqrt(3.0))
+    dPN = cen[f_nb] - cen[f_own]
+    facint = ((f_c - cen[f_own]) * f_S).sum(axis=1) / (dPN * f_S).sum(axis=1)
+    bcell = np.nonzero(bW > 0)[0]
+    b_S = bS[bcell]
+    b_c = bC[bcell] / bW[bcell, None]
+    owner = np.concatenate([f_own, bcell]) + 1
+    S_all = np.concatenate([f_S, b_S]); c_all = np.concatenate([f_c, b_c])
+    # volumes: a^3/2 inside; a hull cell is the polyhedron its own faces close (divergence theorem)
+    vol = np.full(n, 0.5 * a ** 3)
+    vb = np.zeros(n)
+    fv = (c_all * S_all).sum(axis=1) / 3.0
+    np.add.at(vb, owner - 1, fv)
+    np.subtract.at(vb, f_nb, fv[:nin])
+    vol[bcell] = vb[bcell]
+    return Mesh(
+        numCells=n, numInnerFaces=nin, numFaces=owner.size,
+        owner=owner.astype(np.int32), neighbour=(f_nb + 1).astype(np.int32),
+        xc=cen[:, 0].copy(), yc=cen[:, 1].copy(), zc=cen[:, 2].copy(), vol=vol,
+        arx=S_all[:, 0].copy(), ary=S_all[:, 1].copy(), arz=S_all[:, 2].copy(),
+        xf=c_all[:, 0].copy(), yf=c_all[:, 1].copy(), zf=c_all[:, 2].copy(),
+        facint=facint, counts={"wall": int(bcell.size)}, starts={"wall": int(nin)}, gloCells=n)
+
+
+def rcb_ranks(g: Mesh, nranks: int) -> np.ndarray:
+    """Recursive coordinate bisection of the cell centres into ``nranks`` parts of (nearly) equal size:
+    the partitioner for unstructured meshes (the reference relies on OpenFOAM's decomposePar)."""
+    rank = np.zeros(g.numCells, dtype=np.int64)
+    xyz = np.stack([g.xc[:g.numCells], g.yc[:g.numCells], g.zc[:g.numCells]], axis=1)
+
+    def split(idx, r0, k):
+        if k == 1:
+            rank[idx] = r0
+            return
+        kl = k // 2
+        ax = int(np.argmax(np.ptp(xyz[idx], axis=0)))
+        o = idx[np.argsort(xyz[idx, ax], kind="stable")]
+        cut = (o.size * kl) // k
+        split(o[:cut], r0, kl)
+        split(o[cut:], r0 + kl, k - kl)
+
+    split(np.arange(g.numCells), 0, nranks)
+    return rank
 
 
 # --------------------------------------------------------------------------

@@ -142,6 +142,10 @@ void fco_par_exchange(fco_rank *R, int nr, double **phi, int stride);
 void fco_par_grad_gauss(fco_rank *R, int nr, double **phi, int nigrad, double **grad);
 void fco_par_grad_gauss_corrected(fco_rank *R, int nr, double **phi, double **grad);
 void fco_par_laplacian(fco_rank *R, int nr, double **mu, double **phi);
+/* run the ranks of every lock-step phase of fco_par_solve / fco_par_exchange on up to n host threads
+ * (bit-identical results); fco_par_openmp() = 0 when the library was built without OpenMP */
+void fco_par_set_threads(int n);
+int fco_par_openmp(void);
 int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver_opts *o, fco_report *rep,
                   double *hist);
 void fco_par_calcp_assemble(fco_rank *R, int nr, const fco_calcp_opts *o);

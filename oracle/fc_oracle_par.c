@@ -9,18 +9,33 @@
  */
 #include "fc_oracle.c"
 
+/* The ranks of one lock-step phase are independent (they only read halo values copied in an earlier
+ * phase), so a phase may run one rank per host thread: the src-parallel build as R threads instead of
+ * R MPI processes.  Sums are still added in rank order, so the results are bit-identical to the
+ * single-thread run.  Used by bench.py's reference arm; the tests run it with one thread. */
+static int fco_threads = 1;
+void fco_par_set_threads(int n) { fco_threads = n > 1 ? n : 1; }
+int fco_par_openmp(void) {
+#ifdef _OPENMP
+  return 1;
+#else
+  return 0;
+#endif
+}
+#define PAR_RANKS _Pragma("omp parallel for schedule(static, 1) num_threads(fco_threads) if (fco_threads > 1)")
+
 /* phi_r(iProcStart+i) <- phi_q(bufind_q(i')) for every connection r<->q; `stride` addresses one
  * component of an interleaved (3,numPCells) gradient (exchange(dPhidxi(1,:)) passes a strided
  * section; gfortran packs it into a contiguous temporary, the effect is the same). */
 void fco_par_exchange(fco_rank *R, int nr, double **phi, int stride) {
   double **buf = (double **)malloc(sizeof(double *) * (size_t)nr);
-  for (int r = 0; r < nr; ++r) {
+  PAR_RANKS for (int r = 0; r < nr; ++r) {
     const fco_mesh *g = &R[r].g;
     buf[r] = (double *)malloc(sizeof(double) * (size_t)(g->npro > 0 ? g->npro : 1));
     for (int i = 1; i <= g->npro; ++i) /* buffer(i) = phi(bufind(i)), bufind(i) = owner(iProcFacesStart+i) */
       buf[r][i - 1] = phi[r][(size_t)(A1(g->owner, g->iProcFacesStart + i) - 1) * stride];
   }
-  for (int r = 0; r < nr; ++r) {
+  PAR_RANKS for (int r = 0; r < nr; ++r) {
     const fco_mesh *g = &R[r].g;
     for (int c = 0; c < R[r].numConnections; ++c) {
       const int q = R[r].neighbProcNo[c];
@@ -145,14 +160,14 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
   par_scratch *S = (par_scratch *)calloc((size_t)nr, sizeof(par_scratch));
   double *part = (double *)calloc((size_t)nr, sizeof(double)), *part2 = (double *)calloc((size_t)nr, sizeof(double));
   double **vec = (double **)malloc(sizeof(double *) * (size_t)nr);
-  for (int r = 0; r < nr; ++r) {
+  PAR_RANKS for (int r = 0; r < nr; ++r) {
     const size_t np = (size_t)(R[r].g.numCells + R[r].g.npro);
     S[r].pk = (double *)calloc(np, sizeof(double)); S[r].zk = (double *)calloc(np, sizeof(double));
     S[r].d = (double *)calloc(np, sizeof(double)); S[r].reso = (double *)calloc(np, sizeof(double));
     S[r].uk = (double *)calloc(np, sizeof(double)); S[r].vk = (double *)calloc(np, sizeof(double));
     rank_strips(&R[r], &S[r]);
   }
-  for (int r = 0; r < nr; ++r)
+  PAR_RANKS for (int r = 0; r < nr; ++r)
     part[r] = initial_residual(&R[r].m, R[r].f.a, R[r].f.su, fi[r], R[r].f.res, &S[r].st);
   const double res0 = gsum(part, nr);
   double resl = res0;
@@ -160,7 +175,7 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
   rep->res0 = res0; rep->resl = res0; rep->iters = 0;
   if (o->tol >= 0.0 && res0 < o->tol) goto done;
   if (solver != 0)
-    for (int r = 0; r < nr; ++r) { /* rank-local DIC / DILU with +small (src-parallel/iccg.f90:94-100, bicgstab.f90:80-91) */
+    PAR_RANKS for (int r = 0; r < nr; ++r) { /* rank-local DIC / DILU with +small (src-parallel/iccg.f90:94-100, bicgstab.f90:80-91) */
       const fco_csr *m = &R[r].m;
       const double *a = R[r].f.a;
       double *d = S[r].d;
@@ -180,12 +195,12 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
       }
     }
   if (solver == 2)
-    for (int r = 0; r < nr; ++r) memcpy(S[r].reso, R[r].f.res, sizeof(double) * (size_t)R[r].m.n);
+    PAR_RANKS for (int r = 0; r < nr; ++r) memcpy(S[r].reso, R[r].f.res, sizeof(double) * (size_t)R[r].m.n);
   {
     double s0 = (double)1.e20f, alf = 1.0, beto = 1.0, gam = 1.0;
     for (int l = 1; l <= o->nsw; ++l) {
       if (solver != 2) {
-        for (int r = 0; r < nr; ++r) {
+        PAR_RANKS for (int r = 0; r < nr; ++r) {
           const fco_csr *m = &R[r].m;
           const int n = m->n;
           double *res = R[r].f.res, *zk = S[r].zk;
@@ -199,13 +214,13 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
         }
         const double sk = gsum(part, nr);
         const double bet = sk / s0;
-        for (int r = 0; r < nr; ++r) {
+        PAR_RANKS for (int r = 0; r < nr; ++r) {
           const int n = R[r].m.n;
           for (int i = 1; i <= n; ++i) A1(S[r].pk, i) = A1(S[r].zk, i) + bet * A1(S[r].pk, i);
           vec[r] = S[r].pk;
         }
         fco_par_exchange(R, nr, vec, 1);
-        for (int r = 0; r < nr; ++r) {
+        PAR_RANKS for (int r = 0; r < nr; ++r) {
           const int n = R[r].m.n;
           matvec(&R[r].m, R[r].f.a, S[r].pk, S[r].zk, &S[r].st, 1);
           double pkapk = 0.0;
@@ -214,7 +229,7 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
         }
         const double pkapk = gsum(part, nr);
         alf = sk / pkapk;
-        for (int r = 0; r < nr; ++r) {
+        PAR_RANKS for (int r = 0; r < nr; ++r) {
           const int n = R[r].m.n;
           double *res = R[r].f.res;
           for (int i = 1; i <= n; ++i) A1(fi[r], i) = A1(fi[r], i) + alf * A1(S[r].pk, i);
@@ -226,7 +241,7 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
         resl = gsum(part, nr);
         s0 = sk;
       } else {
-        for (int r = 0; r < nr; ++r) {
+        PAR_RANKS for (int r = 0; r < nr; ++r) {
           const int n = R[r].m.n;
           double b = 0.0;
           for (int i = 1; i <= n; ++i) b = b + A1(R[r].f.res, i) * A1(S[r].reso, i);
@@ -235,7 +250,7 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
         const double bet = gsum(part, nr);
         const double om = bet * gam / (alf * beto + o->small);
         beto = bet;
-        for (int r = 0; r < nr; ++r) {
+        PAR_RANKS for (int r = 0; r < nr; ++r) {
           const int n = R[r].m.n;
           for (int i = 1; i <= n; ++i)
             A1(S[r].pk, i) = A1(R[r].f.res, i) + om * (A1(S[r].pk, i) - alf * A1(S[r].uk, i));
@@ -243,7 +258,7 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
           vec[r] = S[r].zk;
         }
         fco_par_exchange(R, nr, vec, 1);
-        for (int r = 0; r < nr; ++r) {
+        PAR_RANKS for (int r = 0; r < nr; ++r) {
           const int n = R[r].m.n;
           matvec(&R[r].m, R[r].f.a, S[r].zk, S[r].uk, &S[r].st, 0);
           double t = 0.0;
@@ -252,7 +267,7 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
         }
         const double ukreso = gsum(part, nr);
         gam = bet / ukreso;
-        for (int r = 0; r < nr; ++r) {
+        PAR_RANKS for (int r = 0; r < nr; ++r) {
           const int n = R[r].m.n;
           double *res = R[r].f.res;
           for (int i = 1; i <= n; ++i) A1(fi[r], i) = A1(fi[r], i) + gam * A1(S[r].zk, i);
@@ -261,7 +276,7 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
           vec[r] = S[r].zk;
         }
         fco_par_exchange(R, nr, vec, 1);
-        for (int r = 0; r < nr; ++r) {
+        PAR_RANKS for (int r = 0; r < nr; ++r) {
           const int n = R[r].m.n;
           matvec(&R[r].m, R[r].f.a, S[r].zk, S[r].vk, &S[r].st, 0);
           double t = 0.0, t2 = 0.0;
@@ -271,7 +286,7 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
         }
         const double svkres = gsum(part, nr), svkvk = gsum(part2, nr);
         alf = svkres / (svkvk + o->small);
-        for (int r = 0; r < nr; ++r) {
+        PAR_RANKS for (int r = 0; r < nr; ++r) {
           const int n = R[r].m.n;
           double *res = R[r].f.res;
           for (int i = 1; i <= n; ++i) A1(fi[r], i) = A1(fi[r], i) + alf * A1(S[r].zk, i);

@@ -14,6 +14,14 @@ import numpy as np
 from . import oracle as O
 
 
+def set_threads(n: int) -> int:
+    """Host threads for the rank loops of the lock-step solver (1 = serial).  Returns the number in effect."""
+    if not O.lib().fco_par_openmp():
+        return 1
+    O.lib().fco_par_set_threads(int(n))
+    return max(1, int(n))
+
+
 class FcoRank(C.Structure):
     _fields_ = [("g", O.FcoMesh), ("m", O.FcoCsr), ("f", O.FcoFields), ("apr", O.dp), ("fmpro", O.dp),
                 ("numConnections", C.c_int), ("neighbProcNo", O.ip), ("neighbProcOffset", O.ip)]

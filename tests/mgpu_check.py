@@ -40,24 +40,28 @@ def main():
 
     failures = []
     for mesh_name, g in (("hex_mixed", cases.hex_case(12, 9, 4 * world, kinds=("inlet", "outlet", "wall", "symmetry", "wall", "wall"))),
-                         ("skew", cases.skew_case(9, 8, 3 * world + 2))):
+                         ("skew", cases.skew_case(9, 8, 3 * world + 2)),
+                         # BASELINE config 5 at test size, cut by recursive coordinate bisection: several
+                         # connections per rank and cells with several processor faces
+                         ("poly", cases.poly_case(5))):
         f = cases.flow_fields(g)
         fmi, flomas = cases.inlet_fluxes(g, f)
         gp = O.grad_gauss(g, f["p"], 1)
-        cell_rank = M.slab_ranks(g.numCells, world)
+        cell_rank = M.rcb_ranks(g, world) if mesh_name == "poly" else M.slab_ranks(g.numCells, world)
         parts = M.partition(g, cell_rank, world)
         part = parts[rank]
         mine = scatter_case(g, part, f, fmi, gp)
         # npcor = 2 (non-orthogonal corrector) only where the mesh is non-orthogonal: on the hex mesh its
         # right-hand side is pure round-off
-        multi = (2, True, 2) if mesh_name == "skew" else (1, False, 2)
+        multi = (2, True, 2) if mesh_name != "hex_mixed" else (1, False, 2)
         for solver, npcor, lsq, nigrad in (("dpcg", 1, False, 1), ("iccg",) + multi, ("bicgstab", 1, False, 1)):
             # With >1 rank the non-orthogonal corrector system of the reference is singular AND inconsistent
             # (each rank evaluates fluxmc of a shared face from its own side and the formula is not
             # antisymmetric: sum(su) != 0), so its CG solve diverges in the reference algorithm itself.
             # The corrector path is therefore compared with both solves capped at 6 iterations.
             kw = dict(solver=solver, flomas=flomas, npcor=npcor, lsq_flag=lsq, nigrad=nigrad, sor=1e-7,
-                      nsw=6 if npcor > 1 else 400)
+                      nsw=6 if npcor > 1 else 400,
+                      flux_variant=1 if mesh_name == "poly" else 0)   # see test_config5_polyhedral_path
             ctx = lib.Context(local)
             parallel.init_comm(ctx)
             ctx.set_mesh(part)

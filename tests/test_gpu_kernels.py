@@ -1,0 +1,184 @@
+"""GPU tests of the kernel variants behind the C ABI: the TMA-staged SpMV pipeline vs the CSR-stream
+kernel, the persistent cooperative DPCG kernel vs one launch per vector operation, ragged and
+over-long rows, and -- at BASELINE's full 216^3 size -- size-independent properties that need no
+oracle run (symmetry of the assembled operator, the true residual of the converged solve).
+"""
+import numpy as np
+import pytest
+
+from freecappuccino_b200 import cases, mesh as M
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fc():
+    from freecappuccino_b200 import lib
+    return lib
+
+
+def banded_csr(n, half_width, rng, ragged=True):
+    """1-based CSR of a symmetric positive definite banded matrix; rows keep a random subset of the band."""
+    rows, cols = [], []
+    for i in range(n):
+        lo, hi = max(0, i - half_width), min(n - 1, i + half_width)
+        for j in range(lo, hi + 1):
+            if j == i or not ragged or ((i * 2654435761 + j * 40503) ^ (j * 2654435761 + i * 40503)) % 3 != 0:
+                rows.append(i); cols.append(j)
+    rows, cols = np.array(rows), np.array(cols)
+    val = np.where(rows == cols, 0.0, -rng.random(rows.size) - 0.1)
+    # symmetrise the values and make the matrix diagonally dominant
+    key = {}
+    for k, (i, j) in enumerate(zip(rows, cols)):
+        key[(i, j)] = k
+    for (i, j), k in key.items():
+        if i < j and (j, i) in key:
+            val[key[(j, i)]] = val[k]
+    rowsum = np.zeros(n)
+    np.add.at(rowsum, rows, np.abs(val))
+    val[rows == cols] = rowsum + 1.0
+    ioffset = np.zeros(n + 1, np.int32)
+    np.add.at(ioffset, rows + 1, 1)
+    ioffset = (np.cumsum(ioffset) + 1).astype(np.int32)
+    diag = np.array([key[(i, i)] + 1 for i in range(n)], np.int32)
+    return ioffset, (cols + 1).astype(np.int32), diag, val
+
+
+@pytest.mark.parametrize("n,half_width", [(5, 1), (333, 3), (1000, 12), (700, 60)])
+@pytest.mark.parametrize("solver", ["dpcg", "iccg", "bicgstab"])
+def test_explicit_csr_ragged_rows_all_kernel_variants(fc, n, half_width, solver):
+    """fc_solve_csr on ragged banded systems: row counts that are not multiples of 32 or 256, rows of
+    very different length, and (half_width 60) 256-row chunks that exceed every staging buffer, which
+    takes the pipeline's straight-from-global fallback.  All kernel variants must agree with the oracle."""
+    rng = np.random.default_rng(n + half_width)
+    ioffset, ja, diag, a = banded_csr(n, half_width, rng)
+    b = rng.standard_normal(n)
+    csr = oracle.Csr(ioffset, ja, diag)
+    xo = np.zeros(n)
+    res0_o, resl_o, iters_o, _ = oracle.solve(solver, csr, a, b, xo, sor=1e-10, nsw=500)
+    opts = fc.solver_opts(1e-10, 500)
+    for spmv_kernel in (0, 1):
+        for persistent in ((0, 1) if solver == "dpcg" else (0,)):
+            ctx = fc.Context(0)
+            ctx.set_tuning(fc.TUNE_SPMV_KERNEL, spmv_kernel)
+            ctx.set_tuning(fc.TUNE_DPCG_PERSISTENT, persistent)
+            x = np.zeros(n)
+            rep = ctx.solve_csr(solver, ioffset, ja, diag, a, b, x, opts)
+            assert abs(rep.iters - iters_o) <= 1, (spmv_kernel, persistent, rep.iters, iters_o)
+            assert rep.res0 == pytest.approx(res0_o, rel=1e-12)
+            assert cases.rel_l2(x, xo) < 1e-8, (spmv_kernel, persistent)
+            if persistent:
+                assert ctx.timings().persist_iters == rep.iters, "the persistent kernel did not run"
+            ctx.close()
+
+
+@pytest.mark.parametrize("name", ["hex", "skew"])
+def test_spmv_variants_bit_identical(fc, name):
+    mesh = cases.hex_case(37, 29, 13) if name == "hex" else cases.skew_case(21, 17, 9)
+    ref = oracle.create_csr(mesh)
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal(mesh.nnz)
+    x = rng.standard_normal(mesh.numTotal)
+    want = oracle.spmv(ref, a, x)
+    for kernel in (0, 1):
+        for geo in (0, 1, 2, 3):
+            ctx = fc.Context(0)
+            ctx.set_mesh(mesh)
+            ctx.create_csr(download=False)
+            ctx.set_tuning(fc.TUNE_SPMV_KERNEL, kernel)
+            ctx.set_tuning(fc.TUNE_PIPE_GEOMETRY, geo)
+            ctx.upload("A", a)
+            ctx.upload("PP", x)
+            ctx.spmv("PP", "SCRATCH_T")
+            assert np.array_equal(ctx.download("SCRATCH_T")[:mesh.numCells], want), (kernel, geo)
+            ctx.close()
+            if kernel == 0:
+                break
+
+
+def test_dpcg_persistent_equals_multi_kernel(fc):
+    """Same system, both DPCG paths: identical iteration count, residual histories equal to round-off
+    (the reductions group the same terms differently), same solution."""
+    mesh = cases.hex_case(40, 36, 20, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry"))
+    out = {}
+    for persistent in (0, 1):
+        ctx = fc.Context(0)
+        ctx.set_mesh(mesh)
+        ctx.create_csr(download=False)
+        ctx.set_tuning(fc.TUNE_DPCG_PERSISTENT, persistent)
+        ctx.upload("APU", -np.ones(mesh.numCells))
+        ctx.upload("SU", cases.poisson_rhs(mesh))
+        ctx.fill("PP", 0.0)
+        ctx.laplacian("APU", "PP")
+        rep = ctx.solve("dpcg", "PP", fc.solver_opts(1e-9, 5000))
+        out[persistent] = (rep.iters, rep.res0, rep.resl, ctx.download("PP")[:mesh.numCells], ctx.timings().persist_iters)
+        ctx.close()
+    assert out[1][4] == out[1][0] and out[0][4] == 0
+    assert out[0][0] == out[1][0]
+    assert out[0][1] == pytest.approx(out[1][1], rel=1e-13)
+    assert out[0][2] == pytest.approx(out[1][2], rel=1e-6)
+    assert cases.rel_l2(out[0][3], out[1][3]) < 1e-10
+
+
+def test_early_return_when_already_converged(fc):
+    """dpcg.f90:66-70: res0 < tol returns before the first iteration (persistent and multi-kernel path)."""
+    mesh = cases.hex_case(8, 8, 8)
+    for persistent in (0, 1):
+        ctx = fc.Context(0)
+        ctx.set_mesh(mesh)
+        ctx.create_csr(download=False)
+        ctx.set_tuning(fc.TUNE_DPCG_PERSISTENT, persistent)
+        ctx.upload("APU", -np.ones(mesh.numCells))
+        ctx.fill("SU", 0.0)
+        ctx.fill("PP", 0.0)
+        ctx.laplacian("APU", "PP")
+        rep = ctx.solve("dpcg", "PP", fc.solver_opts(1e-8, 100))
+        assert rep.iters == 0 and rep.res0 == 0.0
+        assert np.all(ctx.download("PP") == 0.0)
+        ctx.close()
+
+
+def test_full_size_216_properties(fc):
+    """BASELINE config 4 at its full size (10 077 696 cells): the oracle would need minutes, so the checks are
+    size-independent properties -- the assembled p' operator is symmetric (x.Ay == y.Ax), its rows sum to the
+    boundary part only (A 1 = 0 in a closed box), and the converged DPCG solution satisfies the system:
+    |su - A pp|_1 / res0 < sor, with the TRUE residual computed by an independent SpMV launch."""
+    n = 216
+    mesh = M.hex_mesh(n, n, n)
+    f = cases.config4_fields(mesh)
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    for k, name in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("apu", "APU"), ("apv", "APV"),
+                    ("apw", "APW")):
+        ctx.upload(name, f[k])
+    ctx.grad_gauss("P", "DPDXI", 1)
+    opts = fc.calcp_opts(solver="dpcg", const_mflux=True, sor=1e-8, nsw=100000, pRefCell=1, urf_p=0.3)
+    ctx.calcp_assemble(opts)
+    su = ctx.download("SU")
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(mesh.numTotal)
+    y = rng.standard_normal(mesh.numTotal)
+    nc = mesh.numCells
+    ctx.upload("USER0", x)
+    ctx.spmv("USER0", "SCRATCH_T")
+    ax = ctx.download("SCRATCH_T")[:nc]
+    ctx.upload("USER0", y)
+    ctx.spmv("USER0", "SCRATCH_T")
+    ay = ctx.download("SCRATCH_T")[:nc]
+    assert abs(np.dot(y[:nc], ax) - np.dot(x[:nc], ay)) <= 1e-10 * (np.linalg.norm(ax) * np.linalg.norm(y[:nc]))
+    ctx.fill("USER0", 1.0)
+    ctx.spmv("USER0", "SCRATCH_T")
+    assert np.max(np.abs(ctx.download("SCRATCH_T")[:nc])) <= 1e-9 * np.max(np.abs(ax))
+    # conservation: the mass-imbalance source of a closed box sums to zero
+    assert abs(su.sum()) <= 1e-9 * np.abs(su).sum()
+    ctx.fill("PP", 0.0)
+    rep = ctx.solve("dpcg", "PP", fc.solver_opts(1e-8, 100000))
+    assert 1000 < rep.iters < 2500 and rep.resl / rep.res0 < 1e-8
+    assert ctx.timings().persist_iters == rep.iters
+    ctx.spmv("PP", "SCRATCH_T")
+    r = su - ctx.download("SCRATCH_T")[:nc]
+    assert rep.res0 == pytest.approx(np.abs(su).sum(), rel=1e-12)
+    assert np.abs(r).sum() / rep.res0 < 1.05e-8
+    ctx.close()
