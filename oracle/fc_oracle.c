@@ -740,3 +740,5 @@ int fco_calcp(const fco_mesh *g, const fco_csr *m, fco_fields *f, const fco_calc
   rep->globalContErr = gl;
   return 0;
 }
+
+#include "fc_oracle_uvw.c"

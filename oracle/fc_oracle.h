@@ -127,6 +127,41 @@ void fco_fluxmc(const fco_mesh *g, const fco_fields *f, int ijp, int ijn,
                 double xf, double yf, double zf, double arx, double ary, double arz,
                 double lambda, double *fmcor);
 
+/* ---- momentum predictor calcuvw (fc_oracle_uvw.c) ---- */
+typedef struct {
+  const double *vis;                          /* [numTotal] effective viscosity                    */
+  const double *uo, *vo, *wo, *uoo, *voo, *woo; /* [numTotal] previous time levels (bdf / cn)      */
+  const double *t;                            /* [numTotal] temperature (buoyancy) or NULL         */
+  double *sv, *sw, *spu, *spv, *sp;           /* [numCells] module sparse_matrix                   */
+  double *apu, *apv, *apw;                    /* [numCells] written: 1/(a(diag)+small)             */
+} fco_uvw;
+
+typedef struct {
+  int nigrad, nipgrad;
+  int scheme;        /* 0 central, 1 cds-corrected, 2 central-f, 3 linear-f, 4 muscl-f, 5 flux limiter   */
+  int limiter;       /* scheme 5: 0 smart, 1 avl-smart, 2 muscl, 3 umist, 4 koren, 5 charm, 6 ospre, 7 linear */
+  double gds;        /* gds(iu)                                                                      */
+  double urf[3];     /* urf(iu), urf(iv), urf(iw)                                                    */
+  double sor[3];     /* sor(iu..iw)                                                                  */
+  int nsw[3];        /* nsw(iu..iw)                                                                  */
+  int bdf; double btime, timestep; int cn;
+  int const_mflux; double gradPcmf;
+  int lbuoy, boussinesq; double beta, tref, densit, gravx, gravy, gravz;
+  double viscos;
+  fco_solver_opts sol; /* small, tol, parallel (sor / nsw taken from the arrays above)               */
+} fco_uvw_opts;
+
+typedef struct { fco_report rep[3]; } fco_uvw_report;
+
+void fco_facefluxuvw(const fco_mesh *g, const fco_fields *f, const fco_uvw *x, const fco_uvw_opts *o, int ijp,
+                     int ijn, double xf, double yf, double zf, double arx, double ary, double arz, double flomass,
+                     double lambda, double gam, double *cap, double *can, double *sup, double *svp, double *swp);
+int fco_calcuvw_assemble(const fco_mesh *g, const fco_csr *m, fco_fields *f, fco_uvw *x, const fco_uvw_opts *o);
+int fco_calcuvw_component(const fco_mesh *g, const fco_csr *m, fco_fields *f, fco_uvw *x, const fco_uvw_opts *o,
+                          int comp, fco_report *rep);
+int fco_calcuvw(const fco_mesh *g, const fco_csr *m, fco_fields *f, fco_uvw *x, const fco_uvw_opts *o,
+                fco_uvw_report *rep);
+
 /* ---- src-parallel semantics: R ranks in lock step inside one process (fc_oracle_par.c) ---- */
 typedef struct {
   fco_mesh g;

@@ -23,7 +23,7 @@ TOL = float(np.float32(1e-13))        # dpcg.f90:37
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libfc_oracle.so")
-    src = [os.path.join(_HERE, f) for f in ("fc_oracle.c", "fc_oracle_par.c", "fc_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("fc_oracle.c", "fc_oracle_uvw.c", "fc_oracle_par.c", "fc_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libfc_oracle.so"])
     return so
@@ -86,7 +86,8 @@ def lib() -> C.CDLL:
     if _LIB is None:
         _LIB = C.CDLL(build())
         _LIB.fco_create_csr.restype = C.c_int
-        for f in ("fco_dpcg", "fco_iccg", "fco_bicgstab", "fco_calcp"):
+        for f in ("fco_dpcg", "fco_iccg", "fco_bicgstab", "fco_calcp", "fco_calcuvw", "fco_calcuvw_assemble",
+                  "fco_calcuvw_component"):
             getattr(_LIB, f).restype = C.c_int
     return _LIB
 
@@ -251,4 +252,81 @@ def calcp(mesh, csr: Csr, f: Fields, opts: FcoCalcpOpts) -> FcoCalcpReport:
     rep = FcoCalcpReport()
     rc = lib().fco_calcp(C.byref(ms), C.byref(cs), C.byref(fs), C.byref(opts), C.byref(rep))
     assert rc == 0
+    return rep
+
+
+# ---- momentum predictor calcuvw (fc_oracle_uvw.c) ----
+SCHEMES = {"central": (0, 7), "cds-corrected": (1, 7), "central-f": (2, 7), "linear-f": (3, 7), "muscl-f": (4, 7),
+           "smart": (5, 0), "avl-smart": (5, 1), "muscl": (5, 2), "umist": (5, 3), "koren": (5, 4), "charm": (5, 5),
+           "ospre": (5, 6), "linear": (5, 7)}   # read_input.f90:97-133 -> (face_value branch, limiter)
+
+
+class FcoUvw(C.Structure):
+    _fields_ = [(n, dp) for n in ("vis", "uo", "vo", "wo", "uoo", "voo", "woo", "t", "sv", "sw", "spu", "spv", "sp",
+                                  "apu", "apv", "apw")]
+
+
+class FcoUvwOpts(C.Structure):
+    _fields_ = [("nigrad", C.c_int), ("nipgrad", C.c_int), ("scheme", C.c_int), ("limiter", C.c_int),
+                ("gds", C.c_double), ("urf", C.c_double * 3), ("sor", C.c_double * 3), ("nsw", C.c_int * 3),
+                ("bdf", C.c_int), ("btime", C.c_double), ("timestep", C.c_double), ("cn", C.c_int),
+                ("const_mflux", C.c_int), ("gradPcmf", C.c_double),
+                ("lbuoy", C.c_int), ("boussinesq", C.c_int), ("beta", C.c_double), ("tref", C.c_double),
+                ("densit", C.c_double), ("gravx", C.c_double), ("gravy", C.c_double), ("gravz", C.c_double),
+                ("viscos", C.c_double), ("sol", FcoSolverOpts)]
+
+
+class FcoUvwReport(C.Structure):
+    _fields_ = [("rep", FcoReport * 3)]
+
+
+class UvwFields:
+    """The extra arrays of ``module variables`` / ``sparse_matrix`` calcuvw touches (vis, old time levels,
+    sv, sw, spu, spv, sp); apu/apv/apw alias the arrays of a ``Fields`` so that calcp sees the update."""
+
+    NAMES = ("vis", "uo", "vo", "wo", "uoo", "voo", "woo", "t", "sv", "sw", "spu", "spv", "sp", "apu", "apv", "apw")
+
+    def __init__(self, mesh, f: "Fields", viscos: float = 0.0):
+        nt, n = mesh.numTotal, mesh.numCells
+        z = np.zeros
+        self.vis = np.full(nt, float(viscos))
+        self.uo, self.vo, self.wo, self.uoo, self.voo, self.woo = z(nt), z(nt), z(nt), z(nt), z(nt), z(nt)
+        self.t = z(nt)
+        self.sv, self.sw, self.spu, self.spv, self.sp = z(n), z(n), z(n), z(n), z(n)
+        self.apu, self.apv, self.apw = f.apu, f.apv, f.apw
+
+    def c(self) -> FcoUvw:
+        return FcoUvw(*[_d(getattr(self, k)) for k in self.NAMES])
+
+
+def uvw_opts(scheme="muscl-f", gds=1.0, urf=(0.7, 0.7, 0.7), sor=(1e-2, 1e-2, 1e-2), nsw=(20, 20, 20), nigrad=1,
+             bdf=False, btime=0.0, timestep=1e20, cn=False, const_mflux=False, gradPcmf=0.0, lbuoy=False,
+             boussinesq=True, beta=0.0, tref=0.0, densit=1.0, grav=(0.0, 0.0, 0.0), viscos=0.01, small=SMALL,
+             tol=TOL) -> FcoUvwOpts:
+    sc, lim = SCHEMES[scheme]
+    return FcoUvwOpts(nigrad, 2, sc, lim, gds, (C.c_double * 3)(*urf), (C.c_double * 3)(*sor), (C.c_int * 3)(*nsw),
+                      int(bdf), btime, timestep, int(cn), int(const_mflux), gradPcmf, int(lbuoy), int(boussinesq),
+                      beta, tref, densit, grav[0], grav[1], grav[2], viscos, FcoSolverOpts(0.0, 0, small, tol, 0))
+
+
+def calcuvw_assemble(mesh, csr: Csr, f: Fields, x: UvwFields, opts: FcoUvwOpts) -> None:
+    ms, cs, fs, xs = mesh_struct(mesh), csr.c(), f.c(), x.c()
+    rc = lib().fco_calcuvw_assemble(C.byref(ms), C.byref(cs), C.byref(fs), C.byref(xs), C.byref(opts))
+    assert rc == 0, rc
+
+
+def calcuvw_component(mesh, csr: Csr, f: Fields, x: UvwFields, opts: FcoUvwOpts, comp: int) -> FcoReport:
+    ms, cs, fs, xs = mesh_struct(mesh), csr.c(), f.c(), x.c()
+    rep = FcoReport()
+    rc = lib().fco_calcuvw_component(C.byref(ms), C.byref(cs), C.byref(fs), C.byref(xs), C.byref(opts), comp,
+                                     C.byref(rep))
+    assert rc == 0, rc
+    return rep
+
+
+def calcuvw(mesh, csr: Csr, f: Fields, x: UvwFields, opts: FcoUvwOpts) -> FcoUvwReport:
+    ms, cs, fs, xs = mesh_struct(mesh), csr.c(), f.c(), x.c()
+    rep = FcoUvwReport()
+    rc = lib().fco_calcuvw(C.byref(ms), C.byref(cs), C.byref(fs), C.byref(xs), C.byref(opts), C.byref(rep))
+    assert rc == 0, rc
     return rep
