@@ -86,6 +86,7 @@ int alloc_fields(fc_context *ctx) {
 }
 
 int check_field(fc_context *ctx, int f, size_t min_n, const char *who) {
+  if (f >= FC_VIS && f < FC_NUM_FIELDS && !ctx->field[f] && ctx->has_mesh) FC_CHECK(fc_momentum_fields(ctx));
   if (f < 0 || f >= FC_NUM_FIELDS || !ctx->field[f])
     FC_FAIL(FC_ERR_ARG, std::string(who) + ": unknown or unallocated field id " + std::to_string(f));
   if (ctx->field_n[f] < min_n)
@@ -103,7 +104,7 @@ void free_all(fc_context *ctx) {
                   (void *)ctx->vk, (void *)ctx->adiag, (void *)ctx->tt, (void *)ctx->coef, (void *)ctx->facev,
                   (void *)ctx->gtmp, (void *)ctx->partials, (void *)ctx->sc, (void *)ctx->bufind,
                   (void *)ctx->sendbuf, (void *)ctx->strip_off, (void *)ctx->strip_idx,
-                  (void *)ctx->strip_any32, (void *)ctx->persist})
+                  (void *)ctx->strip_any32, (void *)ctx->persist, (void *)ctx->uvw_face})
     if (p) cudaFree(p);
   for (int f = 0; f < FC_NUM_FIELDS; ++f)
     if (ctx->field[f]) cudaFree(ctx->field[f]);
@@ -115,9 +116,21 @@ void free_all(fc_context *ctx) {
 
 }  // namespace
 
+// Fields of the momentum predictor (module variables: vis, uo.., t; sparse_matrix: sv, sw, spu, spv, sp) and its
+// per-face scratch: allocated at the first fc_upload / fc_calcuvw that names them, not per call.
+int fc_momentum_fields(fc_context *ctx) {
+  if (!ctx->has_mesh) FC_FAIL(FC_ERR_ARG, "momentum fields: call fc_set_mesh first");
+  if (ctx->uvw_face) return FC_OK;
+  const size_t n = ctx->n, NT = ctx->NT, NP = (size_t)ctx->n + ctx->npro;
+  for (int f : {FC_VIS, FC_UO, FC_VO, FC_WO, FC_UOO, FC_VOO, FC_WOO, FC_T}) FC_CHECK(alloc_field(ctx, f, NT > NP ? NT : NP));
+  for (int f : {FC_SV, FC_SW, FC_SPU, FC_SPV, FC_SP}) FC_CHECK(alloc_field(ctx, f, n));
+  FC_CHECK(fc_dev_alloc(ctx, &ctx->uvw_face, 6 * (size_t)ctx->F));
+  return FC_OK;
+}
+
 extern "C" {
 
-int fc_version(void) { return 100; }
+int fc_version(void) { return 101; }
 
 const char *fc_last_error(const fc_context *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -201,6 +214,15 @@ int fc_set_mesh(fc_context *ctx, const fc_mesh_desc *m) {
     FC_FAIL(FC_ERR_ARG, "fc_set_mesh: NULL geometry array");
   if (m->npro > 0 && (!m->fpro || !m->neighbProcNo || !m->neighbProcOffset || m->numConnections < 1))
     FC_FAIL(FC_ERR_ARG, "fc_set_mesh: processor boundary without fpro / neighbProcNo / neighbProcOffset");
+  if (ctx->uvw_face) {  // momentum fields are sized by the mesh: drop them, they come back on first use
+    cudaFree(ctx->uvw_face);
+    ctx->uvw_face = nullptr;
+    for (int f = FC_VIS; f < FC_NUM_FIELDS; ++f) {
+      if (ctx->field[f]) cudaFree(ctx->field[f]);
+      ctx->field[f] = nullptr;
+      ctx->field_n[f] = 0;
+    }
+  }
   ctx->m = *m;
   ctx->n = m->numCells; ctx->F = m->numInnerFaces; ctx->NF = m->numFaces; ctx->NT = m->numTotal;
   ctx->npro = m->npro; ctx->NP = m->numCells + m->npro;
@@ -449,6 +471,45 @@ int fc_calcp_host(fc_context *ctx, const fc_calcp_opts *o, double *u, double *v,
   FC_CHECK(fc_calcp_dev(ctx, o, rep));
   const struct { int f; double *h; size_t n; } dn[] = {{FC_U, u, NT}, {FC_V, v, NT}, {FC_W, w, NT}, {FC_P, p, NT},
                                                       {FC_PP, pp, NT}, {FC_FLMASS, flmass, (size_t)ctx->F}};
+  for (auto &t : dn)
+    if (t.h) FC_CUDA(cudaMemcpyAsync(t.h, ctx->field[t.f], sizeof(double) * t.n, cudaMemcpyDeviceToHost, st));
+  FC_CUDA(cudaStreamSynchronize(st));
+  return FC_OK;
+}
+
+int fc_calcuvw_assemble(fc_context *ctx, const fc_calcuvw_opts *o) {
+  if (!ctx || !o) return FC_ERR_ARG;
+  FC_CUDA(cudaSetDevice(ctx->device));
+  return fc_calcuvw_assemble_dev(ctx, o);
+}
+
+int fc_calcuvw_component(fc_context *ctx, const fc_calcuvw_opts *o, int comp, fc_solver_report *rep) {
+  if (!ctx || !o || !rep) return FC_ERR_ARG;
+  FC_CUDA(cudaSetDevice(ctx->device));
+  return fc_calcuvw_component_dev(ctx, o, comp, rep);
+}
+
+int fc_calcuvw(fc_context *ctx, const fc_calcuvw_opts *o, fc_calcuvw_report *rep) {
+  if (!ctx || !o || !rep) return FC_ERR_ARG;
+  FC_CUDA(cudaSetDevice(ctx->device));
+  return fc_calcuvw_dev(ctx, o, rep);
+}
+
+int fc_calcuvw_host(fc_context *ctx, const fc_calcuvw_opts *o, double *u, double *v, double *w, double *p,
+                    const double *vis, const double *flmass, double *apu, double *apv, double *apw,
+                    fc_calcuvw_report *rep) {
+  if (!ctx || !o || !rep || !u || !v || !w || !p || !vis || !flmass) return FC_ERR_ARG;
+  if (!ctx->has_mesh) FC_FAIL(FC_ERR_ARG, "fc_calcuvw_host: no mesh");
+  FC_CUDA(cudaSetDevice(ctx->device));
+  FC_CHECK(fc_momentum_fields(ctx));
+  cudaStream_t st = ctx->stream;
+  const size_t NT = ctx->NT, n = ctx->n;
+  const struct { int f; const double *h; size_t n; } up[] = {{FC_U, u, NT}, {FC_V, v, NT}, {FC_W, w, NT}, {FC_P, p, NT},
+                                                            {FC_VIS, vis, NT}, {FC_FLMASS, flmass, (size_t)ctx->F}};
+  for (auto &t : up) FC_CUDA(cudaMemcpyAsync(ctx->field[t.f], t.h, sizeof(double) * t.n, cudaMemcpyHostToDevice, st));
+  FC_CHECK(fc_calcuvw_dev(ctx, o, rep));
+  const struct { int f; double *h; size_t n; } dn[] = {{FC_U, u, NT}, {FC_V, v, NT}, {FC_W, w, NT}, {FC_P, p, NT},
+                                                      {FC_APU, apu, n}, {FC_APV, apv, n}, {FC_APW, apw, n}};
   for (auto &t : dn)
     if (t.h) FC_CUDA(cudaMemcpyAsync(t.h, ctx->field[t.f], sizeof(double) * t.n, cudaMemcpyDeviceToHost, st));
   FC_CUDA(cudaStreamSynchronize(st));

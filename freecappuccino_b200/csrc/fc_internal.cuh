@@ -125,6 +125,7 @@ struct fc_context {
   double *coef = nullptr;               // per-face coefficient cap = can [F + npro]
   double *facev = nullptr;              // per-face scratch [NF]
   double *gtmp = nullptr;               // previous-pass gradient (3,numCells)
+  double *uvw_face = nullptr;           // momentum predictor: can, cap, sup, svp, swp, fie per inner face [6 F]
   double *partials = nullptr;           // [FC_MAX_RED * FC_RED_GRID]
   fc_scalars *sc = nullptr;             // device
   fc_scalars *sc_host = nullptr;        // pinned
@@ -239,3 +240,7 @@ int fc_dpcg_persistent(fc_context *ctx, double *fi, const fc_solver_opts *o, fc_
                        bool *handled);                                                   // fc_dpcg_persist.cu
 int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opts *o, fc_solver_report *rep,
                     double *hist);
+int fc_momentum_fields(fc_context *ctx);                            // fc_capi.cu: FC_VIS.. + face scratch, first use
+int fc_calcuvw_assemble_dev(fc_context *ctx, const fc_calcuvw_opts *o);                   // fc_momentum.cu
+int fc_calcuvw_component_dev(fc_context *ctx, const fc_calcuvw_opts *o, int comp, fc_solver_report *rep);
+int fc_calcuvw_dev(fc_context *ctx, const fc_calcuvw_opts *o, fc_calcuvw_report *rep);

@@ -1,0 +1,172 @@
+// Momentum predictor `call calcuvw` (src/calcuvw.f90:3-557) on device-resident fields: the step
+// immediately before the pressure-correction path.  It produces apu/apv/apw,
+// u/v/w and leaves the boundary pressure and dPdxi that calcp reads, so a whole SIMPLE iteration
+// (calcuvw + calcp) runs without a host round trip of any field.
+//
+// Launches per call: 3 x grad_gauss (U, V, W) + nipgrad x (bpres + grad_gauss) of the pressure,
+// one face kernel (F threads), one row kernel (n threads), then per velocity component one
+// diagonal / under-relaxation kernel (n threads) and the BiCGStab(DILU) solve of fc_krylov.cu.
+// The per-index arithmetic lives in fc_momentum_body.cuh.
+//
+// Algorithmic bytes (n cells, F inner faces, B boundary faces), each datum once:
+//   face kernel   2 idx 8 + 7 geometry 56 + flmass 8 + 6 results 48 per face = 120 F, plus per cell the
+//                 gathered xc,yc,zc,vis,u,v,w,p (64) and four gradients (96) = 160 n
+//   row kernel    6 face results 48 + 3 area components 24 (each face is read by its two cells: x2)
+//                 + 3 map ints 12 per entry -> (72 + 12) * 2 F + off-diagonals 16 F = 184 F, per cell
+//                 vol, den, 3 old velocities, 6 results = 88 n
+//   component     row of a (8 nnz) + diag/ioffset 8 n + s, sp, phi, su, ap 40 n = 8 nnz + 48 n, x3
+// All HBM-bound; no tensor cores (FP64 gather work).
+#include "fc_momentum_body.cuh"
+#include "fc_reduce.cuh"
+
+// fc_assemble.cu
+int fc_grad_gauss_dev(fc_context *ctx, double *phi, double *grad, int nigrad);
+int fc_bpres_dev(fc_context *ctx, double *p, const double *dPdxi, int istage);
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+k_uvw_faces(fcm_geom g, fcm_flow f, fcm_opts o, fcm_faces out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.F) fcm_face(g, f, o, out, i);
+}
+
+__global__ void __launch_bounds__(256)
+k_uvw_rows(fcm_geom g, fcm_c2f m, fcm_slots sl, fcm_flow f, fcm_opts o, fcm_faces fa, fcm_rows r) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < g.n) fcm_row(g, m, sl, f, o, fa, r, c);
+}
+
+__global__ void __launch_bounds__(256)
+k_uvw_component(fcm_geom g, fcm_c2f m, fcm_comp k) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < g.n) fcm_component(g, m, k, c);
+}
+
+// a = 0.5 a, the whole array (calcuvw.f90:386-389)
+__global__ void k_halve(double *a, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = 0.5 * a[i];
+}
+
+fcm_geom geom_of(const fc_context *ctx) {
+  return fcm_geom{ctx->owner, ctx->neigh, ctx->xc, ctx->yc, ctx->zc, ctx->vol, ctx->arx, ctx->ary, ctx->arz,
+                  ctx->xf, ctx->yf, ctx->zf, ctx->facint, ctx->n, ctx->F};
+}
+fcm_c2f c2f_of(const fc_context *ctx) { return fcm_c2f{ctx->c2f_off, ctx->c2f_face, ctx->c2f_other, ctx->c2f_pos}; }
+fcm_slots slots_of(const fc_context *ctx) {
+  const fc_mesh_desc &m = ctx->m;
+  fcm_slots s;
+  const int cnt[5] = {m.ninl, m.nout, m.nsym, m.nwal, m.npru};
+  const int fst[5] = {m.iInletFacesStart, m.iOutletFacesStart, m.iSymmetryFacesStart, m.iWallFacesStart,
+                      m.iPressOutletFacesStart};
+  int slot = ctx->n + ctx->npro;
+  for (int b = 0; b < 5; ++b) { s.count[b] = cnt[b]; s.face[b] = fst[b]; s.slot[b] = slot; slot += cnt[b]; }
+  return s;
+}
+fcm_flow flow_of(fc_context *ctx) {
+  double **fl = ctx->field;
+  return fcm_flow{fl[FC_U], fl[FC_V], fl[FC_W], fl[FC_P], fl[FC_DEN], fl[FC_VIS], fl[FC_FLMASS], fl[FC_FMI],
+                  fl[FC_FMO], fl[FC_DUDXI], fl[FC_DVDXI], fl[FC_DWDXI], fl[FC_DPDXI], fl[FC_UO], fl[FC_VO],
+                  fl[FC_WO], fl[FC_UOO], fl[FC_VOO], fl[FC_WOO], fl[FC_T]};
+}
+fcm_opts opts_of(const fc_calcuvw_opts *o) {
+  return fcm_opts{o->scheme, o->limiter, o->gds, o->bdf, o->btime, o->timestep, o->cn, o->const_mflux,
+                  o->gradPcmf, o->lbuoy, o->boussinesq, o->beta, o->tref, o->densit, o->gravx, o->gravy,
+                  o->gravz, o->viscos};
+}
+fcm_faces faces_of(const fc_context *ctx) {
+  const size_t F = (size_t)ctx->F;
+  double *b = ctx->uvw_face;
+  return fcm_faces{b, b + F, b + 2 * F, b + 3 * F, b + 4 * F, b + 5 * F};
+}
+
+int check_opts(fc_context *ctx, const fc_calcuvw_opts *o, const char *who) {
+  if (!ctx->has_mesh || !ctx->has_csr || !ctx->c2f_off)
+    FC_FAIL(FC_ERR_ARG, std::string(who) + ": call fc_set_mesh and fc_create_csr first");
+  if (ctx->npro > 0 || ctx->nranks > 1)
+    FC_FAIL(FC_ERR_UNSUPPORTED, std::string(who) + ": the momentum predictor runs on one rank in this version "
+                                                   "(src-parallel/calcuvw.f90 processor faces are not ported yet)");
+  if (o->nigrad < 1 || o->nipgrad < 0) FC_FAIL(FC_ERR_ARG, std::string(who) + ": nigrad >= 1, nipgrad >= 0");
+  if (o->scheme < 0 || o->scheme > 5 || o->limiter < 0 || o->limiter > 7)
+    FC_FAIL(FC_ERR_ARG, std::string(who) + ": unknown convection scheme / limiter");
+  if ((o->bdf || o->cn) && !(o->timestep > 0.0)) FC_FAIL(FC_ERR_ARG, std::string(who) + ": timestep must be > 0");
+  for (int k = 0; k < 3; ++k)
+    if (!(o->urf[k] > 0.0)) FC_FAIL(FC_ERR_ARG, std::string(who) + ": urf must be > 0");
+  if (ctx->F > 0 && ctx->n < 3)  // fieldManipulation.f90:433-435 reads flat element ijn+6 of dPdxi(3,numCells)
+    FC_FAIL(FC_ERR_UNSUPPORTED, std::string(who) + ": needs numCells >= 3 (the reference's df(ijp,3) addressing)");
+  return FC_OK;
+}
+
+}  // namespace
+
+// calcuvw.f90:48-389: everything before the first per-component block
+int fc_calcuvw_assemble_dev(fc_context *ctx, const fc_calcuvw_opts *o) {
+  FC_CHECK(check_opts(ctx, o, "fc_calcuvw_assemble"));
+  FC_CHECK(fc_momentum_fields(ctx));
+  const int B = 256;
+  cudaStream_t st = ctx->stream;
+  FC_CUDA(cudaEventRecord(ctx->ev[2], st));
+  // grad(U), grad(V), grad(W)   (:59-61)
+  FC_CHECK(fc_grad_gauss_dev(ctx, ctx->field[FC_U], ctx->field[FC_DUDXI], o->nigrad));
+  FC_CHECK(fc_grad_gauss_dev(ctx, ctx->field[FC_V], ctx->field[FC_DVDXI], o->nigrad));
+  FC_CHECK(fc_grad_gauss_dev(ctx, ctx->field[FC_W], ctx->field[FC_DWDXI], o->nigrad));
+  // calcPressDiv: boundary pressure + pressure gradient (fieldManipulation.f90:82-87)
+  for (int istage = 1; istage <= o->nipgrad; ++istage) {
+    FC_CHECK(fc_bpres_dev(ctx, ctx->field[FC_P], ctx->field[FC_DPDXI], istage));
+    FC_CHECK(fc_grad_gauss_dev(ctx, ctx->field[FC_P], ctx->field[FC_DPDXI], o->nigrad));
+  }
+  const fcm_geom g = geom_of(ctx);
+  const fcm_flow f = flow_of(ctx);
+  const fcm_opts fo = opts_of(o);
+  const fcm_faces fa = faces_of(ctx);
+  if (ctx->F > 0) {
+    k_uvw_faces<<<fc_blocks(ctx->F, B), B, 0, st>>>(g, f, fo, fa);
+    FC_LAUNCH_CHECK();
+  }
+  double **fl = ctx->field;
+  const fcm_rows r{fl[FC_A], fl[FC_SU], fl[FC_SV], fl[FC_SW], fl[FC_SPU], fl[FC_SPV], fl[FC_SP]};
+  k_uvw_rows<<<fc_blocks(ctx->n, B), B, 0, st>>>(g, c2f_of(ctx), slots_of(ctx), f, fo, fa, r);
+  FC_LAUNCH_CHECK();
+  if (o->cn) {
+    k_halve<<<fc_blocks((size_t)ctx->nnz, B), B, 0, st>>>(fl[FC_A], (size_t)ctx->nnz);
+    FC_LAUNCH_CHECK();
+  }
+  FC_CUDA(cudaEventRecord(ctx->ev[3], st));
+  return FC_OK;
+}
+
+// one velocity component (comp = 0, 1, 2): Crank-Nicolson sources, diagonal, under-relaxation, ap*,
+// then `call bicgstab(u|v|w, iu|iv|iw)`   (calcuvw.f90:391-441, :447-498, :504-556)
+int fc_calcuvw_component_dev(fc_context *ctx, const fc_calcuvw_opts *o, int comp, fc_solver_report *rep) {
+  FC_CHECK(check_opts(ctx, o, "fc_calcuvw_component"));
+  if (comp < 0 || comp > 2) FC_FAIL(FC_ERR_ARG, "fc_calcuvw_component: comp must be 0, 1 or 2");
+  FC_CHECK(fc_momentum_fields(ctx));
+  double **fl = ctx->field;
+  const int s_f[3] = {FC_SU, FC_SV, FC_SW}, sp_f[3] = {FC_SPU, FC_SPV, FC_SP}, phi_f[3] = {FC_U, FC_V, FC_W};
+  const int old_f[3] = {FC_UO, FC_VO, FC_WO}, ap_f[3] = {FC_APU, FC_APV, FC_APW};
+  fcm_comp k{ctx->ioffset, ctx->diag, fl[FC_A], fl[s_f[comp]], fl[sp_f[comp]], fl[FC_SU], fl[ap_f[comp]],
+             fl[phi_f[comp]], fl[old_f[comp]], fl[FC_DEN], 1.0 / o->urf[comp], 1.0 - o->urf[comp],   // init.f90:80-81
+             o->sol.small, o->timestep, o->cn, comp > 0 ? 1 : 0};
+  k_uvw_component<<<fc_blocks(ctx->n, 256), 256, 0, ctx->stream>>>(geom_of(ctx), c2f_of(ctx), k);
+  FC_LAUNCH_CHECK();
+  fc_solver_opts so = o->sol;
+  so.sor = o->sor[comp];
+  so.nsw = o->nsw[comp];
+  return fc_solve_device(ctx, FC_BICGSTAB, fl[phi_f[comp]], &so, rep, nullptr);
+}
+
+int fc_calcuvw_dev(fc_context *ctx, const fc_calcuvw_opts *o, fc_calcuvw_report *rep) {
+  FC_CHECK(fc_calcuvw_assemble_dev(ctx, o));
+  double solve_ms = 0.0;
+  for (int comp = 0; comp < 3; ++comp) {
+    FC_CHECK(fc_calcuvw_component_dev(ctx, o, comp, &rep->rep[comp]));
+    solve_ms += ctx->tm.solve_ms;
+  }
+  FC_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ams = 0.f;
+  FC_CUDA(cudaEventElapsedTime(&ams, ctx->ev[2], ctx->ev[3]));
+  ctx->tm.uvw_assemble_ms = ams;
+  ctx->tm.uvw_solve_ms = solve_ms;
+  return FC_OK;
+}

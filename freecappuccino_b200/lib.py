@@ -22,7 +22,9 @@ DPCG, ICCG, BICGSTAB = 0, 1, 2
 SOLVERS = {"dpcg": DPCG, "iccg": ICCG, "bicgstab": BICGSTAB}
 
 FIELDS = ("U", "V", "W", "P", "PP", "DEN", "FLMASS", "APU", "APV", "APW", "DUDXI", "DVDXI", "DWDXI", "DPDXI",
-          "A", "SU", "RES", "FMI", "FMO", "APR", "FMPRO", "SCRATCH_T", "USER0", "USER1", "USER2", "USER3")
+          "A", "SU", "RES", "FMI", "FMO", "APR", "FMPRO", "SCRATCH_T", "USER0", "USER1", "USER2", "USER3",
+          # momentum predictor (fc_calcuvw), allocated on first use
+          "VIS", "UO", "VO", "WO", "UOO", "VOO", "WOO", "T", "SV", "SW", "SPU", "SPV", "SP")
 F = {name: i for i, name in enumerate(FIELDS)}
 
 SMALL = float(np.float32(1e-20))   # `small` of module parameters is a default-real literal (modules_allocatable.f90:27)
@@ -38,7 +40,8 @@ SYMBOLS = (
     "fc_grad_gauss", "fc_grad_gauss_corrected", "fc_bpres", "fc_laplacian", "fc_solve", "fc_solve_host",
     "fc_solve_csr", "fc_calcp_assemble", "fc_calcp", "fc_calcp_host", "fc_exchange", "fc_global_sum",
     "fc_get_timings", "fc_time_spmv", "fc_stream", "fc_copy", "fc_set_spmv_sampling", "fc_comm_p2p_blob",
-    "fc_comm_p2p_open", "fc_set_tuning",
+    "fc_comm_p2p_open", "fc_set_tuning", "fc_calcuvw_assemble", "fc_calcuvw_component", "fc_calcuvw",
+    "fc_calcuvw_host",
 )
 TUNE_SPMV_KERNEL, TUNE_DPCG_PERSISTENT, TUNE_CTAS_PER_SM, TUNE_PIPE_GEOMETRY = 0, 1, 2, 3
 
@@ -80,7 +83,38 @@ class Timings(C.Structure):
                 ("spmv_ms", C.c_double), ("spmv_samples", C.c_int), ("pad_", C.c_int), ("launches", C.c_longlong),
                 ("persist_ms", C.c_double), ("persist_pupdate_ms", C.c_double), ("persist_spmv_ms", C.c_double),
                 ("persist_update_ms", C.c_double), ("persist_iters", C.c_int), ("persist_grid", C.c_int),
-                ("persist_mail_ms", C.c_double)]
+                ("persist_mail_ms", C.c_double), ("uvw_assemble_ms", C.c_double), ("uvw_solve_ms", C.c_double)]
+
+
+# convective schemes of read_input.f90:97-133 -> (face_value branch, limiter) of fc_calcuvw_opts
+SCHEMES = {"central": (0, 7), "cds-corrected": (1, 7), "central-f": (2, 7), "linear-f": (3, 7), "muscl-f": (4, 7),
+           "smart": (5, 0), "avl-smart": (5, 1), "muscl": (5, 2), "umist": (5, 3), "koren": (5, 4), "charm": (5, 5),
+           "ospre": (5, 6), "linear": (5, 7)}
+
+
+class CalcuvwOpts(C.Structure):
+    _fields_ = [("nigrad", C.c_int), ("nipgrad", C.c_int), ("scheme", C.c_int), ("limiter", C.c_int),
+                ("gds", C.c_double), ("urf", C.c_double * 3), ("sor", C.c_double * 3), ("nsw", C.c_int * 3),
+                ("bdf", C.c_int), ("btime", C.c_double), ("timestep", C.c_double), ("cn", C.c_int),
+                ("const_mflux", C.c_int), ("gradPcmf", C.c_double),
+                ("lbuoy", C.c_int), ("boussinesq", C.c_int), ("beta", C.c_double), ("tref", C.c_double),
+                ("densit", C.c_double), ("gravx", C.c_double), ("gravy", C.c_double), ("gravz", C.c_double),
+                ("viscos", C.c_double), ("sol", SolverOpts)]
+
+
+class CalcuvwReport(C.Structure):
+    _fields_ = [("rep", SolverReport * 3)]
+
+
+def calcuvw_opts(scheme="muscl-f", gds=1.0, urf=(0.7, 0.7, 0.7), sor=(1e-2, 1e-2, 1e-2), nsw=(20, 20, 20), nigrad=1,
+                 bdf=False, btime=0.0, timestep=1e20, cn=False, const_mflux=False, gradPcmf=0.0, lbuoy=False,
+                 boussinesq=True, beta=0.0, tref=0.0, densit=1.0, grav=(0.0, 0.0, 0.0), viscos=0.01, small=SMALL,
+                 tol=TOL) -> CalcuvwOpts:
+    """Options of ``call calcuvw`` with the names of the reference's ``input`` file / module parameters."""
+    sc, lim = SCHEMES[scheme]
+    return CalcuvwOpts(nigrad, 2, sc, lim, gds, (C.c_double * 3)(*urf), (C.c_double * 3)(*sor), (C.c_int * 3)(*nsw),
+                       int(bdf), btime, timestep, int(cn), int(const_mflux), gradPcmf, int(lbuoy), int(boussinesq),
+                       beta, tref, densit, grav[0], grav[1], grav[2], viscos, SolverOpts(0.0, 0, small, tol, 0))
 
 
 class FcError(RuntimeError):
@@ -323,6 +357,26 @@ class Context:
         rep = CalcpReport()
         self._ck(self.lib.fc_calcp_host(self.h, C.byref(opts), _d(u), _d(v), _d(w), _d(p), _d(pp), _d(apu), _d(apv),
                                         _d(apw), _d(flmass), C.byref(rep)))
+        return rep
+
+    # -- momentum predictor ----------------------------
+    def calcuvw_assemble(self, opts: CalcuvwOpts):
+        self._ck(self.lib.fc_calcuvw_assemble(self.h, C.byref(opts)))
+
+    def calcuvw_component(self, opts: CalcuvwOpts, comp: int) -> SolverReport:
+        rep = SolverReport()
+        self._ck(self.lib.fc_calcuvw_component(self.h, C.byref(opts), comp, C.byref(rep)))
+        return rep
+
+    def calcuvw(self, opts: CalcuvwOpts) -> CalcuvwReport:
+        rep = CalcuvwReport()
+        self._ck(self.lib.fc_calcuvw(self.h, C.byref(opts), C.byref(rep)))
+        return rep
+
+    def calcuvw_host(self, opts: CalcuvwOpts, u, v, w, p, vis, flmass, apu, apv, apw) -> CalcuvwReport:
+        rep = CalcuvwReport()
+        self._ck(self.lib.fc_calcuvw_host(self.h, C.byref(opts), _d(u), _d(v), _d(w), _d(p), _d(vis), _d(flmass),
+                                          _d(apu), _d(apv), _d(apw), C.byref(rep)))
         return rep
 
     def exchange(self, field: str):

@@ -53,6 +53,9 @@ enum {
   FC_APR, FC_FMPRO,                                   /* npro               */
   FC_SCRATCH_T,                                       /* numTotal (user vec)*/
   FC_USER0, FC_USER1, FC_USER2, FC_USER3,             /* numTotal, caller's */
+  /* momentum predictor (fc_calcuvw); allocated on first use: */
+  FC_VIS, FC_UO, FC_VO, FC_WO, FC_UOO, FC_VOO, FC_WOO, FC_T, /* numTotal   */
+  FC_SV, FC_SW, FC_SPU, FC_SPV, FC_SP,                /* numCells           */
   FC_NUM_FIELDS
 };
 
@@ -210,6 +213,51 @@ int fc_calcp_host(fc_context *ctx, const fc_calcp_opts *o, double *u, double *v,
                   double *p, double *pp, const double *apu, const double *apv, const double *apw,
                   double *flmass, fc_calcp_report *rep);
 
+/* ---- momentum predictor: `call calcuvw` (src/calcuvw.f90:3-557) -----------
+ * The step immediately before calcp.  Device-resident
+ * inputs: FC_U/V/W, FC_P, FC_DEN, FC_VIS (effective viscosity `vis`), FC_FLMASS,
+ * FC_FMI, FC_FMO and, for bdf / cn, FC_UO..FC_WOO; buoyancy reads FC_T.
+ * Outputs: FC_U/V/W (solved), FC_APU/APV/APW = 1/(a(diag)+small), the boundary
+ * slots of FC_P and FC_DPDXI (calcPressDiv, fieldManipulation.f90:82-87),
+ * FC_DUDXI/DVDXI/DWDXI, FC_SV/SW/SPU/SPV/SP; FC_A / FC_SU hold the W system
+ * afterwards, exactly like the module arrays of the reference.
+ * Laminar form (lturb = .false.), serial `src` semantics, one rank, no O-C cuts. */
+typedef struct {
+  int nigrad, nipgrad;  /* parameters: nigrad, nipgrad (= 2)                        */
+  int scheme;           /* convective scheme (read_input.f90:97-133 -> face_value,
+                           interpolation.f90:36-57): 0 central, 1 cds-corrected,
+                           2 central-f, 3 linear-f, 4 muscl-f, 5 flux limiter       */
+  int limiter;          /* scheme 5: 0 smart, 1 avl-smart, 2 muscl, 3 umist, 4 koren,
+                           5 charm, 6 ospre, 7 linear (psi = 1)                     */
+  double gds;           /* gds(iu): deferred-correction blending                    */
+  double urf[3];        /* urf(iu), urf(iv), urf(iw)                                */
+  double sor[3];        /* sor(iu..iw)                                              */
+  int nsw[3];           /* nsw(iu..iw)                                              */
+  int bdf; double btime, timestep; int cn;
+  int const_mflux; double gradPcmf;
+  int lbuoy, boussinesq; double beta, tref, densit, gravx, gravy, gravz;
+  double viscos;        /* molecular viscosity (wall faces, calcuvw.f90:320)        */
+  fc_solver_opts sol;   /* small, tol, parallel (sor / nsw come from the arrays)    */
+} fc_calcuvw_opts;
+
+typedef struct {
+  fc_solver_report rep[3]; /* bicgstab(u,iu), (v,iv), (w,iw)                        */
+} fc_calcuvw_report;
+
+/* calcuvw.f90:48-389: gradients, calcPressDiv, sources, face fluxes -> FC_SU/SV/SW,
+ * FC_SPU/SPV/SP and the off-diagonals of FC_A.                                     */
+int fc_calcuvw_assemble(fc_context *ctx, const fc_calcuvw_opts *o);
+/* One component (0 u, 1 v, 2 w): diagonal, under-relaxation, ap*, bicgstab.        */
+int fc_calcuvw_component(fc_context *ctx, const fc_calcuvw_opts *o, int comp, fc_solver_report *rep);
+/* `call calcuvw`.                                                                  */
+int fc_calcuvw(fc_context *ctx, const fc_calcuvw_opts *o, fc_calcuvw_report *rep);
+/* Host-buffer form: uploads u,v,w,p,vis (numTotal) and flmass (numInnerFaces), runs
+ * fc_calcuvw, downloads u,v,w,p (numTotal) and apu,apv,apw (numCells).  den, fmi,
+ * fmo and the old time levels are uploaded separately with fc_upload.              */
+int fc_calcuvw_host(fc_context *ctx, const fc_calcuvw_opts *o, double *u, double *v, double *w, double *p,
+                    const double *vis, const double *flmass, double *apu, double *apv, double *apw,
+                    fc_calcuvw_report *rep);
+
 /* ---- src-parallel communication (exchange.f90, global_sum_mpi.f90) ------ */
 int fc_exchange(fc_context *ctx, int field);          /* halo of a numTotal / numPCells field */
 int fc_global_sum(fc_context *ctx, double *value);    /* in-place sum over ranks (host scalar) */
@@ -235,6 +283,8 @@ typedef struct {
   int persist_iters;   /* iterations the phase sums cover                      */
   int persist_grid;    /* CTAs of the persistent kernel                        */
   double persist_mail_ms; /* of the remainder: waiting for the other ranks' partial sums */
+  double uvw_assemble_ms; /* last fc_calcuvw: gradients + face + row kernels            */
+  double uvw_solve_ms;    /* last fc_calcuvw: the three BiCGStab solves                 */
 } fc_timings;
 /* Kernel selection, for measurements and A/B tests (defaults in brackets).     */
 enum {

@@ -1,0 +1,38 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product, never loaded by freecappuccino_b200.
+//
+// Compiles the per-index bodies of the momentum-predictor kernels
+// (freecappuccino_b200/csrc/fc_momentum_body.cuh) with g++ and runs them in plain loops, so that
+// tests/test_momentum_bodies.py can check their index logic and arithmetic order against the oracle
+// on a machine without a GPU.  On the GPU the same bodies are called by the thin __global__ wrappers
+// of fc_momentum.cu (tests/test_gpu_zz_momentum.py compares those with the oracle).  The library has
+// no host path: this file is built only by the test that uses it.
+#include "../../freecappuccino_b200/csrc/fc_momentum_body.cuh"
+
+extern "C" {
+
+void fcm_host_assemble(const fcm_geom *g, const fcm_c2f *m, const fcm_slots *sl, const fcm_flow *f, const fcm_opts *o,
+                       const fcm_faces *fa, const fcm_rows *r, int nnz) {
+  for (int i = 0; i < g->F; ++i) fcm_face(*g, *f, *o, *fa, i);
+  for (int c = 0; c < g->n; ++c) fcm_row(*g, *m, *sl, *f, *o, *fa, *r, c);
+  if (o->cn)
+    for (int k = 0; k < nnz; ++k) r->a[k] = 0.5 * r->a[k];
+}
+
+void fcm_host_component(const fcm_geom *g, const fcm_c2f *m, const fcm_comp *k) {
+  for (int c = 0; c < g->n; ++c) fcm_component(*g, *m, *k, c);
+}
+
+int fcm_host_sizes(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(fcm_geom);
+    case 1: return (int)sizeof(fcm_c2f);
+    case 2: return (int)sizeof(fcm_slots);
+    case 3: return (int)sizeof(fcm_flow);
+    case 4: return (int)sizeof(fcm_opts);
+    case 5: return (int)sizeof(fcm_faces);
+    case 6: return (int)sizeof(fcm_rows);
+    case 7: return (int)sizeof(fcm_comp);
+  }
+  return -1;
+}
+}

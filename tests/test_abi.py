@@ -32,16 +32,19 @@ def test_struct_layouts_match_header(tmp_path):
     src = tmp_path / "abi.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "fcapp.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %d\\n", sizeof(fc_mesh_desc), sizeof(fc_solver_opts),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %d %zu %zu %zu %zu\\n", sizeof(fc_mesh_desc),'
+        ' sizeof(fc_solver_opts),'
         ' sizeof(fc_solver_report), sizeof(fc_calcp_opts), sizeof(fc_calcp_report), sizeof(fc_timings),'
         ' offsetof(fc_mesh_desc, gloCells), offsetof(fc_calcp_opts, sol), offsetof(fc_timings, launches),'
-        ' (int)FC_NUM_FIELDS);return 0;}\n')
+        ' (int)FC_NUM_FIELDS, sizeof(fc_calcuvw_opts), sizeof(fc_calcuvw_report), offsetof(fc_calcuvw_opts, sol),'
+        ' offsetof(fc_calcuvw_opts, viscos));return 0;}\n')
     exe = tmp_path / "abi"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     want = [C.sizeof(lib.MeshDesc), C.sizeof(lib.SolverOpts), C.sizeof(lib.SolverReport), C.sizeof(lib.CalcpOpts),
             C.sizeof(lib.CalcpReport), C.sizeof(lib.Timings), lib.MeshDesc.gloCells.offset, lib.CalcpOpts.sol.offset,
-            lib.Timings.launches.offset, len(lib.FIELDS)]
+            lib.Timings.launches.offset, len(lib.FIELDS), C.sizeof(lib.CalcuvwOpts), C.sizeof(lib.CalcuvwReport),
+            lib.CalcuvwOpts.sol.offset, lib.CalcuvwOpts.viscos.offset]
     assert got == want
 
 
@@ -64,3 +67,5 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "fc_oracle" not in src, f
+                # nor the host build of the kernel bodies the CPU suite uses (tests/kernel_bodies_host)
+                assert "fcm_host" not in src and "libfcm_host" not in src, f

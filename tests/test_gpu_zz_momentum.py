@@ -1,0 +1,237 @@
+"""GPU parity of the momentum predictor `call calcuvw` through the C ABI.
+
+Written after this round's GPU budget was spent: the kernels' per-index bodies are checked bit for bit against
+the oracle on the CPU (tests/test_momentum_bodies.py), these tests are their first run on hardware.  The file
+name sorts last so that the verified suites run first.
+
+Bars: explicit sources / coefficients bit-exact (same summation order, no FMA); after the BiCGStab solves
+iteration counts within +-1 and fields within 1e-10 relative L2 when the counts agree.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from freecappuccino_b200 import cases
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MESHES = {
+    "skew": lambda: cases.skew_case(),
+    "hex_mixed_bc": lambda: cases.hex_case(9, 7, 11, kinds=("inlet", "outlet", "wall", "symmetry", "wall", "prOutlet")),
+    "poly": lambda: cases.poly_case(5),
+    "cavity": lambda: cases.golden_mesh(os.path.join(GOLD, "cavity.npz")),
+    "pitzDaily": lambda: cases.golden_mesh(os.path.join(GOLD, "pitzDaily.npz")),
+}
+
+
+@pytest.fixture(scope="module")
+def fc():
+    from freecappuccino_b200 import lib
+    return lib
+
+
+def linear_fluxes(mesh, of, flip=True):
+    F = mesh.numInnerFaces
+    o, nb = mesh.owner[:F] - 1, mesh.neighbour - 1
+    fx = mesh.facint
+    df = of.den[o] * (1 - fx) + of.den[nb] * fx
+    fl = df * ((of.u[o] * (1 - fx) + of.u[nb] * fx) * mesh.arx[:F] + (of.v[o] * (1 - fx) + of.v[nb] * fx) * mesh.ary[:F]
+               + (of.w[o] * (1 - fx) + of.w[nb] * fx) * mesh.arz[:F])
+    if flip:
+        fl[::3] *= -1.0
+    return fl
+
+
+def make_state(mesh, f, seed=3, stale=True):
+    """Oracle-side state of one calcuvw call (fields of module variables / sparse_matrix)."""
+    rng = np.random.default_rng(seed)
+    csr = oracle.create_csr(mesh)
+    nt = mesh.numTotal
+    of = oracle.Fields(mesh, csr.nnz)
+    for k in ("u", "v", "w", "p", "den"):
+        getattr(of, k)[:] = f[k]
+    of.flmass[:] = linear_fluxes(mesh, of, flip=stale)
+    fmi, flomas = cases.inlet_fluxes(mesh, f)
+    of.fmi[:fmi.size] = fmi
+    fs, sl = mesh.boundary_faces("outlet"), mesh.boundary_slots("outlet")
+    of.fmo[:len(fs)] = f["den"][sl] * (f["u"][sl] * mesh.arx[fs] + f["v"][sl] * mesh.ary[fs] + f["w"][sl] * mesh.arz[fs])
+    if stale:
+        of.a[:] = rng.standard_normal(csr.nnz)
+    x = oracle.UvwFields(mesh, of, 0.0)
+    x.vis[:] = 0.01 * (1.0 + 0.3 * rng.random(nt))
+    for k in ("uo", "vo", "wo", "uoo", "voo", "woo", "t"):
+        getattr(x, k)[:] = rng.standard_normal(nt)
+    return csr, of, x, flomas
+
+
+def upload_state(ctx, mesh, of, x):
+    for name, arr in (("U", of.u), ("V", of.v), ("W", of.w), ("P", of.p), ("DEN", of.den), ("FLMASS", of.flmass),
+                      ("A", of.a), ("DPDXI", of.dPdxi), ("VIS", x.vis), ("UO", x.uo), ("VO", x.vo), ("WO", x.wo),
+                      ("UOO", x.uoo), ("VOO", x.voo), ("WOO", x.woo), ("T", x.t)):
+        ctx.upload(name, arr)
+    if mesh.count("inlet"):
+        ctx.upload("FMI", of.fmi[:mesh.count("inlet")])
+    if mesh.count("outlet"):
+        ctx.upload("FMO", of.fmo[:mesh.count("outlet")])
+
+
+def both_opts(fc, **kw):
+    return oracle.uvw_opts(**kw), fc.calcuvw_opts(**kw)
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+@pytest.mark.parametrize("scheme", ["muscl-f", "linear-f", "central", "smart", "charm"])
+def test_calcuvw_assembly_bit_exact(fc, name, scheme):
+    mesh = MESHES[name]()
+    csr, of, x, _ = make_state(mesh, cases.flow_fields(mesh))
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    upload_state(ctx, mesh, of, x)
+    oo, go = both_opts(fc, scheme=scheme, urf=(0.7, 0.8, 0.6), bdf=True, btime=1.0, timestep=0.02)
+    oracle.calcuvw_assemble(mesh, csr, of, x, oo)
+    ctx.calcuvw_assemble(go)
+    n = mesh.numCells
+    for fld, ref in (("P", of.p), ("DPDXI", of.dPdxi.ravel()), ("DUDXI", of.dUdxi.ravel()), ("SU", of.su), ("SV", x.sv),
+                     ("SW", x.sw), ("SPU", x.spu), ("SPV", x.spv), ("SP", x.sp), ("A", of.a)):
+        got = ctx.download(fld)[:ref.size]
+        assert np.array_equal(got, ref), (fld, float(np.abs(got - ref).max()))
+    # per component: diagonal, under-relaxation, ap* (zero BiCGStab sweeps on both sides)
+    oo0, go0 = both_opts(fc, scheme=scheme, urf=(0.7, 0.8, 0.6), bdf=True, btime=1.0, timestep=0.02, nsw=(0, 0, 0))
+    for comp, apn in enumerate(("APU", "APV", "APW")):
+        oracle.calcuvw_component(mesh, csr, of, x, oo0, comp)
+        ctx.calcuvw_component(go0, comp)
+        assert np.array_equal(ctx.download("A"), of.a), comp
+        assert np.array_equal(ctx.download("SU"), of.su), comp
+        assert np.array_equal(ctx.download(apn)[:n], (x.apu, x.apv, x.apw)[comp][:n]), comp
+    ctx.close()
+
+
+@pytest.mark.parametrize("kw", [dict(cn=True, bdf=True, btime=1.0, timestep=0.02), dict(const_mflux=True, gradPcmf=0.37),
+                                dict(lbuoy=True, boussinesq=True, beta=0.3, tref=0.1, densit=1.1, grav=(0.1, -9.81, 0.2)),
+                                dict(lbuoy=True, boussinesq=False, densit=1.1, grav=(0.1, -9.81, 0.2))])
+def test_calcuvw_source_options_bit_exact(fc, kw):
+    mesh = MESHES["skew"]()
+    csr, of, x, _ = make_state(mesh, cases.flow_fields(mesh))
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    upload_state(ctx, mesh, of, x)
+    oo, go = both_opts(fc, nsw=(0, 0, 0), **kw)
+    oracle.calcuvw(mesh, csr, of, x, oo)
+    ctx.calcuvw(go)
+    n = mesh.numCells
+    for fld, ref in (("SV", x.sv), ("SW", x.sw), ("SPU", x.spu), ("SPV", x.spv), ("SP", x.sp), ("A", of.a),
+                     ("SU", of.su), ("APU", x.apu[:n]), ("APV", x.apv[:n]), ("APW", x.apw[:n])):
+        got = ctx.download(fld)[:ref.size]
+        assert np.array_equal(got, ref), (fld, float(np.abs(got - ref).max()))
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,sor,ftol", [("skew", 1e-8, 1e-7), ("cavity", 1e-8, 1e-6), ("pitzDaily", 1e-6, 1e-4),
+                                           ("poly", 1e-8, 1e-7)])
+def test_calcuvw_full_parity(fc, name, sor, ftol):
+    """`call calcuvw` end to end: BiCGStab iteration counts within +-1; u/v/w to the accuracy the stopping
+    tolerance fixes them (a solve stopped at rsm < sor leaves an O(sor) difference when the counts agree and the
+    last residuals differ in the final digits); ap* do not depend on the solves and are exact."""
+    mesh = MESHES[name]()
+    csr, of, x, _ = make_state(mesh, cases.channel_fields(mesh), stale=False)
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    upload_state(ctx, mesh, of, x)
+    oo, go = both_opts(fc, scheme="muscl-f", sor=(sor,) * 3, nsw=(200,) * 3, bdf=True, timestep=0.05)
+    rr = oracle.calcuvw(mesh, csr, of, x, oo)
+    rg = ctx.calcuvw(go)
+    n = mesh.numCells
+    same = True
+    for k in range(3):
+        assert 0 < rr.rep[k].iters < 200
+        assert abs(rg.rep[k].iters - rr.rep[k].iters) <= 1, (k, rg.rep[k].iters, rr.rep[k].iters)
+        assert rg.rep[k].res0 == pytest.approx(rr.rep[k].res0, rel=1e-9)
+        same = same and rg.rep[k].iters == rr.rep[k].iters
+    assert np.array_equal(ctx.download("APU")[:n], x.apu[:n])
+    if same:
+        for fld, ref in (("U", of.u), ("V", of.v), ("W", of.w)):
+            assert cases.rel_l2(ctx.download(fld)[:n], ref[:n]) < ftol, fld
+    ctx.close()
+
+
+def test_simple_iterations_device_resident_cavity(fc):
+    """Config 1 as shipped (examples/cavity/input: muscl-f, gauss, urf 0.7/0.3, sor 1e-2, nsw 20/100, bdf with
+    timestep 1e20, lid U = 1): ten SIMPLE iterations calcuvw -> calcp with every field staying on the GPU,
+    against the oracle doing the same.  Iteration counts within +-1 at every step; fields compared while the
+    counts agree (a solve stopped at rsm < 1e-2 fixes the fields only to that tolerance otherwise)."""
+    mesh = MESHES["cavity"]()
+    nt = mesh.numTotal
+    f = dict(u=np.zeros(nt), v=np.zeros(nt), w=np.zeros(nt), p=np.zeros(nt), den=np.ones(nt))
+    # the lid: first wall patch of the fixture = 'movingWall' (20 faces, U = (1,0,0)), examples/cavity/0/U
+    f["u"][mesh.boundary_slots("wall")[:20]] = 1.0
+    csr, of, x, _ = make_state(mesh, f, stale=False)
+    x.vis[:] = 0.01
+    for k in ("uo", "vo", "wo", "uoo", "voo", "woo", "t"):
+        getattr(x, k)[:] = 0.0
+    of.flmass[:] = 0.0
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    upload_state(ctx, mesh, of, x)
+    kw_u = dict(scheme="muscl-f", urf=(0.7, 0.7, 0.7), sor=(1e-2,) * 3, nsw=(20,) * 3, bdf=True, btime=0.0,
+                timestep=1e20, viscos=0.01)
+    kw_p = dict(solver="dpcg", sor=1e-2, nsw=100, urf_p=0.3, pRefCell=1, const_mflux=True)
+    oo, go = both_opts(fc, **kw_u)
+    agree = True
+    for it in range(10):
+        ru = oracle.calcuvw(mesh, csr, of, x, oo)
+        gu = ctx.calcuvw(go)
+        rp = oracle.calcp(mesh, csr, of, oracle.calcp_opts(**kw_p))
+        gp = ctx.calcp(fc.calcp_opts(**kw_p))
+        for k in range(3):
+            assert abs(gu.rep[k].iters - ru.rep[k].iters) <= 1, (it, k, gu.rep[k].iters, ru.rep[k].iters)
+            agree = agree and gu.rep[k].iters == ru.rep[k].iters
+        assert abs(gp.rep[0].iters - rp.rep[0].iters) <= 1, (it, gp.rep[0].iters, rp.rep[0].iters)
+        agree = agree and gp.rep[0].iters == rp.rep[0].iters
+        if agree:
+            for fld, ref in (("U", of.u), ("V", of.v), ("P", of.p), ("FLMASS", of.flmass)):
+                assert cases.rel_l2(ctx.download(fld)[:ref.size], ref) < 1e-9, (it, fld)
+    assert np.abs(of.u[:mesh.numCells]).max() > 0.05   # the lid drives a flow
+    ctx.close()
+
+
+def test_calcuvw_host_form(fc):
+    mesh = MESHES["skew"]()
+    csr, of, x, _ = make_state(mesh, cases.channel_fields(mesh), stale=False)
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    upload_state(ctx, mesh, of, x)
+    oo, go = both_opts(fc, sor=(1e-8,) * 3, nsw=(200,) * 3, bdf=True, timestep=0.05)
+    u, v, w, p = of.u.copy(), of.v.copy(), of.w.copy(), of.p.copy()
+    n = mesh.numCells
+    apu, apv, apw = np.zeros(n), np.zeros(n), np.zeros(n)
+    rg = ctx.calcuvw_host(go, u, v, w, p, x.vis, of.flmass, apu, apv, apw)
+    rr = oracle.calcuvw(mesh, csr, of, x, oo)
+    same = True
+    for k in range(3):
+        assert abs(rg.rep[k].iters - rr.rep[k].iters) <= 1
+        same = same and rg.rep[k].iters == rr.rep[k].iters
+    assert np.array_equal(p, of.p)
+    assert np.array_equal(apu, x.apu[:n]) and np.array_equal(apw, x.apw[:n])
+    if same:
+        for got, ref in ((u, of.u), (v, of.v), (w, of.w)):
+            assert cases.rel_l2(got[:n], ref[:n]) < 1e-7
+    ctx.close()
+
+
+def test_calcuvw_rejects_what_it_does_not_cover(fc):
+    mesh = cases.hex_case(2, 1, 1)
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    with pytest.raises(fc.FcError) as e:
+        ctx.calcuvw(fc.calcuvw_opts())
+    assert e.value.code == fc.FC_ERR_UNSUPPORTED   # numCells < 3: the reference's df(ijp,3) leaves the array
+    ctx.close()

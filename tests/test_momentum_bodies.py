@@ -1,0 +1,235 @@
+"""Index logic and arithmetic order of the momentum-predictor kernel bodies, checked WITHOUT a GPU.
+
+freecappuccino_b200/csrc/fc_momentum_body.cuh holds the per-index bodies the CUDA kernels of
+fc_momentum.cu call.  tests/kernel_bodies_host/fcm_host.cpp compiles that header with g++
+(-ffp-contract=off, the host twin of nvcc -fmad=false) and runs the bodies in plain loops over the
+device data layout (0-based indices, cell-to-face map) built here in numpy.  Everything must equal
+the oracle's calcuvw bit for bit.  This is test infrastructure: the product has no host path
+(tests/test_abi.py asserts the package never references it); the GPU twin of this test is
+tests/test_gpu_zz_momentum.py.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from freecappuccino_b200 import cases
+from freecappuccino_b200 import mesh as M
+from oracle import oracle
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kernel_bodies_host")
+dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+
+
+class Geom(C.Structure):
+    _fields_ = [("owner", ip), ("neigh", ip)] + [(k, dp) for k in (
+        "xc", "yc", "zc", "vol", "arx", "ary", "arz", "xf", "yf", "zf", "facint")] + [("n", C.c_int), ("F", C.c_int)]
+
+
+class C2f(C.Structure):
+    _fields_ = [(k, ip) for k in ("off", "face", "other", "pos")]
+
+
+class Slots(C.Structure):
+    _fields_ = [("slot", C.c_int * 5), ("face", C.c_int * 5), ("count", C.c_int * 5)]
+
+
+class Flow(C.Structure):
+    _fields_ = [(k, dp) for k in ("u", "v", "w", "p", "den", "vis", "flmass", "fmi", "fmo", "dU", "dV", "dW", "dP",
+                                  "uo", "vo", "wo", "uoo", "voo", "woo", "t")]
+
+
+class Opts(C.Structure):
+    _fields_ = [("scheme", C.c_int), ("limiter", C.c_int), ("gds", C.c_double), ("bdf", C.c_int),
+                ("btime", C.c_double), ("timestep", C.c_double), ("cn", C.c_int), ("const_mflux", C.c_int),
+                ("gradPcmf", C.c_double), ("lbuoy", C.c_int), ("boussinesq", C.c_int)] + [
+        (k, C.c_double) for k in ("beta", "tref", "densit", "gravx", "gravy", "gravz", "viscos")]
+
+
+class Faces(C.Structure):
+    _fields_ = [(k, dp) for k in ("can", "cap", "sup", "svp", "swp", "fie")]
+
+
+class Rows(C.Structure):
+    _fields_ = [(k, dp) for k in ("a", "su", "sv", "sw", "spu", "spv", "sp")]
+
+
+class Comp(C.Structure):
+    _fields_ = [("ioffset", ip), ("diag", ip)] + [(k, dp) for k in ("a", "s", "spc", "su", "ap", "phi", "phio", "den")] + [
+        (k, C.c_double) for k in ("urfrs", "urfms", "small", "timestep")] + [("cn", C.c_int), ("zero_diag", C.c_int)]
+
+
+@pytest.fixture(scope="module")
+def host():
+    so = os.path.join(HERE, "libfcm_host.so")
+    src = os.path.join(HERE, "fcm_host.cpp")
+    hdr = os.path.join(HERE, "..", "..", "freecappuccino_b200", "csrc", "fc_momentum_body.cuh")
+    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", so, src])
+    lib = C.CDLL(so)
+    for k, st in enumerate((Geom, C2f, Slots, Flow, Opts, Faces, Rows, Comp)):
+        assert lib.fcm_host_sizes(k) == C.sizeof(st), (k, st)
+    return lib
+
+
+def d(a):
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(dp)
+
+
+def i32(a):
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(ip)
+
+
+def device_layout(mesh, csr):
+    """What fc_set_mesh / fc_create_csr keep on the device: 0-based owner / neighbour / CSR and
+    the cell-to-face map in the reference's loop order (fc_csr.cu k_c2f_fill / k_c2f_sort)."""
+    n, F, NF = mesh.numCells, mesh.numInnerFaces, mesh.numFaces
+    owner = (mesh.owner - 1).astype(np.int32)
+    neigh = (mesh.neighbour - 1).astype(np.int32)
+    ioffset = (csr.ioffset - 1).astype(np.int32)
+    ja = (csr.ja - 1).astype(np.int32)
+    diag = (csr.diag - 1).astype(np.int32)
+    ent = [[] for _ in range(n)]
+    for f in range(F):
+        ent[owner[f]].append((f, f, int(neigh[f])))
+        ent[neigh[f]].append((f, f | 0x80000000, int(owner[f])))
+    slots = Slots()
+    for b, kind in enumerate(M.KINDS):
+        fs, sl = mesh.boundary_faces(kind), mesh.boundary_slots(kind)
+        slots.count[b] = len(fs)
+        slots.face[b] = int(fs[0]) if len(fs) else 0
+        slots.slot[b] = int(sl[0]) if len(sl) else 0
+        for f, s in zip(fs, sl):
+            ent[owner[f]].append((F + int(s) - n, int(f), int(s)))
+    off = np.zeros(n + 1, np.int32)
+    face, other, pos = [], [], []
+    for c in range(n):
+        ent[c].sort(key=lambda e: e[0])
+        off[c + 1] = off[c] + len(ent[c])
+        for _, fe, o in ent[c]:
+            face.append(fe)
+            other.append(o)
+            if (fe & 0x7fffffff) < F:
+                row = ja[ioffset[c]:ioffset[c + 1]]
+                pos.append(int(ioffset[c] + np.nonzero(row == o)[0][0]))
+            else:
+                pos.append(-1)
+    face = np.array(face, dtype=np.uint32).view(np.int32).copy()
+    return dict(owner=owner, neigh=neigh, ioffset=ioffset, ja=ja, diag=diag, off=off, face=face,
+                other=np.array(other, np.int32), pos=np.array(pos, np.int32), slots=slots)
+
+
+def fluxes(mesh, of):
+    F = mesh.numInnerFaces
+    o, nb = mesh.owner[:F] - 1, mesh.neighbour - 1
+    fx = mesh.facint
+    df = of.den[o] * (1 - fx) + of.den[nb] * fx
+    fl = df * ((of.u[o] * (1 - fx) + of.u[nb] * fx) * mesh.arx[:F] + (of.v[o] * (1 - fx) + of.v[nb] * fx) * mesh.ary[:F]
+               + (of.w[o] * (1 - fx) + of.w[nb] * fx) * mesh.arz[:F])
+    fl[::3] *= -1.0   # both flow directions on every kind of face
+    return fl
+
+
+def run_case(host, mesh, f, scheme, **kw):
+    rng = np.random.default_rng(3)
+    csr = oracle.create_csr(mesh)
+    n, F, nt = mesh.numCells, mesh.numInnerFaces, mesh.numTotal
+    of = oracle.Fields(mesh, csr.nnz)
+    for k in ("u", "v", "w", "p", "den"):
+        getattr(of, k)[:] = f[k]
+    of.flmass[:] = fluxes(mesh, of)
+    fmi, _ = cases.inlet_fluxes(mesh, f)
+    of.fmi[:fmi.size] = fmi
+    fs, sl = mesh.boundary_faces("outlet"), mesh.boundary_slots("outlet")
+    of.fmo[:len(fs)] = f["den"][sl] * (f["u"][sl] * mesh.arx[fs] + f["v"][sl] * mesh.ary[fs] + f["w"][sl] * mesh.arz[fs])
+    of.a[:] = rng.standard_normal(csr.nnz)   # stale matrix of the previous solve (the U diagonal sum reads it)
+    x = oracle.UvwFields(mesh, of, 0.0)
+    x.vis[:] = 0.01 * (1.0 + 0.3 * rng.random(nt))
+    for k in ("uo", "vo", "wo", "uoo", "voo", "woo", "t"):
+        getattr(x, k)[:] = rng.standard_normal(nt)
+    opts = oracle.uvw_opts(scheme=scheme, urf=(0.7, 0.8, 0.6), sor=(1e-30,) * 3, nsw=(2, 2, 2), **kw)
+
+    # ---- the kernel bodies on the device layout, fed with the oracle's gradients / boundary pressure ----
+    L = device_layout(mesh, csr)
+    g = dict(u=of.u.copy(), v=of.v.copy(), w=of.w.copy(), p=of.p.copy(), a=of.a.copy())
+    dU = oracle.grad_gauss(mesh, g["u"], 1)
+    dV = oracle.grad_gauss(mesh, g["v"], 1)
+    dW = oracle.grad_gauss(mesh, g["w"], 1)
+    dP = of.dPdxi.copy()
+    for istage in (1, 2):
+        oracle.bpres(mesh, g["p"], dP, istage)
+        dP = oracle.grad_gauss(mesh, g["p"], 1)
+    geo = {k: np.ascontiguousarray(getattr(mesh, k), dtype=np.float64) for k in
+           ("xc", "yc", "zc", "vol", "arx", "ary", "arz", "xf", "yf", "zf", "facint")}
+    G = Geom(i32(L["owner"]), i32(L["neigh"]), *[d(geo[k]) for k in ("xc", "yc", "zc", "vol", "arx", "ary", "arz",
+                                                                    "xf", "yf", "zf", "facint")], n, F)
+    Mp = C2f(i32(L["off"]), i32(L["face"]), i32(L["other"]), i32(L["pos"]))
+    den = np.ascontiguousarray(of.den)
+    FL = Flow(d(g["u"]), d(g["v"]), d(g["w"]), d(g["p"]), d(den), d(x.vis), d(of.flmass), d(of.fmi), d(of.fmo),
+              d(dU), d(dV), d(dW), d(dP), d(x.uo), d(x.vo), d(x.wo), d(x.uoo), d(x.voo), d(x.woo), d(x.t))
+    O = Opts(opts.scheme, opts.limiter, opts.gds, opts.bdf, opts.btime, opts.timestep, opts.cn, opts.const_mflux,
+             opts.gradPcmf, opts.lbuoy, opts.boussinesq, opts.beta, opts.tref, opts.densit, opts.gravx, opts.gravy,
+             opts.gravz, opts.viscos)
+    fa = [np.zeros(max(F, 1)) for _ in range(6)]
+    rows = {k: np.zeros(n) for k in ("su", "sv", "sw", "spu", "spv", "sp")}
+    FA = Faces(*[d(a) for a in fa])
+    R = Rows(d(g["a"]), *[d(rows[k]) for k in ("su", "sv", "sw", "spu", "spv", "sp")])
+    host.fcm_host_assemble(C.byref(G), C.byref(Mp), C.byref(L["slots"]), C.byref(FL), C.byref(O), C.byref(FA),
+                           C.byref(R), csr.nnz)
+
+    # ---- oracle ----
+    oracle.calcuvw_assemble(mesh, csr, of, x, opts)
+    assert np.array_equal(g["p"], of.p)
+    assert np.array_equal(dP, of.dPdxi) and np.array_equal(dU, of.dUdxi)
+    for k, ref in (("su", of.su), ("sv", x.sv), ("sw", x.sw), ("spu", x.spu), ("spv", x.spv), ("sp", x.sp)):
+        assert np.array_equal(rows[k], ref), (scheme, k, np.abs(rows[k] - ref).max())
+    assert np.array_equal(g["a"], of.a)
+
+    # ---- per component: diagonal / under-relaxation / ap*, then the oracle's solve moves phi ----
+    ap = [np.zeros(n) for _ in range(3)]
+    su_rhs = rows["su"]
+    for comp, (sk, spk, phik, oldk) in enumerate((("su", "spu", "u", "uo"), ("sv", "spv", "v", "vo"),
+                                                  ("sw", "sp", "w", "wo"))):
+        K = Comp(i32(L["ioffset"]), i32(L["diag"]), d(g["a"]), d(rows[sk]), d(rows[spk]), d(su_rhs), d(ap[comp]),
+                 d(g[phik]), d(getattr(x, oldk)), d(den), 1.0 / opts.urf[comp], 1.0 - opts.urf[comp], opts.sol.small,
+                 opts.timestep, opts.cn, 1 if comp else 0)
+        host.fcm_host_component(C.byref(G), C.byref(Mp), C.byref(K))
+        a_before = g["a"].copy()
+        # oracle: same step + BiCGStab; capture its matrix / rhs through a zero-sweep solve
+        o0 = oracle.uvw_opts(scheme=scheme, urf=(0.7, 0.8, 0.6), sor=(1e-30,) * 3, nsw=(0, 0, 0), **kw)
+        oracle.calcuvw_component(mesh, csr, of, x, o0, comp)
+        assert np.array_equal(a_before, of.a), (scheme, comp)
+        assert np.array_equal(su_rhs, of.su), (scheme, comp)
+        assert np.array_equal(ap[comp], (x.apu, x.apv, x.apw)[comp][:n]), (scheme, comp)
+        assert np.array_equal(rows[sk], (of.su, x.sv, x.sw)[comp]) or comp == 0
+        assert np.array_equal(rows[spk], (x.spu, x.spv, x.sp)[comp])
+    return True
+
+
+MESHES = {
+    "skew": lambda: cases.skew_case(6, 5, 4),
+    "hex_mixed_bc": lambda: cases.hex_case(5, 4, 6, kinds=("inlet", "outlet", "wall", "symmetry", "wall", "prOutlet")),
+    "poly": lambda: cases.poly_case(3),
+}
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+@pytest.mark.parametrize("scheme", ["muscl-f", "central", "cds-corrected", "central-f", "linear-f", "smart", "koren",
+                                    "charm", "ospre", "linear"])
+def test_bodies_equal_oracle_steady(host, name, scheme):
+    mesh = MESHES[name]()
+    assert run_case(host, mesh, cases.flow_fields(mesh), scheme)
+
+
+@pytest.mark.parametrize("kw", [dict(bdf=True, btime=0.0, timestep=0.02), dict(bdf=True, btime=1.0, timestep=0.02),
+                                dict(bdf=True, btime=1.0, timestep=0.02, cn=True),
+                                dict(const_mflux=True, gradPcmf=0.37),
+                                dict(lbuoy=True, boussinesq=True, beta=0.3, tref=0.1, densit=1.1, grav=(0.1, -9.81, 0.2)),
+                                dict(lbuoy=True, boussinesq=False, densit=1.1, grav=(0.1, -9.81, 0.2))])
+def test_bodies_equal_oracle_sources(host, kw):
+    mesh = MESHES["skew"]()
+    assert run_case(host, mesh, cases.flow_fields(mesh), "muscl-f", **kw)
