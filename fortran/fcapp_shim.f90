@@ -3,7 +3,7 @@
 ! host code and libfcapp_cuda.so (C ABI: include/fcapp.h).
 !
 ! Drop-in use: remove  sparse_matrix.f90's create_CSR_matrix_from_mesh_data
-! body, calcp-multiple_correction_SIMPLE.f90, dpcg.f90, iccg.f90,
+! body, calcp-multiple_correction_SIMPLE.f90, calcuvw.f90, dpcg.f90, iccg.f90,
 ! bicgstab.f90, fvm_laplacian.f90 (laplacian) and the 'gauss' branch of
 ! gradients.f90 from the Makefile's object list, add this file, and link
 ! with  -L<repo>/freecappuccino_b200 -lfcapp_cuda .  Every subroutine
@@ -25,7 +25,9 @@ module fcapp_c
   integer(c_int), parameter :: FC_U=0, FC_V=1, FC_W=2, FC_P=3, FC_PP=4, FC_DEN=5, FC_FLMASS=6,      &
                                FC_APU=7, FC_APV=8, FC_APW=9, FC_DUDXI=10, FC_DVDXI=11, FC_DWDXI=12, &
                                FC_DPDXI=13, FC_A=14, FC_SU=15, FC_RES=16, FC_FMI=17, FC_FMO=18,      &
-                               FC_APR=19, FC_FMPRO=20, FC_SCRATCH_T=21, FC_USER0=22
+                               FC_APR=19, FC_FMPRO=20, FC_SCRATCH_T=21, FC_USER0=22,                  &
+                               FC_VIS=26, FC_UO=27, FC_VO=28, FC_WO=29, FC_UOO=30, FC_VOO=31, FC_WOO=32, &
+                               FC_T=33, FC_SV=34, FC_SW=35, FC_SPU=36, FC_SPV=37, FC_SP=38
 
   type, bind(C) :: fc_mesh_desc
     integer(c_int) :: numCells, numInnerFaces, numFaces, numTotal
@@ -67,6 +69,24 @@ module fcapp_c
   type, bind(C) :: fc_calcp_report
     type(fc_solver_report) :: rep(8)
     real(c_double) :: sumLocalContErr, globalContErr
+  end type
+
+  type, bind(C) :: fc_calcuvw_opts
+    integer(c_int) :: nigrad, nipgrad, scheme, limiter
+    real(c_double) :: gds
+    real(c_double) :: urf(3), sor(3)
+    integer(c_int) :: nsw(3)
+    integer(c_int) :: bdf
+    real(c_double) :: btime, timestep
+    integer(c_int) :: cn, const_mflux
+    real(c_double) :: gradPcmf
+    integer(c_int) :: lbuoy, boussinesq
+    real(c_double) :: beta, tref, densit, gravx, gravy, gravz, viscos
+    type(fc_solver_opts) :: sol
+  end type
+
+  type, bind(C) :: fc_calcuvw_report
+    type(fc_solver_report) :: rep(3)
   end type
 
   type(c_ptr), save :: fc_ctx = c_null_ptr   ! one context per rank / GPU
@@ -121,6 +141,12 @@ module fcapp_c
       import; type(c_ptr), value :: ctx; type(fc_calcp_opts) :: o
       real(c_double) :: u(*), v(*), w(*), p(*), pp(*), apu(*), apv(*), apw(*), flmass(*)
       type(fc_calcp_report) :: rep
+    end function
+    integer(c_int) function fc_calcuvw_host(ctx, o, u, v, w, p, vis, flmass, apu, apv, apw, rep) &
+        bind(C, name='fc_calcuvw_host')
+      import; type(c_ptr), value :: ctx; type(fc_calcuvw_opts) :: o
+      real(c_double) :: u(*), v(*), w(*), p(*), vis(*), flmass(*), apu(*), apv(*), apw(*)
+      type(fc_calcuvw_report) :: rep
     end function
     integer(c_int) function fc_exchange(ctx, field) bind(C, name='fc_exchange')
       import; type(c_ptr), value :: ctx; integer(c_int), value :: field
@@ -318,6 +344,82 @@ subroutine calcp
   cumulativeContErr = cumulativeContErr + globalContErr
   write(6,'(3(a,es10.3))') "  time step continuity errors : sum local = ", sumLocalContErr, &
  &                          ", global = ", globalContErr, ", cumulative = ", cumulativeContErr
+end subroutine
+
+! src/calcuvw.f90:3 -- `call calcuvw` (laminar, serial): the momentum predictor on the device.  With calcp
+! above also on the device, u, v, w, p, ap*, flmass and the gradients could stay resident between the two
+! calls (fc_calcuvw + fc_calcp instead of the *_host forms); the host forms keep every module array current
+! for the routines that are still Fortran (turbulence, scalars, output).
+subroutine calcuvw
+  use types
+  use parameters
+  use geometry
+  use sparse_matrix
+  use variables
+  use title_mod
+  use fcapp_c
+  implicit none
+  type(fc_calcuvw_opts) :: o
+  type(fc_calcuvw_report) :: rep
+  integer :: k
+  character(len=1), parameter :: nm(3) = (/ 'U', 'V', 'W' /)
+  if (lturb) stop 'fcapp calcuvw: turbulent stresses (calcstress) are not on the GPU path'
+  o%nigrad = nigrad; o%nipgrad = nipgrad
+  ! face_value dispatch (interpolation.f90:36-57) in the order of its if-chain
+  o%limiter = 7
+  if (lcds) then;           o%scheme = 0
+  elseif (lcdsc) then;      o%scheme = 1
+  elseif (lcds_flnt) then;  o%scheme = 2
+  elseif (l2nd_flnt) then;  o%scheme = 3
+  elseif (lmuscl_flnt) then; o%scheme = 4
+  elseif (flux_limiter) then
+    o%scheme = 5
+    if (lsmart) then;      o%limiter = 0
+    elseif (lavl) then;    o%limiter = 1
+    elseif (lmuscl) then;  o%limiter = 2
+    elseif (lumist) then;  o%limiter = 3
+    elseif (lkoren) then;  o%limiter = 4
+    elseif (lcharm) then;  o%limiter = 5
+    elseif (lospre) then;  o%limiter = 6
+    endif
+  else;                     o%scheme = 4
+  endif
+  o%gds = gds(iu)
+  o%urf = (/ urf(iu), urf(iv), urf(iw) /)
+  o%sor = (/ sor(iu), sor(iv), sor(iw) /)
+  o%nsw = (/ nsw(iu), nsw(iv), nsw(iw) /)
+  o%bdf = merge(1, 0, bdf); o%btime = btime; o%timestep = timestep; o%cn = merge(1, 0, cn)
+  o%const_mflux = merge(1, 0, const_mflux); o%gradPcmf = gradPcmf
+  o%lbuoy = merge(1, 0, lcal(ien) .and. lbuoy); o%boussinesq = merge(1, 0, boussinesq)
+  o%beta = beta; o%tref = tref; o%densit = densit; o%gravx = gravx; o%gravy = gravy; o%gravz = gravz
+  o%viscos = viscos
+  o%sol = solver_opts(iu)
+  call fc_check(fc_upload(fc_ctx, FC_DEN, den, int(numTotal, c_size_t)), 'upload den')
+  if (ninl > 0) call fc_check(fc_upload(fc_ctx, FC_FMI, fmi, int(ninl, c_size_t)), 'upload fmi')
+  if (nout > 0) call fc_check(fc_upload(fc_ctx, FC_FMO, fmo, int(nout, c_size_t)), 'upload fmo')
+  ! `a` is not uploaded: the U row sums read the stale diagonal of the previous solve (calcuvw.f90:423), and every
+  ! solve of this build runs on the device, so the device copy of `a` is the current one by construction
+  if (bdf .or. cn) then
+    call fc_check(fc_upload(fc_ctx, FC_UO, uo, int(numTotal, c_size_t)), 'upload uo')
+    call fc_check(fc_upload(fc_ctx, FC_VO, vo, int(numTotal, c_size_t)), 'upload vo')
+    call fc_check(fc_upload(fc_ctx, FC_WO, wo, int(numTotal, c_size_t)), 'upload wo')
+    call fc_check(fc_upload(fc_ctx, FC_UOO, uoo, int(numTotal, c_size_t)), 'upload uoo')
+    call fc_check(fc_upload(fc_ctx, FC_VOO, voo, int(numTotal, c_size_t)), 'upload voo')
+    call fc_check(fc_upload(fc_ctx, FC_WOO, woo, int(numTotal, c_size_t)), 'upload woo')
+  end if
+  if (lcal(ien) .and. lbuoy) call fc_check(fc_upload(fc_ctx, FC_T, t, int(numTotal, c_size_t)), 'upload t')
+  call fc_check(fc_calcuvw_host(fc_ctx, o, u, v, w, p, vis, flmass, apu, apv, apw, rep), 'fc_calcuvw_host')
+  ! module arrays other Fortran routines read afterwards
+  call fc_check(fc_download(fc_ctx, FC_DUDXI, dUdxi, int(3*numCells, c_size_t)), 'download dUdxi')
+  call fc_check(fc_download(fc_ctx, FC_DVDXI, dVdxi, int(3*numCells, c_size_t)), 'download dVdxi')
+  call fc_check(fc_download(fc_ctx, FC_DWDXI, dWdxi, int(3*numCells, c_size_t)), 'download dWdxi')
+  call fc_check(fc_download(fc_ctx, FC_DPDXI, dPdxi, int(3*numCells, c_size_t)), 'download dPdxi')
+  call fc_check(fc_download(fc_ctx, FC_A, a, int(nnz, c_size_t)), 'download a')
+  do k = 1, 3
+    if (rep%rep(k)%iters > 0) resor(iu+k-1) = rep%rep(k)%res0     ! bicgstab.f90: resor(ifi) = res0
+    write(6,'(3a,1PE10.3,a,1PE10.3,a,I0)') '  BiCGStab(ILU(0)):  Solving for ',nm(k), &
+    ', Initial residual = ',rep%rep(k)%res0,', Final residual = ',rep%rep(k)%resl,', No Iterations ',rep%rep(k)%iters
+  end do
 end subroutine
 
 ! src-parallel/exchange.f90:3 and global_sum_mpi.f90:4 (MPI build: fc_comm_init after MPI_Init, the

@@ -17,7 +17,7 @@ std::vector<dp> xc, yc, zc, vol, arx, ary, arz, xf, yf, zf, facint;
 }  // namespace geometry
 namespace sparse_matrix {
 std::vector<int> ioffset, ja, diag, icell_jcell_csr_value_index, jcell_icell_csr_value_index;
-std::vector<dp> a, su, sv, res, apu, apv, apw;
+std::vector<dp> a, su, sv, sw, spu, spv, sp, res, apu, apv, apw;
 }  // namespace sparse_matrix
 namespace parameters {
 dp small = (dp)1e-20f;
@@ -26,9 +26,14 @@ int nsw[nphi + 1];
 int npcor = 1, nigrad = 1, nipgrad = 2, pRefCell = 1;
 bool const_mflux = false, ltest = false, lstsq_qr = false, lstsq_dm = false;
 dp flomas = 0.0;
+dp densit = 1.0, viscos = 0.01, gds[nphi + 1];
+bool bdf = false, cn = false, lturb = false, lbuoy = false, boussinesq = true, lcal[nphi + 1];
+dp btime = 0.0, timestep = 1e20, gradPcmf = 0.0, beta = 0.0, tref = 0.0, gravx = 0.0, gravy = 0.0, gravz = 0.0;
+std::string convective_scheme = "muscl-f";
 }  // namespace parameters
 namespace variables {
 std::vector<dp> u, v, w, p, pp, den, flmass, fmi, fmo;
+std::vector<dp> vis, uo, vo, wo, uoo, voo, woo, t;
 std::vector<dp> dUdxi, dVdxi, dWdxi, dPdxi;
 dp sumLocalContErr = 0, globalContErr = 0, cumulativeContErr = 0;
 }  // namespace variables
@@ -157,7 +162,8 @@ void fcapp_finalize() {
 void allocate_arrays() {
   using namespace geometry;
   using namespace variables;
-  for (auto *f : {&u, &v, &w, &p, &pp}) f->assign(numTotal, 0.0);
+  for (auto *f : {&u, &v, &w, &p, &pp, &uo, &vo, &wo, &uoo, &voo, &woo, &t}) f->assign(numTotal, 0.0);
+  vis.assign(numTotal, parameters::viscos);
   den.assign(numTotal, 1.0);
   flmass.assign(numFaces, 0.0);
   fmi.assign(ninl > 0 ? ninl : 1, 0.0);
@@ -169,7 +175,7 @@ void create_CSR_matrix_from_mesh_data() {
   using namespace geometry;
   using namespace sparse_matrix;
   ioffset.assign(numCells + 1, 0); ja.assign(nnz, 0); diag.assign(numCells, 0); a.assign(nnz, 0.0);
-  for (auto *x : {&su, &sv, &res, &apu, &apv, &apw}) x->assign(numCells, 0.0);
+  for (auto *x : {&su, &sv, &sw, &spu, &spv, &sp, &res, &apu, &apv, &apw}) x->assign(numCells, 0.0);
   icell_jcell_csr_value_index.assign(numInnerFaces, 0);
   jcell_icell_csr_value_index.assign(numInnerFaces, 0);
   check(fc_create_csr(ctx, ioffset.data(), ja.data(), diag.data(), icell_jcell_csr_value_index.data(),
@@ -238,6 +244,57 @@ void calcp() {
   cumulativeContErr += globalContErr;
   std::printf("  time step continuity errors : sum local = %10.3E, global = %10.3E, cumulative = %10.3E\n",
               sumLocalContErr, globalContErr, cumulativeContErr);
+}
+
+// `call calcuvw` (src/calcuvw.f90:3-557), laminar: the momentum predictor on the device; every module array the
+// remaining host routines read is brought back (same transfers as fortran/fcapp_shim.f90)
+void calcuvw() {
+  using namespace geometry;
+  using namespace parameters;
+  using namespace variables;
+  using namespace sparse_matrix;
+  if (lturb) { std::fprintf(stderr, "calcuvw: turbulent stresses (calcstress) are not on the GPU path\n"); std::exit(1); }
+  fc_calcuvw_opts o{};
+  o.nigrad = nigrad; o.nipgrad = nipgrad;
+  // read_input.f90:97-133 -> face_value (interpolation.f90:36-57)
+  static const struct { const char *name; int scheme, limiter; } table[] = {
+      {"central", 0, 7}, {"cds-corrected", 1, 7}, {"central-f", 2, 7}, {"linear-f", 3, 7}, {"muscl-f", 4, 7},
+      {"smart", 5, 0}, {"avl-smart", 5, 1}, {"muscl", 5, 2}, {"umist", 5, 3}, {"koren", 5, 4}, {"charm", 5, 5},
+      {"ospre", 5, 6}, {"linear", 5, 7}};
+  o.scheme = 5; o.limiter = 2;  // 'Convective scheme not chosen, assigning default muscl scheme'
+  for (auto &e : table)
+    if (convective_scheme == e.name) { o.scheme = e.scheme; o.limiter = e.limiter; }
+  o.gds = gds[iu];
+  for (int k = 0; k < 3; ++k) { o.urf[k] = urf[iu + k]; o.sor[k] = sor[iu + k]; o.nsw[k] = nsw[iu + k]; }
+  o.bdf = bdf; o.btime = btime; o.timestep = timestep; o.cn = cn;
+  o.const_mflux = const_mflux; o.gradPcmf = gradPcmf;
+  o.lbuoy = lcal[ien] && lbuoy; o.boussinesq = boussinesq;
+  o.beta = beta; o.tref = tref; o.densit = densit; o.gravx = gravx; o.gravy = gravy; o.gravz = gravz;
+  o.viscos = viscos;
+  o.sol = solver_opts(iu);
+  check(fc_upload(ctx, FC_DEN, den.data(), numTotal), "upload den");
+  if (ninl > 0) check(fc_upload(ctx, FC_FMI, fmi.data(), ninl), "upload fmi");
+  if (nout > 0) check(fc_upload(ctx, FC_FMO, fmo.data(), nout), "upload fmo");
+  // `a` is NOT uploaded: the U row sums read the stale diagonal of the previous solve (:423), and every solve of
+  // this build runs on the device, so the device copy of `a` is the current one by construction
+  if (bdf || cn) {
+    const struct { int f; std::vector<dp> *h; } old[] = {{FC_UO, &uo}, {FC_VO, &vo}, {FC_WO, &wo},
+                                                         {FC_UOO, &uoo}, {FC_VOO, &voo}, {FC_WOO, &woo}};
+    for (auto &e : old) check(fc_upload(ctx, e.f, e.h->data(), numTotal), "upload old time level");
+  }
+  if (o.lbuoy) check(fc_upload(ctx, FC_T, t.data(), numTotal), "upload t");
+  fc_calcuvw_report rep;
+  check(fc_calcuvw_host(ctx, &o, u.data(), v.data(), w.data(), p.data(), vis.data(), flmass.data(), apu.data(),
+                        apv.data(), apw.data(), &rep), "fc_calcuvw_host");
+  const struct { int f; std::vector<dp> *h; } grads[] = {{FC_DUDXI, &dUdxi}, {FC_DVDXI, &dVdxi}, {FC_DWDXI, &dWdxi},
+                                                         {FC_DPDXI, &dPdxi}};
+  for (auto &e : grads) check(fc_download(ctx, e.f, e.h->data(), 3 * (size_t)numCells), "download gradient");
+  check(fc_download(ctx, FC_A, a.data(), nnz), "download a");
+  for (int k = 0; k < 3; ++k) {
+    if (rep.rep[k].iters > 0) resor[iu + k] = rep.rep[k].res0;
+    std::printf("  BiCGStab(ILU(0)):  Solving for %s, Initial residual = %10.3E, Final residual = %10.3E, No Iterations %d\n",
+                title_mod::chvarSolver[iu + k], rep.rep[k].res0, rep.rep[k].resl, rep.rep[k].iters);
+  }
 }
 
 }  // namespace fcapp

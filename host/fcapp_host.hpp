@@ -5,7 +5,7 @@
 // argument meaning and side effects: module-global arrays (`module geometry`,
 // `sparse_matrix`, `parameters`, `variables`, `title_mod`) and free subroutines
 // `create_CSR_matrix_from_mesh_data`, `laplacian(mu,phi)`, `dpcg(fi,ifi)`, `iccg(fi,ifi)`,
-// `bicgstab(fi,ifi)`, `grad(phi,dPhidxi)`, `calcp()`.  Index VALUES stay 1-based as in Fortran;
+// `bicgstab(fi,ifi)`, `grad(phi,dPhidxi)`, `calcp()`, `calcuvw()`.  Index VALUES stay 1-based as in Fortran;
 // only the C++ container subscripts are 0-based.  Everything computes through libfcapp_cuda
 // (include/fcapp.h); there is no host arithmetic on the path.
 #pragma once
@@ -29,7 +29,7 @@ extern std::vector<dp> xc, yc, zc, vol, arx, ary, arz, xf, yf, zf, facint;
 
 namespace sparse_matrix {  // src/sparse_matrix.f90:8-22
 extern std::vector<int> ioffset, ja, diag, icell_jcell_csr_value_index, jcell_icell_csr_value_index;
-extern std::vector<dp> a, su, sv, res, apu, apv, apw;
+extern std::vector<dp> a, su, sv, sw, spu, spv, sp, res, apu, apv, apw;
 }  // namespace sparse_matrix
 
 namespace parameters {  // src/modules_allocatable.f90:10-137
@@ -41,10 +41,16 @@ extern int nsw[nphi + 1];
 extern int npcor, nigrad, nipgrad, pRefCell;
 extern bool const_mflux, ltest, lstsq_qr, lstsq_dm;
 extern dp flomas;
+// calcuvw (src/calcuvw.f90) reads these as well
+extern dp densit, viscos, gds[nphi + 1];
+extern bool bdf, cn, lturb, lbuoy, boussinesq, lcal[nphi + 1];
+extern dp btime, timestep, gradPcmf, beta, tref, gravx, gravy, gravz;
+extern std::string convective_scheme;  // as in the `input` file: muscl-f, linear-f, central, smart, ... (read_input.f90:97-133)
 }  // namespace parameters
 
 namespace variables {  // src/modules_allocatable.f90:149-200
 extern std::vector<dp> u, v, w, p, pp, den, flmass, fmi, fmo;
+extern std::vector<dp> vis, uo, vo, wo, uoo, voo, woo, t;
 extern std::vector<dp> dUdxi, dVdxi, dWdxi, dPdxi;  // (3,numCells): xyz interleaved
 extern dp sumLocalContErr, globalContErr, cumulativeContErr;
 }  // namespace variables
@@ -68,5 +74,6 @@ void dpcg(dp *fi, int ifi);                              // dpcg.f90:3
 void iccg(dp *fi, int ifi);                              // iccg.f90:3
 void bicgstab(dp *fi, int ifi);                          // bicgstab.f90:1
 void calcp();                                            // calcp-multiple_correction_SIMPLE.f90:3
+void calcuvw();                                          // calcuvw.f90:3 (laminar, serial)
 
 }  // namespace fcapp

@@ -1,8 +1,7 @@
 """GPU parity of the momentum predictor `call calcuvw` through the C ABI.
 
-Written after this round's GPU budget was spent: the kernels' per-index bodies are checked bit for bit against
-the oracle on the CPU (tests/test_momentum_bodies.py), these tests are their first run on hardware.  The file
-name sorts last so that the verified suites run first.
+The kernels' per-index bodies are also checked bit for bit against the oracle on the CPU
+(tests/test_momentum_bodies.py).  First hardware run: profiles/r01_momentum_gpu_tests.txt (37 passed).
 
 Bars: explicit sources / coefficients bit-exact (same summation order, no FMA); after the BiCGStab solves
 iteration counts within +-1 and fields within 1e-10 relative L2 when the counts agree.
@@ -235,3 +234,54 @@ def test_calcuvw_rejects_what_it_does_not_cover(fc):
         ctx.calcuvw(fc.calcuvw_opts())
     assert e.value.code == fc.FC_ERR_UNSUPPORTED   # numCells < 3: the reference's df(ijp,3) leaves the array
     ctx.close()
+
+
+def test_cavity_driver_simple_loop_matches_oracle():
+    """host/cavity: the SIMPLE loop of src/main.f90 (call calcuvw; call calcp) as a compiled program against
+    libfcapp_cuda.so with the shipped cavity settings; every solver report line it prints is compared with the
+    oracle running the same loop (iteration counts within +-1, printed residuals to the printed digits while the
+    counts agree)."""
+    import re
+    import subprocess
+    from freecappuccino_b200 import mesh as M
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "host", "cavity")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(root, "host")])
+    n, outer = 20, 12
+    out = subprocess.run([exe, str(n), str(outer), "1e-30"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = re.compile(r"Solving for (\w+), Initial residual = +(\d\.\d{3}E[+-]\d\d), Final residual = +"
+                      r"(\d\.\d{3}E[+-]\d\d), No Iterations (\d+)$", re.M)
+    got = [(m.group(1), float(m.group(2)), int(m.group(4))) for m in line.finditer(out.stdout)]
+    assert len(got) == 4 * outer, out.stdout[-2000:]
+    its, source, umax = out.stdout.strip().splitlines()[-1].split()
+    assert int(its) == outer
+
+    mesh = M.hex_mesh(n, n, 1, (0.1, 0.1, 0.01), ("wall", "wall", "wall", "wall", "symmetry", "symmetry"))
+    nt = mesh.numTotal
+    f = dict(u=np.zeros(nt), v=np.zeros(nt), w=np.zeros(nt), p=np.zeros(nt), den=np.ones(nt))
+    fs, sl = mesh.boundary_faces("wall"), mesh.boundary_slots("wall")
+    f["u"][sl[mesh.ary[fs] > 0.0]] = 1.0
+    csr, of, x, _ = make_state(mesh, f, stale=False)
+    x.vis[:] = 0.01
+    for k in ("uo", "vo", "wo", "uoo", "voo", "woo", "t"):
+        getattr(x, k)[:] = 0.0
+    of.flmass[:] = 0.0
+    oo = oracle.uvw_opts(scheme="muscl-f", urf=(0.7,) * 3, sor=(1e-2,) * 3, nsw=(20,) * 3, bdf=True, btime=0.0,
+                         timestep=1e20, viscos=0.01)
+    po = oracle.calcp_opts(solver="iccg", sor=1e-2, nsw=100, urf_p=0.3, pRefCell=1, const_mflux=False, flomas=0.0)
+    agree = True
+    for it in range(outer):
+        ru = oracle.calcuvw(mesh, csr, of, x, oo)
+        rp = oracle.calcp(mesh, csr, of, po)
+        ref = [("U", ru.rep[0]), ("V", ru.rep[1]), ("W", ru.rep[2]), ("p", rp.rep[0])]
+        for k, (name, r) in enumerate(ref):
+            g = got[4 * it + k]
+            assert g[0] == name
+            assert abs(g[2] - r.iters) <= 1, (it, name, g[2], r.iters)
+            agree = agree and g[2] == r.iters
+            if agree and r.res0 > 0:
+                assert g[1] == pytest.approx(r.res0, rel=2e-3), (it, name)
+    if agree:
+        assert float(umax) == pytest.approx(float(np.abs(of.u[:mesh.numCells]).max()), rel=1e-3)
