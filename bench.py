@@ -413,6 +413,16 @@ def run_ours(args):
         out["cpu_baseline"] = {"value": v, "unit": "iter/s", "cores": 1, "kind": "port",
                                "sample": f"{used} DPCG iterations of the same {args.n}^3 system (oracle, serial src "
                                          f"semantics, {dt:.1f} s)"}
+    if world == 1 and not args.no_simple:
+        # one whole device-resident SIMPLE iteration (calcuvw -> calcp) on the same mesh, the "SIMPLE iter time" of
+        # BASELINE.json's metric: momentum predictor + this path, no field crossing PCIe
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from simple_iter_bench import measure
+            ctx.set_spmv_sampling(0)
+            out["simple_iteration"] = measure(ctx, mesh, warm=2, steps=3)
+        except Exception as e:   # the headline line must not depend on the widened step
+            out["simple_iteration"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(out))
     ctx.close()
@@ -433,6 +443,7 @@ def main():
     ap.add_argument("--ref-ranks", type=int, default=32, help="reference arm: ranks (= host threads) of the "
                     "src-parallel build, capped by the host's core count")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-simple", action="store_true", help="skip the SIMPLE-iteration (calcuvw + calcp) timing")
     ap.add_argument("--no-persist", action="store_true", help="one launch per vector operation instead of the "
                     "persistent DPCG kernel (A/B)")
     args = ap.parse_args()
