@@ -623,6 +623,34 @@ static void correctBoundaryConditionsVelocity(const fco_mesh *g, fco_fields *f, 
   }
 }
 
+/* continuityErrors.h -- including its flmass(ijp) (not flmass(i)) indexing, :18-19 */
+static void continuity_errors(const fco_mesh *g, fco_fields *f, double *sumLocal, double *global) {
+  const int n = g->numCells;
+  for (int i = 0; i < n; ++i) f->res[i] = 0.0;
+  for (int i = 1; i <= g->numInnerFaces; ++i) {
+    int ijp = A1(g->owner, i), ijn = A1(g->neighbour, i);
+    A1(f->res, ijp) = A1(f->res, ijp) - A1(f->flmass, ijp);
+    A1(f->res, ijn) = A1(f->res, ijn) + A1(f->flmass, ijp);
+  }
+  for (int i = 1; i <= g->noc; ++i) {
+    A1(f->res, A1(g->ijl, i)) = A1(f->res, A1(g->ijl, i)) - A1(f->fmoc, i);
+    A1(f->res, A1(g->ijr, i)) = A1(f->res, A1(g->ijr, i)) + A1(f->fmoc, i);
+  }
+  for (int i = 1; i <= g->ninl; ++i) {
+    int ijp = A1(g->owner, g->iInletFacesStart + i);
+    A1(f->res, ijp) = A1(f->res, ijp) - A1(f->fmi, i);
+  }
+  for (int i = 1; i <= g->nout; ++i) {
+    int ijp = A1(g->owner, g->iOutletFacesStart + i);
+    A1(f->res, ijp) = A1(f->res, ijp) - A1(f->fmo, i);
+  }
+  double sl = 0.0, gl = 0.0;
+  for (int i = 1; i <= n; ++i) sl = sl + fabs(A1(f->res, i));
+  for (int i = 1; i <= n; ++i) gl = gl + A1(f->res, i);
+  *sumLocal = sl;
+  *global = gl;
+}
+
 /* ------------------------------------------------------------------------- */
 /* calcp: src/calcp-multiple_correction_SIMPLE.f90                            */
 /* ------------------------------------------------------------------------- */
@@ -714,31 +742,12 @@ int fco_calcp(const fco_mesh *g, const fco_csr *m, fco_fields *f, const fco_calc
       }
     }
   }
-  /* continuityErrors.h -- including its flmass(ijp) (not flmass(i)) indexing, :18-19 */
-  for (int i = 0; i < n; ++i) f->res[i] = 0.0;
-  for (int i = 1; i <= g->numInnerFaces; ++i) {
-    int ijp = A1(g->owner, i), ijn = A1(g->neighbour, i);
-    A1(f->res, ijp) = A1(f->res, ijp) - A1(f->flmass, ijp);
-    A1(f->res, ijn) = A1(f->res, ijn) + A1(f->flmass, ijp);
-  }
-  for (int i = 1; i <= g->noc; ++i) {
-    A1(f->res, A1(g->ijl, i)) = A1(f->res, A1(g->ijl, i)) - A1(f->fmoc, i);
-    A1(f->res, A1(g->ijr, i)) = A1(f->res, A1(g->ijr, i)) + A1(f->fmoc, i);
-  }
-  for (int i = 1; i <= g->ninl; ++i) {
-    int ijp = A1(g->owner, g->iInletFacesStart + i);
-    A1(f->res, ijp) = A1(f->res, ijp) - A1(f->fmi, i);
-  }
-  for (int i = 1; i <= g->nout; ++i) {
-    int ijp = A1(g->owner, g->iOutletFacesStart + i);
-    A1(f->res, ijp) = A1(f->res, ijp) - A1(f->fmo, i);
-  }
-  double sl = 0.0, gl = 0.0;
-  for (int i = 1; i <= n; ++i) sl = sl + fabs(A1(f->res, i));
-  for (int i = 1; i <= n; ++i) gl = gl + A1(f->res, i);
+  double sl, gl;
+  continuity_errors(g, f, &sl, &gl);
   rep->sumLocalContErr = sl;
   rep->globalContErr = gl;
   return 0;
 }
 
 #include "fc_oracle_uvw.c"
+#include "fc_oracle_piso.c"

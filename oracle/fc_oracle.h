@@ -162,6 +162,29 @@ int fco_calcuvw_component(const fco_mesh *g, const fco_csr *m, fco_fields *f, fc
 int fco_calcuvw(const fco_mesh *g, const fco_csr *m, fco_fields *f, fco_uvw *x, const fco_uvw_opts *o,
                 fco_uvw_report *rep);
 
+/* ---- PISO / PIMPLE pressure equation (fc_oracle_piso.c) ---- */
+typedef struct {
+  int ncorr, npcor, nigrad, nipgrad, pRefCell;
+  int pimple;        /* 0 PISO_multiple_correction, 1 PIMPLE_multiple_correction */
+  double urf_p;      /* PIMPLE: urf(ip) */
+  int const_mflux; double flomas;
+  int bdf; double btime, timestep; int cn;
+  int lbuoy, boussinesq; double beta, tref, densit, gravx, gravy, gravz;
+  fco_solver_opts sol; /* sor(ip), nsw(ip) */
+} fco_piso_opts;
+
+typedef struct {
+  fco_report rep[16];  /* iccg reports in call order (ncorr x npcor, the first 16) */
+  int nsolves;
+  double sumLocalContErr, globalContErr; /* last continuityErrors.h report */
+} fco_piso_report;
+
+void fco_get_rAU_x_UEqnH(const fco_mesh *g, const fco_csr *m, fco_fields *f, fco_uvw *x, const fco_piso_opts *o,
+                         const double *h);
+/* h: scratch of nnz doubles, receives the copy of the momentum matrix (module hcoef) */
+int fco_piso(const fco_mesh *g, const fco_csr *m, fco_fields *f, fco_uvw *x, const fco_piso_opts *o, double *h,
+             fco_piso_report *rep);
+
 /* ---- src-parallel semantics: R ranks in lock step inside one process (fc_oracle_par.c) ---- */
 typedef struct {
   fco_mesh g;

@@ -23,7 +23,7 @@ TOL = float(np.float32(1e-13))        # dpcg.f90:37
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libfc_oracle.so")
-    src = [os.path.join(_HERE, f) for f in ("fc_oracle.c", "fc_oracle_uvw.c", "fc_oracle_par.c", "fc_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("fc_oracle.c", "fc_oracle_uvw.c", "fc_oracle_piso.c", "fc_oracle_par.c", "fc_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libfc_oracle.so"])
     return so
@@ -87,7 +87,7 @@ def lib() -> C.CDLL:
         _LIB = C.CDLL(build())
         _LIB.fco_create_csr.restype = C.c_int
         for f in ("fco_dpcg", "fco_iccg", "fco_bicgstab", "fco_calcp", "fco_calcuvw", "fco_calcuvw_assemble",
-                  "fco_calcuvw_component"):
+                  "fco_calcuvw_component", "fco_piso"):
             getattr(_LIB, f).restype = C.c_int
     return _LIB
 
@@ -328,5 +328,43 @@ def calcuvw(mesh, csr: Csr, f: Fields, x: UvwFields, opts: FcoUvwOpts) -> FcoUvw
     ms, cs, fs, xs = mesh_struct(mesh), csr.c(), f.c(), x.c()
     rep = FcoUvwReport()
     rc = lib().fco_calcuvw(C.byref(ms), C.byref(cs), C.byref(fs), C.byref(xs), C.byref(opts), C.byref(rep))
+    assert rc == 0, rc
+    return rep
+
+
+# ---- PISO / PIMPLE pressure equation (fc_oracle_piso.c) ----
+class FcoPisoOpts(C.Structure):
+    _fields_ = [("ncorr", C.c_int), ("npcor", C.c_int), ("nigrad", C.c_int), ("nipgrad", C.c_int),
+                ("pRefCell", C.c_int), ("pimple", C.c_int), ("urf_p", C.c_double), ("const_mflux", C.c_int),
+                ("flomas", C.c_double), ("bdf", C.c_int), ("btime", C.c_double), ("timestep", C.c_double),
+                ("cn", C.c_int), ("lbuoy", C.c_int), ("boussinesq", C.c_int), ("beta", C.c_double),
+                ("tref", C.c_double), ("densit", C.c_double), ("gravx", C.c_double), ("gravy", C.c_double),
+                ("gravz", C.c_double), ("sol", FcoSolverOpts)]
+
+
+class FcoPisoReport(C.Structure):
+    _fields_ = [("rep", FcoReport * 16), ("nsolves", C.c_int), ("sumLocalContErr", C.c_double),
+                ("globalContErr", C.c_double)]
+
+
+def piso_opts(ncorr=1, npcor=1, nigrad=1, pRefCell=1, pimple=False, urf_p=0.3, const_mflux=False, flomas=0.0,
+              bdf=True, btime=0.0, timestep=1e-3, cn=False, lbuoy=False, boussinesq=True, beta=0.0, tref=0.0,
+              densit=1.0, grav=(0.0, 0.0, 0.0), sor=1e-2, nsw=100, small=SMALL, tol=TOL) -> FcoPisoOpts:
+    return FcoPisoOpts(ncorr, npcor, nigrad, 2, pRefCell, int(pimple), urf_p, int(const_mflux), flomas, int(bdf), btime,
+                       timestep, int(cn), int(lbuoy), int(boussinesq), beta, tref, densit, grav[0], grav[1], grav[2],
+                       FcoSolverOpts(sor, nsw, small, tol, 0))
+
+
+def get_rAU_x_UEqnH(mesh, csr: Csr, f: Fields, x: UvwFields, opts: FcoPisoOpts, h: np.ndarray) -> None:
+    ms, cs, fs, xs = mesh_struct(mesh), csr.c(), f.c(), x.c()
+    lib().fco_get_rAU_x_UEqnH(C.byref(ms), C.byref(cs), C.byref(fs), C.byref(xs), C.byref(opts), _d(h))
+
+
+def piso(mesh, csr: Csr, f: Fields, x: UvwFields, opts: FcoPisoOpts) -> FcoPisoReport:
+    """PISO_multiple_correction / PIMPLE_multiple_correction; f.a must hold the momentum matrix of calcuvw."""
+    ms, cs, fs, xs = mesh_struct(mesh), csr.c(), f.c(), x.c()
+    rep = FcoPisoReport()
+    h = np.zeros(csr.nnz)
+    rc = lib().fco_piso(C.byref(ms), C.byref(cs), C.byref(fs), C.byref(xs), C.byref(opts), _d(h), C.byref(rep))
     assert rc == 0, rc
     return rep
