@@ -3,7 +3,8 @@
 ! host code and libfcapp_cuda.so (C ABI: include/fcapp.h).
 !
 ! Drop-in use: remove  sparse_matrix.f90's create_CSR_matrix_from_mesh_data
-! body, calcp-multiple_correction_SIMPLE.f90, calcuvw.f90, dpcg.f90, iccg.f90,
+! body, calcp-multiple_correction_SIMPLE.f90, calcuvw.f90, PISO_multiple_correction.f90,
+! PIMPLE_multiple_correction.f90, get_rAU_x_UEqnH.f90, dpcg.f90, iccg.f90,
 ! bicgstab.f90, fvm_laplacian.f90 (laplacian) and the 'gauss' branch of
 ! gradients.f90 from the Makefile's object list, add this file, and link
 ! with  -L<repo>/freecappuccino_b200 -lfcapp_cuda .  Every subroutine
@@ -85,6 +86,24 @@ module fcapp_c
     type(fc_solver_opts) :: sol
   end type
 
+  type, bind(C) :: fc_piso_opts
+    integer(c_int) :: ncorr, npcor, nigrad, nipgrad, pRefCell, pimple
+    real(c_double) :: urf_p
+    integer(c_int) :: const_mflux
+    real(c_double) :: flomas
+    integer(c_int) :: bdf
+    real(c_double) :: btime, timestep
+    integer(c_int) :: cn, lbuoy, boussinesq
+    real(c_double) :: beta, tref, densit, gravx, gravy, gravz
+    type(fc_solver_opts) :: sol
+  end type
+
+  type, bind(C) :: fc_piso_report
+    type(fc_solver_report) :: rep(16)
+    integer(c_int) :: nsolves
+    real(c_double) :: sumLocalContErr, globalContErr
+  end type
+
   type, bind(C) :: fc_calcuvw_report
     type(fc_solver_report) :: rep(3)
   end type
@@ -147,6 +166,9 @@ module fcapp_c
       import; type(c_ptr), value :: ctx; type(fc_calcuvw_opts) :: o
       real(c_double) :: u(*), v(*), w(*), p(*), vis(*), flmass(*), apu(*), apv(*), apw(*)
       type(fc_calcuvw_report) :: rep
+    end function
+    integer(c_int) function fc_piso(ctx, o, rep) bind(C, name='fc_piso')
+      import; type(c_ptr), value :: ctx; type(fc_piso_opts) :: o; type(fc_piso_report) :: rep
     end function
     integer(c_int) function fc_exchange(ctx, field) bind(C, name='fc_exchange')
       import; type(c_ptr), value :: ctx; integer(c_int), value :: field
@@ -420,6 +442,59 @@ subroutine calcuvw
     write(6,'(3a,1PE10.3,a,1PE10.3,a,I0)') '  BiCGStab(ILU(0)):  Solving for ',nm(k), &
     ', Initial residual = ',rep%rep(k)%res0,', Final residual = ',rep%rep(k)%resl,', No Iterations ',rep%rep(k)%iters
   end do
+end subroutine
+
+! src/PISO_multiple_correction.f90:2 and src/PIMPLE_multiple_correction.f90:2 -- run directly after calcuvw: the
+! device still holds the momentum matrix (backed up as h = a), ap*, u, v, w, the old time levels and flmass
+subroutine fcapp_piso(pimple)
+  use types
+  use parameters
+  use geometry
+  use sparse_matrix
+  use variables
+  use title_mod
+  use fcapp_c
+  implicit none
+  logical, intent(in) :: pimple
+  type(fc_piso_opts) :: o
+  type(fc_piso_report) :: rep
+  integer :: k
+  o%ncorr = ncorr; o%npcor = npcor; o%nigrad = nigrad; o%nipgrad = nipgrad; o%pRefCell = pRefCell
+  o%pimple = merge(1, 0, pimple); o%urf_p = urf(ip)
+  o%const_mflux = merge(1, 0, const_mflux); o%flomas = flomas
+  o%bdf = merge(1, 0, bdf); o%btime = btime; o%timestep = timestep; o%cn = merge(1, 0, cn)
+  o%lbuoy = merge(1, 0, lcal(ien) .and. lbuoy); o%boussinesq = merge(1, 0, boussinesq)
+  o%beta = beta; o%tref = tref; o%densit = densit; o%gravx = gravx; o%gravy = gravy; o%gravz = gravz
+  o%sol = solver_opts(ip)
+  call fc_check(fc_upload(fc_ctx, FC_PP, pp, int(numTotal, c_size_t)), 'upload pp')   ! pp is not reset (PISO :199)
+  call fc_check(fc_piso(fc_ctx, o, rep), 'fc_piso')
+  call fc_check(fc_download(fc_ctx, FC_U, u, int(numTotal, c_size_t)), 'download u')
+  call fc_check(fc_download(fc_ctx, FC_V, v, int(numTotal, c_size_t)), 'download v')
+  call fc_check(fc_download(fc_ctx, FC_W, w, int(numTotal, c_size_t)), 'download w')
+  call fc_check(fc_download(fc_ctx, FC_P, p, int(numTotal, c_size_t)), 'download p')
+  call fc_check(fc_download(fc_ctx, FC_PP, pp, int(numTotal, c_size_t)), 'download pp')
+  call fc_check(fc_download(fc_ctx, FC_FLMASS, flmass, int(numInnerFaces, c_size_t)), 'download flmass')
+  call fc_check(fc_download(fc_ctx, FC_DPDXI, dPdxi, int(3*numCells, c_size_t)), 'download dPdxi')
+  do k = 1, min(rep%nsolves, 16)
+    if (rep%rep(k)%iters > 0) resor(ip) = rep%rep(k)%res0
+    write(6,'(3a,1PE10.3,a,1PE10.3,a,I0)') '  PCG(IC0):  Solving for ',trim(chvarSolver(ip)), &
+    ', Initial residual = ',rep%rep(k)%res0,', Final residual = ',rep%rep(k)%resl,', No Iterations ',rep%rep(k)%iters
+  end do
+  sumLocalContErr = rep%sumLocalContErr
+  globalContErr = rep%globalContErr
+  cumulativeContErr = cumulativeContErr + globalContErr
+  write(6,'(3(a,es10.3))') "  time step continuity errors : sum local = ", sumLocalContErr, &
+ &                          ", global = ", globalContErr, ", cumulative = ", cumulativeContErr
+end subroutine
+
+subroutine PISO_multiple_correction
+  implicit none
+  call fcapp_piso(.false.)
+end subroutine
+
+subroutine PIMPLE_multiple_correction
+  implicit none
+  call fcapp_piso(.true.)
 end subroutine
 
 ! src-parallel/exchange.f90:3 and global_sum_mpi.f90:4 (MPI build: fc_comm_init after MPI_Init, the

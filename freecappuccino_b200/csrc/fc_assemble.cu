@@ -14,6 +14,7 @@
 // prOutlet) and accumulates left to right.  The result is deterministic and -- because
 // the library is built with -fmad=false and IEEE division / sqrt -- bit-identical to the
 // Fortran loops.
+#include "fc_piso_body.cuh"
 #include "fc_reduce.cuh"
 
 namespace {
@@ -712,5 +713,139 @@ int fc_calcp_dev(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep) 
   ctx->tm.solve_ms = solve_ms;
   cudaEventDestroy(c0);
   cudaEventDestroy(c1);
+  return FC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// PISO / PIMPLE pressure equation (PISO_multiple_correction.f90, PIMPLE_multiple_correction.f90,
+// get_rAU_x_UEqnH.f90).  Bodies: fc_piso_body.cuh.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) k_hbya_rows(fcm_geom g, fcm_c2f m, fcp_hbya k) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < g.n) fcp_hbya_row(g, m, k, c);
+}
+__global__ void __launch_bounds__(256)
+k_hbya_scale(int n, const double *apu, const double *apv, const double *apw, const double *su, const double *sv,
+             const double *sw, double *u, double *v, double *w) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) fcp_hbya_scale(c, apu, apv, apw, su, sv, sw, u, v, w);
+}
+__global__ void k_pin_row(const int *ioffset, const int *diag, double *a, double *su, const double *src, int pref) {
+  fcp_pin_row(ioffset, diag, a, su, src, pref);
+}
+__global__ void __launch_bounds__(256)
+k_flux_correct_matrix(fcm_geom g, const int *icj, const double *a, const double *pp, double *flmass) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.F) fcp_flux_correct(g, icj, a, pp, flmass, i);
+}
+__global__ void __launch_bounds__(256)
+k_piso_velocity_correct(fcm_geom g, const double *apu, const double *apv, const double *apw, const double *dP,
+                        double *u, double *v, double *w) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < g.n) fcp_velocity_correct(g, apu, apv, apw, dP, u, v, w, c);
+}
+__global__ void __launch_bounds__(256) k_relax_p(int n, double urf, const double *pp, double *p) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) fcp_relax_p(urf, pp, p, c);
+}
+
+int piso_continuity(fc_context *ctx, fc_piso_report *rep) {   // continuityErrors.h
+  k_continuity<<<FC_RED_GRID, FC_RED_BLOCK, 0, ctx->stream>>>(geom_of(ctx), c2f_of(ctx), slots_of(ctx),
+                                                             ctx->field[FC_FLMASS], ctx->field[FC_FMPRO],
+                                                             ctx->field[FC_FMI], ctx->field[FC_FMO], ctx->field[FC_RES],
+                                                             ctx->partials, ctx->sc);
+  FC_LAUNCH_CHECK();
+  FC_CUDA(cudaMemcpyAsync(ctx->sc_host, ctx->sc, sizeof(fc_scalars), cudaMemcpyDeviceToHost, ctx->stream));
+  FC_CUDA(cudaStreamSynchronize(ctx->stream));
+  rep->sumLocalContErr = ctx->sc_host->red[0];
+  rep->globalContErr = ctx->sc_host->red[1];
+  return FC_OK;
+}
+
+}  // namespace
+
+int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep) {
+  FC_CHECK(need_mesh(ctx, "fc_piso"));
+  if (ctx->npro > 0 || ctx->nranks > 1)
+    FC_FAIL(FC_ERR_UNSUPPORTED, "fc_piso: one rank in this version (src-parallel/PISO_multiple_correction.f90 "
+                                "processor faces are not ported yet)");
+  if (o->ncorr < 1 || o->npcor < 1 || o->nigrad < 1 || o->nipgrad < 0) FC_FAIL(FC_ERR_ARG, "fc_piso: bad corrector counts");
+  if (o->pRefCell < 1 || o->pRefCell > ctx->n) FC_FAIL(FC_ERR_ARG, "fc_piso: pRefCell out of range");
+  if ((o->bdf || o->cn) && !(o->timestep > 0.0)) FC_FAIL(FC_ERR_ARG, "fc_piso: timestep must be > 0");
+  FC_CHECK(fc_momentum_fields(ctx));
+  if (!ctx->hcoef) FC_CHECK(fc_dev_alloc(ctx, &ctx->hcoef, (size_t)ctx->nnz + 2));
+  const int B = 256, n = ctx->n;
+  cudaStream_t st = ctx->stream;
+  double **fl = ctx->field;
+  const fcm_geom g{ctx->owner, ctx->neigh, ctx->xc, ctx->yc, ctx->zc, ctx->vol, ctx->arx, ctx->ary, ctx->arz,
+                   ctx->xf, ctx->yf, ctx->zf, ctx->facint, ctx->n, ctx->F};
+  const fcm_c2f m{ctx->c2f_off, ctx->c2f_face, ctx->c2f_other, ctx->c2f_pos};
+  // h = a   (PISO :84): the momentum matrix calcuvw left behind
+  FC_CUDA(cudaMemcpyAsync(ctx->hcoef, fl[FC_A], sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDeviceToDevice, st));
+  fc_calcp_opts co{};
+  co.npcor = 1; co.nigrad = o->nigrad; co.nipgrad = o->nipgrad; co.pRefCell = o->pRefCell;
+  co.flux_variant = 2;   // facefluxmass_piso
+  co.const_mflux = o->const_mflux; co.flomas = o->flomas; co.sol = o->sol;
+  rep->nsolves = 0;
+  rep->sumLocalContErr = rep->globalContErr = 0.0;
+  double solve_ms = 0.0;
+  for (int icorr = 1; icorr <= o->ncorr; ++icorr) {
+    const fcp_hbya hk{ctx->ioffset, ctx->diag, ctx->hcoef, fl[FC_U], fl[FC_V], fl[FC_W], fl[FC_UO], fl[FC_VO],
+                      fl[FC_WO], fl[FC_UOO], fl[FC_VOO], fl[FC_WOO], fl[FC_T], fl[FC_DEN], fl[FC_SU], fl[FC_SV],
+                      fl[FC_SW], o->bdf, o->btime, o->timestep, o->cn, o->lbuoy, o->boussinesq, o->beta, o->tref,
+                      o->densit, o->gravx, o->gravy, o->gravz};
+    k_hbya_rows<<<fc_blocks(n, B), B, 0, st>>>(g, m, hk);                                     // get_rAU_x_UEqnH
+    FC_LAUNCH_CHECK();
+    k_hbya_scale<<<fc_blocks(n, B), B, 0, st>>>(n, fl[FC_APU], fl[FC_APV], fl[FC_APW], fl[FC_SU], fl[FC_SV],
+                                                fl[FC_SW], fl[FC_U], fl[FC_V], fl[FC_W]);
+    FC_LAUNCH_CHECK();
+    // grad(U,V,W); a = 0; su = 0; facefluxmass_piso face loop; adjustMassFlow   (PISO :104-181)
+    FC_CHECK(fc_calcp_assemble_dev(ctx, &co));
+    k_pin_row<<<1, 1, 0, st>>>(ctx->ioffset, ctx->diag, fl[FC_A], fl[FC_SU], o->pimple ? fl[FC_PP] : fl[FC_P],
+                               o->pRefCell - 1);                                              // :188-192
+    FC_LAUNCH_CHECK();
+    for (int ipcorr = 1; ipcorr <= o->npcor; ++ipcorr) {
+      fc_solver_report *r = &rep->rep[rep->nsolves < 16 ? rep->nsolves : 15];
+      FC_CHECK(fc_solve_device(ctx, FC_ICCG, fl[FC_PP], &o->sol, r, nullptr));                // call iccg(pp,ip)
+      solve_ms += ctx->tm.solve_ms;
+      rep->nsolves++;
+      if (!o->pimple) {
+        if (ipcorr == o->npcor && ctx->F > 0) {
+          k_flux_correct_matrix<<<fc_blocks(ctx->F, B), B, 0, st>>>(g, ctx->icj, fl[FC_A], fl[FC_PP], fl[FC_FLMASS]);
+          FC_LAUNCH_CHECK();
+        }
+        FC_CHECK(piso_continuity(ctx, rep));
+      }
+    }
+    if (o->pimple) {
+      if (ctx->F > 0) {
+        k_flux_correct_matrix<<<fc_blocks(ctx->F, B), B, 0, st>>>(g, ctx->icj, fl[FC_A], fl[FC_PP], fl[FC_FLMASS]);
+        FC_LAUNCH_CHECK();
+      }
+      FC_CHECK(piso_continuity(ctx, rep));
+      k_relax_p<<<fc_blocks(n, B), B, 0, st>>>(n, o->urf_p, fl[FC_PP], fl[FC_P]);
+      FC_LAUNCH_CHECK();
+    } else {
+      FC_CUDA(cudaMemcpyAsync(fl[FC_P], fl[FC_PP], sizeof(double) * (size_t)ctx->NT, cudaMemcpyDeviceToDevice, st));  // p = pp
+    }
+    for (int istage = 1; istage <= o->nipgrad; ++istage) {
+      FC_CHECK(fc_bpres_dev(ctx, fl[FC_P], fl[FC_DPDXI], istage));
+      FC_CHECK(fc_grad_gauss_dev(ctx, fl[FC_P], fl[FC_DPDXI], o->nigrad));
+    }
+    k_piso_velocity_correct<<<fc_blocks(n, B), B, 0, st>>>(g, fl[FC_APU], fl[FC_APV], fl[FC_APW], fl[FC_DPDXI],
+                                                           fl[FC_U], fl[FC_V], fl[FC_W]);
+    FC_LAUNCH_CHECK();
+    // correctBoundaryConditionsVelocity
+    FC_CHECK(outlet_extrapolate_and_scale(ctx, o->flomas, o->sol.small, false));
+    const slots_t sl = slots_of(ctx);
+    if (sl.count[2] > 0) {
+      k_symmetry_project<<<fc_blocks(sl.count[2], B), B, 0, st>>>(geom_of(ctx), sl, fl[FC_U], fl[FC_V], fl[FC_W]);
+      FC_LAUNCH_CHECK();
+    }
+  }
+  FC_CUDA(cudaStreamSynchronize(st));
+  ctx->tm.solve_ms = solve_ms;
   return FC_OK;
 }

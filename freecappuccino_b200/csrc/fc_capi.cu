@@ -104,7 +104,7 @@ void free_all(fc_context *ctx) {
                   (void *)ctx->vk, (void *)ctx->adiag, (void *)ctx->tt, (void *)ctx->coef, (void *)ctx->facev,
                   (void *)ctx->gtmp, (void *)ctx->partials, (void *)ctx->sc, (void *)ctx->bufind,
                   (void *)ctx->sendbuf, (void *)ctx->strip_off, (void *)ctx->strip_idx,
-                  (void *)ctx->strip_any32, (void *)ctx->persist, (void *)ctx->uvw_face})
+                  (void *)ctx->strip_any32, (void *)ctx->persist, (void *)ctx->uvw_face, (void *)ctx->hcoef})
     if (p) cudaFree(p);
   for (int f = 0; f < FC_NUM_FIELDS; ++f)
     if (ctx->field[f]) cudaFree(ctx->field[f]);
@@ -214,6 +214,7 @@ int fc_set_mesh(fc_context *ctx, const fc_mesh_desc *m) {
     FC_FAIL(FC_ERR_ARG, "fc_set_mesh: NULL geometry array");
   if (m->npro > 0 && (!m->fpro || !m->neighbProcNo || !m->neighbProcOffset || m->numConnections < 1))
     FC_FAIL(FC_ERR_ARG, "fc_set_mesh: processor boundary without fpro / neighbProcNo / neighbProcOffset");
+  if (ctx->hcoef) { cudaFree(ctx->hcoef); ctx->hcoef = nullptr; }
   if (ctx->uvw_face) {  // momentum fields are sized by the mesh: drop them, they come back on first use
     cudaFree(ctx->uvw_face);
     ctx->uvw_face = nullptr;
@@ -514,6 +515,12 @@ int fc_calcuvw_host(fc_context *ctx, const fc_calcuvw_opts *o, double *u, double
     if (t.h) FC_CUDA(cudaMemcpyAsync(t.h, ctx->field[t.f], sizeof(double) * t.n, cudaMemcpyDeviceToHost, st));
   FC_CUDA(cudaStreamSynchronize(st));
   return FC_OK;
+}
+
+int fc_piso(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep) {
+  if (!ctx || !o || !rep) return FC_ERR_ARG;
+  FC_CUDA(cudaSetDevice(ctx->device));
+  return fc_piso_dev(ctx, o, rep);
 }
 
 int fc_exchange(fc_context *ctx, int field) {

@@ -125,6 +125,7 @@ struct fc_context {
   double *coef = nullptr;               // per-face coefficient cap = can [F + npro]
   double *facev = nullptr;              // per-face scratch [NF]
   double *gtmp = nullptr;               // previous-pass gradient (3,numCells)
+  double *hcoef = nullptr;              // PISO: h = a, the momentum matrix backed up before the correctors [nnz]
   double *uvw_face = nullptr;           // momentum predictor: can, cap, sup, svp, swp, fie per inner face [6 F]
   double *partials = nullptr;           // [FC_MAX_RED * FC_RED_GRID]
   fc_scalars *sc = nullptr;             // device
@@ -244,3 +245,4 @@ int fc_momentum_fields(fc_context *ctx);                            // fc_capi.c
 int fc_calcuvw_assemble_dev(fc_context *ctx, const fc_calcuvw_opts *o);                   // fc_momentum.cu
 int fc_calcuvw_component_dev(fc_context *ctx, const fc_calcuvw_opts *o, int comp, fc_solver_report *rep);
 int fc_calcuvw_dev(fc_context *ctx, const fc_calcuvw_opts *o, fc_calcuvw_report *rep);
+int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep);             // fc_assemble.cu

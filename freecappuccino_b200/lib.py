@@ -41,7 +41,7 @@ SYMBOLS = (
     "fc_solve_csr", "fc_calcp_assemble", "fc_calcp", "fc_calcp_host", "fc_exchange", "fc_global_sum",
     "fc_get_timings", "fc_time_spmv", "fc_stream", "fc_copy", "fc_set_spmv_sampling", "fc_comm_p2p_blob",
     "fc_comm_p2p_open", "fc_set_tuning", "fc_calcuvw_assemble", "fc_calcuvw_component", "fc_calcuvw",
-    "fc_calcuvw_host",
+    "fc_calcuvw_host", "fc_piso",
 )
 TUNE_SPMV_KERNEL, TUNE_DPCG_PERSISTENT, TUNE_CTAS_PER_SM, TUNE_PIPE_GEOMETRY = 0, 1, 2, 3
 
@@ -115,6 +115,29 @@ def calcuvw_opts(scheme="muscl-f", gds=1.0, urf=(0.7, 0.7, 0.7), sor=(1e-2, 1e-2
     return CalcuvwOpts(nigrad, 2, sc, lim, gds, (C.c_double * 3)(*urf), (C.c_double * 3)(*sor), (C.c_int * 3)(*nsw),
                        int(bdf), btime, timestep, int(cn), int(const_mflux), gradPcmf, int(lbuoy), int(boussinesq),
                        beta, tref, densit, grav[0], grav[1], grav[2], viscos, SolverOpts(0.0, 0, small, tol, 0))
+
+
+class PisoOpts(C.Structure):
+    _fields_ = [("ncorr", C.c_int), ("npcor", C.c_int), ("nigrad", C.c_int), ("nipgrad", C.c_int),
+                ("pRefCell", C.c_int), ("pimple", C.c_int), ("urf_p", C.c_double), ("const_mflux", C.c_int),
+                ("flomas", C.c_double), ("bdf", C.c_int), ("btime", C.c_double), ("timestep", C.c_double),
+                ("cn", C.c_int), ("lbuoy", C.c_int), ("boussinesq", C.c_int), ("beta", C.c_double),
+                ("tref", C.c_double), ("densit", C.c_double), ("gravx", C.c_double), ("gravy", C.c_double),
+                ("gravz", C.c_double), ("sol", SolverOpts)]
+
+
+class PisoReport(C.Structure):
+    _fields_ = [("rep", SolverReport * 16), ("nsolves", C.c_int), ("sumLocalContErr", C.c_double),
+                ("globalContErr", C.c_double)]
+
+
+def piso_opts(ncorr=1, npcor=1, nigrad=1, pRefCell=1, pimple=False, urf_p=0.3, const_mflux=False, flomas=0.0,
+              bdf=True, btime=0.0, timestep=1e-3, cn=False, lbuoy=False, boussinesq=True, beta=0.0, tref=0.0,
+              densit=1.0, grav=(0.0, 0.0, 0.0), sor=1e-2, nsw=100, small=SMALL, tol=TOL) -> PisoOpts:
+    """Options of ``PISO_multiple_correction`` / ``PIMPLE_multiple_correction`` (pimple=True)."""
+    return PisoOpts(ncorr, npcor, nigrad, 2, pRefCell, int(pimple), urf_p, int(const_mflux), flomas, int(bdf), btime,
+                    timestep, int(cn), int(lbuoy), int(boussinesq), beta, tref, densit, grav[0], grav[1], grav[2],
+                    SolverOpts(sor, nsw, small, tol, 0))
 
 
 class FcError(RuntimeError):
@@ -377,6 +400,11 @@ class Context:
         rep = CalcuvwReport()
         self._ck(self.lib.fc_calcuvw_host(self.h, C.byref(opts), _d(u), _d(v), _d(w), _d(p), _d(vis), _d(flmass),
                                           _d(apu), _d(apv), _d(apw), C.byref(rep)))
+        return rep
+
+    def piso(self, opts: PisoOpts) -> PisoReport:
+        rep = PisoReport()
+        self._ck(self.lib.fc_piso(self.h, C.byref(opts), C.byref(rep)))
         return rep
 
     def exchange(self, field: str):

@@ -23,7 +23,7 @@ namespace parameters {
 dp small = (dp)1e-20f;
 dp sor[nphi + 1], urf[nphi + 1], resor[nphi + 1];
 int nsw[nphi + 1];
-int npcor = 1, nigrad = 1, nipgrad = 2, pRefCell = 1;
+int npcor = 1, nigrad = 1, nipgrad = 2, pRefCell = 1, ncorr = 1;
 bool const_mflux = false, ltest = false, lstsq_qr = false, lstsq_dm = false;
 dp flomas = 0.0;
 dp densit = 1.0, viscos = 0.01, gds[nphi + 1];
@@ -296,5 +296,41 @@ void calcuvw() {
                 title_mod::chvarSolver[iu + k], rep.rep[k].res0, rep.rep[k].resl, rep.rep[k].iters);
   }
 }
+
+// PISO_multiple_correction.f90:2 / PIMPLE_multiple_correction.f90:2 -- directly after calcuvw: the device still holds
+// the momentum matrix (backed up as h = a), ap*, u, v, w, the old time levels and flmass
+static void piso(bool pimple) {
+  using namespace geometry;
+  using namespace parameters;
+  using namespace variables;
+  fc_piso_opts o{};
+  o.ncorr = ncorr; o.npcor = npcor; o.nigrad = nigrad; o.nipgrad = nipgrad; o.pRefCell = pRefCell;
+  o.pimple = pimple; o.urf_p = urf[ip];
+  o.const_mflux = const_mflux; o.flomas = flomas;
+  o.bdf = bdf; o.btime = btime; o.timestep = timestep; o.cn = cn;
+  o.lbuoy = lcal[ien] && lbuoy; o.boussinesq = boussinesq;
+  o.beta = beta; o.tref = tref; o.densit = densit; o.gravx = gravx; o.gravy = gravy; o.gravz = gravz;
+  o.sol = solver_opts(ip);
+  fc_piso_report rep;
+  check(fc_upload(ctx, FC_PP, pp.data(), numTotal), "upload pp");  // pp is not reset between calls (PISO :199)
+  check(fc_piso(ctx, &o, &rep), "fc_piso");
+  const struct { int f; std::vector<dp> *h; size_t n; } dn[] = {
+      {FC_U, &u, (size_t)numTotal}, {FC_V, &v, (size_t)numTotal}, {FC_W, &w, (size_t)numTotal},
+      {FC_P, &p, (size_t)numTotal}, {FC_PP, &pp, (size_t)numTotal}, {FC_FLMASS, &flmass, (size_t)numInnerFaces},
+      {FC_DPDXI, &dPdxi, 3 * (size_t)numCells}};
+  for (auto &e : dn) check(fc_download(ctx, e.f, e.h->data(), e.n), "download");
+  for (int k = 0; k < rep.nsolves && k < 16; ++k) {
+    if (rep.rep[k].iters > 0) resor[ip] = rep.rep[k].res0;
+    std::printf("  PCG(IC0):  Solving for %s, Initial residual = %10.3E, Final residual = %10.3E, No Iterations %d\n",
+                title_mod::chvarSolver[ip], rep.rep[k].res0, rep.rep[k].resl, rep.rep[k].iters);
+  }
+  sumLocalContErr = rep.sumLocalContErr;
+  globalContErr = rep.globalContErr;
+  cumulativeContErr += globalContErr;
+  std::printf("  time step continuity errors : sum local = %10.3E, global = %10.3E, cumulative = %10.3E\n",
+              sumLocalContErr, globalContErr, cumulativeContErr);
+}
+void PISO_multiple_correction() { piso(false); }
+void PIMPLE_multiple_correction() { piso(true); }
 
 }  // namespace fcapp

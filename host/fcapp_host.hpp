@@ -38,7 +38,7 @@ enum { iu = 1, iv, iw, ip, ite, ied, ien, ivis, ivart, icon };  // variable iden
 extern dp small;                       // 1e-20 as a default-real literal
 extern dp sor[nphi + 1], urf[nphi + 1], resor[nphi + 1];
 extern int nsw[nphi + 1];
-extern int npcor, nigrad, nipgrad, pRefCell;
+extern int npcor, nigrad, nipgrad, pRefCell, ncorr;
 extern bool const_mflux, ltest, lstsq_qr, lstsq_dm;
 extern dp flomas;
 // calcuvw (src/calcuvw.f90) reads these as well
@@ -75,5 +75,7 @@ void iccg(dp *fi, int ifi);                              // iccg.f90:3
 void bicgstab(dp *fi, int ifi);                          // bicgstab.f90:1
 void calcp();                                            // calcp-multiple_correction_SIMPLE.f90:3
 void calcuvw();                                          // calcuvw.f90:3 (laminar, serial)
+void PISO_multiple_correction();                         // PISO_multiple_correction.f90:2
+void PIMPLE_multiple_correction();                       // PIMPLE_multiple_correction.f90:2
 
 }  // namespace fcapp

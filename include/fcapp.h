@@ -258,6 +258,30 @@ int fc_calcuvw_host(fc_context *ctx, const fc_calcuvw_opts *o, double *u, double
                     const double *vis, const double *flmass, double *apu, double *apv, double *apw,
                     fc_calcuvw_report *rep);
 
+/* ---- PISO / PIMPLE pressure equation (src/PISO_multiple_correction.f90:2,
+ * src/PIMPLE_multiple_correction.f90:2, src/get_rAU_x_UEqnH.f90:2).
+ * Call after fc_calcuvw: FC_A must still hold the momentum matrix (it is backed up as
+ * `h = a`), FC_APU/APV/APW the reciprocal diagonals.  Works on the pressure itself:
+ * FC_PP is the unknown (not reset between correctors), FC_P receives it (PISO: p = pp;
+ * PIMPLE: p += urf_p (pp - p)).  Serial semantics, one rank, no O-C cuts.          */
+typedef struct {
+  int ncorr, npcor, nigrad, nipgrad, pRefCell; /* pRefCell 1-based                   */
+  int pimple;           /* 0 PISO_multiple_correction, 1 PIMPLE_multiple_correction   */
+  double urf_p;         /* PIMPLE: urf(ip)                                            */
+  int const_mflux; double flomas;
+  int bdf; double btime, timestep; int cn;      /* sources of get_rAU_x_UEqnH          */
+  int lbuoy, boussinesq; double beta, tref, densit, gravx, gravy, gravz;
+  fc_solver_opts sol;   /* sor(ip), nsw(ip), small, tol                               */
+} fc_piso_opts;
+
+typedef struct {
+  fc_solver_report rep[16]; /* iccg(pp,ip) reports in call order (the first 16)      */
+  int nsolves;
+  double sumLocalContErr, globalContErr; /* last continuityErrors.h report          */
+} fc_piso_report;
+
+int fc_piso(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep);
+
 /* ---- src-parallel communication (exchange.f90, global_sum_mpi.f90) ------ */
 int fc_exchange(fc_context *ctx, int field);          /* halo of a numTotal / numPCells field */
 int fc_global_sum(fc_context *ctx, double *value);    /* in-place sum over ranks (host scalar) */

@@ -6,7 +6,7 @@
 // on a machine without a GPU.  On the GPU the same bodies are called by the thin __global__ wrappers
 // of fc_momentum.cu (tests/test_gpu_zz_momentum.py compares those with the oracle).  The library has
 // no host path: this file is built only by the test that uses it.
-#include "../../freecappuccino_b200/csrc/fc_momentum_body.cuh"
+#include "../../freecappuccino_b200/csrc/fc_piso_body.cuh"   // includes fc_momentum_body.cuh
 
 extern "C" {
 
@@ -22,6 +22,24 @@ void fcm_host_component(const fcm_geom *g, const fcm_c2f *m, const fcm_comp *k) 
   for (int c = 0; c < g->n; ++c) fcm_component(*g, *m, *k, c);
 }
 
+// get_rAU_x_UEqnH: all rows first (they read the old u, v, w of their neighbours), then u = apu * su ...
+void fcp_host_hbya(const fcm_geom *g, const fcm_c2f *m, const fcp_hbya *k, const double *apu, const double *apv,
+                   const double *apw, double *u, double *v, double *w) {
+  for (int c = 0; c < g->n; ++c) fcp_hbya_row(*g, *m, *k, c);
+  for (int c = 0; c < g->n; ++c) fcp_hbya_scale(c, apu, apv, apw, k->su, k->sv, k->sw, u, v, w);
+}
+
+// the small kernels of the PISO driver: pin the reference row, flux correction from the matrix, velocity
+// correction, PIMPLE pressure relaxation
+void fcp_host_tail(const fcm_geom *g, const int *ioffset, const int *diag, const int *icj, double *a, double *su,
+                   const double *src, int pref, const double *pp, double *flmass, const double *apu, const double *apv,
+                   const double *apw, const double *dP, double *u, double *v, double *w, double urf, double *p) {
+  fcp_pin_row(ioffset, diag, a, su, src, pref);
+  for (int i = 0; i < g->F; ++i) fcp_flux_correct(*g, icj, a, pp, flmass, i);
+  for (int c = 0; c < g->n; ++c) fcp_velocity_correct(*g, apu, apv, apw, dP, u, v, w, c);
+  for (int c = 0; c < g->n; ++c) fcp_relax_p(urf, pp, p, c);
+}
+
 int fcm_host_sizes(int which) {
   switch (which) {
     case 0: return (int)sizeof(fcm_geom);
@@ -32,6 +50,7 @@ int fcm_host_sizes(int which) {
     case 5: return (int)sizeof(fcm_faces);
     case 6: return (int)sizeof(fcm_rows);
     case 7: return (int)sizeof(fcm_comp);
+    case 8: return (int)sizeof(fcp_hbya);
   }
   return -1;
 }

@@ -61,15 +61,23 @@ class Comp(C.Structure):
         (k, C.c_double) for k in ("urfrs", "urfms", "small", "timestep")] + [("cn", C.c_int), ("zero_diag", C.c_int)]
 
 
+class Hbya(C.Structure):
+    _fields_ = [("ioffset", ip), ("diag", ip)] + [(k, dp) for k in (
+        "h", "u", "v", "w", "uo", "vo", "wo", "uoo", "voo", "woo", "t", "den", "su", "sv", "sw")] + [
+        ("bdf", C.c_int), ("btime", C.c_double), ("timestep", C.c_double), ("cn", C.c_int), ("lbuoy", C.c_int),
+        ("boussinesq", C.c_int)] + [(k, C.c_double) for k in ("beta", "tref", "densit", "gravx", "gravy", "gravz")]
+
+
 @pytest.fixture(scope="module")
 def host():
     so = os.path.join(HERE, "libfcm_host.so")
     src = os.path.join(HERE, "fcm_host.cpp")
-    hdr = os.path.join(HERE, "..", "..", "freecappuccino_b200", "csrc", "fc_momentum_body.cuh")
-    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+    hdrs = [os.path.join(HERE, "..", "..", "freecappuccino_b200", "csrc", h) for h in ("fc_momentum_body.cuh",
+                                                                                         "fc_piso_body.cuh")]
+    if not os.path.exists(so) or max(os.path.getmtime(f) for f in [src] + hdrs) > os.path.getmtime(so):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", so, src])
     lib = C.CDLL(so)
-    for k, st in enumerate((Geom, C2f, Slots, Flow, Opts, Faces, Rows, Comp)):
+    for k, st in enumerate((Geom, C2f, Slots, Flow, Opts, Faces, Rows, Comp, Hbya)):
         assert lib.fcm_host_sizes(k) == C.sizeof(st), (k, st)
     return lib
 
@@ -233,3 +241,77 @@ def test_bodies_equal_oracle_steady(host, name, scheme):
 def test_bodies_equal_oracle_sources(host, kw):
     mesh = MESHES["skew"]()
     assert run_case(host, mesh, cases.flow_fields(mesh), "muscl-f", **kw)
+
+
+# ---- PISO / PIMPLE bodies (fc_piso_body.cuh) ----
+@pytest.mark.parametrize("name", list(MESHES))
+@pytest.mark.parametrize("kw", [dict(bdf=True, btime=0.0, timestep=0.01), dict(bdf=True, btime=1.0, timestep=0.01, cn=True),
+                                dict(bdf=False, lbuoy=True, boussinesq=False, densit=1.1, grav=(0.1, -9.81, 0.2)),
+                                dict(bdf=True, btime=1.0, timestep=0.01, lbuoy=True, beta=0.3, tref=0.1, densit=1.1,
+                                     grav=(0.1, -9.81, 0.2))])
+def test_hbya_body_equals_oracle(host, name, kw):
+    mesh = MESHES[name]()
+    rng = np.random.default_rng(11)
+    csr = oracle.create_csr(mesh)
+    n, F, nt = mesh.numCells, mesh.numInnerFaces, mesh.numTotal
+    f = cases.flow_fields(mesh)
+    of = oracle.Fields(mesh, csr.nnz)
+    for k in ("u", "v", "w", "p", "den"):
+        getattr(of, k)[:] = f[k]
+    of.apu[:], of.apv[:], of.apw[:] = f["apu"], f["apv"], f["apw"]
+    x = oracle.UvwFields(mesh, of, 0.01)
+    for k in ("uo", "vo", "wo", "uoo", "voo", "woo", "t"):
+        getattr(x, k)[:] = rng.standard_normal(nt)
+    h = rng.standard_normal(csr.nnz)
+    L = device_layout(mesh, csr)
+    geo = {k: np.ascontiguousarray(getattr(mesh, k), dtype=np.float64) for k in
+           ("xc", "yc", "zc", "vol", "arx", "ary", "arz", "xf", "yf", "zf", "facint")}
+    G = Geom(i32(L["owner"]), i32(L["neigh"]), *[d(geo[k]) for k in ("xc", "yc", "zc", "vol", "arx", "ary", "arz",
+                                                                    "xf", "yf", "zf", "facint")], n, F)
+    Mp = C2f(i32(L["off"]), i32(L["face"]), i32(L["other"]), i32(L["pos"]))
+    u, v, w = of.u.copy(), of.v.copy(), of.w.copy()
+    su, sv, sw = np.zeros(n), np.zeros(n), np.zeros(n)
+    po = oracle.piso_opts(**kw)
+    den = np.ascontiguousarray(of.den)
+    K = Hbya(i32(L["ioffset"]), i32(L["diag"]), d(h), d(u), d(v), d(w), d(x.uo), d(x.vo), d(x.wo), d(x.uoo), d(x.voo),
+             d(x.woo), d(x.t), d(den), d(su), d(sv), d(sw), po.bdf, po.btime, po.timestep, po.cn, po.lbuoy,
+             po.boussinesq, po.beta, po.tref, po.densit, po.gravx, po.gravy, po.gravz)
+    apu, apv, apw = (np.ascontiguousarray(a[:n]) for a in (of.apu, of.apv, of.apw))
+    host.fcp_host_hbya(C.byref(G), C.byref(Mp), C.byref(K), d(apu), d(apv), d(apw), d(u), d(v), d(w))
+    oracle.get_rAU_x_UEqnH(mesh, csr, of, x, po, h)
+    for got, ref in ((su, of.su), (sv, x.sv), (sw, x.sw), (u, of.u), (v, of.v), (w, of.w)):
+        assert np.array_equal(got, ref)
+
+
+def test_piso_tail_bodies(host):
+    """pin row / flux correction from the matrix / velocity correction / pressure relaxation against the same
+    expressions evaluated with numpy (element-wise IEEE operations in the reference's order)."""
+    mesh = MESHES["skew"]()
+    rng = np.random.default_rng(2)
+    csr = oracle.create_csr(mesh)
+    n, F, nt = mesh.numCells, mesh.numInnerFaces, mesh.numTotal
+    L = device_layout(mesh, csr)
+    geo = {k: np.ascontiguousarray(getattr(mesh, k), dtype=np.float64) for k in
+           ("xc", "yc", "zc", "vol", "arx", "ary", "arz", "xf", "yf", "zf", "facint")}
+    G = Geom(i32(L["owner"]), i32(L["neigh"]), *[d(geo[k]) for k in ("xc", "yc", "zc", "vol", "arx", "ary", "arz",
+                                                                    "xf", "yf", "zf", "facint")], n, F)
+    a, su, pp, p = rng.standard_normal(csr.nnz), rng.standard_normal(n), rng.standard_normal(nt), rng.standard_normal(nt)
+    fl, dP = rng.standard_normal(F), rng.standard_normal((n, 3))
+    u, v, w = rng.standard_normal(nt), rng.standard_normal(nt), rng.standard_normal(nt)
+    apu, apv, apw = rng.random(n), rng.random(n), rng.random(n)
+    icj = (csr.icell_jcell - 1).astype(np.int32)
+    pref, urf = 17, 0.3
+    a0, su0, fl0, u0, v0, w0, p0 = a.copy(), su.copy(), fl.copy(), u.copy(), v.copy(), w.copy(), p.copy()
+    host.fcp_host_tail(C.byref(G), i32(L["ioffset"]), i32(L["diag"]), i32(icj), d(a), d(su), d(p0.copy()), pref, d(pp),
+                       d(fl), d(apu), d(apv), d(apw), d(dP), d(u), d(v), d(w), C.c_double(urf), d(p))
+    a0[L["ioffset"][pref]:L["ioffset"][pref + 1]] = 0.0
+    a0[L["diag"][pref]] = 1.0
+    su0[pref] = p0[pref]
+    assert np.array_equal(a, a0) and np.array_equal(su, su0)
+    o, nb = L["owner"][:F], L["neigh"]
+    assert np.array_equal(fl, fl0 + a0[icj] * (pp[nb] - pp[o]))
+    vol = mesh.vol[:n]
+    assert np.array_equal(u[:n], u0[:n] - apu * dP[:, 0] * vol) and np.array_equal(u[n:], u0[n:])
+    assert np.array_equal(v[:n], v0[:n] - apv * dP[:, 1] * vol)
+    assert np.array_equal(w[:n], w0[:n] - apw * dP[:, 2] * vol)
+    assert np.array_equal(p[:n], p0[:n] + urf * (pp[:n] - p0[:n])) and np.array_equal(p[n:], p0[n:])
