@@ -659,9 +659,9 @@ void fco_calcp_assemble(const fco_mesh *g, const fco_csr *m, fco_fields *f, cons
   for (int k = 0; k < m->nnz; ++k) f->a[k] = 0.0;  /* :34-35 */
   for (int i = 0; i < n; ++i) f->su[i] = 0.0;
   /* grad(U), grad(V), grad(W) :38-40; grad_scalar_field zeroes, then grad_gauss (gradients.f90:104,128) */
-  fco_grad_gauss(g, f->u, o->nigrad, f->dUdxi);
-  fco_grad_gauss(g, f->v, o->nigrad, f->dVdxi);
-  fco_grad_gauss(g, f->w, o->nigrad, f->dWdxi);
+  fco_grad(g, m, f->u, o->nigrad, f->dUdxi);
+  fco_grad(g, m, f->v, o->nigrad, f->dVdxi);
+  fco_grad(g, m, f->w, o->nigrad, f->dWdxi);
   for (int i = 1; i <= g->numInnerFaces; ++i) { /* :45-77 */
     int ijp = A1(g->owner, i), ijn = A1(g->neighbour, i);
     double cap, can;
@@ -699,11 +699,12 @@ int fco_calcp(const fco_mesh *g, const fco_csr *m, fco_fields *f, const fco_calc
     else fco_bicgstab(m, f->a, f->su, f->pp, f->res, &st, &o->sol, r, 0);
     for (int istage = 1; istage <= o->nipgrad; ++istage) { /* :132-140 */
       fco_bpres(g, f->pp, f->dPdxi, istage);
-      fco_grad_gauss(g, f->pp, o->nigrad, f->dPdxi);
+      fco_grad(g, m, f->pp, o->nigrad, f->dPdxi);
     }
     if (o->lsq_flag) { /* :143 -- the option wrapper zeroes dPdxi first (gradients.f90:222) */
       memset(f->dPdxi, 0, sizeof(double) * 3 * (size_t)n);
       fco_grad_gauss_corrected(g, f->pp, f->dPdxi);
+      fco_limit_configured(g, m, f->pp, f->dPdxi); /* grad_scalar_field_w_option ends with the limiter (:240-255) */
     }
     double ppref = A1(f->pp, o->pRefCell); /* :146 */
     for (int iface = 1; iface <= g->numInnerFaces; ++iface) { /* :154-164 */
@@ -750,4 +751,5 @@ int fco_calcp(const fco_mesh *g, const fco_csr *m, fco_fields *f, const fco_calc
 }
 
 #include "fc_oracle_uvw.c"
+#include "fc_oracle_grad.c"
 #include "fc_oracle_piso.c"

@@ -185,6 +185,24 @@ void fco_get_rAU_x_UEqnH(const fco_mesh *g, const fco_csr *m, fco_fields *f, fco
 int fco_piso(const fco_mesh *g, const fco_csr *m, fco_fields *f, fco_uvw *x, const fco_piso_opts *o, double *h,
              fco_piso_report *rep);
 
+/* ---- least-squares gradients + slope limiters behind `grad` (fc_oracle_grad.c) ---- */
+typedef struct {
+  int method;      /* 0 gauss, 1 lstsq, 2 lstsq_qr, 3 lstsq_dm  (gradients.f90:107-128)                       */
+  int limiter;     /* 0 no-limit, 1 Barth-Jespersen, 2 Venkatakrishnan, 3 mVenkatakrishnan (:133-148)         */
+  const double *dmat;   /* (9,numCells) from fco_lsq_matrix, methods 1 and 3                                  */
+  const double *dmatqr; /* (3,6,numCells) from fco_lsq_qr_matrix, method 2                                    */
+  double small;
+} fco_gradient_cfg;
+void fco_lsq_matrix(const fco_mesh *g, int weighted, double *dmat);
+void fco_grad_lsq(const fco_mesh *g, int weighted, const double *dmat, const double *fi, double *dFidxi);
+int  fco_lsq_qr_matrix(const fco_mesh *g, double *D);
+void fco_grad_lsq_qr(const fco_mesh *g, const double *D, const double *fi, double *dFidxi);
+void fco_slope_limiter(const fco_mesh *g, const fco_csr *m, int which, const double *phi, double *dPhidxi, double small);
+/* process-wide gradient configuration used by fco_grad and, through it, by calcp / calcuvw / piso (NULL = gauss) */
+void fco_set_gradient(const fco_gradient_cfg *c);
+void fco_grad(const fco_mesh *g, const fco_csr *m, const double *phi, int nigrad, double *dPhidxi);
+void fco_limit_configured(const fco_mesh *g, const fco_csr *m, const double *phi, double *dPhidxi);
+
 /* ---- src-parallel semantics: R ranks in lock step inside one process (fc_oracle_par.c) ---- */
 typedef struct {
   fco_mesh g;

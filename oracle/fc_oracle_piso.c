@@ -122,7 +122,7 @@ int fco_piso(const fco_mesh *g, const fco_csr *m, fco_fields *f, fco_uvw *x, con
     }
     for (int istage = 1; istage <= o->nipgrad; ++istage) {
       fco_bpres(g, f->p, f->dPdxi, istage);
-      fco_grad_gauss(g, f->p, o->nigrad, f->dPdxi);
+      fco_grad(g, m, f->p, o->nigrad, f->dPdxi);
     }
     for (int inp = 1; inp <= n; ++inp) {
       A1(f->u, inp) = A1(f->u, inp) - A1(x->apu, inp) * G3(f->dPdxi, 0, inp) * A1(g->vol, inp);

@@ -188,13 +188,13 @@ int fco_calcuvw_assemble(const fco_mesh *g, const fco_csr *m, fco_fields *f, fco
   const int iOutletStart = iInletStart + g->ninl, iSymmetryStart = iOutletStart + g->nout;
   const int iWallStart = iSymmetryStart + g->nsym, iPressOutletStart = iWallStart + g->nwal;
   for (int i = 0; i < n; ++i) { f->su[i] = 0.0; x->sv[i] = 0.0; x->sw[i] = 0.0; x->spu[i] = 0.0; x->spv[i] = 0.0; x->sp[i] = 0.0; }
-  fco_grad_gauss(g, f->u, o->nigrad, f->dUdxi); /* :59-61 */
-  fco_grad_gauss(g, f->v, o->nigrad, f->dVdxi);
-  fco_grad_gauss(g, f->w, o->nigrad, f->dWdxi);
+  fco_grad(g, m, f->u, o->nigrad, f->dUdxi); /* :59-61 */
+  fco_grad(g, m, f->v, o->nigrad, f->dVdxi);
+  fco_grad(g, m, f->w, o->nigrad, f->dWdxi);
   /* calcPressDiv (fieldManipulation.f90:57-165) */
   for (int istage = 1; istage <= o->nipgrad; ++istage) {
     fco_bpres(g, f->p, f->dPdxi, istage);
-    fco_grad_gauss(g, f->p, o->nigrad, f->dPdxi);
+    fco_grad(g, m, f->p, o->nigrad, f->dPdxi);
   }
   for (int i = 1; i <= g->numInnerFaces; ++i) {
     int ijp = A1(g->owner, i), ijn = A1(g->neighbour, i);

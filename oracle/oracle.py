@@ -23,7 +23,8 @@ TOL = float(np.float32(1e-13))        # dpcg.f90:37
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libfc_oracle.so")
-    src = [os.path.join(_HERE, f) for f in ("fc_oracle.c", "fc_oracle_uvw.c", "fc_oracle_piso.c", "fc_oracle_par.c", "fc_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("fc_oracle.c", "fc_oracle_uvw.c", "fc_oracle_piso.c", "fc_oracle_grad.c", "fc_oracle_par.c",
+                                           "fc_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libfc_oracle.so"])
     return so
@@ -87,7 +88,7 @@ def lib() -> C.CDLL:
         _LIB = C.CDLL(build())
         _LIB.fco_create_csr.restype = C.c_int
         for f in ("fco_dpcg", "fco_iccg", "fco_bicgstab", "fco_calcp", "fco_calcuvw", "fco_calcuvw_assemble",
-                  "fco_calcuvw_component", "fco_piso"):
+                  "fco_calcuvw_component", "fco_piso", "fco_lsq_qr_matrix"):
             getattr(_LIB, f).restype = C.c_int
     return _LIB
 
@@ -368,3 +369,71 @@ def piso(mesh, csr: Csr, f: Fields, x: UvwFields, opts: FcoPisoOpts) -> FcoPisoR
     rc = lib().fco_piso(C.byref(ms), C.byref(cs), C.byref(fs), C.byref(xs), C.byref(opts), _d(h), C.byref(rep))
     assert rc == 0, rc
     return rep
+
+
+# ---- least-squares gradients + slope limiters (fc_oracle_grad.c) ----
+GRAD_METHODS = {"gauss": 0, "lstsq": 1, "lstsq_qr": 2, "lstsq_dm": 3}
+LIMITERS = {"no-limit": 0, "Barth-Jespersen": 1, "Venkatakrishnan": 2, "mVenkatakrishnan": 3}
+
+
+class FcoGradientCfg(C.Structure):
+    _fields_ = [("method", C.c_int), ("limiter", C.c_int), ("dmat", dp), ("dmatqr", dp), ("small", C.c_double)]
+
+
+def lsq_matrix(mesh, weighted: bool) -> np.ndarray:
+    ms = mesh_struct(mesh)
+    dmat = np.zeros((mesh.numCells, 9))
+    lib().fco_lsq_matrix(C.byref(ms), int(weighted), _d(dmat))
+    return dmat
+
+
+def lsq_qr_matrix(mesh):
+    """Returns (D (numCells,6,3) = R^-1 Q^T stored like Fortran's D(3,6,numCells), cells the routine is undefined for)."""
+    ms = mesh_struct(mesh)
+    D = np.zeros((mesh.numCells, 6, 3))
+    bad = lib().fco_lsq_qr_matrix(C.byref(ms), _d(D))
+    return D, bad
+
+
+def grad_lsq(mesh, weighted: bool, dmat: np.ndarray, fi: np.ndarray) -> np.ndarray:
+    ms = mesh_struct(mesh)
+    out = np.zeros((mesh.numCells + mesh.npro, 3))
+    lib().fco_grad_lsq(C.byref(ms), int(weighted), _d(dmat), _d(fi), _d(out))
+    return out
+
+
+def grad_lsq_qr(mesh, D: np.ndarray, fi: np.ndarray) -> np.ndarray:
+    ms = mesh_struct(mesh)
+    out = np.zeros((mesh.numCells + mesh.npro, 3))
+    lib().fco_grad_lsq_qr(C.byref(ms), _d(D), _d(fi), _d(out))
+    return out
+
+
+def slope_limiter(mesh, csr: Csr, which: str, phi: np.ndarray, grad: np.ndarray, small: float = SMALL) -> None:
+    ms, cs = mesh_struct(mesh), csr.c()
+    lib().fco_slope_limiter(C.byref(ms), C.byref(cs), LIMITERS[which], _d(phi), _d(grad), C.c_double(small))
+
+
+_GRAD_KEEP = []
+
+
+def set_gradient(method: str = "gauss", limiter: str = "no-limit", mesh=None, small: float = SMALL):
+    """Configure the oracle's `grad` dispatcher (process-wide, like the reference's lstsq / lstsq_qr / lstsq_dm /
+    gauss flags and `limiter` string); builds the geometric matrices the method needs (create_lsq_gradients_matrix)."""
+    _GRAD_KEEP.clear()
+    dmat = dmatqr = None
+    if method in ("lstsq", "lstsq_dm"):
+        dmat = lsq_matrix(mesh, method == "lstsq_dm")
+    elif method == "lstsq_qr":
+        dmatqr, bad = lsq_qr_matrix(mesh)
+        assert bad == 0, f"lstsq_qr is defined for cells with exactly 6 neighbours ({bad} cells have another count)"
+    _GRAD_KEEP.extend([dmat, dmatqr])
+    cfg = FcoGradientCfg(GRAD_METHODS[method], LIMITERS[limiter], _d(dmat), _d(dmatqr), small)
+    lib().fco_set_gradient(C.byref(cfg))
+
+
+def grad(mesh, csr: Csr, phi: np.ndarray, nigrad: int = 1) -> np.ndarray:
+    ms, cs = mesh_struct(mesh), csr.c()
+    out = np.zeros((mesh.numCells + mesh.npro, 3))
+    lib().fco_grad(C.byref(ms), C.byref(cs), _d(phi), nigrad, _d(out))
+    return out
