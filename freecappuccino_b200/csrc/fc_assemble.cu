@@ -590,9 +590,9 @@ int fc_calcp_assemble_dev(fc_context *ctx, const fc_calcp_opts *o) {
   FC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
   if (ctx->csr_dup) FC_CUDA(cudaMemsetAsync(ctx->field[FC_A], 0, sizeof(double) * (size_t)ctx->nnz, ctx->stream));
   // grad(U), grad(V), grad(W)   (calcp :38-40)
-  FC_CHECK(fc_grad_gauss_dev(ctx, ctx->field[FC_U], ctx->field[FC_DUDXI], o->nigrad));
-  FC_CHECK(fc_grad_gauss_dev(ctx, ctx->field[FC_V], ctx->field[FC_DVDXI], o->nigrad));
-  FC_CHECK(fc_grad_gauss_dev(ctx, ctx->field[FC_W], ctx->field[FC_DWDXI], o->nigrad));
+  FC_CHECK(fc_grad_dev(ctx, ctx->field[FC_U], ctx->field[FC_DUDXI], o->nigrad));
+  FC_CHECK(fc_grad_dev(ctx, ctx->field[FC_V], ctx->field[FC_DVDXI], o->nigrad));
+  FC_CHECK(fc_grad_dev(ctx, ctx->field[FC_W], ctx->field[FC_DWDXI], o->nigrad));
   if (ctx->F > 0) {
     const int G = fc_blocks(ctx->F, B);
     if (o->flux_variant == 0)
@@ -638,9 +638,12 @@ int fc_calcp_dev(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep) 
     FC_CUDA(cudaEventRecord(c0, st));
     for (int istage = 1; istage <= o->nipgrad; ++istage) {                                    // :132-140
       FC_CHECK(fc_bpres_dev(ctx, pp, dP, istage));
-      FC_CHECK(fc_grad_gauss_dev(ctx, pp, dP, o->nigrad));
+      FC_CHECK(fc_grad_dev(ctx, pp, dP, o->nigrad));
     }
-    if (o->lsq_flag) FC_CHECK(fc_grad_gauss_corrected_dev(ctx, pp, dP, 1));                   // :143
+    if (o->lsq_flag) {                                                                        // :143
+      FC_CHECK(fc_grad_gauss_corrected_dev(ctx, pp, dP, 1));
+      FC_CHECK(fc_limit_gradient_dev(ctx, pp, dP));   // grad_scalar_field_w_option ends with the limiter (gradients.f90:240-255)
+    }
     double *ppref = &ctx->sc->aux[3];
     if (ctx->nranks == 1) {
       k_pick<<<1, 1, 0, st>>>(pp, o->pRefCell - 1, ppref);                                    // :146
@@ -832,7 +835,7 @@ int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep) {
     }
     for (int istage = 1; istage <= o->nipgrad; ++istage) {
       FC_CHECK(fc_bpres_dev(ctx, fl[FC_P], fl[FC_DPDXI], istage));
-      FC_CHECK(fc_grad_gauss_dev(ctx, fl[FC_P], fl[FC_DPDXI], o->nigrad));
+      FC_CHECK(fc_grad_dev(ctx, fl[FC_P], fl[FC_DPDXI], o->nigrad));
     }
     k_piso_velocity_correct<<<fc_blocks(n, B), B, 0, st>>>(g, fl[FC_APU], fl[FC_APV], fl[FC_APW], fl[FC_DPDXI],
                                                            fl[FC_U], fl[FC_V], fl[FC_W]);

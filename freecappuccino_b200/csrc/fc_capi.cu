@@ -104,7 +104,8 @@ void free_all(fc_context *ctx) {
                   (void *)ctx->vk, (void *)ctx->adiag, (void *)ctx->tt, (void *)ctx->coef, (void *)ctx->facev,
                   (void *)ctx->gtmp, (void *)ctx->partials, (void *)ctx->sc, (void *)ctx->bufind,
                   (void *)ctx->sendbuf, (void *)ctx->strip_off, (void *)ctx->strip_idx,
-                  (void *)ctx->strip_any32, (void *)ctx->persist, (void *)ctx->uvw_face, (void *)ctx->hcoef})
+                  (void *)ctx->strip_any32, (void *)ctx->persist, (void *)ctx->uvw_face, (void *)ctx->hcoef, (void *)ctx->dmat,
+                  (void *)ctx->dmatqr})
     if (p) cudaFree(p);
   for (int f = 0; f < FC_NUM_FIELDS; ++f)
     if (ctx->field[f]) cudaFree(ctx->field[f]);
@@ -215,6 +216,7 @@ int fc_set_mesh(fc_context *ctx, const fc_mesh_desc *m) {
   if (m->npro > 0 && (!m->fpro || !m->neighbProcNo || !m->neighbProcOffset || m->numConnections < 1))
     FC_FAIL(FC_ERR_ARG, "fc_set_mesh: processor boundary without fpro / neighbProcNo / neighbProcOffset");
   if (ctx->hcoef) { cudaFree(ctx->hcoef); ctx->hcoef = nullptr; }
+  ctx->grad_method = ctx->grad_limiter = 0;   // the least-squares matrices belong to the old mesh
   if (ctx->uvw_face) {  // momentum fields are sized by the mesh: drop them, they come back on first use
     cudaFree(ctx->uvw_face);
     ctx->uvw_face = nullptr;
@@ -515,6 +517,21 @@ int fc_calcuvw_host(fc_context *ctx, const fc_calcuvw_opts *o, double *u, double
     if (t.h) FC_CUDA(cudaMemcpyAsync(t.h, ctx->field[t.f], sizeof(double) * t.n, cudaMemcpyDeviceToHost, st));
   FC_CUDA(cudaStreamSynchronize(st));
   return FC_OK;
+}
+
+int fc_set_gradient(fc_context *ctx, int method, int limiter, double small) {
+  if (!ctx) return FC_ERR_ARG;
+  FC_CUDA(cudaSetDevice(ctx->device));
+  return fc_set_gradient_dev(ctx, method, limiter, small);
+}
+
+int fc_grad(fc_context *ctx, int phi_field, int grad_field, int nigrad) {
+  if (!ctx) return FC_ERR_ARG;
+  FC_CUDA(cudaSetDevice(ctx->device));
+  FC_CHECK(check_field(ctx, phi_field, (size_t)ctx->NT, "fc_grad"));
+  FC_CHECK(check_field(ctx, grad_field, 3 * (size_t)ctx->NP, "fc_grad"));
+  if (nigrad < 1) FC_FAIL(FC_ERR_ARG, "fc_grad: nigrad < 1");
+  return fc_grad_dev(ctx, ctx->field[phi_field], ctx->field[grad_field], nigrad);
 }
 
 int fc_piso(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep) {

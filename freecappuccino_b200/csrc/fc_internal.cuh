@@ -125,6 +125,11 @@ struct fc_context {
   double *coef = nullptr;               // per-face coefficient cap = can [F + npro]
   double *facev = nullptr;              // per-face scratch [NF]
   double *gtmp = nullptr;               // previous-pass gradient (3,numCells)
+  // gradient scheme of the `grad` dispatcher (fc_set_gradient): 0 gauss, 1 lstsq, 2 lstsq_qr, 3 lstsq_dm; limiter 0..3
+  int grad_method = 0, grad_limiter = 0;
+  double grad_small = 0.0;
+  double *dmat = nullptr;               // (9,numCells) of grad_lsq / grad_lsq_dm
+  double *dmatqr = nullptr;             // (3,6,numCells) R^-1 Q^T of grad_lsq_qr
   double *hcoef = nullptr;              // PISO: h = a, the momentum matrix backed up before the correctors [nnz]
   double *uvw_face = nullptr;           // momentum predictor: can, cap, sup, svp, swp, fie per inner face [6 F]
   double *partials = nullptr;           // [FC_MAX_RED * FC_RED_GRID]
@@ -246,3 +251,6 @@ int fc_calcuvw_assemble_dev(fc_context *ctx, const fc_calcuvw_opts *o);         
 int fc_calcuvw_component_dev(fc_context *ctx, const fc_calcuvw_opts *o, int comp, fc_solver_report *rep);
 int fc_calcuvw_dev(fc_context *ctx, const fc_calcuvw_opts *o, fc_calcuvw_report *rep);
 int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep);             // fc_assemble.cu
+int fc_grad_dev(fc_context *ctx, double *phi, double *grad, int nigrad);                   // fc_gradients.cu
+int fc_limit_gradient_dev(fc_context *ctx, const double *phi, double *grad);
+int fc_set_gradient_dev(fc_context *ctx, int method, int limiter, double small);

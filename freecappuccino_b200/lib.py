@@ -41,8 +41,10 @@ SYMBOLS = (
     "fc_solve_csr", "fc_calcp_assemble", "fc_calcp", "fc_calcp_host", "fc_exchange", "fc_global_sum",
     "fc_get_timings", "fc_time_spmv", "fc_stream", "fc_copy", "fc_set_spmv_sampling", "fc_comm_p2p_blob",
     "fc_comm_p2p_open", "fc_set_tuning", "fc_calcuvw_assemble", "fc_calcuvw_component", "fc_calcuvw",
-    "fc_calcuvw_host", "fc_piso",
+    "fc_calcuvw_host", "fc_piso", "fc_set_gradient", "fc_grad",
 )
+GRAD_METHODS = {"gauss": 0, "lstsq": 1, "lstsq_qr": 2, "lstsq_dm": 3}
+LIMITERS = {"no-limit": 0, "Barth-Jespersen": 1, "Venkatakrishnan": 2, "mVenkatakrishnan": 3}
 TUNE_SPMV_KERNEL, TUNE_DPCG_PERSISTENT, TUNE_CTAS_PER_SM, TUNE_PIPE_GEOMETRY = 0, 1, 2, 3
 
 
@@ -401,6 +403,13 @@ class Context:
         self._ck(self.lib.fc_calcuvw_host(self.h, C.byref(opts), _d(u), _d(v), _d(w), _d(p), _d(vis), _d(flmass),
                                           _d(apu), _d(apv), _d(apw), C.byref(rep)))
         return rep
+
+    def set_gradient(self, method: str = "gauss", limiter: str = "no-limit", small: float = SMALL):
+        """The `grad` dispatcher's scheme (lstsq / lstsq_qr / lstsq_dm / gauss + limiter of the input file)."""
+        self._ck(self.lib.fc_set_gradient(self.h, GRAD_METHODS[method], LIMITERS[limiter], C.c_double(small)))
+
+    def grad(self, phi: str, grad: str, nigrad: int = 1):
+        self._ck(self.lib.fc_grad(self.h, F[phi], F[grad], nigrad))
 
     def piso(self, opts: PisoOpts) -> PisoReport:
         rep = PisoReport()

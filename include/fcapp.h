@@ -137,6 +137,18 @@ int fc_grad_gauss(fc_context *ctx, int phi_field, int grad_field, int nigrad);
  * `zero_seed` != 0 reproduces the option wrapper, which zeroes dPhidxi first
  * (gradients.f90:222).                                                      */
 int fc_grad_gauss_corrected(fc_context *ctx, int phi_field, int grad_field, int zero_seed);
+/* The gradient scheme of the `grad` dispatcher (gradients.f90:95-151: the lstsq /
+ * lstsq_qr / lstsq_dm / gauss flags and the `limiter` string of the input file).
+ * After this call fc_grad, fc_calcp, fc_calcuvw and fc_piso compute their gradients
+ * with it; the geometric matrices (create_lsq_gradients_matrix, :65-90) are built
+ * here.  Default: Gauss, no limiter.  SURVEY.md 8(f) rank 3; one rank.
+ * lstsq_qr follows grad_lsq_qr.f90 and is defined for cells with exactly six
+ * neighbours (FC_ERR_UNSUPPORTED otherwise).                                    */
+enum { FC_GRAD_GAUSS = 0, FC_GRAD_LSTSQ = 1, FC_GRAD_LSTSQ_QR = 2, FC_GRAD_LSTSQ_DM = 3 };
+enum { FC_LIMIT_NONE = 0, FC_LIMIT_BARTH_JESPERSEN = 1, FC_LIMIT_VENKATAKRISHNAN = 2, FC_LIMIT_MVENKATAKRISHNAN = 3 };
+int fc_set_gradient(fc_context *ctx, int method, int limiter, double small);
+/* grad(phi,dPhidxi) with the configured scheme + limiter.                      */
+int fc_grad(fc_context *ctx, int phi_field, int grad_field, int nigrad);
 /* bpres(p,istage) (bpres.f90:37-150), gradient taken from FC_DPDXI.         */
 int fc_bpres(fc_context *ctx, int p_field, int istage);
 

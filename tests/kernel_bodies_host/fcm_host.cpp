@@ -7,6 +7,7 @@
 // of fc_momentum.cu (tests/test_gpu_zz_momentum.py compares those with the oracle).  The library has
 // no host path: this file is built only by the test that uses it.
 #include "../../freecappuccino_b200/csrc/fc_piso_body.cuh"   // includes fc_momentum_body.cuh
+#include "../../freecappuccino_b200/csrc/fc_grad_body.cuh"
 
 extern "C" {
 
@@ -38,6 +39,23 @@ void fcp_host_tail(const fcm_geom *g, const int *ioffset, const int *diag, const
   for (int i = 0; i < g->F; ++i) fcp_flux_correct(*g, icj, a, pp, flmass, i);
   for (int c = 0; c < g->n; ++c) fcp_velocity_correct(*g, apu, apv, apw, dP, u, v, w, c);
   for (int c = 0; c < g->n; ++c) fcp_relax_p(urf, pp, p, c);
+}
+
+// least-squares gradients and limiters (fc_grad_body.cuh)
+void fcg_host_lsq(const fcm_geom *g, const fcm_c2f *m, const fcm_slots *sl, int weighted, double *dmat, const double *fi,
+                  double *out) {
+  for (int c = 0; c < g->n; ++c) fcg_lsq_matrix_row(*g, *m, weighted, dmat, c);
+  for (int c = 0; c < g->n; ++c) fcg_grad_lsq_row(*g, *m, *sl, weighted, dmat, fi, out, c);
+}
+int fcg_host_lsq_qr(const fcm_geom *g, const fcm_c2f *m, double *D, const double *fi, double *out) {
+  int bad = 0;
+  for (int c = 0; c < g->n; ++c) bad += fcg_lsq_qr_matrix_row(*g, *m, D, c);
+  for (int c = 0; c < g->n; ++c) fcg_grad_lsq_qr_row(*g, *m, D, fi, out, c);
+  return bad;
+}
+void fcg_host_limiter(const fcm_geom *g, const int *ioffset, const int *ja, const int *diag, int which,
+                      const double *phi, double *grad, double glomin, double glomax, double small) {
+  for (int c = 0; c < g->n; ++c) fcg_limiter_row(*g, ioffset, ja, diag, which, phi, grad, glomin, glomax, small, c);
 }
 
 int fcm_host_sizes(int which) {

@@ -1,0 +1,138 @@
+"""GPU parity of the least-squares gradients and slope limiters behind `grad` (fc_set_gradient / fc_grad;
+SURVEY 8(f) rank 3) through the C ABI.
+
+Written after this round's GPU budget was spent: the kernel bodies are checked bit for bit against the oracle on the
+CPU (tests/test_momentum_bodies.py); these tests are their first run on hardware and sort after the verified suites.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from freecappuccino_b200 import cases
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MESHES = {
+    "skew": lambda: cases.skew_case(),
+    "hex_mixed_bc": lambda: cases.hex_case(9, 7, 11, kinds=("inlet", "outlet", "wall", "symmetry", "wall", "prOutlet")),
+    "cavity": lambda: cases.golden_mesh(os.path.join(GOLD, "cavity.npz")),
+    "pitzDaily": lambda: cases.golden_mesh(os.path.join(GOLD, "pitzDaily.npz")),
+    "poly": lambda: cases.poly_case(5),
+}
+
+
+@pytest.fixture(scope="module")
+def fc():
+    from freecappuccino_b200 import lib
+    return lib
+
+
+@pytest.fixture(autouse=True)
+def reset_oracle_gradient():
+    yield
+    oracle.set_gradient("gauss", "no-limit")
+
+
+def make_ctx(fc, mesh):
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    return ctx
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+@pytest.mark.parametrize("method", ["lstsq", "lstsq_dm", "lstsq_qr", "gauss"])
+@pytest.mark.parametrize("limiter", ["no-limit", "Barth-Jespersen", "Venkatakrishnan", "mVenkatakrishnan"])
+def test_grad_dispatcher_bit_exact(fc, name, method, limiter):
+    mesh = MESHES[name]()
+    ctx = make_ctx(fc, mesh)
+    if method == "lstsq_qr" and name == "poly":
+        with pytest.raises(fc.FcError) as e:     # 14-faced cells: outside grad_lsq_qr.f90's D(3,6,numCells)
+            ctx.set_gradient(method, limiter)
+        assert e.value.code == fc.FC_ERR_UNSUPPORTED
+        ctx.close()
+        return
+    csr = oracle.create_csr(mesh)
+    oracle.set_gradient(method, limiter, mesh)
+    ctx.set_gradient(method, limiter)
+    f = cases.flow_fields(mesh)
+    n = mesh.numCells
+    for key in ("u", "p"):
+        ref = oracle.grad(mesh, csr, f[key], 1)
+        ctx.upload("SCRATCH_T", f[key])
+        ctx.grad("SCRATCH_T", "DPDXI", 1)
+        got = ctx.download("DPDXI").reshape(-1, 3)[:n]
+        assert np.array_equal(got, ref[:n]), (key, float(np.abs(got - ref[:n]).max()))
+    ctx.close()
+
+
+def upload_flow(ctx, mesh, f, fmi):
+    for k, name in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("apu", "APU"), ("apv", "APV"),
+                    ("apw", "APW")):
+        ctx.upload(name, f[k])
+    if fmi.size:
+        ctx.upload("FMI", fmi)
+
+
+@pytest.mark.parametrize("name,method,limiter,sor,ftol", [
+    ("pitzDaily", "lstsq_qr", "mVenkatakrishnan", 1e-9, 1e-5),   # examples/pitzDaily/input
+    ("skew", "lstsq_qr", "Venkatakrishnan", 1e-8, 1e-6),
+    ("poly", "lstsq_dm", "Barth-Jespersen", 1e-8, 1e-6),
+    ("hex_mixed_bc", "lstsq", "no-limit", 1e-8, 1e-6)])
+def test_calcp_with_configured_gradients(fc, name, method, limiter, sor, ftol):
+    """calcp with the gradient scheme of the `input` file: the assembled system is bit-exact, the solve and the
+    corrections follow within the usual bars (config 2 uses lstsq_qr + mVenkatakrishnan + iccg)."""
+    mesh = MESHES[name]()
+    ctx = make_ctx(fc, mesh)
+    csr = oracle.create_csr(mesh)
+    oracle.set_gradient(method, limiter, mesh)
+    ctx.set_gradient(method, limiter)
+    f = cases.channel_fields(mesh)
+    fmi, flomas = cases.inlet_fluxes(mesh, f)
+    of = oracle.Fields(mesh, csr.nnz)
+    for k in ("u", "v", "w", "p", "den", "apu", "apv", "apw"):
+        getattr(of, k)[:] = f[k]
+    of.fmi[:fmi.size] = fmi
+    of.dPdxi[:] = oracle.grad(mesh, csr, of.p, 1)
+    upload_flow(ctx, mesh, f, fmi)
+    ctx.upload("DPDXI", of.dPdxi)
+    lsq = method in ("lstsq_qr", "lstsq_dm")
+    variant = 1 if name == "poly" else 0
+    kw = dict(solver="iccg", flomas=flomas, sor=sor, nsw=3000, urf_p=0.3, pRefCell=1, lsq_flag=lsq, flux_variant=variant)
+    oa = of.copy()
+    oracle.calcp_assemble(mesh, csr, oa, oracle.calcp_opts(**kw))
+    ctx.calcp_assemble(fc.calcp_opts(**kw))
+    assert np.array_equal(ctx.download("A"), oa.a)
+    assert np.array_equal(ctx.download("SU"), oa.su)
+    assert np.array_equal(ctx.download("FLMASS"), oa.flmass)
+    upload_flow(ctx, mesh, f, fmi)
+    ctx.upload("DPDXI", of.dPdxi)
+    rr = oracle.calcp(mesh, csr, of, oracle.calcp_opts(**kw))
+    rg = ctx.calcp(fc.calcp_opts(**kw))
+    assert rr.rep[0].iters < 3000
+    assert abs(rg.rep[0].iters - rr.rep[0].iters) <= 1
+    if rg.rep[0].iters == rr.rep[0].iters:
+        for fld, ref in (("U", of.u), ("V", of.v), ("P", of.p), ("FLMASS", of.flmass), ("DPDXI", of.dPdxi.ravel())):
+            assert cases.rel_l2(ctx.download(fld)[:ref.size], ref) < ftol, fld
+    ctx.close()
+
+
+def test_calcuvw_with_configured_gradients(fc):
+    from test_gpu_zz_momentum import make_state, upload_state
+    mesh = MESHES["skew"]()
+    ctx = make_ctx(fc, mesh)
+    oracle.set_gradient("lstsq_qr", "mVenkatakrishnan", mesh)
+    ctx.set_gradient("lstsq_qr", "mVenkatakrishnan")
+    csr, of, x, _ = make_state(mesh, cases.flow_fields(mesh))
+    upload_state(ctx, mesh, of, x)
+    kw = dict(scheme="linear-f", urf=(0.7, 0.8, 0.6), bdf=True, btime=1.0, timestep=0.02)
+    oracle.calcuvw_assemble(mesh, csr, of, x, oracle.uvw_opts(**kw))
+    ctx.calcuvw_assemble(fc.calcuvw_opts(**kw))
+    for fld, ref in (("DUDXI", of.dUdxi.ravel()), ("DPDXI", of.dPdxi.ravel()), ("SU", of.su), ("SV", x.sv), ("SW", x.sw),
+                     ("SPU", x.spu), ("A", of.a)):
+        got = ctx.download(fld)[:ref.size]
+        assert np.array_equal(got, ref), (fld, float(np.abs(got - ref).max()))
+    ctx.close()

@@ -73,7 +73,8 @@ def host():
     so = os.path.join(HERE, "libfcm_host.so")
     src = os.path.join(HERE, "fcm_host.cpp")
     hdrs = [os.path.join(HERE, "..", "..", "freecappuccino_b200", "csrc", h) for h in ("fc_momentum_body.cuh",
-                                                                                         "fc_piso_body.cuh")]
+                                                                                         "fc_piso_body.cuh",
+                                                                                         "fc_grad_body.cuh")]
     if not os.path.exists(so) or max(os.path.getmtime(f) for f in [src] + hdrs) > os.path.getmtime(so):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", so, src])
     lib = C.CDLL(so)
@@ -315,3 +316,72 @@ def test_piso_tail_bodies(host):
     assert np.array_equal(v[:n], v0[:n] - apv * dP[:, 1] * vol)
     assert np.array_equal(w[:n], w0[:n] - apw * dP[:, 2] * vol)
     assert np.array_equal(p[:n], p0[:n] + urf * (pp[:n] - p0[:n])) and np.array_equal(p[n:], p0[n:])
+
+
+# ---- least-squares gradients and slope limiters (fc_grad_body.cuh) ----
+def geom_and_map(mesh, csr):
+    L = device_layout(mesh, csr)
+    geo = {k: np.ascontiguousarray(getattr(mesh, k), dtype=np.float64) for k in
+           ("xc", "yc", "zc", "vol", "arx", "ary", "arz", "xf", "yf", "zf", "facint")}
+    G = Geom(i32(L["owner"]), i32(L["neigh"]), *[d(geo[k]) for k in ("xc", "yc", "zc", "vol", "arx", "ary", "arz",
+                                                                    "xf", "yf", "zf", "facint")],
+             mesh.numCells, mesh.numInnerFaces)
+    Mp = C2f(i32(L["off"]), i32(L["face"]), i32(L["other"]), i32(L["pos"]))
+    return L, G, Mp, geo
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+@pytest.mark.parametrize("weighted", [False, True])
+def test_lsq_bodies_equal_oracle(host, name, weighted):
+    mesh = MESHES[name]()
+    csr = oracle.create_csr(mesh)
+    L, G, Mp, _keep = geom_and_map(mesh, csr)
+    n = mesh.numCells
+    fi = cases.flow_fields(mesh)["p"]
+    dmat, out = np.zeros((n, 9)), np.zeros((n, 3))
+    host.fcg_host_lsq(C.byref(G), C.byref(Mp), C.byref(L["slots"]), int(weighted), d(dmat), d(fi), d(out))
+    ref_m = oracle.lsq_matrix(mesh, weighted)
+    assert np.array_equal(dmat, ref_m)
+    assert np.array_equal(out, oracle.grad_lsq(mesh, weighted, ref_m, fi)[:n])
+
+
+@pytest.mark.parametrize("name", ["skew", "hex_mixed_bc"])
+def test_lsq_qr_bodies_equal_oracle(host, name):
+    mesh = MESHES[name]()
+    csr = oracle.create_csr(mesh)
+    L, G, Mp, _keep = geom_and_map(mesh, csr)
+    n = mesh.numCells
+    fi = cases.flow_fields(mesh)["u"]
+    D, out = np.zeros((n, 6, 3)), np.zeros((n, 3))
+    bad = host.fcg_host_lsq_qr(C.byref(G), C.byref(Mp), d(D), d(fi), d(out))
+    ref_D, ref_bad = oracle.lsq_qr_matrix(mesh)
+    assert bad == ref_bad == 0
+    assert np.array_equal(D, ref_D)
+    assert np.array_equal(out, oracle.grad_lsq_qr(mesh, ref_D, fi)[:n])
+
+
+def test_lsq_qr_body_flags_cells_without_six_neighbours(host):
+    mesh = MESHES["poly"]()
+    csr = oracle.create_csr(mesh)
+    L, G, Mp, _keep = geom_and_map(mesh, csr)
+    n = mesh.numCells
+    D, out = np.ones((n, 6, 3)), np.zeros((n, 3))
+    bad = host.fcg_host_lsq_qr(C.byref(G), C.byref(Mp), d(D), d(np.zeros(mesh.numTotal)), d(out))
+    assert bad == oracle.lsq_qr_matrix(mesh)[1] > 0
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+@pytest.mark.parametrize("which", ["Barth-Jespersen", "Venkatakrishnan", "mVenkatakrishnan"])
+def test_limiter_bodies_equal_oracle(host, name, which):
+    mesh = MESHES[name]()
+    csr = oracle.create_csr(mesh)
+    L, G, Mp, _keep = geom_and_map(mesh, csr)
+    n = mesh.numCells
+    phi = cases.flow_fields(mesh)["v"]
+    g0 = oracle.grad_gauss(mesh, phi, 1)
+    got = np.ascontiguousarray(g0[:n].copy())
+    host.fcg_host_limiter(C.byref(G), i32(L["ioffset"]), i32(L["ja"]), i32(L["diag"]), oracle.LIMITERS[which], d(phi),
+                          d(got), C.c_double(phi[:n].min()), C.c_double(phi[:n].max()), C.c_double(oracle.SMALL))
+    ref = g0.copy()
+    oracle.slope_limiter(mesh, csr, which, phi, ref)
+    assert np.array_equal(got, ref[:n])
