@@ -3,7 +3,9 @@
 // max(resor(iu), resor(iv), resor(iw), resor(ip)) < sormax or maxit, on an n x n x 1 box whose y+ wall moves
 // with U = (1,0,0) (examples/cavity/0/U); z faces are symmetry planes.  Prints the solver report lines in the
 // reference's format and, last, "iterations source umax".
-//   usage: cavity <n> [maxit] [sormax]
+//   usage: cavity <n | polyMesh dir> [maxit] [sormax]
+// With a directory the mesh is read by mesh_geometry (fcapp_mesh.cpp), e.g. the polyMesh of
+// examples/cavity/cavity-setup.tar.gz; with a number the n x n x 1 box is generated.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -14,11 +16,13 @@
 using namespace fcapp;
 
 int main(int argc, char **argv) {
-  const int n = argc > 1 ? std::atoi(argv[1]) : 20;
+  const bool from_files = argc > 1 && std::atoi(argv[1]) <= 0;
+  const int n = argc > 1 && !from_files ? std::atoi(argv[1]) : 20;
   const int maxit = argc > 2 ? std::atoi(argv[2]) : 1000;
   const double sormax = argc > 3 ? std::atof(argv[3]) : 1e-6;
   const char *kinds[6] = {"wall", "wall", "wall", "wall", "symmetry", "symmetry"};
-  mesh_geometry_box(n, n, 1, 0.1, 0.1, 0.01, kinds);   // the shipped mesh is 0.1 x 0.1 x 0.01, 20 x 20 x 1
+  if (from_files) mesh_geometry(argv[1]);
+  else mesh_geometry_box(n, n, 1, 0.1, 0.1, 0.01, kinds);   // the shipped mesh is 0.1 x 0.1 x 0.01, 20 x 20 x 1
   using namespace geometry;
   using namespace parameters;
   using namespace variables;

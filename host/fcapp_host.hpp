@@ -62,6 +62,9 @@ extern const char *chvarSolver[parameters::nphi + 1];
 // mesh_geometry for the synthetic boxes of the benchmark configs (poisson.f90 reads a polyMesh
 // instead; the array layout it leaves behind is the same)
 void mesh_geometry_box(int nx, int ny, int nz, dp lx, dp ly, dp lz, const char *kinds[6]);
+// mesh_geometry (src/mesh_geometry_and_topology.f90:310-1081, polyMesh branch): reads points / faces / owner /
+// neighbour / boundary of an OpenFOAM polyMesh directory and computes `module geometry` (fcapp_mesh.cpp)
+void mesh_geometry(const std::string &polymesh_dir);
 
 void fcapp_init(int device);  // after mesh_geometry: hand `module geometry` to the GPU
 void fcapp_finalize();

@@ -285,3 +285,29 @@ def test_cavity_driver_simple_loop_matches_oracle():
                 assert g[1] == pytest.approx(r.res0, rel=2e-3), (it, name)
     if agree:
         assert float(umax) == pytest.approx(float(np.abs(of.u[:mesh.numCells]).max()), rel=1e-3)
+
+
+def test_cavity_driver_on_the_shipped_polymesh(tmp_path):
+    """host/cavity fed with the polyMesh of examples/cavity (read by the C++ mesh_geometry of host/fcapp_mesh.cpp)
+    prints the same solver report lines as with its generated 20 x 20 x 1 box: same mesh, two routes."""
+    import re
+    import subprocess
+    from test_polymesh_reader import write_polymesh
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "host", "cavity")
+    d = np.load(os.path.join(GOLD, "cavity.npz"))
+    patches = [(str(k), int(nf), int(st)) for k, nf, st in zip(d["bkind"], d["bn"], d["bstart"])]
+    pm = os.path.join(str(tmp_path), "polyMesh")
+    write_polymesh(pm, d["points"], d["faces"], d["owner"], d["neighbour"], patches)
+    line = re.compile(r"Solving for (\w+), Initial residual = +(\d\.\d{3}E[+-]\d\d), Final residual = +"
+                      r"(\d\.\d{3}E[+-]\d\d), No Iterations (\d+)$", re.M)
+    outs = []
+    for arg in (pm, "20"):
+        out = subprocess.run([exe, arg, "6", "1e-30"], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        outs.append([(m.group(1), m.group(2), int(m.group(4))) for m in line.finditer(out.stdout)])
+    assert len(outs[0]) == 24
+    for a, b in zip(*outs):
+        assert a[0] == b[0] and abs(a[2] - b[2]) <= 1
+        if a[2] == b[2]:
+            assert float(a[1]) == pytest.approx(float(b[1]), rel=5e-3, abs=1e-12)
