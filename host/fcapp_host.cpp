@@ -261,7 +261,9 @@ void calcuvw() {
       {"central", 0, 7}, {"cds-corrected", 1, 7}, {"central-f", 2, 7}, {"linear-f", 3, 7}, {"muscl-f", 4, 7},
       {"smart", 5, 0}, {"avl-smart", 5, 1}, {"muscl", 5, 2}, {"umist", 5, 3}, {"koren", 5, 4}, {"charm", 5, 5},
       {"ospre", 5, 6}, {"linear", 5, 7}};
-  o.scheme = 5; o.limiter = 2;  // 'Convective scheme not chosen, assigning default muscl scheme'
+  // an unknown name only renames the scheme ('Convective scheme not chosen, assigning default muscl scheme',
+  // read_input.f90:123-126) without setting a flag, so face_value falls through to face_value_muscl
+  o.scheme = 4; o.limiter = 7;
   for (auto &e : table)
     if (convective_scheme == e.name) { o.scheme = e.scheme; o.limiter = e.limiter; }
   o.gds = gds[iu];
