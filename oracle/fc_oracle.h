@@ -226,6 +226,10 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
                   double *hist);
 void fco_par_calcp_assemble(fco_rank *R, int nr, const fco_calcp_opts *o);
 int fco_par_calcp(fco_rank *R, int nr, const fco_calcp_opts *o, fco_calcp_report *rep);
+/* src-parallel/calcuvw.f90 in lock step (fc_oracle_par_uvw.c); X = one fco_uvw per rank, apu.. of numCells+npro */
+void fco_par_calcuvw_assemble(fco_rank *R, int nr, fco_uvw *X, const fco_uvw_opts *o);
+int fco_par_calcuvw_component(fco_rank *R, int nr, fco_uvw *X, const fco_uvw_opts *o, int comp, fco_report *rep);
+int fco_par_calcuvw(fco_rank *R, int nr, fco_uvw *X, const fco_uvw_opts *o, fco_uvw_report *rep);
 
 #ifdef __cplusplus
 }

@@ -527,3 +527,5 @@ int fco_par_calcp(fco_rank *R, int nr, const fco_calcp_opts *o, fco_calcp_report
   free(pp); free(part); free(part2);
   return 0;
 }
+
+#include "fc_oracle_par_uvw.c"

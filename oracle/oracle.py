@@ -23,7 +23,7 @@ TOL = float(np.float32(1e-13))        # dpcg.f90:37
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libfc_oracle.so")
-    src = [os.path.join(_HERE, f) for f in ("fc_oracle.c", "fc_oracle_uvw.c", "fc_oracle_piso.c", "fc_oracle_grad.c", "fc_oracle_par.c",
+    src = [os.path.join(_HERE, f) for f in ("fc_oracle.c", "fc_oracle_uvw.c", "fc_oracle_piso.c", "fc_oracle_grad.c", "fc_oracle_par.c", "fc_oracle_par_uvw.c",
                                            "fc_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libfc_oracle.so"])

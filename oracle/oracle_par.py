@@ -92,3 +92,27 @@ class ParCase:
         rc = O.lib().fco_par_calcp(self.R, self.nr, C.byref(opts), C.byref(rep))
         assert rc == 0
         return rep
+
+    # ---- momentum predictor, src-parallel/calcuvw.f90 (fc_oracle_par_uvw.c) ----
+    def uvw_fields(self, viscos: float = 0.0):
+        """One UvwFields per rank (apu/apv/apw alias the rank's Fields arrays, numCells+npro)."""
+        self.uvw = [O.UvwFields(m, f, viscos) for m, f in zip(self.meshes, self.fields)]
+        self.X = (O.FcoUvw * self.nr)()
+        for r, x in enumerate(self.uvw):
+            self.X[r] = x.c()
+        return self.uvw
+
+    def calcuvw_assemble(self, opts: "O.FcoUvwOpts"):
+        O.lib().fco_par_calcuvw_assemble(self.R, self.nr, self.X, C.byref(opts))
+
+    def calcuvw_component(self, opts: "O.FcoUvwOpts", comp: int) -> "O.FcoReport":
+        rep = O.FcoReport()
+        rc = O.lib().fco_par_calcuvw_component(self.R, self.nr, self.X, C.byref(opts), comp, C.byref(rep))
+        assert rc == 0, rc
+        return rep
+
+    def calcuvw(self, opts: "O.FcoUvwOpts") -> "O.FcoUvwReport":
+        rep = O.FcoUvwReport()
+        rc = O.lib().fco_par_calcuvw(self.R, self.nr, self.X, C.byref(opts), C.byref(rep))
+        assert rc == 0, rc
+        return rep

@@ -170,3 +170,75 @@ def test_predictor_reduces_the_momentum_residual(scheme):
         assert 0 < rep.rep[k].iters < 100
         assert rep.rep[k].resl < 1e-6 * rep.rep[k].res0 * 1.0001
         assert np.isfinite(rep.rep[k].resl)
+
+
+# ---- src-parallel semantics (fc_oracle_par_uvw.c) ----
+def par_setup(mesh, f, nranks, flmass, x_ser):
+    from freecappuccino_b200 import mesh as M
+    from oracle import oracle_par as OP
+    parts = M.partition(mesh, M.slab_ranks(mesh.numCells, nranks), nranks)
+    pc = OP.ParCase(parts)
+    xs = pc.uvw_fields(0.0)
+    for r, part in enumerate(parts):
+        fr = pc.fields[r]
+        for k in ("u", "v", "w", "p", "den"):
+            getattr(fr, k)[:] = M.scatter_total(mesh, part, f[k])
+        gf = part.face_global
+        F = part.numInnerFaces
+        fr.flmass[:] = flmass[gf[:F]]
+        if part.npro:
+            pf = gf[part.iProcFacesStart:part.iProcFacesStart + part.npro]
+            dot = (part.arx[part.iProcFacesStart:] * mesh.arx[pf] + part.ary[part.iProcFacesStart:] * mesh.ary[pf]
+                   + part.arz[part.iProcFacesStart:] * mesh.arz[pf])
+            pc.fmpro[r][:part.npro] = flmass[pf] * np.sign(dot)
+        for kind, dst, src in (("inlet", fr.fmi, None), ("outlet", fr.fmo, None)):
+            c = part.count(kind)
+            if c:
+                g0 = gf[part.faces_start(kind):part.faces_start(kind) + c] - mesh.faces_start(kind)
+                dst[:c] = (x_ser["fmi"] if kind == "inlet" else x_ser["fmo"])[g0]
+        for k in ("vis", "uo", "vo", "wo", "uoo", "voo", "woo", "t"):
+            getattr(xs[r], k)[:] = M.scatter_total(mesh, part, x_ser[k])
+    return parts, pc, xs
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+def test_parallel_predictor_agrees_with_the_serial_one(nranks):
+    """src-parallel/calcuvw.f90 on 1-3 ranks (lock-step oracle) against the serial routine: the processor faces use
+    the same facefluxuvw, so the global system is the serial one up to rounding; with tight BiCGStab solves the
+    fields agree to the solver tolerance.  The pressure is uniform here: on a skewed mesh the reference's
+    df(ijp,k) addressing in presFaceDivInner reads other cells' gradient components by LOCAL flat index, so with a
+    non-trivial pressure the parallel and the serial build legitimately differ."""
+    from freecappuccino_b200 import mesh as M
+    mesh = cases.skew_case(6, 5, 9)
+    f = cases.channel_fields(mesh)
+    f["p"][:] = 2.5
+    rng = np.random.default_rng(4)
+    csr, of, x = setup(mesh, f)
+    nt = mesh.numTotal
+    of.flmass[:] = face_mass_fluxes(mesh, of)
+    of.fmi[:mesh.count("inlet")] = boundary_fluxes(mesh, of, "inlet")
+    of.fmo[:mesh.count("outlet")] = boundary_fluxes(mesh, of, "outlet")
+    x.vis[:] = 0.01 * (1.0 + 0.3 * rng.random(nt))
+    for k in ("uo", "vo", "wo", "uoo", "voo", "woo", "t"):
+        getattr(x, k)[:] = 0.1 * rng.standard_normal(nt)
+    xser = dict(vis=x.vis.copy(), uo=x.uo.copy(), vo=x.vo.copy(), wo=x.wo.copy(), uoo=x.uoo.copy(), voo=x.voo.copy(),
+                woo=x.woo.copy(), t=x.t.copy(), fmi=of.fmi.copy(), fmo=of.fmo.copy())
+    # no Crank-Nicolson here: src-parallel halves apr AFTER the processor faces' full `can` went into sp*
+    # (calcuvw.f90:240-244 vs :427), so its cn diagonal differs from the serial one by construction
+    kw = dict(scheme="muscl-f", urf=(0.7, 0.8, 0.6), sor=(1e-11,) * 3, nsw=(300,) * 3, bdf=True, btime=1.0, timestep=0.05)
+    parts, pc, xs = par_setup(mesh, f, nranks, of.flmass.copy(), xser)
+    rs = oracle.calcuvw(mesh, csr, of, x, oracle.uvw_opts(**kw))
+    rp = pc.calcuvw(oracle.uvw_opts(**kw))
+    n = mesh.numCells
+    for k in range(3):
+        assert rp.rep[k].iters < 300 and rs.rep[k].iters < 300
+        assert rp.rep[k].res0 == pytest.approx(rs.rep[k].res0, rel=1e-9)
+    for name, ser in (("u", of.u), ("v", of.v), ("w", of.w), ("apu", x.apu)):
+        got = M.gather_cells(mesh, parts, [getattr(fr, name) for fr in pc.fields])
+        assert np.allclose(got, ser[:n], rtol=1e-8, atol=1e-10), name
+    # halo of u and apu is current after the final exchanges
+    for r, part in enumerate(parts):
+        if part.npro:
+            assert np.array_equal(pc.fields[r].u[part.numCells:part.numCells + part.npro],
+                                  M.gather_cells(mesh, parts, [fr.u for fr in pc.fields])[part.halo_global])
+            assert np.array_equal(pc.fields[r].apu[part.numCells:], M.gather_cells(mesh, parts, [fr.apu for fr in pc.fields])[part.halo_global])
