@@ -125,7 +125,7 @@ int fc_momentum_fields(fc_context *ctx) {
   const size_t n = ctx->n, NT = ctx->NT, NP = (size_t)ctx->n + ctx->npro;
   for (int f : {FC_VIS, FC_UO, FC_VO, FC_WO, FC_UOO, FC_VOO, FC_WOO, FC_T}) FC_CHECK(alloc_field(ctx, f, NT > NP ? NT : NP));
   for (int f : {FC_SV, FC_SW, FC_SPU, FC_SPV, FC_SP}) FC_CHECK(alloc_field(ctx, f, n));
-  FC_CHECK(fc_dev_alloc(ctx, &ctx->uvw_face, 6 * (size_t)ctx->F));
+  FC_CHECK(fc_dev_alloc(ctx, &ctx->uvw_face, 6 * (size_t)ctx->F + 4 * (size_t)ctx->npro));
   return FC_OK;
 }
 

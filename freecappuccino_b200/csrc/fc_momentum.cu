@@ -3,6 +3,11 @@
 // u/v/w and leaves the boundary pressure and dPdxi that calcp reads, so a whole SIMPLE iteration
 // (calcuvw + calcp) runs without a host round trip of any field.
 //
+// Several ranks (src-parallel/calcuvw.f90): processor faces get their own face kernel (apr = can, the SpMV strip
+// of the BiCGStab solve), the diagonal is the running subtraction of the parallel build, and u, v, w, apu are
+// exchanged at the end; `vis` must arrive with a current halo (fc_exchange), the reference exchanges it where it
+// is updated.
+//
 // Launches per call: 3 x grad_gauss (U, V, W) + nipgrad x (bpres + grad_gauss) of the pressure,
 // one face kernel (F threads), one row kernel (n threads), then per velocity component one
 // diagonal / under-relaxation kernel (n threads) and the BiCGStab(DILU) solve of fc_krylov.cu.
@@ -32,9 +37,15 @@ k_uvw_faces(fcm_geom g, fcm_flow f, fcm_opts o, fcm_faces out) {
 }
 
 __global__ void __launch_bounds__(256)
-k_uvw_rows(fcm_geom g, fcm_c2f m, fcm_slots sl, fcm_flow f, fcm_opts o, fcm_faces fa, fcm_rows r) {
+k_uvw_proc_faces(fcm_geom g, fcm_flow f, fcm_opts o, fcm_proc P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.npro) fcm_proc_face(g, f, o, P, i);
+}
+
+__global__ void __launch_bounds__(256)
+k_uvw_rows(fcm_geom g, fcm_c2f m, fcm_slots sl, fcm_flow f, fcm_opts o, fcm_faces fa, fcm_proc P, fcm_rows r) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < g.n) fcm_row(g, m, sl, f, o, fa, r, c);
+  if (c < g.n) fcm_row(g, m, sl, f, o, fa, P, r, c);
 }
 
 __global__ void __launch_bounds__(256)
@@ -80,13 +91,18 @@ fcm_faces faces_of(const fc_context *ctx) {
   double *b = ctx->uvw_face;
   return fcm_faces{b, b + F, b + 2 * F, b + 3 * F, b + 4 * F, b + 5 * F};
 }
+fcm_proc proc_of(fc_context *ctx) {   // the four per-processor-face arrays follow the six per-inner-face ones
+  const size_t np = (size_t)ctx->npro;
+  double *b = ctx->uvw_face + 6 * (size_t)ctx->F;
+  return fcm_proc{ctx->npro, ctx->m.iProcFacesStart, ctx->fpro, ctx->field[FC_FMPRO], ctx->field[FC_APR],
+                  b, b + np, b + 2 * np, b + 3 * np};
+}
 
 int check_opts(fc_context *ctx, const fc_calcuvw_opts *o, const char *who) {
   if (!ctx->has_mesh || !ctx->has_csr || !ctx->c2f_off)
     FC_FAIL(FC_ERR_ARG, std::string(who) + ": call fc_set_mesh and fc_create_csr first");
-  if (ctx->npro > 0 || ctx->nranks > 1)
-    FC_FAIL(FC_ERR_UNSUPPORTED, std::string(who) + ": the momentum predictor runs on one rank in this version "
-                                                   "(src-parallel/calcuvw.f90 processor faces are not ported yet)");
+  if (ctx->npro > 0 && ctx->nranks == 1)
+    FC_FAIL(FC_ERR_ARG, std::string(who) + ": processor faces without fc_comm_init");
   if (o->nigrad < 1 || o->nipgrad < 0) FC_FAIL(FC_ERR_ARG, std::string(who) + ": nigrad >= 1, nipgrad >= 0");
   if (o->scheme < 0 || o->scheme > 5 || o->limiter < 0 || o->limiter > 7)
     FC_FAIL(FC_ERR_ARG, std::string(who) + ": unknown convection scheme / limiter");
@@ -126,11 +142,20 @@ int fc_calcuvw_assemble_dev(fc_context *ctx, const fc_calcuvw_opts *o) {
   }
   double **fl = ctx->field;
   const fcm_rows r{fl[FC_A], fl[FC_SU], fl[FC_SV], fl[FC_SW], fl[FC_SPU], fl[FC_SPV], fl[FC_SP]};
-  k_uvw_rows<<<fc_blocks(ctx->n, B), B, 0, st>>>(g, c2f_of(ctx), slots_of(ctx), f, fo, fa, r);
+  const fcm_proc P = proc_of(ctx);
+  if (ctx->npro > 0) {   // src-parallel/calcuvw.f90:225-254; the halo of u, v, w, p and the gradients is current
+    k_uvw_proc_faces<<<fc_blocks(ctx->npro, B), B, 0, st>>>(g, f, fo, P);   // (grad exchanges them), vis: the caller's
+    FC_LAUNCH_CHECK();
+  }
+  k_uvw_rows<<<fc_blocks(ctx->n, B), B, 0, st>>>(g, c2f_of(ctx), slots_of(ctx), f, fo, fa, P, r);
   FC_LAUNCH_CHECK();
   if (o->cn) {
     k_halve<<<fc_blocks((size_t)ctx->nnz, B), B, 0, st>>>(fl[FC_A], (size_t)ctx->nnz);
     FC_LAUNCH_CHECK();
+    if (ctx->npro > 0) {   // apr = 0.5 apr (src-parallel/calcuvw.f90:427)
+      k_halve<<<fc_blocks((size_t)ctx->npro, B), B, 0, st>>>(fl[FC_APR], (size_t)ctx->npro);
+      FC_LAUNCH_CHECK();
+    }
   }
   FC_CUDA(cudaEventRecord(ctx->ev[3], st));
   return FC_OK;
@@ -147,12 +172,13 @@ int fc_calcuvw_component_dev(fc_context *ctx, const fc_calcuvw_opts *o, int comp
   const int old_f[3] = {FC_UO, FC_VO, FC_WO}, ap_f[3] = {FC_APU, FC_APV, FC_APW};
   fcm_comp k{ctx->ioffset, ctx->diag, fl[FC_A], fl[s_f[comp]], fl[sp_f[comp]], fl[FC_SU], fl[ap_f[comp]],
              fl[phi_f[comp]], fl[old_f[comp]], fl[FC_DEN], 1.0 / o->urf[comp], 1.0 - o->urf[comp],   // init.f90:80-81
-             o->sol.small, o->timestep, o->cn, comp > 0 ? 1 : 0};
+             o->sol.small, o->timestep, o->cn, comp > 0 ? 1 : 0, ctx->nranks > 1 ? 1 : 0, ctx->npro, fl[FC_APR]};
   k_uvw_component<<<fc_blocks(ctx->n, 256), 256, 0, ctx->stream>>>(geom_of(ctx), c2f_of(ctx), k);
   FC_LAUNCH_CHECK();
   fc_solver_opts so = o->sol;
   so.sor = o->sor[comp];
   so.nsw = o->nsw[comp];
+  if (ctx->nranks > 1) so.parallel = 1;   // src-parallel/bicgstab.f90
   return fc_solve_device(ctx, FC_BICGSTAB, fl[phi_f[comp]], &so, rep, nullptr);
 }
 
@@ -163,6 +189,8 @@ int fc_calcuvw_dev(fc_context *ctx, const fc_calcuvw_opts *o, fc_calcuvw_report 
     FC_CHECK(fc_calcuvw_component_dev(ctx, o, comp, &rep->rep[comp]));
     solve_ms += ctx->tm.solve_ms;
   }
+  if (ctx->npro > 0)   // exchange(u), (v), (w), (apu)   (src-parallel/calcuvw.f90:657-665)
+    for (int fld : {FC_U, FC_V, FC_W, FC_APU}) FC_CHECK(fc_halo_exchange(ctx, ctx->field[fld]));
   FC_CUDA(cudaStreamSynchronize(ctx->stream));
   float ams = 0.f;
   FC_CUDA(cudaEventElapsedTime(&ams, ctx->ev[2], ctx->ev[3]));

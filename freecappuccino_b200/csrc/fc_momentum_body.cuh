@@ -60,6 +60,13 @@ struct fcm_faces {  // per inner face, written by fcm_face and read by fcm_row
 struct fcm_rows {
   double *a, *su, *sv, *sw, *spu, *spv, *sp;
 };
+// processor-boundary faces (src-parallel): face = pface0 + i, halo cell = n + i, i = 0..npro-1
+struct fcm_proc {
+  int npro, pface0;
+  const double *fpro, *fmpro;          // interpolation factor, mass flux of the processor faces
+  double *apr;                         // written: can (the coupling coefficient of the SpMV strip)
+  double *sup, *svp, *swp, *fie;       // per processor face, written by fcm_proc_face and read by fcm_row
+};
 
 #define FCM_G3(p, c, i) ((p)[3 * (size_t)(i) + (c)])
 #define FCM_MAX2(a, b) (((a) > (b)) ? (a) : (b))
@@ -147,12 +154,17 @@ FCM_HD double fcm_face_value(const fcm_geom &g, int scheme, int limiter, int ijp
   }
 }
 
-// one inner face: facefluxuvw (faceflux_velocity.f90:37-196) + presFaceDivInner (fieldManipulation.f90:395-445)
-FCM_HD void fcm_face(const fcm_geom &g, const fcm_flow &f, const fcm_opts &o, const fcm_faces &out, int i) {
-  const int ijp = g.owner[i], ijn = g.neigh[i];
-  const double xf = g.xf[i], yf = g.yf[i], zf = g.zf[i];
-  const double arx = g.arx[i], ary = g.ary[i], arz = g.arz[i];
-  const double lambda = g.facint[i], flomass = f.flmass[i], gam = o.gds;
+// facefluxuvw (faceflux_velocity.f90:37-196) + presFaceDivInner (fieldManipulation.f90:395-445) of one face between
+// cells ijp and ijn (ijn may be a halo cell); fidx = the face's index in the geometry arrays
+struct fcm_face_val {
+  double can, cap, sup, svp, swp, fie;
+};
+FCM_HD fcm_face_val fcm_face_core(const fcm_geom &g, const fcm_flow &f, const fcm_opts &o, int ijp, int ijn, int fidx,
+                                  double lambda, double flomass) {
+  fcm_face_val r;
+  const double xf = g.xf[fidx], yf = g.yf[fidx], zf = g.zf[fidx];
+  const double arx = g.arx[fidx], ary = g.ary[fidx], arz = g.arz[fidx];
+  const double gam = o.gds;
   const double fxn = lambda, fxp = 1.0 - lambda;
   const double xpn = g.xc[ijn] - g.xc[ijp];
   const double ypn = g.yc[ijn] - g.yc[ijp];
@@ -161,8 +173,8 @@ FCM_HD void fcm_face(const fcm_geom &g, const fcm_flow &f, const fcm_opts &o, co
   const double are = sqrt(arx * arx + ary * ary + arz * arz);
   const double game = f.vis[ijp] * fxp + f.vis[ijn] * fxn;
   const double de = game * are / dpn;
-  out.can[i] = -de + FCM_MIN2(flomass, 0.0);
-  out.cap[i] = -de - FCM_MAX2(flomass, 0.0);
+  r.can = -de + FCM_MIN2(flomass, 0.0);
+  r.cap = -de - FCM_MAX2(flomass, 0.0);
   double duxi, duyi, duzi, dvxi, dvyi, dvzi, dwxi, dwyi, dwzi;
   double duxii, duyii, duzii, dvxii, dvyii, dvzii, dwxii, dwyii, dwzii;
   fcm_sngrad(g, ijp, ijn, arx, ary, arz, lambda, f.u, f.dU, duxi, duyi, duzi, duxii, duyii, duzii);
@@ -188,9 +200,9 @@ FCM_HD void fcm_face(const fcm_geom &g, const fcm_flow &f, const fcm_opts &o, co
     we = fcm_face_value(g, o.scheme, o.limiter, ijn, ijp, xf, yf, zf, fxn, f.w, f.dW);
   }
   const double fuhigh = flomass * ue, fvhigh = flomass * ve, fwhigh = flomass * we;
-  out.sup[i] = -gam * (fuhigh - fuuds) + fdue - fdui;
-  out.svp[i] = -gam * (fvhigh - fvuds) + fdve - fdvi;
-  out.swp[i] = -gam * (fwhigh - fwuds) + fdwe - fdwi;
+  r.sup = -gam * (fuhigh - fuuds) + fdue - fdui;
+  r.svp = -gam * (fvhigh - fvuds) + fdve - fdvi;
+  r.swp = -gam * (fwhigh - fwuds) + fdwe - fdwi;
   // pressure at the face centre with the reference's df(ijp,k) addressing: flat ijp, ijp+3, ijp+6
   {
     const double xi = g.xc[ijp] * fxp + g.xc[ijn] * fxn;
@@ -199,15 +211,34 @@ FCM_HD void fcm_face(const fcm_geom &g, const fcm_flow &f, const fcm_opts &o, co
     const double dfxi = f.dP[(size_t)ijp] * fxp + f.dP[(size_t)ijn] * fxn;
     const double dfyi = f.dP[(size_t)ijp + 3] * fxp + f.dP[(size_t)ijn + 3] * fxn;
     const double dfzi = f.dP[(size_t)ijp + 6] * fxp + f.dP[(size_t)ijn + 6] * fxn;
-    out.fie[i] = f.p[ijp] * fxp + f.p[ijn] * fxn + dfxi * (xf - xi) + dfyi * (yf - yi) + dfzi * (zf - zi);
+    r.fie = f.p[ijp] * fxp + f.p[ijn] * fxn + dfxi * (xf - xi) + dfyi * (yf - yi) + dfzi * (zf - zi);
   }
+  return r;
+}
+
+// one inner face
+FCM_HD void fcm_face(const fcm_geom &g, const fcm_flow &f, const fcm_opts &o, const fcm_faces &out, int i) {
+  const fcm_face_val r = fcm_face_core(g, f, o, g.owner[i], g.neigh[i], i, g.facint[i], f.flmass[i]);
+  out.can[i] = r.can; out.cap[i] = r.cap;
+  out.sup[i] = r.sup; out.svp[i] = r.svp; out.swp[i] = r.swp;
+  out.fie[i] = r.fie;
+}
+
+// one processor-boundary face (src-parallel/calcuvw.f90:225-254, src-parallel/fieldManipulation.f90:130-146):
+// the halo cell n + i is the neighbour, fpro(i) the interpolation factor, fmpro(i) the mass flux
+FCM_HD void fcm_proc_face(const fcm_geom &g, const fcm_flow &f, const fcm_opts &o, const fcm_proc &P, int i) {
+  const int fidx = P.pface0 + i;
+  const fcm_face_val r = fcm_face_core(g, f, o, g.owner[fidx], g.n + i, fidx, P.fpro[i], P.fmpro[i]);
+  P.apr[i] = r.can;
+  P.sup[i] = r.sup; P.svp[i] = r.svp; P.swp[i] = r.swp;
+  P.fie[i] = r.fie;
 }
 
 // one cell: everything calcuvw.f90:48-383 accumulates into su/sv/sw, spu/spv/sp and the row's
 // off-diagonals, in the reference's order: calcPressDiv (inner faces, then every boundary kind),
 // the volume sources, the inner-face fluxes, then inlet, outlet, symmetry and wall faces.
 FCM_HD void fcm_row(const fcm_geom &g, const fcm_c2f &m, const fcm_slots &sl, const fcm_flow &f, const fcm_opts &o,
-                    const fcm_faces &fa, const fcm_rows &r, int c) {
+                    const fcm_faces &fa, const fcm_proc &P, const fcm_rows &r, int c) {
   double su = 0.0, sv = 0.0, sw = 0.0, spu = 0.0, spv = 0.0, sp = 0.0;
   const int qs = m.off[c], qe = m.off[c + 1];
   // ---- calcPressDiv (fieldManipulation.f90:91-165) ----
@@ -220,6 +251,9 @@ FCM_HD void fcm_row(const fcm_geom &g, const fcm_c2f &m, const fcm_slots &sl, co
       const double dfxe = fie * sx, dfye = fie * sy, dfze = fie * sz;
       if (fe < 0) { su = su + dfxe; sv = sv + dfye; sw = sw + dfze; }
       else        { su = su - dfxe; sv = sv - dfye; sw = sw - dfze; }
+    } else if (m.other[q] < g.n + P.npro) {  // processor face: the owner side only (src-parallel :130-146)
+      const double fie = P.fie[m.other[q] - g.n];
+      su = su - fie * sx; sv = sv - fie * sy; sw = sw - fie * sz;
     } else {  // presFaceDivBoundary :532-554, all five kinds
       const double pb = f.p[m.other[q]];
       su = su - pb * sx; sv = sv - pb * sy; sw = sw - pb * sz;
@@ -266,10 +300,17 @@ FCM_HD void fcm_row(const fcm_geom &g, const fcm_c2f &m, const fcm_slots &sl, co
       continue;
     }
     const int ijb = m.other[q];
+    if (ijb < g.n + P.npro) {  // processor face (src-parallel/calcuvw.f90:239-251): coupling stays outside the CSR (apr)
+      const int i = ijb - g.n;
+      const double can = P.apr[i];
+      spu = spu - can; spv = spv - can; sp = sp - can;
+      su = su + P.sup[i]; sv = sv + P.svp[i]; sw = sw + P.swp[i];
+      continue;
+    }
     int kind = -1;
     for (int b = 0; b < 5; ++b)
       if (ijb >= sl.slot[b] && ijb < sl.slot[b] + sl.count[b]) kind = b;
-    if (kind < 0 || kind == 4) continue;  // processor faces are not handled here; prOutlet has no loop in calcuvw
+    if (kind < 0 || kind == 4) continue;  // prOutlet has no loop in calcuvw
     const double ax = g.arx[fc], ay = g.ary[fc], az = g.arz[fc];
     const double are = sqrt(ax * ax + ay * ay + az * az);
     if (kind <= 1) {  // inlet / outlet: facefluxuvw_boundary, only cb = can is used (:225-265)
@@ -322,6 +363,9 @@ struct fcm_comp {
   const double *phi, *phio, *den;
   double urfrs, urfms, small, timestep;
   int cn, zero_diag;
+  int parallel;          // src-parallel/calcuvw.f90: running-subtraction diagonal (:485-493), cn terms of the
+  int npro;              // processor faces (:450-463) with apr
+  const double *apr;
 };
 FCM_HD void fcm_component(const fcm_geom &g, const fcm_c2f &m, const fcm_comp &k, int c) {
   double s = k.s[c], spc = k.spc[c];
@@ -331,6 +375,14 @@ FCM_HD void fcm_component(const fcm_geom &g, const fcm_c2f &m, const fcm_comp &k
       const int fc = m.face[q] & 0x7fffffff;
       if (fc < g.F) s = s - k.a[m.pos[q]] * k.phio[m.other[q]];
     }
+    for (int q = m.off[c]; q < m.off[c + 1]; ++q) {   // processor faces come after the inner ones in the map
+      const int fc = m.face[q] & 0x7fffffff;
+      if (fc >= g.F && m.other[q] < g.n + k.npro) {
+        const double ap_ = k.apr[m.other[q] - g.n];
+        s = s - ap_ * k.phio[m.other[q]];
+        s = s + ap_ * k.phio[c];
+      }
+    }
     const double apotime = k.den[c] * g.vol[c] / k.timestep;
     double sum = 0.0;
     for (int p = rs; p < re; ++p) sum = sum + k.a[p];
@@ -339,6 +391,16 @@ FCM_HD void fcm_component(const fcm_geom &g, const fcm_c2f &m, const fcm_comp &k
     spc = spc + apotime;
     k.s[c] = s;
     k.spc[c] = spc;
+  }
+  if (k.parallel) {
+    double d = spc;
+    for (int p = rs; p < re; ++p)
+      if (p != dg) d = d - k.a[p];
+    d = d * k.urfrs;
+    k.a[dg] = d;
+    k.su[c] = s + k.urfms * d * k.phi[c];
+    k.ap[c] = 1.0 / (d + k.small);
+    return;
   }
   const double stale = k.zero_diag ? 0.0 : k.a[dg];
   double sum = 0.0;

@@ -233,7 +233,10 @@ int fc_calcp_host(fc_context *ctx, const fc_calcp_opts *o, double *u, double *v,
  * slots of FC_P and FC_DPDXI (calcPressDiv, fieldManipulation.f90:82-87),
  * FC_DUDXI/DVDXI/DWDXI, FC_SV/SW/SPU/SPV/SP; FC_A / FC_SU hold the W system
  * afterwards, exactly like the module arrays of the reference.
- * Laminar form (lturb = .false.), serial `src` semantics, one rank, no O-C cuts. */
+ * Laminar form (lturb = .false.), no O-C cuts.  One rank: serial `src` semantics.
+ * Several ranks (after fc_comm_init): src-parallel/calcuvw.f90 -- processor faces, the
+ * running-subtraction diagonal, exchange of u, v, w, apu at the end; FC_VIS must
+ * arrive with a current halo (fc_exchange).                                          */
 typedef struct {
   int nigrad, nipgrad;  /* parameters: nigrad, nipgrad (= 2)                        */
   int scheme;           /* convective scheme (read_input.f90:97-133 -> face_value,

@@ -12,11 +12,14 @@
 extern "C" {
 
 void fcm_host_assemble(const fcm_geom *g, const fcm_c2f *m, const fcm_slots *sl, const fcm_flow *f, const fcm_opts *o,
-                       const fcm_faces *fa, const fcm_rows *r, int nnz) {
+                       const fcm_faces *fa, const fcm_proc *P, const fcm_rows *r, int nnz) {
   for (int i = 0; i < g->F; ++i) fcm_face(*g, *f, *o, *fa, i);
-  for (int c = 0; c < g->n; ++c) fcm_row(*g, *m, *sl, *f, *o, *fa, *r, c);
-  if (o->cn)
+  for (int i = 0; i < P->npro; ++i) fcm_proc_face(*g, *f, *o, *P, i);
+  for (int c = 0; c < g->n; ++c) fcm_row(*g, *m, *sl, *f, *o, *fa, *P, *r, c);
+  if (o->cn) {
     for (int k = 0; k < nnz; ++k) r->a[k] = 0.5 * r->a[k];
+    for (int i = 0; i < P->npro; ++i) P->apr[i] = 0.5 * P->apr[i];
+  }
 }
 
 void fcm_host_component(const fcm_geom *g, const fcm_c2f *m, const fcm_comp *k) {
@@ -69,6 +72,7 @@ int fcm_host_sizes(int which) {
     case 6: return (int)sizeof(fcm_rows);
     case 7: return (int)sizeof(fcm_comp);
     case 8: return (int)sizeof(fcp_hbya);
+    case 9: return (int)sizeof(fcm_proc);
   }
   return -1;
 }

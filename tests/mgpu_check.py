@@ -118,6 +118,99 @@ def main():
                     failures.append(f"{tag}: sumLocalContErr {c0} vs {rep_o.sumLocalContErr}")
                 print(f"[mgpu] {'p2p' if p2p else 'nccl'} {tag}: iters {box[0]['iters']} (oracle {[rep_o.rep[k].iters for k in range(npcor)]}) "
                       f"worst field rel L2 {worst:.2e}", flush=True)
+    # ---- momentum predictor on several ranks (src-parallel/calcuvw.f90; fc_calcuvw with processor faces) ----
+    for mesh_name, g in (("skew", cases.skew_case(9, 8, 3 * world + 2)), ("poly", cases.poly_case(5))):
+        rng = np.random.default_rng(21)
+        f = cases.channel_fields(g)
+        nt = g.numTotal
+        fl_g = 1e-2 * rng.standard_normal(g.numInnerFaces)
+        extra = dict(vis=0.01 * (1.0 + 0.3 * rng.random(nt)))
+        for k in ("uo", "vo", "wo", "uoo", "voo", "woo", "t"):
+            extra[k] = 0.1 * rng.standard_normal(nt)
+        fmi_g, _ = cases.inlet_fluxes(g, f)
+        fs, sl = g.boundary_faces("outlet"), g.boundary_slots("outlet")
+        fmo_g = f["den"][sl] * (f["u"][sl] * g.arx[fs] + f["v"][sl] * g.ary[fs] + f["w"][sl] * g.arz[fs])
+        cell_rank = M.rcb_ranks(g, world) if mesh_name == "poly" else M.slab_ranks(g.numCells, world)
+        parts = M.partition(g, cell_rank, world)
+
+        def rank_state(part):
+            st = {k: M.scatter_total(g, part, f[k]) for k in ("u", "v", "w", "p", "den")}
+            st.update({k: M.scatter_total(g, part, extra[k]) for k in extra})
+            gf = part.face_global
+            st["flmass"] = np.ascontiguousarray(fl_g[gf[:part.numInnerFaces]])
+            pf = gf[part.iProcFacesStart:part.iProcFacesStart + part.npro]
+            sgn = np.sign(part.arx[part.iProcFacesStart:] * g.arx[pf] + part.ary[part.iProcFacesStart:] * g.ary[pf]
+                          + part.arz[part.iProcFacesStart:] * g.arz[pf])
+            st["fmpro"] = np.ascontiguousarray(fl_g[pf] * sgn)
+            for kind, src in (("inlet", fmi_g), ("outlet", fmo_g)):
+                c = part.count(kind)
+                gl = gf[part.faces_start(kind):part.faces_start(kind) + c] - g.faces_start(kind)
+                st["fm" + kind[0]] = np.ascontiguousarray(src[gl]) if c else np.zeros(0)
+            return st
+
+        part = parts[rank]
+        st = rank_state(part)
+        kw = dict(scheme="muscl-f", urf=(0.7, 0.8, 0.6), sor=(1e-9,) * 3, nsw=(300,) * 3, bdf=True, btime=1.0, timestep=0.05)
+        ctx = lib.Context(local)
+        parallel.init_comm(ctx)
+        ctx.set_mesh(part)
+        ctx.create_csr()
+        p2p = parallel.enable_p2p(ctx)
+        for k, name in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("vis", "VIS"), ("uo", "UO"),
+                        ("vo", "VO"), ("wo", "WO"), ("uoo", "UOO"), ("voo", "VOO"), ("woo", "WOO"), ("t", "T"),
+                        ("flmass", "FLMASS")):
+            ctx.upload(name, st[k])
+        if part.npro:
+            ctx.upload("FMPRO", st["fmpro"])
+        if st["fmi"].size:
+            ctx.upload("FMI", st["fmi"])
+        if st["fmo"].size:
+            ctx.upload("FMO", st["fmo"])
+        ctx.calcuvw_assemble(lib.calcuvw_opts(**kw))
+        got = {k: ctx.download(k.upper()) for k in ("su", "sv", "sw", "spu", "a", "apr")}
+        rep = ctx.calcuvw(lib.calcuvw_opts(**kw))
+        got.update({k: ctx.download(k.upper()) for k in ("u", "v", "w", "apu")})
+        got["iters"] = [rep.rep[k].iters for k in range(3)]
+        got["res0"] = [rep.rep[k].res0 for k in range(3)]
+        ctx.close()
+        box = [None] * world
+        dist.all_gather_object(box, got)
+        if rank == 0:
+            pc = OP.ParCase(parts)
+            xs = pc.uvw_fields(0.0)
+            for r, m in enumerate(parts):
+                s2 = rank_state(m)
+                for k in ("u", "v", "w", "p", "den"):
+                    getattr(pc.fields[r], k)[:] = s2[k]
+                for k in extra:
+                    getattr(xs[r], k)[:] = s2[k]
+                pc.fields[r].flmass[:] = s2["flmass"]
+                pc.fmpro[r][:m.npro] = s2["fmpro"]
+                pc.fields[r].fmi[:s2["fmi"].size] = s2["fmi"]
+                pc.fields[r].fmo[:s2["fmo"].size] = s2["fmo"]
+            tag = f"{mesh_name}/calcuvw"
+            pc.calcuvw_assemble(O.uvw_opts(**kw))
+            for r, m in enumerate(parts):
+                for k, ref in (("su", pc.fields[r].su), ("sv", xs[r].sv), ("sw", xs[r].sw), ("spu", xs[r].spu),
+                               ("a", pc.fields[r].a), ("apr", pc.apr[r][:m.npro])):
+                    if not np.array_equal(box[r][k][:ref.size], ref):
+                        failures.append(f"{tag}: rank {r} {k} not bit-exact ({np.abs(box[r][k][:ref.size] - ref).max():.2e})")
+            rep_o = pc.calcuvw(O.uvw_opts(**kw))
+            worst = 0.0
+            for k in range(3):
+                if abs(box[0]["iters"][k] - rep_o.rep[k].iters) > 1:
+                    failures.append(f"{tag}: component {k} iterations {box[0]['iters'][k]} vs oracle {rep_o.rep[k].iters}")
+                if abs(box[0]["res0"][k] - rep_o.rep[k].res0) > 1e-9 * abs(rep_o.rep[k].res0):
+                    failures.append(f"{tag}: component {k} res0 {box[0]['res0'][k]} vs {rep_o.rep[k].res0}")
+            for r, m in enumerate(parts):
+                for k, ref in (("u", pc.fields[r].u), ("v", pc.fields[r].v), ("w", pc.fields[r].w), ("apu", xs[r].apu)):
+                    nn = m.numCells + m.npro     # the halo is current after the final exchanges
+                    e = cases.rel_l2(box[r][k][:nn], ref[:nn])
+                    worst = max(worst, e)
+                    if e > 1e-6:
+                        failures.append(f"{tag}: rank {r} field {k} rel L2 {e:.2e}")
+            print(f"[mgpu] {'p2p' if p2p else 'nccl'} {tag}: iters {box[0]['iters']} (oracle "
+                  f"{[rep_o.rep[k].iters for k in range(3)]}) worst field rel L2 {worst:.2e}", flush=True)
     ok = [not failures]
     dist.broadcast_object_list(ok, src=0)
     if rank == 0:

@@ -58,7 +58,14 @@ class Rows(C.Structure):
 
 class Comp(C.Structure):
     _fields_ = [("ioffset", ip), ("diag", ip)] + [(k, dp) for k in ("a", "s", "spc", "su", "ap", "phi", "phio", "den")] + [
-        (k, C.c_double) for k in ("urfrs", "urfms", "small", "timestep")] + [("cn", C.c_int), ("zero_diag", C.c_int)]
+        (k, C.c_double) for k in ("urfrs", "urfms", "small", "timestep")] + [("cn", C.c_int), ("zero_diag", C.c_int),
+                                                                              ("parallel", C.c_int), ("npro", C.c_int),
+                                                                              ("apr", dp)]
+
+
+class Proc(C.Structure):
+    _fields_ = [("npro", C.c_int), ("pface0", C.c_int)] + [(k, dp) for k in ("fpro", "fmpro", "apr", "sup", "svp", "swp",
+                                                                             "fie")]
 
 
 class Hbya(C.Structure):
@@ -78,7 +85,7 @@ def host():
     if not os.path.exists(so) or max(os.path.getmtime(f) for f in [src] + hdrs) > os.path.getmtime(so):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", so, src])
     lib = C.CDLL(so)
-    for k, st in enumerate((Geom, C2f, Slots, Flow, Opts, Faces, Rows, Comp, Hbya)):
+    for k, st in enumerate((Geom, C2f, Slots, Flow, Opts, Faces, Rows, Comp, Hbya, Proc)):
         assert lib.fcm_host_sizes(k) == C.sizeof(st), (k, st)
     return lib
 
@@ -106,6 +113,9 @@ def device_layout(mesh, csr):
     for f in range(F):
         ent[owner[f]].append((f, f, int(neigh[f])))
         ent[neigh[f]].append((f, f | 0x80000000, int(owner[f])))
+    for i in range(mesh.npro):                 # processor faces: halo slot n + i, between inner and boundary entries
+        f = mesh.iProcFacesStart + i
+        ent[owner[f]].append((F + i, f, n + i))
     slots = Slots()
     for b, kind in enumerate(M.KINDS):
         fs, sl = mesh.boundary_faces(kind), mesh.boundary_slots(kind)
@@ -187,8 +197,10 @@ def run_case(host, mesh, f, scheme, **kw):
     rows = {k: np.zeros(n) for k in ("su", "sv", "sw", "spu", "spv", "sp")}
     FA = Faces(*[d(a) for a in fa])
     R = Rows(d(g["a"]), *[d(rows[k]) for k in ("su", "sv", "sw", "spu", "spv", "sp")])
+    one = np.zeros(1)
+    P0 = Proc(0, 0, *[d(one)] * 7)
     host.fcm_host_assemble(C.byref(G), C.byref(Mp), C.byref(L["slots"]), C.byref(FL), C.byref(O), C.byref(FA),
-                           C.byref(R), csr.nnz)
+                           C.byref(P0), C.byref(R), csr.nnz)
 
     # ---- oracle ----
     oracle.calcuvw_assemble(mesh, csr, of, x, opts)
@@ -205,7 +217,7 @@ def run_case(host, mesh, f, scheme, **kw):
                                                   ("sw", "sp", "w", "wo"))):
         K = Comp(i32(L["ioffset"]), i32(L["diag"]), d(g["a"]), d(rows[sk]), d(rows[spk]), d(su_rhs), d(ap[comp]),
                  d(g[phik]), d(getattr(x, oldk)), d(den), 1.0 / opts.urf[comp], 1.0 - opts.urf[comp], opts.sol.small,
-                 opts.timestep, opts.cn, 1 if comp else 0)
+                 opts.timestep, opts.cn, 1 if comp else 0, 0, 0, d(one))
         host.fcm_host_component(C.byref(G), C.byref(Mp), C.byref(K))
         a_before = g["a"].copy()
         # oracle: same step + BiCGStab; capture its matrix / rhs through a zero-sweep solve
@@ -385,3 +397,89 @@ def test_limiter_bodies_equal_oracle(host, name, which):
     ref = g0.copy()
     oracle.slope_limiter(mesh, csr, which, phi, ref)
     assert np.array_equal(got, ref[:n])
+
+
+# ---- several ranks: processor faces, running-subtraction diagonal (src-parallel/calcuvw.f90) ----
+@pytest.mark.parametrize("kw", [dict(), dict(bdf=True, btime=1.0, timestep=0.02, cn=True)])
+@pytest.mark.parametrize("name,nranks", [("skew", 2), ("skew", 3), ("poly", 2)])
+def test_bodies_equal_parallel_oracle(host, name, nranks, kw):
+    """Every rank's kernel bodies (inner + processor faces, rows, the three component steps with the parallel
+    diagonal) against the lock-step multi-rank oracle, bit for bit.  Halos, gradients and the boundary pressure are
+    taken from the oracle (on the GPU the verified halo exchange / gradient kernels provide them)."""
+    from oracle import oracle_par as OP
+    mesh = cases.skew_case(6, 5, 7) if name == "skew" else MESHES["poly"]()
+    f = cases.flow_fields(mesh)
+    rng = np.random.default_rng(8)
+    nt = mesh.numTotal
+    cell_rank = M.rcb_ranks(mesh, nranks) if name == "poly" else M.slab_ranks(mesh.numCells, nranks)
+    parts = M.partition(mesh, cell_rank, nranks)
+    pc = OP.ParCase(parts)
+    xs = pc.uvw_fields(0.0)
+    gl = dict(vis=0.01 * (1.0 + 0.3 * rng.random(nt)))
+    for k in ("uo", "vo", "wo", "uoo", "voo", "woo", "t"):
+        gl[k] = rng.standard_normal(nt)
+    fl_g = rng.standard_normal(mesh.numInnerFaces) * 1e-2
+    for r, part in enumerate(parts):
+        fr = pc.fields[r]
+        for k in ("u", "v", "w", "p", "den"):
+            getattr(fr, k)[:] = M.scatter_total(mesh, part, f[k])
+        gf = part.face_global
+        fr.flmass[:] = fl_g[gf[:part.numInnerFaces]]
+        pf = gf[part.iProcFacesStart:part.iProcFacesStart + part.npro]
+        pc.fmpro[r][:part.npro] = fl_g[pf] * np.sign(part.arx[part.iProcFacesStart:] * mesh.arx[pf] +
+                                                     part.ary[part.iProcFacesStart:] * mesh.ary[pf] +
+                                                     part.arz[part.iProcFacesStart:] * mesh.arz[pf])
+        fr.fmi[:] = rng.standard_normal(fr.fmi.size) * 1e-2
+        fr.fmo[:] = rng.standard_normal(fr.fmo.size) * 1e-2
+        fr.a[:] = rng.standard_normal(fr.a.size)
+        for k in gl:
+            getattr(xs[r], k)[:] = M.scatter_total(mesh, part, gl[k])
+    opts = oracle.uvw_opts(scheme="muscl-f", urf=(0.7, 0.8, 0.6), nsw=(0, 0, 0), **kw)
+    a_in = [fr.a.copy() for fr in pc.fields]
+    pc.calcuvw_assemble(opts)
+    keep = []
+    for r, part in enumerate(parts):
+        fr, x, csr = pc.fields[r], xs[r], pc.csr[r]
+        n, F, npro = part.numCells, part.numInnerFaces, part.npro
+        L, G, Mp, geo = geom_and_map(part, csr)
+        den = np.ascontiguousarray(fr.den)
+        FL = Flow(d(fr.u), d(fr.v), d(fr.w), d(fr.p), d(den), d(x.vis), d(fr.flmass), d(fr.fmi), d(fr.fmo), d(fr.dUdxi),
+                  d(fr.dVdxi), d(fr.dWdxi), d(fr.dPdxi), d(x.uo), d(x.vo), d(x.wo), d(x.uoo), d(x.voo), d(x.woo), d(x.t))
+        O = Opts(opts.scheme, opts.limiter, opts.gds, opts.bdf, opts.btime, opts.timestep, opts.cn, opts.const_mflux,
+                 opts.gradPcmf, opts.lbuoy, opts.boussinesq, opts.beta, opts.tref, opts.densit, opts.gravx, opts.gravy,
+                 opts.gravz, opts.viscos)
+        fa = [np.zeros(max(F, 1)) for _ in range(6)]
+        pa = [np.zeros(max(npro, 1)) for _ in range(5)]     # apr, sup, svp, swp, fie
+        rows = {k: np.zeros(n) for k in ("su", "sv", "sw", "spu", "spv", "sp")}
+        a = a_in[r].copy()
+        fpro = np.ascontiguousarray(part.fpro, dtype=np.float64) if npro else np.zeros(1)
+        P = Proc(npro, part.iProcFacesStart, d(fpro), d(pc.fmpro[r]), *[d(v) for v in pa])
+        host.fcm_host_assemble(C.byref(G), C.byref(Mp), C.byref(L["slots"]), C.byref(FL), C.byref(O),
+                               C.byref(Faces(*[d(v) for v in fa])), C.byref(P),
+                               C.byref(Rows(d(a), *[d(rows[k]) for k in ("su", "sv", "sw", "spu", "spv", "sp")])), csr.nnz)
+        for k, ref in (("su", fr.su), ("sv", x.sv), ("sw", x.sw), ("spu", x.spu), ("spv", x.spv), ("sp", x.sp)):
+            assert np.array_equal(rows[k], ref), (r, k, np.abs(rows[k] - ref).max())
+        assert np.array_equal(a, fr.a)
+        assert np.array_equal(pa[0][:npro], pc.apr[r][:npro])
+        keep.append((L, G, Mp, geo, den, rows, a, pa, fpro))
+    # component steps: all ranks of one component, then the next (the oracle's zero-sweep solve leaves u, v, w alone)
+    for comp, (sk, spk, phik, oldk, apk) in enumerate((("su", "spu", "u", "uo", "apu"), ("sv", "spv", "v", "vo", "apv"),
+                                                       ("sw", "sp", "w", "wo", "apw"))):
+        got = []
+        for r, part in enumerate(parts):
+            L, G, Mp, geo, den, rows, a, pa, fpro = keep[r]
+            fr, x = pc.fields[r], xs[r]
+            n = part.numCells
+            ap = np.zeros(n)
+            K = Comp(i32(L["ioffset"]), i32(L["diag"]), d(a), d(rows[sk]), d(rows[spk]), d(rows["su"]), d(ap),
+                     d(getattr(fr, phik)), d(getattr(x, oldk)), d(den), 1.0 / opts.urf[comp], 1.0 - opts.urf[comp],
+                     opts.sol.small, opts.timestep, opts.cn, 1 if comp else 0, 1, part.npro, d(pa[0]))
+            host.fcm_host_component(C.byref(G), C.byref(Mp), C.byref(K))
+            got.append(ap)
+        pc.calcuvw_component(opts, comp)
+        for r, part in enumerate(parts):
+            L, G, Mp, geo, den, rows, a, pa, fpro = keep[r]
+            n = part.numCells
+            assert np.array_equal(a, pc.fields[r].a), (comp, r)
+            assert np.array_equal(rows["su"], pc.fields[r].su), (comp, r)
+            assert np.array_equal(got[r], getattr(xs[r], apk)[:n]), (comp, r)
