@@ -4,7 +4,7 @@
 // (freecappuccino_b200/csrc/fc_momentum_body.cuh) with g++ and runs them in plain loops, so that
 // tests/test_momentum_bodies.py can check their index logic and arithmetic order against the oracle
 // on a machine without a GPU.  On the GPU the same bodies are called by the thin __global__ wrappers
-// of fc_momentum.cu (tests/test_gpu_zz_momentum.py compares those with the oracle).  The library has
+// of fc_momentum.cu (tests/test_gpu_zz1_momentum.py compares those with the oracle).  The library has
 // no host path: this file is built only by the test that uses it.
 #include "../../freecappuccino_b200/csrc/fc_piso_body.cuh"   // includes fc_momentum_body.cuh
 #include "../../freecappuccino_b200/csrc/fc_grad_body.cuh"

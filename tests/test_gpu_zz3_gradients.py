@@ -121,7 +121,7 @@ def test_calcp_with_configured_gradients(fc, name, method, limiter, sor, ftol):
 
 
 def test_calcuvw_with_configured_gradients(fc):
-    from test_gpu_zz_momentum import make_state, upload_state
+    from test_gpu_zz1_momentum import make_state, upload_state
     mesh = MESHES["skew"]()
     ctx = make_ctx(fc, mesh)
     oracle.set_gradient("lstsq_qr", "mVenkatakrishnan", mesh)

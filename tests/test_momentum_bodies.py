@@ -6,7 +6,7 @@ fc_momentum.cu call.  tests/kernel_bodies_host/fcm_host.cpp compiles that header
 device data layout (0-based indices, cell-to-face map) built here in numpy.  Everything must equal
 the oracle's calcuvw bit for bit.  This is test infrastructure: the product has no host path
 (tests/test_abi.py asserts the package never references it); the GPU twin of this test is
-tests/test_gpu_zz_momentum.py.
+tests/test_gpu_zz1_momentum.py.
 """
 import ctypes as C
 import os
