@@ -236,7 +236,8 @@ int fc_calcp_host(fc_context *ctx, const fc_calcp_opts *o, double *u, double *v,
  * Laminar form (lturb = .false.), no O-C cuts.  One rank: serial `src` semantics.
  * Several ranks (after fc_comm_init): src-parallel/calcuvw.f90 -- processor faces, the
  * running-subtraction diagonal, exchange of u, v, w, apu at the end; FC_VIS must
- * arrive with a current halo (fc_exchange).                                          */
+ * arrive with a current halo (fc_exchange); the processor faces' mass fluxes are
+ * FC_FMPRO as fc_calcp leaves them.                                                  */
 typedef struct {
   int nigrad, nipgrad;  /* parameters: nigrad, nipgrad (= 2)                        */
   int scheme;           /* convective scheme (read_input.f90:97-133 -> face_value,
