@@ -311,3 +311,25 @@ def test_cavity_driver_on_the_shipped_polymesh(tmp_path):
         assert a[0] == b[0] and abs(a[2] - b[2]) <= 1
         if a[2] == b[2]:
             assert float(a[1]) == pytest.approx(float(b[1]), rel=5e-3, abs=1e-12)
+
+
+@pytest.mark.parametrize("make", [lambda: cases.hex_case(3, 1, 1),
+                                  lambda: cases.hex_case(20, 20, 1, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry")),
+                                  lambda: cases.hex_case(4, 3, 2, kinds=("symmetry",) * 6)])
+def test_calcuvw_edge_meshes_bit_exact(fc, make):
+    """Smallest mesh the predictor accepts (three cells in a row), a one-cell-thick slab, a single boundary kind."""
+    mesh = make()
+    csr, of, x, _ = make_state(mesh, cases.flow_fields(mesh))
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    upload_state(ctx, mesh, of, x)
+    oo, go = both_opts(fc, bdf=True, btime=1.0, timestep=0.05, nsw=(0, 0, 0))
+    oracle.calcuvw(mesh, csr, of, x, oo)
+    ctx.calcuvw(go)
+    n = mesh.numCells
+    for fld, ref in (("SV", x.sv), ("SW", x.sw), ("SPU", x.spu), ("SP", x.sp), ("A", of.a), ("SU", of.su),
+                     ("APU", x.apu[:n]), ("APW", x.apw[:n])):
+        got = ctx.download(fld)[:ref.size]
+        assert np.array_equal(got, ref), (fld, float(np.abs(got - ref).max()))
+    ctx.close()

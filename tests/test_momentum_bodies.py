@@ -483,3 +483,14 @@ def test_bodies_equal_parallel_oracle(host, name, nranks, kw):
             assert np.array_equal(a, pc.fields[r].a), (comp, r)
             assert np.array_equal(rows["su"], pc.fields[r].su), (comp, r)
             assert np.array_equal(got[r], getattr(xs[r], apk)[:n]), (comp, r)
+
+
+# ---- edge cases: smallest mesh the predictor accepts, one-cell-thick slab, a single boundary kind ----
+@pytest.mark.parametrize("make", [lambda: cases.hex_case(3, 1, 1), lambda: cases.hex_case(20, 20, 1, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry")),
+                                  lambda: cases.hex_case(4, 3, 2, kinds=("symmetry",) * 6), lambda: cases.hex_case(1, 1, 1)])
+def test_bodies_equal_oracle_edge_meshes(host, make):
+    mesh = make()
+    f = cases.flow_fields(mesh)
+    if mesh.numCells < 3 and mesh.numInnerFaces > 0:
+        pytest.skip("outside the reference's df(ijp,3) addressing")
+    assert run_case(host, mesh, f, "muscl-f", bdf=True, btime=1.0, timestep=0.05)
