@@ -622,3 +622,97 @@ def gather_cells(g: Mesh, parts: List[Mesh], arrs: List[np.ndarray]) -> np.ndarr
 def scatter_faces(part: Mesh, arr: np.ndarray) -> np.ndarray:
     """Global per-boundary-kind face list helper: values of a global per-face array at the rank's faces."""
     return np.ascontiguousarray(arr[part.face_global])
+
+
+# --------------------------------------------------------------------------
+# polyMesh / decomposition writers (SURVEY 8(f) rank 4)
+# --------------------------------------------------------------------------
+_FOAM_HEADER = """/*--------------------------------*- C++ -*----------------------------------*\\
+| =========                 |                                                 |
+| \\\\      /  F ield         | freeCappuccino polyMesh (OpenFOAM ASCII layout)  |
+\\*---------------------------------------------------------------------------*/
+FoamFile
+{
+    version     2.0;
+    format      ascii;
+    class       %s;
+    location    "constant/polyMesh";
+    object      %s;
+}
+// * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * //
+
+"""
+
+
+def write_polymesh(polymesh_dir: str, points: np.ndarray, faces, owner0: np.ndarray, neighbour0: np.ndarray,
+                   patches: Sequence[Tuple[str, int, int]]) -> None:
+    """Write ``points / faces / owner / neighbour`` in OpenFOAM ASCII and the reference's simplified ``boundary``
+    table (``#type nFaces startFace``): what ``read_polymesh`` here, ``mesh_geometry`` of the reference
+    (src/mesh_geometry_and_topology.f90:395-470, 540-600) and host/fcapp_mesh.cpp read.  ``owner0`` /
+    ``neighbour0`` are 0-based like the files."""
+    os.makedirs(polymesh_dir, exist_ok=True)
+    with open(os.path.join(polymesh_dir, "points"), "w") as fh:
+        fh.write(_FOAM_HEADER % ("vectorField", "points") + f"\n{len(points)}\n(\n")
+        fh.writelines("(%s %s %s)\n" % (repr(float(p[0])), repr(float(p[1])), repr(float(p[2]))) for p in points)
+        fh.write(")\n")
+    with open(os.path.join(polymesh_dir, "faces"), "w") as fh:
+        fh.write(_FOAM_HEADER % ("faceList", "faces") + f"\n{len(faces)}\n(\n")
+        fh.writelines("%d(%s)\n" % (len(f), " ".join(str(int(v)) for v in f)) for f in faces)
+        fh.write(")\n")
+    for name, arr in (("owner", owner0), ("neighbour", neighbour0)):
+        with open(os.path.join(polymesh_dir, name), "w") as fh:
+            fh.write(_FOAM_HEADER % ("labelList", name) + f"\n{len(arr)}\n(\n")
+            fh.write("\n".join(str(int(v)) for v in arr) + ("\n" if len(arr) else "") + ")\n")
+    with open(os.path.join(polymesh_dir, "boundary"), "w") as fh:
+        fh.write("#type nFaces startFace\n")
+        fh.writelines(f"{kind} {int(nf)} {int(st)}\n" for kind, nf, st in patches)
+
+
+def _write_labels(path: str, name: str, arr: np.ndarray) -> None:
+    with open(path, "w") as fh:
+        fh.write(_FOAM_HEADER % ("labelList", name) + f"\n{len(arr)}\n(\n")
+        fh.write("\n".join(str(int(v)) for v in arr) + ("\n" if len(arr) else "") + ")\n")
+
+
+def write_decomposition(case_dir: str, points: np.ndarray, faces, g: Mesh, cell_rank: np.ndarray, nranks: int,
+                        patches: Sequence[Tuple[str, int, int]]) -> List[Mesh]:
+    """The decomposition ``src-parallel`` reads (examples/*/…-setup-parallel.tar.gz): for every rank
+    ``processor<r>/constant/polyMesh/`` with points, faces, owner, neighbour, the ``boundary`` table of the rank's
+    share of every global patch (empty patches keep their row, like decomposePar), the ``process`` file
+    (``neighbProcNo nfaces startFace`` per connection, src-parallel/mesh_geometry_and_topology.f90:497-515) and
+    OpenFOAM's ``cellProcAddressing`` / ``faceProcAddressing`` (1-based global face, negative when the rank sees
+    the face flipped).  ``patches`` is the global boundary table; returns the per-rank meshes of ``partition``."""
+    parts = partition(g, cell_rank, nranks)
+    nI = g.numInnerFaces
+    for r, p in enumerate(parts):
+        d = os.path.join(case_dir, f"processor{r}", "constant", "polyMesh")
+        gf = p.face_global
+        flip = np.zeros(gf.size, bool)
+        if p.npro:   # processor faces whose global owner is remote are seen reversed
+            pf = gf[p.iProcFacesStart:]
+            flip[p.iProcFacesStart:] = cell_rank[g.owner[pf].astype(np.int64) - 1] != r
+        used = np.unique(np.concatenate([np.asarray(faces[f], dtype=np.int64) for f in gf]))
+        g2l = np.full(len(points), -1, dtype=np.int64)
+        g2l[used] = np.arange(used.size)
+        lf = []
+        for f, fl in zip(gf, flip):
+            nodes = g2l[np.asarray(faces[f], dtype=np.int64)]
+            # OpenFOAM's reverseFace: keep the first node, reverse the rest -- the fan triangulation about node 1
+            # then consists of the same triangles, so the area vector and the volume sums are exactly negated
+            lf.append(np.concatenate([nodes[:1], nodes[:0:-1]]) if fl else nodes)
+        # boundary rows: every global patch keeps a row; rows of equal kind are contiguous in the rank's numbering
+        rows, pos = [], p.numInnerFaces
+        for kind, nf, st in sorted(patches, key=lambda t: t[2]):
+            mine = int(np.count_nonzero((gf[p.numInnerFaces:p.iProcFacesStart] >= st)
+                                        & (gf[p.numInnerFaces:p.iProcFacesStart] < st + nf)))
+            rows.append((kind, mine, pos))
+            pos += mine
+        write_polymesh(d, points[used], lf, p.owner - 1, p.neighbour - 1, rows)
+        with open(os.path.join(d, "process"), "w") as fh:
+            fh.write("# neighbProcNo nfaces startFace\n%d\n" % len(p.neighbProcNo))
+            for c, q in enumerate(p.neighbProcNo):
+                s, e = int(p.neighbProcOffset[c]), int(p.neighbProcOffset[c + 1])
+                fh.write("%d %d %d\n" % (int(q), e - s, p.iProcFacesStart + s - 1))
+        _write_labels(os.path.join(d, "cellProcAddressing"), "cellProcAddressing", p.cell_global)
+        _write_labels(os.path.join(d, "faceProcAddressing"), "faceProcAddressing", np.where(flip, -(gf + 1), gf + 1))
+    return parts
