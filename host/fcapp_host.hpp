@@ -65,6 +65,10 @@ void mesh_geometry_box(int nx, int ny, int nz, dp lx, dp ly, dp lz, const char *
 // mesh_geometry (src/mesh_geometry_and_topology.f90:310-1081, polyMesh branch): reads points / faces / owner /
 // neighbour / boundary of an OpenFOAM polyMesh directory and computes `module geometry` (fcapp_mesh.cpp)
 void mesh_geometry(const std::string &polymesh_dir);
+// restart files in the reference's unformatted sequential format (fcapp_restart.cpp): write_restart_files.f90:16-62,
+// readfiles.f90:12-52
+void write_restart_files(const std::string &path, int itime, dp time);
+void readfiles(const std::string &path, int *itime, dp *time);
 
 void fcapp_init(int device);  // after mesh_geometry: hand `module geometry` to the GPU
 void fcapp_finalize();
