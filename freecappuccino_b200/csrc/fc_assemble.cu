@@ -14,6 +14,7 @@
 // prOutlet) and accumulates left to right.  The result is deterministic and -- because
 // the library is built with -fmad=false and IEEE division / sqrt -- bit-identical to the
 // Fortran loops.
+#include "fc_body_views.cuh"
 #include "fc_piso_body.cuh"
 #include "fc_reduce.cuh"
 
@@ -782,9 +783,8 @@ int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep) {
   const int B = 256, n = ctx->n;
   cudaStream_t st = ctx->stream;
   double **fl = ctx->field;
-  const fcm_geom g{ctx->owner, ctx->neigh, ctx->xc, ctx->yc, ctx->zc, ctx->vol, ctx->arx, ctx->ary, ctx->arz,
-                   ctx->xf, ctx->yf, ctx->zf, ctx->facint, ctx->n, ctx->F};
-  const fcm_c2f m{ctx->c2f_off, ctx->c2f_face, ctx->c2f_other, ctx->c2f_pos};
+  const fcm_geom g = fcm_geom_of(ctx);
+  const fcm_c2f m = fcm_c2f_of(ctx);
   // h = a   (PISO :84): the momentum matrix calcuvw left behind
   FC_CUDA(cudaMemcpyAsync(ctx->hcoef, fl[FC_A], sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDeviceToDevice, st));
   fc_calcp_opts co{};

@@ -9,27 +9,13 @@
 //   limiter                  CSR row 4 nnz + neighbour phi and centres 32 nnz + gradient 48 n
 // All HBM / L2-gather bound; FP64, no tensor cores.
 #include "fc_grad_body.cuh"
+#include "fc_body_views.cuh"
 #include "fc_reduce.cuh"
 
 int fc_grad_gauss_dev(fc_context *ctx, double *phi, double *grad, int nigrad);   // fc_assemble.cu
 
 namespace {
 
-fcm_geom geom_of(const fc_context *ctx) {
-  return fcm_geom{ctx->owner, ctx->neigh, ctx->xc, ctx->yc, ctx->zc, ctx->vol, ctx->arx, ctx->ary, ctx->arz,
-                  ctx->xf, ctx->yf, ctx->zf, ctx->facint, ctx->n, ctx->F};
-}
-fcm_c2f c2f_of(const fc_context *ctx) { return fcm_c2f{ctx->c2f_off, ctx->c2f_face, ctx->c2f_other, ctx->c2f_pos}; }
-fcm_slots slots_of(const fc_context *ctx) {
-  const fc_mesh_desc &m = ctx->m;
-  fcm_slots s;
-  const int cnt[5] = {m.ninl, m.nout, m.nsym, m.nwal, m.npru};
-  const int fst[5] = {m.iInletFacesStart, m.iOutletFacesStart, m.iSymmetryFacesStart, m.iWallFacesStart,
-                      m.iPressOutletFacesStart};
-  int slot = ctx->n + ctx->npro;
-  for (int b = 0; b < 5; ++b) { s.count[b] = cnt[b]; s.face[b] = fst[b]; s.slot[b] = slot; slot += cnt[b]; }
-  return s;
-}
 
 __global__ void __launch_bounds__(256) k_lsq_matrix(fcm_geom g, fcm_c2f m, int weighted, double *dmat) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,7 +82,7 @@ int fc_limit_gradient_dev(fc_context *ctx, const double *phi, double *grad) {
   FC_LAUNCH_CHECK();
   k_minmax_final<<<1, 1, 0, ctx->stream>>>(nb, ctx->partials, &ctx->sc->aux[0]);
   FC_LAUNCH_CHECK();
-  k_limiter<<<fc_blocks(ctx->n, 256), 256, 0, ctx->stream>>>(geom_of(ctx), ctx->ioffset, ctx->ja, ctx->diag,
+  k_limiter<<<fc_blocks(ctx->n, 256), 256, 0, ctx->stream>>>(fcm_geom_of(ctx), ctx->ioffset, ctx->ja, ctx->diag,
                                                              ctx->grad_limiter, phi, grad, &ctx->sc->aux[0],
                                                              ctx->grad_small);
   FC_LAUNCH_CHECK();
@@ -111,9 +97,9 @@ int fc_grad_dev(fc_context *ctx, double *phi, double *grad, int nigrad) {
     if (!ctx->has_mesh || !ctx->c2f_off) FC_FAIL(FC_ERR_ARG, "fc_grad: call fc_set_mesh and fc_create_csr first");
     const int B = 256, G = fc_blocks(ctx->n, B);
     if (ctx->grad_method == 2)
-      k_grad_lsq_qr<<<G, B, 0, ctx->stream>>>(geom_of(ctx), c2f_of(ctx), ctx->dmatqr, phi, grad);
+      k_grad_lsq_qr<<<G, B, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), ctx->dmatqr, phi, grad);
     else
-      k_grad_lsq<<<G, B, 0, ctx->stream>>>(geom_of(ctx), c2f_of(ctx), slots_of(ctx), ctx->grad_method == 3 ? 1 : 0,
+      k_grad_lsq<<<G, B, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), fcm_slots_of(ctx), ctx->grad_method == 3 ? 1 : 0,
                                            ctx->dmat, phi, grad);
     FC_LAUNCH_CHECK();
   }
@@ -133,14 +119,14 @@ int fc_set_gradient_dev(fc_context *ctx, int method, int limiter, double small) 
   const int B = 256, G = fc_blocks(ctx->n, B);
   if (method == 1 || method == 3) {
     FC_CHECK(fc_dev_alloc(ctx, &ctx->dmat, 9 * (size_t)ctx->n));
-    k_lsq_matrix<<<G, B, 0, ctx->stream>>>(geom_of(ctx), c2f_of(ctx), method == 3 ? 1 : 0, ctx->dmat);
+    k_lsq_matrix<<<G, B, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), method == 3 ? 1 : 0, ctx->dmat);
     FC_LAUNCH_CHECK();
   } else if (method == 2) {
     FC_CHECK(fc_dev_alloc(ctx, &ctx->dmatqr, 18 * (size_t)ctx->n));
     int *bad = nullptr, host_bad = 0;
     FC_CUDA(cudaMalloc((void **)&bad, sizeof(int)));
     FC_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
-    k_lsq_qr_matrix<<<fc_blocks(ctx->n, 128), 128, 0, ctx->stream>>>(geom_of(ctx), c2f_of(ctx), ctx->dmatqr, bad);
+    k_lsq_qr_matrix<<<fc_blocks(ctx->n, 128), 128, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), ctx->dmatqr, bad);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(&host_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);

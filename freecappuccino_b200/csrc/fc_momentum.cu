@@ -22,6 +22,7 @@
 //   component     row of a (8 nnz) + diag/ioffset 8 n + s, sp, phi, su, ap 40 n = 8 nnz + 48 n, x3
 // All HBM-bound; no tensor cores (FP64 gather work).
 #include "fc_momentum_body.cuh"
+#include "fc_body_views.cuh"
 #include "fc_reduce.cuh"
 
 // fc_assemble.cu
@@ -60,21 +61,6 @@ __global__ void k_halve(double *a, size_t n) {
   if (i < n) a[i] = 0.5 * a[i];
 }
 
-fcm_geom geom_of(const fc_context *ctx) {
-  return fcm_geom{ctx->owner, ctx->neigh, ctx->xc, ctx->yc, ctx->zc, ctx->vol, ctx->arx, ctx->ary, ctx->arz,
-                  ctx->xf, ctx->yf, ctx->zf, ctx->facint, ctx->n, ctx->F};
-}
-fcm_c2f c2f_of(const fc_context *ctx) { return fcm_c2f{ctx->c2f_off, ctx->c2f_face, ctx->c2f_other, ctx->c2f_pos}; }
-fcm_slots slots_of(const fc_context *ctx) {
-  const fc_mesh_desc &m = ctx->m;
-  fcm_slots s;
-  const int cnt[5] = {m.ninl, m.nout, m.nsym, m.nwal, m.npru};
-  const int fst[5] = {m.iInletFacesStart, m.iOutletFacesStart, m.iSymmetryFacesStart, m.iWallFacesStart,
-                      m.iPressOutletFacesStart};
-  int slot = ctx->n + ctx->npro;
-  for (int b = 0; b < 5; ++b) { s.count[b] = cnt[b]; s.face[b] = fst[b]; s.slot[b] = slot; slot += cnt[b]; }
-  return s;
-}
 fcm_flow flow_of(fc_context *ctx) {
   double **fl = ctx->field;
   return fcm_flow{fl[FC_U], fl[FC_V], fl[FC_W], fl[FC_P], fl[FC_DEN], fl[FC_VIS], fl[FC_FLMASS], fl[FC_FMI],
@@ -132,7 +118,7 @@ int fc_calcuvw_assemble_dev(fc_context *ctx, const fc_calcuvw_opts *o) {
     FC_CHECK(fc_bpres_dev(ctx, ctx->field[FC_P], ctx->field[FC_DPDXI], istage));
     FC_CHECK(fc_grad_dev(ctx, ctx->field[FC_P], ctx->field[FC_DPDXI], o->nigrad));
   }
-  const fcm_geom g = geom_of(ctx);
+  const fcm_geom g = fcm_geom_of(ctx);
   const fcm_flow f = flow_of(ctx);
   const fcm_opts fo = opts_of(o);
   const fcm_faces fa = faces_of(ctx);
@@ -147,7 +133,7 @@ int fc_calcuvw_assemble_dev(fc_context *ctx, const fc_calcuvw_opts *o) {
     k_uvw_proc_faces<<<fc_blocks(ctx->npro, B), B, 0, st>>>(g, f, fo, P);   // (grad exchanges them), vis: the caller's
     FC_LAUNCH_CHECK();
   }
-  k_uvw_rows<<<fc_blocks(ctx->n, B), B, 0, st>>>(g, c2f_of(ctx), slots_of(ctx), f, fo, fa, P, r);
+  k_uvw_rows<<<fc_blocks(ctx->n, B), B, 0, st>>>(g, fcm_c2f_of(ctx), fcm_slots_of(ctx), f, fo, fa, P, r);
   FC_LAUNCH_CHECK();
   if (o->cn) {
     k_halve<<<fc_blocks((size_t)ctx->nnz, B), B, 0, st>>>(fl[FC_A], (size_t)ctx->nnz);
@@ -173,7 +159,7 @@ int fc_calcuvw_component_dev(fc_context *ctx, const fc_calcuvw_opts *o, int comp
   fcm_comp k{ctx->ioffset, ctx->diag, fl[FC_A], fl[s_f[comp]], fl[sp_f[comp]], fl[FC_SU], fl[ap_f[comp]],
              fl[phi_f[comp]], fl[old_f[comp]], fl[FC_DEN], 1.0 / o->urf[comp], 1.0 - o->urf[comp],   // init.f90:80-81
              o->sol.small, o->timestep, o->cn, comp > 0 ? 1 : 0, ctx->nranks > 1 ? 1 : 0, ctx->npro, fl[FC_APR]};
-  k_uvw_component<<<fc_blocks(ctx->n, 256), 256, 0, ctx->stream>>>(geom_of(ctx), c2f_of(ctx), k);
+  k_uvw_component<<<fc_blocks(ctx->n, 256), 256, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), k);
   FC_LAUNCH_CHECK();
   fc_solver_opts so = o->sol;
   so.sor = o->sor[comp];
