@@ -534,6 +534,16 @@ int fc_grad(fc_context *ctx, int phi_field, int grad_field, int nigrad) {
   return fc_grad_dev(ctx, ctx->field[phi_field], ctx->field[grad_field], nigrad);
 }
 
+int fc_dpcg(fc_context *ctx, int fi_field, const fc_solver_opts *o, fc_solver_report *rep) {
+  return fc_solve(ctx, FC_DPCG, fi_field, o, rep);
+}
+int fc_iccg(fc_context *ctx, int fi_field, const fc_solver_opts *o, fc_solver_report *rep) {
+  return fc_solve(ctx, FC_ICCG, fi_field, o, rep);
+}
+int fc_bicgstab(fc_context *ctx, int fi_field, const fc_solver_opts *o, fc_solver_report *rep) {
+  return fc_solve(ctx, FC_BICGSTAB, fi_field, o, rep);
+}
+
 int fc_piso(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep) {
   if (!ctx || !o || !rep) return FC_ERR_ARG;
   FC_CUDA(cudaSetDevice(ctx->device));

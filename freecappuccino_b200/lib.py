@@ -41,7 +41,7 @@ SYMBOLS = (
     "fc_solve_csr", "fc_calcp_assemble", "fc_calcp", "fc_calcp_host", "fc_exchange", "fc_global_sum",
     "fc_get_timings", "fc_time_spmv", "fc_stream", "fc_copy", "fc_set_spmv_sampling", "fc_comm_p2p_blob",
     "fc_comm_p2p_open", "fc_set_tuning", "fc_calcuvw_assemble", "fc_calcuvw_component", "fc_calcuvw",
-    "fc_calcuvw_host", "fc_piso", "fc_set_gradient", "fc_grad",
+    "fc_calcuvw_host", "fc_piso", "fc_set_gradient", "fc_grad", "fc_dpcg", "fc_iccg", "fc_bicgstab",
 )
 GRAD_METHODS = {"gauss": 0, "lstsq": 1, "lstsq_qr": 2, "lstsq_dm": 3}
 LIMITERS = {"no-limit": 0, "Barth-Jespersen": 1, "Venkatakrishnan": 2, "mVenkatakrishnan": 3}
@@ -354,6 +354,22 @@ class Context:
     def solve(self, solver: str, fi: str, opts: SolverOpts) -> SolverReport:
         rep = SolverReport()
         self._ck(self.lib.fc_solve(self.h, SOLVERS[solver], F[fi], C.byref(opts), C.byref(rep)))
+        return rep
+
+    def dpcg(self, fi: str, opts: SolverOpts) -> SolverReport:
+        """``call dpcg(fi,ifi)`` on a device-resident field (fc_dpcg)."""
+        rep = SolverReport()
+        self._ck(self.lib.fc_dpcg(self.h, F[fi], C.byref(opts), C.byref(rep)))
+        return rep
+
+    def iccg(self, fi: str, opts: SolverOpts) -> SolverReport:
+        rep = SolverReport()
+        self._ck(self.lib.fc_iccg(self.h, F[fi], C.byref(opts), C.byref(rep)))
+        return rep
+
+    def bicgstab(self, fi: str, opts: SolverOpts) -> SolverReport:
+        rep = SolverReport()
+        self._ck(self.lib.fc_bicgstab(self.h, F[fi], C.byref(opts), C.byref(rep)))
         return rep
 
     def solve_host(self, solver: str, a: np.ndarray, su: np.ndarray, fi: np.ndarray, opts: SolverOpts,

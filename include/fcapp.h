@@ -175,6 +175,13 @@ typedef struct {
 int fc_solve(fc_context *ctx, int solver, int fi_field, const fc_solver_opts *o,
              fc_solver_report *rep);
 
+/* The same under the reference's own subroutine names: dpcg(fi,ifi) (src/dpcg.f90:3),
+ * iccg(fi,ifi) (src/iccg.f90:3), bicgstab(fi,ifi) (src/bicgstab.f90:1); sor(ifi), nsw(ifi)
+ * travel in `o`.                                                                   */
+int fc_dpcg(fc_context *ctx, int fi_field, const fc_solver_opts *o, fc_solver_report *rep);
+int fc_iccg(fc_context *ctx, int fi_field, const fc_solver_opts *o, fc_solver_report *rep);
+int fc_bicgstab(fc_context *ctx, int fi_field, const fc_solver_opts *o, fc_solver_report *rep);
+
 /* Host-buffer form, the drop-in body of `subroutine dpcg(fi,ifi)` when the
  * matrix lives in the Fortran module arrays: uploads a(nnz), su(numCells),
  * fi(numTotal), solves, downloads fi(1:numCells) and res(numCells).  All

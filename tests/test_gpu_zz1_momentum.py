@@ -333,3 +333,24 @@ def test_calcuvw_edge_meshes_bit_exact(fc, make):
         got = ctx.download(fld)[:ref.size]
         assert np.array_equal(got, ref), (fld, float(np.abs(got - ref).max()))
     ctx.close()
+
+
+@pytest.mark.parametrize("solver", ["dpcg", "iccg", "bicgstab"])
+def test_named_solver_entry_points(fc, solver):
+    """fc_dpcg / fc_iccg / fc_bicgstab (the reference's subroutine names) are fc_solve with the solver fixed."""
+    mesh = cases.hex_case(8, 7, 6, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry"))
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    su = cases.poisson_rhs(mesh)
+    ctx.upload("APU", -np.ones(mesh.numCells))
+    out = []
+    for call in (lambda o: ctx.solve(solver, "PP", o), lambda o: getattr(ctx, solver)("PP", o)):
+        ctx.upload("SU", su)
+        ctx.fill("PP", 0.0)
+        ctx.laplacian("APU", "PP")
+        rep = call(fc.solver_opts(1e-8, 500))
+        out.append((rep.iters, rep.res0, rep.resl, ctx.download("PP")))
+    assert out[0][0] == out[1][0] > 0 and out[0][1] == out[1][1] and out[0][2] == out[1][2]
+    assert np.array_equal(out[0][3], out[1][3])
+    ctx.close()
