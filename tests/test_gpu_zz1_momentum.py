@@ -354,3 +354,35 @@ def test_named_solver_entry_points(fc, solver):
     assert out[0][0] == out[1][0] > 0 and out[0][1] == out[1][1] and out[0][2] == out[1][2]
     assert np.array_equal(out[0][3], out[1][3])
     ctx.close()
+
+
+def test_gpu_simple_loop_reproduces_ghia_re100(fc):
+    """The device-resident SIMPLE loop (fc_calcuvw + fc_calcp, no field leaves the GPU between iterations) run to
+    convergence on the 20 x 20 lid-driven cavity at Re = 100, compared directly with the benchmark table of Ghia, Ghia &
+    Shin (1982) -- an oracle-independent check of the CUDA path -- and with the oracle's converged field."""
+    from test_oracle_ghia import cavity_mesh, centreline_error, lid_slots, simple_to_convergence
+    n = 20
+    mesh = cavity_mesh(n)
+    nt = mesh.numTotal
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    u0 = np.zeros(nt)
+    u0[lid_slots(mesh)] = 1.0
+    ctx.upload("U", u0)
+    ctx.upload("VIS", np.full(nt, 0.01))
+    uo = fc.calcuvw_opts(scheme="muscl-f", urf=(0.7,) * 3, sor=(1e-2,) * 3, nsw=(20,) * 3, bdf=True, btime=0.0,
+                         timestep=1e20, viscos=0.01)
+    po = fc.calcp_opts(solver="iccg", sor=1e-2, nsw=100, urf_p=0.3, pRefCell=1)
+    for it in range(1, 3001):
+        ru = ctx.calcuvw(uo)
+        rp = ctx.calcp(po)
+        if max(ru.rep[0].res0, ru.rep[1].res0, rp.rep[0].res0) < 1e-7:
+            break
+    u = ctx.download("U")
+    err, umin = centreline_error(mesh, n, u)
+    assert it < 3000 and err < 0.02 and abs(umin + 0.2109) < 0.01
+    _, of, it_o = simple_to_convergence(n)
+    assert abs(it - it_o) <= max(3, it_o // 100)      # hundreds of loosely converged solves: a few iterations of slack
+    assert cases.rel_l2(u[:mesh.numCells], of.u[:mesh.numCells]) < 1e-5
+    ctx.close()
