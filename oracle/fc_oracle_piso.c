@@ -13,6 +13,8 @@
  * Parity status: UNPINNED (the reference stores no outputs of these routines); checked by properties in
  * tests/test_oracle_piso.py.
  *
+ * H(u) of get_rAU_x_UEqnH keeps only the unsteady, buoyancy and neighbour terms (get_rAU_x_UEqnH.f90:24-200): the
+ * wall-shear / inlet / deferred-correction sources of calcuvw are not carried over.  Restated as written.
  * Quirks kept: only the ROW of pRefCell is cleared (the column entries stay, so iccg works on a matrix that
  * is no longer symmetric, PISO :188-192); the final flux correction reads a(icell_jcell) from that matrix, so
  * faces owned by pRefCell get no correction (:262); pp is not reset between correctors (:199-200);
