@@ -58,3 +58,44 @@ def test_lid_driven_cavity_re100_matches_ghia():
         assert abs(umin - (-0.2109)) < (0.01 if n == 20 else 0.002)
     assert errs[20] < 0.02 and errs[40] < 0.006
     assert errs[20] / errs[40] > 3.0        # second-order convergence towards the benchmark
+
+
+def poiseuille(nx, ny, maxit=4000):
+    """Plane Poiseuille flow, Re = 10: parabolic inlet profile, outlet, two walls.  Exercises the inlet / outlet
+    branches of calcuvw (facefluxuvw_boundary) and calcp (adjustMassFlow, outlet extrapolation and scaling)."""
+    lx, h, nu = 3.0, 1.0, 0.1
+    mesh = M.hex_mesh(nx, ny, 1, (lx, h, h / ny), ("inlet", "outlet", "wall", "wall", "symmetry", "symmetry"))
+    nc = mesh.numCells
+    csr = oracle.create_csr(mesh)
+    of = oracle.Fields(mesh, csr.nnz)
+    fs, sl = mesh.boundary_faces("inlet"), mesh.boundary_slots("inlet")
+    of.u[sl] = 6.0 * mesh.yf[fs] * (1.0 - mesh.yf[fs])
+    of.u[:nc] = 1.0
+    of.fmi[:len(fs)] = of.den[sl] * of.u[sl] * mesh.arx[fs]          # bcin.f90: fmi = den (U . S), negative = inflow
+    flomas = float(-of.fmi[:len(fs)].sum())
+    F = mesh.numInnerFaces
+    o, nb = mesh.owner[:F] - 1, mesh.neighbour - 1
+    of.flmass[:] = 0.5 * (of.u[o] + of.u[nb]) * mesh.arx[:F]
+    x = oracle.UvwFields(mesh, of, nu)
+    oo = oracle.uvw_opts(scheme="muscl-f", urf=(0.7,) * 3, sor=(1e-2,) * 3, nsw=(20,) * 3, bdf=True, timestep=1e20, viscos=nu)
+    po = oracle.calcp_opts(solver="iccg", sor=1e-2, nsw=100, urf_p=0.3, pRefCell=1, flomas=flomas)
+    for it in range(1, maxit + 1):
+        ru = oracle.calcuvw(mesh, csr, of, x, oo)
+        rp = oracle.calcp(mesh, csr, of, po)
+        if max(ru.rep[0].res0, ru.rep[1].res0, rp.rep[0].res0) < 1e-8:
+            break
+    U, P = of.u[:nc].reshape(ny, nx), of.p[:nc].reshape(ny, nx)
+    yc, xc = mesh.yc[:nc].reshape(ny, nx)[:, 0], mesh.xc[:nc].reshape(ny, nx)[0, :]
+    i = nx // 2
+    err = float(np.abs(U[:, i] - 6.0 * yc * (1.0 - yc)).max())
+    dpdx = float((P[ny // 2, i + 2] - P[ny // 2, i - 2]) / (xc[i + 2] - xc[i - 2]))
+    return it, err, dpdx
+
+
+def test_plane_poiseuille_flow_is_second_order():
+    """Analytic solution: u = 6 y (1 - y), dp/dx = -12 nu U / H^2 = -1.2."""
+    it1, e1, g1 = poiseuille(15, 10)
+    it2, e2, g2 = poiseuille(30, 20)
+    assert it1 < 4000 and it2 < 4000
+    assert e1 < 0.025 and e2 < 0.007 and e1 / e2 > 3.0
+    assert abs(g1 + 1.2) < 0.04 and abs(g2 + 1.2) < 0.01
