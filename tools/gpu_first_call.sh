@@ -1,0 +1,21 @@
+#!/usr/bin/env bash
+# First gpurun call of a round (1 GPU, about 6-8 minutes):
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_first_call.sh'
+# Runs the GPU test suite, the per-operation roofline table, the bench line, the ncu launch list of the bench and one
+# full ncu capture of the assembly / momentum / sweep kernels; everything lands in gpurun_out/ (copy what should be
+# judged into profiles/).
+set -u
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
+timeout 600 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+timeout 200 python tools/kernel_bench.py 216 10 > gpurun_out/kernel_bench_216.jsonl 2> gpurun_out/kernel_bench.err
+timeout 120 python tools/simple_iter_bench.py 216 2 3 > gpurun_out/simple_iter_216.json 2>&1
+timeout 300 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+tail -c 600 gpurun_out/bench_n1.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_simple.csv \
+    python tools/simple_iter_bench.py 128 1 1 > gpurun_out/ncu_launches.log 2>&1
+python tools/ncu_summary.py gpurun_out/launches_simple.csv > gpurun_out/launches_simple.txt 2>/dev/null
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_uvw_faces|k_uvw_rows|k_calcp_faces|k_grad_pass|k_rows_gather|k_tri_sweep' \
+    -c 12 -o gpurun_out/prof_assembly python tools/simple_iter_bench.py 128 0 1 > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out | tail -20
