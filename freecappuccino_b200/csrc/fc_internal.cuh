@@ -82,7 +82,15 @@ struct fc_levels {                      // level schedule of the strict lower / 
   unsigned int *ready = nullptr;        // [nlev] number of the last sweep whose level is complete
   unsigned int *ticket = nullptr;       // dynamic block id
   unsigned long long epoch = 0;         // sweeps run so far
+  // point-to-point mode (FC_TUNE_SWEEP_P2P): a block waits for the flags of the blocks it gathers from instead of
+  // for the whole previous level
+  int nblocks = 0;
+  int *prod = nullptr;                  // [nblocks * FC_TRI_MAXP] producer blocks
+  int *prod_cnt = nullptr;              // [nblocks]
+  unsigned int *flag = nullptr;         // [nblocks] number of the last sweep whose rows the block has published
+  bool p2p_ok = false;                  // every block has <= FC_TRI_MAXP producers
 };
+constexpr int FC_TRI_MAXP = 16;
 
 struct fc_context {
   int device = 0;
@@ -161,6 +169,7 @@ struct fc_context {
   int tune_persist = 1;                 // 1: DPCG as one persistent cooperative kernel
   int tune_pipe = 1;                    // staging geometry of the TMA pipeline (threads, capacity, stages)
   int tune_ctas_per_sm = 0;             // persistent kernel: CTAs per SM (0 = as many as fit)
+  int tune_sweep_p2p = 0;               // triangular sweeps: 1 = point-to-point block flags instead of level counters
   fc_persist_state *persist = nullptr;  // device: grid barrier + phase clocks of the persistent kernel
   fc_persist_state *persist_host = nullptr;
 

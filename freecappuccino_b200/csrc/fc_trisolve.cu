@@ -11,6 +11,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "fc_internal.cuh"
+#include "fc_tma.cuh"
 
 constexpr int TRI_BLOCK = 128;
 
@@ -55,6 +56,50 @@ __global__ void k_level_place(const int *__restrict__ sorted_level, const int *_
 __global__ void k_fill(int *p, int v, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+}
+
+// ---- point-to-point mode: which blocks does a block gather from? ----
+__global__ void k_slot_of_row(const int *__restrict__ rows, int nslots, int *slot_of_row) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nslots && rows[s] >= 0) slot_of_row[rows[s]] = s;
+}
+
+// one CTA per block: the set of blocks holding the rows its own rows depend on (lock-free insertion into a small
+// shared table; more than FC_TRI_MAXP distinct producers raises `overflow` and the level counters stay in use)
+__global__ void __launch_bounds__(TRI_BLOCK)
+k_block_producers(const int *__restrict__ rows, const int *__restrict__ slot_of_row, const int *__restrict__ ioffset,
+                  const int *__restrict__ ja, const int *__restrict__ diag, int n, int lower, int *prod, int *prod_cnt,
+                  int *overflow) {
+  __shared__ int s_set[FC_TRI_MAXP];
+  __shared__ int s_over;
+  const int b = blockIdx.x;
+  if (threadIdx.x < FC_TRI_MAXP) s_set[threadIdx.x] = -1;
+  if (threadIdx.x == 0) s_over = 0;
+  __syncthreads();
+  const int row = rows[b * TRI_BLOCK + threadIdx.x];
+  if (row >= 0) {
+    const int s = lower ? ioffset[row] : diag[row] + 1;
+    const int e = lower ? diag[row] : ioffset[row + 1];
+    for (int k = s; k < e; ++k) {
+      const int j = ja[k];
+      if (j >= n) continue;
+      const int pb = slot_of_row[j] / TRI_BLOCK;
+      bool placed = false;
+      for (int i = 0; i < FC_TRI_MAXP && !placed; ++i) {
+        const int old = atomicCAS(&s_set[i], -1, pb);
+        placed = (old == -1 || old == pb);
+      }
+      if (!placed) s_over = 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int i = 0; i < FC_TRI_MAXP; ++i)
+      if (s_set[i] >= 0) prod[b * FC_TRI_MAXP + c++] = s_set[i];
+    prod_cnt[b] = c;
+    if (s_over) atomicExch(overflow, 1);
+  }
 }
 
 int build_one(fc_context *ctx, fc_levels &L, int lower) {
@@ -139,7 +184,25 @@ int build_one(fc_context *ctx, fc_levels &L, int lower) {
   FC_CUDA(cudaMemsetAsync(L.ready, 0, sizeof(unsigned int) * (size_t)nlev, ctx->stream));
   FC_CUDA(cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), ctx->stream));
   L.epoch = 0;
+  // producer tables of the point-to-point mode
+  L.nblocks = nblocks;
+  int *slot_of_row = nullptr, *overflow = nullptr, h_over = 0;
+  FC_CHECK(fc_dev_alloc(ctx, &slot_of_row, (size_t)n));
+  FC_CHECK(fc_dev_alloc(ctx, &overflow, 1));
+  FC_CHECK(fc_dev_alloc(ctx, &L.prod, (size_t)nblocks * FC_TRI_MAXP));
+  FC_CHECK(fc_dev_alloc(ctx, &L.prod_cnt, (size_t)nblocks));
+  FC_CHECK(fc_dev_alloc(ctx, &L.flag, (size_t)nblocks));
+  FC_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), ctx->stream));
+  FC_CUDA(cudaMemsetAsync(L.flag, 0, sizeof(unsigned int) * (size_t)nblocks, ctx->stream));
+  k_slot_of_row<<<fc_blocks(L.nslots, B), B, 0, ctx->stream>>>(L.rows, L.nslots, slot_of_row);
+  FC_LAUNCH_CHECK();
+  k_block_producers<<<nblocks, TRI_BLOCK, 0, ctx->stream>>>(L.rows, slot_of_row, ctx->ioffset, ctx->ja, ctx->diag, n,
+                                                            lower, L.prod, L.prod_cnt, overflow);
+  FC_LAUNCH_CHECK();
+  FC_CUDA(cudaMemcpyAsync(&h_over, overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   FC_CUDA(cudaStreamSynchronize(ctx->stream));
+  L.p2p_ok = (h_over == 0);
+  cudaFree(slot_of_row); cudaFree(overflow);
   cudaFree(level); cudaFree(changed); cudaFree(rowid); cudaFree(slevel); cudaFree(srow); cudaFree(hist);
   cudaFree(dstart); cudaFree(dslot);
   return FC_OK;
@@ -168,10 +231,15 @@ constexpr int TRI_PRE = 4;  // matrix entries of a row fetched before the wait (
 // store -> CTA barrier -> one acq_rel atomic per CTA; the CTA that completes the level publishes
 // ready[lev].  Everything that does not depend on other rows (row bounds, d, r and the first TRI_PRE
 // matrix entries) is already in registers when the wait ends.
-template <int MODE>
+// P2P = true (FC_TUNE_SWEEP_P2P): instead of the level counter a block waits for the flags of the (at most FC_TRI_MAXP)
+// blocks it gathers from and publishes its own flag -- no atomic on the critical path and no barrier across a level.
+// Tickets are drawn in block order and a block only depends on blocks with smaller numbers, so a resident block never
+// waits for one that has not started; the waits are bounded (fc_spin_guard traps) all the same.
+template <int MODE, bool P2P>
 __global__ void __launch_bounds__(TRI_BLOCK)
 k_tri_sweep(const int *__restrict__ rows, const int *__restrict__ blk_level,
             const int *__restrict__ lev_blocks_before, unsigned int *done, unsigned int *ready, unsigned int *ticket,
+            const int *__restrict__ prod, const int *__restrict__ prod_cnt, unsigned int *flag,
             unsigned int ticket_base, unsigned int sweep_no, const int *__restrict__ ioffset,
             const int *__restrict__ ja, const int *__restrict__ diag, const int *__restrict__ tpos,
             const double *__restrict__ a, const double *__restrict__ d, const double *__restrict__ in,
@@ -203,7 +271,15 @@ k_tri_sweep(const int *__restrict__ rows, const int *__restrict__ blk_level,
     else if (MODE == TRI_BWD) { di = d[row]; v = in[row] / (di + small); }   // z = z/(d+small), iccg.f90:102
     else v = a[diag[row]];
   }
-  if (lev > 0) {
+  if (P2P) {
+    const int np = prod_cnt[b];
+    if ((int)threadIdx.x < np) {
+      const unsigned int *r = flag + prod[b * FC_TRI_MAXP + threadIdx.x];
+      fc_spin_guard g;
+      while (ld_acquire(r) < sweep_no) g.tick();
+    }
+    if (np > 0) __syncthreads();
+  } else if (lev > 0) {
     if (threadIdx.x == 0) {
       const unsigned int *r = ready + (lev - 1);
       while (ld_acquire(r) < sweep_no) {}
@@ -239,10 +315,14 @@ k_tri_sweep(const int *__restrict__ rows, const int *__restrict__ blk_level,
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    // release this CTA's rows; the CTA that completes the level has acquired every other CTA's release
-    const unsigned int nb = (unsigned int)(lev_blocks_before[lev + 1] - lev_blocks_before[lev]);
-    const unsigned int old = atom_add_acq_rel(done + lev, 1u);
-    if (old + 1u == sweep_no * nb) st_release(ready + lev, sweep_no);
+    if (P2P) {
+      st_release(flag + b, sweep_no);   // this CTA's rows are ordered before it by the barrier above
+    } else {
+      // release this CTA's rows; the CTA that completes the level has acquired every other CTA's release
+      const unsigned int nb = (unsigned int)(lev_blocks_before[lev + 1] - lev_blocks_before[lev]);
+      const unsigned int old = atom_add_acq_rel(done + lev, 1u);
+      if (old + 1u == sweep_no * nb) st_release(ready + lev, sweep_no);
+    }
   }
 }
 
@@ -252,9 +332,16 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
   const int nblocks = L.nslots / TRI_BLOCK;
   const unsigned int base = (unsigned int)(L.epoch * (unsigned long long)nblocks);
   L.epoch++;
-  k_tri_sweep<MODE><<<nblocks, TRI_BLOCK, 0, ctx->stream>>>(
-      L.rows, L.blk_level, L.lev_blocks_before, L.done, L.ready, L.ticket, base, (unsigned int)L.epoch, ctx->ioffset,
-      ctx->ja, ctx->diag, ctx->tpos, a, d, in, out, small, padd, ctx->n, guarded ? ctx->sc : nullptr);
+  if (ctx->tune_sweep_p2p && L.p2p_ok)
+    k_tri_sweep<MODE, true><<<nblocks, TRI_BLOCK, 0, ctx->stream>>>(
+        L.rows, L.blk_level, L.lev_blocks_before, L.done, L.ready, L.ticket, L.prod, L.prod_cnt, L.flag, base,
+        (unsigned int)L.epoch, ctx->ioffset, ctx->ja, ctx->diag, ctx->tpos, a, d, in, out, small, padd, ctx->n,
+        guarded ? ctx->sc : nullptr);
+  else
+    k_tri_sweep<MODE, false><<<nblocks, TRI_BLOCK, 0, ctx->stream>>>(
+        L.rows, L.blk_level, L.lev_blocks_before, L.done, L.ready, L.ticket, L.prod, L.prod_cnt, L.flag, base,
+        (unsigned int)L.epoch, ctx->ioffset, ctx->ja, ctx->diag, ctx->tpos, a, d, in, out, small, padd, ctx->n,
+        guarded ? ctx->sc : nullptr);
   FC_LAUNCH_CHECK();
   return FC_OK;
 }
@@ -263,7 +350,7 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
 
 void fc_levels_free(fc_levels &L) {
   cudaFree(L.rows); cudaFree(L.blk_level); cudaFree(L.lev_blocks_before); cudaFree(L.done); cudaFree(L.ready);
-  cudaFree(L.ticket);
+  cudaFree(L.ticket); cudaFree(L.prod); cudaFree(L.prod_cnt); cudaFree(L.flag);
   L = fc_levels{};
 }
 
@@ -281,6 +368,7 @@ int fc_levels_reset(fc_context *ctx) {
     FC_CUDA(cudaMemsetAsync(L->done, 0, sizeof(unsigned int) * (size_t)L->nlev, ctx->stream));
     FC_CUDA(cudaMemsetAsync(L->ready, 0, sizeof(unsigned int) * (size_t)L->nlev, ctx->stream));
     FC_CUDA(cudaMemsetAsync(L->ticket, 0, sizeof(unsigned int), ctx->stream));
+    if (L->flag) FC_CUDA(cudaMemsetAsync(L->flag, 0, sizeof(unsigned int) * (size_t)L->nblocks, ctx->stream));
     L->epoch = 0;
   }
   return FC_OK;

@@ -340,8 +340,11 @@ enum {
   FC_TUNE_DPCG_PERSISTENT = 1, /* 0 one launch per vector op, [1] whole DPCG loop
                                   as one persistent cooperative kernel            */
   FC_TUNE_CTAS_PER_SM = 2,     /* persistent kernel: CTAs per SM, [0] = all that fit */
-  FC_TUNE_PIPE_GEOMETRY = 3    /* TMA pipeline (threads, non-zeros staged, stages):
+  FC_TUNE_PIPE_GEOMETRY = 3,   /* TMA pipeline (threads, non-zeros staged, stages):
                                   0 256/2304/3, [1] 256/2304/2, 2 256/2048/2, 3 128/1024/2 */
+  FC_TUNE_SWEEP_P2P = 4        /* triangular sweeps (iccg, bicgstab): [0] one counter per level,
+                                  1 point-to-point flags between 128-row blocks (experimental:
+                                  same row sums, bit-identical results)                      */
 };
 int fc_set_tuning(fc_context *ctx, int key, int value);
 /* Bracket up to `max_samples` SpMV launches of every following solve with CUDA

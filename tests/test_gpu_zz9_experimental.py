@@ -1,0 +1,60 @@
+"""Opt-in checks of experimental kernel variants that are OFF by default (fc_set_tuning).  They have not run on
+hardware yet, so the default `pytest -m gpu` skips them; enable with FCAPP_EXPERIMENTAL=1.
+
+FC_TUNE_SWEEP_P2P: point-to-point block flags instead of one counter per level in the DIC / DILU triangular sweeps
+(fc_trisolve.cu).  The row sums are unchanged, so every iterate must be bit-identical to the default mode."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from freecappuccino_b200 import cases
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("FCAPP_EXPERIMENTAL") != "1", reason="set FCAPP_EXPERIMENTAL=1")]
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MESHES = {
+    "hex": lambda: cases.hex_case(40, 36, 30, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry")),
+    "poly": lambda: cases.poly_case(10),
+    "pitzDaily": lambda: cases.golden_mesh(os.path.join(GOLD, "pitzDaily.npz")),
+    "slab": lambda: cases.hex_case(60, 60, 1, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry")),
+}
+
+
+@pytest.fixture(scope="module")
+def fc():
+    from freecappuccino_b200 import lib
+    return lib
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+@pytest.mark.parametrize("solver", ["iccg", "bicgstab"])
+def test_p2p_sweeps_are_bit_identical_to_level_sweeps(fc, name, solver):
+    mesh = MESHES[name]()
+    su = np.random.default_rng(5).standard_normal(mesh.numCells) * mesh.vol[:mesh.numCells]
+    res = []
+    for p2p in (0, 1):
+        ctx = fc.Context(0)
+        ctx.set_mesh(mesh)
+        ctx.create_csr(download=False)
+        ctx.set_tuning(fc.TUNE_SWEEP_P2P, p2p)
+        ctx.upload("APU", -np.ones(mesh.numCells))
+        ctx.upload("SU", su)
+        ctx.fill("PP", 0.0)
+        ctx.laplacian("APU", "PP")
+        best = None
+        for rep_i in range(3):
+            ctx.fill("PP", 0.0)
+            t0 = time.perf_counter()
+            rep = ctx.solve(solver, "PP", fc.solver_opts(1e-9, 300))
+            wall = time.perf_counter() - t0
+            ms = ctx.timings().solve_ms
+            best = ms if best is None else min(best, ms)
+        res.append((rep.iters, rep.res0, rep.resl, ctx.download("PP"), ctx.download("RES"), best))
+        ctx.close()
+    (i0, a0, b0, x0, r0, t0), (i1, a1, b1, x1, r1, t1) = res
+    print(f"\\n[p2p sweeps] {name} {solver}: {i0} iterations, level mode {t0:.3f} ms, p2p mode {t1:.3f} ms")
+    assert i0 == i1 and a0 == a1 and b0 == b1
+    assert np.array_equal(x0, x1) and np.array_equal(r0, r1)
