@@ -38,6 +38,8 @@ def stats(name, mesh):
     prod = [set() for _ in range(nblocks)]
     for c, p in zip(block_of[hi], block_of[lo]):
         prod[c].add(p)
+    # deadlock freedom of the ticket scheme: a block only waits for blocks with smaller numbers (drawn earlier)
+    assert all(p < b for b, s in enumerate(prod) for p in s)
     k = np.array([len(s) for s in prod])
     back = np.array([max((b - min(s)) if s else 0 for b, s in [(b, prod[b])]) for b in range(nblocks)])
     blk_level = np.repeat(np.arange(nlev), blocks_per_level)
