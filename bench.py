@@ -254,6 +254,10 @@ def run_ours(args):
     ctx.set_spmv_sampling(512)
     if args.no_persist:
         ctx.set_tuning(lib.TUNE_DPCG_PERSISTENT, 0)
+    if args.ctas_per_sm > 0:      # A/B knobs of the persistent kernel (library defaults otherwise)
+        ctx.set_tuning(lib.TUNE_CTAS_PER_SM, args.ctas_per_sm)
+    if args.pipe >= 0:
+        ctx.set_tuning(lib.TUNE_PIPE_GEOMETRY, args.pipe)
     stream = torch.cuda.ExternalStream(ctx.lib.fc_stream(ctx.h), device=torch.device("cuda", local))
 
     def restore():  # device-to-device: the step always starts from the same fields
@@ -444,6 +448,8 @@ def main():
                     "src-parallel build, capped by the host's core count")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-simple", action="store_true", help="skip the SIMPLE-iteration (calcuvw + calcp) timing")
+    ap.add_argument("--ctas-per-sm", type=int, default=0, help="persistent DPCG kernel: CTAs per SM (0 = library default)")
+    ap.add_argument("--pipe", type=int, default=-1, help="TMA pipeline geometry 0..3 (-1 = library default)")
     ap.add_argument("--no-persist", action="store_true", help="one launch per vector operation instead of the "
                     "persistent DPCG kernel (A/B)")
     args = ap.parse_args()
