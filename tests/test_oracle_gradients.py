@@ -122,3 +122,19 @@ def test_dispatcher_drives_calcp():
     oracle.slope_limiter(mesh, csr, "mVenkatakrishnan", f["u"], g)
     assert np.array_equal(b.dUdxi, g)
     assert not np.array_equal(a.su, b.su)
+
+
+def test_simple_loop_with_lsq_qr_gradients_reproduces_ghia():
+    """The QR least-squares gradient (DGEQR2 restatement) drives the whole SIMPLE loop to the same benchmark solution
+    as the Gauss gradient; the normal-equation variants, whose y-component is computed as written in
+    grad_lsq.f90:303, do not -- evidence that the restated quirk is what the formula does, not a transcription slip."""
+    import test_oracle_ghia as G
+    err = {}
+    for method in ("lstsq_qr", "lstsq"):
+        mesh = G.cavity_mesh(20)
+        oracle.set_gradient(method, "no-limit", mesh)
+        mesh, of, it = G.simple_to_convergence(20)
+        err[method], _ = G.centreline_error(mesh, 20, of.u)
+        oracle.set_gradient("gauss", "no-limit")
+    assert err["lstsq_qr"] < 0.025
+    assert err["lstsq"] > 0.05
