@@ -80,3 +80,20 @@ def test_written_ranks_are_readable_by_the_cpp_reader(tmp_path):
         own = M.read_polymesh(pm)
         assert np.allclose(own.vol, p.vol[:p.numCells], rtol=1e-11)
         assert np.allclose(own.arx, p.arx, atol=1e-15) and np.allclose(own.xf, p.xf, atol=1e-14)
+
+
+def test_decompose_cli_on_the_shipped_cavity_mesh(tmp_path):
+    import sys
+    d = np.load(os.path.join(GOLD, "cavity.npz"))
+    patches = [(str(k), int(nf), int(st)) for k, nf, st in zip(d["bkind"], d["bn"], d["bstart"])]
+    M.write_polymesh(os.path.join(str(tmp_path), "polyMesh"), d["points"], d["faces"], d["owner"], d["neighbour"], patches)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "decompose.py"), str(tmp_path), "4"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    cells = 0
+    for r in range(4):
+        own = M.read_polymesh_rank(os.path.join(str(tmp_path), f"processor{r}", "constant", "polyMesh")) \
+            if hasattr(M, "read_polymesh_rank") else None
+        cellproc = labels(os.path.join(str(tmp_path), f"processor{r}", "constant", "polyMesh", "cellProcAddressing"))
+        cells += cellproc.size
+    assert cells == 400 and out.stdout.count("processor") == 4
