@@ -92,8 +92,6 @@ def test_decompose_cli_on_the_shipped_cavity_mesh(tmp_path):
     assert out.returncode == 0, out.stderr
     cells = 0
     for r in range(4):
-        own = M.read_polymesh_rank(os.path.join(str(tmp_path), f"processor{r}", "constant", "polyMesh")) \
-            if hasattr(M, "read_polymesh_rank") else None
         cellproc = labels(os.path.join(str(tmp_path), f"processor{r}", "constant", "polyMesh", "cellProcAddressing"))
         cells += cellproc.size
-    assert cells == 400 and out.stdout.count("processor") == 4
+    assert cells == 400 and len(out.stdout.strip().splitlines()) == 4
