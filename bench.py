@@ -417,19 +417,22 @@ def run_ours(args):
         out["cpu_baseline"] = {"value": v, "unit": "iter/s", "cores": 1, "kind": "port",
                                "sample": f"{used} DPCG iterations of the same {args.n}^3 system (oracle, serial src "
                                          f"semantics, {dt:.1f} s)"}
+    ctx.close()
     if world == 1 and not args.no_simple:
         # one whole device-resident SIMPLE iteration (calcuvw -> calcp) on the same mesh, the "SIMPLE iter time" of
-        # BASELINE.json's metric: momentum predictor + this path, no field crossing PCIe
+        # BASELINE.json's metric: momentum predictor + this path, no field crossing PCIe.  Run in
+        # its own process (tools/simple_iter_bench.py) so that the headline line cannot depend on the widened step.
         try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            from simple_iter_bench import measure
-            ctx.set_spmv_sampling(0)
-            out["simple_iteration"] = measure(ctx, mesh, warm=2, steps=3)
-        except Exception as e:   # the headline line must not depend on the widened step
+            import subprocess
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "simple_iter_bench.py"), str(args.n), "2", "3"],
+                               capture_output=True, text=True, timeout=240)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            out["simple_iteration"] = json.loads(lines[-1]) if r.returncode == 0 and lines else \
+                {"error": f"exit {r.returncode}: {r.stderr[-300:]}"}
+        except Exception as e:
             out["simple_iteration"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(out))
-    ctx.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
