@@ -215,6 +215,28 @@ int fc_set_mesh(fc_context *ctx, const fc_mesh_desc *m) {
     FC_FAIL(FC_ERR_ARG, "fc_set_mesh: NULL geometry array");
   if (m->npro > 0 && (!m->fpro || !m->neighbProcNo || !m->neighbProcOffset || m->numConnections < 1))
     FC_FAIL(FC_ERR_ARG, "fc_set_mesh: processor boundary without fpro / neighbProcNo / neighbProcOffset");
+  // every kernel indexes with these arrays unchecked: reject a mesh that would send them out of bounds
+  {
+    const int nb = m->ninl + m->nout + m->nsym + m->nwal + m->npru;
+    if (m->ninl < 0 || m->nout < 0 || m->nsym < 0 || m->nwal < 0 || m->npru < 0 || m->npro < 0 ||
+        m->numTotal < m->numCells + m->npro + nb)
+      FC_FAIL(FC_ERR_ARG, "fc_set_mesh: numTotal is smaller than numCells + npro + the boundary face counts");
+    const struct { const char *name; int start, count; } patch[] = {
+        {"processor", m->iProcFacesStart, m->npro},   {"inlet", m->iInletFacesStart, m->ninl},
+        {"outlet", m->iOutletFacesStart, m->nout},    {"symmetry", m->iSymmetryFacesStart, m->nsym},
+        {"wall", m->iWallFacesStart, m->nwal},        {"prOutlet", m->iPressOutletFacesStart, m->npru}};
+    for (const auto &pt : patch)
+      if (pt.count > 0 && (pt.start < m->numInnerFaces || pt.start > m->numFaces - pt.count))
+        FC_FAIL(FC_ERR_ARG, std::string("fc_set_mesh: ") + pt.name + " faces lie outside numInnerFaces+1..numFaces");
+    for (int i = 0; i < m->numFaces; ++i)
+      if (m->owner[i] < 1 || m->owner[i] > m->numCells)
+        FC_FAIL(FC_ERR_ARG, "fc_set_mesh: owner(" + std::to_string(i + 1) + ") = " + std::to_string(m->owner[i]) +
+                                " is outside 1..numCells");
+    for (int i = 0; i < m->numInnerFaces; ++i)
+      if (m->neighbour[i] < 1 || m->neighbour[i] > m->numCells || m->neighbour[i] == m->owner[i])
+        FC_FAIL(FC_ERR_ARG, "fc_set_mesh: neighbour(" + std::to_string(i + 1) + ") = " + std::to_string(m->neighbour[i]) +
+                                " is outside 1..numCells or equals its owner");
+  }
   if (ctx->hcoef) { cudaFree(ctx->hcoef); ctx->hcoef = nullptr; }
   ctx->grad_method = ctx->grad_limiter = 0;   // the least-squares matrices belong to the old mesh
   if (ctx->uvw_face) {  // momentum fields are sized by the mesh: drop them, they come back on first use
