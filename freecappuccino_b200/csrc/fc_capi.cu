@@ -451,6 +451,15 @@ int fc_solve_csr(fc_context *ctx, int solver, int numCells, int nnz, const int *
   if (!ctx || !ioffset || !ja || !diag || !a || !su || !fi || !o || !rep) return FC_ERR_ARG;
   if (ctx->has_mesh) FC_FAIL(FC_ERR_ARG, "fc_solve_csr: context is bound to a mesh; use fc_solve_host");
   if (numCells < 1 || nnz < numCells) FC_FAIL(FC_ERR_ARG, "fc_solve_csr: bad sizes");
+  // the sweeps and the SpMV index with these arrays unchecked (1-based, LIS_linear_solver_library.f95:106-119)
+  if (ioffset[0] != 1 || ioffset[numCells] != nnz + 1) FC_FAIL(FC_ERR_ARG, "fc_solve_csr: ioffset must run from 1 to nnz+1");
+  for (int i = 0; i < numCells; ++i) {
+    if (ioffset[i + 1] < ioffset[i]) FC_FAIL(FC_ERR_ARG, "fc_solve_csr: ioffset decreases at row " + std::to_string(i + 1));
+    if (diag[i] < ioffset[i] || diag[i] >= ioffset[i + 1] || ja[diag[i] - 1] != i + 1)
+      FC_FAIL(FC_ERR_ARG, "fc_solve_csr: diag(" + std::to_string(i + 1) + ") does not point at the diagonal of its row");
+  }
+  for (int k = 0; k < nnz; ++k)
+    if (ja[k] < 1 || ja[k] > numCells) FC_FAIL(FC_ERR_ARG, "fc_solve_csr: ja(" + std::to_string(k + 1) + ") is outside 1..numCells");
   FC_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->csr_external || ctx->n != numCells || ctx->nnz != nnz) {
     ctx->n = numCells; ctx->nnz = nnz; ctx->npro = 0; ctx->NP = numCells; ctx->NT = numCells; ctx->F = 0; ctx->NF = 0;

@@ -42,3 +42,42 @@ def test_set_mesh_refuses_out_of_range_indices(fc, what):
     ioffset, ja, diag, icj, jci = ctx.create_csr()
     assert ioffset[-1] == good.nnz + 1
     ctx.close()
+
+
+def tridiag(n):
+    """1-based CSR of the 1-D Laplacian."""
+    rows = []
+    for i in range(n):
+        rows.append([j for j in (i - 1, i, i + 1) if 0 <= j < n])
+    ioffset = np.cumsum([1] + [len(r) for r in rows]).astype(np.int32)
+    ja = np.array([j + 1 for r in rows for j in r], np.int32)
+    diag = np.array([ioffset[i] + r.index(i) for i, r in enumerate(rows)], np.int32)
+    a = np.array([2.0 if j == i else -1.0 for i, r in enumerate(rows) for j in r])
+    return ioffset, ja, diag, a
+
+
+@pytest.mark.parametrize("what", ["ja-high", "ja-zero", "diag-off", "ioffset-end", "ioffset-decreasing"])
+def test_solve_csr_refuses_a_broken_pattern(fc, what):
+    n = 50
+    ioffset, ja, diag, a = tridiag(n)
+    b, x = np.ones(n), np.zeros(n)
+    opts = fc.solver_opts(1e-10, 500)
+    ctx = fc.Context(0)
+    bad = [ioffset.copy(), ja.copy(), diag.copy()]
+    if what == "ja-high":
+        bad[1][7] = n + 1
+    elif what == "ja-zero":
+        bad[1][0] = 0
+    elif what == "diag-off":
+        bad[2][10] += 1
+    elif what == "ioffset-end":
+        bad[0][-1] += 1
+    elif what == "ioffset-decreasing":
+        bad[0][5], bad[0][6] = bad[0][6], bad[0][5]
+    with pytest.raises(fc.FcError) as e:
+        ctx.solve_csr("iccg", bad[0], bad[1], bad[2], a, b, x, opts)
+    assert e.value.code == fc.FC_ERR_ARG and "fc_solve_csr" in str(e.value)
+    rep = ctx.solve_csr("iccg", ioffset, ja, diag, a, b, x, opts)     # the context still works
+    assert rep.resl / rep.res0 < 1e-10
+    assert np.abs(x[1:-1] * 2 - x[:-2] - x[2:] - 1).max() < 1e-8
+    ctx.close()
