@@ -89,6 +89,10 @@ struct fc_levels {                      // level schedule of the strict lower / 
   int *prod_cnt = nullptr;              // [nblocks]
   unsigned int *flag = nullptr;         // [nblocks] number of the last sweep whose rows the block has published
   bool p2p_ok = false;                  // every block has <= FC_TRI_MAXP producers
+  // tiled mode (FC_TUNE_SWEEP_TILED, fc_tile_schedule.hpp): a block = one spatial tile of FC_TILE slots, `nlev` etc.
+  // count tile levels, and inside the tile the rows are walked by local level
+  int *llev = nullptr;                  // [nslots] local level of the row, -1 for padding
+  int *blk_nlev = nullptr;              // [nblocks] local levels of the tile
 };
 constexpr int FC_TRI_MAXP = 16;
 
@@ -146,6 +150,10 @@ struct fc_context {
   size_t scratch_n = 0;
   fc_levels lower, upper;
   bool has_levels = false;
+  fc_levels tile_lower, tile_upper;     // tiled schedule of the same sweeps (only when tune_sweep_tiled)
+  int *tja = nullptr;                   // [nnz] column, or -(slot+1) when the column's row sits in the same tile
+  bool tiles_tried = false, tiles_ok = false;
+  std::string tiles_why;                // why the mesh got no tiling
 
   // ---- communication ----
   ncclComm_t comm = nullptr;
@@ -170,6 +178,7 @@ struct fc_context {
   int tune_pipe = 1;                    // staging geometry of the TMA pipeline (threads, capacity, stages)
   int tune_ctas_per_sm = 0;             // persistent kernel: CTAs per SM (0 = as many as fit)
   int tune_sweep_p2p = 0;               // triangular sweeps: 1 = point-to-point block flags instead of level counters
+  int tune_sweep_tiled = 0;             // triangular sweeps: 1 = two-level tiled schedule where the mesh allows it
   fc_persist_state *persist = nullptr;  // device: grid barrier + phase clocks of the persistent kernel
   fc_persist_state *persist_host = nullptr;
 

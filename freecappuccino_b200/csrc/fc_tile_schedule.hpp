@@ -1,0 +1,241 @@
+// Two-level ("tiled") schedule of the DIC / DILU triangular sweeps -- plain C++, no CUDA, so that the same code is
+// compiled into the library (fc_trisolve.cu) and into the g++ test harness (tests/kernel_bodies_host).
+//
+// The level schedule of fc_trisolve.cu needs one grid-wide hand-over per dependency level: 646 of them on the
+// 216^3 hexahedral mesh (3*216-2 hyperplanes), about 4 us each, although a level holds only ~16 k rows.  Here the
+// rows are grouped into spatial tiles of at most FC_TILE cells (bins of ~8 cells per axis over the cell centres); a
+// CTA owns a tile and walks the tile's *local* dependency levels with __syncthreads and shared memory, and only the
+// tile-to-tile dependencies (3*27-2 = 79 levels at 216^3) go through global memory.  The preconditioner is unchanged:
+// rows keep their natural numbering (iccg.f90:77-111, bicgstab.f90:68-79, :117-136), every row is still summed left
+// to right, only the order in which independent rows are visited differs.
+//
+// A tiling is usable when the tile-to-tile dependency graph is acyclic (always true for lexicographically numbered
+// structured meshes; checked, never assumed) and no tile exceeds FC_TILE rows; otherwise `ok` is false and the
+// caller keeps the level schedule.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+constexpr int FC_TILE = 512;   // rows per tile = threads per CTA of k_tile_sweep
+
+struct fc_tile_dir {                     // one sweep direction (strict lower or strict upper triangle)
+  int nlev = 0;                          // tile levels
+  int nblocks = 0;                       // tiles, in ticket order (tile-level-major)
+  int max_local_levels = 0;
+  std::vector<int> rows;                 // [nblocks * FC_TILE] row id (0-based) or -1; ascending inside a tile
+  std::vector<int> llev;                 // [nblocks * FC_TILE] local level of that row, -1 for padding
+  std::vector<int> blk_nlev;             // [nblocks] local levels of the tile
+  std::vector<int> blk_level;            // [nblocks] tile level
+  std::vector<int> lev_blocks_before;    // [nlev + 1] tiles in tile levels < L
+};
+
+struct fc_tile_schedule {
+  bool ok = false;
+  std::string why;                       // why not, when !ok
+  int ntiles = 0;
+  int cells_per_axis = 0;                // the bin width that worked
+  int max_tile_rows = 0;
+  std::vector<int> tja;                  // [nnz] column j, or -(q+1) when row j is slot q of the same tile
+  fc_tile_dir lower, upper;
+};
+
+namespace fc_tile_detail {
+
+// tile id of every row from bins over the cell centres; returns the number of (non-empty, renumbered) tiles
+// `shrink` = 0, 1, 2 ...: bins of FC_TILE^(1/dims) cells per axis (8 in 3-D, 22 in 2-D), each step 1/8 narrower
+inline int assign_tiles(int n, const double *xc, const double *yc, const double *zc, int shrink, std::vector<int> &tile,
+                        int &target) {
+  const double *c[3] = {xc, yc, zc};
+  double lo[3], len[3];
+  int dims = 0;
+  double vol = 1.0;
+  double longest = 0.0;
+  for (int ax = 0; ax < 3; ++ax) {
+    double mn = c[ax][0], mx = c[ax][0];
+    for (int i = 1; i < n; ++i) { mn = std::min(mn, c[ax][i]); mx = std::max(mx, c[ax][i]); }
+    lo[ax] = mn; len[ax] = mx - mn;
+    longest = std::max(longest, len[ax]);
+  }
+  for (int ax = 0; ax < 3; ++ax) {
+    if (len[ax] <= 1e-9 * longest) len[ax] = 0.0;   // one layer of cells (2-D cases): rounding noise is not an extent
+    if (len[ax] > 0.0) { vol *= len[ax]; ++dims; }
+  }
+  int nb[3] = {1, 1, 1};
+  target = FC_TILE;
+  if (dims > 0) {
+    target = (int)std::floor(std::pow((double)FC_TILE, 1.0 / dims) + 1e-9);
+    target = std::max(2, target - (shrink * std::max(1, target / 8)));
+    // mean spacing; the box of the centres is one spacing short of the box of the cells
+    const double h0 = std::pow(vol / n, 1.0 / dims);
+    double vol1 = 1.0;
+    for (int ax = 0; ax < 3; ++ax)
+      if (len[ax] > 0.0) { lo[ax] -= 0.5 * h0; len[ax] += h0; vol1 *= len[ax]; }
+    const double h = std::pow(vol1 / n, 1.0 / dims);
+    for (int ax = 0; ax < 3; ++ax)
+      if (len[ax] > 0.0) nb[ax] = std::max(1, (int)std::ceil(len[ax] / (target * h) - 1e-9));
+  }
+  std::vector<long long> raw(n);
+  for (int i = 0; i < n; ++i) {
+    long long id = 0;
+    for (int ax = 2; ax >= 0; --ax) {
+      int b = 0;
+      if (len[ax] > 0.0) b = std::min(nb[ax] - 1, std::max(0, (int)((c[ax][i] - lo[ax]) / len[ax] * nb[ax])));
+      id = id * nb[ax] + b;
+    }
+    raw[i] = id;
+  }
+  // renumber the non-empty bins densely, in ascending bin order
+  std::vector<long long> used(raw);
+  std::sort(used.begin(), used.end());
+  used.erase(std::unique(used.begin(), used.end()), used.end());
+  tile.resize(n);
+  for (int i = 0; i < n; ++i) tile[i] = (int)(std::lower_bound(used.begin(), used.end(), raw[i]) - used.begin());
+  return (int)used.size();
+}
+
+// dependency range of row i in the triangle of `lower`
+inline void tri_range(const int *ioffset, const int *diag, int i, bool lower, int &s, int &e) {
+  if (lower) { s = ioffset[i]; e = diag[i]; }
+  else { s = diag[i] + 1; e = ioffset[i + 1]; }
+}
+
+inline bool build_dir(int n, const int *ioffset, const int *ja, const int *diag, const std::vector<int> &tile,
+                      const std::vector<int> &tile_start, const std::vector<int> &pos, int ntiles, bool lower,
+                      fc_tile_dir &D, std::string &why) {
+  // tile-to-tile edges producer -> consumer
+  std::vector<uint64_t> edges;
+  for (int i = 0; i < n; ++i) {
+    int s, e;
+    tri_range(ioffset, diag, i, lower, s, e);
+    for (int k = s; k < e; ++k) {
+      const int j = ja[k];
+      if (j < n && tile[j] != tile[i]) edges.push_back(((uint64_t)(uint32_t)tile[j] << 32) | (uint32_t)tile[i]);
+    }
+    if ((i & 0xfffff) == 0xfffff) {   // keep the list short on large meshes
+      std::sort(edges.begin(), edges.end());
+      edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+    }
+  }
+  std::sort(edges.begin(), edges.end());
+  edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+  std::vector<int> indeg(ntiles, 0), adj_off(ntiles + 1, 0), adj(edges.size());
+  for (uint64_t ed : edges) { adj_off[(ed >> 32) + 1]++; indeg[(uint32_t)ed]++; }
+  for (int t = 0; t < ntiles; ++t) adj_off[t + 1] += adj_off[t];
+  {
+    std::vector<int> fill(adj_off.begin(), adj_off.end() - 1);
+    for (uint64_t ed : edges) adj[fill[ed >> 32]++] = (int)(uint32_t)ed;
+  }
+  // Kahn: tile level = longest path from a source
+  std::vector<int> tlev(ntiles, 0), queue;
+  queue.reserve(ntiles);
+  for (int t = 0; t < ntiles; ++t)
+    if (indeg[t] == 0) queue.push_back(t);
+  for (size_t h = 0; h < queue.size(); ++h) {
+    const int t = queue[h];
+    for (int q = adj_off[t]; q < adj_off[t + 1]; ++q) {
+      const int c = adj[q];
+      tlev[c] = std::max(tlev[c], tlev[t] + 1);
+      if (--indeg[c] == 0) queue.push_back(c);
+    }
+  }
+  if ((int)queue.size() != ntiles) {
+    why = "the tile-to-tile dependency graph has a cycle (cell numbering not monotone across the bins)";
+    return false;
+  }
+  // local levels: only dependencies inside the tile count, the others are complete before the tile starts
+  std::vector<int> ll(n, 0);
+  if (lower) {
+    for (int i = 0; i < n; ++i) {
+      int s, e, l = 0;
+      tri_range(ioffset, diag, i, true, s, e);
+      for (int k = s; k < e; ++k) {
+        const int j = ja[k];
+        if (j < n && tile[j] == tile[i]) l = std::max(l, ll[j] + 1);
+      }
+      ll[i] = l;
+    }
+  } else {
+    for (int i = n - 1; i >= 0; --i) {
+      int s, e, l = 0;
+      tri_range(ioffset, diag, i, false, s, e);
+      for (int k = s; k < e; ++k) {
+        const int j = ja[k];
+        if (j < n && tile[j] == tile[i]) l = std::max(l, ll[j] + 1);
+      }
+      ll[i] = l;
+    }
+  }
+  // tiles in ticket order: by tile level, then tile id
+  D.nlev = 0;
+  for (int t = 0; t < ntiles; ++t) D.nlev = std::max(D.nlev, tlev[t] + 1);
+  D.nblocks = ntiles;
+  D.lev_blocks_before.assign(D.nlev + 1, 0);
+  for (int t = 0; t < ntiles; ++t) D.lev_blocks_before[tlev[t] + 1]++;
+  for (int l = 0; l < D.nlev; ++l) D.lev_blocks_before[l + 1] += D.lev_blocks_before[l];
+  std::vector<int> block_of_tile(ntiles), fill(D.lev_blocks_before.begin(), D.lev_blocks_before.end() - 1);
+  for (int t = 0; t < ntiles; ++t) block_of_tile[t] = fill[tlev[t]]++;
+  D.rows.assign((size_t)ntiles * FC_TILE, -1);
+  D.llev.assign((size_t)ntiles * FC_TILE, -1);
+  D.blk_nlev.assign(ntiles, 0);
+  D.blk_level.assign(ntiles, 0);
+  D.max_local_levels = 0;
+  for (int t = 0; t < ntiles; ++t) D.blk_level[block_of_tile[t]] = tlev[t];
+  for (int i = 0; i < n; ++i) {
+    const int b = block_of_tile[tile[i]];
+    const size_t slot = (size_t)b * FC_TILE + pos[i];
+    D.rows[slot] = i;
+    D.llev[slot] = ll[i];
+    D.blk_nlev[b] = std::max(D.blk_nlev[b], ll[i] + 1);
+    D.max_local_levels = std::max(D.max_local_levels, ll[i] + 1);
+  }
+  (void)tile_start;
+  return true;
+}
+
+}  // namespace fc_tile_detail
+
+// 0-based CSR (columns ascending inside a row, diag = position of the diagonal) and the cell centres of its rows
+inline fc_tile_schedule fc_build_tile_schedule(int n, const int *ioffset, const int *ja, const int *diag,
+                                               const double *xc, const double *yc, const double *zc) {
+  using namespace fc_tile_detail;
+  fc_tile_schedule S;
+  if (n < 1) { S.why = "empty matrix"; return S; }
+  std::vector<int> tile, count;
+  int ntiles = 0;
+  for (int shrink = 0; shrink <= 4; ++shrink) {
+    int target = 0;
+    ntiles = assign_tiles(n, xc, yc, zc, shrink, tile, target);
+    count.assign(ntiles, 0);
+    for (int i = 0; i < n; ++i) count[tile[i]]++;
+    S.max_tile_rows = *std::max_element(count.begin(), count.end());
+    S.cells_per_axis = target;
+    if (S.max_tile_rows <= FC_TILE) break;
+  }
+  if (S.max_tile_rows > FC_TILE) {
+    S.why = "no bin width down to " + std::to_string(S.cells_per_axis) + " cells per axis keeps every tile within " +
+            std::to_string(FC_TILE) + " rows (strongly graded mesh)";
+    return S;
+  }
+  S.ntiles = ntiles;
+  // slot of a row inside its tile: ascending row id (the same for both directions, so one tja serves both)
+  std::vector<int> tile_start(ntiles + 1, 0), pos(n);
+  for (int t = 0; t < ntiles; ++t) tile_start[t + 1] = tile_start[t] + count[t];
+  {
+    std::vector<int> fill(ntiles, 0);
+    for (int i = 0; i < n; ++i) pos[i] = fill[tile[i]]++;
+  }
+  const int nnz = ioffset[n];
+  S.tja.resize(nnz);
+  for (int i = 0; i < n; ++i)
+    for (int k = ioffset[i]; k < ioffset[i + 1]; ++k) {
+      const int j = ja[k];
+      S.tja[k] = (j != i && j < n && tile[j] == tile[i]) ? -(pos[j] + 1) : j;
+    }
+  if (!build_dir(n, ioffset, ja, diag, tile, tile_start, pos, ntiles, true, S.lower, S.why)) return S;
+  if (!build_dir(n, ioffset, ja, diag, tile, tile_start, pos, ntiles, false, S.upper, S.why)) return S;
+  S.ok = true;
+  return S;
+}

@@ -11,6 +11,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "fc_internal.cuh"
+#include "fc_tile_schedule.hpp"
 #include "fc_tma.cuh"
 
 constexpr int TRI_BLOCK = 128;
@@ -326,9 +327,109 @@ k_tri_sweep(const int *__restrict__ rows, const int *__restrict__ blk_level,
   }
 }
 
+// Tiled mode (FC_TUNE_SWEEP_TILED; schedule: fc_tile_schedule.hpp).  A CTA owns one spatial tile of at most FC_TILE
+// rows, thread = slot.  Hand-overs through global memory happen once per TILE level (79 at 216^3 instead of 646 row
+// levels), with the same done / ready counters as the level mode; inside the tile the rows are walked by local level
+// with __syncthreads, and a dependency that sits in the same tile is read from shared memory (tja < 0 names its
+// slot).  Each row is still summed left to right over its triangle, so the result is bit-identical.
+template <int MODE>
+__global__ void __launch_bounds__(FC_TILE)
+k_tile_sweep(const int *__restrict__ rows, const int *__restrict__ llev, const int *__restrict__ blk_nlev,
+             const int *__restrict__ blk_level, const int *__restrict__ lev_blocks_before, unsigned int *done,
+             unsigned int *ready, unsigned int *ticket, unsigned int ticket_base, unsigned int sweep_no,
+             const int *__restrict__ ioffset, const int *__restrict__ tja, const int *__restrict__ diag,
+             const int *__restrict__ tpos, const double *__restrict__ a, const double *__restrict__ d,
+             const double *__restrict__ in, double *out, double small, double padd, const fc_scalars *sc) {
+  __shared__ double s_z[FC_TILE];
+  __shared__ unsigned int s_b;
+  if (sc && sc->done) return;
+  if (threadIdx.x == 0) s_b = atomicAdd(ticket, 1u) - ticket_base;
+  __syncthreads();
+  const unsigned int b = s_b;
+  const int lev = blk_level[b], nl = blk_nlev[b];
+  const size_t slot = (size_t)b * FC_TILE + threadIdx.x;
+  const int row = rows[slot];
+  const int my = llev[slot];
+  int s = 0, e = 0;
+  double v = 0.0, di = 0.0;
+  double pa[TRI_PRE], pt[TRI_PRE], zq[TRI_PRE];
+  int pj[TRI_PRE];
+  if (row >= 0) {
+    if (MODE == TRI_BWD) { s = diag[row] + 1; e = ioffset[row + 1]; }
+    else { s = ioffset[row]; e = diag[row]; }
+#pragma unroll
+    for (int q = 0; q < TRI_PRE; ++q) {
+      const int k = s + q;
+      if (k < e) {
+        pa[q] = a[k];
+        pj[q] = tja[k];
+        if (MODE == TRI_DILU) pt[q] = a[tpos[k]];
+      }
+    }
+    if (MODE == TRI_FWD) { v = in[row]; di = d[row]; }
+    else if (MODE == TRI_BWD) { di = d[row]; v = in[row] / (di + small); }   // z = z/(d+small), iccg.f90:102
+    else v = a[diag[row]];
+  }
+  if (lev > 0) {   // every tile of the previous tile level has published its rows
+    if (threadIdx.x == 0) {
+      const unsigned int *r = ready + (lev - 1);
+      while (ld_acquire(r) < sweep_no) {}
+    }
+    __syncthreads();
+  }
+  if (row >= 0) {   // rows of other tiles: complete, fetch them now (one L2 round trip for the whole tile)
+#pragma unroll
+    for (int q = 0; q < TRI_PRE; ++q)
+      if (s + q < e && pj[q] >= 0) zq[q] = __ldcg(out + pj[q]);
+  }
+  for (int l = 0; l < nl; ++l) {
+    if (my == l) {
+#pragma unroll
+      for (int q = 0; q < TRI_PRE; ++q) {
+        if (s + q < e) {
+          const double ak = pa[q], zj = pj[q] < 0 ? s_z[-pj[q] - 1] : zq[q];
+          if (MODE == TRI_FWD || MODE == TRI_BWD) v = v - ak * zj;
+          else if (MODE == TRI_DIC) v = v - (ak * ak) * zj;            // iccg.f90:80
+          else if (MODE == TRI_DIC_PAR) v = v - ak * zj * ak;          // src-parallel/iccg.f90:97
+          else v = v - ak * zj * pt[q];                                // bicgstab.f90:76
+        }
+      }
+      for (int k = s + TRI_PRE; k < e; ++k) {                          // long rows (polyhedral cells)
+        const int j = tja[k];
+        const double zj = j < 0 ? s_z[-j - 1] : __ldcg(out + j);
+        const double ak = a[k];
+        if (MODE == TRI_FWD || MODE == TRI_BWD) v = v - ak * zj;
+        else if (MODE == TRI_DIC) v = v - (ak * ak) * zj;
+        else if (MODE == TRI_DIC_PAR) v = v - ak * zj * ak;
+        else v = v - ak * zj * a[tpos[k]];
+      }
+      const double r = (MODE == TRI_FWD || MODE == TRI_BWD) ? v * di : 1.0 / (v + padd);
+      s_z[threadIdx.x] = r;
+      out[row] = r;
+    }
+    __syncthreads();   // the last one also orders every row's store before thread 0's release below
+  }
+  if (threadIdx.x == 0) {
+    const unsigned int nb = (unsigned int)(lev_blocks_before[lev + 1] - lev_blocks_before[lev]);
+    const unsigned int old = atom_add_acq_rel(done + lev, 1u);
+    if (old + 1u == sweep_no * nb) st_release(ready + lev, sweep_no);
+  }
+}
+
 template <int MODE>
 int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const double *in, double *out,
           double small, double padd, bool guarded) {
+  if (ctx->tune_sweep_tiled && ctx->tiles_ok) {
+    fc_levels &T = (&L == &ctx->lower) ? ctx->tile_lower : ctx->tile_upper;
+    const unsigned int tbase = (unsigned int)(T.epoch * (unsigned long long)T.nblocks);
+    T.epoch++;
+    k_tile_sweep<MODE><<<T.nblocks, FC_TILE, 0, ctx->stream>>>(
+        T.rows, T.llev, T.blk_nlev, T.blk_level, T.lev_blocks_before, T.done, T.ready, T.ticket, tbase,
+        (unsigned int)T.epoch, ctx->ioffset, ctx->tja, ctx->diag, ctx->tpos, a, d, in, out, small, padd,
+        guarded ? ctx->sc : nullptr);
+    FC_LAUNCH_CHECK();
+    return FC_OK;
+  }
   const int nblocks = L.nslots / TRI_BLOCK;
   const unsigned int base = (unsigned int)(L.epoch * (unsigned long long)nblocks);
   L.epoch++;
@@ -350,21 +451,86 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
 
 void fc_levels_free(fc_levels &L) {
   cudaFree(L.rows); cudaFree(L.blk_level); cudaFree(L.lev_blocks_before); cudaFree(L.done); cudaFree(L.ready);
-  cudaFree(L.ticket); cudaFree(L.prod); cudaFree(L.prod_cnt); cudaFree(L.flag);
+  cudaFree(L.ticket); cudaFree(L.prod); cudaFree(L.prod_cnt); cudaFree(L.flag); cudaFree(L.llev); cudaFree(L.blk_nlev);
   L = fc_levels{};
 }
 
+namespace {
+
+int upload_tile_dir(fc_context *ctx, const fc_tile_dir &D, fc_levels &L) {
+  fc_levels_free(L);
+  L.nlev = D.nlev;
+  L.nblocks = D.nblocks;
+  L.nslots = D.nblocks * FC_TILE;
+  FC_CHECK(fc_dev_alloc(ctx, &L.rows, D.rows.size()));
+  FC_CHECK(fc_dev_alloc(ctx, &L.llev, D.llev.size()));
+  FC_CHECK(fc_dev_alloc(ctx, &L.blk_nlev, D.blk_nlev.size()));
+  FC_CHECK(fc_dev_alloc(ctx, &L.blk_level, D.blk_level.size()));
+  FC_CHECK(fc_dev_alloc(ctx, &L.lev_blocks_before, D.lev_blocks_before.size()));
+  FC_CHECK(fc_dev_alloc(ctx, &L.done, (size_t)D.nlev));
+  FC_CHECK(fc_dev_alloc(ctx, &L.ready, (size_t)D.nlev));
+  FC_CHECK(fc_dev_alloc(ctx, &L.ticket, 1));
+  const struct { int *dst; const std::vector<int> *src; } up[] = {
+      {L.rows, &D.rows}, {L.llev, &D.llev}, {L.blk_nlev, &D.blk_nlev}, {L.blk_level, &D.blk_level},
+      {L.lev_blocks_before, &D.lev_blocks_before}};
+  for (const auto &u : up)
+    FC_CUDA(cudaMemcpyAsync(u.dst, u.src->data(), sizeof(int) * u.src->size(), cudaMemcpyHostToDevice, ctx->stream));
+  FC_CUDA(cudaMemsetAsync(L.done, 0, sizeof(unsigned int) * (size_t)D.nlev, ctx->stream));
+  FC_CUDA(cudaMemsetAsync(L.ready, 0, sizeof(unsigned int) * (size_t)D.nlev, ctx->stream));
+  FC_CUDA(cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), ctx->stream));
+  FC_CUDA(cudaStreamSynchronize(ctx->stream));   // the host vectors go away
+  L.epoch = 0;
+  return FC_OK;
+}
+
+// FC_TUNE_SWEEP_TILED: the schedule is built on the host from the pattern and the cell centres (once per mesh, about
+// a second per 10 M cells); a mesh that cannot be tiled keeps the level schedule and ctx->tiles_why says why
+int build_tiles(fc_context *ctx) {
+  ctx->tiles_tried = true;
+  ctx->tiles_ok = false;
+  if (!ctx->has_mesh || !ctx->xc) {
+    ctx->tiles_why = "no cell centres (explicit-CSR context)";
+    return FC_OK;
+  }
+  const size_t n = (size_t)ctx->n, nnz = (size_t)ctx->nnz;
+  std::vector<int> ioffset(n + 1), ja(nnz), diag(n);
+  std::vector<double> xc(n), yc(n), zc(n);
+  FC_CUDA(cudaStreamSynchronize(ctx->stream));
+  FC_CUDA(cudaMemcpy(ioffset.data(), ctx->ioffset, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost));
+  FC_CUDA(cudaMemcpy(ja.data(), ctx->ja, sizeof(int) * nnz, cudaMemcpyDeviceToHost));
+  FC_CUDA(cudaMemcpy(diag.data(), ctx->diag, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  FC_CUDA(cudaMemcpy(xc.data(), ctx->xc, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  FC_CUDA(cudaMemcpy(yc.data(), ctx->yc, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  FC_CUDA(cudaMemcpy(zc.data(), ctx->zc, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  const fc_tile_schedule S =
+      fc_build_tile_schedule(ctx->n, ioffset.data(), ja.data(), diag.data(), xc.data(), yc.data(), zc.data());
+  ctx->tiles_why = S.why;
+  if (!S.ok) return FC_OK;
+  FC_CHECK(fc_dev_alloc(ctx, &ctx->tja, nnz));
+  FC_CUDA(cudaMemcpy(ctx->tja, S.tja.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
+  FC_CHECK(upload_tile_dir(ctx, S.lower, ctx->tile_lower));
+  FC_CHECK(upload_tile_dir(ctx, S.upper, ctx->tile_upper));
+  ctx->tiles_ok = true;
+  return FC_OK;
+}
+
+}  // namespace
+
 int fc_levels_build(fc_context *ctx) {
-  if (ctx->has_levels) return FC_OK;
-  FC_CHECK(build_one(ctx, ctx->lower, 1));
-  FC_CHECK(build_one(ctx, ctx->upper, 0));
-  ctx->has_levels = true;
+  if (!ctx->has_levels) {
+    FC_CHECK(build_one(ctx, ctx->lower, 1));
+    FC_CHECK(build_one(ctx, ctx->upper, 0));
+    ctx->has_levels = true;
+    ctx->tiles_tried = ctx->tiles_ok = false;   // a new pattern: the old tiling is void
+  }
+  if (ctx->tune_sweep_tiled && !ctx->tiles_tried) FC_CHECK(build_tiles(ctx));
   return FC_OK;
 }
 
 // counters are monotone over the sweeps of one solve; restart them so that they never wrap
 int fc_levels_reset(fc_context *ctx) {
-  for (fc_levels *L : {&ctx->lower, &ctx->upper}) {
+  for (fc_levels *L : {&ctx->lower, &ctx->upper, &ctx->tile_lower, &ctx->tile_upper}) {
+    if (!L->done) continue;   // no tiling for this mesh
     FC_CUDA(cudaMemsetAsync(L->done, 0, sizeof(unsigned int) * (size_t)L->nlev, ctx->stream));
     FC_CUDA(cudaMemsetAsync(L->ready, 0, sizeof(unsigned int) * (size_t)L->nlev, ctx->stream));
     FC_CUDA(cudaMemsetAsync(L->ticket, 0, sizeof(unsigned int), ctx->stream));

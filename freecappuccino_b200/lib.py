@@ -46,6 +46,7 @@ SYMBOLS = (
 GRAD_METHODS = {"gauss": 0, "lstsq": 1, "lstsq_qr": 2, "lstsq_dm": 3}
 LIMITERS = {"no-limit": 0, "Barth-Jespersen": 1, "Venkatakrishnan": 2, "mVenkatakrishnan": 3}
 TUNE_SPMV_KERNEL, TUNE_DPCG_PERSISTENT, TUNE_CTAS_PER_SM, TUNE_PIPE_GEOMETRY, TUNE_SWEEP_P2P = 0, 1, 2, 3, 4
+TUNE_SWEEP_TILED = 5
 
 
 class MeshDesc(C.Structure):
@@ -82,7 +83,7 @@ class CalcpReport(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("solve_ms", C.c_double), ("assemble_ms", C.c_double), ("correct_ms", C.c_double),
-                ("spmv_ms", C.c_double), ("spmv_samples", C.c_int), ("pad_", C.c_int), ("launches", C.c_longlong),
+                ("spmv_ms", C.c_double), ("spmv_samples", C.c_int), ("sweep_tiles", C.c_int), ("launches", C.c_longlong),
                 ("persist_ms", C.c_double), ("persist_pupdate_ms", C.c_double), ("persist_spmv_ms", C.c_double),
                 ("persist_update_ms", C.c_double), ("persist_iters", C.c_int), ("persist_grid", C.c_int),
                 ("persist_mail_ms", C.c_double), ("uvw_assemble_ms", C.c_double), ("uvw_solve_ms", C.c_double)]

@@ -319,7 +319,8 @@ typedef struct {
   double spmv_ms;      /* mean duration of the SpMV(+dot) launches sampled    */
                        /* inside the last solve (fc_set_spmv_sampling)        */
   int spmv_samples;    /* how many launches that mean is over                 */
-  int pad_;
+  int sweep_tiles;     /* tiles of the tiled sweep schedule in use (FC_TUNE_SWEEP_TILED), */
+                       /* 0 = the level schedule                              */
   long long launches;  /* kernels launched by the library since creation      */
   /* persistent DPCG kernel of the last solve (zero when the multi-kernel path ran):
    * device time of the whole kernel and of its three phases summed over the
@@ -342,9 +343,14 @@ enum {
   FC_TUNE_CTAS_PER_SM = 2,     /* persistent kernel: CTAs per SM, [0] = all that fit */
   FC_TUNE_PIPE_GEOMETRY = 3,   /* TMA pipeline (threads, non-zeros staged, stages):
                                   0 256/2304/3, [1] 256/2304/2, 2 256/2048/2, 3 128/1024/2 */
-  FC_TUNE_SWEEP_P2P = 4        /* triangular sweeps (iccg, bicgstab): [0] one counter per level,
+  FC_TUNE_SWEEP_P2P = 4,       /* triangular sweeps (iccg, bicgstab): [0] one counter per level,
                                   1 point-to-point flags between 128-row blocks (experimental:
                                   same row sums, bit-identical results)                      */
+  FC_TUNE_SWEEP_TILED = 5      /* triangular sweeps: [0] one hand-over per dependency level,
+                                  1 two-level schedule -- spatial tiles of <= 512 cells walked
+                                  inside one CTA, hand-overs only between tiles (experimental;
+                                  needs a mesh whose numbering is monotone across the tiles, else
+                                  the level schedule stays; same row sums, bit-identical results) */
 };
 int fc_set_tuning(fc_context *ctx, int key, int value);
 /* Bracket up to `max_samples` SpMV launches of every following solve with CUDA

@@ -1,0 +1,102 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product, never loaded by freecappuccino_b200.
+//
+// Compiles the tile-schedule builder of the triangular sweeps (freecappuccino_b200/csrc/fc_tile_schedule.hpp, the
+// same header fc_trisolve.cu includes) with g++ and walks the schedule exactly as k_tile_sweep does -- tiles in
+// ticket order, local levels in order, rows of a local level in any order, in-tile values through the tile's
+// shared array, the others through the output vector -- so that tests/test_tile_schedule.py can check on a machine
+// without a GPU that (a) no row is visited before the rows it depends on, (b) a value read through global memory
+// was produced by a tile of a strictly lower tile level (the only ordering the kernel's level counters give) and
+// (c) the result is bit-identical to the natural-order sweep of iccg.f90:94-111 / bicgstab.f90:68-79.
+#include <cmath>
+#include <limits>
+
+#include "../../freecappuccino_b200/csrc/fc_tile_schedule.hpp"
+
+enum { TRI_FWD = 0, TRI_BWD = 1, TRI_DIC = 2, TRI_DIC_PAR = 3, TRI_DILU = 4 };
+
+static inline double step(int mode, double v, double ak, double zj, double atk) {
+  if (mode == TRI_FWD || mode == TRI_BWD) return v - ak * zj;
+  if (mode == TRI_DIC) return v - (ak * ak) * zj;
+  if (mode == TRI_DIC_PAR) return v - ak * zj * ak;
+  return v - ak * zj * atk;
+}
+static inline double start(int mode, int row, const int *diag, const double *a, const double *d, const double *in,
+                           double small, double &di) {
+  di = 0.0;
+  if (mode == TRI_FWD) { di = d[row]; return in[row]; }
+  if (mode == TRI_BWD) { di = d[row]; return in[row] / (di + small); }
+  return a[diag[row]];
+}
+static inline double finish(int mode, double v, double di, double padd) {
+  return (mode == TRI_FWD || mode == TRI_BWD) ? v * di : 1.0 / (v + padd);
+}
+
+extern "C" {
+
+void *fct_build(int n, const int *ioffset, const int *ja, const int *diag, const double *xc, const double *yc,
+                const double *zc) {
+  return new fc_tile_schedule(fc_build_tile_schedule(n, ioffset, ja, diag, xc, yc, zc));
+}
+void fct_free(void *h) { delete (fc_tile_schedule *)h; }
+int fct_ok(void *h) { return ((fc_tile_schedule *)h)->ok ? 1 : 0; }
+const char *fct_why(void *h) { return ((fc_tile_schedule *)h)->why.c_str(); }
+void fct_info(void *h, int *out) {
+  const fc_tile_schedule &S = *(fc_tile_schedule *)h;
+  out[0] = S.ntiles; out[1] = S.cells_per_axis; out[2] = S.max_tile_rows;
+  out[3] = S.lower.nlev; out[4] = S.lower.max_local_levels;
+  out[5] = S.upper.nlev; out[6] = S.upper.max_local_levels;
+}
+
+// the sweep in the reference's own order: rows ascending (lower triangle) or descending (upper)
+void fct_reference_sweep(int mode, int n, const int *ioffset, const int *ja, const int *diag, const int *tpos,
+                         const double *a, const double *d, const double *in, double *out, double small, double padd) {
+  const bool bwd = mode == TRI_BWD;
+  for (int q = 0; q < n; ++q) {
+    const int row = bwd ? n - 1 - q : q;
+    const int s = bwd ? diag[row] + 1 : ioffset[row], e = bwd ? ioffset[row + 1] : diag[row];
+    double di, v = start(mode, row, diag, a, d, in, small, di);
+    for (int k = s; k < e; ++k) v = step(mode, v, a[k], out[ja[k]], mode == TRI_DILU ? a[tpos[k]] : 0.0);
+    out[row] = finish(mode, v, di, padd);
+  }
+}
+
+// the sweep as k_tile_sweep walks it; `out` must arrive filled with NaN.  Returns the number of ordering violations.
+int fct_sweep(void *h, int mode, int n, const int *ioffset, const int *diag, const int *tpos, const double *a,
+              const double *d, const double *in, double *out, double small, double padd) {
+  const fc_tile_schedule &S = *(fc_tile_schedule *)h;
+  const fc_tile_dir &D = mode == TRI_BWD ? S.upper : S.lower;
+  const bool bwd = mode == TRI_BWD;
+  std::vector<int> produced_level(n, -1);
+  std::vector<double> s_z(FC_TILE);
+  int bad = 0, visited = 0;
+  for (int b = 0; b < D.nblocks; ++b) {
+    const int lev = D.blk_level[b];
+    if (b < D.lev_blocks_before[lev] || b >= D.lev_blocks_before[lev + 1]) ++bad;   // ticket order is level-major
+    std::fill(s_z.begin(), s_z.end(), std::numeric_limits<double>::quiet_NaN());
+    for (int l = 0; l < D.blk_nlev[b]; ++l)
+      for (int t = FC_TILE - 1; t >= 0; --t) {   // any order inside a local level: take the reverse one
+        const size_t slot = (size_t)b * FC_TILE + t;
+        const int row = D.rows[slot];
+        if (row < 0 || D.llev[slot] != l) continue;
+        const int s = bwd ? diag[row] + 1 : ioffset[row], e = bwd ? ioffset[row + 1] : diag[row];
+        double di, v = start(mode, row, diag, a, d, in, small, di);
+        for (int k = s; k < e; ++k) {
+          const int j = S.tja[k];
+          double zj;
+          if (j < 0) zj = s_z[-j - 1];
+          else { zj = out[j]; if (produced_level[j] < 0 || produced_level[j] >= lev) ++bad; }
+          if (std::isnan(zj)) ++bad;
+          v = step(mode, v, a[k], zj, mode == TRI_DILU ? a[tpos[k]] : 0.0);
+        }
+        const double r = finish(mode, v, di, padd);
+        s_z[t] = r;
+        out[row] = r;
+        produced_level[row] = lev;
+        ++visited;
+      }
+  }
+  if (visited != n) ++bad;
+  return bad;
+}
+
+}  // extern "C"

@@ -2,7 +2,9 @@
 hardware yet, so the default `pytest -m gpu` skips them; enable with FCAPP_EXPERIMENTAL=1.
 
 FC_TUNE_SWEEP_P2P: point-to-point block flags instead of one counter per level in the DIC / DILU triangular sweeps
-(fc_trisolve.cu).  The row sums are unchanged, so every iterate must be bit-identical to the default mode."""
+(fc_trisolve.cu).  FC_TUNE_SWEEP_TILED: two-level schedule, spatial tiles walked inside one CTA (fc_tile_schedule.hpp;
+its schedule is checked on the CPU by tests/test_tile_schedule.py).  The row sums are unchanged in both, so every
+iterate must be bit-identical to the default mode."""
 import os
 import time
 
@@ -31,15 +33,17 @@ def fc():
 
 @pytest.mark.parametrize("name", list(MESHES))
 @pytest.mark.parametrize("solver", ["iccg", "bicgstab"])
-def test_p2p_sweeps_are_bit_identical_to_level_sweeps(fc, name, solver):
+@pytest.mark.parametrize("mode", ["p2p", "tiled"])
+def test_sweep_variants_are_bit_identical_to_level_sweeps(fc, name, solver, mode):
     mesh = MESHES[name]()
+    key = fc.TUNE_SWEEP_P2P if mode == "p2p" else fc.TUNE_SWEEP_TILED
     su = np.random.default_rng(5).standard_normal(mesh.numCells) * mesh.vol[:mesh.numCells]
     res = []
     for p2p in (0, 1):
         ctx = fc.Context(0)
         ctx.set_mesh(mesh)
         ctx.create_csr(download=False)
-        ctx.set_tuning(fc.TUNE_SWEEP_P2P, p2p)
+        ctx.set_tuning(key, p2p)
         ctx.upload("APU", -np.ones(mesh.numCells))
         ctx.upload("SU", su)
         ctx.fill("PP", 0.0)
@@ -53,8 +57,10 @@ def test_p2p_sweeps_are_bit_identical_to_level_sweeps(fc, name, solver):
             ms = ctx.timings().solve_ms
             best = ms if best is None else min(best, ms)
         res.append((rep.iters, rep.res0, rep.resl, ctx.download("PP"), ctx.download("RES"), best))
+        if mode == "tiled" and p2p and name in ("hex", "slab", "poly"):
+            assert ctx.timings().sweep_tiles > 0, "the tiled schedule was not used"
         ctx.close()
     (i0, a0, b0, x0, r0, t0), (i1, a1, b1, x1, r1, t1) = res
-    print(f"\\n[p2p sweeps] {name} {solver}: {i0} iterations, level mode {t0:.3f} ms, p2p mode {t1:.3f} ms")
+    print(f"\\n[{mode} sweeps] {name} {solver}: {i0} iterations, level mode {t0:.3f} ms, {mode} mode {t1:.3f} ms")
     assert i0 == i1 and a0 == a1 and b0 == b1
     assert np.array_equal(x0, x1) and np.array_equal(r0, r1)

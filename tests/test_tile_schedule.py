@@ -1,0 +1,149 @@
+"""The tiled schedule of the DIC / DILU triangular sweeps (freecappuccino_b200/csrc/fc_tile_schedule.hpp, used by
+k_tile_sweep of fc_trisolve.cu under FC_TUNE_SWEEP_TILED) checked on the CPU: tests/kernel_bodies_host/fct_host.cpp
+compiles the same header with g++ and walks the schedule the way the kernel does.  Every sweep mode must be
+bit-identical to the natural-order sweep of the reference (iccg.f90:77-111, bicgstab.f90:68-79, :117-136) and must
+never read a value before its producer -- through shared memory inside a tile, through a strictly lower tile level
+otherwise."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from freecappuccino_b200 import cases, mesh as M
+from oracle import oracle
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kernel_bodies_host")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FWD, BWD, DIC, DIC_PAR, DILU = range(5)
+
+
+@pytest.fixture(scope="module")
+def host():
+    src = os.path.join(HERE, "fct_host.cpp")
+    so = os.path.join(HERE, "_fct_host.so")
+    hdr = os.path.join(HERE, "..", "..", "freecappuccino_b200", "csrc", "fc_tile_schedule.hpp")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.fct_build.restype = C.c_void_p
+    lib.fct_why.restype = C.c_char_p
+    return lib
+
+
+def ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class System:
+    """0-based CSR of the mesh's pattern with a diagonally dominant non-symmetric matrix on it."""
+
+    def __init__(self, mesh, seed=3):
+        csr = oracle.create_csr(mesh)
+        self.n = n = mesh.numCells
+        self.ioffset = (csr.ioffset - 1).astype(np.int32)
+        self.ja = (csr.ja - 1).astype(np.int32)
+        self.diag = (csr.diag - 1).astype(np.int32)
+        rng = np.random.default_rng(seed)
+        self.a = -(0.2 + rng.random(self.ja.size))
+        row = np.repeat(np.arange(n), np.diff(self.ioffset))
+        rowsum = np.zeros(n)
+        np.add.at(rowsum, row, np.abs(self.a))
+        self.a[self.diag] = rowsum + 1.0
+        # position of the transposed entry (bicgstab.f90:68-79 finds a_ki by a search in row k)
+        key = row.astype(np.int64) * n + self.ja
+        order = np.argsort(key)
+        tkey = self.ja.astype(np.int64) * n + row
+        self.tpos = order[np.searchsorted(key[order], tkey)].astype(np.int32)
+        assert np.array_equal(self.ja[self.tpos], row)
+        self.xc, self.yc, self.zc = (np.ascontiguousarray(v[:n], dtype=np.float64) for v in (mesh.xc, mesh.yc, mesh.zc))
+        self.r = rng.standard_normal(n)
+
+
+MESHES = {
+    "hex-24x20x17": lambda: cases.hex_case(24, 20, 17),
+    "hex-32^3": lambda: cases.hex_case(32, 32, 32),
+    "hex-9^3": lambda: cases.hex_case(9, 9, 9),
+    "slab-60x60x1": lambda: cases.hex_case(60, 60, 1, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry")),
+    "line-100": lambda: cases.hex_case(100, 1, 1),
+    "one-cell": lambda: cases.hex_case(1, 1, 1),
+    "skew": lambda: cases.skew_case(12),
+    "poly-6": lambda: cases.poly_case(6),
+    "cavity": lambda: cases.golden_mesh(os.path.join(GOLD, "cavity.npz")),
+    "pitzDaily": lambda: cases.golden_mesh(os.path.join(GOLD, "pitzDaily.npz")),
+    "hex-rank-of-3": lambda: M.partition(cases.hex_case(16, 16, 24), M.slab_ranks(16 * 16 * 24, 3), 3)[1],
+}
+
+
+def build(host, s):
+    h = host.fct_build(s.n, ip(s.ioffset), ip(s.ja), ip(s.diag), dp(s.xc), dp(s.yc), dp(s.zc))
+    info = np.zeros(7, np.int32)
+    host.fct_info(C.c_void_p(h), ip(info))
+    return h, info
+
+
+def run(host, h, s, mode, d, src, padd=0.0, small=1e-20):
+    ref = np.zeros(s.n)
+    host.fct_reference_sweep(mode, s.n, ip(s.ioffset), ip(s.ja), ip(s.diag), ip(s.tpos), dp(s.a), dp(d), dp(src), dp(ref),
+                             C.c_double(small), C.c_double(padd))
+    out = np.full(s.n, np.nan)
+    bad = host.fct_sweep(C.c_void_p(h), mode, s.n, ip(s.ioffset), ip(s.diag), ip(s.tpos), dp(s.a), dp(d), dp(src), dp(out),
+                         C.c_double(small), C.c_double(padd))
+    return ref, out, bad
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+def test_tiled_sweeps_equal_natural_order_sweeps(host, name):
+    s = System(MESHES[name]())
+    h, info = build(host, s)
+    try:
+        if not host.fct_ok(C.c_void_p(h)):
+            # a refusal must say why and is only expected where bins cannot work
+            why = host.fct_why(C.c_void_p(h)).decode()
+            assert name in ("pitzDaily", "poly-6", "skew"), (name, why)
+            assert why
+            pytest.skip(f"{name}: no tiling ({why}); the library keeps the level schedule")
+        ntiles, cells, maxrows, lnlev, lloc, unlev, uloc = info
+        assert 1 <= maxrows <= 512 and ntiles >= 1 and 2 <= cells <= 512
+        zero = np.zeros(s.n)
+        for mode in (DIC, DIC_PAR, DILU):
+            ref, out, bad = run(host, h, s, mode, zero, zero, padd=1e-20 if mode == DIC_PAR else 0.0)
+            assert bad == 0, (name, mode, bad)
+            assert np.array_equal(ref, out), (name, mode)
+        d = ref                                   # the DILU diagonal
+        rt, t, bad = run(host, h, s, FWD, d, s.r)
+        assert bad == 0 and np.array_equal(rt, t)
+        rz, z, bad = run(host, h, s, BWD, d, t)
+        assert bad == 0 and np.array_equal(rz, z)
+        assert np.all(np.isfinite(z))
+    finally:
+        host.fct_free(C.c_void_p(h))
+
+
+def test_tile_levels_of_a_cube_are_the_tile_hyperplanes(host):
+    """n = 32: 4 x 4 x 4 tiles of 8^3 cells -> 3*4-2 = 10 tile levels instead of 3*32-2 = 94 row levels, and
+    3*8-2 = 22 local levels per tile."""
+    s = System(cases.hex_case(32, 32, 32))
+    h, info = build(host, s)
+    ntiles, cells, maxrows, lnlev, lloc, unlev, uloc = info
+    host.fct_free(C.c_void_p(h))
+    assert (ntiles, cells, maxrows) == (64, 8, 512)
+    assert (lnlev, unlev) == (10, 10) and (lloc, uloc) == (22, 22)
+
+
+def test_a_numbering_that_is_not_monotone_across_the_bins_is_refused(host):
+    """Rows renumbered at random: tile A needs tile B and tile B needs tile A -> no tile order exists, the builder
+    must say so instead of emitting a schedule that deadlocks."""
+    m = cases.hex_case(20, 20, 20)
+    s = System(m)
+    perm = np.random.default_rng(0).permutation(s.n)
+    xc, yc, zc = s.xc[perm].copy(), s.yc[perm].copy(), s.zc[perm].copy()   # centres no longer follow the numbering
+    h = host.fct_build(s.n, ip(s.ioffset), ip(s.ja), ip(s.diag), dp(xc), dp(yc), dp(zc))
+    ok, why = host.fct_ok(C.c_void_p(h)), host.fct_why(C.c_void_p(h)).decode()
+    host.fct_free(C.c_void_p(h))
+    assert not ok and "cycle" in why

@@ -7,7 +7,8 @@ GB/s is reported against the algorithmic byte count of DESIGN.md 4 and the measu
 
 Covers: grad_gauss pass, bpres, the calcp assembly (gradients + face kernel + row gather), the momentum predictor's
 explicit part, the least-squares gradients and limiters, SpMV, and the per-iteration cost of dpcg / iccg / bicgstab
-(solve_ms / iterations).  Meant as the first gpurun call of a round: one JSON line per operation.
+(solve_ms / iterations), and the same with the experimental sweep schedules (FC_TUNE_SWEEP_TILED, FC_TUNE_SWEEP_P2P).
+Meant as the first gpurun call of a round: one JSON line per operation.
 """
 import json
 import os
@@ -96,6 +97,20 @@ def main():
             rep = ctx.solve(solver, "PP", lib.solver_opts(1e-30, its))
         t = ctx.timings()
         report(f"{solver} iteration", t.solve_ms / max(rep.iters, 1), nbytes, iters=rep.iters, solve_ms=t.solve_ms)
+    # experimental sweep schedules (off by default), last so that a failure cannot take the lines above with it
+    for key, label in ((lib.TUNE_SWEEP_TILED, "tiled sweeps"), (lib.TUNE_SWEEP_P2P, "p2p sweeps")):
+        try:
+            ctx.set_tuning(key, 1)
+            for solver, nbytes in (("iccg", 24 * nnz + 164 * nc), ("bicgstab", 2 * (24 * nnz + 164 * nc))):
+                for _ in range(2):
+                    ctx.fill("PP", 0.0)
+                    rep = ctx.solve(solver, "PP", lib.solver_opts(1e-30, 20))
+                t = ctx.timings()
+                report(f"{solver} iteration, {label}", t.solve_ms / max(rep.iters, 1), nbytes, iters=rep.iters,
+                       solve_ms=t.solve_ms, sweep_tiles=t.sweep_tiles)
+        except lib.FcError as e:
+            print(json.dumps(dict(op=label, error=str(e))), flush=True)
+        ctx.set_tuning(key, 0)
     ctx.close()
 
 
