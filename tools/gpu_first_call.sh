@@ -10,7 +10,7 @@ python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
 timeout 600 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 FCAPP_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz9_experimental.py -q -m gpu -s > gpurun_out/pytest_experimental.log 2>&1
-grep "p2p sweeps\|passed\|failed" gpurun_out/pytest_experimental.log | tail -12
+grep "sweeps\]\|passed\|failed" gpurun_out/pytest_experimental.log | tail -24
 timeout 200 python tools/kernel_bench.py 216 10 > gpurun_out/kernel_bench_216.jsonl 2> gpurun_out/kernel_bench.err
 timeout 120 python tools/simple_iter_bench.py 216 2 3 > gpurun_out/simple_iter_216.json 2>&1
 timeout 300 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
