@@ -152,7 +152,7 @@ struct fc_context {
   bool has_levels = false;
   fc_levels tile_lower, tile_upper;     // tiled schedule of the same sweeps (only when tune_sweep_tiled)
   int *tja = nullptr;                   // [nnz] column, or -(slot+1) when the column's row sits in the same tile
-  bool tiles_tried = false, tiles_ok = false;
+  bool tiles_tried = false, tiles_ok = false, tiles_pre8 = false;
   std::string tiles_why;                // why the mesh got no tiling
 
   // ---- communication ----

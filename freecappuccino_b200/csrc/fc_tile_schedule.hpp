@@ -38,6 +38,7 @@ struct fc_tile_schedule {
   int ntiles = 0;
   int cells_per_axis = 0;                // the bin width that worked
   int max_tile_rows = 0;
+  int max_tri_len = 0;                   // longest strict-triangle row (how many entries the kernel keeps in registers)
   std::vector<int> tja;                  // [nnz] column j, or -(q+1) when row j is slot q of the same tile
   fc_tile_dir lower, upper;
 };
@@ -229,11 +230,13 @@ inline fc_tile_schedule fc_build_tile_schedule(int n, const int *ioffset, const 
   }
   const int nnz = ioffset[n];
   S.tja.resize(nnz);
-  for (int i = 0; i < n; ++i)
+  for (int i = 0; i < n; ++i) {
+    S.max_tri_len = std::max(S.max_tri_len, std::max(diag[i] - ioffset[i], ioffset[i + 1] - diag[i] - 1));
     for (int k = ioffset[i]; k < ioffset[i + 1]; ++k) {
       const int j = ja[k];
       S.tja[k] = (j != i && j < n && tile[j] == tile[i]) ? -(pos[j] + 1) : j;
     }
+  }
   if (!build_dir(n, ioffset, ja, diag, tile, tile_start, pos, ntiles, true, S.lower, S.why)) return S;
   if (!build_dir(n, ioffset, ja, diag, tile, tile_start, pos, ntiles, false, S.upper, S.why)) return S;
   S.ok = true;

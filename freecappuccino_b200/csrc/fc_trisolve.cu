@@ -332,7 +332,9 @@ k_tri_sweep(const int *__restrict__ rows, const int *__restrict__ blk_level,
 // levels), with the same done / ready counters as the level mode; inside the tile the rows are walked by local level
 // with __syncthreads, and a dependency that sits in the same tile is read from shared memory (tja < 0 names its
 // slot).  Each row is still summed left to right over its triangle, so the result is bit-identical.
-template <int MODE>
+// PRE = matrix entries of a row held in registers before the walk starts (4 covers hexahedra, 8 the 14-faced
+// polyhedra): an entry fetched inside the walk would put an L2 round trip on the critical path of a local level.
+template <int MODE, int PRE>
 __global__ void __launch_bounds__(FC_TILE)
 k_tile_sweep(const int *__restrict__ rows, const int *__restrict__ llev, const int *__restrict__ blk_nlev,
              const int *__restrict__ blk_level, const int *__restrict__ lev_blocks_before, unsigned int *done,
@@ -352,13 +354,13 @@ k_tile_sweep(const int *__restrict__ rows, const int *__restrict__ llev, const i
   const int my = llev[slot];
   int s = 0, e = 0;
   double v = 0.0, di = 0.0;
-  double pa[TRI_PRE], pt[TRI_PRE], zq[TRI_PRE];
-  int pj[TRI_PRE];
+  double pa[PRE], pt[PRE], zq[PRE];
+  int pj[PRE];
   if (row >= 0) {
     if (MODE == TRI_BWD) { s = diag[row] + 1; e = ioffset[row + 1]; }
     else { s = ioffset[row]; e = diag[row]; }
 #pragma unroll
-    for (int q = 0; q < TRI_PRE; ++q) {
+    for (int q = 0; q < PRE; ++q) {
       const int k = s + q;
       if (k < e) {
         pa[q] = a[k];
@@ -379,13 +381,13 @@ k_tile_sweep(const int *__restrict__ rows, const int *__restrict__ llev, const i
   }
   if (row >= 0) {   // rows of other tiles: complete, fetch them now (one L2 round trip for the whole tile)
 #pragma unroll
-    for (int q = 0; q < TRI_PRE; ++q)
+    for (int q = 0; q < PRE; ++q)
       if (s + q < e && pj[q] >= 0) zq[q] = __ldcg(out + pj[q]);
   }
   for (int l = 0; l < nl; ++l) {
     if (my == l) {
 #pragma unroll
-      for (int q = 0; q < TRI_PRE; ++q) {
+      for (int q = 0; q < PRE; ++q) {
         if (s + q < e) {
           const double ak = pa[q], zj = pj[q] < 0 ? s_z[-pj[q] - 1] : zq[q];
           if (MODE == TRI_FWD || MODE == TRI_BWD) v = v - ak * zj;
@@ -394,7 +396,7 @@ k_tile_sweep(const int *__restrict__ rows, const int *__restrict__ llev, const i
           else v = v - ak * zj * pt[q];                                // bicgstab.f90:76
         }
       }
-      for (int k = s + TRI_PRE; k < e; ++k) {                          // long rows (polyhedral cells)
+      for (int k = s + PRE; k < e; ++k) {                          // long rows (polyhedral cells)
         const int j = tja[k];
         const double zj = j < 0 ? s_z[-j - 1] : __ldcg(out + j);
         const double ak = a[k];
@@ -423,10 +425,16 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
     fc_levels &T = (&L == &ctx->lower) ? ctx->tile_lower : ctx->tile_upper;
     const unsigned int tbase = (unsigned int)(T.epoch * (unsigned long long)T.nblocks);
     T.epoch++;
-    k_tile_sweep<MODE><<<T.nblocks, FC_TILE, 0, ctx->stream>>>(
-        T.rows, T.llev, T.blk_nlev, T.blk_level, T.lev_blocks_before, T.done, T.ready, T.ticket, tbase,
-        (unsigned int)T.epoch, ctx->ioffset, ctx->tja, ctx->diag, ctx->tpos, a, d, in, out, small, padd,
-        guarded ? ctx->sc : nullptr);
+    if (ctx->tiles_pre8)
+      k_tile_sweep<MODE, 8><<<T.nblocks, FC_TILE, 0, ctx->stream>>>(
+          T.rows, T.llev, T.blk_nlev, T.blk_level, T.lev_blocks_before, T.done, T.ready, T.ticket, tbase,
+          (unsigned int)T.epoch, ctx->ioffset, ctx->tja, ctx->diag, ctx->tpos, a, d, in, out, small, padd,
+          guarded ? ctx->sc : nullptr);
+    else
+      k_tile_sweep<MODE, 4><<<T.nblocks, FC_TILE, 0, ctx->stream>>>(
+          T.rows, T.llev, T.blk_nlev, T.blk_level, T.lev_blocks_before, T.done, T.ready, T.ticket, tbase,
+          (unsigned int)T.epoch, ctx->ioffset, ctx->tja, ctx->diag, ctx->tpos, a, d, in, out, small, padd,
+          guarded ? ctx->sc : nullptr);
     FC_LAUNCH_CHECK();
     return FC_OK;
   }
@@ -510,6 +518,7 @@ int build_tiles(fc_context *ctx) {
   FC_CUDA(cudaMemcpy(ctx->tja, S.tja.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
   FC_CHECK(upload_tile_dir(ctx, S.lower, ctx->tile_lower));
   FC_CHECK(upload_tile_dir(ctx, S.upper, ctx->tile_upper));
+  ctx->tiles_pre8 = S.max_tri_len > 4;
   ctx->tiles_ok = true;
   return FC_OK;
 }
