@@ -19,7 +19,8 @@
 #include <string>
 #include <vector>
 
-constexpr int FC_TILE = 512;   // rows per tile = threads per CTA of k_tile_sweep
+constexpr int FC_TILE = 512;       // rows per tile = threads per CTA of k_tile_sweep
+constexpr int FC_TILE_MAXP = 16;   // producer tiles a tile can name for the point-to-point hand-over
 
 struct fc_tile_dir {                     // one sweep direction (strict lower or strict upper triangle)
   int nlev = 0;                          // tile levels
@@ -30,6 +31,12 @@ struct fc_tile_dir {                     // one sweep direction (strict lower or
   std::vector<int> blk_nlev;             // [nblocks] local levels of the tile
   std::vector<int> blk_level;            // [nblocks] tile level
   std::vector<int> lev_blocks_before;    // [nlev + 1] tiles in tile levels < L
+  // point-to-point hand-over: the tiles (block numbers, all smaller than the tile's own) whose rows a tile reads
+  // through global memory; p2p_ok = every tile has at most FC_TILE_MAXP of them
+  bool p2p_ok = false;
+  int max_producers = 0;
+  std::vector<int> prod;                 // [nblocks * FC_TILE_MAXP]
+  std::vector<int> prod_cnt;             // [nblocks]
 };
 
 struct fc_tile_schedule {
@@ -193,6 +200,21 @@ inline bool build_dir(int n, const int *ioffset, const int *ja, const int *diag,
     D.max_local_levels = std::max(D.max_local_levels, ll[i] + 1);
   }
   (void)tile_start;
+  D.prod.assign((size_t)ntiles * FC_TILE_MAXP, -1);
+  D.prod_cnt.assign(ntiles, 0);
+  D.p2p_ok = true;
+  D.max_producers = 0;
+  std::vector<int> nprod(ntiles, 0);
+  for (uint64_t ed : edges) {   // unique (producer, consumer) pairs
+    const int pb = block_of_tile[ed >> 32], cb = block_of_tile[(uint32_t)ed];
+    if (nprod[cb] < FC_TILE_MAXP) D.prod[(size_t)cb * FC_TILE_MAXP + nprod[cb]] = pb;
+    nprod[cb]++;
+  }
+  for (int b = 0; b < ntiles; ++b) {
+    D.max_producers = std::max(D.max_producers, nprod[b]);
+    D.prod_cnt[b] = std::min(nprod[b], FC_TILE_MAXP);
+    if (nprod[b] > FC_TILE_MAXP) D.p2p_ok = false;
+  }
   return true;
 }
 

@@ -334,11 +334,15 @@ k_tri_sweep(const int *__restrict__ rows, const int *__restrict__ blk_level,
 // slot).  Each row is still summed left to right over its triangle, so the result is bit-identical.
 // PRE = matrix entries of a row held in registers before the walk starts (4 covers hexahedra, 8 the 14-faced
 // polyhedra): an entry fetched inside the walk would put an L2 round trip on the critical path of a local level.
-template <int MODE, int PRE>
+// P2P (FC_TUNE_SWEEP_TILED = 2): a tile waits for the flags of the tiles it reads through global memory (3 on a
+// hexahedral mesh) instead of for the whole previous tile level, so tiles run ahead where the tile graph allows.
+static_assert(FC_TILE_MAXP == FC_TRI_MAXP, "one producer-table width");
+template <int MODE, int PRE, bool P2P>
 __global__ void __launch_bounds__(FC_TILE)
 k_tile_sweep(const int *__restrict__ rows, const int *__restrict__ llev, const int *__restrict__ blk_nlev,
              const int *__restrict__ blk_level, const int *__restrict__ lev_blocks_before, unsigned int *done,
-             unsigned int *ready, unsigned int *ticket, unsigned int ticket_base, unsigned int sweep_no,
+             unsigned int *ready, unsigned int *ticket, const int *__restrict__ prod,
+             const int *__restrict__ prod_cnt, unsigned int *flag, unsigned int ticket_base, unsigned int sweep_no,
              const int *__restrict__ ioffset, const int *__restrict__ tja, const int *__restrict__ diag,
              const int *__restrict__ tpos, const double *__restrict__ a, const double *__restrict__ d,
              const double *__restrict__ in, double *out, double small, double padd, const fc_scalars *sc) {
@@ -372,7 +376,15 @@ k_tile_sweep(const int *__restrict__ rows, const int *__restrict__ llev, const i
     else if (MODE == TRI_BWD) { di = d[row]; v = in[row] / (di + small); }   // z = z/(d+small), iccg.f90:102
     else v = a[diag[row]];
   }
-  if (lev > 0) {   // every tile of the previous tile level has published its rows
+  if (P2P) {
+    const int np = prod_cnt[b];
+    if ((int)threadIdx.x < np) {
+      const unsigned int *r = flag + prod[b * FC_TILE_MAXP + threadIdx.x];
+      fc_spin_guard g;
+      while (ld_acquire(r) < sweep_no) g.tick();
+    }
+    if (np > 0) __syncthreads();
+  } else if (lev > 0) {   // every tile of the previous tile level has published its rows
     if (threadIdx.x == 0) {
       const unsigned int *r = ready + (lev - 1);
       while (ld_acquire(r) < sweep_no) {}
@@ -412,9 +424,13 @@ k_tile_sweep(const int *__restrict__ rows, const int *__restrict__ llev, const i
     __syncthreads();   // the last one also orders every row's store before thread 0's release below
   }
   if (threadIdx.x == 0) {
-    const unsigned int nb = (unsigned int)(lev_blocks_before[lev + 1] - lev_blocks_before[lev]);
-    const unsigned int old = atom_add_acq_rel(done + lev, 1u);
-    if (old + 1u == sweep_no * nb) st_release(ready + lev, sweep_no);
+    if (P2P) {
+      st_release(flag + b, sweep_no);
+    } else {
+      const unsigned int nb = (unsigned int)(lev_blocks_before[lev + 1] - lev_blocks_before[lev]);
+      const unsigned int old = atom_add_acq_rel(done + lev, 1u);
+      if (old + 1u == sweep_no * nb) st_release(ready + lev, sweep_no);
+    }
   }
 }
 
@@ -425,16 +441,15 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
     fc_levels &T = (&L == &ctx->lower) ? ctx->tile_lower : ctx->tile_upper;
     const unsigned int tbase = (unsigned int)(T.epoch * (unsigned long long)T.nblocks);
     T.epoch++;
-    if (ctx->tiles_pre8)
-      k_tile_sweep<MODE, 8><<<T.nblocks, FC_TILE, 0, ctx->stream>>>(
-          T.rows, T.llev, T.blk_nlev, T.blk_level, T.lev_blocks_before, T.done, T.ready, T.ticket, tbase,
-          (unsigned int)T.epoch, ctx->ioffset, ctx->tja, ctx->diag, ctx->tpos, a, d, in, out, small, padd,
-          guarded ? ctx->sc : nullptr);
-    else
-      k_tile_sweep<MODE, 4><<<T.nblocks, FC_TILE, 0, ctx->stream>>>(
-          T.rows, T.llev, T.blk_nlev, T.blk_level, T.lev_blocks_before, T.done, T.ready, T.ticket, tbase,
-          (unsigned int)T.epoch, ctx->ioffset, ctx->tja, ctx->diag, ctx->tpos, a, d, in, out, small, padd,
-          guarded ? ctx->sc : nullptr);
+    const bool p2p = ctx->tune_sweep_tiled == 2 && T.p2p_ok;
+#define FC_TILE_LAUNCH(PRE_, P2P_)                                                                                   \
+  k_tile_sweep<MODE, PRE_, P2P_><<<T.nblocks, FC_TILE, 0, ctx->stream>>>(                                             \
+      T.rows, T.llev, T.blk_nlev, T.blk_level, T.lev_blocks_before, T.done, T.ready, T.ticket, T.prod, T.prod_cnt,    \
+      T.flag, tbase, (unsigned int)T.epoch, ctx->ioffset, ctx->tja, ctx->diag, ctx->tpos, a, d, in, out, small, padd, \
+      guarded ? ctx->sc : nullptr)
+    if (ctx->tiles_pre8) { if (p2p) FC_TILE_LAUNCH(8, true); else FC_TILE_LAUNCH(8, false); }
+    else                 { if (p2p) FC_TILE_LAUNCH(4, true); else FC_TILE_LAUNCH(4, false); }
+#undef FC_TILE_LAUNCH
     FC_LAUNCH_CHECK();
     return FC_OK;
   }
@@ -478,14 +493,19 @@ int upload_tile_dir(fc_context *ctx, const fc_tile_dir &D, fc_levels &L) {
   FC_CHECK(fc_dev_alloc(ctx, &L.done, (size_t)D.nlev));
   FC_CHECK(fc_dev_alloc(ctx, &L.ready, (size_t)D.nlev));
   FC_CHECK(fc_dev_alloc(ctx, &L.ticket, 1));
+  FC_CHECK(fc_dev_alloc(ctx, &L.prod, D.prod.size()));
+  FC_CHECK(fc_dev_alloc(ctx, &L.prod_cnt, D.prod_cnt.size()));
+  FC_CHECK(fc_dev_alloc(ctx, &L.flag, (size_t)D.nblocks));
+  L.p2p_ok = D.p2p_ok;
   const struct { int *dst; const std::vector<int> *src; } up[] = {
       {L.rows, &D.rows}, {L.llev, &D.llev}, {L.blk_nlev, &D.blk_nlev}, {L.blk_level, &D.blk_level},
-      {L.lev_blocks_before, &D.lev_blocks_before}};
+      {L.lev_blocks_before, &D.lev_blocks_before}, {L.prod, &D.prod}, {L.prod_cnt, &D.prod_cnt}};
   for (const auto &u : up)
     FC_CUDA(cudaMemcpyAsync(u.dst, u.src->data(), sizeof(int) * u.src->size(), cudaMemcpyHostToDevice, ctx->stream));
   FC_CUDA(cudaMemsetAsync(L.done, 0, sizeof(unsigned int) * (size_t)D.nlev, ctx->stream));
   FC_CUDA(cudaMemsetAsync(L.ready, 0, sizeof(unsigned int) * (size_t)D.nlev, ctx->stream));
   FC_CUDA(cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), ctx->stream));
+  FC_CUDA(cudaMemsetAsync(L.flag, 0, sizeof(unsigned int) * (size_t)D.nblocks, ctx->stream));
   FC_CUDA(cudaStreamSynchronize(ctx->stream));   // the host vectors go away
   L.epoch = 0;
   return FC_OK;

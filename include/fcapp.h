@@ -348,7 +348,8 @@ enum {
                                   same row sums, bit-identical results)                      */
   FC_TUNE_SWEEP_TILED = 5      /* triangular sweeps: [0] one hand-over per dependency level,
                                   1 two-level schedule -- spatial tiles of <= 512 cells walked
-                                  inside one CTA, hand-overs only between tiles (experimental;
+                                  inside one CTA, hand-overs only between tile levels, 2 the
+                                  same with point-to-point flags between tiles (experimental;
                                   needs a mesh whose numbering is monotone across the tiles, else
                                   the level schedule stays; same row sums, bit-identical results) */
 };

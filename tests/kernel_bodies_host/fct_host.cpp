@@ -45,6 +45,8 @@ void fct_info(void *h, int *out) {
   out[0] = S.ntiles; out[1] = S.cells_per_axis; out[2] = S.max_tile_rows;
   out[3] = S.lower.nlev; out[4] = S.lower.max_local_levels;
   out[5] = S.upper.nlev; out[6] = S.upper.max_local_levels;
+  out[7] = S.lower.p2p_ok && S.upper.p2p_ok ? 1 : 0;
+  out[8] = std::max(S.lower.max_producers, S.upper.max_producers);
 }
 
 // the sweep in the reference's own order: rows ascending (lower triangle) or descending (upper)
@@ -66,7 +68,7 @@ int fct_sweep(void *h, int mode, int n, const int *ioffset, const int *diag, con
   const fc_tile_schedule &S = *(fc_tile_schedule *)h;
   const fc_tile_dir &D = mode == TRI_BWD ? S.upper : S.lower;
   const bool bwd = mode == TRI_BWD;
-  std::vector<int> produced_level(n, -1);
+  std::vector<int> produced_level(n, -1), produced_block(n, -1);
   std::vector<double> s_z(FC_TILE);
   int bad = 0, visited = 0;
   for (int b = 0; b < D.nblocks; ++b) {
@@ -84,7 +86,15 @@ int fct_sweep(void *h, int mode, int n, const int *ioffset, const int *diag, con
           const int j = S.tja[k];
           double zj;
           if (j < 0) zj = s_z[-j - 1];
-          else { zj = out[j]; if (produced_level[j] < 0 || produced_level[j] >= lev) ++bad; }
+          else {
+            zj = out[j];
+            if (produced_level[j] < 0 || produced_level[j] >= lev) ++bad;
+            if (D.p2p_ok) {   // point-to-point hand-over: the producing tile must be one the tile waits for
+              bool named = false;
+              for (int p = 0; p < D.prod_cnt[b]; ++p) named = named || D.prod[(size_t)b * FC_TILE_MAXP + p] == produced_block[j];
+              if (!named || produced_block[j] >= b) ++bad;
+            }
+          }
           if (std::isnan(zj)) ++bad;
           v = step(mode, v, a[k], zj, mode == TRI_DILU ? a[tpos[k]] : 0.0);
         }
@@ -92,6 +102,7 @@ int fct_sweep(void *h, int mode, int n, const int *ioffset, const int *diag, con
         s_z[t] = r;
         out[row] = r;
         produced_level[row] = lev;
+        produced_block[row] = b;
         ++visited;
       }
   }

@@ -33,17 +33,17 @@ def fc():
 
 @pytest.mark.parametrize("name", list(MESHES))
 @pytest.mark.parametrize("solver", ["iccg", "bicgstab"])
-@pytest.mark.parametrize("mode", ["p2p", "tiled"])
+@pytest.mark.parametrize("mode", ["p2p", "tiled", "tiled-p2p"])
 def test_sweep_variants_are_bit_identical_to_level_sweeps(fc, name, solver, mode):
     mesh = MESHES[name]()
-    key = fc.TUNE_SWEEP_P2P if mode == "p2p" else fc.TUNE_SWEEP_TILED
+    key, value = {"p2p": (fc.TUNE_SWEEP_P2P, 1), "tiled": (fc.TUNE_SWEEP_TILED, 1), "tiled-p2p": (fc.TUNE_SWEEP_TILED, 2)}[mode]
     su = np.random.default_rng(5).standard_normal(mesh.numCells) * mesh.vol[:mesh.numCells]
     res = []
     for p2p in (0, 1):
         ctx = fc.Context(0)
         ctx.set_mesh(mesh)
         ctx.create_csr(download=False)
-        ctx.set_tuning(key, p2p)
+        ctx.set_tuning(key, value * p2p)
         ctx.upload("APU", -np.ones(mesh.numCells))
         ctx.upload("SU", su)
         ctx.fill("PP", 0.0)
@@ -57,7 +57,7 @@ def test_sweep_variants_are_bit_identical_to_level_sweeps(fc, name, solver, mode
             ms = ctx.timings().solve_ms
             best = ms if best is None else min(best, ms)
         res.append((rep.iters, rep.res0, rep.resl, ctx.download("PP"), ctx.download("RES"), best))
-        if mode == "tiled" and p2p and name in ("hex", "slab", "poly"):
+        if mode.startswith("tiled") and p2p and name in ("hex", "slab", "poly"):
             assert ctx.timings().sweep_tiles > 0, "the tiled schedule was not used"
         ctx.close()
     (i0, a0, b0, x0, r0, t0), (i1, a1, b1, x1, r1, t1) = res

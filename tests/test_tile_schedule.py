@@ -82,7 +82,7 @@ MESHES = {
 
 def build(host, s):
     h = host.fct_build(s.n, ip(s.ioffset), ip(s.ja), ip(s.diag), dp(s.xc), dp(s.yc), dp(s.zc))
-    info = np.zeros(7, np.int32)
+    info = np.zeros(9, np.int32)
     host.fct_info(C.c_void_p(h), ip(info))
     return h, info
 
@@ -108,7 +108,7 @@ def test_tiled_sweeps_equal_natural_order_sweeps(host, name):
             assert name in ("pitzDaily", "poly-6", "skew"), (name, why)
             assert why
             pytest.skip(f"{name}: no tiling ({why}); the library keeps the level schedule")
-        ntiles, cells, maxrows, lnlev, lloc, unlev, uloc = info
+        ntiles, cells, maxrows, lnlev, lloc, unlev, uloc, p2p_ok, maxprod = info
         assert 1 <= maxrows <= 512 and ntiles >= 1 and 2 <= cells <= 512
         zero = np.zeros(s.n)
         for mode in (DIC, DIC_PAR, DILU):
@@ -130,10 +130,11 @@ def test_tile_levels_of_a_cube_are_the_tile_hyperplanes(host):
     3*8-2 = 22 local levels per tile."""
     s = System(cases.hex_case(32, 32, 32))
     h, info = build(host, s)
-    ntiles, cells, maxrows, lnlev, lloc, unlev, uloc = info
+    ntiles, cells, maxrows, lnlev, lloc, unlev, uloc, p2p_ok, maxprod = info
     host.fct_free(C.c_void_p(h))
     assert (ntiles, cells, maxrows) == (64, 8, 512)
     assert (lnlev, unlev) == (10, 10) and (lloc, uloc) == (22, 22)
+    assert p2p_ok == 1 and maxprod == 3          # the three face neighbours on the low (high) side
 
 
 def test_a_numbering_that_is_not_monotone_across_the_bins_is_refused(host):

@@ -98,9 +98,10 @@ def main():
         t = ctx.timings()
         report(f"{solver} iteration", t.solve_ms / max(rep.iters, 1), nbytes, iters=rep.iters, solve_ms=t.solve_ms)
     # experimental sweep schedules (off by default), last so that a failure cannot take the lines above with it
-    for key, label in ((lib.TUNE_SWEEP_TILED, "tiled sweeps"), (lib.TUNE_SWEEP_P2P, "p2p sweeps")):
+    for key, value, label in ((lib.TUNE_SWEEP_TILED, 1, "tiled sweeps"), (lib.TUNE_SWEEP_TILED, 2, "tiled sweeps + p2p flags"),
+                              (lib.TUNE_SWEEP_P2P, 1, "p2p sweeps")):
         try:
-            ctx.set_tuning(key, 1)
+            ctx.set_tuning(key, value)
             for solver, nbytes in (("iccg", 24 * nnz + 164 * nc), ("bicgstab", 2 * (24 * nnz + 164 * nc))):
                 for _ in range(2):
                     ctx.fill("PP", 0.0)
