@@ -237,3 +237,73 @@ FCM_HD void fcg_limiter_row(const fcm_geom &g, const int *ioffset, const int *ja
   FCM_G3(grad, 1, c) = slopelimit * gy;
   FCM_G3(grad, 2, c) = slopelimit * gz;
 }
+
+// ---- three Gauss gradients in one walk (opt-in, FC_TUNE_FUSED_GRAD) ----
+// grad_gauss (grad_gauss.f90:43-113; gradco :128-190; gradbc :194-211) applied to u, v and w at once: calcuvw
+// (:59-61) and calcp (:38-40) always ask for the three velocity gradients together, and two thirds of what one pass
+// reads -- the cell-to-face map, the face vectors and the interpolation factors -- does not depend on the field.
+// Per field the expressions and their order are those of k_grad_pass (fc_assemble.cu), so each gradient is
+// bit-identical to the one-field pass.  npro / fpro: processor faces of the multi-rank build
+// (src-parallel/grad_gauss.f90:68-75), halo cell = n + i.
+struct fcg_gauss3 {
+  int npro;
+  const double *fpro;
+  const double *phi[3];   // u, v, w  [numTotal]
+  const double *old[3];   // gradients of the previous pass (HAS_OLD) or unused
+  double *out[3];         // (3,numCells)
+};
+
+template <bool HAS_OLD>
+FCM_HD void fcg_gauss3_row(const fcm_geom &g, const fcm_c2f &m, const fcg_gauss3 &k, int c) {
+  double gx[3] = {0.0, 0.0, 0.0}, gy[3] = {0.0, 0.0, 0.0}, gz[3] = {0.0, 0.0, 0.0};
+  const int s = m.off[c], e = m.off[c + 1];
+  for (int q = s; q < e; ++q) {
+    const int fe = m.face[q];
+    const int f = fe & 0x7fffffff;
+    const int o = m.other[q];
+    const double sx = g.arx[f], sy = g.ary[f], sz = g.arz[f];
+    if (f < g.F || o < g.n + k.npro) {
+      const bool nb = fe < 0;
+      const int ijp = nb ? o : c, ijn = nb ? c : o;
+      const double fxn = (f < g.F) ? g.facint[f] : k.fpro[o - g.n], fxp = 1.0 - fxn;
+      double dx = 0.0, dy = 0.0, dz = 0.0;
+      if (HAS_OLD) {
+        const double xi = g.xc[ijp] * fxp + g.xc[ijn] * fxn;
+        const double yi = g.yc[ijp] * fxp + g.yc[ijn] * fxn;
+        const double zi = g.zc[ijp] * fxp + g.zc[ijn] * fxn;
+        dx = g.xf[f] - xi; dy = g.yf[f] - yi; dz = g.zf[f] - zi;
+      }
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+      for (int t = 0; t < 3; ++t) {
+        const double *phi = k.phi[t];
+        double fie = phi[ijp] * fxp + phi[ijn] * fxn;
+        if (HAS_OLD) {
+          const double *dfo = k.old[t];
+          const double dfxi = FCM_G3(dfo, 0, ijp) * fxp + FCM_G3(dfo, 0, ijn) * fxn;
+          const double dfyi = FCM_G3(dfo, 1, ijp) * fxp + FCM_G3(dfo, 1, ijn) * fxn;
+          const double dfzi = FCM_G3(dfo, 2, ijp) * fxp + FCM_G3(dfo, 2, ijn) * fxn;
+          fie = fie + dfxi * dx + dfyi * dy + dfzi * dz;
+        }
+        const double dfxe = fie * sx, dfye = fie * sy, dfze = fie * sz;
+        if (nb) { gx[t] = gx[t] - dfxe; gy[t] = gy[t] - dfye; gz[t] = gz[t] - dfze; }
+        else    { gx[t] = gx[t] + dfxe; gy[t] = gy[t] + dfye; gz[t] = gz[t] + dfze; }
+      }
+    } else {
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+      for (int t = 0; t < 3; ++t) {
+        const double fi = k.phi[t][o];
+        gx[t] = gx[t] + fi * sx; gy[t] = gy[t] + fi * sy; gz[t] = gz[t] + fi * sz;
+      }
+    }
+  }
+  const double volr = 1.0 / g.vol[c];
+  for (int t = 0; t < 3; ++t) {
+    FCM_G3(k.out[t], 0, c) = gx[t] * volr;
+    FCM_G3(k.out[t], 1, c) = gy[t] * volr;
+    FCM_G3(k.out[t], 2, c) = gz[t] * volr;
+  }
+}

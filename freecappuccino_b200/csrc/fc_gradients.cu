@@ -36,6 +36,13 @@ k_grad_lsq_qr(fcm_geom g, fcm_c2f m, const double *D, const double *fi, double *
   if (c < g.n) fcg_grad_lsq_qr_row(g, m, D, fi, out, c);
 }
 
+// u, v, w in one walk over the map (fcg_gauss3_row); 5 CTAs of 256 threads per SM keep 3 x 3 accumulators in registers
+template <bool HAS_OLD>
+__global__ void __launch_bounds__(256) k_grad_pass3(fcm_geom g, fcm_c2f m, fcg_gauss3 k) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < g.n) fcg_gauss3_row<HAS_OLD>(g, m, k, c);
+}
+
 // glomin / glomax = minval / maxval(phi(1:numCells)): min and max do not depend on the order, so a plain
 // two-stage tree gives the reference's values exactly
 __global__ void __launch_bounds__(256) k_minmax_partial(int n, const double *phi, double *part) {
@@ -104,6 +111,40 @@ int fc_grad_dev(fc_context *ctx, double *phi, double *grad, int nigrad) {
     FC_LAUNCH_CHECK();
   }
   return fc_limit_gradient_dev(ctx, phi, grad);
+}
+
+// grad(U), grad(V), grad(W) as calcuvw (:59-61) and calcp (:38-40) ask for them.  With FC_TUNE_FUSED_GRAD and plain Gauss
+// gradients the three fields share one kernel per pass; otherwise three calls of the dispatcher.
+int fc_grad_uvw_dev(fc_context *ctx, int nigrad) {
+  double **fl = ctx->field;
+  double *phi[3] = {fl[FC_U], fl[FC_V], fl[FC_W]}, *grad[3] = {fl[FC_DUDXI], fl[FC_DVDXI], fl[FC_DWDXI]};
+  if (!ctx->tune_fused_grad || ctx->grad_method != 0 || ctx->grad_limiter != 0 || !ctx->has_mesh || !ctx->c2f_off) {
+    for (int t = 0; t < 3; ++t) FC_CHECK(fc_grad_dev(ctx, phi[t], grad[t], nigrad));
+    return FC_OK;
+  }
+  if (nigrad < 1) FC_FAIL(FC_ERR_ARG, "fc_grad_gauss: nigrad < 1");
+  const size_t g3 = 3 * (size_t)ctx->NP;
+  if (nigrad > 1 && !ctx->gtmp3) FC_CHECK(fc_dev_alloc(ctx, &ctx->gtmp3, 3 * g3));
+  const int B = 256, G = fc_blocks(ctx->n, B);
+  if (ctx->npro > 0)
+    for (int t = 0; t < 3; ++t) FC_CHECK(fc_halo_exchange(ctx, phi[t]));
+  fcg_gauss3 k{ctx->npro, ctx->fpro, {phi[0], phi[1], phi[2]}, {nullptr, nullptr, nullptr}, {grad[0], grad[1], grad[2]}};
+  for (int lc = 1; lc <= nigrad; ++lc) {
+    if (lc == 1) {
+      k_grad_pass3<false><<<G, B, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), k);
+    } else {
+      for (int t = 0; t < 3; ++t) {
+        if (ctx->npro > 0) FC_CHECK(fc_halo_exchange3(ctx, grad[t]));
+        FC_CUDA(cudaMemcpyAsync(ctx->gtmp3 + t * g3, grad[t], sizeof(double) * g3, cudaMemcpyDeviceToDevice, ctx->stream));
+        k.old[t] = ctx->gtmp3 + t * g3;
+      }
+      k_grad_pass3<true><<<G, B, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), k);
+    }
+    FC_LAUNCH_CHECK();
+  }
+  if (ctx->npro > 0)
+    for (int t = 0; t < 3; ++t) FC_CHECK(fc_halo_exchange3(ctx, grad[t]));
+  return FC_OK;
 }
 
 // lstsq / lstsq_qr / lstsq_dm / gauss flags + `limiter` of the input file; builds the geometric matrices

@@ -137,6 +137,7 @@ struct fc_context {
   double *coef = nullptr;               // per-face coefficient cap = can [F + npro]
   double *facev = nullptr;              // per-face scratch [NF]
   double *gtmp = nullptr;               // previous-pass gradient (3,numCells)
+  double *gtmp3 = nullptr;              // the same for the fused u, v, w pass (FC_TUNE_FUSED_GRAD, nigrad > 1)
   // gradient scheme of the `grad` dispatcher (fc_set_gradient): 0 gauss, 1 lstsq, 2 lstsq_qr, 3 lstsq_dm; limiter 0..3
   int grad_method = 0, grad_limiter = 0;
   double grad_small = 0.0;
@@ -178,6 +179,7 @@ struct fc_context {
   int tune_pipe = 1;                    // staging geometry of the TMA pipeline (threads, capacity, stages)
   int tune_ctas_per_sm = 0;             // persistent kernel: CTAs per SM (0 = as many as fit)
   int tune_sweep_p2p = 0;               // triangular sweeps: 1 = point-to-point block flags instead of level counters
+  int tune_fused_grad = 0;              // 1: the three velocity gradients of calcuvw / calcp in one kernel per pass
   int tune_sweep_tiled = 0;             // triangular sweeps: 1 = two-level tiled schedule where the mesh allows it
   fc_persist_state *persist = nullptr;  // device: grid barrier + phase clocks of the persistent kernel
   fc_persist_state *persist_host = nullptr;
@@ -270,5 +272,6 @@ int fc_calcuvw_component_dev(fc_context *ctx, const fc_calcuvw_opts *o, int comp
 int fc_calcuvw_dev(fc_context *ctx, const fc_calcuvw_opts *o, fc_calcuvw_report *rep);
 int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep);             // fc_assemble.cu
 int fc_grad_dev(fc_context *ctx, double *phi, double *grad, int nigrad);                   // fc_gradients.cu
+int fc_grad_uvw_dev(fc_context *ctx, int nigrad);                                              // fc_gradients.cu: grad(U), grad(V), grad(W)
 int fc_limit_gradient_dev(fc_context *ctx, const double *phi, double *grad);
 int fc_set_gradient_dev(fc_context *ctx, int method, int limiter, double small);

@@ -110,9 +110,7 @@ int fc_calcuvw_assemble_dev(fc_context *ctx, const fc_calcuvw_opts *o) {
   cudaStream_t st = ctx->stream;
   FC_CUDA(cudaEventRecord(ctx->ev[2], st));
   // grad(U), grad(V), grad(W)   (:59-61)
-  FC_CHECK(fc_grad_dev(ctx, ctx->field[FC_U], ctx->field[FC_DUDXI], o->nigrad));
-  FC_CHECK(fc_grad_dev(ctx, ctx->field[FC_V], ctx->field[FC_DVDXI], o->nigrad));
-  FC_CHECK(fc_grad_dev(ctx, ctx->field[FC_W], ctx->field[FC_DWDXI], o->nigrad));
+  FC_CHECK(fc_grad_uvw_dev(ctx, o->nigrad));
   // calcPressDiv: boundary pressure + pressure gradient (fieldManipulation.f90:82-87)
   for (int istage = 1; istage <= o->nipgrad; ++istage) {
     FC_CHECK(fc_bpres_dev(ctx, ctx->field[FC_P], ctx->field[FC_DPDXI], istage));

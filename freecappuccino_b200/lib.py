@@ -47,6 +47,7 @@ GRAD_METHODS = {"gauss": 0, "lstsq": 1, "lstsq_qr": 2, "lstsq_dm": 3}
 LIMITERS = {"no-limit": 0, "Barth-Jespersen": 1, "Venkatakrishnan": 2, "mVenkatakrishnan": 3}
 TUNE_SPMV_KERNEL, TUNE_DPCG_PERSISTENT, TUNE_CTAS_PER_SM, TUNE_PIPE_GEOMETRY, TUNE_SWEEP_P2P = 0, 1, 2, 3, 4
 TUNE_SWEEP_TILED = 5
+TUNE_FUSED_GRAD = 6
 
 
 class MeshDesc(C.Structure):

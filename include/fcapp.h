@@ -346,6 +346,8 @@ enum {
   FC_TUNE_SWEEP_P2P = 4,       /* triangular sweeps (iccg, bicgstab): [0] one counter per level,
                                   1 point-to-point flags between 128-row blocks (experimental:
                                   same row sums, bit-identical results)                      */
+  FC_TUNE_FUSED_GRAD = 6,      /* grad(U), grad(V), grad(W) of calcuvw / calcp: [0] three Gauss passes, 1 one kernel
+                                  per pass for the three fields (experimental; each gradient bit-identical) */
   FC_TUNE_SWEEP_TILED = 5      /* triangular sweeps: [0] one hand-over per dependency level,
                                   1 two-level schedule -- spatial tiles of <= 512 cells walked
                                   inside one CTA, hand-overs only between tile levels, 2 the

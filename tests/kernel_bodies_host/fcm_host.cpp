@@ -61,6 +61,21 @@ void fcg_host_limiter(const fcm_geom *g, const int *ioffset, const int *ja, cons
   for (int c = 0; c < g->n; ++c) fcg_limiter_row(*g, ioffset, ja, diag, which, phi, grad, glomin, glomax, small, c);
 }
 
+// u, v, w Gauss gradients in one walk (fcg_gauss3_row): nigrad passes, the later ones seeded with the previous result
+void fcg_host_gauss3(const fcm_geom *g, const fcm_c2f *m, int npro, const double *fpro, const double *u,
+                     const double *v, const double *w, double *dU, double *dV, double *dW, double *oU, double *oV,
+                     double *oW, int nigrad) {
+  fcg_gauss3 k{npro, fpro, {u, v, w}, {oU, oV, oW}, {dU, dV, dW}};
+  for (int lc = 1; lc <= nigrad; ++lc) {
+    if (lc == 1) {
+      for (int c = 0; c < g->n; ++c) fcg_gauss3_row<false>(*g, *m, k, c);
+    } else {
+      for (size_t i = 0; i < 3 * (size_t)g->n; ++i) { oU[i] = dU[i]; oV[i] = dV[i]; oW[i] = dW[i]; }
+      for (int c = 0; c < g->n; ++c) fcg_gauss3_row<true>(*g, *m, k, c);
+    }
+  }
+}
+
 int fcm_host_sizes(int which) {
   switch (which) {
     case 0: return (int)sizeof(fcm_geom);

@@ -64,3 +64,32 @@ def test_sweep_variants_are_bit_identical_to_level_sweeps(fc, name, solver, mode
     print(f"\\n[{mode} sweeps] {name} {solver}: {i0} iterations, level mode {t0:.3f} ms, {mode} mode {t1:.3f} ms")
     assert i0 == i1 and a0 == a1 and b0 == b1
     assert np.array_equal(x0, x1) and np.array_equal(r0, r1)
+
+
+@pytest.mark.parametrize("name", ["hex", "poly", "pitzDaily"])
+@pytest.mark.parametrize("nigrad", [1, 2])
+def test_fused_velocity_gradients_are_bit_identical(fc, name, nigrad):
+    """FC_TUNE_FUSED_GRAD: grad(U), grad(V), grad(W) of calcp / calcuvw in one kernel per pass; gradients, matrix and
+    right-hand side of both assemblies must not change by a bit."""
+    mesh = MESHES[name]()
+    f = cases.flow_fields(mesh)
+    res = []
+    for fused in (0, 1):
+        ctx = fc.Context(0)
+        ctx.set_mesh(mesh)
+        ctx.create_csr(download=False)
+        ctx.set_tuning(fc.TUNE_FUSED_GRAD, fused)
+        for k, fld in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("apu", "APU"), ("apv", "APV"),
+                       ("apw", "APW")):
+            ctx.upload(fld, f[k])
+        ctx.upload("VIS", np.full(mesh.numTotal, 0.01))
+        ctx.fill("FLMASS", 0.0)
+        ctx.grad_gauss("P", "DPDXI", 1)
+        ctx.calcp_assemble(fc.calcp_opts(solver="iccg", const_mflux=True, nigrad=nigrad))
+        out = [ctx.download(k) for k in ("DUDXI", "DVDXI", "DWDXI", "A", "SU", "FLMASS")]
+        ctx.calcuvw_assemble(fc.calcuvw_opts(scheme="muscl-f", nigrad=nigrad))
+        out += [ctx.download(k) for k in ("DUDXI", "A", "SU", "SV", "SW")]
+        res.append(out)
+        ctx.close()
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)

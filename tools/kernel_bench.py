@@ -74,6 +74,12 @@ def main():
     ctx.fill("FLMASS", 0.0)
     report("calcuvw explicit part (5 grads + bpres + faces + rows)", timed(lambda: ctx.calcuvw_assemble(uo), 5),
            5 * grad_b + (120 * F + 160 * nc) + (184 * F + 88 * nc))
+    ctx.set_tuning(lib.TUNE_FUSED_GRAD, 1)
+    report("calcp assembly, fused u/v/w gradient", timed(lambda: ctx.calcp_assemble(po), 5),
+           3 * grad_b + 96 * F + 208 * nc + 16 * F)
+    report("calcuvw explicit part, fused u/v/w gradient", timed(lambda: ctx.calcuvw_assemble(uo), 5),
+           5 * grad_b + (120 * F + 160 * nc) + (184 * F + 88 * nc))
+    ctx.set_tuning(lib.TUNE_FUSED_GRAD, 0)
     for method, nbytes in (("lstsq", 44 * (2 * F + B) + 96 * nc), ("lstsq_dm", 44 * (2 * F + B) + 96 * nc),
                            ("lstsq_qr", 12 * (2 * F + B) + 168 * nc)):
         try:
