@@ -48,6 +48,31 @@ def test_struct_layouts_match_header(tmp_path):
     assert got == want
 
 
+def test_enum_constants_match_header(tmp_path):
+    """Tuning keys, gradient / limiter ids, solver ids and error codes of lib.py are the header's values."""
+    import subprocess
+    from freecappuccino_b200 import lib
+    names = ["FC_TUNE_SPMV_KERNEL", "FC_TUNE_DPCG_PERSISTENT", "FC_TUNE_CTAS_PER_SM", "FC_TUNE_PIPE_GEOMETRY",
+             "FC_TUNE_SWEEP_P2P", "FC_TUNE_SWEEP_TILED", "FC_TUNE_FUSED_GRAD", "FC_DPCG", "FC_ICCG", "FC_BICGSTAB",
+             "FC_OK", "FC_ERR_ARG", "FC_ERR_CUDA", "FC_ERR_NCCL", "FC_ERR_UNSUPPORTED", "FC_ERR_NODEVICE",
+             "FC_VIS", "FC_SP", "FC_FLMASS", "FC_USER3"]
+    src = tmp_path / "enums.c"
+    src.write_text('#include <stdio.h>\n#include "fcapp.h"\nint main(void){printf("' + " ".join(["%d"] * len(names)) +
+                   '\\n", ' + ", ".join(f"(int){n}" for n in names) + ");return 0;}\n")
+    exe = tmp_path / "enums"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(zip(names, (int(x) for x in subprocess.check_output([str(exe)], text=True).split())))
+    want = {"FC_TUNE_SPMV_KERNEL": lib.TUNE_SPMV_KERNEL, "FC_TUNE_DPCG_PERSISTENT": lib.TUNE_DPCG_PERSISTENT,
+            "FC_TUNE_CTAS_PER_SM": lib.TUNE_CTAS_PER_SM, "FC_TUNE_PIPE_GEOMETRY": lib.TUNE_PIPE_GEOMETRY,
+            "FC_TUNE_SWEEP_P2P": lib.TUNE_SWEEP_P2P, "FC_TUNE_SWEEP_TILED": lib.TUNE_SWEEP_TILED,
+            "FC_TUNE_FUSED_GRAD": lib.TUNE_FUSED_GRAD, "FC_DPCG": lib.DPCG, "FC_ICCG": lib.ICCG,
+            "FC_BICGSTAB": lib.BICGSTAB, "FC_OK": lib.FC_OK, "FC_ERR_ARG": lib.FC_ERR_ARG, "FC_ERR_CUDA": lib.FC_ERR_CUDA,
+            "FC_ERR_NCCL": lib.FC_ERR_NCCL, "FC_ERR_UNSUPPORTED": lib.FC_ERR_UNSUPPORTED,
+            "FC_ERR_NODEVICE": lib.FC_ERR_NODEVICE, "FC_VIS": lib.F["VIS"], "FC_SP": lib.F["SP"],
+            "FC_FLMASS": lib.F["FLMASS"], "FC_USER3": lib.F["USER3"]}
+    assert got == want
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
