@@ -9,9 +9,13 @@
 // rows keep their natural numbering (iccg.f90:77-111, bicgstab.f90:68-79, :117-136), every row is still summed left
 // to right, only the order in which independent rows are visited differs.
 //
-// A tiling is usable when the tile-to-tile dependency graph is acyclic (always true for lexicographically numbered
-// structured meshes; checked, never assumed) and no tile exceeds FC_TILE rows; otherwise `ok` is false and the
-// caller keeps the level schedule.
+// The tile-to-tile dependency graph must be acyclic and no tile may exceed FC_TILE rows.  Bins over a
+// lexicographically numbered structured mesh satisfy both; anywhere else (block-structured or renumbered meshes,
+// strong grading) the offending bins are found (strongly connected components) and cut into runs of consecutive row
+// numbers, which are acyclic by construction (repair_tiles).  The result is always valid (build_dir re-checks); it is
+// not always *good* -- a mesh whose numbering ignores space altogether ends up as one long chain -- so the schedule
+// carries a critical-path estimate (`cost`) and the caller keeps the level schedule unless the tiling is clearly
+// cheaper.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -45,6 +49,8 @@ struct fc_tile_schedule {
   int ntiles = 0;
   int cells_per_axis = 0;                // the bin width that worked
   int max_tile_rows = 0;
+  int repaired_rows = 0;                 // rows of bins that had to be cut into runs of consecutive row numbers
+  long long cost = 0;                    // critical path estimate in 0.1 us: see fc_tile_cost
   int max_tri_len = 0;                   // longest strict-triangle row (how many entries the kernel keeps in registers)
   std::vector<int> tja;                  // [nnz] column j, or -(q+1) when row j is slot q of the same tile
   fc_tile_dir lower, upper;
@@ -218,6 +224,107 @@ inline bool build_dir(int n, const int *ioffset, const int *ja, const int *diag,
   return true;
 }
 
+// Make any bin assignment usable: bins that depend on each other in a circle (cell numbering not monotone across
+// them -- multi-block or renumbered meshes) are merged into one group, and every group that is merged or larger than
+// FC_TILE rows is cut again into runs of consecutive row numbers.  Runs of one group depend on each other only from
+// low to high row number (the matrix is triangular in the natural numbering), and a tile outside a group is either
+// upstream or downstream of the whole group (otherwise it would belong to it), so the result has no cycle.
+// Returns the new number of tiles; `repaired` counts the rows that ended up in such runs.
+inline int repair_tiles(int n, const int *ioffset, const int *ja, const int *diag, std::vector<int> &tile, int ntiles,
+                        int &repaired) {
+  // tile graph of the lower triangle (the upper one is its reverse: same strongly connected components)
+  std::vector<uint64_t> edges;
+  for (int i = 0; i < n; ++i) {
+    for (int k = ioffset[i]; k < diag[i]; ++k) {
+      const int j = ja[k];
+      if (j < n && tile[j] != tile[i]) edges.push_back(((uint64_t)(uint32_t)tile[j] << 32) | (uint32_t)tile[i]);
+    }
+    if ((i & 0xfffff) == 0xfffff) {
+      std::sort(edges.begin(), edges.end());
+      edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+    }
+  }
+  std::sort(edges.begin(), edges.end());
+  edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+  std::vector<int> off(ntiles + 1, 0), adj(edges.size());
+  for (uint64_t ed : edges) off[(ed >> 32) + 1]++;
+  for (int t = 0; t < ntiles; ++t) off[t + 1] += off[t];
+  {
+    std::vector<int> fill(off.begin(), off.end() - 1);
+    for (uint64_t ed : edges) adj[fill[ed >> 32]++] = (int)(uint32_t)ed;
+  }
+  // Tarjan's strongly connected components, iterative
+  std::vector<int> index(ntiles, -1), low(ntiles, 0), comp(ntiles, -1), stack, next(ntiles, 0), call;
+  std::vector<char> on_stack(ntiles, 0);
+  int counter = 0, ncomp = 0;
+  for (int root = 0; root < ntiles; ++root) {
+    if (index[root] >= 0) continue;
+    call.push_back(root);
+    while (!call.empty()) {
+      const int v = call.back();
+      if (index[v] < 0) { index[v] = low[v] = counter++; stack.push_back(v); on_stack[v] = 1; next[v] = off[v]; }
+      bool descended = false;
+      while (next[v] < off[v + 1]) {
+        const int w = adj[next[v]++];
+        if (index[w] < 0) { call.push_back(w); descended = true; break; }
+        if (on_stack[w]) low[v] = std::min(low[v], index[w]);
+      }
+      if (descended) continue;
+      if (low[v] == index[v]) {
+        for (;;) {
+          const int w = stack.back();
+          stack.pop_back();
+          on_stack[w] = 0;
+          comp[w] = ncomp;
+          if (w == v) break;
+        }
+        ++ncomp;
+      }
+      call.pop_back();
+      if (!call.empty()) low[call.back()] = std::min(low[call.back()], low[v]);
+    }
+  }
+  std::vector<int> comp_tiles(ncomp, 0), comp_rows(ncomp, 0);
+  {
+    std::vector<char> seen(ntiles, 0);
+    for (int i = 0; i < n; ++i) {
+      const int t = tile[i];
+      comp_rows[comp[t]]++;
+      if (!seen[t]) { seen[t] = 1; comp_tiles[comp[t]]++; }
+    }
+  }
+  // new numbering: untouched groups keep one tile; the others get ceil(rows / FC_TILE) runs of (nearly) equal length
+  std::vector<int> first(ncomp, 0), runs(ncomp, 1);
+  int total = 0;
+  repaired = 0;
+  for (int c = 0; c < ncomp; ++c) {
+    const bool cut = comp_tiles[c] > 1 || comp_rows[c] > FC_TILE;
+    runs[c] = cut ? (comp_rows[c] + FC_TILE - 1) / FC_TILE : 1;
+    if (cut) repaired += comp_rows[c];
+    first[c] = total;
+    total += runs[c];
+  }
+  std::vector<int> seen_rows(ncomp, 0);
+  for (int i = 0; i < n; ++i) {   // ascending row number: the q-th row of a group goes to run q * runs / rows
+    const int c = comp[tile[i]];
+    const int q = seen_rows[c]++;
+    tile[i] = first[c] + (int)((long long)q * runs[c] / comp_rows[c]);
+  }
+  return total;
+}
+
+// critical path of one sweep in units of 0.1 us: per tile level one hand-over through global memory (~3.5 us) plus the
+// local walk of its slowest tile (~0.15 us per local level)
+inline long long dir_cost(const fc_tile_dir &D) {
+  long long c = 0;
+  for (int l = 0; l < D.nlev; ++l) {
+    int worst = 0;
+    for (int b = D.lev_blocks_before[l]; b < D.lev_blocks_before[l + 1]; ++b) worst = std::max(worst, D.blk_nlev[b]);
+    c += 35 + (3 * (long long)worst + 1) / 2;
+  }
+  return c;
+}
+
 }  // namespace fc_tile_detail
 
 // 0-based CSR (columns ascending inside a row, diag = position of the diagonal) and the cell centres of its rows
@@ -237,9 +344,13 @@ inline fc_tile_schedule fc_build_tile_schedule(int n, const int *ioffset, const 
     S.cells_per_axis = target;
     if (S.max_tile_rows <= FC_TILE) break;
   }
-  if (S.max_tile_rows > FC_TILE) {
-    S.why = "no bin width down to " + std::to_string(S.cells_per_axis) + " cells per axis keeps every tile within " +
-            std::to_string(FC_TILE) + " rows (strongly graded mesh)";
+  // circular bins (numbering not monotone across them) and oversized bins are cut into runs of consecutive rows
+  ntiles = repair_tiles(n, ioffset, ja, diag, tile, ntiles, S.repaired_rows);
+  count.assign(ntiles, 0);
+  for (int i = 0; i < n; ++i) count[tile[i]]++;
+  S.max_tile_rows = *std::max_element(count.begin(), count.end());
+  if (S.max_tile_rows > FC_TILE || *std::min_element(count.begin(), count.end()) < 1) {
+    S.why = "internal: tile repair left an empty or oversized tile";
     return S;
   }
   S.ntiles = ntiles;
@@ -261,6 +372,11 @@ inline fc_tile_schedule fc_build_tile_schedule(int n, const int *ioffset, const 
   }
   if (!build_dir(n, ioffset, ja, diag, tile, tile_start, pos, ntiles, true, S.lower, S.why)) return S;
   if (!build_dir(n, ioffset, ja, diag, tile, tile_start, pos, ntiles, false, S.upper, S.why)) return S;
+  S.cost = std::max(fc_tile_detail::dir_cost(S.lower), fc_tile_detail::dir_cost(S.upper));
   S.ok = true;
   return S;
 }
+
+// The same estimate for the one-level schedule of fc_trisolve.cu (one hand-over of about 4.2 us per row level, measured
+// on B200): the caller keeps the level schedule unless the tiling promises to be clearly faster.
+inline long long fc_level_cost(int row_levels) { return 42LL * row_levels; }

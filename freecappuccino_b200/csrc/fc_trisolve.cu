@@ -534,6 +534,14 @@ int build_tiles(fc_context *ctx) {
       fc_build_tile_schedule(ctx->n, ioffset.data(), ja.data(), diag.data(), xc.data(), yc.data(), zc.data());
   ctx->tiles_why = S.why;
   if (!S.ok) return FC_OK;
+  // bins cut into runs of consecutive rows (fc_tile_schedule.hpp repair_tiles) can degenerate into a long chain: keep
+  // the level schedule unless the estimated critical path is clearly shorter
+  const long long level_cost = fc_level_cost(ctx->lower.nlev > ctx->upper.nlev ? ctx->lower.nlev : ctx->upper.nlev);
+  if (10 * S.cost > 7 * level_cost) {
+    ctx->tiles_why = "tiling not worth it: estimated critical path " + std::to_string(S.cost / 10) + " us against " +
+                     std::to_string(level_cost / 10) + " us of the level schedule";
+    return FC_OK;
+  }
   FC_CHECK(fc_dev_alloc(ctx, &ctx->tja, nnz));
   FC_CUDA(cudaMemcpy(ctx->tja, S.tja.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
   FC_CHECK(upload_tile_dir(ctx, S.lower, ctx->tile_lower));

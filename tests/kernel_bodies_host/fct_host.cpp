@@ -47,6 +47,8 @@ void fct_info(void *h, int *out) {
   out[5] = S.upper.nlev; out[6] = S.upper.max_local_levels;
   out[7] = S.lower.p2p_ok && S.upper.p2p_ok ? 1 : 0;
   out[8] = std::max(S.lower.max_producers, S.upper.max_producers);
+  out[9] = S.repaired_rows;
+  out[10] = (int)std::min<long long>(S.cost, 2000000000LL);
 }
 
 // the sweep in the reference's own order: rows ascending (lower triangle) or descending (upper)

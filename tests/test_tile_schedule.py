@@ -82,7 +82,7 @@ MESHES = {
 
 def build(host, s):
     h = host.fct_build(s.n, ip(s.ioffset), ip(s.ja), ip(s.diag), dp(s.xc), dp(s.yc), dp(s.zc))
-    info = np.zeros(9, np.int32)
+    info = np.zeros(11, np.int32)
     host.fct_info(C.c_void_p(h), ip(info))
     return h, info
 
@@ -102,13 +102,8 @@ def test_tiled_sweeps_equal_natural_order_sweeps(host, name):
     s = System(MESHES[name]())
     h, info = build(host, s)
     try:
-        if not host.fct_ok(C.c_void_p(h)):
-            # a refusal must say why and is only expected where bins cannot work
-            why = host.fct_why(C.c_void_p(h)).decode()
-            assert name in ("pitzDaily", "poly-6", "skew"), (name, why)
-            assert why
-            pytest.skip(f"{name}: no tiling ({why}); the library keeps the level schedule")
-        ntiles, cells, maxrows, lnlev, lloc, unlev, uloc, p2p_ok, maxprod = info
+        assert host.fct_ok(C.c_void_p(h)), host.fct_why(C.c_void_p(h)).decode()
+        ntiles, cells, maxrows, lnlev, lloc, unlev, uloc, p2p_ok, maxprod, repaired, cost = info
         assert 1 <= maxrows <= 512 and ntiles >= 1 and 2 <= cells <= 512
         zero = np.zeros(s.n)
         for mode in (DIC, DIC_PAR, DILU):
@@ -130,21 +125,53 @@ def test_tile_levels_of_a_cube_are_the_tile_hyperplanes(host):
     3*8-2 = 22 local levels per tile."""
     s = System(cases.hex_case(32, 32, 32))
     h, info = build(host, s)
-    ntiles, cells, maxrows, lnlev, lloc, unlev, uloc, p2p_ok, maxprod = info
+    ntiles, cells, maxrows, lnlev, lloc, unlev, uloc, p2p_ok, maxprod, repaired, cost = info
     host.fct_free(C.c_void_p(h))
     assert (ntiles, cells, maxrows) == (64, 8, 512)
     assert (lnlev, unlev) == (10, 10) and (lloc, uloc) == (22, 22)
     assert p2p_ok == 1 and maxprod == 3          # the three face neighbours on the low (high) side
 
 
-def test_a_numbering_that_is_not_monotone_across_the_bins_is_refused(host):
-    """Rows renumbered at random: tile A needs tile B and tile B needs tile A -> no tile order exists, the builder
-    must say so instead of emitting a schedule that deadlocks."""
-    m = cases.hex_case(20, 20, 20)
-    s = System(m)
+def row_levels(s):
+    """Dependency levels of the strict lower triangle = hand-overs of the one-level schedule."""
+    lev = np.zeros(s.n, np.int64)
+    for i in range(s.n):
+        k0, k1 = s.ioffset[i], s.diag[i]
+        if k1 > k0:
+            lev[i] = lev[s.ja[k0:k1]].max() + 1
+    return int(lev.max()) + 1
+
+
+def test_a_numbering_that_is_not_monotone_across_the_bins_is_repaired_not_trusted(host):
+    """Cell centres that do not follow the numbering at all: every bin depends on every other one in a circle.  The
+    builder must not emit a schedule that deadlocks -- it cuts the circular bins into runs of consecutive rows (a
+    chain) -- and the walk must still be exact.  (Whether such a chain is used is the library's decision from the
+    cost estimate: at 8 000 rows it still beats 58 row levels, at 10 M rows it would not.)"""
+    s = System(cases.hex_case(20, 20, 20))
     perm = np.random.default_rng(0).permutation(s.n)
-    xc, yc, zc = s.xc[perm].copy(), s.yc[perm].copy(), s.zc[perm].copy()   # centres no longer follow the numbering
-    h = host.fct_build(s.n, ip(s.ioffset), ip(s.ja), ip(s.diag), dp(xc), dp(yc), dp(zc))
-    ok, why = host.fct_ok(C.c_void_p(h)), host.fct_why(C.c_void_p(h)).decode()
+    s.xc, s.yc, s.zc = s.xc[perm].copy(), s.yc[perm].copy(), s.zc[perm].copy()
+    h, info = build(host, s)
+    ntiles, cells, maxrows, lnlev, lloc, unlev, uloc, p2p_ok, maxprod, repaired, cost = info
+    try:
+        assert host.fct_ok(C.c_void_p(h))
+        assert repaired == s.n and ntiles == -(-s.n // 512) and lnlev == ntiles      # one chain of runs
+        zero = np.zeros(s.n)
+        ref, out, bad = run(host, h, s, DILU, zero, zero)
+        assert bad == 0 and np.array_equal(ref, out)
+        rz, z, bad = run(host, h, s, BWD, ref, s.r)
+        assert bad == 0 and np.array_equal(rz, z)
+        assert cost >= 35 * ntiles                    # a chain: one hand-over per run, the estimate says so
+    finally:
+        host.fct_free(C.c_void_p(h))
+
+
+def test_block_structured_mesh_is_tiled_after_repair(host):
+    """pitzDaily (five blocks, each numbered on its own): the bins along the block interfaces are circular and get cut
+    into runs, the rest keeps its spatial tiles; far fewer hand-overs than row levels."""
+    s = System(cases.golden_mesh(os.path.join(GOLD, "pitzDaily.npz")))
+    h, info = build(host, s)
+    ntiles, cells, maxrows, lnlev, lloc, unlev, uloc, p2p_ok, maxprod, repaired, cost = info
     host.fct_free(C.c_void_p(h))
-    assert not ok and "cycle" in why
+    nlev = row_levels(s)
+    assert 0 < repaired < s.n // 4
+    assert lnlev < nlev // 4 and cost < 0.7 * 42 * nlev
