@@ -60,8 +60,8 @@ namespace fc_tile_detail {
 
 // tile id of every row from bins over the cell centres; returns the number of (non-empty, renumbered) tiles
 // `shrink` = 0, 1, 2 ...: bins of FC_TILE^(1/dims) cells per axis (8 in 3-D, 22 in 2-D), each step 1/8 narrower
-inline int assign_tiles(int n, const double *xc, const double *yc, const double *zc, int shrink, std::vector<int> &tile,
-                        int &target) {
+inline int assign_tiles(int n, const int *ioffset, const int *ja, const int *diag, const double *xc, const double *yc,
+                        const double *zc, int shrink, std::vector<int> &tile, int &target) {
   const double *c[3] = {xc, yc, zc};
   double lo[3], len[3];
   int dims = 0;
@@ -91,16 +91,26 @@ inline int assign_tiles(int n, const double *xc, const double *yc, const double 
     for (int ax = 0; ax < 3; ++ax)
       if (len[ax] > 0.0) nb[ax] = std::max(1, (int)std::ceil(len[ax] / (target * h) - 1e-9));
   }
-  std::vector<long long> raw(n);
-  for (int i = 0; i < n; ++i) {
-    long long id = 0;
-    for (int ax = 2; ax >= 0; --ax) {
+  // bin coordinates, then made monotone along the dependencies: a row never sits in a lower bin (in any direction)
+  // than a row it depends on.  With all three coordinates non-decreasing along every edge, tiles cannot depend on
+  // each other in a circle.  A lexicographically numbered mesh is monotone already; the pass matters for cells whose
+  // centre lies on a bin boundary (jittered or unstructured meshes), which would otherwise land on either side at random.
+  std::vector<int> bin(3 * (size_t)n);
+  for (int i = 0; i < n; ++i)
+    for (int ax = 0; ax < 3; ++ax) {
       int b = 0;
       if (len[ax] > 0.0) b = std::min(nb[ax] - 1, std::max(0, (int)((c[ax][i] - lo[ax]) / len[ax] * nb[ax])));
-      id = id * nb[ax] + b;
+      bin[3 * (size_t)i + ax] = b;
     }
-    raw[i] = id;
-  }
+  for (int i = 0; i < n; ++i)
+    for (int k = ioffset[i]; k < diag[i]; ++k) {
+      const int j = ja[k];
+      if (j >= i) continue;   // the strict lower triangle only
+      for (int ax = 0; ax < 3; ++ax) bin[3 * (size_t)i + ax] = std::max(bin[3 * (size_t)i + ax], bin[3 * (size_t)j + ax]);
+    }
+  std::vector<long long> raw(n);
+  for (int i = 0; i < n; ++i)
+    raw[i] = bin[3 * (size_t)i] + (long long)nb[0] * (bin[3 * (size_t)i + 1] + (long long)nb[1] * bin[3 * (size_t)i + 2]);
   // renumber the non-empty bins densely, in ascending bin order
   std::vector<long long> used(raw);
   std::sort(used.begin(), used.end());
@@ -337,7 +347,7 @@ inline fc_tile_schedule fc_build_tile_schedule(int n, const int *ioffset, const 
   int ntiles = 0;
   for (int shrink = 0; shrink <= 4; ++shrink) {
     int target = 0;
-    ntiles = assign_tiles(n, xc, yc, zc, shrink, tile, target);
+    ntiles = assign_tiles(n, ioffset, ja, diag, xc, yc, zc, shrink, tile, target);
     count.assign(ntiles, 0);
     for (int i = 0; i < n; ++i) count[tile[i]]++;
     S.max_tile_rows = *std::max_element(count.begin(), count.end());

@@ -154,7 +154,7 @@ def test_a_numbering_that_is_not_monotone_across_the_bins_is_repaired_not_truste
     ntiles, cells, maxrows, lnlev, lloc, unlev, uloc, p2p_ok, maxprod, repaired, cost = info
     try:
         assert host.fct_ok(C.c_void_p(h))
-        assert repaired == s.n and ntiles == -(-s.n // 512) and lnlev == ntiles      # one chain of runs
+        assert repaired > 0.9 * s.n and lnlev > 0.8 * ntiles      # (almost) one chain of runs
         zero = np.zeros(s.n)
         ref, out, bad = run(host, h, s, DILU, zero, zero)
         assert bad == 0 and np.array_equal(ref, out)
@@ -165,13 +165,18 @@ def test_a_numbering_that_is_not_monotone_across_the_bins_is_repaired_not_truste
         host.fct_free(C.c_void_p(h))
 
 
-def test_block_structured_mesh_is_tiled_after_repair(host):
-    """pitzDaily (five blocks, each numbered on its own): the bins along the block interfaces are circular and get cut
-    into runs, the rest keeps its spatial tiles; far fewer hand-overs than row levels."""
+def test_block_structured_and_jittered_meshes_tile_without_repair(host):
+    """pitzDaily (five blocks, each numbered on its own) and the jittered polyhedral mesh (centres on the bin
+    boundaries fall on either side at random): raw bins are circular there; after the monotone pass over the bin
+    coordinates no bin has to be cut, and the sweeps need far fewer hand-overs than row levels."""
     s = System(cases.golden_mesh(os.path.join(GOLD, "pitzDaily.npz")))
     h, info = build(host, s)
     ntiles, cells, maxrows, lnlev, lloc, unlev, uloc, p2p_ok, maxprod, repaired, cost = info
     host.fct_free(C.c_void_p(h))
     nlev = row_levels(s)
-    assert 0 < repaired < s.n // 4
+    assert repaired == 0
     assert lnlev < nlev // 4 and cost < 0.7 * 42 * nlev
+    s = System(cases.poly_case(16))
+    h, info = build(host, s)
+    host.fct_free(C.c_void_p(h))
+    assert info[9] == 0 and info[3] < row_levels(s) // 3 and info[10] < 0.7 * 42 * row_levels(s)
