@@ -48,6 +48,9 @@ LIMITERS = {"no-limit": 0, "Barth-Jespersen": 1, "Venkatakrishnan": 2, "mVenkata
 TUNE_SPMV_KERNEL, TUNE_DPCG_PERSISTENT, TUNE_CTAS_PER_SM, TUNE_PIPE_GEOMETRY, TUNE_SWEEP_P2P = 0, 1, 2, 3, 4
 TUNE_SWEEP_TILED = 5
 TUNE_FUSED_GRAD = 6
+TUNE_KEYS = {"spmv_kernel": TUNE_SPMV_KERNEL, "dpcg_persistent": TUNE_DPCG_PERSISTENT, "ctas_per_sm": TUNE_CTAS_PER_SM,
+             "pipe_geometry": TUNE_PIPE_GEOMETRY, "sweep_p2p": TUNE_SWEEP_P2P, "sweep_tiled": TUNE_SWEEP_TILED,
+             "fused_grad": TUNE_FUSED_GRAD}
 
 
 class MeshDesc(C.Structure):
@@ -209,6 +212,10 @@ class Context:
             raise FcError(rc, (self.lib.fc_last_error(None) or b"").decode())
         self.mesh = None
         self._keep = []
+        # A/B switch for measurements without touching the caller: FCAPP_TUNE="sweep_tiled=2,fused_grad=1"
+        for item in filter(None, os.environ.get("FCAPP_TUNE", "").replace(" ", "").split(",")):
+            name, _, value = item.partition("=")
+            self.set_tuning(TUNE_KEYS[name.lower()], int(value))
 
     # -- plumbing ---------------------------------------------------------
     def _ck(self, rc: int):

@@ -13,6 +13,8 @@ FCAPP_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz9_experimenta
 grep "sweeps\]\|passed\|failed" gpurun_out/pytest_experimental.log | tail -24
 timeout 200 python tools/kernel_bench.py 216 10 > gpurun_out/kernel_bench_216.jsonl 2> gpurun_out/kernel_bench.err
 timeout 120 python tools/simple_iter_bench.py 216 2 3 > gpurun_out/simple_iter_216.json 2>&1
+FCAPP_TUNE="sweep_tiled=1,fused_grad=1" timeout 120 python tools/simple_iter_bench.py 216 2 3 > gpurun_out/simple_iter_216_tiled.json 2>&1
+FCAPP_TUNE="sweep_tiled=2,fused_grad=1" timeout 120 python tools/simple_iter_bench.py 216 2 3 > gpurun_out/simple_iter_216_tiled_p2p.json 2>&1
 timeout 300 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 tail -c 600 gpurun_out/bench_n1.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_simple.csv \
