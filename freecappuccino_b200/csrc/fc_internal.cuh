@@ -179,6 +179,7 @@ struct fc_context {
   int tune_pipe = 1;                    // staging geometry of the TMA pipeline (threads, capacity, stages)
   int tune_ctas_per_sm = 0;             // persistent kernel: CTAs per SM (0 = as many as fit)
   int tune_sweep_p2p = 0;               // triangular sweeps: 1 = point-to-point block flags instead of level counters
+  int first_batch[3] = {8, 8, 8};       // per solver: iterations enqueued before the first look at `done`
   int tune_fused_grad = 0;              // 1: the three velocity gradients of calcuvw / calcp in one kernel per pass
   int tune_sweep_tiled = 0;             // triangular sweeps: 1 = two-level tiled schedule where the mesh allows it
   fc_persist_state *persist = nullptr;  // device: grid barrier + phase clocks of the persistent kernel

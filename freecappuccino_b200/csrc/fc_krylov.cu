@@ -301,7 +301,9 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
     FC_CUDA(cudaMemsetAsync(ctx->uk, 0, sizeof(double) * (size_t)n, st));
   }
 
-  int batch = 8;
+  // iterations enqueued before the host looks at `done`: a solve that ends after one or two iterations (the momentum
+  // predictor's bicgstab calls) should not enqueue eight; start from what the last solve of this kind needed
+  int batch = ctx->first_batch[solver];
   int launched = 0;
   while (launched < o->nsw) {
     const int todo = (o->nsw - launched) < batch ? (o->nsw - launched) : batch;
@@ -363,6 +365,7 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
   FC_CHECK(poll(ctx));
   rep->resl = ctx->sc_host->resl;
   rep->iters = ctx->sc_host->iters;
+  ctx->first_batch[solver] = rep->iters + 1 < 2 ? 2 : (rep->iters + 1 > 8 ? 8 : rep->iters + 1);
   if (hist) {
     if (rep->iters > 0)
       FC_CUDA(cudaMemcpy(hist_host, hist, sizeof(double) * (size_t)rep->iters, cudaMemcpyDeviceToHost));
