@@ -387,7 +387,8 @@ k_tile_sweep(const int *__restrict__ rows, const int *__restrict__ llev, const i
   } else if (lev > 0) {   // every tile of the previous tile level has published its rows
     if (threadIdx.x == 0) {
       const unsigned int *r = ready + (lev - 1);
-      while (ld_acquire(r) < sweep_no) {}
+      fc_spin_guard g;      // a schedule bug must trap, not hang the device
+      while (ld_acquire(r) < sweep_no) g.tick();
     }
     __syncthreads();
   }
