@@ -7,12 +7,42 @@
 // without a GPU that (a) no row is visited before the rows it depends on, (b) a value read through global memory
 // was produced by a tile of a strictly lower tile level (the only ordering the kernel's level counters give) and
 // (c) the result is bit-identical to the natural-order sweep of iccg.f90:94-111 / bicgstab.f90:68-79.
+//
+// fct_emu_sweep goes one step further: it compiles the kernel source itself (fc_tile_sweep.cuh) for the host -- one
+// std::thread per CUDA thread of a CTA, std::barrier for __syncthreads, GCC atomics for the acquire / release words --
+// and runs the CTAs one after the other in ticket order, twice in a row on the same counters (sweep numbers 1, 2).
+// That checks the kernel's own index arithmetic, register prefetch and barrier structure, not a restatement of it.
+#include <barrier>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
+#include <thread>
 
 #include "../../freecappuccino_b200/csrc/fc_tile_schedule.hpp"
 
 enum { TRI_FWD = 0, TRI_BWD = 1, TRI_DIC = 2, TRI_DIC_PAR = 3, TRI_DILU = 4 };
+
+// ---- host stand-ins for what fc_tile_sweep.cuh expects from its includer ----
+struct fc_scalars { int done; };
+namespace {
+thread_local unsigned fct_tid = 0;
+std::barrier<> *fct_bar = nullptr;
+}
+#define FCT_KERNEL static void
+#define FCT_SHARED static
+#define FCT_TID fct_tid
+#define FCT_SYNC() fct_bar->arrive_and_wait()
+#define FCT_TICKET(p) __atomic_fetch_add((p), 1u, __ATOMIC_RELAXED)
+#define FCT_LDCG(p) (*(const volatile double *)(p))
+#define FCT_UNROLL
+static inline unsigned int ld_acquire(const unsigned int *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void st_release(unsigned int *p, unsigned int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline unsigned int atom_add_acq_rel(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
+struct fc_spin_guard {   // CTAs run in ticket order here, so a wait that does not end at once is a schedule bug
+  unsigned long long n = 0;
+  void tick() { if (++n > (1ull << 24)) std::abort(); std::this_thread::yield(); }
+};
+#include "../../freecappuccino_b200/csrc/fc_tile_sweep.cuh"
 
 static inline double step(int mode, double v, double ak, double zj, double atk) {
   if (mode == TRI_FWD || mode == TRI_BWD) return v - ak * zj;
@@ -110,6 +140,53 @@ int fct_sweep(void *h, int mode, int n, const int *ioffset, const int *diag, con
   }
   if (visited != n) ++bad;
   return bad;
+}
+
+// the kernel source itself, CTA by CTA; `nsweeps` launches in a row on the same counters.  Returns 0, or -1 for an
+// unknown mode.  `out` is refilled with NaN before every launch.
+int fct_emu_sweep(void *h, int mode, int pre8, int p2p, int nsweeps, int n, const int *ioffset, const int *diag,
+                  const int *tpos, const double *a, const double *d, const double *in, double *out, double small,
+                  double padd) {
+  const fc_tile_schedule &S = *(fc_tile_schedule *)h;
+  const fc_tile_dir &D = mode == TRI_BWD ? S.upper : S.lower;
+  std::vector<unsigned int> done(D.nlev, 0), ready(D.nlev, 0), flag(D.nblocks, 0);
+  unsigned int ticket = 0;
+  using kernel_t = void (*)(const int *, const int *, const int *, const int *, const int *, unsigned int *,
+                            unsigned int *, unsigned int *, const int *, const int *, unsigned int *, unsigned int,
+                            unsigned int, const int *, const int *, const int *, const int *, const double *,
+                            const double *, const double *, double *, double, double, const fc_scalars *);
+  kernel_t k = nullptr;
+#define FCT_PICK(M)                                                                                          \
+  case M:                                                                                                    \
+    k = pre8 ? (p2p ? k_tile_sweep<M, 8, true> : k_tile_sweep<M, 8, false>)                                  \
+             : (p2p ? k_tile_sweep<M, 4, true> : k_tile_sweep<M, 4, false>);                                 \
+    break;
+  switch (mode) {
+    FCT_PICK(TRI_FWD) FCT_PICK(TRI_BWD) FCT_PICK(TRI_DIC) FCT_PICK(TRI_DIC_PAR) FCT_PICK(TRI_DILU)
+    default: return -1;
+  }
+#undef FCT_PICK
+  std::barrier<> bar(FC_TILE);
+  fct_bar = &bar;
+  for (int sweep = 1; sweep <= nsweeps; ++sweep) {
+    for (int i = 0; i < n; ++i) out[i] = std::numeric_limits<double>::quiet_NaN();
+    const unsigned int base = (unsigned int)(sweep - 1) * (unsigned int)D.nblocks;
+    std::vector<std::thread> th;
+    th.reserve(FC_TILE);
+    for (int t = 0; t < FC_TILE; ++t)
+      th.emplace_back([&, t]() {
+        fct_tid = (unsigned)t;
+        for (int b = 0; b < D.nblocks; ++b) {   // one CTA after the other: the static "shared" arrays are reused
+          k(D.rows.data(), D.llev.data(), D.blk_nlev.data(), D.blk_level.data(), D.lev_blocks_before.data(),
+            done.data(), ready.data(), &ticket, D.prod.data(), D.prod_cnt.data(), flag.data(), base,
+            (unsigned int)sweep, ioffset, S.tja.data(), diag, tpos, a, d, in, out, small, padd, nullptr);
+          bar.arrive_and_wait();
+        }
+      });
+    for (auto &x : th) x.join();
+  }
+  fct_bar = nullptr;
+  return 0;
 }
 
 }  // extern "C"

@@ -23,9 +23,10 @@ FWD, BWD, DIC, DIC_PAR, DILU = range(5)
 def host():
     src = os.path.join(HERE, "fct_host.cpp")
     so = os.path.join(HERE, "_fct_host.so")
-    hdr = os.path.join(HERE, "..", "..", "freecappuccino_b200", "csrc", "fc_tile_schedule.hpp")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", so, src])
+    hdrs = [os.path.join(HERE, "..", "..", "freecappuccino_b200", "csrc", f) for f in ("fc_tile_schedule.hpp",
+                                                                                        "fc_tile_sweep.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++20", "-pthread", "-o", so, src])
     lib = C.CDLL(so)
     lib.fct_build.restype = C.c_void_p
     lib.fct_why.restype = C.c_char_p
@@ -180,3 +181,43 @@ def test_block_structured_and_jittered_meshes_tile_without_repair(host):
     h, info = build(host, s)
     host.fct_free(C.c_void_p(h))
     assert info[9] == 0 and info[3] < row_levels(s) // 3 and info[10] < 0.7 * 42 * row_levels(s)
+
+
+MESHES["hex-16x12x10"] = lambda: cases.hex_case(16, 12, 10)
+MESHES["slab-40x30x1"] = lambda: cases.hex_case(40, 30, 1, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry"))
+# 512 host threads and a std::barrier per local level: keep the meshes to a few tiles (pitzDaily would take 40 s)
+EMU_MESHES = ["hex-16x12x10", "slab-40x30x1", "poly-6", "skew", "hex-rank-of-3", "one-cell"]
+
+
+@pytest.mark.parametrize("name", EMU_MESHES)
+@pytest.mark.parametrize("p2p", [0, 1])
+def test_kernel_source_run_on_host_threads_equals_natural_order_sweeps(host, name, p2p):
+    """fc_tile_sweep.cuh itself (not a restatement): 512 host threads per CTA, std::barrier for __syncthreads, CTAs in
+    ticket order, two launches in a row on the same counters.  All five modes, both register-prefetch widths."""
+    s = System(MESHES[name]())
+    h, info = build(host, s)
+    try:
+        assert host.fct_ok(C.c_void_p(h))
+        if p2p:
+            assert info[7] == 1
+        zero = np.zeros(s.n)
+
+        def emu(mode, d, src, padd=0.0, pre8=0):
+            ref = np.zeros(s.n)
+            host.fct_reference_sweep(mode, s.n, ip(s.ioffset), ip(s.ja), ip(s.diag), ip(s.tpos), dp(s.a), dp(d), dp(src),
+                                     dp(ref), C.c_double(1e-20), C.c_double(padd))
+            out = np.zeros(s.n)
+            rc = host.fct_emu_sweep(C.c_void_p(h), mode, pre8, p2p, 2, s.n, ip(s.ioffset), ip(s.diag), ip(s.tpos), dp(s.a),
+                                    dp(d), dp(src), dp(out), C.c_double(1e-20), C.c_double(padd))
+            assert rc == 0
+            assert np.array_equal(ref, out), (name, mode, pre8, p2p)
+            return out
+
+        for pre8 in (0, 1):
+            emu(DIC, zero, zero, pre8=pre8)
+            emu(DIC_PAR, zero, zero, padd=1e-20, pre8=pre8)
+            d = emu(DILU, zero, zero, pre8=pre8)
+            t = emu(FWD, d, s.r, pre8=pre8)
+            emu(BWD, d, t, pre8=pre8)
+    finally:
+        host.fct_free(C.c_void_p(h))
