@@ -617,86 +617,80 @@ int fc_calcp_assemble_dev(fc_context *ctx, const fc_calcp_opts *o) {
   return FC_OK;
 }
 
-int fc_calcp_dev(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep) {
-  FC_CHECK(need_mesh(ctx, "fc_calcp"));
+// Post-solve part of one pressure corrector (calcp :132-223): boundary pressure + gradient of pp, reference value,
+// flux / velocity / pressure correction, boundary velocities and, unless it is the last corrector, the
+// non-orthogonal corrector source in su.  PP holds the solved correction.
+int fc_calcp_correct_dev(fc_context *ctx, const fc_calcp_opts *o, int ipcorr) {
+  FC_CHECK(need_mesh(ctx, "fc_calcp_correct"));
   if (o->npcor < 1 || o->npcor > 8) FC_FAIL(FC_ERR_ARG, "fc_calcp: npcor must be in 1..8");
   if (o->pRefCell < 1 || o->pRefCell > ctx->n) FC_FAIL(FC_ERR_ARG, "fc_calcp: pRefCell out of range");
+  if (ipcorr < 1 || ipcorr > o->npcor) FC_FAIL(FC_ERR_ARG, "fc_calcp_correct: ipcorr must be in 1..npcor");
   const int B = 256, n = ctx->n;
   cudaStream_t st = ctx->stream;
-  FC_CHECK(fc_calcp_assemble_dev(ctx, o));
   double *pp = ctx->field[FC_PP], *dP = ctx->field[FC_DPDXI];
-  double solve_ms = 0.0;
-  cudaEvent_t c0, c1;
-  FC_CUDA(cudaEventCreate(&c0));
-  FC_CUDA(cudaEventCreate(&c1));
-  float corr_ms = 0.f;
-  for (int ipcorr = 1; ipcorr <= o->npcor; ++ipcorr) {
-    FC_CUDA(cudaMemsetAsync(pp, 0, sizeof(double) * (size_t)ctx->NT, st));                    // pp = 0 (:115)
-    FC_CHECK(fc_solve_device(ctx, o->solver, pp, &o->sol, &rep->rep[ipcorr - 1], nullptr));   // :118-120
-    solve_ms += ctx->tm.solve_ms;
-    FC_CUDA(cudaEventRecord(c0, st));
-    for (int istage = 1; istage <= o->nipgrad; ++istage) {                                    // :132-140
-      FC_CHECK(fc_bpres_dev(ctx, pp, dP, istage));
-      FC_CHECK(fc_grad_dev(ctx, pp, dP, o->nigrad));
-    }
-    if (o->lsq_flag) {                                                                        // :143
-      FC_CHECK(fc_grad_gauss_corrected_dev(ctx, pp, dP, 1));
-      FC_CHECK(fc_limit_gradient_dev(ctx, pp, dP));   // grad_scalar_field_w_option ends with the limiter (gradients.f90:240-255)
-    }
-    double *ppref = &ctx->sc->aux[3];
-    if (ctx->nranks == 1) {
-      k_pick<<<1, 1, 0, st>>>(pp, o->pRefCell - 1, ppref);                                    // :146
-      FC_LAUNCH_CHECK();
-    } else {  // src-parallel/calcp :175-177: ppref = global mean of pp
-      k_sum<<<FC_RED_GRID, FC_RED_BLOCK, 0, st>>>(n, pp, ctx->partials, ctx->sc);
-      FC_LAUNCH_CHECK();
-      FC_CHECK(fc_allreduce_scalars(ctx, ctx->sc->red, 1));
-      k_mean<<<1, 1, 0, st>>>(ctx->sc, (double)ctx->m.gloCells, ppref);
-      FC_LAUNCH_CHECK();
-    }
+  for (int istage = 1; istage <= o->nipgrad; ++istage) {                                    // :132-140
+    FC_CHECK(fc_bpres_dev(ctx, pp, dP, istage));
+    FC_CHECK(fc_grad_dev(ctx, pp, dP, o->nigrad));
+  }
+  if (o->lsq_flag) {                                                                        // :143
+    FC_CHECK(fc_grad_gauss_corrected_dev(ctx, pp, dP, 1));
+    FC_CHECK(fc_limit_gradient_dev(ctx, pp, dP));   // grad_scalar_field_w_option ends with the limiter (gradients.f90:240-255)
+  }
+  double *ppref = &ctx->sc->aux[3];
+  if (ctx->nranks == 1) {
+    k_pick<<<1, 1, 0, st>>>(pp, o->pRefCell - 1, ppref);                                    // :146
+    FC_LAUNCH_CHECK();
+  } else {  // src-parallel/calcp :175-177: ppref = global mean of pp
+    k_sum<<<FC_RED_GRID, FC_RED_BLOCK, 0, st>>>(n, pp, ctx->partials, ctx->sc);
+    FC_LAUNCH_CHECK();
+    FC_CHECK(fc_allreduce_scalars(ctx, ctx->sc->red, 1));
+    k_mean<<<1, 1, 0, st>>>(ctx->sc, (double)ctx->m.gloCells, ppref);
+    FC_LAUNCH_CHECK();
+  }
+  if (ctx->F > 0) {
+    k_flux_correct<<<fc_blocks(ctx->F, B), B, 0, st>>>(geom_of(ctx), ctx->coef, pp, ctx->field[FC_FLMASS]);
+    FC_LAUNCH_CHECK();
+  }
+  if (ctx->npro > 0) {
+    k_fmpro_correct<<<fc_blocks(ctx->npro, B), B, 0, st>>>(geom_of(ctx), ctx->field[FC_APR], pp,
+                                                           ctx->field[FC_FMPRO]);
+    FC_LAUNCH_CHECK();
+  }
+  k_cell_correct<<<fc_blocks(n, B), B, 0, st>>>(geom_of(ctx), ctx->field[FC_U], ctx->field[FC_V], ctx->field[FC_W],
+                                                ctx->field[FC_P], pp, dP, ctx->field[FC_APU], ctx->field[FC_APV],
+                                                ctx->field[FC_APW], o->urf_p, ppref);
+  FC_LAUNCH_CHECK();
+  // correctBoundaryConditionsVelocity (:184)
+  FC_CHECK(outlet_extrapolate_and_scale(ctx, o->flomas, o->sol.small, false));
+  const slots_t sl = slots_of(ctx);
+  if (sl.count[2] > 0) {
+    k_symmetry_project<<<fc_blocks(sl.count[2], B), B, 0, st>>>(geom_of(ctx), sl, ctx->field[FC_U],
+                                                                ctx->field[FC_V], ctx->field[FC_W]);
+    FC_LAUNCH_CHECK();
+  }
+  if (ipcorr != o->npcor) {  // non-orthogonal corrector source (:187-223)
     if (ctx->F > 0) {
-      k_flux_correct<<<fc_blocks(ctx->F, B), B, 0, st>>>(geom_of(ctx), ctx->coef, pp, ctx->field[FC_FLMASS]);
+      k_fluxmc_faces<<<fc_blocks(ctx->F, B), B, 0, st>>>(geom_of(ctx), flow_of(ctx), ctx->facev,
+                                                         ctx->field[FC_FLMASS]);
       FC_LAUNCH_CHECK();
     }
     if (ctx->npro > 0) {
-      k_fmpro_correct<<<fc_blocks(ctx->npro, B), B, 0, st>>>(geom_of(ctx), ctx->field[FC_APR], pp,
-                                                             ctx->field[FC_FMPRO]);
+      k_fluxmc_proc_faces<<<fc_blocks(ctx->npro, B), B, 0, st>>>(geom_of(ctx), flow_of(ctx), ctx->facev + ctx->F,
+                                                                 ctx->field[FC_FMPRO]);
       FC_LAUNCH_CHECK();
     }
-    k_cell_correct<<<fc_blocks(n, B), B, 0, st>>>(geom_of(ctx), ctx->field[FC_U], ctx->field[FC_V], ctx->field[FC_W],
-                                                  ctx->field[FC_P], pp, dP, ctx->field[FC_APU], ctx->field[FC_APV],
-                                                  ctx->field[FC_APW], o->urf_p, ppref);
+    k_rows_gather<ROWS_SU_ONLY><<<fc_blocks(n, B), B, 0, st>>>(
+        geom_of(ctx), c2f_of(ctx), sl, ctx->diag, ctx->coef, ctx->facev, nullptr, ctx->facev + ctx->F, nullptr,
+        nullptr, 0, nullptr, nullptr, ctx->field[FC_A], ctx->field[FC_SU]);
     FC_LAUNCH_CHECK();
-    // correctBoundaryConditionsVelocity (:184)
-    FC_CHECK(outlet_extrapolate_and_scale(ctx, o->flomas, o->sol.small, false));
-    const slots_t sl = slots_of(ctx);
-    if (sl.count[2] > 0) {
-      k_symmetry_project<<<fc_blocks(sl.count[2], B), B, 0, st>>>(geom_of(ctx), sl, ctx->field[FC_U],
-                                                                  ctx->field[FC_V], ctx->field[FC_W]);
-      FC_LAUNCH_CHECK();
-    }
-    if (ipcorr != o->npcor) {  // non-orthogonal corrector source (:187-223)
-      if (ctx->F > 0) {
-        k_fluxmc_faces<<<fc_blocks(ctx->F, B), B, 0, st>>>(geom_of(ctx), flow_of(ctx), ctx->facev,
-                                                           ctx->field[FC_FLMASS]);
-        FC_LAUNCH_CHECK();
-      }
-      if (ctx->npro > 0) {
-        k_fluxmc_proc_faces<<<fc_blocks(ctx->npro, B), B, 0, st>>>(geom_of(ctx), flow_of(ctx), ctx->facev + ctx->F,
-                                                                   ctx->field[FC_FMPRO]);
-        FC_LAUNCH_CHECK();
-      }
-      k_rows_gather<ROWS_SU_ONLY><<<fc_blocks(n, B), B, 0, st>>>(
-          geom_of(ctx), c2f_of(ctx), sl, ctx->diag, ctx->coef, ctx->facev, nullptr, ctx->facev + ctx->F, nullptr,
-          nullptr, 0, nullptr, nullptr, ctx->field[FC_A], ctx->field[FC_SU]);
-      FC_LAUNCH_CHECK();
-    }
-    FC_CUDA(cudaEventRecord(c1, st));
-    FC_CUDA(cudaEventSynchronize(c1));
-    float ms = 0.f;
-    FC_CUDA(cudaEventElapsedTime(&ms, c0, c1));
-    corr_ms += ms;
   }
+  return FC_OK;
+}
+
+// End of calcp: halo of the corrected fields on several ranks (src-parallel/calcp :289-292) and continuityErrors.h
+int fc_calcp_finish_dev(fc_context *ctx, fc_calcp_report *rep) {
+  FC_CHECK(need_mesh(ctx, "fc_calcp_finish"));
+  cudaStream_t st = ctx->stream;
   if (ctx->npro > 0)  // src-parallel/calcp :289-292
     for (int fld : {FC_U, FC_V, FC_W, FC_P}) FC_CHECK(fc_halo_exchange(ctx, ctx->field[fld]));
   k_continuity<<<FC_RED_GRID, FC_RED_BLOCK, 0, st>>>(geom_of(ctx), c2f_of(ctx), slots_of(ctx), ctx->field[FC_FLMASS],
@@ -708,6 +702,34 @@ int fc_calcp_dev(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep) 
   FC_CUDA(cudaStreamSynchronize(st));
   rep->sumLocalContErr = ctx->sc_host->red[0];
   rep->globalContErr = ctx->sc_host->red[1];
+  return FC_OK;
+}
+
+int fc_calcp_dev(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep) {
+  FC_CHECK(need_mesh(ctx, "fc_calcp"));
+  if (o->npcor < 1 || o->npcor > 8) FC_FAIL(FC_ERR_ARG, "fc_calcp: npcor must be in 1..8");
+  if (o->pRefCell < 1 || o->pRefCell > ctx->n) FC_FAIL(FC_ERR_ARG, "fc_calcp: pRefCell out of range");
+  cudaStream_t st = ctx->stream;
+  FC_CHECK(fc_calcp_assemble_dev(ctx, o));
+  double *pp = ctx->field[FC_PP];
+  double solve_ms = 0.0;
+  cudaEvent_t c0, c1;
+  FC_CUDA(cudaEventCreate(&c0));
+  FC_CUDA(cudaEventCreate(&c1));
+  float corr_ms = 0.f;
+  for (int ipcorr = 1; ipcorr <= o->npcor; ++ipcorr) {
+    FC_CUDA(cudaMemsetAsync(pp, 0, sizeof(double) * (size_t)ctx->NT, st));                    // pp = 0 (:115)
+    FC_CHECK(fc_solve_device(ctx, o->solver, pp, &o->sol, &rep->rep[ipcorr - 1], nullptr));   // :118-120
+    solve_ms += ctx->tm.solve_ms;
+    FC_CUDA(cudaEventRecord(c0, st));
+    FC_CHECK(fc_calcp_correct_dev(ctx, o, ipcorr));
+    FC_CUDA(cudaEventRecord(c1, st));
+    FC_CUDA(cudaEventSynchronize(c1));
+    float ms = 0.f;
+    FC_CUDA(cudaEventElapsedTime(&ms, c0, c1));
+    corr_ms += ms;
+  }
+  FC_CHECK(fc_calcp_finish_dev(ctx, rep));
   float ams = 0.f;
   FC_CUDA(cudaEventElapsedTime(&ams, ctx->ev[2], ctx->ev[3]));
   ctx->tm.assemble_ms = ams;

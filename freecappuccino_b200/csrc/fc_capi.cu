@@ -10,6 +10,8 @@ int fc_bpres_dev(fc_context *ctx, double *p, const double *dPdxi, int istage);
 int fc_laplacian_dev(fc_context *ctx, double *mu, const double *phi);
 int fc_calcp_assemble_dev(fc_context *ctx, const fc_calcp_opts *o);
 int fc_calcp_dev(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep);
+int fc_calcp_correct_dev(fc_context *ctx, const fc_calcp_opts *o, int ipcorr);
+int fc_calcp_finish_dev(fc_context *ctx, fc_calcp_report *rep);
 
 namespace {
 
@@ -486,6 +488,18 @@ int fc_calcp_assemble(fc_context *ctx, const fc_calcp_opts *o) {
   if (!ctx || !o) return FC_ERR_ARG;
   FC_CUDA(cudaSetDevice(ctx->device));
   return fc_calcp_assemble_dev(ctx, o);
+}
+
+int fc_calcp_correct(fc_context *ctx, const fc_calcp_opts *o, int ipcorr, fc_calcp_report *rep) {
+  if (!ctx || !o) return FC_ERR_ARG;
+  FC_CUDA(cudaSetDevice(ctx->device));
+  FC_CHECK(fc_calcp_correct_dev(ctx, o, ipcorr));
+  if (ipcorr == o->npcor) {
+    fc_calcp_report tmp;
+    FC_CHECK(fc_calcp_finish_dev(ctx, rep ? rep : &tmp));
+  }
+  FC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FC_OK;
 }
 
 int fc_calcp(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep) {

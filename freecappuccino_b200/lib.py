@@ -42,6 +42,7 @@ SYMBOLS = (
     "fc_get_timings", "fc_time_spmv", "fc_stream", "fc_copy", "fc_set_spmv_sampling", "fc_comm_p2p_blob",
     "fc_comm_p2p_open", "fc_set_tuning", "fc_calcuvw_assemble", "fc_calcuvw_component", "fc_calcuvw",
     "fc_calcuvw_host", "fc_piso", "fc_set_gradient", "fc_grad", "fc_dpcg", "fc_iccg", "fc_bicgstab",
+    "fc_calcp_correct",
 )
 GRAD_METHODS = {"gauss": 0, "lstsq": 1, "lstsq_qr": 2, "lstsq_dm": 3}
 LIMITERS = {"no-limit": 0, "Barth-Jespersen": 1, "Venkatakrishnan": 2, "mVenkatakrishnan": 3}
@@ -401,6 +402,13 @@ class Context:
     def calcp(self, opts: CalcpOpts) -> CalcpReport:
         rep = CalcpReport()
         self._ck(self.lib.fc_calcp(self.h, C.byref(opts), C.byref(rep)))
+        return rep
+
+    def calcp_correct(self, opts: CalcpOpts, ipcorr: int) -> CalcpReport:
+        """Post-solve half of corrector ``ipcorr`` (FC_PP = the solved correction); the report's continuity errors are
+        filled after the last corrector."""
+        rep = CalcpReport()
+        self._ck(self.lib.fc_calcp_correct(self.h, C.byref(opts), int(ipcorr), C.byref(rep)))
         return rep
 
     def calcp_host(self, opts: CalcpOpts, u, v, w, p, pp, apu, apv, apw, flmass) -> CalcpReport:

@@ -223,6 +223,13 @@ int fc_calcp_assemble(fc_context *ctx, const fc_calcp_opts *o);
 /* `call calcp`: assemble + npcor x (solve, bpres/grad, flux / velocity /
  * pressure correction) + continuity report, all on device-resident fields. */
 int fc_calcp(fc_context *ctx, const fc_calcp_opts *o, fc_calcp_report *rep);
+/* The post-solve half of pressure corrector `ipcorr` (1..npcor) for a host that solves the system itself between
+ * fc_calcp_assemble and this call (calcp :132-223): FC_PP holds the solved correction; boundary pressure and
+ * gradient of pp, flux / velocity / pressure correction, boundary velocities and -- unless ipcorr = npcor -- the
+ * non-orthogonal corrector source in FC_SU for the next solve.  After the last corrector the multi-rank halo of
+ * u, v, w, p is refreshed and, when `rep` is not NULL, its continuity errors are filled (continuityErrors.h).
+ * fc_calcp = fc_calcp_assemble, then per corrector: FC_PP = 0, solve, fc_calcp_correct.                        */
+int fc_calcp_correct(fc_context *ctx, const fc_calcp_opts *o, int ipcorr, fc_calcp_report *rep);
 
 /* Host-buffer form of `call calcp`: uploads u,v,w,p (numTotal), apu,apv,apw
  * (numCells+npro), runs fc_calcp, downloads u,v,w,p,pp (numTotal) and flmass
