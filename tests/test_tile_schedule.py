@@ -221,3 +221,66 @@ def test_kernel_source_run_on_host_threads_equals_natural_order_sweeps(host, nam
             emu(BWD, d, t, pre8=pre8)
     finally:
         host.fct_free(C.c_void_p(h))
+
+
+def renumbered(s, perm):
+    """The same matrix with rows / columns renumbered: new row perm[i] = old row i; columns ascending again."""
+    n = s.n
+    row = np.repeat(np.arange(n), np.diff(s.ioffset))
+    r2, c2 = perm[row], perm[s.ja]
+    order = np.lexsort((c2, r2))
+    t = System.__new__(System)
+    t.n = n
+    t.ja = c2[order].astype(np.int32)
+    t.a = s.a[order].copy()
+    rr = r2[order]
+    t.ioffset = np.zeros(n + 1, np.int32)
+    np.add.at(t.ioffset, rr + 1, 1)
+    t.ioffset = np.cumsum(t.ioffset).astype(np.int32)
+    t.diag = np.flatnonzero(t.ja == rr).astype(np.int32)
+    key = rr.astype(np.int64) * n + t.ja
+    tkey = t.ja.astype(np.int64) * n + rr
+    t.tpos = np.searchsorted(key, tkey).astype(np.int32)          # key is sorted: rows ascending, columns ascending
+    inv = np.empty(n, np.int64)
+    inv[perm] = np.arange(n)
+    t.xc, t.yc, t.zc = s.xc[inv].copy(), s.yc[inv].copy(), s.zc[inv].copy()
+    t.r = s.r[inv].copy()
+    return t
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_any_numbering_gives_a_valid_and_exact_schedule(host, seed):
+    """Numberings between 'lexicographic' and 'random': blocks of cells renumbered at random, slabs reversed, a few
+    cells swapped.  Whatever the bins look like afterwards (circular, oversized, cut into runs), the walk must visit
+    every row after its dependencies and reproduce the natural-order sweep of the renumbered matrix bit for bit."""
+    rng = np.random.default_rng(seed)
+    base = System(cases.hex_case(14, 11, 9) if seed % 2 == 0 else cases.poly_case(7))
+    n = base.n
+    perm = np.arange(n)
+    kind = seed % 4
+    if kind == 0:                                   # random renumbering of one third of the cells
+        idx = rng.choice(n, n // 3, replace=False)
+        perm[idx] = perm[rng.permutation(idx)]
+    elif kind == 1:                                 # reverse the numbering of the upper half
+        perm[n // 2:] = perm[n // 2:][::-1]
+    elif kind == 2:                                 # blocks of 50 consecutive cells in random order
+        blocks = [np.arange(i, min(i + 50, n)) for i in range(0, n, 50)]
+        perm = np.empty(n, np.int64)
+        perm[np.concatenate([blocks[b] for b in rng.permutation(len(blocks))])] = np.arange(n)
+    else:                                           # completely random
+        perm = rng.permutation(n)
+    s = renumbered(base, perm)
+    assert np.array_equal(s.ja[s.diag], np.arange(n)) and np.array_equal(s.ja[s.tpos], np.repeat(np.arange(n), np.diff(s.ioffset)))
+    h, info = build(host, s)
+    try:
+        assert host.fct_ok(C.c_void_p(h)), host.fct_why(C.c_void_p(h)).decode()
+        assert info[2] <= 512
+        zero = np.zeros(n)
+        d, out, bad = run(host, h, s, DILU, zero, zero)
+        assert bad == 0 and np.array_equal(d, out)
+        rt, t, bad = run(host, h, s, FWD, d, s.r)
+        assert bad == 0 and np.array_equal(rt, t)
+        rz, z, bad = run(host, h, s, BWD, d, t)
+        assert bad == 0 and np.array_equal(rz, z)
+    finally:
+        host.fct_free(C.c_void_p(h))
