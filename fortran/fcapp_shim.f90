@@ -167,6 +167,14 @@ module fcapp_c
       real(c_double) :: u(*), v(*), w(*), p(*), vis(*), flmass(*), apu(*), apv(*), apw(*)
       type(fc_calcuvw_report) :: rep
     end function
+    ! the two halves of calcp around the solve, for a host that keeps its own linear solver (LIS solve_csr)
+    integer(c_int) function fc_calcp_assemble(ctx, o) bind(C, name='fc_calcp_assemble')
+      import; type(c_ptr), value :: ctx; type(fc_calcp_opts) :: o
+    end function
+    integer(c_int) function fc_calcp_correct(ctx, o, ipcorr, rep) bind(C, name='fc_calcp_correct')
+      import; type(c_ptr), value :: ctx; type(fc_calcp_opts) :: o; integer(c_int), value :: ipcorr
+      type(fc_calcp_report) :: rep
+    end function
     integer(c_int) function fc_piso(ctx, o, rep) bind(C, name='fc_piso')
       import; type(c_ptr), value :: ctx; type(fc_piso_opts) :: o; type(fc_piso_report) :: rep
     end function
