@@ -20,7 +20,12 @@ tail -c 600 gpurun_out/bench_n1.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_simple.csv \
     python tools/simple_iter_bench.py 128 1 1 > gpurun_out/ncu_launches.log 2>&1
 python tools/ncu_summary.py launches gpurun_out/launches_simple.csv > gpurun_out/launches_simple.txt 2>/dev/null
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_uvw_faces|k_uvw_rows|k_calcp_faces|k_grad_pass|k_rows_gather|k_tri_sweep' \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_uvw_faces|k_uvw_rows|k_calcp_faces|k_grad_pass|k_rows_gather|k_tri_sweep|k_tile_sweep' \
     -c 12 -o gpurun_out/prof_assembly python tools/simple_iter_bench.py 128 0 1 > gpurun_out/ncu_full.log 2>&1
 python tools/ncu_summary.py full gpurun_out/prof_assembly.ncu-rep > gpurun_out/prof_assembly.txt 2>/dev/null
 ls -la gpurun_out | tail -20
+# the tiled sweep kernel under ncu (it only runs when the tuning key is set)
+FCAPP_TUNE="sweep_tiled=1" timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_tile_sweep' -c 6 \
+    -o gpurun_out/prof_tile_sweep python tools/simple_iter_bench.py 128 0 1 > gpurun_out/ncu_tile.log 2>&1
+python tools/ncu_summary.py full gpurun_out/prof_tile_sweep.ncu-rep > gpurun_out/prof_tile_sweep.txt 2>/dev/null
+ls -la gpurun_out | tail -8
