@@ -273,7 +273,7 @@ FCM_HD void fcg_gauss3_row(const fcm_geom &g, const fcm_c2f &m, const fcg_gauss3
         const double zi = g.zc[ijp] * fxp + g.zc[ijn] * fxn;
         dx = g.xf[f] - xi; dy = g.yf[f] - yi; dz = g.zf[f] - zi;
       }
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
       for (int t = 0; t < 3; ++t) {
@@ -291,7 +291,7 @@ FCM_HD void fcg_gauss3_row(const fcm_geom &g, const fcm_c2f &m, const fcg_gauss3
         else    { gx[t] = gx[t] + dfxe; gy[t] = gy[t] + dfye; gz[t] = gz[t] + dfze; }
       }
     } else {
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
       for (int t = 0; t < 3; ++t) {
