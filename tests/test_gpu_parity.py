@@ -317,37 +317,3 @@ def test_reference_golden_5x5_through_fc_solve_csr(fc):
         assert [f"{v:5.2f}".strip() for v in x] == g["sol"], name
         assert np.allclose(x, xo, rtol=1e-12, atol=1e-13)
     ctx.close()
-
-
-@pytest.mark.parametrize("solver", ["dpcg", "iccg"])
-@pytest.mark.parametrize("name,npcor,lsq", [("hex_mixed_bc", 1, False), ("skew", 2, True)])
-def test_calcp_split_at_the_solve_equals_calcp(fc, solver, name, npcor, lsq):
-    """fc_calcp_assemble -> (FC_PP = 0, fc_solve) -> fc_calcp_correct per corrector, the form a host with its own
-    linear solver uses, runs the same kernels in the same order as fc_calcp: every field bit-identical."""
-    mesh = MESHES[name]()
-    f = cases.flow_fields(mesh)
-    fmi, flomas = cases.inlet_fluxes(mesh, f)
-    kw = dict(solver=solver, flomas=flomas, npcor=npcor, lsq_flag=lsq, sor=1e-8, nsw=500, pRefCell=3)
-    opts = fc.calcp_opts(**kw)
-    got = []
-    for split in (False, True):
-        ctx, _ = make_ctx(fc, mesh)
-        upload_flow(ctx, mesh, f, fmi)
-        ctx.upload("DPDXI", oracle.grad_gauss(mesh, f["p"], 1))
-        if not split:
-            rep = ctx.calcp(opts)
-            iters = [rep.rep[k].iters for k in range(npcor)]
-        else:
-            ctx.calcp_assemble(opts)
-            iters = []
-            for ip in range(1, npcor + 1):
-                ctx.fill("PP", 0.0)
-                iters.append(ctx.solve(solver, "PP", fc.solver_opts(1e-8, 500)).iters)
-                rep = ctx.calcp_correct(opts, ip)
-        got.append((iters, rep.sumLocalContErr, rep.globalContErr,
-                    [ctx.download(k) for k in ("U", "V", "W", "P", "PP", "FLMASS", "SU", "DPDXI")]))
-        ctx.close()
-    assert got[0][0] == got[1][0]
-    assert got[0][1] == got[1][1] and got[0][2] == got[1][2]
-    for a, b in zip(got[0][3], got[1][3]):
-        assert np.array_equal(a, b)

@@ -1,0 +1,69 @@
+"""fc_calcp_assemble -> solve -> fc_calcp_correct, the split form of `call calcp` for a host that keeps its own linear
+solver between assembly and correction.  Written after the round's GPU budget was spent:
+first run on hardware, hence the late-sorting file name."""
+import numpy as np
+import pytest
+
+from freecappuccino_b200 import cases
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+MESHES = {
+    "hex_mixed_bc": lambda: cases.hex_case(9, 7, 11, kinds=("inlet", "outlet", "wall", "symmetry", "wall", "prOutlet")),
+    "skew": lambda: cases.skew_case(),
+}
+
+
+@pytest.fixture(scope="module")
+def fc():
+    from freecappuccino_b200 import lib
+    return lib
+
+
+def make_ctx(fc, mesh):
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    return ctx, ctx.create_csr()
+
+
+def upload_flow(ctx, mesh, f, fmi):
+    for k, name in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("apu", "APU"), ("apv", "APV"),
+                    ("apw", "APW")):
+        ctx.upload(name, f[k])
+    if fmi.size:
+        ctx.upload("FMI", fmi)
+
+
+@pytest.mark.parametrize("solver", ["dpcg", "iccg"])
+@pytest.mark.parametrize("name,npcor,lsq", [("hex_mixed_bc", 1, False), ("skew", 2, True)])
+def test_calcp_split_at_the_solve_equals_calcp(fc, solver, name, npcor, lsq):
+    """fc_calcp_assemble -> (FC_PP = 0, fc_solve) -> fc_calcp_correct per corrector, the form a host with its own
+    linear solver uses, runs the same kernels in the same order as fc_calcp: every field bit-identical."""
+    mesh = MESHES[name]()
+    f = cases.flow_fields(mesh)
+    fmi, flomas = cases.inlet_fluxes(mesh, f)
+    kw = dict(solver=solver, flomas=flomas, npcor=npcor, lsq_flag=lsq, sor=1e-8, nsw=500, pRefCell=3)
+    opts = fc.calcp_opts(**kw)
+    got = []
+    for split in (False, True):
+        ctx, _ = make_ctx(fc, mesh)
+        upload_flow(ctx, mesh, f, fmi)
+        ctx.upload("DPDXI", oracle.grad_gauss(mesh, f["p"], 1))
+        if not split:
+            rep = ctx.calcp(opts)
+            iters = [rep.rep[k].iters for k in range(npcor)]
+        else:
+            ctx.calcp_assemble(opts)
+            iters = []
+            for ip in range(1, npcor + 1):
+                ctx.fill("PP", 0.0)
+                iters.append(ctx.solve(solver, "PP", fc.solver_opts(1e-8, 500)).iters)
+                rep = ctx.calcp_correct(opts, ip)
+        got.append((iters, rep.sumLocalContErr, rep.globalContErr,
+                    [ctx.download(k) for k in ("U", "V", "W", "P", "PP", "FLMASS", "SU", "DPDXI")]))
+        ctx.close()
+    assert got[0][0] == got[1][0]
+    assert got[0][1] == got[1][1] and got[0][2] == got[1][2]
+    for a, b in zip(got[0][3], got[1][3]):
+        assert np.array_equal(a, b)
