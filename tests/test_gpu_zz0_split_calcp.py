@@ -1,6 +1,6 @@
 """fc_calcp_assemble -> solve -> fc_calcp_correct, the split form of `call calcp` for a host that keeps its own linear
 solver between assembly and correction.  Written after the round's GPU budget was spent:
-first run on hardware, hence the late-sorting file name."""
+first run on hardware, it sorts after the suites that have run on hardware and before the riskier widened ones."""
 import numpy as np
 import pytest
 
