@@ -7,7 +7,7 @@
 #pragma once
 
 #ifdef __CUDACC__
-#define FCT_KERNEL __global__ void __launch_bounds__(FC_TILE)
+#define FCT_KERNEL(OCC) __global__ void __launch_bounds__(FC_TILE, OCC)
 #define FCT_SHARED __shared__
 #define FCT_TID threadIdx.x
 #define FCT_SYNC() __syncthreads()
@@ -25,8 +25,10 @@
 // polyhedra): an entry fetched inside the walk would put an L2 round trip on the critical path of a local level.
 // P2P (FC_TUNE_SWEEP_TILED = 2): a tile waits for the flags of the tiles it reads through global memory (3 on a
 // hexahedral mesh) instead of for the whole previous tile level, so tiles run ahead where the tile graph allows.
-template <int MODE, int PRE, bool P2P>
-FCT_KERNEL
+// OCC = CTAs per SM the register allocation has to allow (2: 58-64 registers, no spills; 3: 40 registers and 36-44 B of
+// spills on hexahedra) -- a measurement knob, FC_TUNE_TILE_CTAS.
+template <int MODE, int PRE, bool P2P, int OCC>
+FCT_KERNEL(OCC)
 k_tile_sweep(const int *__restrict__ rows, const int *__restrict__ llev, const int *__restrict__ blk_nlev,
              const int *__restrict__ blk_level, const int *__restrict__ lev_blocks_before, unsigned int *done,
              unsigned int *ready, unsigned int *ticket, const int *__restrict__ prod,

@@ -338,14 +338,20 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
     const unsigned int tbase = (unsigned int)(T.epoch * (unsigned long long)T.nblocks);
     T.epoch++;
     const bool p2p = ctx->tune_sweep_tiled == 2 && T.p2p_ok;
-#define FC_TILE_LAUNCH(PRE_, P2P_)                                                                                   \
-  k_tile_sweep<MODE, PRE_, P2P_><<<T.nblocks, FC_TILE, 0, ctx->stream>>>(                                             \
+#define FC_TILE_LAUNCH_OCC(PRE_, P2P_, OCC_)                                                                         \
+  k_tile_sweep<MODE, PRE_, P2P_, OCC_><<<T.nblocks, FC_TILE, 0, ctx->stream>>>(                                       \
       T.rows, T.llev, T.blk_nlev, T.blk_level, T.lev_blocks_before, T.done, T.ready, T.ticket, T.prod, T.prod_cnt,    \
       T.flag, tbase, (unsigned int)T.epoch, ctx->ioffset, ctx->tja, ctx->diag, ctx->tpos, a, d, in, out, small, padd, \
       guarded ? ctx->sc : nullptr)
+#define FC_TILE_LAUNCH(PRE_, P2P_)                                            \
+  do {                                                                        \
+    if (ctx->tune_tile_ctas == 3) FC_TILE_LAUNCH_OCC(PRE_, P2P_, 3);          \
+    else FC_TILE_LAUNCH_OCC(PRE_, P2P_, 2);                                   \
+  } while (0)
     if (ctx->tiles_pre8) { if (p2p) FC_TILE_LAUNCH(8, true); else FC_TILE_LAUNCH(8, false); }
     else                 { if (p2p) FC_TILE_LAUNCH(4, true); else FC_TILE_LAUNCH(4, false); }
 #undef FC_TILE_LAUNCH
+#undef FC_TILE_LAUNCH_OCC
     FC_LAUNCH_CHECK();
     return FC_OK;
   }

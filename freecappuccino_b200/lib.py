@@ -49,9 +49,10 @@ LIMITERS = {"no-limit": 0, "Barth-Jespersen": 1, "Venkatakrishnan": 2, "mVenkata
 TUNE_SPMV_KERNEL, TUNE_DPCG_PERSISTENT, TUNE_CTAS_PER_SM, TUNE_PIPE_GEOMETRY, TUNE_SWEEP_P2P = 0, 1, 2, 3, 4
 TUNE_SWEEP_TILED = 5
 TUNE_FUSED_GRAD = 6
+TUNE_TILE_CTAS = 7
 TUNE_KEYS = {"spmv_kernel": TUNE_SPMV_KERNEL, "dpcg_persistent": TUNE_DPCG_PERSISTENT, "ctas_per_sm": TUNE_CTAS_PER_SM,
              "pipe_geometry": TUNE_PIPE_GEOMETRY, "sweep_p2p": TUNE_SWEEP_P2P, "sweep_tiled": TUNE_SWEEP_TILED,
-             "fused_grad": TUNE_FUSED_GRAD}
+             "fused_grad": TUNE_FUSED_GRAD, "tile_ctas": TUNE_TILE_CTAS}
 
 
 class MeshDesc(C.Structure):

@@ -355,6 +355,7 @@ enum {
                                   same row sums, bit-identical results)                      */
   FC_TUNE_FUSED_GRAD = 6,      /* grad(U), grad(V), grad(W) of calcuvw / calcp: [0] three Gauss passes, 1 one kernel
                                   per pass for the three fields (experimental; each gradient bit-identical) */
+  FC_TUNE_TILE_CTAS = 7,       /* tiled sweeps: CTAs per SM the kernel's registers allow, [2] or 3           */
   FC_TUNE_SWEEP_TILED = 5      /* triangular sweeps: [0] one hand-over per dependency level,
                                   1 two-level schedule -- spatial tiles of <= 512 cells walked
                                   inside one CTA, hand-overs only between tile levels, 2 the

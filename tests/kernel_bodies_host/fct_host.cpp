@@ -28,7 +28,7 @@ namespace {
 thread_local unsigned fct_tid = 0;
 std::barrier<> *fct_bar = nullptr;
 }
-#define FCT_KERNEL static void
+#define FCT_KERNEL(OCC) static void
 #define FCT_SHARED static
 #define FCT_TID fct_tid
 #define FCT_SYNC() fct_bar->arrive_and_wait()
@@ -158,8 +158,8 @@ int fct_emu_sweep(void *h, int mode, int pre8, int p2p, int nsweeps, int n, cons
   kernel_t k = nullptr;
 #define FCT_PICK(M)                                                                                          \
   case M:                                                                                                    \
-    k = pre8 ? (p2p ? k_tile_sweep<M, 8, true> : k_tile_sweep<M, 8, false>)                                  \
-             : (p2p ? k_tile_sweep<M, 4, true> : k_tile_sweep<M, 4, false>);                                 \
+    k = pre8 ? (p2p ? k_tile_sweep<M, 8, true, 2> : k_tile_sweep<M, 8, false, 2>)                            \
+             : (p2p ? k_tile_sweep<M, 4, true, 2> : k_tile_sweep<M, 4, false, 2>);                           \
     break;
   switch (mode) {
     FCT_PICK(TRI_FWD) FCT_PICK(TRI_BWD) FCT_PICK(TRI_DIC) FCT_PICK(TRI_DIC_PAR) FCT_PICK(TRI_DILU)

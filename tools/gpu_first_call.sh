@@ -15,6 +15,7 @@ timeout 200 python tools/kernel_bench.py 216 10 > gpurun_out/kernel_bench_216.js
 timeout 120 python tools/simple_iter_bench.py 216 2 3 > gpurun_out/simple_iter_216.json 2>&1
 FCAPP_TUNE="sweep_tiled=1,fused_grad=1" timeout 120 python tools/simple_iter_bench.py 216 2 3 > gpurun_out/simple_iter_216_tiled.json 2>&1
 FCAPP_TUNE="sweep_tiled=2,fused_grad=1" timeout 120 python tools/simple_iter_bench.py 216 2 3 > gpurun_out/simple_iter_216_tiled_p2p.json 2>&1
+FCAPP_TUNE="sweep_tiled=2,tile_ctas=3,fused_grad=1" timeout 120 python tools/simple_iter_bench.py 216 2 3 > gpurun_out/simple_iter_216_tiled_p2p_occ3.json 2>&1
 timeout 300 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 tail -c 600 gpurun_out/bench_n1.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_simple.csv \
