@@ -91,7 +91,7 @@ struct fc_levels {                      // level schedule of the strict lower / 
   bool p2p_ok = false;                  // every block has <= FC_TRI_MAXP producers
   // tiled mode (FC_TUNE_SWEEP_TILED, fc_tile_schedule.hpp): a block = one spatial tile of FC_TILE slots, `nlev` etc.
   // count tile levels, and inside the tile the rows are walked by local level
-  int *llev = nullptr;                  // [nslots] local level of the row, -1 for padding
+  int4 *meta = nullptr;                 // [nslots] per slot: row (-1 = padding), local level, triangle range [s, e) in a / tja
   int *blk_nlev = nullptr;              // [nblocks] local levels of the tile
 };
 constexpr int FC_TRI_MAXP = 16;

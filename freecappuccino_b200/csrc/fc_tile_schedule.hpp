@@ -32,6 +32,8 @@ struct fc_tile_dir {                     // one sweep direction (strict lower or
   int max_local_levels = 0;
   std::vector<int> rows;                 // [nblocks * FC_TILE] row id (0-based) or -1; ascending inside a tile
   std::vector<int> llev;                 // [nblocks * FC_TILE] local level of that row, -1 for padding
+  std::vector<int> meta;                 // [nblocks * FC_TILE * 4] what the kernel reads per slot in one 16-byte load:
+                                         // row, local level, first and one-past-last position of its triangle in a / tja
   std::vector<int> blk_nlev;             // [nblocks] local levels of the tile
   std::vector<int> blk_level;            // [nblocks] tile level
   std::vector<int> lev_blocks_before;    // [nlev + 1] tiles in tile levels < L
@@ -203,6 +205,7 @@ inline bool build_dir(int n, const int *ioffset, const int *ja, const int *diag,
   for (int t = 0; t < ntiles; ++t) block_of_tile[t] = fill[tlev[t]]++;
   D.rows.assign((size_t)ntiles * FC_TILE, -1);
   D.llev.assign((size_t)ntiles * FC_TILE, -1);
+  D.meta.assign((size_t)ntiles * FC_TILE * 4, -1);
   D.blk_nlev.assign(ntiles, 0);
   D.blk_level.assign(ntiles, 0);
   D.max_local_levels = 0;
@@ -212,6 +215,9 @@ inline bool build_dir(int n, const int *ioffset, const int *ja, const int *diag,
     const size_t slot = (size_t)b * FC_TILE + pos[i];
     D.rows[slot] = i;
     D.llev[slot] = ll[i];
+    int ts, te;
+    tri_range(ioffset, diag, i, lower, ts, te);
+    D.meta[4 * slot] = i; D.meta[4 * slot + 1] = ll[i]; D.meta[4 * slot + 2] = ts; D.meta[4 * slot + 3] = te;
     D.blk_nlev[b] = std::max(D.blk_nlev[b], ll[i] + 1);
     D.max_local_levels = std::max(D.max_local_levels, ll[i] + 1);
   }

@@ -29,12 +29,11 @@
 // spills on hexahedra) -- a measurement knob, FC_TUNE_TILE_CTAS.
 template <int MODE, int PRE, bool P2P, int OCC>
 FCT_KERNEL(OCC)
-k_tile_sweep(const int *__restrict__ rows, const int *__restrict__ llev, const int *__restrict__ blk_nlev,
+k_tile_sweep(const int4 *__restrict__ meta, const int *__restrict__ blk_nlev,
              const int *__restrict__ blk_level, const int *__restrict__ lev_blocks_before, unsigned int *done,
              unsigned int *ready, unsigned int *ticket, const int *__restrict__ prod,
              const int *__restrict__ prod_cnt, unsigned int *flag, unsigned int ticket_base, unsigned int sweep_no,
-             const int *__restrict__ ioffset, const int *__restrict__ tja, const int *__restrict__ diag,
-             const int *__restrict__ tpos, const double *__restrict__ a, const double *__restrict__ d,
+             const int *__restrict__ tja, const int *__restrict__ diag, const int *__restrict__ tpos, const double *__restrict__ a, const double *__restrict__ d,
              const double *__restrict__ in, double *out, double small, double padd, const fc_scalars *sc) {
   FCT_SHARED double s_z[FC_TILE];
   FCT_SHARED unsigned int s_b;
@@ -43,16 +42,12 @@ k_tile_sweep(const int *__restrict__ rows, const int *__restrict__ llev, const i
   FCT_SYNC();
   const unsigned int b = s_b;
   const int lev = blk_level[b], nl = blk_nlev[b];
-  const size_t slot = (size_t)b * FC_TILE + FCT_TID;
-  const int row = rows[slot];
-  const int my = llev[slot];
-  int s = 0, e = 0;
+  const int4 mt = meta[(size_t)b * FC_TILE + FCT_TID];   // row, local level, triangle [s, e): one 16-byte load
+  const int row = mt.x, my = mt.y, s = mt.z, e = mt.w;
   double v = 0.0, di = 0.0;
   double pa[PRE], pt[PRE], zq[PRE];
   int pj[PRE];
   if (row >= 0) {
-    if (MODE == TRI_BWD) { s = diag[row] + 1; e = ioffset[row + 1]; }
-    else { s = ioffset[row]; e = diag[row]; }
 FCT_UNROLL
     for (int q = 0; q < PRE; ++q) {
       const int k = s + q;

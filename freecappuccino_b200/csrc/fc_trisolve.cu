@@ -340,8 +340,8 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
     const bool p2p = ctx->tune_sweep_tiled == 2 && T.p2p_ok;
 #define FC_TILE_LAUNCH_OCC(PRE_, P2P_, OCC_)                                                                         \
   k_tile_sweep<MODE, PRE_, P2P_, OCC_><<<T.nblocks, FC_TILE, 0, ctx->stream>>>(                                       \
-      T.rows, T.llev, T.blk_nlev, T.blk_level, T.lev_blocks_before, T.done, T.ready, T.ticket, T.prod, T.prod_cnt,    \
-      T.flag, tbase, (unsigned int)T.epoch, ctx->ioffset, ctx->tja, ctx->diag, ctx->tpos, a, d, in, out, small, padd, \
+      T.meta, T.blk_nlev, T.blk_level, T.lev_blocks_before, T.done, T.ready, T.ticket, T.prod, T.prod_cnt, T.flag,    \
+      tbase, (unsigned int)T.epoch, ctx->tja, ctx->diag, ctx->tpos, a, d, in, out, small, padd,                      \
       guarded ? ctx->sc : nullptr)
 #define FC_TILE_LAUNCH(PRE_, P2P_)                                            \
   do {                                                                        \
@@ -376,7 +376,7 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
 
 void fc_levels_free(fc_levels &L) {
   cudaFree(L.rows); cudaFree(L.blk_level); cudaFree(L.lev_blocks_before); cudaFree(L.done); cudaFree(L.ready);
-  cudaFree(L.ticket); cudaFree(L.prod); cudaFree(L.prod_cnt); cudaFree(L.flag); cudaFree(L.llev); cudaFree(L.blk_nlev);
+  cudaFree(L.ticket); cudaFree(L.prod); cudaFree(L.prod_cnt); cudaFree(L.flag); cudaFree(L.meta); cudaFree(L.blk_nlev);
   L = fc_levels{};
 }
 
@@ -387,8 +387,7 @@ int upload_tile_dir(fc_context *ctx, const fc_tile_dir &D, fc_levels &L) {
   L.nlev = D.nlev;
   L.nblocks = D.nblocks;
   L.nslots = D.nblocks * FC_TILE;
-  FC_CHECK(fc_dev_alloc(ctx, &L.rows, D.rows.size()));
-  FC_CHECK(fc_dev_alloc(ctx, &L.llev, D.llev.size()));
+  FC_CHECK(fc_dev_alloc(ctx, &L.meta, D.meta.size() / 4));
   FC_CHECK(fc_dev_alloc(ctx, &L.blk_nlev, D.blk_nlev.size()));
   FC_CHECK(fc_dev_alloc(ctx, &L.blk_level, D.blk_level.size()));
   FC_CHECK(fc_dev_alloc(ctx, &L.lev_blocks_before, D.lev_blocks_before.size()));
@@ -400,7 +399,7 @@ int upload_tile_dir(fc_context *ctx, const fc_tile_dir &D, fc_levels &L) {
   FC_CHECK(fc_dev_alloc(ctx, &L.flag, (size_t)D.nblocks));
   L.p2p_ok = D.p2p_ok;
   const struct { int *dst; const std::vector<int> *src; } up[] = {
-      {L.rows, &D.rows}, {L.llev, &D.llev}, {L.blk_nlev, &D.blk_nlev}, {L.blk_level, &D.blk_level},
+      {(int *)L.meta, &D.meta}, {L.blk_nlev, &D.blk_nlev}, {L.blk_level, &D.blk_level},
       {L.lev_blocks_before, &D.lev_blocks_before}, {L.prod, &D.prod}, {L.prod_cnt, &D.prod_cnt}};
   for (const auto &u : up)
     FC_CUDA(cudaMemcpyAsync(u.dst, u.src->data(), sizeof(int) * u.src->size(), cudaMemcpyHostToDevice, ctx->stream));

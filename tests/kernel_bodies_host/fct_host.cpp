@@ -24,6 +24,7 @@ enum { TRI_FWD = 0, TRI_BWD = 1, TRI_DIC = 2, TRI_DIC_PAR = 3, TRI_DILU = 4 };
 
 // ---- host stand-ins for what fc_tile_sweep.cuh expects from its includer ----
 struct fc_scalars { int done; };
+struct int4 { int x, y, z, w; };
 namespace {
 thread_local unsigned fct_tid = 0;
 std::barrier<> *fct_bar = nullptr;
@@ -151,10 +152,10 @@ int fct_emu_sweep(void *h, int mode, int pre8, int p2p, int nsweeps, int n, cons
   const fc_tile_dir &D = mode == TRI_BWD ? S.upper : S.lower;
   std::vector<unsigned int> done(D.nlev, 0), ready(D.nlev, 0), flag(D.nblocks, 0);
   unsigned int ticket = 0;
-  using kernel_t = void (*)(const int *, const int *, const int *, const int *, const int *, unsigned int *,
-                            unsigned int *, unsigned int *, const int *, const int *, unsigned int *, unsigned int,
-                            unsigned int, const int *, const int *, const int *, const int *, const double *,
-                            const double *, const double *, double *, double, double, const fc_scalars *);
+  using kernel_t = void (*)(const int4 *, const int *, const int *, const int *, unsigned int *, unsigned int *,
+                            unsigned int *, const int *, const int *, unsigned int *, unsigned int, unsigned int,
+                            const int *, const int *, const int *, const double *, const double *, const double *,
+                            double *, double, double, const fc_scalars *);
   kernel_t k = nullptr;
 #define FCT_PICK(M)                                                                                          \
   case M:                                                                                                    \
@@ -177,9 +178,9 @@ int fct_emu_sweep(void *h, int mode, int pre8, int p2p, int nsweeps, int n, cons
       th.emplace_back([&, t]() {
         fct_tid = (unsigned)t;
         for (int b = 0; b < D.nblocks; ++b) {   // one CTA after the other: the static "shared" arrays are reused
-          k(D.rows.data(), D.llev.data(), D.blk_nlev.data(), D.blk_level.data(), D.lev_blocks_before.data(),
+          k((const int4 *)D.meta.data(), D.blk_nlev.data(), D.blk_level.data(), D.lev_blocks_before.data(),
             done.data(), ready.data(), &ticket, D.prod.data(), D.prod_cnt.data(), flag.data(), base,
-            (unsigned int)sweep, ioffset, S.tja.data(), diag, tpos, a, d, in, out, small, padd, nullptr);
+            (unsigned int)sweep, S.tja.data(), diag, tpos, a, d, in, out, small, padd, nullptr);
           bar.arrive_and_wait();
         }
       });
