@@ -11,7 +11,7 @@ timeout 600 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1
 tail -5 gpurun_out/pytest_gpu.log
 FCAPP_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz9_experimental.py -q -m gpu -s > gpurun_out/pytest_experimental.log 2>&1
 grep "sweeps\]\|passed\|failed" gpurun_out/pytest_experimental.log | tail -24
-timeout 200 python tools/kernel_bench.py 216 10 > gpurun_out/kernel_bench_216.jsonl 2> gpurun_out/kernel_bench.err
+timeout 300 python tools/kernel_bench.py 216 10 > gpurun_out/kernel_bench_216.jsonl 2> gpurun_out/kernel_bench.err
 timeout 120 python tools/simple_iter_bench.py 216 2 3 > gpurun_out/simple_iter_216.json 2>&1
 FCAPP_TUNE="sweep_tiled=1,fused_grad=1" timeout 120 python tools/simple_iter_bench.py 216 2 3 > gpurun_out/simple_iter_216_tiled.json 2>&1
 FCAPP_TUNE="sweep_tiled=2,fused_grad=1" timeout 120 python tools/simple_iter_bench.py 216 2 3 > gpurun_out/simple_iter_216_tiled_p2p.json 2>&1
