@@ -629,6 +629,18 @@ int fc_set_tuning(fc_context *ctx, int key, int value) {
   return FC_OK;
 }
 
+const char *fc_sweep_schedule_info(fc_context *ctx) {
+  if (!ctx) return "";
+  if (!ctx->has_levels) { ctx->sweep_info = "no sweep has run on this pattern yet"; return ctx->sweep_info.c_str(); }
+  ctx->sweep_info = "level schedule: " + std::to_string(ctx->lower.nlev) + " / " + std::to_string(ctx->upper.nlev) +
+                    " row levels (lower / upper triangle)";
+  if (ctx->tune_sweep_tiled) {
+    if (ctx->tiles_ok) ctx->sweep_info += "; in use: tiled schedule, " + ctx->tiles_info;
+    else ctx->sweep_info += "; tiled schedule requested but not used: " + (ctx->tiles_tried ? ctx->tiles_why : std::string("not built yet"));
+  }
+  return ctx->sweep_info.c_str();
+}
+
 int fc_get_timings(const fc_context *ctx, fc_timings *t) {
   if (!ctx || !t) return FC_ERR_ARG;
   *t = ctx->tm;

@@ -155,6 +155,8 @@ struct fc_context {
   int *tja = nullptr;                   // [nnz] column, or -(slot+1) when the column's row sits in the same tile
   bool tiles_tried = false, tiles_ok = false, tiles_pre8 = false;
   std::string tiles_why;                // why the mesh got no tiling
+  std::string tiles_info;               // tiles, tile levels, local levels of the tiling in use
+  std::string sweep_info;               // fc_sweep_schedule_info's answer
 
   // ---- communication ----
   ncclComm_t comm = nullptr;

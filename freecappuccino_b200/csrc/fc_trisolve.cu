@@ -448,6 +448,12 @@ int build_tiles(fc_context *ctx) {
   FC_CHECK(upload_tile_dir(ctx, S.lower, ctx->tile_lower));
   FC_CHECK(upload_tile_dir(ctx, S.upper, ctx->tile_upper));
   ctx->tiles_pre8 = S.max_tri_len > 4;
+  ctx->tiles_info = std::to_string(S.ntiles) + " tiles of <= " + std::to_string(S.max_tile_rows) + " rows (bins of " +
+                    std::to_string(S.cells_per_axis) + " cells per axis, " + std::to_string(S.repaired_rows) +
+                    " rows in cut bins), " + std::to_string(S.lower.nlev) + " / " + std::to_string(S.upper.nlev) +
+                    " tile levels, <= " + std::to_string(std::max(S.lower.max_local_levels, S.upper.max_local_levels)) +
+                    " local levels, <= " + std::to_string(std::max(S.lower.max_producers, S.upper.max_producers)) +
+                    " producer tiles, estimated critical path " + std::to_string(S.cost / 10) + " us";
   ctx->tiles_ok = true;
   return FC_OK;
 }

@@ -42,7 +42,7 @@ SYMBOLS = (
     "fc_get_timings", "fc_time_spmv", "fc_stream", "fc_copy", "fc_set_spmv_sampling", "fc_comm_p2p_blob",
     "fc_comm_p2p_open", "fc_set_tuning", "fc_calcuvw_assemble", "fc_calcuvw_component", "fc_calcuvw",
     "fc_calcuvw_host", "fc_piso", "fc_set_gradient", "fc_grad", "fc_dpcg", "fc_iccg", "fc_bicgstab",
-    "fc_calcp_correct",
+    "fc_calcp_correct", "fc_sweep_schedule_info",
 )
 GRAD_METHODS = {"gauss": 0, "lstsq": 1, "lstsq_qr": 2, "lstsq_dm": 3}
 LIMITERS = {"no-limit": 0, "Barth-Jespersen": 1, "Venkatakrishnan": 2, "mVenkatakrishnan": 3}
@@ -168,12 +168,14 @@ def load() -> C.CDLL:
                 "(or __graft_entry__.build()).  freecappuccino_b200 has no CPU fallback.")
         lib = C.CDLL(LIB_PATH)
         lib.fc_last_error.restype = C.c_char_p
+        lib.fc_sweep_schedule_info.restype = C.c_char_p
+        lib.fc_sweep_schedule_info.argtypes = [C.c_void_p]
         lib.fc_last_error.argtypes = [C.c_void_p]
         lib.fc_stream.restype = C.c_void_p
         lib.fc_stream.argtypes = [C.c_void_p]
         for name in SYMBOLS:
             fn = getattr(lib, name)
-            if name not in ("fc_last_error", "fc_stream"):
+            if name not in ("fc_last_error", "fc_stream", "fc_sweep_schedule_info"):
                 fn.restype = C.c_int
         _LIB = lib
     return _LIB
@@ -334,6 +336,10 @@ class Context:
     def set_tuning(self, key: int, value: int):
         """Kernel selection for A/B measurements (TUNE_* keys, include/fcapp.h)."""
         self._ck(self.lib.fc_set_tuning(self.h, int(key), int(value)))
+
+    def sweep_schedule_info(self) -> str:
+        """Which schedule the triangular sweeps of the last iccg / bicgstab solve used (fc_sweep_schedule_info)."""
+        return (self.lib.fc_sweep_schedule_info(self.h) or b"").decode()
 
     def set_spmv_sampling(self, max_samples: int):
         self._ck(self.lib.fc_set_spmv_sampling(self.h, max_samples))

@@ -364,6 +364,10 @@ enum {
                                   the level schedule stays; same row sums, bit-identical results) */
 };
 int fc_set_tuning(fc_context *ctx, int key, int value);
+/* One line on the schedule the triangular sweeps of the last iccg / bicgstab solve used: row levels of the level
+ * schedule and, with FC_TUNE_SWEEP_TILED, the tiling (tiles, tile levels, local levels) or why the mesh got none.
+ * The string belongs to the context and is valid until the next call.                                          */
+const char *fc_sweep_schedule_info(fc_context *ctx);
 /* Bracket up to `max_samples` SpMV launches of every following solve with CUDA
  * events on the library stream (0 switches it off).                          */
 int fc_set_spmv_sampling(fc_context *ctx, int max_samples);

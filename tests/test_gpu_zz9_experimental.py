@@ -57,8 +57,10 @@ def test_sweep_variants_are_bit_identical_to_level_sweeps(fc, name, solver, mode
             ms = ctx.timings().solve_ms
             best = ms if best is None else min(best, ms)
         res.append((rep.iters, rep.res0, rep.resl, ctx.download("PP"), ctx.download("RES"), best))
-        if mode.startswith("tiled") and p2p and name in ("hex", "slab", "poly"):
-            assert ctx.timings().sweep_tiles > 0, "the tiled schedule was not used"
+        if mode.startswith("tiled") and p2p:
+            print("\n[schedule]", name, ctx.sweep_schedule_info())
+            if name in ("hex", "slab", "poly"):
+                assert ctx.timings().sweep_tiles > 0, "the tiled schedule was not used: " + ctx.sweep_schedule_info()
         ctx.close()
     (i0, a0, b0, x0, r0, t0), (i1, a1, b1, x1, r1, t1) = res
     print(f"\\n[{mode} sweeps] {name} {solver}: {i0} iterations, level mode {t0:.3f} ms, {mode} mode {t1:.3f} ms")

@@ -114,7 +114,7 @@ def main():
                     rep = ctx.solve(solver, "PP", lib.solver_opts(1e-30, 20))
                 t = ctx.timings()
                 report(f"{solver} iteration, {label}", t.solve_ms / max(rep.iters, 1), nbytes, iters=rep.iters,
-                       solve_ms=t.solve_ms, sweep_tiles=t.sweep_tiles)
+                       solve_ms=t.solve_ms, sweep_tiles=t.sweep_tiles, schedule=ctx.sweep_schedule_info())
         except lib.FcError as e:
             print(json.dumps(dict(op=label, error=str(e))), flush=True)
         ctx.set_tuning(key, 0)
