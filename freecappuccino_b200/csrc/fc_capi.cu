@@ -106,7 +106,7 @@ void free_all(fc_context *ctx) {
                   (void *)ctx->vk, (void *)ctx->adiag, (void *)ctx->tt, (void *)ctx->coef, (void *)ctx->facev,
                   (void *)ctx->gtmp, (void *)ctx->partials, (void *)ctx->sc, (void *)ctx->bufind,
                   (void *)ctx->sendbuf, (void *)ctx->strip_off, (void *)ctx->strip_idx,
-                  (void *)ctx->strip_any32, (void *)ctx->persist, (void *)ctx->uvw_face, (void *)ctx->hcoef, (void *)ctx->dmat, (void *)ctx->tja, (void *)ctx->gtmp3,
+                  (void *)ctx->strip_any32, (void *)ctx->persist, (void *)ctx->uvw_face, (void *)ctx->hcoef, (void *)ctx->dmat, (void *)ctx->tja, (void *)ctx->gtmp3, (void *)ctx->sweep_chk,
                   (void *)ctx->dmatqr})
     if (p) cudaFree(p);
   for (int f = 0; f < FC_NUM_FIELDS; ++f)
@@ -622,6 +622,7 @@ int fc_set_tuning(fc_context *ctx, int key, int value) {
     case FC_TUNE_CTAS_PER_SM: if (value < 0 || value > 8) return FC_ERR_ARG; ctx->tune_ctas_per_sm = value; break;
     case FC_TUNE_SWEEP_P2P: if (value < 0 || value > 1) return FC_ERR_ARG; ctx->tune_sweep_p2p = value; break;
     case FC_TUNE_FUSED_GRAD: if (value < 0 || value > 1) return FC_ERR_ARG; ctx->tune_fused_grad = value; break;
+    case FC_TUNE_SWEEP_CHECK: if (value < 0 || value > 1) return FC_ERR_ARG; ctx->tune_sweep_check = value; break;
     case FC_TUNE_TILE_CTAS: if (value != 2 && value != 3) return FC_ERR_ARG; ctx->tune_tile_ctas = value; break;
     case FC_TUNE_SWEEP_TILED: if (value < 0 || value > 2) return FC_ERR_ARG; ctx->tune_sweep_tiled = value; break;
     default: FC_FAIL(FC_ERR_ARG, "fc_set_tuning: unknown key");

@@ -183,6 +183,8 @@ struct fc_context {
   int tune_sweep_p2p = 0;               // triangular sweeps: 1 = point-to-point block flags instead of level counters
   int first_batch[3] = {8, 8, 8};       // per solver: iterations enqueued before the first look at `done`
   int tune_fused_grad = 0;              // 1: the three velocity gradients of calcuvw / calcp in one kernel per pass
+  int tune_sweep_check = 0;             // debugging: every tiled sweep is repeated with the level schedule and compared
+  double *sweep_chk = nullptr;          // [n + 2] scratch of that comparison (+ two counters)
   int tune_tile_ctas = 2;               // tiled sweeps: CTAs per SM the kernel is compiled for (2 or 3)
   int tune_sweep_tiled = 0;             // triangular sweeps: 1 = two-level tiled schedule where the mesh allows it
   fc_persist_state *persist = nullptr;  // device: grid barrier + phase clocks of the persistent kernel

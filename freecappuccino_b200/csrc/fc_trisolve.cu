@@ -330,6 +330,17 @@ k_tri_sweep(const int *__restrict__ rows, const int *__restrict__ blk_level,
 static_assert(FC_TILE_MAXP == FC_TRI_MAXP, "one producer-table width");
 #include "fc_tile_sweep.cuh"   // k_tile_sweep<MODE, PRE, P2P>
 
+// FC_TUNE_SWEEP_CHECK: rows whose bits differ between two sweeps of the same input (count, lowest row)
+__global__ void k_sweep_compare(int n, const double *__restrict__ x, const double *__restrict__ y, unsigned int *bad,
+                                const fc_scalars *sc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (sc && sc->done)) return;   // a solve that has converged skips both sweeps: nothing to compare
+  if (__double_as_longlong(x[i]) != __double_as_longlong(y[i])) {
+    atomicAdd(bad, 1u);
+    atomicMin(bad + 1, (unsigned int)i);
+  }
+}
+
 template <int MODE>
 int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const double *in, double *out,
           double small, double padd, bool guarded) {
@@ -353,6 +364,27 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
 #undef FC_TILE_LAUNCH
 #undef FC_TILE_LAUNCH_OCC
     FC_LAUNCH_CHECK();
+    if (!ctx->tune_sweep_check) return FC_OK;
+    // debugging aid: the same sweep once more with the level schedule into a scratch vector, compared bit for bit
+    if (!ctx->sweep_chk) FC_CHECK(fc_dev_alloc(ctx, &ctx->sweep_chk, (size_t)ctx->n + 2));
+    unsigned int *bad = reinterpret_cast<unsigned int *>(ctx->sweep_chk + ctx->n);
+    const unsigned int init[2] = {0u, 0xffffffffu};
+    FC_CUDA(cudaMemcpyAsync(bad, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    const int saved = ctx->tune_sweep_tiled;
+    ctx->tune_sweep_tiled = 0;
+    const int rc = sweep<MODE>(ctx, L, a, d, in, ctx->sweep_chk, small, padd, guarded);
+    ctx->tune_sweep_tiled = saved;
+    FC_CHECK(rc);
+    k_sweep_compare<<<fc_blocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->n, out, ctx->sweep_chk, bad,
+                                                                        guarded ? ctx->sc : nullptr);
+    FC_LAUNCH_CHECK();
+    unsigned int h[2] = {0u, 0u};
+    FC_CUDA(cudaMemcpyAsync(h, bad, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    FC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h[0] > 0)
+      FC_FAIL(FC_ERR_CUDA, "tiled sweep (mode " + std::to_string(MODE) + (&L == &ctx->lower ? ", lower" : ", upper") +
+                               " triangle, sweep " + std::to_string(T.epoch) + ") differs from the level sweep in " +
+                               std::to_string(h[0]) + " rows, first row " + std::to_string(h[1] + 1));
     return FC_OK;
   }
   const int nblocks = L.nslots / TRI_BLOCK;

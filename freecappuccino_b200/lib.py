@@ -50,9 +50,10 @@ TUNE_SPMV_KERNEL, TUNE_DPCG_PERSISTENT, TUNE_CTAS_PER_SM, TUNE_PIPE_GEOMETRY, TU
 TUNE_SWEEP_TILED = 5
 TUNE_FUSED_GRAD = 6
 TUNE_TILE_CTAS = 7
+TUNE_SWEEP_CHECK = 8
 TUNE_KEYS = {"spmv_kernel": TUNE_SPMV_KERNEL, "dpcg_persistent": TUNE_DPCG_PERSISTENT, "ctas_per_sm": TUNE_CTAS_PER_SM,
              "pipe_geometry": TUNE_PIPE_GEOMETRY, "sweep_p2p": TUNE_SWEEP_P2P, "sweep_tiled": TUNE_SWEEP_TILED,
-             "fused_grad": TUNE_FUSED_GRAD, "tile_ctas": TUNE_TILE_CTAS}
+             "fused_grad": TUNE_FUSED_GRAD, "tile_ctas": TUNE_TILE_CTAS, "sweep_check": TUNE_SWEEP_CHECK}
 
 
 class MeshDesc(C.Structure):

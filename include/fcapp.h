@@ -355,6 +355,8 @@ enum {
                                   same row sums, bit-identical results)                      */
   FC_TUNE_FUSED_GRAD = 6,      /* grad(U), grad(V), grad(W) of calcuvw / calcp: [0] three Gauss passes, 1 one kernel
                                   per pass for the three fields (experimental; each gradient bit-identical) */
+  FC_TUNE_SWEEP_CHECK = 8,     /* debugging: 1 repeats every tiled sweep with the level schedule and fails the call
+                                  (FC_ERR_CUDA, first differing row in fc_last_error) if a single bit differs     */
   FC_TUNE_TILE_CTAS = 7,       /* tiled sweeps: CTAs per SM the kernel's registers allow, [2] or 3           */
   FC_TUNE_SWEEP_TILED = 5      /* triangular sweeps: [0] one hand-over per dependency level,
                                   1 two-level schedule -- spatial tiles of <= 512 cells walked

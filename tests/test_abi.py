@@ -53,7 +53,7 @@ def test_enum_constants_match_header(tmp_path):
     import subprocess
     from freecappuccino_b200 import lib
     names = ["FC_TUNE_SPMV_KERNEL", "FC_TUNE_DPCG_PERSISTENT", "FC_TUNE_CTAS_PER_SM", "FC_TUNE_PIPE_GEOMETRY",
-             "FC_TUNE_SWEEP_P2P", "FC_TUNE_SWEEP_TILED", "FC_TUNE_FUSED_GRAD", "FC_TUNE_TILE_CTAS", "FC_DPCG", "FC_ICCG", "FC_BICGSTAB",
+             "FC_TUNE_SWEEP_P2P", "FC_TUNE_SWEEP_TILED", "FC_TUNE_FUSED_GRAD", "FC_TUNE_TILE_CTAS", "FC_TUNE_SWEEP_CHECK", "FC_DPCG", "FC_ICCG", "FC_BICGSTAB",
              "FC_OK", "FC_ERR_ARG", "FC_ERR_CUDA", "FC_ERR_NCCL", "FC_ERR_UNSUPPORTED", "FC_ERR_NODEVICE",
              "FC_VIS", "FC_SP", "FC_FLMASS", "FC_USER3"]
     src = tmp_path / "enums.c"
@@ -65,7 +65,7 @@ def test_enum_constants_match_header(tmp_path):
     want = {"FC_TUNE_SPMV_KERNEL": lib.TUNE_SPMV_KERNEL, "FC_TUNE_DPCG_PERSISTENT": lib.TUNE_DPCG_PERSISTENT,
             "FC_TUNE_CTAS_PER_SM": lib.TUNE_CTAS_PER_SM, "FC_TUNE_PIPE_GEOMETRY": lib.TUNE_PIPE_GEOMETRY,
             "FC_TUNE_SWEEP_P2P": lib.TUNE_SWEEP_P2P, "FC_TUNE_SWEEP_TILED": lib.TUNE_SWEEP_TILED,
-            "FC_TUNE_FUSED_GRAD": lib.TUNE_FUSED_GRAD, "FC_TUNE_TILE_CTAS": lib.TUNE_TILE_CTAS, "FC_DPCG": lib.DPCG, "FC_ICCG": lib.ICCG,
+            "FC_TUNE_FUSED_GRAD": lib.TUNE_FUSED_GRAD, "FC_TUNE_TILE_CTAS": lib.TUNE_TILE_CTAS, "FC_TUNE_SWEEP_CHECK": lib.TUNE_SWEEP_CHECK, "FC_DPCG": lib.DPCG, "FC_ICCG": lib.ICCG,
             "FC_BICGSTAB": lib.BICGSTAB, "FC_OK": lib.FC_OK, "FC_ERR_ARG": lib.FC_ERR_ARG, "FC_ERR_CUDA": lib.FC_ERR_CUDA,
             "FC_ERR_NCCL": lib.FC_ERR_NCCL, "FC_ERR_UNSUPPORTED": lib.FC_ERR_UNSUPPORTED,
             "FC_ERR_NODEVICE": lib.FC_ERR_NODEVICE, "FC_VIS": lib.F["VIS"], "FC_SP": lib.F["SP"],

@@ -44,12 +44,16 @@ def test_sweep_variants_are_bit_identical_to_level_sweeps(fc, name, solver, mode
         ctx.set_mesh(mesh)
         ctx.create_csr(download=False)
         ctx.set_tuning(key, value * p2p)
+        if mode.startswith("tiled") and p2p:
+            ctx.set_tuning(fc.TUNE_SWEEP_CHECK, 1)    # every tiled sweep is compared with the level sweep on the device
         ctx.upload("APU", -np.ones(mesh.numCells))
         ctx.upload("SU", su)
         ctx.fill("PP", 0.0)
         ctx.laplacian("APU", "PP")
         best = None
         for rep_i in range(3):
+            if rep_i == 1:
+                ctx.set_tuning(fc.TUNE_SWEEP_CHECK, 0)   # the first solve checks, the others are timed
             ctx.fill("PP", 0.0)
             t0 = time.perf_counter()
             rep = ctx.solve(solver, "PP", fc.solver_opts(1e-9, 300))
