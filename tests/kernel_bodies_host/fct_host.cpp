@@ -143,6 +143,19 @@ int fct_sweep(void *h, int mode, int n, const int *ioffset, const int *diag, con
   return bad;
 }
 
+// can this machine run FC_TILE threads at once?  (the emulation would dead-lock in its barrier otherwise)
+int fct_can_emulate(void) {
+  std::vector<std::thread> th;
+  bool ok = true;
+  try {
+    for (int t = 0; t < FC_TILE; ++t) th.emplace_back([]() {});
+  } catch (...) {
+    ok = false;
+  }
+  for (auto &x : th) x.join();
+  return ok ? 1 : 0;
+}
+
 // the kernel source itself, CTA by CTA; `nsweeps` launches in a row on the same counters.  Returns 0, or -1 for an
 // unknown mode.  `out` is refilled with NaN before every launch.
 int fct_emu_sweep(void *h, int mode, int pre8, int p2p, int nsweeps, int n, const int *ioffset, const int *diag,
