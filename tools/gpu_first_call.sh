@@ -30,3 +30,11 @@ FCAPP_TUNE="sweep_tiled=1" timeout 300 ncu --set full --clock-control none --imp
     -o gpurun_out/prof_tile_sweep python tools/simple_iter_bench.py 128 0 1 > gpurun_out/ncu_tile.log 2>&1
 python tools/ncu_summary.py full gpurun_out/prof_tile_sweep.ncu-rep > gpurun_out/prof_tile_sweep.txt 2>/dev/null
 ls -la gpurun_out | tail -8
+# memory / race checks of the kernels that have never run before (small meshes; a few minutes)
+FCAPP_EXPERIMENTAL=1 timeout 300 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_zz9_experimental.py -q -m gpu \
+    -k "tiled and poly and iccg" > gpurun_out/sanitizer_race_tile.log 2>&1
+FCAPP_EXPERIMENTAL=1 timeout 300 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_zz9_experimental.py -q -m gpu \
+    -k "(tiled and slab and bicgstab) or (fused and poly)" > gpurun_out/sanitizer_mem_experimental.log 2>&1
+timeout 400 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_zz2_piso.py tests/test_gpu_zz3_gradients.py -q -m gpu \
+    -k "(without_krylov and skew) or (dispatcher and poly) or configured_gradients" > gpurun_out/sanitizer_mem_widened.log 2>&1
+grep -h "ERROR SUMMARY\|passed\|failed" gpurun_out/sanitizer_*.log
