@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
-# First gpurun call of a round (1 GPU, about 15-20 minutes):
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_first_call.sh'
+# First gpurun call of a round (1 GPU, about 20-25 minutes):
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/gpu_first_call.sh'
 # Runs the GPU test suite, the per-operation roofline table, the bench line, the ncu launch list of the bench and one
 # full ncu capture of the assembly / momentum / sweep kernels; everything lands in gpurun_out/ (copy what should be
 # judged into profiles/).
