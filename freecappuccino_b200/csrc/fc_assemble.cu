@@ -591,7 +591,7 @@ int fc_calcp_assemble_dev(fc_context *ctx, const fc_calcp_opts *o) {
   FC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
   if (ctx->csr_dup) FC_CUDA(cudaMemsetAsync(ctx->field[FC_A], 0, sizeof(double) * (size_t)ctx->nnz, ctx->stream));
   // grad(U), grad(V), grad(W)   (calcp :38-40)
-  FC_CHECK(fc_grad_uvw_dev(ctx, o->nigrad));
+  FC_CHECK(fc_grad_uvw_dev(ctx, o->nigrad, false));
   if (ctx->F > 0) {
     const int G = fc_blocks(ctx->F, B);
     if (o->flux_variant == 0)

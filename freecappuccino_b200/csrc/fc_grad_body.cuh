@@ -238,24 +238,26 @@ FCM_HD void fcg_limiter_row(const fcm_geom &g, const int *ioffset, const int *ja
   FCM_G3(grad, 2, c) = slopelimit * gz;
 }
 
-// ---- three Gauss gradients in one walk (opt-in, FC_TUNE_FUSED_GRAD) ----
-// grad_gauss (grad_gauss.f90:43-113; gradco :128-190; gradbc :194-211) applied to u, v and w at once: calcuvw
-// (:59-61) and calcp (:38-40) always ask for the three velocity gradients together, and two thirds of what one pass
-// reads -- the cell-to-face map, the face vectors and the interpolation factors -- does not depend on the field.
-// Per field the expressions and their order are those of k_grad_pass (fc_assemble.cu), so each gradient is
-// bit-identical to the one-field pass.  npro / fpro: processor faces of the multi-rank build
-// (src-parallel/grad_gauss.f90:68-75), halo cell = n + i.
-struct fcg_gauss3 {
+// ---- several Gauss gradients in one walk (opt-in, FC_TUNE_FUSED_GRAD) ----
+// grad_gauss (grad_gauss.f90:43-113; gradco :128-190; gradbc :194-211) applied to NF fields at once: calcuvw
+// (:59-61) and calcp (:38-40) always ask for the three velocity gradients together (calcuvw also for the first
+// pressure stage right after them), and two thirds of what one pass reads -- the cell-to-face map, the face vectors
+// and the interpolation factors -- does not depend on the field.  Per field the expressions and their order are those
+// of k_grad_pass (fc_assemble.cu), so each gradient is bit-identical to the one-field pass.  npro / fpro: processor
+// faces of the multi-rank build (src-parallel/grad_gauss.f90:68-75), halo cell = n + i.
+constexpr int FCG_MAXF = 4;
+struct fcg_gaussn {
   int npro;
   const double *fpro;
-  const double *phi[3];   // u, v, w  [numTotal]
-  const double *old[3];   // gradients of the previous pass (HAS_OLD) or unused
-  double *out[3];         // (3,numCells)
+  const double *phi[FCG_MAXF];   // e.g. u, v, w, p  [numTotal]
+  const double *old[FCG_MAXF];   // gradients of the previous pass (HAS_OLD) or unused
+  double *out[FCG_MAXF];         // (3,numCells)
 };
 
-template <bool HAS_OLD>
-FCM_HD void fcg_gauss3_row(const fcm_geom &g, const fcm_c2f &m, const fcg_gauss3 &k, int c) {
-  double gx[3] = {0.0, 0.0, 0.0}, gy[3] = {0.0, 0.0, 0.0}, gz[3] = {0.0, 0.0, 0.0};
+template <int NF, bool HAS_OLD>
+FCM_HD void fcg_gaussn_row(const fcm_geom &g, const fcm_c2f &m, const fcg_gaussn &k, int c) {
+  double gx[NF], gy[NF], gz[NF];
+  for (int t = 0; t < NF; ++t) gx[t] = gy[t] = gz[t] = 0.0;
   const int s = m.off[c], e = m.off[c + 1];
   for (int q = s; q < e; ++q) {
     const int fe = m.face[q];
@@ -276,7 +278,7 @@ FCM_HD void fcg_gauss3_row(const fcm_geom &g, const fcm_c2f &m, const fcg_gauss3
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-      for (int t = 0; t < 3; ++t) {
+      for (int t = 0; t < NF; ++t) {
         const double *phi = k.phi[t];
         double fie = phi[ijp] * fxp + phi[ijn] * fxn;
         if (HAS_OLD) {
@@ -294,14 +296,14 @@ FCM_HD void fcg_gauss3_row(const fcm_geom &g, const fcm_c2f &m, const fcg_gauss3
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-      for (int t = 0; t < 3; ++t) {
+      for (int t = 0; t < NF; ++t) {
         const double fi = k.phi[t][o];
         gx[t] = gx[t] + fi * sx; gy[t] = gy[t] + fi * sy; gz[t] = gz[t] + fi * sz;
       }
     }
   }
   const double volr = 1.0 / g.vol[c];
-  for (int t = 0; t < 3; ++t) {
+  for (int t = 0; t < NF; ++t) {
     FCM_G3(k.out[t], 0, c) = gx[t] * volr;
     FCM_G3(k.out[t], 1, c) = gy[t] * volr;
     FCM_G3(k.out[t], 2, c) = gz[t] * volr;

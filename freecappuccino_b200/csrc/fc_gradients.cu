@@ -13,6 +13,7 @@
 #include "fc_reduce.cuh"
 
 int fc_grad_gauss_dev(fc_context *ctx, double *phi, double *grad, int nigrad);   // fc_assemble.cu
+int fc_bpres_dev(fc_context *ctx, double *p, const double *dPdxi, int istage);       // fc_assemble.cu
 
 namespace {
 
@@ -36,11 +37,11 @@ k_grad_lsq_qr(fcm_geom g, fcm_c2f m, const double *D, const double *fi, double *
   if (c < g.n) fcg_grad_lsq_qr_row(g, m, D, fi, out, c);
 }
 
-// u, v, w in one walk over the map (fcg_gauss3_row); 5 CTAs of 256 threads per SM keep 3 x 3 accumulators in registers
-template <bool HAS_OLD>
-__global__ void __launch_bounds__(256) k_grad_pass3(fcm_geom g, fcm_c2f m, fcg_gauss3 k) {
+// u, v, w (and p) in one walk over the map (fcg_gaussn_row)
+template <int NF, bool HAS_OLD>
+__global__ void __launch_bounds__(256) k_grad_passn(fcm_geom g, fcm_c2f m, fcg_gaussn k) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < g.n) fcg_gauss3_row<HAS_OLD>(g, m, k, c);
+  if (c < g.n) fcg_gaussn_row<NF, HAS_OLD>(g, m, k, c);
 }
 
 // glomin / glomax = minval / maxval(phi(1:numCells)): min and max do not depend on the order, so a plain
@@ -113,37 +114,51 @@ int fc_grad_dev(fc_context *ctx, double *phi, double *grad, int nigrad) {
   return fc_limit_gradient_dev(ctx, phi, grad);
 }
 
-// grad(U), grad(V), grad(W) as calcuvw (:59-61) and calcp (:38-40) ask for them.  With FC_TUNE_FUSED_GRAD and plain Gauss
-// gradients the three fields share one kernel per pass; otherwise three calls of the dispatcher.
-int fc_grad_uvw_dev(fc_context *ctx, int nigrad) {
+// grad(U), grad(V), grad(W) as calcuvw (:59-61) and calcp (:38-40) ask for them, optionally followed by the first stage
+// of calcPressDiv (bpres(p,1); grad(p), fieldManipulation.f90:82-87) which does not depend on them.  With
+// FC_TUNE_FUSED_GRAD and plain Gauss gradients the fields share one kernel per pass; otherwise one dispatcher call each.
+int fc_grad_uvw_dev(fc_context *ctx, int nigrad, bool with_p_stage1) {
   double **fl = ctx->field;
-  double *phi[3] = {fl[FC_U], fl[FC_V], fl[FC_W]}, *grad[3] = {fl[FC_DUDXI], fl[FC_DVDXI], fl[FC_DWDXI]};
+  double *phi[FCG_MAXF] = {fl[FC_U], fl[FC_V], fl[FC_W], fl[FC_P]};
+  double *grad[FCG_MAXF] = {fl[FC_DUDXI], fl[FC_DVDXI], fl[FC_DWDXI], fl[FC_DPDXI]};
+  const int nf = with_p_stage1 ? 4 : 3;
   if (!ctx->tune_fused_grad || ctx->grad_method != 0 || ctx->grad_limiter != 0 || !ctx->has_mesh || !ctx->c2f_off) {
     for (int t = 0; t < 3; ++t) FC_CHECK(fc_grad_dev(ctx, phi[t], grad[t], nigrad));
+    if (with_p_stage1) {
+      FC_CHECK(fc_bpres_dev(ctx, phi[3], grad[3], 1));
+      FC_CHECK(fc_grad_dev(ctx, phi[3], grad[3], nigrad));
+    }
     return FC_OK;
   }
   if (nigrad < 1) FC_FAIL(FC_ERR_ARG, "fc_grad_gauss: nigrad < 1");
+  // bpres(p,1) only copies owner values into the boundary slots of p: it commutes with the velocity gradients
+  if (with_p_stage1) FC_CHECK(fc_bpres_dev(ctx, phi[3], grad[3], 1));
   const size_t g3 = 3 * (size_t)ctx->NP;
-  if (nigrad > 1 && !ctx->gtmp3) FC_CHECK(fc_dev_alloc(ctx, &ctx->gtmp3, 3 * g3));
+  if (nigrad > 1 && !ctx->gtmp3) FC_CHECK(fc_dev_alloc(ctx, &ctx->gtmp3, FCG_MAXF * g3));
   const int B = 256, G = fc_blocks(ctx->n, B);
   if (ctx->npro > 0)
-    for (int t = 0; t < 3; ++t) FC_CHECK(fc_halo_exchange(ctx, phi[t]));
-  fcg_gauss3 k{ctx->npro, ctx->fpro, {phi[0], phi[1], phi[2]}, {nullptr, nullptr, nullptr}, {grad[0], grad[1], grad[2]}};
+    for (int t = 0; t < nf; ++t) FC_CHECK(fc_halo_exchange(ctx, phi[t]));
+  fcg_gaussn k{};
+  k.npro = ctx->npro;
+  k.fpro = ctx->fpro;
+  for (int t = 0; t < nf; ++t) { k.phi[t] = phi[t]; k.old[t] = nullptr; k.out[t] = grad[t]; }
   for (int lc = 1; lc <= nigrad; ++lc) {
     if (lc == 1) {
-      k_grad_pass3<false><<<G, B, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), k);
+      if (nf == 4) k_grad_passn<4, false><<<G, B, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), k);
+      else k_grad_passn<3, false><<<G, B, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), k);
     } else {
-      for (int t = 0; t < 3; ++t) {
+      for (int t = 0; t < nf; ++t) {
         if (ctx->npro > 0) FC_CHECK(fc_halo_exchange3(ctx, grad[t]));
         FC_CUDA(cudaMemcpyAsync(ctx->gtmp3 + t * g3, grad[t], sizeof(double) * g3, cudaMemcpyDeviceToDevice, ctx->stream));
         k.old[t] = ctx->gtmp3 + t * g3;
       }
-      k_grad_pass3<true><<<G, B, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), k);
+      if (nf == 4) k_grad_passn<4, true><<<G, B, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), k);
+      else k_grad_passn<3, true><<<G, B, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), k);
     }
     FC_LAUNCH_CHECK();
   }
   if (ctx->npro > 0)
-    for (int t = 0; t < 3; ++t) FC_CHECK(fc_halo_exchange3(ctx, grad[t]));
+    for (int t = 0; t < nf; ++t) FC_CHECK(fc_halo_exchange3(ctx, grad[t]));
   return FC_OK;
 }
 

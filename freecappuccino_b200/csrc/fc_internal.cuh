@@ -278,6 +278,6 @@ int fc_calcuvw_component_dev(fc_context *ctx, const fc_calcuvw_opts *o, int comp
 int fc_calcuvw_dev(fc_context *ctx, const fc_calcuvw_opts *o, fc_calcuvw_report *rep);
 int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep);             // fc_assemble.cu
 int fc_grad_dev(fc_context *ctx, double *phi, double *grad, int nigrad);                   // fc_gradients.cu
-int fc_grad_uvw_dev(fc_context *ctx, int nigrad);                                              // fc_gradients.cu: grad(U), grad(V), grad(W)
+int fc_grad_uvw_dev(fc_context *ctx, int nigrad, bool with_p_stage1);                                              // fc_gradients.cu: grad(U), grad(V), grad(W)
 int fc_limit_gradient_dev(fc_context *ctx, const double *phi, double *grad);
 int fc_set_gradient_dev(fc_context *ctx, int method, int limiter, double small);

@@ -109,10 +109,10 @@ int fc_calcuvw_assemble_dev(fc_context *ctx, const fc_calcuvw_opts *o) {
   const int B = 256;
   cudaStream_t st = ctx->stream;
   FC_CUDA(cudaEventRecord(ctx->ev[2], st));
-  // grad(U), grad(V), grad(W)   (:59-61)
-  FC_CHECK(fc_grad_uvw_dev(ctx, o->nigrad));
-  // calcPressDiv: boundary pressure + pressure gradient (fieldManipulation.f90:82-87)
-  for (int istage = 1; istage <= o->nipgrad; ++istage) {
+  // grad(U), grad(V), grad(W) (:59-61) and the first stage of calcPressDiv
+  FC_CHECK(fc_grad_uvw_dev(ctx, o->nigrad, o->nipgrad >= 1));
+  // calcPressDiv, remaining stages: boundary pressure + pressure gradient (fieldManipulation.f90:82-87)
+  for (int istage = 2; istage <= o->nipgrad; ++istage) {
     FC_CHECK(fc_bpres_dev(ctx, ctx->field[FC_P], ctx->field[FC_DPDXI], istage));
     FC_CHECK(fc_grad_dev(ctx, ctx->field[FC_P], ctx->field[FC_DPDXI], o->nigrad));
   }

@@ -61,17 +61,19 @@ void fcg_host_limiter(const fcm_geom *g, const int *ioffset, const int *ja, cons
   for (int c = 0; c < g->n; ++c) fcg_limiter_row(*g, ioffset, ja, diag, which, phi, grad, glomin, glomax, small, c);
 }
 
-// u, v, w Gauss gradients in one walk (fcg_gauss3_row): nigrad passes, the later ones seeded with the previous result
-void fcg_host_gauss3(const fcm_geom *g, const fcm_c2f *m, int npro, const double *fpro, const double *u,
-                     const double *v, const double *w, double *dU, double *dV, double *dW, double *oU, double *oV,
-                     double *oW, int nigrad) {
-  fcg_gauss3 k{npro, fpro, {u, v, w}, {oU, oV, oW}, {dU, dV, dW}};
+// nf = 3 or 4 Gauss gradients in one walk (fcg_gaussn_row): nigrad passes, the later ones seeded with the previous result
+void fcg_host_gaussn(const fcm_geom *g, const fcm_c2f *m, int npro, const double *fpro, int nf, const double **phi,
+                     double **out, double **old, int nigrad) {
+  fcg_gaussn k{};
+  k.npro = npro; k.fpro = fpro;
+  for (int t = 0; t < nf; ++t) { k.phi[t] = phi[t]; k.old[t] = old[t]; k.out[t] = out[t]; }
   for (int lc = 1; lc <= nigrad; ++lc) {
-    if (lc == 1) {
-      for (int c = 0; c < g->n; ++c) fcg_gauss3_row<false>(*g, *m, k, c);
-    } else {
-      for (size_t i = 0; i < 3 * (size_t)g->n; ++i) { oU[i] = dU[i]; oV[i] = dV[i]; oW[i] = dW[i]; }
-      for (int c = 0; c < g->n; ++c) fcg_gauss3_row<true>(*g, *m, k, c);
+    if (lc > 1)
+      for (int t = 0; t < nf; ++t)
+        for (size_t i = 0; i < 3 * (size_t)g->n; ++i) old[t][i] = out[t][i];
+    for (int c = 0; c < g->n; ++c) {
+      if (nf == 3) { if (lc == 1) fcg_gaussn_row<3, false>(*g, *m, k, c); else fcg_gaussn_row<3, true>(*g, *m, k, c); }
+      else         { if (lc == 1) fcg_gaussn_row<4, false>(*g, *m, k, c); else fcg_gaussn_row<4, true>(*g, *m, k, c); }
     }
   }
 }

@@ -399,21 +399,29 @@ def test_limiter_bodies_equal_oracle(host, name, which):
     assert np.array_equal(got, ref[:n])
 
 
+def gaussn(host, G, Mp, npro, fpro, fields, n, nigrad):
+    nf = len(fields)
+    out = [np.zeros((n, 3)) for _ in range(nf)]
+    old = [np.zeros((n, 3)) for _ in range(nf)]
+    dpp = C.POINTER(C.c_double) * nf
+    host.fcg_host_gaussn(C.byref(G), C.byref(Mp), npro, d(fpro), nf, dpp(*[d(v) for v in fields]),
+                         dpp(*[d(v) for v in out]), dpp(*[d(v) for v in old]), nigrad)
+    return out
+
+
 @pytest.mark.parametrize("name", list(MESHES))
 @pytest.mark.parametrize("nigrad", [1, 2])
-def test_fused_gauss_gradient_body_equals_three_oracle_passes(host, name, nigrad):
-    """fcg_gauss3_row (FC_TUNE_FUSED_GRAD): u, v, w gradients in one walk over the cell-to-face map, each
+@pytest.mark.parametrize("keys", [("u", "v", "w"), ("u", "v", "w", "p")])
+def test_fused_gauss_gradient_body_equals_single_field_oracle_passes(host, name, nigrad, keys):
+    """fcg_gaussn_row (FC_TUNE_FUSED_GRAD): three or four gradients in one walk over the cell-to-face map, each
     bit-identical to grad_gauss of that field alone."""
     mesh = MESHES[name]()
     csr = oracle.create_csr(mesh)
     L, G, Mp, _keep = geom_and_map(mesh, csr)
     n = mesh.numCells
     f = cases.flow_fields(mesh)
-    out = [np.zeros((n, 3)) for _ in range(3)]
-    old = [np.zeros((n, 3)) for _ in range(3)]
-    host.fcg_host_gauss3(C.byref(G), C.byref(Mp), 0, d(np.zeros(1)), d(f["u"]), d(f["v"]), d(f["w"]),
-                         *[d(o) for o in out], *[d(o) for o in old], nigrad)
-    for got, k in zip(out, ("u", "v", "w")):
+    fields = [np.ascontiguousarray(f[k], dtype=np.float64) for k in keys]
+    for got, k in zip(gaussn(host, G, Mp, 0, np.zeros(1), fields, n, nigrad), keys):
         assert np.array_equal(got, oracle.grad_gauss(mesh, f[k], nigrad)[:n]), (name, k)
 
 
@@ -424,17 +432,14 @@ def test_fused_gauss_gradient_body_on_processor_faces(host, name, nranks):
     f = cases.flow_fields(mesh)
     parts = M.partition(mesh, M.rcb_ranks(mesh, nranks) if name == "poly" else M.slab_ranks(mesh.numCells, nranks), nranks)
     pc = OP.ParCase(parts)
-    phis = {k: [np.ascontiguousarray(M.scatter_total(mesh, p, f[k])) for p in parts] for k in ("u", "v", "w")}
-    ref = {k: pc.grad_gauss(phis[k], 1) for k in ("u", "v", "w")}     # exchanges the halo of phi first
+    keys = ("u", "v", "w", "p")
+    phis = {k: [np.ascontiguousarray(M.scatter_total(mesh, p, f[k])) for p in parts] for k in keys}
+    ref = {k: pc.grad_gauss(phis[k], 1) for k in keys}     # exchanges the halo of phi first
     for r, part in enumerate(parts):
         L, G, Mp, _keep = geom_and_map(part, pc.csr[r])
         n, npro = part.numCells, part.npro
         fpro = np.ascontiguousarray(part.fpro, dtype=np.float64) if npro else np.zeros(1)
-        out = [np.zeros((n, 3)) for _ in range(3)]
-        old = [np.zeros((n, 3)) for _ in range(3)]
-        host.fcg_host_gauss3(C.byref(G), C.byref(Mp), npro, d(fpro), d(phis["u"][r]), d(phis["v"][r]), d(phis["w"][r]),
-                             *[d(o) for o in out], *[d(o) for o in old], 1)
-        for got, k in zip(out, ("u", "v", "w")):
+        for got, k in zip(gaussn(host, G, Mp, npro, fpro, [phis[k][r] for k in keys], n, 1), keys):
             assert np.array_equal(got, np.asarray(ref[k][r]).reshape(-1, 3)[:n]), (name, r, k)
 
 
