@@ -78,6 +78,9 @@ MESHES = {
     "cavity": lambda: cases.golden_mesh(os.path.join(GOLD, "cavity.npz")),
     "pitzDaily": lambda: cases.golden_mesh(os.path.join(GOLD, "pitzDaily.npz")),
     "hex-rank-of-3": lambda: M.partition(cases.hex_case(16, 16, 24), M.slab_ranks(16 * 16 * 24, 3), 3)[1],
+    "poly-rank-of-4": lambda: (lambda g: M.partition(g, M.rcb_ranks(g, 4), 4)[2])(cases.poly_case(9)),
+    "pitzDaily-rank-of-2": lambda: (lambda g: M.partition(g, M.rcb_ranks(g, 2), 2)[1])(
+        cases.golden_mesh(os.path.join(GOLD, "pitzDaily.npz"))),
 }
 
 
