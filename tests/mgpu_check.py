@@ -39,11 +39,15 @@ def main():
     from oracle import oracle as O, oracle_par as OP
 
     failures = []
-    for mesh_name, g in (("hex_mixed", cases.hex_case(12, 9, 4 * world, kinds=("inlet", "outlet", "wall", "symmetry", "wall", "wall"))),
-                         ("skew", cases.skew_case(9, 8, 3 * world + 2)),
-                         # BASELINE config 5 at test size, cut by recursive coordinate bisection: several
-                         # connections per rank and cells with several processor faces
-                         ("poly", cases.poly_case(5))):
+    # MGPU_SECTIONS: "core" = the pressure-correction path (verified on hardware), "momentum" = the multi-rank momentum
+    # predictor (first hardware run pending); tests/test_gpu_multi.py and tests/test_gpu_zz1_multi_momentum.py run one each
+    sections = os.environ.get("MGPU_SECTIONS", "core,momentum").split(",")
+    core_cases = (("hex_mixed", cases.hex_case(12, 9, 4 * world, kinds=("inlet", "outlet", "wall", "symmetry", "wall", "wall"))),
+                  ("skew", cases.skew_case(9, 8, 3 * world + 2)),
+                  # BASELINE config 5 at test size, cut by recursive coordinate bisection: several
+                  # connections per rank and cells with several processor faces
+                  ("poly", cases.poly_case(5))) if "core" in sections else ()
+    for mesh_name, g in core_cases:
         f = cases.flow_fields(g)
         fmi, flomas = cases.inlet_fluxes(g, f)
         gp = O.grad_gauss(g, f["p"], 1)
@@ -119,7 +123,9 @@ def main():
                 print(f"[mgpu] {'p2p' if p2p else 'nccl'} {tag}: iters {box[0]['iters']} (oracle {[rep_o.rep[k].iters for k in range(npcor)]}) "
                       f"worst field rel L2 {worst:.2e}", flush=True)
     # ---- momentum predictor on several ranks (src-parallel/calcuvw.f90; fc_calcuvw with processor faces) ----
-    for mesh_name, g in (("skew", cases.skew_case(9, 8, 3 * world + 2)), ("poly", cases.poly_case(5))):
+    momentum_cases = (("skew", cases.skew_case(9, 8, 3 * world + 2)), ("poly", cases.poly_case(5))) \
+        if "momentum" in sections else ()
+    for mesh_name, g in momentum_cases:
         rng = np.random.default_rng(21)
         f = cases.channel_fields(g)
         nt = g.numTotal

@@ -1,4 +1,6 @@
-"""Launches the multi-GPU parity check (tests/mgpu_check.py) when the box has >= 2 GPUs."""
+"""The multi-rank momentum predictor section of tests/mgpu_check.py (src-parallel/calcuvw.f90 through fc_calcuvw with
+processor faces) when the box has >= 2 GPUs.  Its kernel bodies are checked on the CPU against the lock-step multi-rank
+oracle; this is the first run on hardware, so it sorts after the suites that have run."""
 import os
 import subprocess
 import sys
@@ -10,19 +12,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("mode", ["p2p", "nccl"])
-def test_two_rank_parity(mode):
+def test_two_rank_momentum_predictor(mode):
     """2 ranks, halo + reductions over direct NVLink stores (p2p) or NCCL collectives (nccl)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29517" if mode == "p2p" else "29518", os.path.join(ROOT, "tests", "mgpu_check.py")]
-    env = dict(os.environ, FC_NO_P2P="0" if mode == "p2p" else "1", MGPU_SECTIONS="core")
+           "127.0.0.1", "--master-port", "29527" if mode == "p2p" else "29528", os.path.join(ROOT, "tests", "mgpu_check.py")]
+    env = dict(os.environ, FC_NO_P2P="0" if mode == "p2p" else "1", MGPU_SECTIONS="momentum")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     lines = [l for l in out.stdout.splitlines() if l.startswith("[mgpu]")]
     try:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"mgpu_pytest_{mode}.log"), "w") as fh:
+        with open(os.path.join(ROOT, "gpurun_out", f"mgpu_momentum_pytest_{mode}.log"), "w") as fh:
             fh.write(out.stdout + "\n--- stderr ---\n" + out.stderr)
     except OSError:
         pass
