@@ -129,8 +129,7 @@ inline void tri_range(const int *ioffset, const int *diag, int i, bool lower, in
 }
 
 inline bool build_dir(int n, const int *ioffset, const int *ja, const int *diag, const std::vector<int> &tile,
-                      const std::vector<int> &tile_start, const std::vector<int> &pos, int ntiles, bool lower,
-                      fc_tile_dir &D, std::string &why) {
+                      const std::vector<int> &pos, int ntiles, bool lower, fc_tile_dir &D, std::string &why) {
   // tile-to-tile edges producer -> consumer
   std::vector<uint64_t> edges;
   for (int i = 0; i < n; ++i) {
@@ -221,7 +220,6 @@ inline bool build_dir(int n, const int *ioffset, const int *ja, const int *diag,
     D.blk_nlev[b] = std::max(D.blk_nlev[b], ll[i] + 1);
     D.max_local_levels = std::max(D.max_local_levels, ll[i] + 1);
   }
-  (void)tile_start;
   D.prod.assign((size_t)ntiles * FC_TILE_MAXP, -1);
   D.prod_cnt.assign(ntiles, 0);
   D.p2p_ok = true;
@@ -371,8 +369,7 @@ inline fc_tile_schedule fc_build_tile_schedule(int n, const int *ioffset, const 
   }
   S.ntiles = ntiles;
   // slot of a row inside its tile: ascending row id (the same for both directions, so one tja serves both)
-  std::vector<int> tile_start(ntiles + 1, 0), pos(n);
-  for (int t = 0; t < ntiles; ++t) tile_start[t + 1] = tile_start[t] + count[t];
+  std::vector<int> pos(n);
   {
     std::vector<int> fill(ntiles, 0);
     for (int i = 0; i < n; ++i) pos[i] = fill[tile[i]]++;
@@ -386,8 +383,8 @@ inline fc_tile_schedule fc_build_tile_schedule(int n, const int *ioffset, const 
       S.tja[k] = (j != i && j < n && tile[j] == tile[i]) ? -(pos[j] + 1) : j;
     }
   }
-  if (!build_dir(n, ioffset, ja, diag, tile, tile_start, pos, ntiles, true, S.lower, S.why)) return S;
-  if (!build_dir(n, ioffset, ja, diag, tile, tile_start, pos, ntiles, false, S.upper, S.why)) return S;
+  if (!build_dir(n, ioffset, ja, diag, tile, pos, ntiles, true, S.lower, S.why)) return S;
+  if (!build_dir(n, ioffset, ja, diag, tile, pos, ntiles, false, S.upper, S.why)) return S;
   S.cost = std::max(fc_tile_detail::dir_cost(S.lower), fc_tile_detail::dir_cost(S.upper));
   S.ok = true;
   return S;
