@@ -73,9 +73,15 @@ int fco_create_csr(int numCells, int numInnerFaces, const int *owner, const int 
   return 0;
 }
 
+/* Host threads INSIDE one rank's row loops (bench.py's reference arm and its full-size parity solve).  Only loops
+ * whose iterations are independent (one row / one cell each) are split, so every result is bit-identical to the
+ * one-thread run; the inner products stay sequential left-to-right sums. */
+static int fco_inner = 1;
+#define ROWS_MT _Pragma("omp parallel for schedule(static) num_threads(fco_inner) if (fco_inner > 1)")
+
 /* y = A x, row loop of src/dpcg.f90:105-110 */
 void fco_spmv(const fco_csr *m, const double *a, const double *x, double *y) {
-  for (int i = 1; i <= m->n; ++i) {
+  ROWS_MT for (int i = 1; i <= m->n; ++i) {
     double s = 0.0;
     for (int k = A1(m->ioffset, i); k <= A1(m->ioffset, i + 1) - 1; ++k)
       s = s + A1(a, k) * A1(x, A1(m->ja, k));
@@ -93,7 +99,7 @@ static const fco_strips no_strips = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 static double initial_residual(const fco_csr *m, const double *a, const double *su, const double *fi,
                                double *res, const fco_strips *s) {
   const int n = m->n;
-  for (int i = 1; i <= n; ++i) {
+  ROWS_MT for (int i = 1; i <= n; ++i) {
     double r = A1(su, i);
     for (int k = A1(m->ioffset, i); k <= A1(m->ioffset, i + 1) - 1; ++k)
       r = r - A1(a, k) * A1(fi, A1(m->ja, k));
@@ -162,21 +168,22 @@ int fco_dpcg(const fco_csr *m, const double *a, const double *su, double *fi, do
   double s0 = (double)1.e20f;
   int used = 0;
   for (int l = 1; l <= o->nsw; ++l) {
-    if (o->parallel)
-      for (int i = 1; i <= n; ++i) A1(zk, i) = A1(res, i) / (A1(a, A1(m->diag, i)) + o->small);
-    else
-      for (int i = 1; i <= n; ++i) A1(zk, i) = A1(res, i) / A1(a, A1(m->diag, i));
+    if (o->parallel) {
+      ROWS_MT for (int i = 1; i <= n; ++i) A1(zk, i) = A1(res, i) / (A1(a, A1(m->diag, i)) + o->small);
+    } else {
+      ROWS_MT for (int i = 1; i <= n; ++i) A1(zk, i) = A1(res, i) / A1(a, A1(m->diag, i));
+    }
     double sk = 0.0;
     for (int i = 1; i <= n; ++i) sk = sk + A1(res, i) * A1(zk, i);
     double bet = sk / s0;
-    for (int i = 1; i <= n; ++i) A1(pk, i) = A1(zk, i) + bet * A1(pk, i);
+    ROWS_MT for (int i = 1; i <= n; ++i) A1(pk, i) = A1(zk, i) + bet * A1(pk, i);
     /* single-rank "exchange": a lone rank has npro = 0; multi-rank runs go through fco_par_* */
     matvec(m, a, pk, zk, s, 1);
     double pkapk = 0.0;
     for (int i = 1; i <= n; ++i) pkapk = pkapk + A1(pk, i) * A1(zk, i);
     double alf = sk / pkapk;
-    for (int i = 1; i <= n; ++i) A1(fi, i) = A1(fi, i) + alf * A1(pk, i);
-    for (int i = 1; i <= n; ++i) A1(res, i) = A1(res, i) - alf * A1(zk, i);
+    ROWS_MT for (int i = 1; i <= n; ++i) A1(fi, i) = A1(fi, i) + alf * A1(pk, i);
+    ROWS_MT for (int i = 1; i <= n; ++i) A1(res, i) = A1(res, i) - alf * A1(zk, i);
     resl = 0.0;
     for (int i = 1; i <= n; ++i) resl = resl + fabs(A1(res, i));
     s0 = sk;

@@ -7,6 +7,9 @@
  * checker for the multi-GPU (NCCL) path and is compiled as one translation unit with the
  * serial oracle so that both share the same face-flux / gradient helpers.
  */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "fc_oracle.c"
 
 /* The ranks of one lock-step phase are independent (they only read halo values copied in an earlier
@@ -15,6 +18,14 @@
  * single-thread run.  Used by bench.py's reference arm; the tests run it with one thread. */
 static int fco_threads = 1;
 void fco_par_set_threads(int n) { fco_threads = n > 1 ? n : 1; }
+/* `outer` threads over the ranks x `inner` threads inside each rank's row loops (fc_oracle.c, ROWS_MT) */
+void fco_par_set_threads2(int outer, int inner) {
+  fco_threads = outer > 1 ? outer : 1;
+  fco_inner = inner > 1 ? inner : 1;
+#ifdef _OPENMP
+  omp_set_max_active_levels(fco_threads > 1 && fco_inner > 1 ? 2 : 1);
+#endif
+}
 int fco_par_openmp(void) {
 #ifdef _OPENMP
   return 1;
@@ -204,8 +215,9 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
           const fco_csr *m = &R[r].m;
           const int n = m->n;
           double *res = R[r].f.res, *zk = S[r].zk;
-          if (solver == 0)
-            for (int i = 1; i <= n; ++i) A1(zk, i) = A1(res, i) / (A1(R[r].f.a, A1(m->diag, i)) + o->small);
+          if (solver == 0) {
+            ROWS_MT for (int i = 1; i <= n; ++i) A1(zk, i) = A1(res, i) / (A1(R[r].f.a, A1(m->diag, i)) + o->small);
+          }
           else
             precond_sweeps(m, R[r].f.a, S[r].d, res, zk, o->small);
           double sk = 0.0;
@@ -216,7 +228,7 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
         const double bet = sk / s0;
         PAR_RANKS for (int r = 0; r < nr; ++r) {
           const int n = R[r].m.n;
-          for (int i = 1; i <= n; ++i) A1(S[r].pk, i) = A1(S[r].zk, i) + bet * A1(S[r].pk, i);
+          ROWS_MT for (int i = 1; i <= n; ++i) A1(S[r].pk, i) = A1(S[r].zk, i) + bet * A1(S[r].pk, i);
           vec[r] = S[r].pk;
         }
         fco_par_exchange(R, nr, vec, 1);
@@ -232,8 +244,8 @@ int fco_par_solve(fco_rank *R, int nr, int solver, double **fi, const fco_solver
         PAR_RANKS for (int r = 0; r < nr; ++r) {
           const int n = R[r].m.n;
           double *res = R[r].f.res;
-          for (int i = 1; i <= n; ++i) A1(fi[r], i) = A1(fi[r], i) + alf * A1(S[r].pk, i);
-          for (int i = 1; i <= n; ++i) A1(res, i) = A1(res, i) - alf * A1(S[r].zk, i);
+          ROWS_MT for (int i = 1; i <= n; ++i) A1(fi[r], i) = A1(fi[r], i) + alf * A1(S[r].pk, i);
+          ROWS_MT for (int i = 1; i <= n; ++i) A1(res, i) = A1(res, i) - alf * A1(S[r].zk, i);
           double rl = 0.0;
           for (int i = 1; i <= n; ++i) rl = rl + fabs(A1(res, i));
           part[r] = rl;

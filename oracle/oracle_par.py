@@ -22,6 +22,16 @@ def set_threads(n: int) -> int:
     return max(1, int(n))
 
 
+def set_threads2(outer: int, inner: int):
+    """`outer` host threads over the ranks x `inner` threads inside every rank's row loops (SpMV, AXPY; the inner
+    products stay sequential, so all results are bit-identical to the one-thread run).  Returns (outer, inner) in
+    effect."""
+    if not O.lib().fco_par_openmp():
+        return 1, 1
+    O.lib().fco_par_set_threads2(int(outer), int(inner))
+    return max(1, int(outer)), max(1, int(inner))
+
+
 class FcoRank(C.Structure):
     _fields_ = [("g", O.FcoMesh), ("m", O.FcoCsr), ("f", O.FcoFields), ("apr", O.dp), ("fmpro", O.dp),
                 ("numConnections", C.c_int), ("neighbProcNo", O.ip), ("neighbProcOffset", O.ip)]
