@@ -107,7 +107,7 @@ void free_all(fc_context *ctx) {
                   (void *)ctx->gtmp, (void *)ctx->partials, (void *)ctx->sc, (void *)ctx->bufind,
                   (void *)ctx->sendbuf, (void *)ctx->strip_off, (void *)ctx->strip_idx,
                   (void *)ctx->strip_any32, (void *)ctx->persist, (void *)ctx->uvw_face, (void *)ctx->hcoef, (void *)ctx->dmat, (void *)ctx->tja, (void *)ctx->gtmp3, (void *)ctx->sweep_chk,
-                  (void *)ctx->dmatqr})
+                  (void *)ctx->dmatqr, (void *)ctx->hist})
     if (p) cudaFree(p);
   for (int f = 0; f < FC_NUM_FIELDS; ++f)
     if (ctx->field[f]) cudaFree(ctx->field[f]);
@@ -162,6 +162,8 @@ int fc_create(int device, fc_context **out) {
   };
   auto init = [&]() -> int {
     FC_CUDA(cudaSetDevice(device));
+    FC_CUDA(cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device));
+    if (ctx->sms < 1) ctx->sms = FC_SMS;
     FC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto &ev : ctx->ev) FC_CUDA(cudaEventCreate(&ev));
     FC_CHECK(fc_dev_alloc(ctx, &ctx->sc, 1));
@@ -276,6 +278,16 @@ int fc_set_mesh(fc_context *ctx, const fc_mesh_desc *m) {
   if (m->npro > 0) {
     for (int c = 0; c < m->numConnections; ++c) ctx->nbr_rank.push_back(m->neighbProcNo[c]);
     for (int c = 0; c <= m->numConnections; ++c) ctx->nbr_off.push_back(m->neighbProcOffset[c] - 1);
+    // the pack kernels and the send / receive lengths index with this table unchecked
+    if (ctx->nbr_off.front() != 0) FC_FAIL(FC_ERR_ARG, "fc_set_mesh: neighbProcOffset(1) must be 1");
+    for (int c = 0; c < m->numConnections; ++c) {
+      if (ctx->nbr_off[c + 1] < ctx->nbr_off[c])
+        FC_FAIL(FC_ERR_ARG, "fc_set_mesh: neighbProcOffset decreases at connection " + std::to_string(c + 1));
+      if (ctx->nbr_rank[c] < 0) FC_FAIL(FC_ERR_ARG, "fc_set_mesh: negative neighbProcNo");
+      if (ctx->nranks > 1 && (ctx->nbr_rank[c] >= ctx->nranks || ctx->nbr_rank[c] == ctx->rank))
+        FC_FAIL(FC_ERR_ARG, "fc_set_mesh: neighbProcNo(" + std::to_string(c + 1) + ") = " + std::to_string(ctx->nbr_rank[c]) +
+                                " is not another rank of the communicator");
+    }
     if (ctx->nbr_off.back() != m->npro) FC_FAIL(FC_ERR_ARG, "fc_set_mesh: neighbProcOffset does not cover npro");
     // bufind(i) = owner(iProcFacesStart + i)   (src-parallel/mesh_geometry_and_topology.f90:879-881)
     FC_CHECK(fc_dev_alloc(ctx, &ctx->bufind, (size_t)m->npro));

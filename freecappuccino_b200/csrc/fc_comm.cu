@@ -118,6 +118,12 @@ extern "C" int fc_comm_init(fc_context *ctx, int rank, int nranks, const char id
   if (nranks < 1 || rank < 0 || rank >= nranks) FC_FAIL(FC_ERR_ARG, "fc_comm_init: bad rank / nranks");
   FC_CUDA(cudaSetDevice(ctx->device));
   fc_comm_destroy(ctx);
+  // a mesh set before the communicator: its neighbour table is checked here (a self or out-of-range peer would
+  // hang the first ncclSend / ncclRecv pair)
+  for (size_t c = 0; c < ctx->nbr_rank.size(); ++c)
+    if (nranks > 1 && (ctx->nbr_rank[c] < 0 || ctx->nbr_rank[c] >= nranks || ctx->nbr_rank[c] == rank))
+      FC_FAIL(FC_ERR_ARG, "fc_comm_init: neighbProcNo(" + std::to_string(c + 1) + ") = " + std::to_string(ctx->nbr_rank[c]) +
+                              " of the mesh is not another rank of the communicator");
   ctx->rank = rank;
   ctx->nranks = nranks;
   if (nranks == 1) return FC_OK;

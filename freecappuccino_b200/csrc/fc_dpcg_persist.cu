@@ -172,6 +172,7 @@ __device__ __forceinline__ void grid_reduce(const persist_args &A, sync_ctx &S, 
       for (int r = 0; r < NR; ++r) sc->red[r] = v[r];
       fc_scalar_step(sc, step, A.hist);
       if (step == STEP_RES0_SK && A.tol >= 0.0 && sc->res0 < A.tol) sc->done = 1;   // dpcg.f90:66-70
+      if (step == STEP_RES0_SK && sc->nsw <= 0) sc->done = 1;   // `do l=1,ns` with ns = 0: no iteration, fi untouched
       release_barrier(A.ps, S.my_gen, phase, s_tarr);
     }
   } else if (threadIdx.x == 0) {
@@ -369,17 +370,21 @@ template <int T, int CAP, int S, bool STRIP>
 int launch_persist(fc_context *ctx, persist_args &A, bool *ok) {
   auto kern = k_dpcg_persist<T, CAP, S, STRIP>;
   const size_t smem = sizeof(fc_spmv_smem<T, CAP, S>);
-  static int per_sm = -1;
-  if (per_sm < 0) {
+  // per instantiation and per device (the shared-memory opt-in is a per-device function attribute)
+  static int per_sm_dev[FC_MAX_DEVICES];
+  static bool per_sm_set[FC_MAX_DEVICES];
+  const int dev = ctx->device >= 0 && ctx->device < FC_MAX_DEVICES ? ctx->device : 0;
+  if (!per_sm_set[dev] || dev != ctx->device) {
+    int v = 0;
     FC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
-    if (per_sm < 1) per_sm = 0;
+    FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, T, smem));
+    per_sm_dev[dev] = v < 1 ? 0 : v;
+    per_sm_set[dev] = true;
   }
-  int use = per_sm;
+  int use = per_sm_dev[dev];
   if (ctx->tune_ctas_per_sm > 0 && ctx->tune_ctas_per_sm < use) use = ctx->tune_ctas_per_sm;
   if (use == 0) { *ok = false; return FC_OK; }
-  int sms = FC_SMS;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int sms = ctx->sms;
   const long long groups = ((long long)A.M.n + 31) / 32;
   long long grid = (long long)sms * use;
   if (grid > groups) grid = groups;

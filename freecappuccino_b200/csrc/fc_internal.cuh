@@ -13,6 +13,7 @@
 
 // Number of SMs the persistent / grid-stride kernels are sized for (B200).
 constexpr int FC_SMS = 148;
+constexpr int FC_MAX_DEVICES = 64;               // per-device caches of kernel attributes (one process may hold several contexts)
 constexpr int FC_RED_BLOCK = 512;               // threads of the streaming vector kernels
 constexpr int FC_RED_GRID = FC_SMS * 4;         // 4 resident CTAs of 512 threads per SM
 constexpr int FC_MAX_RED = 4;                   // scalars reduced by one kernel
@@ -98,6 +99,9 @@ constexpr int FC_TRI_MAXP = 16;
 
 struct fc_context {
   int device = 0;
+  int sms = FC_SMS;                     // SM count of `device` (queried in fc_create)
+  double *hist = nullptr;               // residual history of a solve (fc_solve_csr's `hist`), grown on demand
+  size_t hist_cap = 0;
   cudaStream_t stream = nullptr;
   std::string err;
   long long launches = 0;
@@ -182,11 +186,11 @@ struct fc_context {
   int tune_ctas_per_sm = 0;             // persistent kernel: CTAs per SM (0 = as many as fit)
   int tune_sweep_p2p = 0;               // triangular sweeps: 1 = point-to-point block flags instead of level counters
   int first_batch[3] = {8, 8, 8};       // per solver: iterations enqueued before the first look at `done`
-  int tune_fused_grad = 0;              // 1: the three velocity gradients of calcuvw / calcp in one kernel per pass
+  int tune_fused_grad = 1;              // 1: the three velocity gradients of calcuvw / calcp in one kernel per pass
   int tune_sweep_check = 0;             // debugging: every tiled sweep is repeated with the level schedule and compared
   double *sweep_chk = nullptr;          // [n + 2] scratch of that comparison (+ two counters)
   int tune_tile_ctas = 2;               // tiled sweeps: CTAs per SM the kernel is compiled for (2 or 3)
-  int tune_sweep_tiled = 0;             // triangular sweeps: 1 = two-level tiled schedule where the mesh allows it
+  int tune_sweep_tiled = 2;             // triangular sweeps: 1 = two-level tiled schedule where the mesh allows it
   fc_persist_state *persist = nullptr;  // device: grid barrier + phase clocks of the persistent kernel
   fc_persist_state *persist_host = nullptr;
 

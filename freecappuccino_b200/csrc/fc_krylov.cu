@@ -242,8 +242,19 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
   double *pk = ctx->pk, *zk = ctx->zk, *d = ctx->dd;
   const double padd = o->parallel ? o->small : 0.0;
   cudaStream_t st = ctx->stream;
+  // residual history: a context-owned buffer (grown on demand, freed with the context), so that no early return
+  // of this function can leak it
   double *hist = nullptr;
-  if (hist_host && o->nsw > 0) FC_CUDA(cudaMalloc((void **)&hist, sizeof(double) * (size_t)o->nsw));
+  if (hist_host && o->nsw > 0) {
+    if (ctx->hist_cap < (size_t)o->nsw) {
+      cudaFree(ctx->hist);
+      ctx->hist = nullptr;
+      ctx->hist_cap = 0;
+      FC_CHECK(fc_dev_alloc(ctx, &ctx->hist, (size_t)o->nsw));
+      ctx->hist_cap = (size_t)o->nsw;
+    }
+    hist = ctx->hist;
+  }
 
   ctx->spmv_sampled = 0;
   FC_CUDA(cudaEventRecord(ctx->ev[0], st));
@@ -263,11 +274,8 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
       if (ctx->npro > 0 && !(o->tol >= 0.0 && rep->res0 < o->tol))
         FC_CHECK(fc_halo_exchange(ctx, fi));  // src-parallel/dpcg.f90:173
       FC_CUDA(cudaStreamSynchronize(st));
-      if (hist) {
-        if (rep->iters > 0)
-          FC_CUDA(cudaMemcpy(hist_host, hist, sizeof(double) * (size_t)rep->iters, cudaMemcpyDeviceToHost));
-        cudaFree(hist);
-      }
+      if (hist && rep->iters > 0)
+        FC_CUDA(cudaMemcpy(hist_host, hist, sizeof(double) * (size_t)rep->iters, cudaMemcpyDeviceToHost));
       float ms = 0.f;
       FC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
       ctx->tm.solve_ms = ms;
@@ -283,7 +291,12 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
   rep->resl = ctx->sc_host->res0;
   rep->iters = 0;
   if (o->tol >= 0.0 && rep->res0 < o->tol) {  // dpcg.f90:66-70
-    if (hist) cudaFree(hist);
+    FC_CUDA(cudaEventRecord(ctx->ev[1], st));
+    FC_CUDA(cudaEventSynchronize(ctx->ev[1]));
+    float ms0 = 0.f;
+    FC_CUDA(cudaEventElapsedTime(&ms0, ctx->ev[0], ctx->ev[1]));
+    ctx->tm.solve_ms = ms0;
+    ctx->tm.spmv_samples = 0;
     return FC_OK;
   }
   FC_CUDA(cudaMemsetAsync(pk, 0, sizeof(double) * ((size_t)n + ctx->npro), st));
@@ -366,11 +379,8 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
   rep->resl = ctx->sc_host->resl;
   rep->iters = ctx->sc_host->iters;
   ctx->first_batch[solver] = rep->iters + 1 < 2 ? 2 : (rep->iters + 1 > 8 ? 8 : rep->iters + 1);
-  if (hist) {
-    if (rep->iters > 0)
-      FC_CUDA(cudaMemcpy(hist_host, hist, sizeof(double) * (size_t)rep->iters, cudaMemcpyDeviceToHost));
-    cudaFree(hist);
-  }
+  if (hist && rep->iters > 0)
+    FC_CUDA(cudaMemcpy(hist_host, hist, sizeof(double) * (size_t)rep->iters, cudaMemcpyDeviceToHost));
   float ms = 0.f;
   FC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   ctx->tm.solve_ms = ms;

@@ -124,15 +124,22 @@ int launch_tma(fc_context *ctx, const fc_spmv_mat &M, const fc_spmv_vec &V, cons
                const fc_sync &sy, bool *ok) {
   auto kern = k_spmv_tma<T, CAP, S, MODE, STRIP>;
   const size_t smem = sizeof(fc_spmv_smem<T, CAP, S>);
-  static int per_sm = -1;   // per instantiation
-  if (per_sm < 0) {
+  // per instantiation AND per device: the opt-in above 48 KB of dynamic shared memory is a per-device function
+  // attribute, so a second context on another GPU of the same process has to set it again
+  static int per_sm_dev[FC_MAX_DEVICES];
+  static bool per_sm_set[FC_MAX_DEVICES];
+  const int dev = ctx->device >= 0 && ctx->device < FC_MAX_DEVICES ? ctx->device : 0;
+  if (!per_sm_set[dev] || dev != ctx->device) {
+    int v = 0;
     FC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
-    if (per_sm < 1) per_sm = 0;
+    FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, T, smem));
+    per_sm_dev[dev] = v < 1 ? 0 : v;
+    per_sm_set[dev] = true;
   }
+  const int per_sm = per_sm_dev[dev];
   if (per_sm == 0) { *ok = false; return FC_OK; }
   const long long groups = ((long long)M.n + 31) / 32;
-  long long grid = (long long)FC_SMS * per_sm;
+  long long grid = (long long)ctx->sms * per_sm;
   if (grid > groups) grid = groups;
   if (grid < 1) grid = 1;
   // the chunk boundaries of a CTA must fit its shared-memory table (an unweighted share is the largest)
@@ -182,10 +189,10 @@ int launch(fc_context *ctx, const double *a, const double *x, double *y, const d
     if (ok) return FC_OK;
   }
   const int nchunks = (n + 255) / 256;
-  int grid = nchunks < FC_SMS * 8 ? nchunks : FC_SMS * 8;
+  int grid = nchunks < ctx->sms * 8 ? nchunks : ctx->sms * 8;
   if (grid < 1) grid = 1;
   const bool small_rows = ctx->spmv_max_chunk <= 2304;
-  if (!small_rows && grid > FC_SMS * 4) grid = FC_SMS * 4;
+  if (!small_rows && grid > ctx->sms * 4) grid = ctx->sms * 4;
 #define FC_SPMV_LAUNCH(CAP, STRIP)                                                                              \
   k_spmv<256, CAP, MODE, STRIP><<<grid, 256, 0, ctx->stream>>>(n, ctx->ioffset, ctx->ja, a, x, y, su, w, ctx->diag, \
                                                                adiag, st, ctx->partials, ctx->sc, step, sy)

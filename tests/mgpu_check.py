@@ -63,8 +63,11 @@ def main():
             # (each rank evaluates fluxmc of a shared face from its own side and the formula is not
             # antisymmetric: sum(su) != 0), so its CG solve diverges in the reference algorithm itself.
             # The corrector path is therefore compared with both solves capped at 6 iterations.
-            kw = dict(solver=solver, flomas=flomas, npcor=npcor, lsq_flag=lsq, nigrad=nigrad, sor=1e-7,
-                      nsw=6 if npcor > 1 else 400,
+            # Tight solves (rsm < 1e-12; BiCGStab stagnates in round-off below ~1e-11) so that the fields can be held
+            # to the north star's 1e-10 relative L2: GPU and oracle differ only in the order of the inner-product sums.
+            kw = dict(solver=solver, flomas=flomas, npcor=npcor, lsq_flag=lsq, nigrad=nigrad,
+                      sor=float(os.environ.get("MGPU_SOR", "1e-11" if solver == "bicgstab" else "1e-12")),
+                      nsw=6 if npcor > 1 else 2000,
                       flux_variant=1 if mesh_name == "poly" else 0)   # see test_config5_polyhedral_path
             ctx = lib.Context(local)
             parallel.init_comm(ctx)
@@ -110,7 +113,7 @@ def main():
                         ref = getattr(pc.fields[r], k)
                         e = cases.rel_l2(box[r][k][:ref.size], ref)
                         worst = max(worst, e)
-                        if e > 1e-5:   # solves stop at rsm < 1e-7
+                        if e > 1e-10:   # north star: final fields within 1e-10 relative L2
                             failures.append(f"{tag}: rank {r} field {k} rel L2 {e:.2e}")
                     if npcor == 1:   # the matrix is bit-exact (for npcor > 1 it is unchanged too, su differs)
                         if not np.array_equal(box[r]["a"], pc.fields[r].a):
@@ -156,7 +159,7 @@ def main():
 
         part = parts[rank]
         st = rank_state(part)
-        kw = dict(scheme="muscl-f", urf=(0.7, 0.8, 0.6), sor=(1e-9,) * 3, nsw=(300,) * 3, bdf=True, btime=1.0, timestep=0.05)
+        kw = dict(scheme="muscl-f", urf=(0.7, 0.8, 0.6), sor=(1e-12,) * 3, nsw=(300,) * 3, bdf=True, btime=1.0, timestep=0.05)
         ctx = lib.Context(local)
         parallel.init_comm(ctx)
         ctx.set_mesh(part)
@@ -213,7 +216,7 @@ def main():
                     nn = m.numCells + m.npro     # the halo is current after the final exchanges
                     e = cases.rel_l2(box[r][k][:nn], ref[:nn])
                     worst = max(worst, e)
-                    if e > 1e-6:
+                    if e > 1e-10:
                         failures.append(f"{tag}: rank {r} field {k} rel L2 {e:.2e}")
             print(f"[mgpu] {'p2p' if p2p else 'nccl'} {tag}: iters {box[0]['iters']} (oracle "
                   f"{[rep_o.rep[k].iters for k in range(3)]}) worst field rel L2 {worst:.2e}", flush=True)
