@@ -42,6 +42,7 @@ struct persist_args {
   fc_p2p_dev *p2p;
   unsigned long long red_seq0, halo_seq0;
   double *hist;
+  int l2keep;   // the Krylov vectors fit the L2: mark them evict_last (the matrix stream is evict_first)
 };
 
 enum { PH_PUPDATE = 0, PH_SPMV = 1, PH_UPDATE = 2, PH_SETUP = 3 };
@@ -202,6 +203,9 @@ k_dpcg_persist(persist_args A) {
   int rbeg, rend;
   fc_row_range(n, STRIP ? A.st.off : nullptr, &rbeg, &rend);
   pipe.init(sm, A.M.ioffset, rbeg, rend, STRIP ? A.st.off : nullptr);
+  // L2 policy of the vector traffic (pk, zk, res, adiag): evict_last when they fit the L2 next to the matrix stream
+  const unsigned long long vpol = A.l2keep ? fc_policy_evict_last() : fc_policy_evict_normal();
+  pipe.pol_y = vpol;
   pipe.prefetch(A.M);
   const bool p2p = STRIP && A.p2p != nullptr;
   if (p2p) {
@@ -236,35 +240,40 @@ k_dpcg_persist(persist_args A) {
       first = false;
       int i = rbeg + tid, j = 0;
       for (; i + 3 * T < rend; i += 4 * T) {
-        const double r0 = A.res[i], r1 = A.res[i + T], r2 = A.res[i + 2 * T], r3 = A.res[i + 3 * T];
-        const double d0 = A.adiag[i], d1 = A.adiag[i + T], d2 = A.adiag[i + 2 * T], d3 = A.adiag[i + 3 * T];
-        const double p0 = A.pk[i], p1 = A.pk[i + T], p2 = A.pk[i + 2 * T], p3 = A.pk[i + 3 * T];
+        const double r0 = fc_ld_pol(A.res + i, vpol), r1 = fc_ld_pol(A.res + i + T, vpol),
+                     r2 = fc_ld_pol(A.res + i + 2 * T, vpol), r3 = fc_ld_pol(A.res + i + 3 * T, vpol);
+        const double d0 = fc_ld_pol(A.adiag + i, vpol), d1 = fc_ld_pol(A.adiag + i + T, vpol),
+                     d2 = fc_ld_pol(A.adiag + i + 2 * T, vpol), d3 = fc_ld_pol(A.adiag + i + 3 * T, vpol);
+        const double p0 = fc_ld_pol(A.pk + i, vpol), p1 = fc_ld_pol(A.pk + i + T, vpol),
+                     p2 = fc_ld_pol(A.pk + i + 2 * T, vpol), p3 = fc_ld_pol(A.pk + i + 3 * T, vpol);
         const double f0 = A.fi[i], f1 = A.fi[i + T], f2 = A.fi[i + 2 * T], f3 = A.fi[i + 3 * T];
         A.fi[i] = f0 + alfp * p0;
         A.fi[i + T] = f1 + alfp * p1;
         A.fi[i + 2 * T] = f2 + alfp * p2;
         A.fi[i + 3 * T] = f3 + alfp * p3;
-        A.pk[i] = r0 / (d0 + A.padd) + bet * p0;
-        A.pk[i + T] = r1 / (d1 + A.padd) + bet * p1;
-        A.pk[i + 2 * T] = r2 / (d2 + A.padd) + bet * p2;
-        A.pk[i + 3 * T] = r3 / (d3 + A.padd) + bet * p3;
+        fc_st_pol(A.pk + i, r0 / (d0 + A.padd) + bet * p0, vpol);
+        fc_st_pol(A.pk + i + T, r1 / (d1 + A.padd) + bet * p1, vpol);
+        fc_st_pol(A.pk + i + 2 * T, r2 / (d2 + A.padd) + bet * p2, vpol);
+        fc_st_pol(A.pk + i + 3 * T, r3 / (d3 + A.padd) + bet * p3, vpol);
       }
       if (i < rend) {   // up to three rows left: one predicated batch instead of three dependent round trips
         const bool b1 = i + T < rend, b2 = i + 2 * T < rend;
-        const double r0 = A.res[i], d0 = A.adiag[i], p0 = A.pk[i], f0 = A.fi[i];
-        const double r1 = b1 ? A.res[i + T] : 0.0, d1 = b1 ? A.adiag[i + T] : 1.0, p1 = b1 ? A.pk[i + T] : 0.0;
+        const double r0 = fc_ld_pol(A.res + i, vpol), d0 = fc_ld_pol(A.adiag + i, vpol), p0 = fc_ld_pol(A.pk + i, vpol),
+                     f0 = A.fi[i];
+        const double r1 = b1 ? fc_ld_pol(A.res + i + T, vpol) : 0.0, d1 = b1 ? fc_ld_pol(A.adiag + i + T, vpol) : 1.0,
+                     p1 = b1 ? fc_ld_pol(A.pk + i + T, vpol) : 0.0;
         const double f1 = b1 ? A.fi[i + T] : 0.0;
-        const double r2 = b2 ? A.res[i + 2 * T] : 0.0, d2 = b2 ? A.adiag[i + 2 * T] : 1.0;
-        const double p2 = b2 ? A.pk[i + 2 * T] : 0.0, f2 = b2 ? A.fi[i + 2 * T] : 0.0;
+        const double r2 = b2 ? fc_ld_pol(A.res + i + 2 * T, vpol) : 0.0, d2 = b2 ? fc_ld_pol(A.adiag + i + 2 * T, vpol) : 1.0;
+        const double p2 = b2 ? fc_ld_pol(A.pk + i + 2 * T, vpol) : 0.0, f2 = b2 ? A.fi[i + 2 * T] : 0.0;
         A.fi[i] = f0 + alfp * p0;
-        A.pk[i] = r0 / (d0 + A.padd) + bet * p0;
+        fc_st_pol(A.pk + i, r0 / (d0 + A.padd) + bet * p0, vpol);
         if (b1) {
           A.fi[i + T] = f1 + alfp * p1;
-          A.pk[i + T] = r1 / (d1 + A.padd) + bet * p1;
+          fc_st_pol(A.pk + i + T, r1 / (d1 + A.padd) + bet * p1, vpol);
         }
         if (b2) {
           A.fi[i + 2 * T] = f2 + alfp * p2;
-          A.pk[i + 2 * T] = r2 / (d2 + A.padd) + bet * p2;
+          fc_st_pol(A.pk + i + 2 * T, r2 / (d2 + A.padd) + bet * p2, vpol);
         }
       }
       if (p2p && pipe.cta_strip) {
@@ -322,14 +331,17 @@ k_dpcg_persist(persist_args A) {
       double a0 = 0.0, a1 = 0.0;
       int i = rbeg + tid;
       for (; i + 3 * T < rend; i += 4 * T) {
-        const double r0 = A.res[i], r1 = A.res[i + T], r2 = A.res[i + 2 * T], r3 = A.res[i + 3 * T];
-        const double z0 = A.zk[i], z1 = A.zk[i + T], z2 = A.zk[i + 2 * T], z3 = A.zk[i + 3 * T];
-        const double d0 = A.adiag[i], d1 = A.adiag[i + T], d2 = A.adiag[i + 2 * T], d3 = A.adiag[i + 3 * T];
+        const double r0 = fc_ld_pol(A.res + i, vpol), r1 = fc_ld_pol(A.res + i + T, vpol),
+                     r2 = fc_ld_pol(A.res + i + 2 * T, vpol), r3 = fc_ld_pol(A.res + i + 3 * T, vpol);
+        const double z0 = fc_ld_pol(A.zk + i, vpol), z1 = fc_ld_pol(A.zk + i + T, vpol),
+                     z2 = fc_ld_pol(A.zk + i + 2 * T, vpol), z3 = fc_ld_pol(A.zk + i + 3 * T, vpol);
+        const double d0 = fc_ld_pol(A.adiag + i, vpol), d1 = fc_ld_pol(A.adiag + i + T, vpol),
+                     d2 = fc_ld_pol(A.adiag + i + 2 * T, vpol), d3 = fc_ld_pol(A.adiag + i + 3 * T, vpol);
         const double n0 = r0 - alf * z0, n1 = r1 - alf * z1, n2 = r2 - alf * z2, n3 = r3 - alf * z3;
-        A.res[i] = n0;
-        A.res[i + T] = n1;
-        A.res[i + 2 * T] = n2;
-        A.res[i + 3 * T] = n3;
+        fc_st_pol(A.res + i, n0, vpol);
+        fc_st_pol(A.res + i + T, n1, vpol);
+        fc_st_pol(A.res + i + 2 * T, n2, vpol);
+        fc_st_pol(A.res + i + 3 * T, n3, vpol);
         a0 += fabs(n0); a1 += n0 * (n0 / (d0 + A.padd));
         a0 += fabs(n1); a1 += n1 * (n1 / (d1 + A.padd));
         a0 += fabs(n2); a1 += n2 * (n2 / (d2 + A.padd));
@@ -337,21 +349,22 @@ k_dpcg_persist(persist_args A) {
       }
       if (i < rend) {
         const bool b1 = i + T < rend, b2 = i + 2 * T < rend;
-        const double r0 = A.res[i], z0 = A.zk[i], d0 = A.adiag[i];
-        const double r1 = b1 ? A.res[i + T] : 0.0, z1 = b1 ? A.zk[i + T] : 0.0, d1 = b1 ? A.adiag[i + T] : 1.0;
-        const double r2 = b2 ? A.res[i + 2 * T] : 0.0, z2 = b2 ? A.zk[i + 2 * T] : 0.0;
-        const double d2 = b2 ? A.adiag[i + 2 * T] : 1.0;
+        const double r0 = fc_ld_pol(A.res + i, vpol), z0 = fc_ld_pol(A.zk + i, vpol), d0 = fc_ld_pol(A.adiag + i, vpol);
+        const double r1 = b1 ? fc_ld_pol(A.res + i + T, vpol) : 0.0, z1 = b1 ? fc_ld_pol(A.zk + i + T, vpol) : 0.0,
+                     d1 = b1 ? fc_ld_pol(A.adiag + i + T, vpol) : 1.0;
+        const double r2 = b2 ? fc_ld_pol(A.res + i + 2 * T, vpol) : 0.0, z2 = b2 ? fc_ld_pol(A.zk + i + 2 * T, vpol) : 0.0;
+        const double d2 = b2 ? fc_ld_pol(A.adiag + i + 2 * T, vpol) : 1.0;
         const double n0 = r0 - alf * z0;
-        A.res[i] = n0;
+        fc_st_pol(A.res + i, n0, vpol);
         a0 += fabs(n0); a1 += n0 * (n0 / (d0 + A.padd));
         if (b1) {
           const double n1 = r1 - alf * z1;
-          A.res[i + T] = n1;
+          fc_st_pol(A.res + i + T, n1, vpol);
           a0 += fabs(n1); a1 += n1 * (n1 / (d1 + A.padd));
         }
         if (b2) {
           const double n2 = r2 - alf * z2;
-          A.res[i + 2 * T] = n2;
+          fc_st_pol(A.res + i + 2 * T, n2, vpol);
           a0 += fabs(n2); a1 += n2 * (n2 / (d2 + A.padd));
         }
       }
@@ -447,6 +460,8 @@ int fc_dpcg_persistent(fc_context *ctx, double *fi, const fc_solver_opts *o, fc_
   A.red_seq0 = ctx->red_seq;
   A.halo_seq0 = ctx->halo_seq;
   A.hist = hist;
+  // four vectors of (n + npro) doubles against the 126 MB L2, which the matrix stream shares
+  A.l2keep = ctx->tune_l2_keep == 1 || (ctx->tune_l2_keep == 2 && 32.0 * ((double)n + ctx->npro) <= 56e6);
 
   FC_CUDA(cudaMemsetAsync(ctx->pk, 0, sizeof(double) * ((size_t)n + ctx->npro), st));
   k_persist_begin<<<1, 1, 0, st>>>(ctx->persist);

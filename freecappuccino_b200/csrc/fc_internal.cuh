@@ -186,8 +186,10 @@ struct fc_context {
   int tune_ctas_per_sm = 0;             // persistent kernel: CTAs per SM (0 = as many as fit)
   int tune_sweep_p2p = 0;               // triangular sweeps: 1 = point-to-point block flags instead of level counters
   int first_batch[3] = {8, 8, 8};       // per solver: iterations enqueued before the first look at `done`
+  int tune_l2_keep = 2;                 // persistent DPCG: Krylov vectors evict_last in L2 (0 off, 1 on, 2 when they fit)
   int tune_fused_grad = 1;              // 1: the three velocity gradients of calcuvw / calcp in one kernel per pass
   int tune_sweep_check = 0;             // debugging: every tiled sweep is repeated with the level schedule and compared
+  double *vf_armed = nullptr;           // value-as-flag sweeps: the vector currently known to be all "unset"
   double *sweep_chk = nullptr;          // [n + 2] scratch of that comparison (+ two counters)
   int tune_tile_ctas = 2;               // tiled sweeps: CTAs per SM the kernel is compiled for (2 or 3)
   int tune_sweep_tiled = 2;             // triangular sweeps: 1 = two-level tiled schedule where the mesh allows it

@@ -102,6 +102,7 @@ struct fc_spmv_pipe {
   bool halo_pending;             // set by the caller before a sweep whose halo arrives by peer stores
   bool cta_strip;                // this CTA owns rows with processor faces
   unsigned long long pol;
+  unsigned long long pol_y;      // L2 policy of the result vector's stores (evict_normal unless the caller overrides it)
 
   __device__ __forceinline__ int row0(int j) const { return rbeg + j * T; }
 
@@ -116,6 +117,7 @@ struct fc_spmv_pipe {
     next = 0;
     halo_pending = false;
     pol = fc_policy_evict_first();
+    pol_y = fc_policy_evict_normal();
     int any = 0;
     for (int j = threadIdx.x; j < nch; j += blockDim.x) {
       const int r0 = row0(j);
@@ -260,7 +262,7 @@ struct fc_spmv_pipe {
             }
           }
         }
-        V.y[r] = v;
+        fc_st_pol(V.y + r, v, pol_y);
         if (MODE == FC_MODE_DOT || MODE == FC_MODE_DOT2) acc += V.w[r] * v;
         if (MODE == FC_MODE_DOT2) acc2 += v * v;
         if (RES) {

@@ -45,6 +45,22 @@ __device__ __forceinline__ unsigned long long fc_policy_evict_last() {
   return p;
 }
 
+__device__ __forceinline__ unsigned long long fc_policy_evict_normal() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// 8-byte loads / stores that carry an L2 eviction policy (the Krylov vectors of a partition that fits the L2 are
+// marked evict_last so that the matrix stream, which is evict_first, cannot push them out between two phases)
+__device__ __forceinline__ double fc_ld_pol(const double *p, unsigned long long pol) {
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void fc_st_pol(double *p, double v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+
 // global -> shared bulk copy of `bytes` (multiple of 16; both addresses 16-byte aligned), completing
 // `bytes` transaction bytes on `bar`
 __device__ __forceinline__ void fc_bulk_g2s(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar,

@@ -341,14 +341,45 @@ __global__ void k_sweep_compare(int n, const double *__restrict__ x, const doubl
   }
 }
 
+// `arm` (forward sweep of the value-as-flag mode): the vector the following backward sweep writes, see fc_tile_sweep.cuh
 template <int MODE>
 int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const double *in, double *out,
-          double small, double padd, bool guarded) {
+          double small, double padd, bool guarded, double *arm = nullptr) {
   if (ctx->tune_sweep_tiled && ctx->tiles_ok) {
     fc_levels &T = (&L == &ctx->lower) ? ctx->tile_lower : ctx->tile_upper;
     const unsigned int tbase = (unsigned int)(T.epoch * (unsigned long long)T.nblocks);
     T.epoch++;
     const bool p2p = ctx->tune_sweep_tiled == 2 && T.p2p_ok;
+    if (ctx->tune_sweep_tiled == 3) {
+      // value-as-flag hand-over: `out` must be all "unset" when the kernel starts.  The factor sweeps and a forward
+      // sweep whose target has not been re-armed by the previous backward sweep pay one memset; in the steady state
+      // of a solve the sweeps re-arm each other's vectors (FWD arms z, BWD re-arms t) and no pass is added.
+      const bool check = ctx->tune_sweep_check != 0;
+      if (MODE == TRI_FWD || MODE == TRI_BWD) {
+        if (ctx->vf_armed != out) FC_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * (size_t)ctx->n, ctx->stream));
+      } else {
+        FC_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * (size_t)ctx->n, ctx->stream));
+      }
+      ctx->vf_armed = nullptr;
+      double *in_rw = const_cast<double *>(in);
+      // the comparison sweep of FC_TUNE_SWEEP_CHECK reads the same input afterwards: do not overwrite it then
+      const double vf_small = small;
+#define FC_VF_LAUNCH_OCC(PRE_, OCC_)                                                                           \
+  k_tile_sweep_vf<MODE, PRE_, OCC_><<<T.nblocks, FC_TILE, 0, ctx->stream>>>(                                    \
+      T.meta, T.blk_nlev, T.ticket, tbase, ctx->tja, ctx->diag, ctx->tpos, a, d, in_rw, out,                    \
+      MODE == TRI_FWD ? arm : nullptr, vf_small, padd, guarded ? ctx->sc : nullptr, !check)
+#define FC_VF_LAUNCH(PRE_)                                       \
+  do {                                                           \
+    if (ctx->tune_tile_ctas == 3) FC_VF_LAUNCH_OCC(PRE_, 3);     \
+    else FC_VF_LAUNCH_OCC(PRE_, 2);                              \
+  } while (0)
+      if (ctx->tiles_pre8) FC_VF_LAUNCH(8); else FC_VF_LAUNCH(4);
+#undef FC_VF_LAUNCH
+#undef FC_VF_LAUNCH_OCC
+      FC_LAUNCH_CHECK();
+      if (MODE == TRI_FWD && arm) ctx->vf_armed = arm;              // z is unset: the backward sweep may start
+      if (MODE == TRI_BWD && !check) ctx->vf_armed = in_rw;         // t is unset again: the next forward sweep may start
+    } else
 #define FC_TILE_LAUNCH_OCC(PRE_, P2P_, OCC_)                                                                         \
   k_tile_sweep<MODE, PRE_, P2P_, OCC_><<<T.nblocks, FC_TILE, 0, ctx->stream>>>(                                       \
       T.meta, T.blk_nlev, T.blk_level, T.lev_blocks_before, T.done, T.ready, T.ticket, T.prod, T.prod_cnt, T.flag,    \
@@ -359,11 +390,13 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
     if (ctx->tune_tile_ctas == 3) FC_TILE_LAUNCH_OCC(PRE_, P2P_, 3);          \
     else FC_TILE_LAUNCH_OCC(PRE_, P2P_, 2);                                   \
   } while (0)
+    {
     if (ctx->tiles_pre8) { if (p2p) FC_TILE_LAUNCH(8, true); else FC_TILE_LAUNCH(8, false); }
     else                 { if (p2p) FC_TILE_LAUNCH(4, true); else FC_TILE_LAUNCH(4, false); }
+    FC_LAUNCH_CHECK();
+    }
 #undef FC_TILE_LAUNCH
 #undef FC_TILE_LAUNCH_OCC
-    FC_LAUNCH_CHECK();
     if (!ctx->tune_sweep_check) return FC_OK;
     // debugging aid: the same sweep once more with the level schedule into a scratch vector, compared bit for bit
     if (!ctx->sweep_chk) FC_CHECK(fc_dev_alloc(ctx, &ctx->sweep_chk, (size_t)ctx->n + 2));
@@ -518,6 +551,7 @@ int fc_levels_reset(fc_context *ctx) {
 
 // kind: 0 DIC serial, 1 DIC src-parallel, 2 DILU
 int fc_precond_factor(fc_context *ctx, int kind, const double *a, double *d, double padd) {
+  ctx->vf_armed = nullptr;   // a new solve: nothing is known about the scratch vectors of the last one
   if (kind == 0) return sweep<TRI_DIC>(ctx, ctx->lower, a, nullptr, nullptr, d, 0.0, padd, false);
   if (kind == 1) return sweep<TRI_DIC_PAR>(ctx, ctx->lower, a, nullptr, nullptr, d, 0.0, padd, false);
   return sweep<TRI_DILU>(ctx, ctx->lower, a, nullptr, nullptr, d, 0.0, padd, false);
@@ -526,6 +560,6 @@ int fc_precond_factor(fc_context *ctx, int kind, const double *a, double *d, dou
 // z = (D+U)^-1 D (D+L)^-1 r with the reference's intermediate z/(d+small); t is scratch
 int fc_precond_apply(fc_context *ctx, const double *a, const double *d, const double *r, double *t, double *z,
                      double small) {
-  FC_CHECK(sweep<TRI_FWD>(ctx, ctx->lower, a, d, r, t, small, 0.0, true));
+  FC_CHECK(sweep<TRI_FWD>(ctx, ctx->lower, a, d, r, t, small, 0.0, true, z));
   return sweep<TRI_BWD>(ctx, ctx->upper, a, d, t, z, small, 0.0, true);
 }

@@ -357,11 +357,14 @@ enum {
                                   per pass for the three fields (experimental; each gradient bit-identical) */
   FC_TUNE_SWEEP_CHECK = 8,     /* debugging: 1 repeats every tiled sweep with the level schedule and fails the call
                                   (FC_ERR_CUDA, first differing row in fc_last_error) if a single bit differs     */
+  FC_TUNE_L2_KEEP = 9,         /* persistent DPCG kernel: pk, zk, res, a_ii marked L2 evict_last (the matrix
+                                  stream is evict_first): 0 never, 1 always, [2] when the four vectors fit  */
   FC_TUNE_TILE_CTAS = 7,       /* tiled sweeps: CTAs per SM the kernel's registers allow, [2] or 3           */
-  FC_TUNE_SWEEP_TILED = 5      /* triangular sweeps: [0] one hand-over per dependency level,
+  FC_TUNE_SWEEP_TILED = 5      /* triangular sweeps: 0 one hand-over per dependency level,
                                   1 two-level schedule -- spatial tiles of <= 512 cells walked
-                                  inside one CTA, hand-overs only between tile levels, 2 the
-                                  same with point-to-point flags between tiles (experimental;
+                                  inside one CTA, hand-overs only between tile levels, [2] the
+                                  same with point-to-point flags between tiles, 3 no flags at all:
+                                  a row polls the VALUE of an out-of-tile dependency (experimental;
                                   needs a mesh whose numbering is monotone across the tiles, else
                                   the level schedule stays; same row sums, bit-identical results) */
 };

@@ -36,6 +36,23 @@ std::barrier<> *fct_bar = nullptr;
 #define FCT_TICKET(p) __atomic_fetch_add((p), 1u, __ATOMIC_RELAXED)
 #define FCT_LDCG(p) (*(const volatile double *)(p))
 #define FCT_UNROLL
+// value-as-flag mode: relaxed 8-byte atomics stand in for ld.relaxed.gpu / st.relaxed.gpu
+#include <cstring>
+static inline double fct_ld_poll(const double *p) {
+  const long long x = __atomic_load_n((const long long *)p, __ATOMIC_RELAXED);
+  double v;
+  std::memcpy(&v, &x, 8);
+  return v;
+}
+static inline void fct_st_pub(double *p, double v) {
+  long long x;
+  std::memcpy(&x, &v, 8);
+  __atomic_store_n((long long *)p, x, __ATOMIC_RELAXED);
+}
+static inline bool fct_is_unset(double v) { long long x; std::memcpy(&x, &v, 8); return x == -1ll; }
+static inline double fct_unset() { const long long x = -1ll; double v; std::memcpy(&v, &x, 8); return v; }
+#define FCT_LD_POLL(p) fct_ld_poll(p)
+#define FCT_ST_PUB(p, v) fct_st_pub((p), (v))
 static inline unsigned int ld_acquire(const unsigned int *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 static inline void st_release(unsigned int *p, unsigned int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 static inline unsigned int atom_add_acq_rel(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
@@ -201,6 +218,49 @@ int fct_emu_sweep(void *h, int mode, int pre8, int p2p, int nsweeps, int n, cons
   }
   fct_bar = nullptr;
   return 0;
+}
+
+// k_tile_sweep_vf (value-as-flag hand-over), CTA by CTA in ticket order.  `out` arrives in any state: it is filled
+// with the "unset" pattern here, as the library's memset does; `in` is copied because the backward sweep re-arms it.
+// `arm` (n doubles or null) must come back all-unset after a forward sweep, `in_copy` all-unset after a backward one:
+// returns the number of entries for which that does not hold (0 = ok), -1 for an unknown mode.
+int fct_emu_sweep_vf(void *h, int mode, int pre8, int n, const int *ioffset, const int *diag, const int *tpos,
+                     const double *a, const double *d, const double *in, double *out, double small, double padd) {
+  const fc_tile_schedule &S = *(fc_tile_schedule *)h;
+  const fc_tile_dir &D = mode == TRI_BWD ? S.upper : S.lower;
+  unsigned int ticket = 0;
+  using kernel_t = void (*)(const int4 *, const int *, unsigned int *, unsigned int, const int *, const int *,
+                            const int *, const double *, const double *, double *, double *, double *, double, double,
+                            const fc_scalars *, bool);
+  kernel_t k = nullptr;
+#define FCT_PICK(M) case M: k = pre8 ? k_tile_sweep_vf<M, 8, 2> : k_tile_sweep_vf<M, 4, 2>; break;
+  switch (mode) {
+    FCT_PICK(TRI_FWD) FCT_PICK(TRI_BWD) FCT_PICK(TRI_DIC) FCT_PICK(TRI_DIC_PAR) FCT_PICK(TRI_DILU)
+    default: return -1;
+  }
+#undef FCT_PICK
+  std::vector<double> in_copy(in, in + n), arm(n, 0.0);
+  for (int i = 0; i < n; ++i) out[i] = fct_unset();
+  std::barrier<> bar(FC_TILE);
+  fct_bar = &bar;
+  std::vector<std::thread> th;
+  th.reserve(FC_TILE);
+  for (int t = 0; t < FC_TILE; ++t)
+    th.emplace_back([&, t]() {
+      fct_tid = (unsigned)t;
+      for (int b = 0; b < D.nblocks; ++b) {
+        k((const int4 *)D.meta.data(), D.blk_nlev.data(), &ticket, 0u, S.tja.data(), diag, tpos, a, d, in_copy.data(),
+          out, mode == TRI_FWD ? arm.data() : nullptr, small, padd, nullptr, true);
+        bar.arrive_and_wait();
+      }
+    });
+  for (auto &x : th) x.join();
+  fct_bar = nullptr;
+  int bad = 0;
+  if (mode == TRI_FWD) for (int i = 0; i < n; ++i) bad += fct_is_unset(arm[i]) ? 0 : 1;
+  if (mode == TRI_BWD) for (int i = 0; i < n; ++i) bad += fct_is_unset(in_copy[i]) ? 0 : 1;
+  for (int i = 0; i < n; ++i) bad += fct_is_unset(out[i]) ? 1 : 0;
+  return bad;
 }
 
 }  // extern "C"

@@ -33,16 +33,18 @@ def fc():
 
 @pytest.mark.parametrize("name", list(MESHES))
 @pytest.mark.parametrize("solver", ["iccg", "bicgstab"])
-@pytest.mark.parametrize("mode", ["p2p", "tiled", "tiled-p2p"])
+@pytest.mark.parametrize("mode", ["p2p", "tiled", "tiled-p2p", "tiled-vf"])
 def test_sweep_variants_are_bit_identical_to_level_sweeps(fc, name, solver, mode):
     mesh = MESHES[name]()
-    key, value = {"p2p": (fc.TUNE_SWEEP_P2P, 1), "tiled": (fc.TUNE_SWEEP_TILED, 1), "tiled-p2p": (fc.TUNE_SWEEP_TILED, 2)}[mode]
+    key, value = {"p2p": (fc.TUNE_SWEEP_P2P, 1), "tiled": (fc.TUNE_SWEEP_TILED, 1), "tiled-p2p": (fc.TUNE_SWEEP_TILED, 2),
+                  "tiled-vf": (fc.TUNE_SWEEP_TILED, 3)}[mode]
     su = np.random.default_rng(5).standard_normal(mesh.numCells) * mesh.vol[:mesh.numCells]
     res = []
     for p2p in (0, 1):
         ctx = fc.Context(0)
         ctx.set_mesh(mesh)
         ctx.create_csr(download=False)
+        ctx.set_tuning(fc.TUNE_SWEEP_TILED, 0)     # the baseline of the comparison is the level schedule
         ctx.set_tuning(key, value * p2p)
         if mode.startswith("tiled") and p2p:
             ctx.set_tuning(fc.TUNE_SWEEP_CHECK, 1)    # every tiled sweep is compared with the level sweep on the device

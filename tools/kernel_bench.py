@@ -69,6 +69,7 @@ def main():
     report("bpres stage 2", timed(lambda: ctx.bpres("USER0", 2)), 76 * B)
     report("spmv", ctx.time_spmv("USER0", "SCRATCH_T", 50), 12 * nnz + 20 * nc)
     po = lib.calcp_opts(solver="dpcg", const_mflux=True, sor=1e-8, nsw=100000)
+    ctx.set_tuning(lib.TUNE_FUSED_GRAD, 0)
     report("calcp assembly (3 grads + faces + rows)", timed(lambda: ctx.calcp_assemble(po), 5), 3 * grad_b + 96 * F + 208 * nc + 16 * F)
     uo = lib.calcuvw_opts(scheme="muscl-f", bdf=True, timestep=1e-2)
     ctx.fill("FLMASS", 0.0)
@@ -79,7 +80,6 @@ def main():
            3 * grad_b + 96 * F + 208 * nc + 16 * F)
     report("calcuvw explicit part, fused u/v/w gradient", timed(lambda: ctx.calcuvw_assemble(uo), 5),
            5 * grad_b + (120 * F + 160 * nc) + (184 * F + 88 * nc))
-    ctx.set_tuning(lib.TUNE_FUSED_GRAD, 0)
     for method, nbytes in (("lstsq", 44 * (2 * F + B) + 96 * nc), ("lstsq_dm", 44 * (2 * F + B) + 96 * nc),
                            ("lstsq_qr", 12 * (2 * F + B) + 168 * nc)):
         try:
@@ -94,8 +94,9 @@ def main():
         t_plain = timed(lambda: ctx.grad("USER0", "DPDXI", 1))
         report(f"limiter {limiter}", max(t_both - t_plain, 1e-6), 36 * nnz + 56 * nc)
     ctx.set_gradient("gauss", "no-limit")
-    # Krylov solvers: per-iteration cost on the assembled p' system
+    # Krylov solvers: per-iteration cost on the assembled p' system (level-scheduled sweeps first)
     ctx.calcp_assemble(po)
+    ctx.set_tuning(lib.TUNE_SWEEP_TILED, 0)
     for solver, nbytes in (("dpcg", 12 * nnz + 116 * nc), ("iccg", 24 * nnz + 164 * nc), ("bicgstab", 2 * (24 * nnz + 164 * nc))):
         its = 200 if solver == "dpcg" else 20
         for _ in range(2):                     # first run builds the level schedules
@@ -104,8 +105,13 @@ def main():
         t = ctx.timings()
         report(f"{solver} iteration", t.solve_ms / max(rep.iters, 1), nbytes, iters=rep.iters, solve_ms=t.solve_ms)
     # experimental sweep schedules (off by default), last so that a failure cannot take the lines above with it
-    for key, value, label in ((lib.TUNE_SWEEP_TILED, 1, "tiled sweeps"), (lib.TUNE_SWEEP_TILED, 2, "tiled sweeps + p2p flags"),
-                              (lib.TUNE_SWEEP_P2P, 1, "p2p sweeps")):
+    ctx.set_tuning(lib.TUNE_SWEEP_TILED, 0)
+    only = os.environ.get("KB_SWEEPS")       # e.g. KB_SWEEPS=3 : only the value-as-flag mode
+    variants = ((lib.TUNE_SWEEP_TILED, 1, "tiled sweeps"), (lib.TUNE_SWEEP_TILED, 2, "tiled sweeps + p2p flags"),
+                (lib.TUNE_SWEEP_TILED, 3, "tiled sweeps, value-as-flag"), (lib.TUNE_SWEEP_P2P, 1, "p2p sweeps"))
+    if only:
+        variants = tuple(v for v in variants if v[0] == lib.TUNE_SWEEP_TILED and str(v[1]) in only.split(","))
+    for key, value, label in variants:
         try:
             ctx.set_tuning(key, value)
             for solver, nbytes in (("iccg", 24 * nnz + 164 * nc), ("bicgstab", 2 * (24 * nnz + 164 * nc))):

@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""A/B timings on one GPU (JSON lines):
+  * ICCG / BiCGStab per-iteration cost on the config-4 p' system for every triangular-sweep schedule
+    (FC_TUNE_SWEEP_TILED 0..3) and tile occupancy (FC_TUNE_TILE_CTAS 2, 3), with a bit-identity check of the iterate
+    against the level schedule;
+  * the persistent DPCG kernel's phase times with and without the L2 evict_last marking of the Krylov vectors
+    (FC_TUNE_L2_KEEP) -- at 108^3 one GPU holds what a rank of the 8-GPU 216^3 run holds.
+
+    python tools/sweep_bench.py sweeps 216     |     python tools/sweep_bench.py l2 108 136
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from freecappuccino_b200 import cases, lib  # noqa: E402
+
+
+def setup(n):
+    m = cases.hex_case(n, n, n)
+    f = cases.config4_fields(m)
+    ctx = lib.Context(0)
+    ctx.set_mesh(m)
+    ctx.create_csr(download=False)
+    for k, name in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("apu", "APU"), ("apv", "APV"),
+                    ("apw", "APW")):
+        ctx.upload(name, f[k])
+    ctx.grad_gauss("P", "DPDXI", 1)
+    ctx.calcp_assemble(lib.calcp_opts(solver="dpcg", const_mflux=True, sor=1e-8, nsw=100000))
+    return m, ctx
+
+
+def sweeps(n):
+    m, ctx = setup(n)
+    nnz, nc = m.nnz, m.numCells
+    ref = {}
+    for tiled, occ in ((0, 2), (2, 2), (2, 3), (3, 2), (3, 3), (1, 2)):
+        ctx.set_tuning(lib.TUNE_SWEEP_TILED, tiled)
+        ctx.set_tuning(lib.TUNE_TILE_CTAS, occ)
+        for solver, nbytes, its in (("iccg", 24 * nnz + 164 * nc, 20), ("bicgstab", 2 * (24 * nnz + 164 * nc), 10)):
+            try:
+                best = None
+                for _ in range(3):
+                    ctx.fill("PP", 0.0)
+                    rep = ctx.solve(solver, "PP", lib.solver_opts(1e-30, its))
+                    ms = ctx.timings().solve_ms
+                    best = ms if best is None else min(best, ms)
+                x = ctx.download("PP")[:nc]
+                if tiled == 0:
+                    ref[solver] = x
+                ms_it = best / max(rep.iters, 1)
+                print(json.dumps(dict(op=f"{solver} iteration", n=n, sweep_tiled=tiled, tile_ctas=occ, ms_per_iteration=ms_it,
+                                      gbs=nbytes / ms_it / 1e6, iters=rep.iters, resl=rep.resl,
+                                      bit_identical_to_level_schedule=bool(np.array_equal(x, ref[solver])),
+                                      schedule=ctx.sweep_schedule_info()[:160])), flush=True)
+            except lib.FcError as e:
+                print(json.dumps(dict(op=f"{solver} iteration", sweep_tiled=tiled, tile_ctas=occ, error=str(e))), flush=True)
+    ctx.close()
+
+
+def l2(n):
+    m, ctx = setup(n)
+    nnz, nc = m.nnz, m.numCells
+    for keep in (0, 1, 0, 1):
+        ctx.set_tuning(lib.TUNE_L2_KEEP, keep)
+        for _ in range(2):
+            ctx.fill("PP", 0.0)
+            rep = ctx.solve("dpcg", "PP", lib.solver_opts(1e-30, 400))
+        t = ctx.timings()
+        it = max(t.persist_iters, 1)
+        print(json.dumps(dict(op="dpcg persistent", n=n, cells=nc, l2_keep=keep, iters=rep.iters, us_per_iteration=1e3 * t.solve_ms / it,
+                              gbs=(12 * nnz + 116 * nc) / (t.solve_ms / it) / 1e6,
+                              p_update_us=1e3 * t.persist_pupdate_ms / it, spmv_us=1e3 * t.persist_spmv_ms / it,
+                              update_us=1e3 * t.persist_update_ms / it,
+                              sync_us=1e3 * (t.persist_ms - t.persist_pupdate_ms - t.persist_spmv_ms - t.persist_update_ms) / it,
+                              resl=rep.resl)), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    what = sys.argv[1]
+    for n in [int(x) for x in sys.argv[2:]]:
+        (sweeps if what == "sweeps" else l2)(n)
