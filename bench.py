@@ -262,6 +262,19 @@ def run_reference(args):
     }))
 
 
+def run_tool(cmd, timeout):
+    """Run a tools/ script in its own process and return its last JSON line (or an error object)."""
+    try:
+        r = subprocess.run([sys.executable] + [os.path.join(ROOT, cmd[0])] + cmd[1:], capture_output=True, text=True,
+                           timeout=timeout)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {"error": f"exit {r.returncode}: {r.stderr[-300:]}"}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def parity_check(args, ctx, opts, step, gmesh, gf, mesh, rank, world):
     """Outside every timed region: one more device-resident step, then rank 0 runs the oracle (test infrastructure,
     here only as the checker) on the SAME z-slab partition -- assembly and a DPCG solve to the same tolerance, with all
@@ -536,6 +549,33 @@ def run_ours(args):
                 {"error": f"exit {r.returncode}: {r.stderr[-300:]}"}
         except Exception as e:
             out["simple_iteration"] = {"error": repr(e)}
+    if world == 1 and not args.no_configs:
+        # the other two GPU configurations of BASELINE.json, each in its own process: config 3 (100^3 Poisson, DPCG and
+        # ICCG, oracle iteration counts beside them) and config 5 (20 M-cell polyhedral mesh, gauss_corrected +
+        # npcor = 2 + ICCG; needs ~25 GB of host memory for the mesh, skipped with a note when the box has less)
+        out["config3"] = run_tool(["tools/config3_bench.py", "100"], 300)
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available / 1e9
+        except Exception:
+            avail = 0.0
+        if avail >= 40.0:
+            out["config5"] = run_tool(["tools/poly_bench.py", "--n", str(args.poly_n), "--npcor", "2", "--steps", "1",
+                                       "--warmup", "1"], 900)
+        else:
+            out["config5"] = {"skipped": f"{avail:.0f} GB of host memory available, the 2*{args.poly_n}^3 mesh needs ~25 GB"}
+    if world > 1 and not args.no_configs and args.poly_n % world == 0:
+        # config 5 on the same ranks (layer slabs generated rank by rank; npcor = 1: with several ranks the reference's
+        # non-orthogonal corrector system is inconsistent, see tools/poly_bench.py)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import poly_bench
+            res = poly_bench.run(poly_bench.parse(["--n", str(args.poly_n), "--npcor", "1", "--steps", "1", "--warmup", "1"]))
+            if rank == 0:
+                out["config5"] = res
+        except Exception as e:   # the headline line must not depend on the widened run
+            if rank == 0:
+                out["config5"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -558,6 +598,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the full-size oracle comparison (1-2 minutes of "
                     "host time on rank 0, outside the timed regions)")
     ap.add_argument("--no-tol-solve", action="store_true", help="reference arm: skip the untimed solve to rsm<1e-8")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config 3 / config 5 sub-benchmarks (N = 1)")
+    ap.add_argument("--poly-n", type=int, default=216, help="config 5: 2 n^3 polyhedral cells (216 = 20.2 M)")
     ap.add_argument("--no-simple", action="store_true", help="skip the SIMPLE-iteration (calcuvw + calcp) timing")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="persistent DPCG kernel: CTAs per SM (0 = library default)")
     ap.add_argument("--pipe", type=int, default=-1, help="TMA pipeline geometry 0..3 (-1 = library default)")

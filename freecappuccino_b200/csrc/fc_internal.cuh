@@ -92,6 +92,7 @@ struct fc_levels {                      // level schedule of the strict lower / 
   bool p2p_ok = false;                  // every block has <= FC_TRI_MAXP producers
   // tiled mode (FC_TUNE_SWEEP_TILED, fc_tile_schedule.hpp): a block = one spatial tile of FC_TILE slots, `nlev` etc.
   // count tile levels, and inside the tile the rows are walked by local level
+  int4 *meta_rm = nullptr;              // [nslots] the same in ascending row order: row, slot | level << 16, [s, e) (k_tile_walk)
   int4 *meta = nullptr;                 // [nslots] per slot: row (-1 = padding), local level, triangle range [s, e) in a / tja
   int *blk_nlev = nullptr;              // [nblocks] local levels of the tile
 };
@@ -157,7 +158,7 @@ struct fc_context {
   bool has_levels = false;
   fc_levels tile_lower, tile_upper;     // tiled schedule of the same sweeps (only when tune_sweep_tiled)
   int *tja = nullptr;                   // [nnz] column, or -(slot+1) when the column's row sits in the same tile
-  bool tiles_tried = false, tiles_ok = false, tiles_pre8 = false;
+  bool tiles_tried = false, tiles_ok = false, tiles_pre8 = false, tiles_pre3 = false;
   std::string tiles_why;                // why the mesh got no tiling
   std::string tiles_info;               // tiles, tile levels, local levels of the tiling in use
   std::string sweep_info;               // fc_sweep_schedule_info's answer
@@ -192,7 +193,7 @@ struct fc_context {
   double *vf_armed = nullptr;           // value-as-flag sweeps: the vector currently known to be all "unset"
   double *sweep_chk = nullptr;          // [n + 2] scratch of that comparison (+ two counters)
   int tune_tile_ctas = 2;               // tiled sweeps: CTAs per SM the kernel is compiled for (2 or 3)
-  int tune_sweep_tiled = 2;             // triangular sweeps: 1 = two-level tiled schedule where the mesh allows it
+  int tune_sweep_tiled = 4;             // triangular sweeps: 1 = two-level tiled schedule where the mesh allows it
   fc_persist_state *persist = nullptr;  // device: grid barrier + phase clocks of the persistent kernel
   fc_persist_state *persist_host = nullptr;
 

@@ -30,10 +30,14 @@ struct fc_tile_dir {                     // one sweep direction (strict lower or
   int nlev = 0;                          // tile levels
   int nblocks = 0;                       // tiles, in ticket order (tile-level-major)
   int max_local_levels = 0;
-  std::vector<int> rows;                 // [nblocks * FC_TILE] row id (0-based) or -1; ascending inside a tile
+  std::vector<int> rows;                 // [nblocks * FC_TILE] row id (0-based) or -1 (padding, at the end of a tile);
+                                         // slots of a tile are ordered by local level, then row id
   std::vector<int> llev;                 // [nblocks * FC_TILE] local level of that row, -1 for padding
   std::vector<int> meta;                 // [nblocks * FC_TILE * 4] what the kernel reads per slot in one 16-byte load:
                                          // row, local level, first and one-past-last position of its triangle in a / tja
+  std::vector<int> meta_rm;              // [nblocks * FC_TILE * 4] the same rows in ASCENDING ROW ORDER inside the tile (the
+                                         // order in which their matrix entries lie in memory): row, slot | level << 16,
+                                         // triangle [s, e); -1 padding.  k_tile_walk stages the tile with these (coalesced)
   std::vector<int> blk_nlev;             // [nblocks] local levels of the tile
   std::vector<int> blk_level;            // [nblocks] tile level
   std::vector<int> lev_blocks_before;    // [nlev + 1] tiles in tile levels < L
@@ -54,7 +58,8 @@ struct fc_tile_schedule {
   int repaired_rows = 0;                 // rows of bins that had to be cut into runs of consecutive row numbers
   long long cost = 0;                    // critical path estimate in 0.1 us: see fc_tile_cost
   int max_tri_len = 0;                   // longest strict-triangle row (how many entries the kernel keeps in registers)
-  std::vector<int> tja;                  // [nnz] column j, or -(q+1) when row j is slot q of the same tile
+  std::vector<int> tja;                  // [nnz] column j, or -(q+1) when row j is slot q of the same tile IN THE DIRECTION
+                                         // THAT READS THE ENTRY (strict lower triangle: lower.rows, upper: upper.rows)
   fc_tile_dir lower, upper;
 };
 
@@ -128,8 +133,10 @@ inline void tri_range(const int *ioffset, const int *diag, int i, bool lower, in
   else { s = diag[i] + 1; e = ioffset[i + 1]; }
 }
 
+// `pos` (out): slot of every row inside its tile for this direction -- rows ordered by local level, then row id, so
+// that the rows of one local level are consecutive slots (k_tile_walk hands a level to consecutive threads)
 inline bool build_dir(int n, const int *ioffset, const int *ja, const int *diag, const std::vector<int> &tile,
-                      const std::vector<int> &pos, int ntiles, bool lower, fc_tile_dir &D, std::string &why) {
+                      std::vector<int> &pos, int ntiles, bool lower, fc_tile_dir &D, std::string &why) {
   // tile-to-tile edges producer -> consumer
   std::vector<uint64_t> edges;
   for (int i = 0; i < n; ++i) {
@@ -193,6 +200,21 @@ inline bool build_dir(int n, const int *ioffset, const int *ja, const int *diag,
       ll[i] = l;
     }
   }
+  // slots: counting sort of every tile's rows by local level (ascending row id inside a level)
+  {
+    std::vector<int> tnl(ntiles, 0);
+    for (int i = 0; i < n; ++i) tnl[tile[i]] = std::max(tnl[tile[i]], ll[i] + 1);
+    std::vector<size_t> hoff(ntiles + 1, 0);
+    for (int t = 0; t < ntiles; ++t) hoff[t + 1] = hoff[t] + (size_t)tnl[t];
+    std::vector<int> cnt(hoff[ntiles], 0);
+    for (int i = 0; i < n; ++i) cnt[hoff[tile[i]] + ll[i]]++;
+    for (int t = 0; t < ntiles; ++t) {   // exclusive prefix inside the tile
+      int run = 0;
+      for (size_t q = hoff[t]; q < hoff[t + 1]; ++q) { const int c = cnt[q]; cnt[q] = run; run += c; }
+    }
+    pos.assign(n, 0);
+    for (int i = 0; i < n; ++i) pos[i] = cnt[hoff[tile[i]] + ll[i]]++;
+  }
   // tiles in ticket order: by tile level, then tile id
   D.nlev = 0;
   for (int t = 0; t < ntiles; ++t) D.nlev = std::max(D.nlev, tlev[t] + 1);
@@ -205,6 +227,8 @@ inline bool build_dir(int n, const int *ioffset, const int *ja, const int *diag,
   D.rows.assign((size_t)ntiles * FC_TILE, -1);
   D.llev.assign((size_t)ntiles * FC_TILE, -1);
   D.meta.assign((size_t)ntiles * FC_TILE * 4, -1);
+  D.meta_rm.assign((size_t)ntiles * FC_TILE * 4, -1);
+  std::vector<int> rm_fill(ntiles, 0);
   D.blk_nlev.assign(ntiles, 0);
   D.blk_level.assign(ntiles, 0);
   D.max_local_levels = 0;
@@ -217,6 +241,8 @@ inline bool build_dir(int n, const int *ioffset, const int *ja, const int *diag,
     int ts, te;
     tri_range(ioffset, diag, i, lower, ts, te);
     D.meta[4 * slot] = i; D.meta[4 * slot + 1] = ll[i]; D.meta[4 * slot + 2] = ts; D.meta[4 * slot + 3] = te;
+    const size_t rm = (size_t)b * FC_TILE + rm_fill[b]++;   // rows are visited in ascending order
+    D.meta_rm[4 * rm] = i; D.meta_rm[4 * rm + 1] = pos[i] | (ll[i] << 16); D.meta_rm[4 * rm + 2] = ts; D.meta_rm[4 * rm + 3] = te;
     D.blk_nlev[b] = std::max(D.blk_nlev[b], ll[i] + 1);
     D.max_local_levels = std::max(D.max_local_levels, ll[i] + 1);
   }
@@ -368,23 +394,21 @@ inline fc_tile_schedule fc_build_tile_schedule(int n, const int *ioffset, const 
     return S;
   }
   S.ntiles = ntiles;
-  // slot of a row inside its tile: ascending row id (the same for both directions, so one tja serves both)
-  std::vector<int> pos(n);
-  {
-    std::vector<int> fill(ntiles, 0);
-    for (int i = 0; i < n; ++i) pos[i] = fill[tile[i]]++;
-  }
+  std::vector<int> pos_lower, pos_upper;
+  if (!build_dir(n, ioffset, ja, diag, tile, pos_lower, ntiles, true, S.lower, S.why)) return S;
+  if (!build_dir(n, ioffset, ja, diag, tile, pos_upper, ntiles, false, S.upper, S.why)) return S;
+  // in-tile dependencies name the slot of the direction that reads them: an entry of the strict lower triangle is
+  // only ever read by the forward / factor sweeps, one of the strict upper triangle by the backward sweep
   const int nnz = ioffset[n];
   S.tja.resize(nnz);
   for (int i = 0; i < n; ++i) {
     S.max_tri_len = std::max(S.max_tri_len, std::max(diag[i] - ioffset[i], ioffset[i + 1] - diag[i] - 1));
     for (int k = ioffset[i]; k < ioffset[i + 1]; ++k) {
       const int j = ja[k];
+      const std::vector<int> &pos = k < diag[i] ? pos_lower : pos_upper;
       S.tja[k] = (j != i && j < n && tile[j] == tile[i]) ? -(pos[j] + 1) : j;
     }
   }
-  if (!build_dir(n, ioffset, ja, diag, tile, pos, ntiles, true, S.lower, S.why)) return S;
-  if (!build_dir(n, ioffset, ja, diag, tile, pos, ntiles, false, S.upper, S.why)) return S;
   S.cost = std::max(fc_tile_detail::dir_cost(S.lower), fc_tile_detail::dir_cost(S.upper));
   S.ok = true;
   return S;

@@ -27,6 +27,10 @@ __device__ __forceinline__ bool fct_is_unset(double v) { return __double_as_long
 __device__ __forceinline__ double fct_unset() { return __longlong_as_double(-1ll); }
 #define FCT_LD_POLL(p) fct_ld_poll(p)
 #define FCT_ST_PUB(p, v) fct_st_pub((p), (v))
+#define FCT_WALK_KERNEL(T, OCC) __global__ void __launch_bounds__(T, OCC)
+// barrier among the first N threads of the CTA only (the other warps have retired): named barrier 1
+#define FCT_WALK_SYNC(N) asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory")
+#define FCT_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
 // Tiled mode (FC_TUNE_SWEEP_TILED; schedule: fc_tile_schedule.hpp).  A CTA owns one spatial tile of at most FC_TILE
@@ -234,4 +238,242 @@ FCT_UNROLL
     }
     FCT_SYNC();
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_tile_walk (FC_TUNE_SWEEP_TILED = 4): stage the tile with many threads, walk it with few.
+//
+// Measured on B200 (%globaltimer stamps of every 16th tile, profiles/r02_sweep_trace.txt): with one thread per slot
+// (k_tile_sweep) a tile of the 216^3 mesh lives 11.7 us, 5.6 us of them in the walk of its 22 local levels -- a local
+// level of an 8x8x8 tile holds <= 48 rows, yet all 16 warps execute the (predicated) level body, so the walk is bound by
+// instruction issue; all CTA slots are busy all the time, i.e. the sweep (0.83 ms) is bound by tile THROUGHPUT, not by
+// the tile-to-tile hand-over.  A first narrow version (64 threads do everything) was slower still: 8 slots of staging
+// per thread and ~100 dependent instructions per level with 2.5 warps per scheduler is pure instruction latency.  Hence:
+//   * ST threads stage the tile (NS / ST slots each, all loads of a pass in flight together) in ASCENDING ROW ORDER
+//     (fc_tile_dir::meta_rm: matrix entries, d and input of consecutive rows are neighbours in memory) into shared
+//     memory, scattered to the row's slot; slots are ordered by local level (fc_tile_schedule.hpp);
+//   * after the producers' flags (or the tile-level counter) are seen, every value of another tile is loaded in one
+//     batch and FOLDED into the staged coefficient: the entry becomes (product, dep = "one"), where slot NS of the value
+//     array holds 1.0, so that the walk needs no case distinction: v - c * z[dep] with c * 1.0 = c exactly.  Entries
+//     past the end of a short row are (0, "one"): v - 0 * 1 = v exactly.  (DIC_PAR / DILU carry a second factor c2:
+//     v - (c * z[dep]) * c2, again 1.0 for folded entries.)  The sums are the same left-to-right sums, bit-identical;
+//   * then all warps but the first WT / 32 retire and the walk runs branch-free on WT threads: level l = slots
+//     [start[l], start[l+1]), one pass of 64 threads on hexahedra, ~25 instructions per row, one CTA barrier per level.
+// Rows with more than PRE entries in their triangle (none on hexahedra with PRE = 4 or BCC polyhedra with PRE = 8) take
+// a slow path through global memory after the staged entries.
+// Shared layout (NS = FC_TILE slots): c[NS][PRE] | c2[NS][PRE] (DIC_PAR, DILU) | z[NS + 1] | di[NS] (FWD/BWD) |
+// dep[NS][PRE] (u16) | row[NS] | s[NS] | e[NS] | lev[NS] (short) | start[NS + 2] (short)
+template <int MODE, int PRE>
+struct fct_walk_layout {
+  static constexpr int NS = FC_TILE;
+  static constexpr bool TWO = MODE == TRI_DILU || MODE == TRI_DIC_PAR;
+  static constexpr bool SOLVE = MODE == TRI_FWD || MODE == TRI_BWD;
+  static constexpr size_t off_c = 0;
+  static constexpr size_t off_c2 = off_c + sizeof(double) * PRE * NS;
+  static constexpr size_t off_z = off_c2 + (TWO ? sizeof(double) * PRE * NS : 0);
+  static constexpr size_t off_di = off_z + sizeof(double) * (NS + 2);
+  static constexpr size_t off_dep = off_di + (SOLVE ? sizeof(double) * NS : 0);
+  static constexpr size_t off_row = off_dep + sizeof(unsigned short) * PRE * NS;
+  static constexpr size_t off_s = off_row + sizeof(int) * NS;
+  static constexpr size_t off_e = off_s + sizeof(int) * NS;
+  static constexpr size_t off_lev = off_e + sizeof(int) * NS;
+  static constexpr size_t off_start = off_lev + sizeof(short) * NS;
+  static constexpr size_t bytes = off_start + sizeof(short) * (NS + 2);
+};
+
+#ifndef FCT_TRACE   // measurement aid (-DFC_SWEEP_TRACE builds define it): time stamp number i of tile b
+#define FCT_TRACE(i)
+#endif
+struct fct_handover {   // FLAGS: the producers' flags (fc_tile_dir::prod); otherwise the tile-level counters
+  const int *blk_level, *lev_blocks_before, *prod, *prod_cnt;
+  unsigned int *done, *ready, *flag;
+  unsigned int sweep_no;
+};
+
+template <int MODE, int PRE, int ST, int WT, int OCC, bool FLAGS>
+FCT_WALK_KERNEL(ST, OCC)
+k_tile_walk(const int4 *__restrict__ meta_rm, const int *__restrict__ blk_nlev, unsigned int *ticket,
+            unsigned int ticket_base, const int *__restrict__ tja, const int *__restrict__ diag,
+            const int *__restrict__ tpos, const double *__restrict__ a, const double *__restrict__ d,
+            const double *__restrict__ in, double *out, double small, double padd, const fc_scalars *sc,
+            fct_handover H) {
+  using L = fct_walk_layout<MODE, PRE>;
+  constexpr int NS = FC_TILE;
+  constexpr int ONE = NS;   // z[ONE] = 1.0
+  FCT_DYN_SMEM(fct_raw);
+  FCT_SHARED unsigned int s_b;
+  FCT_SHARED int s_long;
+  double *const s_c = reinterpret_cast<double *>(fct_raw + L::off_c);
+  double *const s_c2 = reinterpret_cast<double *>(fct_raw + L::off_c2);
+  double *const s_z = reinterpret_cast<double *>(fct_raw + L::off_z);
+  double *const s_di = reinterpret_cast<double *>(fct_raw + L::off_di);
+  unsigned short *const s_dep = reinterpret_cast<unsigned short *>(fct_raw + L::off_dep);
+  int *const s_row = reinterpret_cast<int *>(fct_raw + L::off_row);
+  int *const s_s = reinterpret_cast<int *>(fct_raw + L::off_s);
+  int *const s_e = reinterpret_cast<int *>(fct_raw + L::off_e);
+  short *const s_lev = reinterpret_cast<short *>(fct_raw + L::off_lev);
+  short *const s_start = reinterpret_cast<short *>(fct_raw + L::off_start);
+  if (sc && sc->done) return;
+  const int tid = (int)FCT_TID;
+  if (tid == 0) { s_b = FCT_TICKET(ticket) - ticket_base; s_long = 0; s_z[ONE] = 1.0; }
+  FCT_SYNC();
+  const unsigned int b = s_b;
+  FCT_TRACE(0);
+  const int nl = blk_nlev[b];
+  // ---- pass 1: descriptors, in ascending row order; padding entries sit behind the rows in both orders
+  //      (entry i >= rows <-> slot i >= rows) and sort behind the last level ----
+  constexpr int SPT = NS / ST;
+  int rw[SPT], ss[SPT], ee[SPT], sl[SPT];
+FCT_UNROLL
+  for (int u = 0; u < SPT; ++u) {
+    const int4 mt = meta_rm[(size_t)b * NS + tid + u * ST];   // row, slot | level << 16, triangle [s, e)
+    const int slot = mt.x >= 0 ? (mt.y & 0xffff) : tid + u * ST;
+    rw[u] = mt.x; ss[u] = mt.z; ee[u] = mt.w; sl[u] = slot;
+    s_row[slot] = mt.x;
+    s_lev[slot] = (short)(mt.x >= 0 ? (mt.y >> 16) : nl);
+    s_s[slot] = mt.z;
+    s_e[slot] = mt.w;
+    if (mt.x >= 0 && mt.w - mt.z > PRE) s_long = 1;
+  }
+  FCT_TRACE(1);
+  // ---- pass 2: start value, d, the first PRE coefficients and columns: every load before the first store (no
+  //      branches: padding, or a position past the end of the row, loads position 0 / row 0) ----
+  double av[SPT][PRE], tv[SPT][PRE], vv[SPT], dv[SPT];
+  int jv[SPT][PRE];
+FCT_UNROLL
+  for (int u = 0; u < SPT; ++u) {
+    const int row = rw[u] >= 0 ? rw[u] : 0;
+    if (MODE == TRI_FWD || MODE == TRI_BWD) { vv[u] = in[row]; dv[u] = d[row]; }
+    else { vv[u] = a[diag[row]]; dv[u] = 0.0; }
+FCT_UNROLL
+    for (int q = 0; q < PRE; ++q) {
+      const bool live = rw[u] >= 0 && ss[u] + q < ee[u];
+      const int k = live ? ss[u] + q : 0;
+      av[u][q] = a[k];
+      jv[u][q] = live ? tja[k] : -(ONE + 1);   // a dead entry depends on "one" with coefficient 0
+      if (MODE == TRI_DILU) tv[u][q] = a[tpos[k]];
+      if (!live) av[u][q] = 0.0;
+    }
+  }
+  // everything that does not depend on other tiles goes to shared memory now, before the wait: start value, d,
+  // in-tile and dead entries
+FCT_UNROLL
+  for (int u = 0; u < SPT; ++u) {
+    const int slot = sl[u];
+    if (rw[u] < 0) continue;
+    s_z[slot] = MODE == TRI_BWD ? vv[u] / (dv[u] + small) : vv[u];   // z = z/(d+small), iccg.f90:102
+    if (L::SOLVE) s_di[slot] = dv[u];
+FCT_UNROLL
+    for (int q = 0; q < PRE; ++q) {
+      if (jv[u][q] < 0) {
+        double c = av[u][q], c2 = 1.0;
+        const int dep = -jv[u][q] - 1;   // slot of the same tile, or ONE for a dead entry (c = 0)
+        if (MODE == TRI_DIC) c = c * c;
+        else if (MODE == TRI_DIC_PAR) c2 = dep == ONE ? 1.0 : c;
+        else if (MODE == TRI_DILU) c2 = dep == ONE ? 1.0 : tv[u][q];
+        s_c[slot * PRE + q] = c;
+        if (L::TWO) s_c2[slot * PRE + q] = c2;
+        s_dep[slot * PRE + q] = (unsigned short)dep;
+      }
+    }
+  }
+  FCT_SYNC();
+  // first slot of every local level (levels 0 .. nl-1 are all non-empty; `nl` = the padding)
+  for (int slot = tid; slot < NS; slot += ST) {
+    const int lv = s_lev[slot];
+    if (slot == 0 || s_lev[slot - 1] != lv) s_start[lv] = (short)slot;
+    if (slot == NS - 1 && lv != nl) s_start[nl] = (short)NS;   // a full tile has no padding slot
+  }
+  FCT_TRACE(2);
+  // ---- the rows of other tiles exist: producers' flags, or the counter of the previous tile level ----
+  if (FLAGS) {
+    const int np = H.prod_cnt[b];
+    if (tid < np) {
+      const unsigned int *r = H.flag + H.prod[b * FC_TILE_MAXP + tid];
+      fc_spin_guard g;
+      while (ld_acquire(r) < H.sweep_no) g.tick();
+    }
+  } else {
+    const int lev = H.blk_level[b];
+    if (lev > 0 && tid == 0) {
+      const unsigned int *r = H.ready + (lev - 1);
+      fc_spin_guard g;
+      while (ld_acquire(r) < H.sweep_no) g.tick();
+    }
+  }
+  FCT_SYNC();
+  FCT_TRACE(3);
+  // ---- pass 3: values of other tiles, one batch, folded into the coefficient: the walk subtracts c * 1.0 (* 1.0) ----
+  double zv[SPT][PRE];
+FCT_UNROLL
+  for (int u = 0; u < SPT; ++u)
+FCT_UNROLL
+    for (int q = 0; q < PRE; ++q) zv[u][q] = jv[u][q] >= 0 ? FCT_LDCG(out + jv[u][q]) : 1.0;
+FCT_UNROLL
+  for (int u = 0; u < SPT; ++u) {
+    const int slot = sl[u];
+FCT_UNROLL
+    for (int q = 0; q < PRE; ++q) {
+      if (jv[u][q] >= 0) {
+        double c = av[u][q];
+        const double zj = zv[u][q];
+        if (MODE == TRI_FWD || MODE == TRI_BWD) c = c * zj;
+        else if (MODE == TRI_DIC) c = (c * c) * zj;            // iccg.f90:80
+        else if (MODE == TRI_DIC_PAR) c = c * zj * c;          // src-parallel/iccg.f90:97
+        else c = c * zj * tv[u][q];                            // bicgstab.f90:76
+        s_c[slot * PRE + q] = c;
+        if (L::TWO) s_c2[slot * PRE + q] = 1.0;
+        s_dep[slot * PRE + q] = (unsigned short)ONE;
+      }
+    }
+  }
+  FCT_SYNC();
+  FCT_TRACE(4);
+  FCT_TRACE(5);
+  if (tid >= WT) return;   // the staging warps retire; barriers below count the remaining threads only
+  // ---- walk the local levels: branch-free, shared memory only ----
+  // (fetching the next level's coefficients before the barrier was measured and lost: 5.4 us against 3.5 us per tile)
+  const bool any_long = s_long != 0;
+  for (int l = 0; l < nl; ++l) {
+    const int s0 = s_start[l], s1 = s_start[l + 1];
+    for (int slot = s0 + tid; slot < s1; slot += WT) {
+      double v = s_z[slot];
+FCT_UNROLL
+      for (int q = 0; q < PRE; ++q) {
+        double t = s_c[slot * PRE + q] * s_z[s_dep[slot * PRE + q]];
+        if (L::TWO) t = t * s_c2[slot * PRE + q];
+        v = v - t;
+      }
+      const int row = s_row[slot];
+      if (any_long) {                                              // rows longer than PRE (none on hex / BCC meshes)
+        const int e = s_e[slot];
+        for (int k = s_s[slot] + PRE; k < e; ++k) {
+          const int j = tja[k];
+          const double zj = j < 0 ? s_z[-j - 1] : FCT_LDCG(out + j);
+          const double ak = a[k];
+          if (MODE == TRI_FWD || MODE == TRI_BWD) v = v - ak * zj;
+          else if (MODE == TRI_DIC) v = v - (ak * ak) * zj;
+          else if (MODE == TRI_DIC_PAR) v = v - ak * zj * ak;
+          else v = v - ak * zj * a[tpos[k]];
+        }
+      }
+      const double r = L::SOLVE ? v * s_di[slot] : 1.0 / (v + padd);
+      s_z[slot] = r;
+      out[row] = r;
+    }
+    FCT_WALK_SYNC(WT);   // the last one also orders every row's store before thread 0's release below
+  }
+  FCT_TRACE(6);
+  if (tid == 0) {
+    if (FLAGS) {
+      st_release(H.flag + b, H.sweep_no);
+    } else {
+      const int lev = H.blk_level[b];
+      const unsigned int nb = (unsigned int)(H.lev_blocks_before[lev + 1] - H.lev_blocks_before[lev]);
+      const unsigned int old = atom_add_acq_rel(H.done + lev, 1u);
+      if (old + 1u == H.sweep_no * nb) st_release(H.ready + lev, H.sweep_no);
+    }
+  }
+  FCT_TRACE(7);
 }

@@ -327,8 +327,89 @@ k_tri_sweep(const int *__restrict__ rows, const int *__restrict__ blk_level,
   }
 }
 
+#ifdef FC_SWEEP_TRACE
+__device__ unsigned long long *fct_trace_buf = nullptr;
+#define FCT_TRACE(i)                                                                                       \
+  do {                                                                                                     \
+    if (fct_trace_buf && threadIdx.x == 0 && (b & 15u) == 0u) fct_trace_buf[(size_t)(b >> 4) * 12 + (i)] = fc_globaltimer(); \
+  } while (0)
+#endif
 static_assert(FC_TILE_MAXP == FC_TRI_MAXP, "one producer-table width");
 #include "fc_tile_sweep.cuh"   // k_tile_sweep<MODE, PRE, P2P>
+
+#ifdef FC_SWEEP_TRACE
+// Measurement aid (compiled only with -DFC_SWEEP_TRACE, never in the shipped library): the point-to-point tiled
+// forward sweep with %globaltimer stamps of every 16th tile -- ticket drawn, descriptors loaded, coefficients loaded,
+// producers' flags seen, out-of-tile values loaded, walk done, flag published.
+__global__ void __launch_bounds__(FC_TILE, 2)
+k_tile_sweep_trace(const int4 *__restrict__ meta, const int *__restrict__ blk_nlev, unsigned int *ticket,
+                   const int *__restrict__ prod, const int *__restrict__ prod_cnt, unsigned int *flag,
+                   unsigned int ticket_base, unsigned int sweep_no, const int *__restrict__ tja,
+                   const double *__restrict__ a, const double *__restrict__ d, const double *__restrict__ in,
+                   double *out, unsigned long long *trace) {
+  constexpr int PRE = 4;
+  __shared__ double s_z[FC_TILE];
+  __shared__ unsigned int s_b;
+  const unsigned long long t0 = fc_globaltimer();
+  if (threadIdx.x == 0) s_b = atomicAdd(ticket, 1u) - ticket_base;
+  __syncthreads();
+  const unsigned int b = s_b;
+  const bool tr = threadIdx.x == 0 && (b & 15u) == 0u;
+  unsigned long long *T = trace + (size_t)(b >> 4) * 12;
+  if (tr) { T[0] = t0; T[1] = fc_globaltimer(); }
+  const int nl = blk_nlev[b];
+  const int4 mt = meta[(size_t)b * FC_TILE + threadIdx.x];
+  const int row = mt.x, my = mt.y, s = mt.z, e = mt.w;
+  double v = 0.0, di = 0.0;
+  double pa[PRE], zq[PRE];
+  int pj[PRE];
+  if (tr) T[2] = fc_globaltimer() + (unsigned long long)(row & 0);
+  if (row >= 0) {
+#pragma unroll
+    for (int q = 0; q < PRE; ++q) {
+      const int k = s + q;
+      if (k < e) { pa[q] = a[k]; pj[q] = tja[k]; }
+    }
+    v = in[row]; di = d[row];
+  }
+  __syncthreads();
+  if (tr) T[3] = fc_globaltimer() + (unsigned long long)(__double_as_longlong(v) & 0);
+  const int np = prod_cnt[b];
+  if ((int)threadIdx.x < np) {
+    const unsigned int *r = flag + prod[b * FC_TILE_MAXP + threadIdx.x];
+    fc_spin_guard g;
+    while (ld_acquire(r) < sweep_no) g.tick();
+  }
+  if (np > 0) __syncthreads();
+  if (tr) T[4] = fc_globaltimer();
+  if (row >= 0) {
+#pragma unroll
+    for (int q = 0; q < PRE; ++q)
+      if (s + q < e && pj[q] >= 0) zq[q] = __ldcg(out + pj[q]);
+  }
+  __syncthreads();
+  if (tr) T[5] = fc_globaltimer() + (unsigned long long)(row >= 0 && s < e && pj[0] >= 0 ? (__double_as_longlong(zq[0]) & 0) : 0);
+  for (int l = 0; l < nl; ++l) {
+    if (my == l) {
+#pragma unroll
+      for (int q = 0; q < PRE; ++q) {
+        if (s + q < e) {
+          const double ak = pa[q], zj = pj[q] < 0 ? s_z[-pj[q] - 1] : zq[q];
+          v = v - ak * zj;
+        }
+      }
+      const double r = v * di;
+      s_z[threadIdx.x] = r;
+      out[row] = r;
+    }
+    __syncthreads();
+    if (tr && l == 7) T[8] = fc_globaltimer();
+  }
+  if (tr) T[6] = fc_globaltimer();
+  if (threadIdx.x == 0) st_release(flag + b, sweep_no);
+  if (tr) { T[7] = fc_globaltimer(); T[9] = (unsigned long long)nl; T[10] = (unsigned long long)np; T[11] = b; }
+}
+#endif
 
 // FC_TUNE_SWEEP_CHECK: rows whose bits differ between two sweeps of the same input (count, lowest row)
 __global__ void k_sweep_compare(int n, const double *__restrict__ x, const double *__restrict__ y, unsigned int *bad,
@@ -341,6 +422,27 @@ __global__ void k_sweep_compare(int n, const double *__restrict__ x, const doubl
   }
 }
 
+constexpr int FC_STAGE_THREADS = 256;   // k_tile_walk: threads that stage a tile ...
+constexpr int FC_WALK_THREADS = 64;     // ... and threads that walk it
+
+template <int MODE, int PRE, bool FLAGS, int ST = FC_STAGE_THREADS>
+int launch_walk(fc_context *ctx, fc_levels &T, unsigned int tbase, const double *a, const double *d, const double *in,
+                double *out, double small, double padd, bool guarded) {
+  auto kern = k_tile_walk<MODE, PRE, ST, FC_WALK_THREADS, ST == 256 ? 3 : 4, FLAGS>;
+  constexpr size_t smem = fct_walk_layout<MODE, PRE>::bytes;
+  static bool set[FC_MAX_DEVICES];   // per instantiation and per device: the opt-in above 48 KB is a per-device attribute
+  const int dev = ctx->device >= 0 && ctx->device < FC_MAX_DEVICES ? ctx->device : 0;
+  if (!set[dev] || dev != ctx->device) {
+    FC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set[dev] = true;
+  }
+  const fct_handover H{T.blk_level, T.lev_blocks_before, T.prod, T.prod_cnt, T.done, T.ready, T.flag, (unsigned int)T.epoch};
+  kern<<<T.nblocks, ST, smem, ctx->stream>>>(T.meta_rm, T.blk_nlev, T.ticket, tbase, ctx->tja, ctx->diag,
+                                                           ctx->tpos, a, d, in, out, small, padd,
+                                                           guarded ? ctx->sc : nullptr, H);
+  return FC_OK;
+}
+
 // `arm` (forward sweep of the value-as-flag mode): the vector the following backward sweep writes, see fc_tile_sweep.cuh
 template <int MODE>
 int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const double *in, double *out,
@@ -350,7 +452,47 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
     const unsigned int tbase = (unsigned int)(T.epoch * (unsigned long long)T.nblocks);
     T.epoch++;
     const bool p2p = ctx->tune_sweep_tiled == 2 && T.p2p_ok;
-    if (ctx->tune_sweep_tiled == 3) {
+    if (ctx->tune_sweep_tiled == 4) {
+      // k_tile_walk: the tile staged in shared memory by 256 threads, walked by 64; flags of the producer tiles, or the
+      // tile-level counters when a tile names more than FC_TILE_MAXP producers
+#define FC_WALK4(PRE_)                                                                                             \
+  do {                                                                                                             \
+    if (!T.p2p_ok) FC_CHECK((launch_walk<MODE, PRE_, false>(ctx, T, tbase, a, d, in, out, small, padd, guarded)));  \
+    else if (ctx->tune_tile_ctas == 3)                                                                             \
+      FC_CHECK((launch_walk<MODE, PRE_, true, 128>(ctx, T, tbase, a, d, in, out, small, padd, guarded)));           \
+    else FC_CHECK((launch_walk<MODE, PRE_, true>(ctx, T, tbase, a, d, in, out, small, padd, guarded)));             \
+  } while (0)
+#ifdef FC_SWEEP_TRACE
+      unsigned long long *trbuf = nullptr;
+      const bool tracing = MODE == TRI_FWD && getenv("FC_SWEEP_TRACE_FILE") && T.epoch == 5;
+      const size_t ntr = ((size_t)T.nblocks / 16 + 1) * 12;
+      if (tracing) {
+        FC_CUDA(cudaMalloc((void **)&trbuf, ntr * 8));
+        FC_CUDA(cudaMemsetAsync(trbuf, 0, ntr * 8, ctx->stream));
+        FC_CUDA(cudaMemcpyToSymbolAsync(fct_trace_buf, &trbuf, sizeof(trbuf), 0, cudaMemcpyHostToDevice, ctx->stream));
+      }
+#endif
+      if (ctx->tiles_pre8) FC_WALK4(8); else if (ctx->tiles_pre3) FC_WALK4(3); else FC_WALK4(4);
+#undef FC_WALK4
+      FC_LAUNCH_CHECK();
+#ifdef FC_SWEEP_TRACE
+      if (tracing) {
+        std::vector<unsigned long long> h(ntr);
+        FC_CUDA(cudaMemcpyAsync(h.data(), trbuf, ntr * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        unsigned long long *nullp = nullptr;
+        FC_CUDA(cudaMemcpyToSymbolAsync(fct_trace_buf, &nullp, sizeof(nullp), 0, cudaMemcpyHostToDevice, ctx->stream));
+        FC_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(trbuf);
+        if (FILE *fp = fopen(getenv("FC_SWEEP_TRACE_FILE"), "w")) {
+          for (size_t i = 0; i + 12 <= ntr; i += 12) {
+            for (int c = 0; c < 12; ++c) fprintf(fp, "%llu ", h[i + c]);
+            fprintf(fp, "\n");
+          }
+          fclose(fp);
+        }
+      }
+#endif
+    } else if (ctx->tune_sweep_tiled == 3) {
       // value-as-flag hand-over: `out` must be all "unset" when the kernel starts.  The factor sweeps and a forward
       // sweep whose target has not been re-armed by the previous backward sweep pay one memset; in the steady state
       // of a solve the sweeps re-arm each other's vectors (FWD arms z, BWD re-arms t) and no pass is added.
@@ -390,6 +532,27 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
     if (ctx->tune_tile_ctas == 3) FC_TILE_LAUNCH_OCC(PRE_, P2P_, 3);          \
     else FC_TILE_LAUNCH_OCC(PRE_, P2P_, 2);                                   \
   } while (0)
+#ifdef FC_SWEEP_TRACE
+    if (MODE == TRI_FWD && p2p && !ctx->tiles_pre8 && getenv("FC_SWEEP_TRACE_FILE") && T.epoch == 5) {
+      const size_t nt = ((size_t)T.nblocks / 16 + 1) * 12;
+      unsigned long long *tr = nullptr;
+      FC_CUDA(cudaMalloc((void **)&tr, nt * 8));
+      FC_CUDA(cudaMemsetAsync(tr, 0, nt * 8, ctx->stream));
+      k_tile_sweep_trace<<<T.nblocks, FC_TILE, 0, ctx->stream>>>(T.meta, T.blk_nlev, T.ticket, T.prod, T.prod_cnt, T.flag,
+                                                                 tbase, (unsigned int)T.epoch, ctx->tja, a, d, in, out, tr);
+      std::vector<unsigned long long> h(nt);
+      FC_CUDA(cudaMemcpyAsync(h.data(), tr, nt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      FC_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(tr);
+      if (FILE *fp = fopen(getenv("FC_SWEEP_TRACE_FILE"), "w")) {
+        for (size_t i = 0; i + 12 <= nt; i += 12) {
+          for (int c = 0; c < 12; ++c) fprintf(fp, "%llu ", h[i + c]);
+          fprintf(fp, "\n");
+        }
+        fclose(fp);
+      }
+    } else
+#endif
     {
     if (ctx->tiles_pre8) { if (p2p) FC_TILE_LAUNCH(8, true); else FC_TILE_LAUNCH(8, false); }
     else                 { if (p2p) FC_TILE_LAUNCH(4, true); else FC_TILE_LAUNCH(4, false); }
@@ -442,6 +605,7 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
 void fc_levels_free(fc_levels &L) {
   cudaFree(L.rows); cudaFree(L.blk_level); cudaFree(L.lev_blocks_before); cudaFree(L.done); cudaFree(L.ready);
   cudaFree(L.ticket); cudaFree(L.prod); cudaFree(L.prod_cnt); cudaFree(L.flag); cudaFree(L.meta); cudaFree(L.blk_nlev);
+  cudaFree(L.meta_rm);
   L = fc_levels{};
 }
 
@@ -453,6 +617,7 @@ int upload_tile_dir(fc_context *ctx, const fc_tile_dir &D, fc_levels &L) {
   L.nblocks = D.nblocks;
   L.nslots = D.nblocks * FC_TILE;
   FC_CHECK(fc_dev_alloc(ctx, &L.meta, D.meta.size() / 4));
+  FC_CHECK(fc_dev_alloc(ctx, &L.meta_rm, D.meta_rm.size() / 4));
   FC_CHECK(fc_dev_alloc(ctx, &L.blk_nlev, D.blk_nlev.size()));
   FC_CHECK(fc_dev_alloc(ctx, &L.blk_level, D.blk_level.size()));
   FC_CHECK(fc_dev_alloc(ctx, &L.lev_blocks_before, D.lev_blocks_before.size()));
@@ -464,7 +629,7 @@ int upload_tile_dir(fc_context *ctx, const fc_tile_dir &D, fc_levels &L) {
   FC_CHECK(fc_dev_alloc(ctx, &L.flag, (size_t)D.nblocks));
   L.p2p_ok = D.p2p_ok;
   const struct { int *dst; const std::vector<int> *src; } up[] = {
-      {(int *)L.meta, &D.meta}, {L.blk_nlev, &D.blk_nlev}, {L.blk_level, &D.blk_level},
+      {(int *)L.meta, &D.meta}, {(int *)L.meta_rm, &D.meta_rm}, {L.blk_nlev, &D.blk_nlev}, {L.blk_level, &D.blk_level},
       {L.lev_blocks_before, &D.lev_blocks_before}, {L.prod, &D.prod}, {L.prod_cnt, &D.prod_cnt}};
   for (const auto &u : up)
     FC_CUDA(cudaMemcpyAsync(u.dst, u.src->data(), sizeof(int) * u.src->size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -513,6 +678,7 @@ int build_tiles(fc_context *ctx) {
   FC_CHECK(upload_tile_dir(ctx, S.lower, ctx->tile_lower));
   FC_CHECK(upload_tile_dir(ctx, S.upper, ctx->tile_upper));
   ctx->tiles_pre8 = S.max_tri_len > 4;
+  ctx->tiles_pre3 = S.max_tri_len <= 3;   // hexahedra: one dependent subtraction less per row in k_tile_walk
   ctx->tiles_info = std::to_string(S.ntiles) + " tiles of <= " + std::to_string(S.max_tile_rows) + " rows (bins of " +
                     std::to_string(S.cells_per_axis) + " cells per axis, " + std::to_string(S.repaired_rows) +
                     " rows in cut bins), " + std::to_string(S.lower.nlev) + " / " + std::to_string(S.upper.nlev) +

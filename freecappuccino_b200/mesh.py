@@ -398,31 +398,40 @@ def _splitmix64(x: np.ndarray) -> np.ndarray:
         return z ^ (z >> np.uint64(31))
 
 
-def bcc_poly_mesh(N: int, jitter: float = 0.15, seed: int = 2024, length: float = 1.0) -> Mesh:
+def bcc_poly_mesh(N: int, jitter: float = 0.15, seed: int = 2024, length: float = 1.0,
+                  layers: Optional[Tuple[int, int]] = None) -> Mesh:
     """Voronoi tessellation of a body-centred cubic lattice over N^3 cubic unit cells: 2 N^3 truncated
     octahedra, each with 8 hexagonal faces towards the (+-1/2,+-1/2,+-1/2) neighbours and 6 square faces
     towards the (+-1,0,0) neighbours = 14 faces per cell (nnz/row = 15).  The geometry arrays are emitted
     directly (no points / faces files): face area vectors and face centres are those of the regular
     tessellation, cell centres are displaced by up to ``jitter`` x the nearest-neighbour spacing
-    (splitmix64 keyed by cell id), which makes every face non-orthogonal; ``facint`` follows from the
+    (splitmix64 keyed by the GLOBAL cell id), which makes every face non-orthogonal; ``facint`` follows from the
     displaced centres (intersection of the P-N line with the face plane, mesh_geometry...:1040-1062).
     A cell on the hull of the lattice is closed by ONE wall face carrying the sum of its missing faces'
     area vectors, so that sum(S) = 0 holds for every cell.  Cells are numbered unit cell by unit cell
-    (corner site, then body centre; i fastest), faces in OpenFOAM's upper-triangular order."""
+    (corner site, then body centre; i fastest), faces in OpenFOAM's upper-triangular order.
+
+    ``layers = (ka, kb)``: only the unit-cell layers ka <= k < kb are generated (cells keep their relative order,
+    local id = global id - 2 N^2 ka; faces towards cells outside the range are left out, every per-cell quantity --
+    centre, volume, wall closure -- is the global mesh's).  ``poly_slab_part`` builds one rank's partition from such
+    a sub-lattice, so that a 20 M-cell case never needs the global mesh on every rank."""
     a = length / N
-    n = 2 * N ** 3
-    ii, jj, kk = np.meshgrid(np.arange(N), np.arange(N), np.arange(N), indexing="ij")
-    order = np.argsort((ii + N * (jj + N * kk)).ravel(), kind="stable")
-    ci, cj, ck = (v.ravel()[order].astype(np.int64) for v in (ii, jj, kk))
-    ucell = ci + N * (cj + N * ck)                                   # unit-cell id
+    ka, kb = (0, N) if layers is None else (max(0, int(layers[0])), min(N, int(layers[1])))
+    nk = kb - ka
+    n = 2 * N * N * nk
+    id0 = 2 * N * N * ka
+    # unit cells in numbering order (i fastest, then j, then k)
+    ck, cj, ci = (v.ravel().astype(np.int64) for v in np.meshgrid(np.arange(ka, kb), np.arange(N), np.arange(N),
+                                                                   indexing="ij"))
     # site positions in units of a/2: corner sites (type 0) at even, body centres (type 1) at odd coordinates
     P = np.empty((n, 3), dtype=np.int64)
     P[0::2] = np.stack([2 * ci, 2 * cj, 2 * ck], axis=1)
     P[1::2] = P[0::2] + 1
-    cid = np.arange(n, dtype=np.int64)
+    del ci, cj, ck
+    cid = np.arange(n, dtype=np.int64)          # local ids; global id = cid + id0
 
     def site_id(q):
-        """cell id of the site at half-lattice coordinates q [m,3], or -1 outside the lattice"""
+        """GLOBAL cell id of the site at half-lattice coordinates q [m,3], or -1 outside the lattice"""
         t = q[:, 0] & 1
         same = ((q[:, 1] & 1) == t) & ((q[:, 2] & 1) == t)
         u = (q - t[:, None]) >> 1
@@ -438,52 +447,87 @@ def bcc_poly_mesh(N: int, jitter: float = 0.15, seed: int = 2024, length: float 
     a_hex, a_sq = 3.0 * a * a / 16.0, a * a / 8.0                    # |S_hex| / sqrt(3) per component, |S_sq|
     Sdir = np.concatenate([hexd * a_hex, (sqd // 2) * a_sq]).astype(np.float64)
 
-    f_own, f_nb, f_S, f_c = [], [], [], []
+    f_own, f_nb, f_dir = [], [], []
     bS = np.zeros((n, 3)); bC = np.zeros((n, 3)); bW = np.zeros(n)
-    for d, S in zip(dirs, Sdir):
-        q = P + d
-        nb = site_id(q)
+    vsum = np.zeros(n)                                               # sum over the cell's faces of (c . S_outward) / 3
+    for di, (d, S) in enumerate(zip(dirs, Sdir)):
+        nb = site_id(P + d) 
         ctr = (P + 0.5 * d) * (0.5 * a)                              # face centre = midpoint of the two sites
-        keep = nb > cid                                              # every inner face once, owner < neighbour
-        f_own.append(cid[keep]); f_nb.append(nb[keep])
-        f_S.append(np.broadcast_to(S, (int(keep.sum()), 3))); f_c.append(ctr[keep])
+        vsum += (ctr * S).sum(axis=1) / 3.0 * (nb >= 0)
         miss = nb < 0
         w = float(np.sqrt((S * S).sum()))
         bS[miss] += S; bC[miss] += w * ctr[miss]; bW[miss] += w
-    f_own = np.concatenate(f_own); f_nb = np.concatenate(f_nb)
-    f_S = np.concatenate(f_S); f_c = np.concatenate(f_c)
+        nbl = nb - id0
+        keep = (nbl > cid) & (nbl < n)                               # every inner face once, owner < neighbour
+        f_own.append(cid[keep]); f_nb.append(nbl[keep])
+        f_dir.append(np.full(int(keep.sum()), di, dtype=np.int8))
+        del nb, nbl, ctr, keep, miss
+    f_own = np.concatenate(f_own); f_nb = np.concatenate(f_nb); f_dir = np.concatenate(f_dir)
     o = np.lexsort((f_nb, f_own))
-    f_own, f_nb, f_S, f_c = f_own[o], f_nb[o], f_S[o], f_c[o]
+    f_own, f_nb, f_dir = f_own[o], f_nb[o], f_dir[o]
+    del o
     nin = f_own.size
+    f_S = Sdir[f_dir]
+    f_c = (P[f_own] + 0.5 * dirs[f_dir]) * (0.5 * a)
+    del f_dir
     # displaced cell centres
     spacing = a * np.sqrt(3.0) / 2.0
     cen = P * (0.5 * a)
     if jitter > 0.0:
-        u = np.stack([_splitmix64(np.uint64(seed) * np.uint64(0x100000001B3) + (cid * 3 + c).astype(np.uint64))
+        gid = cid + id0
+        u = np.stack([_splitmix64(np.uint64(seed) * np.uint64(0x100000001B3) + (gid * 3 + c).astype(np.uint64))
                       for c in range(3)], axis=1)
         u = (u >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)     # [0,1)
         cen = cen + (2.0 * u - 1.0) * (jitter * spacing / np.sqrt(3.0))
+        del u, gid
+    del P
     dPN = cen[f_nb] - cen[f_own]
     facint = ((f_c - cen[f_own]) * f_S).sum(axis=1) / (dPN * f_S).sum(axis=1)
+    del dPN
     bcell = np.nonzero(bW > 0)[0]
     b_S = bS[bcell]
     b_c = bC[bcell] / bW[bcell, None]
     owner = np.concatenate([f_own, bcell]) + 1
-    S_all = np.concatenate([f_S, b_S]); c_all = np.concatenate([f_c, b_c])
-    # volumes: a^3/2 inside; a hull cell is the polyhedron its own faces close (divergence theorem)
+    # volumes: a^3/2 inside; a hull cell is the polyhedron its own faces close (divergence theorem over its existing
+    # faces and its closing wall face)
     vol = np.full(n, 0.5 * a ** 3)
-    vb = np.zeros(n)
-    fv = (c_all * S_all).sum(axis=1) / 3.0
-    np.add.at(vb, owner - 1, fv)
-    np.subtract.at(vb, f_nb, fv[:nin])
-    vol[bcell] = vb[bcell]
+    vol[bcell] = vsum[bcell] + (b_c * b_S).sum(axis=1) / 3.0
+    del bS, bC, bW, vsum
+    arx = np.concatenate([f_S[:, 0], b_S[:, 0]]); ary = np.concatenate([f_S[:, 1], b_S[:, 1]])
+    arz = np.concatenate([f_S[:, 2], b_S[:, 2]])
+    del f_S
+    xf = np.concatenate([f_c[:, 0], b_c[:, 0]]); yf = np.concatenate([f_c[:, 1], b_c[:, 1]])
+    zf = np.concatenate([f_c[:, 2], b_c[:, 2]])
+    del f_c
     return Mesh(
         numCells=n, numInnerFaces=nin, numFaces=owner.size,
         owner=owner.astype(np.int32), neighbour=(f_nb + 1).astype(np.int32),
         xc=cen[:, 0].copy(), yc=cen[:, 1].copy(), zc=cen[:, 2].copy(), vol=vol,
-        arx=S_all[:, 0].copy(), ary=S_all[:, 1].copy(), arz=S_all[:, 2].copy(),
-        xf=c_all[:, 0].copy(), yf=c_all[:, 1].copy(), zf=c_all[:, 2].copy(),
-        facint=facint, counts={"wall": int(bcell.size)}, starts={"wall": int(nin)}, gloCells=n)
+        arx=arx, ary=ary, arz=arz, xf=xf, yf=yf, zf=zf,
+        facint=facint, counts={"wall": int(bcell.size)}, starts={"wall": int(nin)}, gloCells=2 * N ** 3)
+
+
+def poly_slab_part(N: int, rank: int, nranks: int, jitter: float = 0.15, seed: int = 2024) -> Mesh:
+    """Rank ``rank``'s mesh of ``partition(bcc_poly_mesh(N), slab_ranks(2 N^3, nranks), nranks)`` without the global
+    mesh: the rank's unit-cell layers plus one ghost layer on either side are generated (``layers`` of
+    ``bcc_poly_mesh``) and cut with the same routine, so every array equals the global partition's
+    (tests/test_poly_mesh.py); ``cell_global`` etc. are shifted back to global numbers.  N must be a multiple of
+    ``nranks`` (cell-id blocks = whole layers)."""
+    if N % nranks:
+        raise ValueError("poly_slab_part: N must be a multiple of the number of ranks")
+    per = N // nranks
+    k0, k1 = rank * per, (rank + 1) * per
+    ka, kb = max(0, k0 - 1), min(N, k1 + 1)
+    sub = bcc_poly_mesh(N, jitter, seed, layers=(ka, kb))
+    id0 = 2 * N * N * ka
+    ntot = 2 * N ** 3
+    cell_rank = ((np.arange(sub.numCells, dtype=np.int64) + id0) * nranks) // ntot
+    part = partition(sub, cell_rank, nranks, only=rank)[0]
+    part.gloCells = ntot
+    part.cell_global = part.cell_global + id0
+    part.halo_global = part.halo_global + id0
+    part.face_global = None            # numbers of the sub-lattice's face list: meaningless outside this function
+    return part
 
 
 def rcb_ranks(g: Mesh, nranks: int) -> np.ndarray:

@@ -364,7 +364,9 @@ enum {
                                   1 two-level schedule -- spatial tiles of <= 512 cells walked
                                   inside one CTA, hand-overs only between tile levels, [2] the
                                   same with point-to-point flags between tiles, 3 no flags at all:
-                                  a row polls the VALUE of an out-of-tile dependency (experimental;
+                                  a row polls the VALUE of an out-of-tile dependency, 4 the flags of
+                                  mode 2 with the tile staged in shared memory by 256 threads and
+                                  walked branch-free by 64 (experimental;
                                   needs a mesh whose numbering is monotone across the tiles, else
                                   the level schedule stays; same row sums, bit-identical results) */
 };

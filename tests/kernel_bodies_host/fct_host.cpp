@@ -53,6 +53,10 @@ static inline bool fct_is_unset(double v) { long long x; std::memcpy(&x, &v, 8);
 static inline double fct_unset() { const long long x = -1ll; double v; std::memcpy(&v, &x, 8); return v; }
 #define FCT_LD_POLL(p) fct_ld_poll(p)
 #define FCT_ST_PUB(p, v) fct_st_pub((p), (v))
+#define FCT_WALK_KERNEL(T, OCC) static void
+namespace { std::barrier<> *fct_walk_bar = nullptr; }
+#define FCT_WALK_SYNC(N) fct_walk_bar->arrive_and_wait()
+#define FCT_DYN_SMEM(name) alignas(16) static unsigned char name[160 * 1024]
 static inline unsigned int ld_acquire(const unsigned int *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 static inline void st_release(unsigned int *p, unsigned int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 static inline unsigned int atom_add_acq_rel(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
@@ -261,6 +265,57 @@ int fct_emu_sweep_vf(void *h, int mode, int pre8, int n, const int *ioffset, con
   if (mode == TRI_BWD) for (int i = 0; i < n; ++i) bad += fct_is_unset(in_copy[i]) ? 0 : 1;
   for (int i = 0; i < n; ++i) bad += fct_is_unset(out[i]) ? 1 : 0;
   return bad;
+}
+
+// k_tile_walk (256 threads stage a tile in shared memory, 64 walk it; flags or tile-level counters), CTA by CTA in
+// ticket order, two launches in a row on the same flags / counters.  `flags` = 1: producer flags, 0: level counters.
+int fct_emu_walk(void *h, int mode, int pre8, int flags, int n, const int *ioffset, const int *diag, const int *tpos,
+                 const double *a, const double *d, const double *in, double *out, double small, double padd) {
+  const fc_tile_schedule &S = *(fc_tile_schedule *)h;
+  const fc_tile_dir &D = mode == TRI_BWD ? S.upper : S.lower;
+  unsigned int ticket = 0;
+  constexpr int ST = 256, WT = 64;
+  using kernel_t = void (*)(const int4 *, const int *, unsigned int *, unsigned int, const int *, const int *,
+                            const int *, const double *, const double *, const double *, double *, double, double,
+                            const fc_scalars *, fct_handover);
+  kernel_t k = nullptr;
+#define FCT_PICK(M)                                                                                        \
+  case M:                                                                                                  \
+    k = pre8 == 2 ? (flags ? k_tile_walk<M, 3, ST, WT, 2, true> : k_tile_walk<M, 3, ST, WT, 2, false>)     \
+      : flags     ? (pre8 ? k_tile_walk<M, 8, ST, WT, 2, true> : k_tile_walk<M, 4, ST, WT, 2, true>)       \
+                  : (pre8 ? k_tile_walk<M, 8, ST, WT, 2, false> : k_tile_walk<M, 4, ST, WT, 2, false>);    \
+    break;
+  switch (mode) {
+    FCT_PICK(TRI_FWD) FCT_PICK(TRI_BWD) FCT_PICK(TRI_DIC) FCT_PICK(TRI_DIC_PAR) FCT_PICK(TRI_DILU)
+    default: return -1;
+  }
+#undef FCT_PICK
+  std::vector<unsigned int> done(D.nlev, 0), ready(D.nlev, 0), flag(D.nblocks, 0);
+  std::barrier<> bar(ST), wbar(WT);
+  fct_bar = &bar;
+  fct_walk_bar = &wbar;
+  for (int sweep = 1; sweep <= 2; ++sweep) {
+    // NaN, so that a value read before it was produced cannot go unnoticed
+    for (int i = 0; i < n; ++i) out[i] = std::numeric_limits<double>::quiet_NaN();
+    const fct_handover H{D.blk_level.data(), D.lev_blocks_before.data(), D.prod.data(), D.prod_cnt.data(), done.data(),
+                         ready.data(), flag.data(), (unsigned int)sweep};
+    const unsigned int base = (unsigned int)(sweep - 1) * (unsigned int)D.nblocks;
+    std::vector<std::thread> th;
+    th.reserve(ST);
+    for (int t = 0; t < ST; ++t)
+      th.emplace_back([&, t]() {
+        fct_tid = (unsigned)t;
+        for (int b = 0; b < D.nblocks; ++b) {
+          k((const int4 *)D.meta_rm.data(), D.blk_nlev.data(), &ticket, base, S.tja.data(), diag, tpos, a, d, in, out,
+            small, padd, nullptr, H);
+          bar.arrive_and_wait();   // next CTA: the static "shared" arrays are reused
+        }
+      });
+    for (auto &x : th) x.join();
+  }
+  fct_bar = nullptr;
+  fct_walk_bar = nullptr;
+  return 0;
 }
 
 }  // extern "C"

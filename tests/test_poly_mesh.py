@@ -121,3 +121,19 @@ def test_config5_path_converges_with_facefluxmass2_and_not_with_the_simple_varia
     offd = o1.a.copy()
     offd[csr.diag - 1] = 0.0
     assert offd.max() <= 0.0 and rep.rep[0].iters < 100 and rep.rep[1].iters < 100
+
+
+def test_layer_slab_parts_equal_the_global_partition():
+    """poly_slab_part (one rank's layers + a ghost layer, never the global mesh: how tools/poly_bench.py feeds the
+    20 M-cell config 5 to 8 GPUs) against partition(global mesh, slab_ranks): every array identical."""
+    from freecappuccino_b200 import mesh as M
+    N, R = 8, 4
+    g = M.bcc_poly_mesh(N)
+    parts = M.partition(g, M.slab_ranks(g.numCells, R), R)
+    for r in range(R):
+        p, q = M.poly_slab_part(N, r, R), parts[r]
+        for k in ("numCells", "numInnerFaces", "numFaces", "npro", "iProcFacesStart", "counts", "starts", "gloCells"):
+            assert getattr(p, k) == getattr(q, k), (r, k)
+        for k in ("owner", "neighbour", "xc", "yc", "zc", "vol", "arx", "ary", "arz", "xf", "yf", "zf", "facint", "fpro",
+                  "neighbProcNo", "neighbProcOffset", "cell_global", "halo_global"):
+            assert np.array_equal(getattr(p, k), getattr(q, k)), (r, k)

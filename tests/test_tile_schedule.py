@@ -228,6 +228,40 @@ def test_kernel_source_run_on_host_threads_equals_natural_order_sweeps(host, nam
         host.fct_free(C.c_void_p(h))
 
 
+@pytest.mark.parametrize("name", EMU_MESHES + ["pitzDaily", "poly-rank-of-4", "hex-24x20x17"])
+@pytest.mark.parametrize("hand", [1, 0])
+def test_tile_walk_kernel_source_on_host_threads_equals_natural_order_sweeps(host, name, hand):
+    """k_tile_walk of fc_tile_sweep.cuh (FC_TUNE_SWEEP_TILED = 4: 256 threads stage the tile in shared memory in
+    ascending row order, fold the values of other tiles into the coefficients and retire; 64 threads walk the local
+    levels branch-free; hand-over by producer flags (1) or tile-level counters (0)): the kernel source on host threads,
+    two launches in a row."""
+    s = System(MESHES[name]())
+    h, info = build(host, s)
+    try:
+        assert host.fct_ok(C.c_void_p(h))
+        zero = np.zeros(s.n)
+
+        def emu(mode, d, src, padd=0.0, pre8=0):
+            ref = np.zeros(s.n)
+            host.fct_reference_sweep(mode, s.n, ip(s.ioffset), ip(s.ja), ip(s.diag), ip(s.tpos), dp(s.a), dp(d), dp(src),
+                                     dp(ref), C.c_double(1e-20), C.c_double(padd))
+            out = np.zeros(s.n)
+            rc = host.fct_emu_walk(C.c_void_p(h), mode, pre8, hand, s.n, ip(s.ioffset), ip(s.diag), ip(s.tpos), dp(s.a),
+                                   dp(d), dp(src), dp(out), C.c_double(1e-20), C.c_double(padd))
+            assert rc == 0, (name, mode, pre8, rc)
+            assert np.array_equal(ref, out), (name, mode, pre8)
+            return out
+
+        for pre8 in (0, 1, 2):   # registers / shared slots per row: 4, 8, 3 (rows longer than that take the slow path)
+            emu(DIC, zero, zero, pre8=pre8)
+            emu(DIC_PAR, zero, zero, padd=1e-20, pre8=pre8)
+            d = emu(DILU, zero, zero, pre8=pre8)
+            t = emu(FWD, d, s.r, pre8=pre8)
+            emu(BWD, d, t, pre8=pre8)
+    finally:
+        host.fct_free(C.c_void_p(h))
+
+
 @pytest.mark.parametrize("name", EMU_MESHES)
 def test_value_as_flag_kernel_source_on_host_threads_equals_natural_order_sweeps(host, name):
     """k_tile_sweep_vf of fc_tile_sweep.cuh (FC_TUNE_SWEEP_TILED = 3: a row polls the VALUE of an out-of-tile dependency,

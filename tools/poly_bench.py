@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=128)
     ap.add_argument("--npcor", type=int, default=1)
@@ -33,32 +33,52 @@ def main():
     ap.add_argument("--solver", default="iccg", choices=["dpcg", "iccg", "bicgstab"])
     ap.add_argument("--sor", type=float, default=1e-8)
     ap.add_argument("--nsw", type=int, default=2000)
-    args = ap.parse_args()
+    ap.add_argument("--rcb", action="store_true", help="recursive coordinate bisection of the global mesh instead of "
+                    "layer slabs generated rank by rank")
+    return ap.parse_args(argv)
+
+
+def run(args):
+    """Runs on every rank of an (already initialised or to-be-initialised) torch.distributed world; returns the
+    result object on rank 0, None elsewhere."""
     import torch
     from freecappuccino_b200 import cases, lib, mesh as M, parallel
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    own_pg = False
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            own_pg = True
     t0 = time.perf_counter()
-    g = cases.poly_case(args.n)
-    f = cases.flow_fields(g)
-    fmi, flomas = cases.inlet_fluxes(g, f)
-    t_mesh = time.perf_counter() - t0
     ctx = lib.Context(local)
-    if world > 1:
+    slabs = world > 1 and args.n % world == 0 and not args.rcb
+    if slabs:
+        # layer slabs: every rank generates only its own layers (+ one ghost layer), identical to the global
+        # partition (tests/test_poly_mesh.py) -- the 20 M-cell mesh is never built in one piece
         parallel.init_comm(ctx)
-        mesh = M.partition(g, M.rcb_ranks(g, world), world, only=rank)[0]
-        fl = {k: M.scatter_total(g, mesh, f[k]) for k in ("u", "v", "w", "p", "den")}
-        fl.update({k: M.scatter_cells(g, mesh, f[k]) for k in ("apu", "apv", "apw")})
-        c = mesh.count("inlet")
-        gf = mesh.face_global[mesh.faces_start("inlet"):mesh.faces_start("inlet") + c]
-        fmi_l = np.ascontiguousarray(fmi[gf - g.faces_start("inlet")]) if c else np.zeros(0)
+        mesh = M.poly_slab_part(args.n, rank, world)
+        fl = cases.config4_fields(mesh)
+        fmi_l, flomas = np.zeros(0), 0.0
+        n_glob, F_glob = 2 * args.n ** 3, None
     else:
-        mesh, fl, fmi_l = g, f, fmi
+        g = cases.poly_case(args.n)
+        f = cases.config4_fields(g)
+        fmi, flomas = cases.inlet_fluxes(g, f)
+        n_glob, F_glob = g.numCells, g.numInnerFaces
+        if world > 1:
+            parallel.init_comm(ctx)
+            mesh = M.partition(g, M.rcb_ranks(g, world), world, only=rank)[0]
+            fl = {k: M.scatter_total(g, mesh, f[k]) for k in ("u", "v", "w", "p", "den")}
+            fl.update({k: M.scatter_cells(g, mesh, f[k]) for k in ("apu", "apv", "apw")})
+            fmi_l = np.zeros(0)
+        else:
+            mesh, fl, fmi_l = g, f, fmi
+        del g
+    t_mesh = time.perf_counter() - t0
     ctx.set_mesh(mesh)
     ctx.create_csr(download=False)
     p2p = parallel.enable_p2p(ctx) if world > 1 else False
@@ -75,6 +95,7 @@ def main():
     def step():
         for s, d in (("USER0", "U"), ("USER1", "V"), ("USER2", "W"), ("USER3", "P")):
             ctx.copy(s, d)
+        ctx.grad_gauss("P", "DPDXI", 1)      # calcp leaves grad(pp) there; every step starts from grad(p)
         return ctx.calcp(opts)
 
     def barrier():
@@ -100,24 +121,55 @@ def main():
         tt = torch.tensor([wall, solve_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         wall, solve_ms = float(tt[0]), float(tt[1])
+    # size-independent check of the solve (the oracle cannot follow to 20 M cells inside a bench): the residual the
+    # solver reports against one recomputed from scratch, || su - A pp ||_1 over all ranks
+    if world > 1:
+        ctx.exchange("PP")
+    ctx.spmv("PP", "SCRATCH_T")
+    nc = mesh.numCells
+    true_res = float(np.abs(ctx.download("SU")[:nc] - ctx.download("SCRATCH_T")[:nc]).sum())
+    nloc_faces = torch.tensor([float(mesh.numInnerFaces), float(mesh.npro), true_res], device="cuda", dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(nloc_faces)
+    true_res = float(nloc_faces[2].item())
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
     if rank == 0:
-        n, nnz = g.numCells, g.nnz
+        n = n_glob
+        F = int(nloc_faces[0].item() + nloc_faces[1].item() / 2) if F_glob is None else F_glob
+        nnz = n + 2 * F
         per_iter = {"dpcg": 12 * nnz + 116 * n, "iccg": 24 * nnz + 164 * n, "bicgstab": 2 * (24 * nnz + 164 * n)}[args.solver]
         ms_it = solve_ms / max(iters, 1)
-        print(json.dumps({
+        result = ({
             "workload": f"config 5: BCC-Voronoi polyhedral mesh 2*{args.n}^3, calcp with gauss_corrected + {args.solver}",
-            "cells": n, "inner_faces": g.numInnerFaces, "nnz": nnz, "n_gpus": world,
-            "partition": "1 rank" if world == 1 else f"rcb, {mesh.npro} processor faces on rank 0",
+            "cells": n, "inner_faces": F, "nnz": nnz, "n_gpus": world,
+            "partition": "1 rank" if world == 1 else f"{'layer slabs' if slabs else 'rcb'}, {mesh.npro} processor faces on rank 0",
             "comm": "none" if world == 1 else ("p2p" if p2p else "nccl"), "npcor": args.npcor,
             "iterations_per_step": iters / args.steps, "iter_per_s": iters / wall, "ms_per_iteration": ms_it,
             "algorithmic_gbs_per_iteration": per_iter / ms_it / 1e6,
+            "frac_of_hbm_peak_per_gpu": per_iter / ms_it / 1e6 / world / peak, "hbm_peak_gbs": peak,
+            "last_solve": {"iters": rep.rep[args.npcor - 1].iters, "res0": rep.rep[args.npcor - 1].res0,
+                           "resl_reported": rep.rep[args.npcor - 1].resl, "resl_recomputed": true_res,
+                           "rsm_recomputed": true_res / rep.rep[args.npcor - 1].res0},
             "ms_per_step": {"assemble": asm_ms / args.steps, "solve": solve_ms / args.steps, "correct": corr_ms / args.steps,
                             "wall": 1e3 * wall / args.steps},
-            "res0": rep.rep[0].res0, "resl": rep.rep[0].resl, "mesh_build_s": t_mesh}), flush=True)
+            "res0": rep.rep[0].res0, "resl": rep.rep[0].resl, "mesh_build_s": t_mesh})
+    else:
+        result = None
     ctx.close()
-    if world > 1:
+    if own_pg:
         import torch.distributed as dist
         dist.destroy_process_group()
+    return result
+
+
+def main():
+    res = run(parse())
+    if res is not None:
+        print(json.dumps(res), flush=True)
 
 
 if __name__ == "__main__":

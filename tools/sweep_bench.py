@@ -37,7 +37,7 @@ def sweeps(n):
     m, ctx = setup(n)
     nnz, nc = m.nnz, m.numCells
     ref = {}
-    for tiled, occ in ((0, 2), (2, 2), (2, 3), (3, 2), (3, 3), (1, 2)):
+    for tiled, occ in ((0, 2), (2, 2), (4, 2), (4, 3)):
         ctx.set_tuning(lib.TUNE_SWEEP_TILED, tiled)
         ctx.set_tuning(lib.TUNE_TILE_CTAS, occ)
         for solver, nbytes, its in (("iccg", 24 * nnz + 164 * nc, 20), ("bicgstab", 2 * (24 * nnz + 164 * nc), 10)):

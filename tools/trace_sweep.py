@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Measurement aid: per-tile time stamps of the point-to-point tiled forward sweep (library built with -DFC_SWEEP_TRACE)."""
+import os, sys, json
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["FC_SWEEP_TRACE_FILE"] = os.path.join(ROOT, "gpurun_out", "sweep_trace.txt")
+from freecappuccino_b200 import cases, lib
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 216
+m = cases.hex_case(n, n, n)
+f = cases.config4_fields(m)
+ctx = lib.Context(0)
+ctx.set_mesh(m); ctx.create_csr(download=False)
+for k, name in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("apu", "APU"), ("apv", "APV"), ("apw", "APW")):
+    ctx.upload(name, f[k])
+ctx.grad_gauss("P", "DPDXI", 1)
+ctx.calcp_assemble(lib.calcp_opts(solver="dpcg", const_mflux=True, sor=1e-8, nsw=100000))
+mode = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+ctx.set_tuning(lib.TUNE_SWEEP_TILED, mode)
+ctx.fill("PP", 0.0)
+rep = ctx.solve("iccg", "PP", lib.solver_opts(1e-30, 10))
+print("iters", rep.iters, "solve_ms", ctx.timings().solve_ms)
+t = np.loadtxt(os.environ["FC_SWEEP_TRACE_FILE"])
+t = t[t[:, 0] > 0]
+t0 = t[:, 0].min()
+names = ["start->ticket", "ticket->meta", "meta->loaded", "loaded->flags", "flags->ldcg", "ldcg->walk_done", "walk_done->released"]
+if mode == 4:
+    names = ["ticket->metas", "metas->pass2", "pass2->flags", "flags->pass3", "pass3->levstart", "levstart->walk_done", "walk_done->released"]
+d = np.diff(t[:, :8], axis=1)
+print("tiles traced", len(t), "sweep span us", (t[:, 7].max() - t0) / 1e3)
+for i, nm in enumerate(names):
+    print(f"{nm:22s} median {np.median(d[:, i]):8.0f} ns  mean {d[:, i].mean():8.0f}  p90 {np.percentile(d[:, i], 90):8.0f}")
+if mode != 4:
+    print("first 8 levels of the walk: median", np.median(t[:, 8] - t[:, 5]), "ns ; levels", np.median(t[:, 9]))
+print("whole tile (start->released): median", np.median(t[:, 7] - t[:, 0]), "mean", (t[:, 7] - t[:, 0]).mean())
+# concurrency: how many traced tiles are alive at a time (x16 since every 16th is traced)
+ev = np.concatenate([np.stack([t[:, 0], np.ones(len(t))], 1), np.stack([t[:, 7], -np.ones(len(t))], 1)])
+ev = ev[np.argsort(ev[:, 0])]
+alive = np.cumsum(ev[:, 1])
+print("alive tiles (x16): mean", 16 * alive.mean(), "max", 16 * alive.max())
+ctx.close()
