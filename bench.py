@@ -526,6 +526,32 @@ def run_ours(args):
         "clocks": clk,
         "roofline": roof,
     }
+    # ---- the other two Krylov solvers of the path on the same system and partition (src/iccg.f90, src/bicgstab.f90;
+    #      the shipped parallel calcp solves p' with bicgstab, the serial one with iccg): per-iteration cost of a short
+    #      run, outside the headline's timed region ----
+    out["other_solvers"] = {}
+    ctx.calcp_assemble(opts)
+    for solver, its, per_iter in (("iccg", 30, 24 * gmesh.nnz + 164 * gmesh.numCells),
+                                  ("bicgstab", 15, 2 * (24 * gmesh.nnz + 164 * gmesh.numCells))):
+        try:
+            best = None
+            for _ in range(3):   # the first run builds the sweep schedules
+                ctx.fill("PP", 0.0)
+                r = ctx.solve(solver, "PP", lib.solver_opts(1e-30, its, parallel=world > 1))
+                ms = ctx.timings().solve_ms
+                if world > 1:
+                    import torch.distributed as dist
+                    tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    ms = float(tt.item())
+                best = ms if best is None else min(best, ms)
+            ms_it = best / max(r.iters, 1)
+            out["other_solvers"][solver] = {
+                "iterations_timed": int(r.iters), "ms_per_iteration": ms_it, "iter_per_s": 1e3 / ms_it,
+                "algorithmic_gbs_all_gpus": per_iter / ms_it / 1e6, "frac_of_hbm_peak_per_gpu": per_iter / ms_it / 1e6 / world / peak,
+                "sweeps": ctx.sweep_schedule_info()[:220]}
+        except Exception as e:
+            out["other_solvers"][solver] = {"error": repr(e)}
     if not args.no_parity:
         out["parity"] = parity_check(args, ctx, opts, step, gmesh, gf, mesh, rank, world)
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -589,17 +615,19 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=216, help="cells per edge of the synthetic hex box")
+    ap.add_argument("--n", type=int, default=int(os.environ.get("FC_BENCH_N", "216")),
+                    help="cells per edge of the synthetic hex box (also FC_BENCH_N: torchrun's own parser trips over "
+                         "an option that starts with --n)")
     ap.add_argument("--cpu-iters", type=int, default=60, help="DPCG iterations of the cpu_baseline sample")
     ap.add_argument("--ref-iters", type=int, default=20, help="DPCG iterations per step of the reference arm")
     ap.add_argument("--ref-ranks", type=int, default=32, help="reference arm: ranks (= host threads) of the "
                     "src-parallel build, capped by the host's core count")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-parity", action="store_true", help="skip the full-size oracle comparison (1-2 minutes of "
+    ap.add_argument("--no-parity", action="store_true", default=os.environ.get("FC_BENCH_NO_PARITY") == "1", help="skip the full-size oracle comparison (1-2 minutes of "
                     "host time on rank 0, outside the timed regions)")
     ap.add_argument("--no-tol-solve", action="store_true", help="reference arm: skip the untimed solve to rsm<1e-8")
-    ap.add_argument("--no-configs", action="store_true", help="skip the config 3 / config 5 sub-benchmarks (N = 1)")
-    ap.add_argument("--poly-n", type=int, default=216, help="config 5: 2 n^3 polyhedral cells (216 = 20.2 M)")
+    ap.add_argument("--no-configs", action="store_true", default=os.environ.get("FC_BENCH_NO_CONFIGS") == "1", help="skip the config 3 / config 5 sub-benchmarks (N = 1)")
+    ap.add_argument("--poly-n", type=int, default=int(os.environ.get("FC_BENCH_POLY_N", "216")), help="config 5: 2 n^3 polyhedral cells (216 = 20.2 M)")
     ap.add_argument("--no-simple", action="store_true", help="skip the SIMPLE-iteration (calcuvw + calcp) timing")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="persistent DPCG kernel: CTAs per SM (0 = library default)")
     ap.add_argument("--pipe", type=int, default=-1, help="TMA pipeline geometry 0..3 (-1 = library default)")

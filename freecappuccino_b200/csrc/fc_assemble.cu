@@ -181,8 +181,10 @@ __device__ __forceinline__ void facefluxmass(const geom_t &g, const flow_t &f, i
   fluxmass = dene * (ue * arx + ve * ary + we * arz);
 }
 
-template <int VARIANT>
-__global__ void __launch_bounds__(256)
+// OCC = CTAs per SM the register allocation must allow (FC_TUNE_FACE_OCC): the kernel is bound by the latency of its
+// ~55 gathers per face (ncu: long-scoreboard stalls, 23 % of the warps resident at 100 registers)
+template <int VARIANT, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 k_calcp_faces(geom_t g, flow_t f, double *__restrict__ coef, double *__restrict__ flmass) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.F) return;
@@ -594,12 +596,22 @@ int fc_calcp_assemble_dev(fc_context *ctx, const fc_calcp_opts *o) {
   FC_CHECK(fc_grad_uvw_dev(ctx, o->nigrad, false));
   if (ctx->F > 0) {
     const int G = fc_blocks(ctx->F, B);
+#define FC_FACES(V)                                                                                                   \
+  do {                                                                                                                \
+    if (ctx->tune_face_occ >= 4)                                                                                      \
+      k_calcp_faces<V, 4><<<G, B, 0, ctx->stream>>>(geom_of(ctx), flow_of(ctx), ctx->coef, ctx->field[FC_FLMASS]);    \
+    else if (ctx->tune_face_occ == 3)                                                                                 \
+      k_calcp_faces<V, 3><<<G, B, 0, ctx->stream>>>(geom_of(ctx), flow_of(ctx), ctx->coef, ctx->field[FC_FLMASS]);    \
+    else                                                                                                              \
+      k_calcp_faces<V, 2><<<G, B, 0, ctx->stream>>>(geom_of(ctx), flow_of(ctx), ctx->coef, ctx->field[FC_FLMASS]);    \
+  } while (0)
     if (o->flux_variant == 0)
-      k_calcp_faces<0><<<G, B, 0, ctx->stream>>>(geom_of(ctx), flow_of(ctx), ctx->coef, ctx->field[FC_FLMASS]);
+      FC_FACES(0);
     else if (o->flux_variant == 1)
-      k_calcp_faces<1><<<G, B, 0, ctx->stream>>>(geom_of(ctx), flow_of(ctx), ctx->coef, ctx->field[FC_FLMASS]);
+      FC_FACES(1);
     else
-      k_calcp_faces<2><<<G, B, 0, ctx->stream>>>(geom_of(ctx), flow_of(ctx), ctx->coef, ctx->field[FC_FLMASS]);
+      FC_FACES(2);
+#undef FC_FACES
     FC_LAUNCH_CHECK();
   }
   if (ctx->npro > 0) {

@@ -634,6 +634,8 @@ int fc_set_tuning(fc_context *ctx, int key, int value) {
     case FC_TUNE_CTAS_PER_SM: if (value < 0 || value > 8) return FC_ERR_ARG; ctx->tune_ctas_per_sm = value; break;
     case FC_TUNE_SWEEP_P2P: if (value < 0 || value > 1) return FC_ERR_ARG; ctx->tune_sweep_p2p = value; break;
     case FC_TUNE_FUSED_GRAD: if (value < 0 || value > 1) return FC_ERR_ARG; ctx->tune_fused_grad = value; break;
+    case FC_TUNE_DPCG_FUSED: if (value < 0 || value > 2) return FC_ERR_ARG; ctx->tune_dpcg_fused = value; break;
+    case FC_TUNE_FACE_OCC: if (value < 2 || value > 4) return FC_ERR_ARG; ctx->tune_face_occ = value; break;
     case FC_TUNE_L2_KEEP: if (value < 0 || value > 2) return FC_ERR_ARG; ctx->tune_l2_keep = value; break;
     case FC_TUNE_SWEEP_CHECK: if (value < 0 || value > 1) return FC_ERR_ARG; ctx->tune_sweep_check = value; break;
     case FC_TUNE_TILE_CTAS: if (value != 2 && value != 3) return FC_ERR_ARG; ctx->tune_tile_ctas = value; break;

@@ -43,6 +43,9 @@ struct persist_args {
   unsigned long long red_seq0, halo_seq0;
   double *hist;
   int l2keep;   // the Krylov vectors fit the L2: mark them evict_last (the matrix stream is evict_first)
+  // "fused p" scheme (FUSED kernels): q = res / (a_ii + padd) (in the arena: the neighbours store its halo), the product's
+  // result y, and the second direction buffer (pk / pk2 alternate as pold / pnew)
+  double *q, *y, *pk2;
 };
 
 enum { PH_PUPDATE = 0, PH_SPMV = 1, PH_UPDATE = 2, PH_SETUP = 3 };
@@ -101,16 +104,20 @@ __device__ __forceinline__ void grid_barrier(const persist_args &A, sync_ctx &S,
 
 // grid barrier that carries a reduction: v[] = per-thread partial sums on entry.  The last CTA
 // finishes the sum, exchanges it with the other ranks and runs the scalar step `step`.
+// `hseq` != 0 (fused-p scheme): the CTAs stored halo values into the neighbours' memory before this barrier; the last
+// CTA raises the neighbours' halo-arrival flags before it releases its own grid (`sent_remote`: this CTA did store).
 template <int NR>
 __device__ __forceinline__ void grid_reduce(const persist_args &A, sync_ctx &S, double (&v)[NR], int step, int phase,
-                                            unsigned long long seq) {
+                                            unsigned long long seq, unsigned long long hseq = 0ull,
+                                            bool sent_remote = false) {
   const int G = gridDim.x;
   __shared__ unsigned long long s_tarr;
   fc_block_sum<NR>(v, S.s_red);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int r = 0; r < NR; ++r) A.partials[r * G + blockIdx.x] = v[r];
-    __threadfence();
+    if (sent_remote) __threadfence_system();
+    else __threadfence();
     const unsigned t = atomicAdd(&A.ps->count, 1u);
     *S.s_last = (t == (unsigned)G - 1u);
     if (*S.s_last) s_tarr = fc_globaltimer();
@@ -118,6 +125,10 @@ __device__ __forceinline__ void grid_reduce(const persist_args &A, sync_ctx &S, 
   __syncthreads();
   if (*S.s_last) {
     __threadfence();
+    if (hseq && A.p2p && threadIdx.x == 0) {   // every CTA's halo stores are ordered before its arrival
+      __threadfence_system();
+      for (int c = 0; c < A.p2p->nconn; ++c) fc_st_relaxed_sys(A.p2p->peer_hflag[c], hseq);
+    }
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       double w = 0.0;
@@ -184,7 +195,7 @@ __device__ __forceinline__ void grid_reduce(const persist_args &A, sync_ctx &S, 
   __syncthreads();
 }
 
-template <int T, int CAP, int S, bool STRIP>
+template <int T, int CAP, int S, bool STRIP, bool FUSED>
 __global__ void __launch_bounds__(T, 768 / T)   // <= 85 registers: three 256-thread CTAs per SM
 k_dpcg_persist(persist_args A) {
   extern __shared__ __align__(128) unsigned char fc_smem_raw[];
@@ -210,13 +221,135 @@ k_dpcg_persist(persist_args A) {
   const bool p2p = STRIP && A.p2p != nullptr;
   if (p2p) {
     if (tid <= A.p2p->nconn) s_conn_off[tid] = A.p2p->conn_off[tid];
-    if (tid < A.p2p->nconn) s_peer_pk[tid] = A.p2p->peer_pk[tid];
+    if (tid < A.p2p->nconn) s_peer_pk[tid] = FUSED ? A.p2p->peer_zk[tid] : A.p2p->peer_pk[tid];   // FUSED: q lives in zk
     __syncthreads();
   }
   const int nch = pipe.nch;
   fc_strip st = A.st;
   st.hseq = 0ull;   // the residual uses fi's halo as it is (src-parallel/dpcg.f90:58-66)
   unsigned long long red_seq = A.red_seq0, halo_seq = A.halo_seq0;
+
+  // my cells on a processor boundary: their values of `src` go straight into the neighbours' halo slots
+  auto send_halo = [&](const double *src) {
+    __syncthreads();
+    for (int j = 0; j < nch; j += 2) {   // two chunks at a time: the load chains of the two rows overlap
+      int row[2], q0[2], q1[2], f[2];
+      double v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        row[u] = rbeg + (j + u) * T + tid;
+        const bool act = j + u < nch && sm->cs[j + u] && row[u] < rend;
+        q0[u] = act ? A.st.off[row[u]] : 0;
+        q1[u] = act ? A.st.off[row[u] + 1] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (q1[u] > q0[u]) {
+          f[u] = A.st.idx[q0[u]];
+          v[u] = src[row[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        for (int q = q0[u]; q < q1[u]; ++q) {
+          const int ff = q == q0[u] ? f[u] : A.st.idx[q];
+          int c = 0;
+          while (ff >= s_conn_off[c + 1]) ++c;
+          s_peer_pk[c][ff - s_conn_off[c]] = v[u];
+        }
+      }
+    }
+  };
+
+  if (FUSED) {
+    // ================= "fused p" scheme: two phases and two grid barriers per iteration =================
+    // The direction vector is never swept on its own.  The x/r update leaves q = res/(a_ii[+small]) behind (it needs
+    // that quotient for the next sk anyway) and sends the boundary values of q to the neighbours; the product then
+    // gathers p(j) = q(j) + bet*pold(j) -- dpcg.f90:95-100 evaluated where it is used, same operands and rounding,
+    // so every iterate is bit-identical to the three-phase kernel -- writes the row's own p to the other direction
+    // buffer and carries the deferred x update.  A rank forms the p of its halo cells itself from the q it received
+    // and the pold it formed an iteration earlier.  One phase (48 n bytes, a division per row) and one grid barrier
+    // less per iteration: what limits the strong scaling at ~1.3 M cells per GPU.
+    {
+      fc_spmv_vec V{A.fi, A.res, A.su, nullptr, A.diag, A.adiag, A.padd};
+      V.qout = A.q;
+      double v[2] = {0.0, 0.0};
+      pipe.template sweep<FC_MODE_RESID_SK, STRIP>(A.M, V, st, v[0], v[1]);
+      pipe.prefetch(A.M);
+      if (p2p && pipe.cta_strip) send_halo(A.q);
+      ++halo_seq;
+      grid_reduce<2>(A, SY, v, STEP_RES0_SK, PH_SETUP, ++red_seq, p2p ? halo_seq : 0ull, p2p && pipe.cta_strip);
+    }
+    double *pold = A.pk, *pnew = A.pk2;
+    bool first = true;
+    while (!__ldcg(&sc->done)) {
+      // ---- y = A p, p = q + bet*pold ; pkapk = p.y ; fi += alf_prev*pold   (dpcg.f90:95-124) ----
+      {
+        if (p2p) {
+          st.hseq = halo_seq;
+          pipe.halo_pending = pipe.cta_strip;   // only CTAs that own rows with processor faces wait for the q halo
+        }
+        fc_spmv_vec V{pold, A.y, nullptr, nullptr, nullptr, nullptr, 0.0};
+        V.q = A.q;
+        V.pnew = pnew;
+        V.fi = A.fi;
+        V.bet = __ldcg(&sc->sk) / __ldcg(&sc->s0);
+        V.alfp = first ? 0.0 : __ldcg(&sc->s0) / __ldcg(&sc->pkapk);
+        first = false;
+        double v[1] = {0.0};
+        double unused = 0.0;
+        pipe.template sweep<FC_MODE_DOT_FUSED, STRIP>(A.M, V, st, v[0], unused);
+        pipe.prefetch(A.M);
+        grid_reduce<1>(A, SY, v, STEP_PKAPK, PH_SPMV, ++red_seq);
+      }
+      // ---- res -= alf*y ; q = res/(a_ii[+small]) ; resl = sum|res| ; sk = sum res*q   (dpcg.f90:125-142, :85-90) ----
+      {
+        const double alf = __ldcg(&sc->sk) / __ldcg(&sc->pkapk);
+        double a0 = 0.0, a1 = 0.0;
+        int i = rbeg + tid;
+        for (; i + 3 * T < rend; i += 4 * T) {
+          const double r0 = fc_ld_pol(A.res + i, vpol), r1 = fc_ld_pol(A.res + i + T, vpol),
+                       r2 = fc_ld_pol(A.res + i + 2 * T, vpol), r3 = fc_ld_pol(A.res + i + 3 * T, vpol);
+          const double z0 = fc_ld_pol(A.y + i, vpol), z1 = fc_ld_pol(A.y + i + T, vpol),
+                       z2 = fc_ld_pol(A.y + i + 2 * T, vpol), z3 = fc_ld_pol(A.y + i + 3 * T, vpol);
+          const double d0 = fc_ld_pol(A.adiag + i, vpol), d1 = fc_ld_pol(A.adiag + i + T, vpol),
+                       d2 = fc_ld_pol(A.adiag + i + 2 * T, vpol), d3 = fc_ld_pol(A.adiag + i + 3 * T, vpol);
+          const double n0 = r0 - alf * z0, n1 = r1 - alf * z1, n2 = r2 - alf * z2, n3 = r3 - alf * z3;
+          const double q0 = n0 / (d0 + A.padd), q1 = n1 / (d1 + A.padd), q2 = n2 / (d2 + A.padd), q3 = n3 / (d3 + A.padd);
+          fc_st_pol(A.res + i, n0, vpol);
+          fc_st_pol(A.res + i + T, n1, vpol);
+          fc_st_pol(A.res + i + 2 * T, n2, vpol);
+          fc_st_pol(A.res + i + 3 * T, n3, vpol);
+          fc_st_pol(A.q + i, q0, vpol);
+          fc_st_pol(A.q + i + T, q1, vpol);
+          fc_st_pol(A.q + i + 2 * T, q2, vpol);
+          fc_st_pol(A.q + i + 3 * T, q3, vpol);
+          a0 += fabs(n0); a1 += n0 * q0;
+          a0 += fabs(n1); a1 += n1 * q1;
+          a0 += fabs(n2); a1 += n2 * q2;
+          a0 += fabs(n3); a1 += n3 * q3;
+        }
+        for (; i < rend; i += T) {
+          const double n0 = fc_ld_pol(A.res + i, vpol) - alf * fc_ld_pol(A.y + i, vpol);
+          const double q0 = n0 / (fc_ld_pol(A.adiag + i, vpol) + A.padd);
+          fc_st_pol(A.res + i, n0, vpol);
+          fc_st_pol(A.q + i, q0, vpol);
+          a0 += fabs(n0); a1 += n0 * q0;
+        }
+        if (p2p && pipe.cta_strip) send_halo(A.q);
+        ++halo_seq;
+        double v[2] = {a0, a1};
+        grid_reduce<2>(A, SY, v, STEP_CG_UPDATE_SK, PH_UPDATE, ++red_seq, p2p ? halo_seq : 0ull, p2p && pipe.cta_strip);
+      }
+      double *t = pold; pold = pnew; pnew = t;
+    }
+    if (!first) {   // the x update of the last iteration (dpcg.f90:121-124); pold = the direction of that iteration
+      const double alf = __ldcg(&sc->s0) / __ldcg(&sc->pkapk);
+      for (int i = rbeg + tid; i < rend; i += T) A.fi[i] = A.fi[i] + alf * pold[i];
+    }
+    pipe.drain();
+    return;
+  }
 
   // ---- res = su - A fi ; res0 = sum|res| ; sk = sum res*res/(a_ii[+small])   (dpcg.f90:51-90) ----
   {
@@ -238,7 +371,7 @@ k_dpcg_persist(persist_args A) {
       const double bet = __ldcg(&sc->sk) / __ldcg(&sc->s0);
       const double alfp = first ? 0.0 : __ldcg(&sc->s0) / __ldcg(&sc->pkapk);
       first = false;
-      int i = rbeg + tid, j = 0;
+      int i = rbeg + tid;
       for (; i + 3 * T < rend; i += 4 * T) {
         const double r0 = fc_ld_pol(A.res + i, vpol), r1 = fc_ld_pol(A.res + i + T, vpol),
                      r2 = fc_ld_pol(A.res + i + 2 * T, vpol), r3 = fc_ld_pol(A.res + i + 3 * T, vpol);
@@ -276,37 +409,7 @@ k_dpcg_persist(persist_args A) {
           fc_st_pol(A.pk + i + 2 * T, r2 / (d2 + A.padd) + bet * p2, vpol);
         }
       }
-      if (p2p && pipe.cta_strip) {
-        // my cells on a processor boundary: their new values go straight into the neighbours' halo slots
-        __syncthreads();
-        for (j = 0; j < nch; j += 2) {   // two chunks at a time: the load chains of the two rows overlap
-          int row[2], q0[2], q1[2], f[2];
-          double v[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            row[u] = rbeg + (j + u) * T + tid;
-            const bool act = j + u < nch && sm->cs[j + u] && row[u] < rend;
-            q0[u] = act ? A.st.off[row[u]] : 0;
-            q1[u] = act ? A.st.off[row[u] + 1] : 0;
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (q1[u] > q0[u]) {
-              f[u] = A.st.idx[q0[u]];
-              v[u] = A.pk[row[u]];
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            for (int q = q0[u]; q < q1[u]; ++q) {
-              const int ff = q == q0[u] ? f[u] : A.st.idx[q];
-              int c = 0;
-              while (ff >= s_conn_off[c + 1]) ++c;
-              s_peer_pk[c][ff - s_conn_off[c]] = v[u];
-            }
-          }
-        }
-      }
+      if (p2p && pipe.cta_strip) send_halo(A.pk);   // exchange(pk): straight into the neighbours' halo slots
     }
     ++halo_seq;
     grid_barrier(A, SY, PH_PUPDATE, p2p ? halo_seq : 0ull, p2p && pipe.cta_strip);
@@ -379,9 +482,9 @@ k_dpcg_persist(persist_args A) {
   pipe.drain();   // no CTA may exit with bulk copies in flight
 }
 
-template <int T, int CAP, int S, bool STRIP>
+template <int T, int CAP, int S, bool STRIP, bool FUSED>
 int launch_persist(fc_context *ctx, persist_args &A, bool *ok) {
-  auto kern = k_dpcg_persist<T, CAP, S, STRIP>;
+  auto kern = k_dpcg_persist<T, CAP, S, STRIP, FUSED>;
   const size_t smem = sizeof(fc_spmv_smem<T, CAP, S>);
   // per instantiation and per device (the shared-memory opt-in is a per-device function attribute)
   static int per_sm_dev[FC_MAX_DEVICES];
@@ -463,15 +566,22 @@ int fc_dpcg_persistent(fc_context *ctx, double *fi, const fc_solver_opts *o, fc_
   // four vectors of (n + npro) doubles against the 126 MB L2, which the matrix stream shares
   A.l2keep = ctx->tune_l2_keep == 1 || (ctx->tune_l2_keep == 2 && 32.0 * ((double)n + ctx->npro) <= 56e6);
 
+  // fused-p scheme (FC_TUNE_DPCG_FUSED: 0 never, 1 always, [2] on partitioned meshes, where an iteration is short and
+  // the phase / barrier it saves is a fifth of it; on one GPU at 10 M cells the extra gathers cost more than it saves)
+  const bool fused = ctx->tune_dpcg_fused == 1 || (ctx->tune_dpcg_fused == 2 && ctx->nranks > 1);
+  A.q = ctx->zk; A.y = ctx->uk; A.pk2 = ctx->reso;
   FC_CUDA(cudaMemsetAsync(ctx->pk, 0, sizeof(double) * ((size_t)n + ctx->npro), st));
+  if (fused) FC_CUDA(cudaMemsetAsync(ctx->reso, 0, sizeof(double) * ((size_t)n + ctx->npro), st));
   k_persist_begin<<<1, 1, 0, st>>>(ctx->persist);
   FC_LAUNCH_CHECK();
   const bool strip = ctx->npro > 0;
   bool ok = false;
-#define FC_PERSIST(T, CAP, S)                                                     \
-  do {                                                                            \
-    if (strip) FC_CHECK((launch_persist<T, CAP, S, true>(ctx, A, &ok)));          \
-    else       FC_CHECK((launch_persist<T, CAP, S, false>(ctx, A, &ok)));         \
+#define FC_PERSIST(T, CAP, S)                                                                 \
+  do {                                                                                        \
+    if (strip && fused) FC_CHECK((launch_persist<T, CAP, S, true, true>(ctx, A, &ok)));       \
+    else if (strip)     FC_CHECK((launch_persist<T, CAP, S, true, false>(ctx, A, &ok)));      \
+    else if (fused)     FC_CHECK((launch_persist<T, CAP, S, false, true>(ctx, A, &ok)));      \
+    else                FC_CHECK((launch_persist<T, CAP, S, false, false>(ctx, A, &ok)));     \
   } while (0)
   if (ctx->spmv_max_chunk <= 2000) {
     switch (ctx->tune_pipe) {
@@ -493,7 +603,7 @@ int fc_dpcg_persistent(fc_context *ctx, double *fi, const fc_solver_opts *o, fc_
   rep->iters = ctx->sc_host->iters;
   // the sequence numbers the kernel consumed (identical on every rank)
   ctx->red_seq += 1ull + 2ull * (unsigned long long)rep->iters;
-  ctx->halo_seq += (unsigned long long)rep->iters;
+  ctx->halo_seq += (unsigned long long)rep->iters + (fused ? 1ull : 0ull);   // fused: q's halo also after the residual
   const fc_persist_state &ps = *ctx->persist_host;
   ctx->tm.persist_ms = 1e-6 * (double)ps.t_total;
   ctx->tm.persist_pupdate_ms = 1e-6 * (double)ps.t_phase[PH_PUPDATE];

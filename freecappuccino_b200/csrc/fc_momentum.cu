@@ -31,7 +31,8 @@ int fc_bpres_dev(fc_context *ctx, double *p, const double *dPdxi, int istage);
 
 namespace {
 
-__global__ void __launch_bounds__(256)
+template <int OCC>   // CTAs per SM the register allocation must allow (FC_TUNE_FACE_OCC), see k_calcp_faces
+__global__ void __launch_bounds__(256, OCC)
 k_uvw_faces(fcm_geom g, fcm_flow f, fcm_opts o, fcm_faces out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < g.F) fcm_face(g, f, o, out, i);
@@ -121,7 +122,9 @@ int fc_calcuvw_assemble_dev(fc_context *ctx, const fc_calcuvw_opts *o) {
   const fcm_opts fo = opts_of(o);
   const fcm_faces fa = faces_of(ctx);
   if (ctx->F > 0) {
-    k_uvw_faces<<<fc_blocks(ctx->F, B), B, 0, st>>>(g, f, fo, fa);
+    if (ctx->tune_face_occ >= 4) k_uvw_faces<4><<<fc_blocks(ctx->F, B), B, 0, st>>>(g, f, fo, fa);
+    else if (ctx->tune_face_occ == 3) k_uvw_faces<3><<<fc_blocks(ctx->F, B), B, 0, st>>>(g, f, fo, fa);
+    else k_uvw_faces<2><<<fc_blocks(ctx->F, B), B, 0, st>>>(g, f, fo, fa);
     FC_LAUNCH_CHECK();
   }
   double **fl = ctx->field;

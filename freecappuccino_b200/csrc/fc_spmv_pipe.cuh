@@ -23,7 +23,11 @@
 constexpr int FC_KB_MAX = 512;   // chunks per CTA whose boundaries are cached in shared memory
 
 // DOT: w.y ; DOT2: w.y and y.y ; RESID: y = su - A x, sum|y| ; RESID_SK: + sum y*y/(a_ii + padd)
-enum { FC_MODE_SPMV = 0, FC_MODE_DOT = 1, FC_MODE_RESID = 2, FC_MODE_DOT2 = 3, FC_MODE_RESID_SK = 4 };
+// DOT_FUSED (persistent DPCG, "fused p" scheme): the direction vector is never swept on its own -- the product gathers
+//   p(j) = q(j) + bet * pold(j)   with q = res / (a_ii + padd) left behind by the x/r update,
+// the expression of dpcg.f90:95-100 evaluated where it is used (same operands, same rounding: bit-identical); the row's
+// own p goes to `pnew`, the deferred x update fi += alfp * pold rides along, red[0] = p.y.
+enum { FC_MODE_SPMV = 0, FC_MODE_DOT = 1, FC_MODE_RESID = 2, FC_MODE_DOT2 = 3, FC_MODE_RESID_SK = 4, FC_MODE_DOT_FUSED = 5 };
 
 struct fc_strip {              // processor-boundary coupling kept outside the CSR (src-parallel `apr`)
   const int *off;              // [n+1] per-row range into idx, or nullptr on a single rank
@@ -51,6 +55,10 @@ struct fc_spmv_vec {
   const int *diag;       // RESID: adiag[r] = a[diag[r]]
   double *adiag;
   double padd;           // RESID_SK: `small` of the parallel preconditioner (src-parallel/dpcg.f90:96)
+  // DOT_FUSED (x = pold); RESID_SK also stores q = res / (a_ii + padd) when `qout` is set
+  const double *q = nullptr;
+  double *qout = nullptr, *pnew = nullptr, *fi = nullptr;
+  double bet = 0.0, alfp = 0.0;
 };
 
 // Rows [rbeg, rend) of CTA b out of G: equal shares of cost(r) = r + FC_STRIP_WEIGHT * (processor faces of
@@ -208,7 +216,12 @@ struct fc_spmv_pipe {
           if (sq1 > sq0) {
             const int i = st.idx[sq0];
             sap = st.apr[i];
-            sxh = __ldcg(V.x + st.halo0 + i);
+            if (MODE == FC_MODE_DOT_FUSED) {   // the neighbour sent q; its p is formed here, like every other p
+              sxh = __ldcg(V.q + st.halo0 + i) + V.bet * V.x[st.halo0 + i];
+              V.pnew[st.halo0 + i] = sxh;
+            } else {
+              sxh = __ldcg(V.x + st.halo0 + i);
+            }
           }
         }
       }
@@ -235,8 +248,16 @@ struct fc_spmv_pipe {
               id[u] = in ? pj[c + u] : r;
               av[u] = in ? pa[c + u] : 0.0;
             }
+            if (MODE == FC_MODE_DOT_FUSED) {
+              double qv[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) xv[u] = V.x[id[u]];
+              for (int u = 0; u < U; ++u) { qv[u] = V.q[id[u]]; xv[u] = V.x[id[u]]; }
+#pragma unroll
+              for (int u = 0; u < U; ++u) xv[u] = qv[u] + V.bet * xv[u];
+            } else {
+#pragma unroll
+              for (int u = 0; u < U; ++u) xv[u] = V.x[id[u]];
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               if (c + u < e - ka) {
@@ -247,7 +268,9 @@ struct fc_spmv_pipe {
           }
         } else {  // a chunk too long for the staging buffers: straight from global memory
           for (int k = s; k < e; ++k) {
-            double t = M.a[k] * V.x[M.ja[k]];
+            const int jc = M.ja[k];
+            const double xj = MODE == FC_MODE_DOT_FUSED ? V.q[jc] + V.bet * V.x[jc] : V.x[jc];
+            double t = M.a[k] * xj;
             v = RES ? v - t : v + t;
           }
         }
@@ -257,19 +280,37 @@ struct fc_spmv_pipe {
             v = RES ? v - t : v + t;
             for (int q = sq0 + 1; q < sq1; ++q) {
               const int i = st.idx[q];
-              t = st.apr[i] * __ldcg(V.x + st.halo0 + i);
+              double xh;
+              if (MODE == FC_MODE_DOT_FUSED) {
+                xh = __ldcg(V.q + st.halo0 + i) + V.bet * V.x[st.halo0 + i];
+                V.pnew[st.halo0 + i] = xh;
+              } else {
+                xh = __ldcg(V.x + st.halo0 + i);
+              }
+              t = st.apr[i] * xh;
               v = RES ? v - t : v + t;
             }
           }
         }
         fc_st_pol(V.y + r, v, pol_y);
         if (MODE == FC_MODE_DOT || MODE == FC_MODE_DOT2) acc += V.w[r] * v;
+        if (MODE == FC_MODE_DOT_FUSED) {
+          const double po = V.x[r];
+          const double pn = V.q[r] + V.bet * po;
+          fc_st_pol(V.pnew + r, pn, pol_y);
+          V.fi[r] = V.fi[r] + V.alfp * po;   // x update of the previous iteration (dpcg.f90:121-124), deferred
+          acc += pn * v;
+        }
         if (MODE == FC_MODE_DOT2) acc2 += v * v;
         if (RES) {
           acc += fabs(v);
           const double ad = staged ? pa[V.diag[r] - ka] : M.a[V.diag[r]];
           V.adiag[r] = ad;
-          if (MODE == FC_MODE_RESID_SK) acc2 += v * (v / (ad + V.padd));
+          if (MODE == FC_MODE_RESID_SK) {
+            const double qv = v / (ad + V.padd);
+            acc2 += v * qv;
+            if (V.qout) V.qout[r] = qv;
+          }
         }
       }
       __syncthreads();

@@ -52,9 +52,11 @@ TUNE_FUSED_GRAD = 6
 TUNE_TILE_CTAS = 7
 TUNE_SWEEP_CHECK = 8
 TUNE_L2_KEEP = 9
+TUNE_DPCG_FUSED = 10
+TUNE_FACE_OCC = 11
 TUNE_KEYS = {"spmv_kernel": TUNE_SPMV_KERNEL, "dpcg_persistent": TUNE_DPCG_PERSISTENT, "ctas_per_sm": TUNE_CTAS_PER_SM,
              "pipe_geometry": TUNE_PIPE_GEOMETRY, "sweep_p2p": TUNE_SWEEP_P2P, "sweep_tiled": TUNE_SWEEP_TILED,
-             "fused_grad": TUNE_FUSED_GRAD, "tile_ctas": TUNE_TILE_CTAS, "sweep_check": TUNE_SWEEP_CHECK, "l2_keep": TUNE_L2_KEEP}
+             "fused_grad": TUNE_FUSED_GRAD, "tile_ctas": TUNE_TILE_CTAS, "sweep_check": TUNE_SWEEP_CHECK, "l2_keep": TUNE_L2_KEEP, "dpcg_fused": TUNE_DPCG_FUSED, "face_occ": TUNE_FACE_OCC}
 
 
 class MeshDesc(C.Structure):

@@ -357,6 +357,13 @@ enum {
                                   per pass for the three fields (experimental; each gradient bit-identical) */
   FC_TUNE_SWEEP_CHECK = 8,     /* debugging: 1 repeats every tiled sweep with the level schedule and fails the call
                                   (FC_ERR_CUDA, first differing row in fc_last_error) if a single bit differs     */
+  FC_TUNE_DPCG_FUSED = 10,     /* persistent DPCG kernel, "fused p" scheme: the product gathers p = q + bet*pold
+                                  instead of a separate p-update phase (one phase and one grid barrier less per
+                                  iteration, bit-identical iterates): [0] never, 1 always, 2 on partitioned meshes.
+                                  Measured slower than the three-phase kernel at every size (the second gather per
+                                  non-zero costs what the phase saved), so it stays an option                   */
+  FC_TUNE_FACE_OCC = 11,       /* face kernels of calcp / calcuvw: CTAs of 256 threads per SM the register allocation
+                                  must allow, [2], 3 or 4 (they are bound by the latency of their gathers)      */
   FC_TUNE_L2_KEEP = 9,         /* persistent DPCG kernel: pk, zk, res, a_ii marked L2 evict_last (the matrix
                                   stream is evict_first): 0 never, 1 always, [2] when the four vectors fit  */
   FC_TUNE_TILE_CTAS = 7,       /* tiled sweeps: CTAs per SM the kernel's registers allow, [2] or 3           */

@@ -121,6 +121,34 @@ def test_dpcg_persistent_equals_multi_kernel(fc):
     assert cases.rel_l2(out[0][3], out[1][3]) < 1e-10
 
 
+@pytest.mark.parametrize("name", ["hex", "poly", "skew"])
+def test_dpcg_fused_p_scheme_is_bit_identical(fc, name):
+    """FC_TUNE_DPCG_FUSED: the persistent kernel without a p-update phase (the product gathers p = q + bet*pold, the
+    x/r update leaves q = res/a_ii behind).  Same operands and rounding in every expression and the same grid, hence
+    the same partial sums: iteration count, residuals, solution and final residual vector must not differ by a bit.
+    Also nsw = 0 and an early exit after one iteration (the deferred x update of the last iteration)."""
+    mesh = {"hex": lambda: cases.hex_case(40, 36, 20, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry")),
+            "poly": lambda: cases.poly_case(9), "skew": lambda: cases.skew_case(14, 12, 10)}[name]()
+    su = np.random.default_rng(3).standard_normal(mesh.numCells) * mesh.vol[:mesh.numCells]
+    for sor, nsw in ((1e-9, 5000), (1e-30, 1), (1e-30, 7), (1e-9, 0)):
+        out = {}
+        for fused in (0, 1):
+            ctx = fc.Context(0)
+            ctx.set_mesh(mesh)
+            ctx.create_csr(download=False)
+            ctx.set_tuning(fc.TUNE_DPCG_FUSED, fused)
+            ctx.upload("APU", -np.ones(mesh.numCells))
+            ctx.upload("SU", su)
+            ctx.upload("PP", 0.01 * np.cos(np.arange(mesh.numTotal)))
+            ctx.laplacian("APU", "PP")
+            rep = ctx.solve("dpcg", "PP", fc.solver_opts(sor, nsw))
+            assert ctx.timings().persist_iters == rep.iters
+            out[fused] = (rep.iters, rep.res0, rep.resl, ctx.download("PP"), ctx.download("RES"))
+            ctx.close()
+        assert out[0][:3] == out[1][:3], (name, sor, nsw, out[0][:3], out[1][:3])
+        assert np.array_equal(out[0][3], out[1][3]) and np.array_equal(out[0][4], out[1][4]), (name, sor, nsw)
+
+
 def test_early_return_when_already_converged(fc):
     """dpcg.f90:66-70: res0 < tol returns before the first iteration (persistent and multi-kernel path)."""
     mesh = cases.hex_case(8, 8, 8)

@@ -61,17 +61,18 @@ def sweeps(n):
     ctx.close()
 
 
-def l2(n):
+def l2(n, key=None):
     m, ctx = setup(n)
     nnz, nc = m.nnz, m.numCells
+    key = lib.TUNE_L2_KEEP if key is None else key
     for keep in (0, 1, 0, 1):
-        ctx.set_tuning(lib.TUNE_L2_KEEP, keep)
+        ctx.set_tuning(key, keep)
         for _ in range(2):
             ctx.fill("PP", 0.0)
             rep = ctx.solve("dpcg", "PP", lib.solver_opts(1e-30, 400))
         t = ctx.timings()
         it = max(t.persist_iters, 1)
-        print(json.dumps(dict(op="dpcg persistent", n=n, cells=nc, l2_keep=keep, iters=rep.iters, us_per_iteration=1e3 * t.solve_ms / it,
+        print(json.dumps(dict(op="dpcg persistent", n=n, cells=nc, knob="l2_keep" if key == lib.TUNE_L2_KEEP else "dpcg_fused", value=keep, iters=rep.iters, us_per_iteration=1e3 * t.solve_ms / it,
                               gbs=(12 * nnz + 116 * nc) / (t.solve_ms / it) / 1e6,
                               p_update_us=1e3 * t.persist_pupdate_ms / it, spmv_us=1e3 * t.persist_spmv_ms / it,
                               update_us=1e3 * t.persist_update_ms / it,
@@ -80,7 +81,52 @@ def l2(n):
     ctx.close()
 
 
+def faces(n):
+    """Assembly times for every register budget of the face kernels (FC_TUNE_FACE_OCC)."""
+    import torch
+    m, ctx = setup(n)
+    nc, F, B = m.numCells, m.numInnerFaces, m.numFaces - m.numInnerFaces
+    ctx.upload("VIS", np.full(m.numTotal, 0.01))
+    ctx.fill("FLMASS", 0.0)
+    stream = torch.cuda.ExternalStream(ctx.lib.fc_stream(ctx.h), device=torch.device("cuda", 0))
+    po = lib.calcp_opts(solver="dpcg", const_mflux=True, sor=1e-8, nsw=100000)
+    uo = lib.calcuvw_opts(scheme="muscl-f", bdf=True, timestep=1e-2)
+    grad_b = 64 * F + 64 * nc + 36 * B
+
+    def timed(fn, r=10):
+        fn(); ctx.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(r):
+            fn()
+        e1.record(stream)
+        ctx.synchronize(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / r
+    ref = None
+    for occ in (2, 3, 4, 2, 3):
+        ctx.set_tuning(lib.TUNE_FACE_OCC, occ)
+        tp = timed(lambda: ctx.calcp_assemble(po))
+        out = [ctx.download(k) for k in ("A", "SU", "FLMASS")]
+        tu = timed(lambda: ctx.calcuvw_assemble(uo))
+        out += [ctx.download(k) for k in ("A", "SU", "SV", "SW")]
+        if ref is None:
+            ref = out
+        same = all(np.array_equal(a, b) for a, b in zip(ref, out))
+        bp = 3 * grad_b + 96 * F + 208 * nc + 16 * F
+        bu = 5 * grad_b + (120 * F + 160 * nc) + (184 * F + 88 * nc)
+        print(json.dumps(dict(op="assembly", n=n, face_occ=occ, calcp_assemble_ms=tp, calcp_gbs=bp / tp / 1e6,
+                              calcuvw_assemble_ms=tu, calcuvw_gbs=bu / tu / 1e6, bit_identical=bool(same))), flush=True)
+    ctx.close()
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     for n in [int(x) for x in sys.argv[2:]]:
-        (sweeps if what == "sweeps" else l2)(n)
+        if what == "sweeps":
+            sweeps(n)
+        elif what == "faces":
+            faces(n)
+        elif what == "fused":
+            l2(n, lib.TUNE_DPCG_FUSED)
+        else:
+            l2(n)
