@@ -188,7 +188,7 @@ struct fc_context {
   int tune_sweep_p2p = 0;               // triangular sweeps: 1 = point-to-point block flags instead of level counters
   int first_batch[3] = {8, 8, 8};       // per solver: iterations enqueued before the first look at `done`
   int tune_dpcg_fused = 0;              // persistent DPCG: fused-p scheme (0 never [default: measured slower, profiles/r02_fused_p.txt], 1 always, 2 on partitioned meshes)
-  int tune_face_occ = 2;                // face kernels of calcp / calcuvw: CTAs per SM their registers must allow (2, 3, 4)
+  int tune_face_occ = 3;                // k_calcp_faces: CTAs per SM its registers must allow (2: 102 registers, 3: 80, 4: 64 + spills)
   int tune_l2_keep = 2;                 // persistent DPCG: Krylov vectors evict_last in L2 (0 off, 1 on, 2 when they fit)
   int tune_fused_grad = 1;              // 1: the three velocity gradients of calcuvw / calcp in one kernel per pass
   int tune_sweep_check = 0;             // debugging: every tiled sweep is repeated with the level schedule and compared

@@ -122,9 +122,9 @@ int fc_calcuvw_assemble_dev(fc_context *ctx, const fc_calcuvw_opts *o) {
   const fcm_opts fo = opts_of(o);
   const fcm_faces fa = faces_of(ctx);
   if (ctx->F > 0) {
-    if (ctx->tune_face_occ >= 4) k_uvw_faces<4><<<fc_blocks(ctx->F, B), B, 0, st>>>(g, f, fo, fa);
-    else if (ctx->tune_face_occ == 3) k_uvw_faces<3><<<fc_blocks(ctx->F, B), B, 0, st>>>(g, f, fo, fa);
-    else k_uvw_faces<2><<<fc_blocks(ctx->F, B), B, 0, st>>>(g, f, fo, fa);
+    // 128 registers, two CTAs per SM: tighter budgets spill and were measured slower (4.97 / 5.03 / 5.75 ms at 216^3
+    // for 2 / 3 / 4 CTAs per SM, profiles/r02_face_occ.jsonl)
+    k_uvw_faces<2><<<fc_blocks(ctx->F, B), B, 0, st>>>(g, f, fo, fa);
     FC_LAUNCH_CHECK();
   }
   double **fl = ctx->field;

@@ -362,8 +362,9 @@ enum {
                                   iteration, bit-identical iterates): [0] never, 1 always, 2 on partitioned meshes.
                                   Measured slower than the three-phase kernel at every size (the second gather per
                                   non-zero costs what the phase saved), so it stays an option                   */
-  FC_TUNE_FACE_OCC = 11,       /* face kernels of calcp / calcuvw: CTAs of 256 threads per SM the register allocation
-                                  must allow, [2], 3 or 4 (they are bound by the latency of their gathers)      */
+  FC_TUNE_FACE_OCC = 11,       /* face kernel of calcp: CTAs of 256 threads per SM the register allocation must
+                                  allow, 2, [3] or 4 (it is bound by the latency of its ~55 gathers per face;
+                                  calcp assembly at 216^3: 2.72 / 2.45 / 2.84 ms)                               */
   FC_TUNE_L2_KEEP = 9,         /* persistent DPCG kernel: pk, zk, res, a_ii marked L2 evict_last (the matrix
                                   stream is evict_first): 0 never, 1 always, [2] when the four vectors fit  */
   FC_TUNE_TILE_CTAS = 7,       /* tiled sweeps: CTAs per SM the kernel's registers allow, [2] or 3           */
