@@ -20,14 +20,32 @@ struct fcp_hbya {
   double btime, timestep;
   int cn, lbuoy, boussinesq;
   double beta, tref, densit, gravx, gravy, gravz;
+  // several ranks (src-parallel/get_rAU_x_UEqnH.f90): processor-face terms with the CURRENT apr (momentum coefficients
+  // in the first corrector, the pressure equation's afterwards).  The reference writes them to su for ALL THREE
+  // components (`su(ijp) = su(ijp) - apr(i)*v(ijn)` in the v and w blocks too); restated as written.
+  const double *apr;
+  int npro;
 };
 
+// One component.  `s` = its own source so far; `*su` = the u source, which also collects the processor-face terms of
+// this component (for the u component the caller passes su = &s's storage, see fcp_hbya_row).
 FCM_HD double fcp_hbya_component(const fcm_geom &g, const fcm_c2f &m, const fcp_hbya &k, int c, double s,
-                                 const double *phi, const double *phio) {
+                                 const double *phi, const double *phio, double *su, bool is_u) {
   const int qs = m.off[c], qe = m.off[c + 1];
   if (k.cn) {
     for (int q = qs; q < qe; ++q)
       if ((m.face[q] & 0x7fffffff) < g.F) s = s - k.h[m.pos[q]] * phio[m.other[q]];
+    if (k.npro > 0) {
+      double t = is_u ? s : *su;
+      for (int q = qs; q < qe; ++q) {
+        const int fc = m.face[q] & 0x7fffffff, ijn = m.other[q];
+        if (fc >= g.F && ijn < g.n + k.npro) {
+          t = t - k.apr[ijn - g.n] * phio[ijn];
+          t = t + k.apr[ijn - g.n] * phio[c];
+        }
+      }
+      if (is_u) s = t; else *su = t;
+    }
     const double apotime = k.den[c] * g.vol[c] / k.timestep;
     double sum = 0.0;
     for (int p = k.ioffset[c]; p < k.ioffset[c + 1]; ++p) sum = sum + k.h[p];
@@ -36,6 +54,14 @@ FCM_HD double fcp_hbya_component(const fcm_geom &g, const fcm_c2f &m, const fcp_
   }
   for (int q = qs; q < qe; ++q)
     if ((m.face[q] & 0x7fffffff) < g.F) s = s - k.h[m.pos[q]] * phi[m.other[q]];
+  if (k.npro > 0) {
+    double t = is_u ? s : *su;
+    for (int q = qs; q < qe; ++q) {
+      const int fc = m.face[q] & 0x7fffffff, ijn = m.other[q];
+      if (fc >= g.F && ijn < g.n + k.npro) t = t - k.apr[ijn - g.n] * phi[ijn];
+    }
+    if (is_u) s = t; else *su = t;
+  }
   return s;
 }
 
@@ -62,9 +88,10 @@ FCM_HD void fcp_hbya_row(const fcm_geom &g, const fcm_c2f &m, const fcp_hbya &k,
     }
     su = su + sut; sv = sv + svt; sw = sw + swt;
   }
-  k.su[c] = fcp_hbya_component(g, m, k, c, su, k.u, k.uo);
-  k.sv[c] = fcp_hbya_component(g, m, k, c, sv, k.v, k.vo);
-  k.sw[c] = fcp_hbya_component(g, m, k, c, sw, k.w, k.wo);
+  su = fcp_hbya_component(g, m, k, c, su, k.u, k.uo, &su, true);
+  k.sv[c] = fcp_hbya_component(g, m, k, c, sv, k.v, k.vo, &su, false);
+  k.sw[c] = fcp_hbya_component(g, m, k, c, sw, k.w, k.wo, &su, false);
+  k.su[c] = su;
 }
 
 // u(1:numCells) = apu*su ...   (get_rAU_x_UEqnH.f90:203-205) -- a separate pass: the H sums read the old field

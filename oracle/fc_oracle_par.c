@@ -364,7 +364,7 @@ static void par_grad_field(fco_rank *R, int nr, int which_phi, int which_grad, i
   double **phi = (double **)malloc(sizeof(double *) * (size_t)nr), **gr = (double **)malloc(sizeof(double *) * (size_t)nr);
   FOR_RANKS {
     fco_fields *f = &R[r].f;
-    phi[r] = which_phi == 0 ? f->u : which_phi == 1 ? f->v : which_phi == 2 ? f->w : f->pp;
+    phi[r] = which_phi == 0 ? f->u : which_phi == 1 ? f->v : which_phi == 2 ? f->w : which_phi == 4 ? f->p : f->pp;
     gr[r] = which_grad == 0 ? f->dUdxi : which_grad == 1 ? f->dVdxi : which_grad == 2 ? f->dWdxi : f->dPdxi;
   }
   if (nigrad > 0) fco_par_grad_gauss(R, nr, phi, nigrad, gr);
@@ -372,7 +372,8 @@ static void par_grad_field(fco_rank *R, int nr, int which_phi, int which_grad, i
   free(phi); free(gr);
 }
 
-void fco_par_calcp_assemble(fco_rank *R, int nr, const fco_calcp_opts *o) {
+/* `proc_variant`: flux routine of the processor faces -- 1 facefluxmass2 (calcp :113), 2 facefluxmass_piso (PISO :187) */
+static void par_calcp_assemble_v(fco_rank *R, int nr, const fco_calcp_opts *o, int proc_variant) {
   FOR_RANKS {
     for (int k = 0; k < R[r].m.nnz; ++k) R[r].f.a[k] = 0.0;
     for (int i = 0; i < R[r].g.npro; ++i) R[r].apr[i] = 0.0;
@@ -400,7 +401,7 @@ void fco_par_calcp_assemble(fco_rank *R, int nr, const fco_calcp_opts *o) {
     for (int i = 1; i <= g->npro; ++i) { /* :107-128: facefluxmass2 on processor faces */
       int iface = g->iProcFacesStart + i, ijp = A1(g->owner, iface), ijn = g->numCells + i;
       double cap, can;
-      fco_facefluxmass(g, f, 1, ijp, ijn, A1(g->xf, iface), A1(g->yf, iface), A1(g->zf, iface), A1(g->arx, iface),
+      fco_facefluxmass(g, f, proc_variant, ijp, ijn, A1(g->xf, iface), A1(g->yf, iface), A1(g->zf, iface), A1(g->arx, iface),
                        A1(g->ary, iface), A1(g->arz, iface), A1(g->fpro, i), &cap, &can, &A1(R[r].fmpro, i));
       A1(R[r].apr, i) = can;
       A1(f->a, A1(m->diag, ijp)) = A1(f->a, A1(m->diag, ijp)) - can;
@@ -416,6 +417,25 @@ void fco_par_calcp_assemble(fco_rank *R, int nr, const fco_calcp_opts *o) {
       }
     }
     par_outlet(R, nr, o->flomas, o->sol.small, 1, 1);
+  }
+}
+
+void fco_par_calcp_assemble(fco_rank *R, int nr, const fco_calcp_opts *o) { par_calcp_assemble_v(R, nr, o, 1); }
+
+/* correctBoundaryConditionsVelocity of src-parallel: outlet extrapolation scaled with the LOCAL outflow, symmetry */
+static void par_correct_bc_velocity(fco_rank *R, int nr, double flomas, double small) {
+  par_outlet(R, nr, flomas, small, 0, 0);
+  FOR_RANKS {
+    const fco_mesh *g = &R[r].g;
+    fco_fields *f = &R[r].f;
+    const int iSymmetryStart = g->numCells + g->npro + g->ninl + g->nout;
+    for (int i = 1; i <= g->nsym; ++i) {
+      int iface = g->iSymmetryFacesStart + i, ijp = A1(g->owner, iface), ijb = iSymmetryStart + i;
+      double Unmag = A1(f->u, ijp) * A1(g->arx, iface) + A1(f->v, ijp) * A1(g->ary, iface) + A1(f->w, ijp) * A1(g->arz, iface);
+      A1(f->u, ijb) = A1(f->u, ijp) - Unmag * A1(g->arx, iface);
+      A1(f->v, ijb) = A1(f->v, ijp) - Unmag * A1(g->ary, iface);
+      A1(f->w, ijb) = A1(f->w, ijp) - Unmag * A1(g->arz, iface);
+    }
   }
 }
 
@@ -541,3 +561,4 @@ int fco_par_calcp(fco_rank *R, int nr, const fco_calcp_opts *o, fco_calcp_report
 }
 
 #include "fc_oracle_par_uvw.c"
+#include "fc_oracle_par_piso.c"

@@ -126,3 +126,17 @@ class ParCase:
         rc = O.lib().fco_par_calcuvw(self.R, self.nr, self.X, C.byref(opts), C.byref(rep))
         assert rc == 0, rc
         return rep
+
+    # ---- PISO / PIMPLE on several ranks (fc_oracle_par_piso.c) ----
+    def piso(self, opts: "O.FcoPisoOpts") -> "O.FcoPisoReport":
+        """src-parallel/PISO_multiple_correction.f90 (PIMPLE with opts.pimple); uvw_fields() must have been called and
+        fields[r].a must hold the momentum matrix calcuvw left behind (apr[r] its processor coefficients)."""
+        rep = O.FcoPisoReport()
+        hs = [np.zeros(c.nnz) for c in self.csr]
+        rc = O.lib().fco_par_piso(self.R, self.nr, self.X, C.byref(opts), self._ptrs(hs), C.byref(rep))
+        assert rc == 0, rc
+        return rep
+
+    def get_rAU_x_UEqnH(self, opts: "O.FcoPisoOpts", hs: List[np.ndarray]) -> None:
+        """src-parallel/get_rAU_x_UEqnH.f90 on every rank; hs[r] = the backed-up momentum matrix of rank r."""
+        O.lib().fco_par_get_rAU_x_UEqnH(self.R, self.nr, self.X, C.byref(opts), self._ptrs(hs))

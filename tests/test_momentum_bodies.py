@@ -72,7 +72,8 @@ class Hbya(C.Structure):
     _fields_ = [("ioffset", ip), ("diag", ip)] + [(k, dp) for k in (
         "h", "u", "v", "w", "uo", "vo", "wo", "uoo", "voo", "woo", "t", "den", "su", "sv", "sw")] + [
         ("bdf", C.c_int), ("btime", C.c_double), ("timestep", C.c_double), ("cn", C.c_int), ("lbuoy", C.c_int),
-        ("boussinesq", C.c_int)] + [(k, C.c_double) for k in ("beta", "tref", "densit", "gravx", "gravy", "gravz")]
+        ("boussinesq", C.c_int)] + [(k, C.c_double) for k in ("beta", "tref", "densit", "gravx", "gravy", "gravz")] + [
+        ("apr", dp), ("npro", C.c_int)]
 
 
 @pytest.fixture(scope="module")
@@ -288,12 +289,65 @@ def test_hbya_body_equals_oracle(host, name, kw):
     den = np.ascontiguousarray(of.den)
     K = Hbya(i32(L["ioffset"]), i32(L["diag"]), d(h), d(u), d(v), d(w), d(x.uo), d(x.vo), d(x.wo), d(x.uoo), d(x.voo),
              d(x.woo), d(x.t), d(den), d(su), d(sv), d(sw), po.bdf, po.btime, po.timestep, po.cn, po.lbuoy,
-             po.boussinesq, po.beta, po.tref, po.densit, po.gravx, po.gravy, po.gravz)
+             po.boussinesq, po.beta, po.tref, po.densit, po.gravx, po.gravy, po.gravz, None, 0)
     apu, apv, apw = (np.ascontiguousarray(a[:n]) for a in (of.apu, of.apv, of.apw))
     host.fcp_host_hbya(C.byref(G), C.byref(Mp), C.byref(K), d(apu), d(apv), d(apw), d(u), d(v), d(w))
     oracle.get_rAU_x_UEqnH(mesh, csr, of, x, po, h)
     for got, ref in ((su, of.su), (sv, x.sv), (sw, x.sw), (u, of.u), (v, of.v), (w, of.w)):
         assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("kw", [dict(bdf=True, btime=1.0, timestep=0.01), dict(bdf=True, cn=True, timestep=0.02),
+                                dict(bdf=True, btime=1.0, timestep=0.01, lbuoy=True, beta=0.3, tref=0.1, densit=1.1,
+                                     grav=(0.1, -9.81, 0.2))])
+@pytest.mark.parametrize("name", ["skew", "poly"])
+def test_hbya_body_on_a_partitioned_mesh_equals_the_lock_step_oracle(host, name, kw):
+    """src-parallel/get_rAU_x_UEqnH.f90: processor-face terms with apr, all three components' terms landing in su."""
+    from freecappuccino_b200 import mesh as M
+    from oracle import oracle_par
+    g = MESHES[name]()
+    nr = 3
+    parts = M.partition(g, M.rcb_ranks(g, nr) if name == "poly" else M.slab_ranks(g.numCells, nr), nr)
+    rng = np.random.default_rng(12)
+    pc = oracle_par.ParCase(parts)
+    xs = pc.uvw_fields(0.01)
+    po = oracle.piso_opts(**kw)
+    hs, devs = [], []
+    for r, mesh in enumerate(parts):
+        nt, n = mesh.numTotal, mesh.numCells
+        fr = pc.fields[r]
+        for k in ("u", "v", "w", "den"):
+            getattr(fr, k)[:] = rng.standard_normal(nt) if k != "den" else 1.0 + 0.1 * rng.random(nt)
+        for k in ("uo", "vo", "wo", "uoo", "voo", "woo", "t"):
+            getattr(xs[r], k)[:] = rng.standard_normal(nt)
+        xs[r].apu[:], xs[r].apv[:], xs[r].apw[:] = (rng.random(n + mesh.npro) + 0.5 for _ in range(3))
+        pc.apr[r][:] = rng.standard_normal(pc.apr[r].size)
+        hs.append(rng.standard_normal(pc.csr[r].nnz))
+    for r, mesh in enumerate(parts):
+        n, F = mesh.numCells, mesh.numInnerFaces
+        fr, x, csr = pc.fields[r], xs[r], pc.csr[r]
+        L = device_layout(mesh, csr)
+        geo = {k: np.ascontiguousarray(getattr(mesh, k), dtype=np.float64) for k in
+               ("xc", "yc", "zc", "vol", "arx", "ary", "arz", "xf", "yf", "zf", "facint")}
+        G = Geom(i32(L["owner"]), i32(L["neigh"]), *[d(geo[k]) for k in ("xc", "yc", "zc", "vol", "arx", "ary", "arz",
+                                                                        "xf", "yf", "zf", "facint")], n, F)
+        Mp = C2f(i32(L["off"]), i32(L["face"]), i32(L["other"]), i32(L["pos"]))
+        u, v, w = fr.u.copy(), fr.v.copy(), fr.w.copy()
+        su, sv, sw = np.zeros(n), np.zeros(n), np.zeros(n)
+        den = np.ascontiguousarray(fr.den)
+        apr = np.ascontiguousarray(pc.apr[r])
+        K = Hbya(i32(L["ioffset"]), i32(L["diag"]), d(hs[r]), d(u), d(v), d(w), d(x.uo), d(x.vo), d(x.wo), d(x.uoo),
+                 d(x.voo), d(x.woo), d(x.t), d(den), d(su), d(sv), d(sw), po.bdf, po.btime, po.timestep, po.cn, po.lbuoy,
+                 po.boussinesq, po.beta, po.tref, po.densit, po.gravx, po.gravy, po.gravz, d(apr), mesh.npro)
+        apu, apv, apw = (np.ascontiguousarray(a[:n]) for a in (x.apu, x.apv, x.apw))
+        host.fcp_host_hbya(C.byref(G), C.byref(Mp), C.byref(K), d(apu), d(apv), d(apw), d(u), d(v), d(w))
+        devs.append((su, sv, sw, u, v, w))
+    pc.get_rAU_x_UEqnH(po, hs)
+    for r in range(nr):
+        fr, x = pc.fields[r], xs[r]
+        n = parts[r].numCells
+        for got, ref, nm in zip(devs[r], (fr.su, x.sv, x.sw, fr.u, fr.v, fr.w), ("su", "sv", "sw", "u", "v", "w")):
+            assert np.array_equal(got[:n], ref[:n]), (r, nm)
 
 
 def test_piso_tail_bodies(host):
