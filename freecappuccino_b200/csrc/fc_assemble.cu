@@ -211,15 +211,17 @@ k_laplacian_faces(geom_t g, const double *__restrict__ mu, double *__restrict__ 
   coef[i] = (fxp * mu[ijp] + fxn * mu[ijn]) * smdpn;
 }
 
-// processor-boundary faces (src-parallel/calcp :107-128): facefluxmass2 with the halo cell as neighbour
+// processor-boundary faces with the halo cell as neighbour: facefluxmass2 in calcp (src-parallel/calcp :107-128,
+// VARIANT 1), facefluxmass_piso in PISO / PIMPLE (src-parallel/PISO_multiple_correction.f90:181-202, VARIANT 2)
+template <int VARIANT>
 __global__ void __launch_bounds__(256)
 k_calcp_proc_faces(geom_t g, flow_t f, double *__restrict__ apr, double *__restrict__ fmpro) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.npro) return;
   const int fc = g.pface0 + i;
   double cap, fl;
-  facefluxmass<1>(g, f, g.owner[fc], g.n + i, g.xf[fc], g.yf[fc], g.zf[fc], g.arx[fc], g.ary[fc], g.arz[fc], g.fpro[i],
-                  cap, fl);
+  facefluxmass<VARIANT>(g, f, g.owner[fc], g.n + i, g.xf[fc], g.yf[fc], g.zf[fc], g.arx[fc], g.ary[fc], g.arz[fc], g.fpro[i],
+                        cap, fl);
   apr[i] = cap;
   fmpro[i] = fl;
 }
@@ -615,8 +617,12 @@ int fc_calcp_assemble_dev(fc_context *ctx, const fc_calcp_opts *o) {
     FC_LAUNCH_CHECK();
   }
   if (ctx->npro > 0) {
-    k_calcp_proc_faces<<<fc_blocks(ctx->npro, B), B, 0, ctx->stream>>>(geom_of(ctx), flow_of(ctx), ctx->field[FC_APR],
-                                                                       ctx->field[FC_FMPRO]);
+    if (o->flux_variant == 2)
+      k_calcp_proc_faces<2><<<fc_blocks(ctx->npro, B), B, 0, ctx->stream>>>(geom_of(ctx), flow_of(ctx), ctx->field[FC_APR],
+                                                                            ctx->field[FC_FMPRO]);
+    else
+      k_calcp_proc_faces<1><<<fc_blocks(ctx->npro, B), B, 0, ctx->stream>>>(geom_of(ctx), flow_of(ctx), ctx->field[FC_APR],
+                                                                            ctx->field[FC_FMPRO]);
     FC_LAUNCH_CHECK();
   }
   if (!o->const_mflux) FC_CHECK(outlet_extrapolate_and_scale(ctx, o->flomas, o->sol.small, true));  // adjustMassFlow
@@ -793,6 +799,7 @@ int piso_continuity(fc_context *ctx, fc_piso_report *rep) {   // continuityError
                                                              ctx->field[FC_FMI], ctx->field[FC_FMO], ctx->field[FC_RES],
                                                              ctx->partials, ctx->sc);
   FC_LAUNCH_CHECK();
+  FC_CHECK(fc_allreduce_scalars(ctx, ctx->sc->red, 2));   // global_sum of src-parallel's continuityErrors.h (no-op on one rank)
   FC_CUDA(cudaMemcpyAsync(ctx->sc_host, ctx->sc, sizeof(fc_scalars), cudaMemcpyDeviceToHost, ctx->stream));
   FC_CUDA(cudaStreamSynchronize(ctx->stream));
   rep->sumLocalContErr = ctx->sc_host->red[0];
@@ -800,15 +807,26 @@ int piso_continuity(fc_context *ctx, fc_piso_report *rep) {   // continuityError
   return FC_OK;
 }
 
+// p(inp) = urf(ip)*pp(inp) + (1-urf(ip))*p(inp)   (src-parallel/PIMPLE_multiple_correction.f90:92)
+__global__ void __launch_bounds__(256) k_relax_p_par(int n, double urf, const double *pp, double *p) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) p[c] = urf * pp[c] + (1.0 - urf) * p[c];
+}
+
 }  // namespace
 
 int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep) {
   FC_CHECK(need_mesh(ctx, "fc_piso"));
-  if (ctx->npro > 0 || ctx->nranks > 1)
-    FC_FAIL(FC_ERR_UNSUPPORTED, "fc_piso: one rank in this version (src-parallel/PISO_multiple_correction.f90 "
-                                "processor faces are not ported yet)");
+  // Several ranks = src-parallel/PISO_multiple_correction.f90 / PIMPLE_multiple_correction.f90: processor faces with
+  // facefluxmass_piso, the reference pressure pinned on rank 0 only (iPrefProcess = 0, read_input.f90:316; su = p(pRefCell)
+  // in both variants), flux correction and continuity report once after the npcor loop, PIMPLE's relaxation written as
+  // urf*pp + (1-urf)*p, u, v, w, p exchanged once at the end, get_rAU_x_UEqnH with the processor terms of the parallel
+  // routine (fc_piso_body.cuh).
+  const bool par = ctx->nranks > 1;
+  if (ctx->npro > 0 && !ctx->comm) FC_FAIL(FC_ERR_ARG, "fc_piso: processor faces without fc_comm_init");
   if (o->ncorr < 1 || o->npcor < 1 || o->nigrad < 1 || o->nipgrad < 0) FC_FAIL(FC_ERR_ARG, "fc_piso: bad corrector counts");
-  if (o->pRefCell < 1 || o->pRefCell > ctx->n) FC_FAIL(FC_ERR_ARG, "fc_piso: pRefCell out of range");
+  if ((!par || ctx->rank == 0) && (o->pRefCell < 1 || o->pRefCell > ctx->n))
+    FC_FAIL(FC_ERR_ARG, "fc_piso: pRefCell out of range (with several ranks it is a cell of rank 0)");
   if ((o->bdf || o->cn) && !(o->timestep > 0.0)) FC_FAIL(FC_ERR_ARG, "fc_piso: timestep must be > 0");
   FC_CHECK(fc_momentum_fields(ctx));
   if (!ctx->hcoef) FC_CHECK(fc_dev_alloc(ctx, &ctx->hcoef, (size_t)ctx->nnz + 2));
@@ -823,6 +841,8 @@ int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep) {
   co.npcor = 1; co.nigrad = o->nigrad; co.nipgrad = o->nipgrad; co.pRefCell = o->pRefCell;
   co.flux_variant = 2;   // facefluxmass_piso
   co.const_mflux = o->const_mflux; co.flomas = o->flomas; co.sol = o->sol;
+  fc_solver_opts so = o->sol;
+  if (par) { co.sol.parallel = 1; so.parallel = 1; }   // the parallel iccg (`+small`, rank-local DIC, exchange(pp) at exit)
   rep->nsolves = 0;
   rep->sumLocalContErr = rep->globalContErr = 0.0;
   double solve_ms = 0.0;
@@ -830,7 +850,7 @@ int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep) {
     const fcp_hbya hk{ctx->ioffset, ctx->diag, ctx->hcoef, fl[FC_U], fl[FC_V], fl[FC_W], fl[FC_UO], fl[FC_VO],
                       fl[FC_WO], fl[FC_UOO], fl[FC_VOO], fl[FC_WOO], fl[FC_T], fl[FC_DEN], fl[FC_SU], fl[FC_SV],
                       fl[FC_SW], o->bdf, o->btime, o->timestep, o->cn, o->lbuoy, o->boussinesq, o->beta, o->tref,
-                      o->densit, o->gravx, o->gravy, o->gravz};
+                      o->densit, o->gravx, o->gravy, o->gravz, fl[FC_APR], ctx->npro};
     k_hbya_rows<<<fc_blocks(n, B), B, 0, st>>>(g, m, hk);                                     // get_rAU_x_UEqnH
     FC_LAUNCH_CHECK();
     k_hbya_scale<<<fc_blocks(n, B), B, 0, st>>>(n, fl[FC_APU], fl[FC_APV], fl[FC_APW], fl[FC_SU], fl[FC_SV],
@@ -838,15 +858,17 @@ int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep) {
     FC_LAUNCH_CHECK();
     // grad(U,V,W); a = 0; su = 0; facefluxmass_piso face loop; adjustMassFlow   (PISO :104-181)
     FC_CHECK(fc_calcp_assemble_dev(ctx, &co));
-    k_pin_row<<<1, 1, 0, st>>>(ctx->ioffset, ctx->diag, fl[FC_A], fl[FC_SU], o->pimple ? fl[FC_PP] : fl[FC_P],
-                               o->pRefCell - 1);                                              // :188-192
-    FC_LAUNCH_CHECK();
+    if (!par || ctx->rank == 0) {
+      k_pin_row<<<1, 1, 0, st>>>(ctx->ioffset, ctx->diag, fl[FC_A], fl[FC_SU], (o->pimple && !par) ? fl[FC_PP] : fl[FC_P],
+                                 o->pRefCell - 1);                                            // :188-192
+      FC_LAUNCH_CHECK();
+    }
     for (int ipcorr = 1; ipcorr <= o->npcor; ++ipcorr) {
       fc_solver_report *r = &rep->rep[rep->nsolves < 16 ? rep->nsolves : 15];
-      FC_CHECK(fc_solve_device(ctx, FC_ICCG, fl[FC_PP], &o->sol, r, nullptr));                // call iccg(pp,ip)
+      FC_CHECK(fc_solve_device(ctx, FC_ICCG, fl[FC_PP], &so, r, nullptr));                    // call iccg(pp,ip)
       solve_ms += ctx->tm.solve_ms;
       rep->nsolves++;
-      if (!o->pimple) {
+      if (!o->pimple && !par) {
         if (ipcorr == o->npcor && ctx->F > 0) {
           k_flux_correct_matrix<<<fc_blocks(ctx->F, B), B, 0, st>>>(g, ctx->icj, fl[FC_A], fl[FC_PP], fl[FC_FLMASS]);
           FC_LAUNCH_CHECK();
@@ -854,13 +876,20 @@ int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep) {
         FC_CHECK(piso_continuity(ctx, rep));
       }
     }
-    if (o->pimple) {
+    if (o->pimple || par) {   // one flux correction and one continuity report after the npcor loop
       if (ctx->F > 0) {
         k_flux_correct_matrix<<<fc_blocks(ctx->F, B), B, 0, st>>>(g, ctx->icj, fl[FC_A], fl[FC_PP], fl[FC_FLMASS]);
         FC_LAUNCH_CHECK();
       }
+      if (ctx->npro > 0) {    // fmpro(i) += apr(i)*(pp(halo) - pp(owner)); iccg left pp's halo current
+        k_fmpro_correct<<<fc_blocks(ctx->npro, B), B, 0, st>>>(geom_of(ctx), fl[FC_APR], fl[FC_PP], fl[FC_FMPRO]);
+        FC_LAUNCH_CHECK();
+      }
       FC_CHECK(piso_continuity(ctx, rep));
-      k_relax_p<<<fc_blocks(n, B), B, 0, st>>>(n, o->urf_p, fl[FC_PP], fl[FC_P]);
+    }
+    if (o->pimple) {
+      if (par) k_relax_p_par<<<fc_blocks(n, B), B, 0, st>>>(n, o->urf_p, fl[FC_PP], fl[FC_P]);
+      else k_relax_p<<<fc_blocks(n, B), B, 0, st>>>(n, o->urf_p, fl[FC_PP], fl[FC_P]);
       FC_LAUNCH_CHECK();
     } else {
       FC_CUDA(cudaMemcpyAsync(fl[FC_P], fl[FC_PP], sizeof(double) * (size_t)ctx->NT, cudaMemcpyDeviceToDevice, st));  // p = pp
@@ -880,6 +909,8 @@ int fc_piso_dev(fc_context *ctx, const fc_piso_opts *o, fc_piso_report *rep) {
       FC_LAUNCH_CHECK();
     }
   }
+  if (ctx->npro > 0)   // src-parallel/PISO_multiple_correction.f90:383-386
+    for (int fld : {FC_U, FC_V, FC_W, FC_P}) FC_CHECK(fc_halo_exchange(ctx, fl[fld]));
   FC_CUDA(cudaStreamSynchronize(st));
   ctx->tm.solve_ms = solve_ms;
   return FC_OK;

@@ -181,6 +181,15 @@ def main():
         got.update({k: ctx.download(k.upper()) for k in ("u", "v", "w", "apu")})
         got["iters"] = [rep.rep[k].iters for k in range(3)]
         got["res0"] = [rep.rep[k].res0 for k in range(3)]
+        # ---- PISO / PIMPLE on the state calcuvw left behind (src-parallel/PISO_multiple_correction.f90; fc_piso with
+        #      processor faces); pRefCell is a cell of rank 0 ----
+        _, flomas = cases.inlet_fluxes(g, f)
+        pkw = dict(ncorr=2, npcor=1, pRefCell=3, flomas=flomas, bdf=True, btime=1.0, timestep=0.05, sor=1e-12, nsw=600)
+        for tag_p, pimple in (("piso", False), ("pimple", True)):
+            rp = ctx.piso(lib.piso_opts(pimple=pimple, urf_p=0.8, **pkw))
+            got[tag_p] = {k: ctx.download(k.upper()) for k in ("u", "v", "w", "p", "pp", "flmass", "fmpro")}
+            got[tag_p]["iters"] = [rp.rep[k].iters for k in range(rp.nsolves)]
+            got[tag_p]["cont"] = (rp.sumLocalContErr, rp.globalContErr)
         ctx.close()
         box = [None] * world
         dist.all_gather_object(box, got)
@@ -220,6 +229,29 @@ def main():
                         failures.append(f"{tag}: rank {r} field {k} rel L2 {e:.2e}")
             print(f"[mgpu] {'p2p' if p2p else 'nccl'} {tag}: iters {box[0]['iters']} (oracle "
                   f"{[rep_o.rep[k].iters for k in range(3)]}) worst field rel L2 {worst:.2e}", flush=True)
+            for tag_p, pimple in (("piso", False), ("pimple", True)):
+                rp_o = pc.piso(O.piso_opts(pimple=pimple, urf_p=0.8, **pkw))
+                tag = f"{mesh_name}/{tag_p}"
+                its_o = [rp_o.rep[k].iters for k in range(rp_o.nsolves)]
+                if len(its_o) != len(box[0][tag_p]["iters"]) or any(abs(a - b) > 1 for a, b in zip(box[0][tag_p]["iters"], its_o)):
+                    failures.append(f"{tag}: iterations {box[0][tag_p]['iters']} vs oracle {its_o}")
+                worst = 0.0
+                for r, m in enumerate(parts):
+                    nn = m.numCells + m.npro
+                    for k, ref in (("u", pc.fields[r].u[:nn]), ("v", pc.fields[r].v[:nn]), ("w", pc.fields[r].w[:nn]),
+                                   ("p", pc.fields[r].p[:nn]), ("pp", pc.fields[r].pp[:nn]), ("flmass", pc.fields[r].flmass),
+                                   ("fmpro", pc.fmpro[r][:m.npro])):
+                        if ref.size == 0:
+                            continue
+                        e = cases.rel_l2(box[r][tag_p][k][:ref.size], ref)
+                        worst = max(worst, e)
+                        if e > 1e-10:
+                            failures.append(f"{tag}: rank {r} field {k} rel L2 {e:.2e}")
+                c0 = box[0][tag_p]["cont"][0]
+                if abs(c0 - rp_o.sumLocalContErr) > 1e-6 * abs(rp_o.sumLocalContErr) + 1e-13:
+                    failures.append(f"{tag}: sumLocalContErr {c0} vs {rp_o.sumLocalContErr}")
+                print(f"[mgpu] {'p2p' if p2p else 'nccl'} {tag}: iters {box[0][tag_p]['iters']} (oracle {its_o}) "
+                      f"worst field rel L2 {worst:.2e}", flush=True)
     ok = [not failures]
     dist.broadcast_object_list(ok, src=0)
     if rank == 0:
