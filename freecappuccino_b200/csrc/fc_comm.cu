@@ -104,6 +104,14 @@ int fc_allreduce_scalars(fc_context *ctx, double *dev, int count) {
   return FC_OK;
 }
 
+// element-wise maximum over the ranks (global_max of src-parallel; a minimum travels negated)
+int fc_allreduce_max(fc_context *ctx, double *dev, int count) {
+  if (ctx->nranks == 1) return FC_OK;
+  if (!ctx->comm) FC_FAIL(FC_ERR_ARG, "all-reduce needs fc_comm_init");
+  FC_NCCL(ncclAllReduce(dev, dev, (size_t)count, ncclDouble, ncclMax, ctx->comm, ctx->stream));
+  return FC_OK;
+}
+
 extern "C" int fc_comm_unique_id(char id128[128]) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
   ncclUniqueId id;

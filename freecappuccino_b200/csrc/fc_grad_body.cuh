@@ -118,7 +118,9 @@ FCM_HD double fcg_lapy2(double x, double y) {
 
 // matrix stage (grad_lsq_qr.f90:62-247): D(3,6,numCells) = R1^-1 Q1^T.  Returns 1 when the cell does not have
 // exactly six neighbours (the routine is not defined for it; its D is zeroed).
-FCM_HD int fcg_lsq_qr_matrix_row(const fcm_geom &g, const fcm_c2f &m, double *D, int c) {
+// `npro`: processor faces of a partitioned mesh count as cell neighbours (the halo cell n + i;
+// src-parallel/grad_lsq_qr.f90:55-64), in the position the cell-to-face map gives them: after the inner faces.
+FCM_HD int fcg_lsq_qr_matrix_row(const fcm_geom &g, const fcm_c2f &m, double *D, int c, int npro = 0) {
   double *Dc = D + 18 * (size_t)c;
   const int qs = m.off[c], qe = m.off[c + 1];
   if (qe - qs != 6) {
@@ -128,7 +130,7 @@ FCM_HD int fcg_lsq_qr_matrix_row(const fcm_geom &g, const fcm_c2f &m, double *D,
   double A[18], tau[3];   // column-major 6 x 3: A[j*6 + r]
   for (int r = 0; r < 6; ++r) {
     const int q = qs + r, fe = m.face[q], fc = fe & 0x7fffffff;
-    if (fc < g.F) {
+    if (fc < g.F || m.other[q] < g.n + npro) {
       const int o = m.other[q];
       A[r] = g.xc[o] - g.xc[c]; A[6 + r] = g.yc[o] - g.yc[c]; A[12 + r] = g.zc[o] - g.zc[c];
     } else {
@@ -220,6 +222,53 @@ FCM_HD void fcg_limiter_row(const fcm_geom &g, const int *ioffset, const int *ja
       const double deltam = cell_neighbour_value - phi_p;
       double deltap;
       if (deltam > 0.0) deltap = phi_max - phi_p; else deltap = phi_min - phi_p;
+      const double epsi = 0.05 * (glomax - glomin);
+      const double val = 1.0 / (deltam + small) * ((deltap * deltap + epsi * epsi) * deltam + 2 * (deltam * deltam) * deltap) /
+                         (deltap * deltap + 2 * (deltam * deltam) + deltap * deltam + epsi * epsi + small);
+      slopelimit = FCM_MAX2(FCM_MIN2(slopelimit, val), 0.0);
+    } else {
+      double r;
+      if (fabs(gradfiXdr) < (double)1.e-6f) r = 1.0;
+      else if (gradfiXdr > 0.0) r = deltamax / gradfiXdr;
+      else r = deltamin / gradfiXdr;
+      if (which == 1) slopelimit = FCM_MIN2(slopelimit, r);
+      else slopelimit = FCM_MIN2(slopelimit, (r * r + 2.0 * r) / (r * r + r + 2.0));
+    }
+  }
+  FCM_G3(grad, 0, c) = slopelimit * gx;
+  FCM_G3(grad, 1, c) = slopelimit * gy;
+  FCM_G3(grad, 2, c) = slopelimit * gz;
+}
+
+// The limiters of src-parallel/gradients.f90 (glomin / glomax already reduced over the ranks).  Barth-Jespersen and
+// Venkatakrishnan are the serial loops; the modified Venkatakrishnan limiter of the parallel build takes phimax / phimin
+// from set_phi_min_max -- the cell, its inner-face neighbours and its processor-face neighbours, true min and max (order
+// independent, so the walk over the cell-to-face map gives the reference's values exactly).
+FCM_HD void fcg_limiter_row_par(const fcm_geom &g, const fcm_c2f &m, int npro, const int *ioffset, const int *ja,
+                                const int *diag, int which, const double *phi, double *grad, double glomin,
+                                double glomax, double small, int c) {
+  const double phi_p = phi[c];
+  double phimax = phi_p, phimin = phi_p;
+  if (which == 3)
+    for (int q = m.off[c]; q < m.off[c + 1]; ++q) {
+      const int fc = m.face[q] & 0x7fffffff, o = m.other[q];
+      if (fc < g.F || o < g.n + npro) {
+        phimax = FCM_MAX2(phimax, phi[o]);
+        phimin = FCM_MIN2(phimin, phi[o]);
+      }
+    }
+  const double deltamax = glomax - phi[c], deltamin = glomin - phi[c];
+  const double gx = FCM_G3(grad, 0, c), gy = FCM_G3(grad, 1, c), gz = FCM_G3(grad, 2, c);
+  double slopelimit = 1.0;
+  for (int k = ioffset[c]; k < ioffset[c + 1]; ++k) {
+    if (k == diag[c]) continue;
+    const int ijn = ja[k];
+    const double gradfiXdr = gx * (g.xc[ijn] - g.xc[c]) + gy * (g.yc[ijn] - g.yc[c]) + gz * (g.zc[ijn] - g.zc[c]);
+    if (which == 3) {
+      const double cell_neighbour_value = phi_p + gradfiXdr;
+      const double deltam = cell_neighbour_value - phi_p;
+      double deltap;
+      if (deltam > 0.0) deltap = phimax - phi_p; else deltap = phimin - phi_p;
       const double epsi = 0.05 * (glomax - glomin);
       const double val = 1.0 / (deltam + small) * ((deltap * deltap + epsi * epsi) * deltam + 2 * (deltam * deltam) * deltap) /
                          (deltap * deltap + 2 * (deltam * deltam) + deltap * deltam + epsi * epsi + small);

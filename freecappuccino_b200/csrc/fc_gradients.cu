@@ -27,9 +27,9 @@ k_grad_lsq(fcm_geom g, fcm_c2f m, fcm_slots sl, int weighted, const double *dmat
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < g.n) fcg_grad_lsq_row(g, m, sl, weighted, dmat, fi, out, c);
 }
-__global__ void __launch_bounds__(128) k_lsq_qr_matrix(fcm_geom g, fcm_c2f m, double *D, int *bad) {
+__global__ void __launch_bounds__(128) k_lsq_qr_matrix(fcm_geom g, fcm_c2f m, double *D, int *bad, int npro) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < g.n && fcg_lsq_qr_matrix_row(g, m, D, c)) atomicAdd(bad, 1);
+  if (c < g.n && fcg_lsq_qr_matrix_row(g, m, D, c, npro)) atomicAdd(bad, 1);
 }
 __global__ void __launch_bounds__(256)
 k_grad_lsq_qr(fcm_geom g, fcm_c2f m, const double *D, const double *fi, double *out) {
@@ -79,6 +79,14 @@ k_limiter(fcm_geom g, const int *ioffset, const int *ja, const int *diag, int wh
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < g.n) fcg_limiter_row(g, ioffset, ja, diag, which, phi, grad, minmax[0], minmax[1], small, c);
 }
+// several ranks: minmax = {-glomin, glomax} after the all-reduce (one ncclMax covers both)
+__global__ void __launch_bounds__(256)
+k_limiter_par(fcm_geom g, fcm_c2f m, int npro, const int *ioffset, const int *ja, const int *diag, int which,
+              const double *phi, double *grad, const double *minmax, double small) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < g.n) fcg_limiter_row_par(g, m, npro, ioffset, ja, diag, which, phi, grad, -minmax[0], minmax[1], small, c);
+}
+__global__ void k_negate_first(double *v) { v[0] = -v[0]; }
 
 }  // namespace
 
@@ -90,6 +98,16 @@ int fc_limit_gradient_dev(fc_context *ctx, const double *phi, double *grad) {
   FC_LAUNCH_CHECK();
   k_minmax_final<<<1, 1, 0, ctx->stream>>>(nb, ctx->partials, &ctx->sc->aux[0]);
   FC_LAUNCH_CHECK();
+  if (ctx->nranks > 1) {   // src-parallel/gradients.f90: global_min / global_max, then the parallel build's limiters
+    k_negate_first<<<1, 1, 0, ctx->stream>>>(&ctx->sc->aux[0]);
+    FC_LAUNCH_CHECK();
+    FC_CHECK(fc_allreduce_max(ctx, &ctx->sc->aux[0], 2));
+    k_limiter_par<<<fc_blocks(ctx->n, 256), 256, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), ctx->npro, ctx->ioffset,
+                                                                   ctx->ja, ctx->diag, ctx->grad_limiter, phi, grad,
+                                                                   &ctx->sc->aux[0], ctx->grad_small);
+    FC_LAUNCH_CHECK();
+    return FC_OK;
+  }
   k_limiter<<<fc_blocks(ctx->n, 256), 256, 0, ctx->stream>>>(fcm_geom_of(ctx), ctx->ioffset, ctx->ja, ctx->diag,
                                                              ctx->grad_limiter, phi, grad, &ctx->sc->aux[0],
                                                              ctx->grad_small);
@@ -97,12 +115,14 @@ int fc_limit_gradient_dev(fc_context *ctx, const double *phi, double *grad) {
   return FC_OK;
 }
 
-// grad(phi,dPhidxi) (gradients.f90:95-151)
+// grad(phi,dPhidxi) (gradients.f90:95-151; several ranks: src-parallel/gradients.f90:95-160 -- exchange(phi) first, the
+// three gradient components exchanged after the limiter)
 int fc_grad_dev(fc_context *ctx, double *phi, double *grad, int nigrad) {
   if (ctx->grad_method == 0) {
-    FC_CHECK(fc_grad_gauss_dev(ctx, phi, grad, nigrad));
+    FC_CHECK(fc_grad_gauss_dev(ctx, phi, grad, nigrad));   // exchanges phi before and the gradient after
   } else {
     if (!ctx->has_mesh || !ctx->c2f_off) FC_FAIL(FC_ERR_ARG, "fc_grad: call fc_set_mesh and fc_create_csr first");
+    if (ctx->npro > 0) FC_CHECK(fc_halo_exchange(ctx, phi));
     const int B = 256, G = fc_blocks(ctx->n, B);
     if (ctx->grad_method == 2)
       k_grad_lsq_qr<<<G, B, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), ctx->dmatqr, phi, grad);
@@ -111,7 +131,9 @@ int fc_grad_dev(fc_context *ctx, double *phi, double *grad, int nigrad) {
                                            ctx->dmat, phi, grad);
     FC_LAUNCH_CHECK();
   }
-  return fc_limit_gradient_dev(ctx, phi, grad);
+  FC_CHECK(fc_limit_gradient_dev(ctx, phi, grad));
+  if (ctx->npro > 0 && (ctx->grad_method != 0 || ctx->grad_limiter != 0)) FC_CHECK(fc_halo_exchange3(ctx, grad));
+  return FC_OK;
 }
 
 // grad(U), grad(V), grad(W) as calcuvw (:59-61) and calcp (:38-40) ask for them, optionally followed by the first stage
@@ -169,8 +191,9 @@ int fc_set_gradient_dev(fc_context *ctx, int method, int limiter, double small) 
   if (method != 0 || limiter != 0) {
     if (!ctx->has_mesh || !ctx->has_csr || !ctx->c2f_off)
       FC_FAIL(FC_ERR_ARG, "fc_set_gradient: call fc_set_mesh and fc_create_csr first");
-    if (ctx->npro > 0 || ctx->nranks > 1)
-      FC_FAIL(FC_ERR_UNSUPPORTED, "fc_set_gradient: least-squares gradients / limiters run on one rank in this version");
+    if ((ctx->npro > 0 || ctx->nranks > 1) && (method == 1 || method == 3))
+      FC_FAIL(FC_ERR_UNSUPPORTED, "fc_set_gradient: lstsq / lstsq_dm run on one rank in this version (on several ranks: "
+                                  "gauss or lstsq_qr, with any limiter)");
   }
   const int B = 256, G = fc_blocks(ctx->n, B);
   if (method == 1 || method == 3) {
@@ -182,7 +205,8 @@ int fc_set_gradient_dev(fc_context *ctx, int method, int limiter, double small) 
     int *bad = nullptr, host_bad = 0;
     FC_CUDA(cudaMalloc((void **)&bad, sizeof(int)));
     FC_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
-    k_lsq_qr_matrix<<<fc_blocks(ctx->n, 128), 128, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), ctx->dmatqr, bad);
+    k_lsq_qr_matrix<<<fc_blocks(ctx->n, 128), 128, 0, ctx->stream>>>(fcm_geom_of(ctx), fcm_c2f_of(ctx), ctx->dmatqr, bad,
+                                                                     ctx->npro);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(&host_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);

@@ -277,6 +277,7 @@ int fc_strip_build(fc_context *ctx);
 int fc_p2p_pack(fc_context *ctx, double *x);                          // fc_p2p.cu: halo of pk / zk by peer stores
 void fc_p2p_close(fc_context *ctx);                                 // fc_csr.cu: per-row processor faces
 int fc_allreduce_scalars(fc_context *ctx, double *dev, int count);
+int fc_allreduce_max(fc_context *ctx, double *dev, int count);   // element-wise maximum over the ranks
 int fc_dpcg_persistent(fc_context *ctx, double *fi, const fc_solver_opts *o, fc_solver_report *rep, double *hist,
                        bool *handled);                                                   // fc_dpcg_persist.cu
 int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opts *o, fc_solver_report *rep,

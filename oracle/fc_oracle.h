@@ -198,6 +198,8 @@ void fco_grad_lsq(const fco_mesh *g, int weighted, const double *dmat, const dou
 int  fco_lsq_qr_matrix(const fco_mesh *g, double *D);
 void fco_grad_lsq_qr(const fco_mesh *g, const double *D, const double *fi, double *dFidxi);
 void fco_slope_limiter(const fco_mesh *g, const fco_csr *m, int which, const double *phi, double *dPhidxi, double small);
+void fco_slope_limiter_par(const fco_mesh *g, const fco_csr *m, int which, const double *phi, double *dPhidxi, double small,
+                           double glomin, double glomax);
 /* process-wide gradient configuration used by fco_grad and, through it, by calcp / calcuvw / piso (NULL = gauss) */
 void fco_set_gradient(const fco_gradient_cfg *c);
 void fco_grad(const fco_mesh *g, const fco_csr *m, const double *phi, int nigrad, double *dPhidxi);

@@ -185,6 +185,10 @@ int fco_lsq_qr_matrix(const fco_mesh *g, double *D) {
     PUT(ijp, A1(g->xc, ijn) - A1(g->xc, ijp), A1(g->yc, ijn) - A1(g->yc, ijp), A1(g->zc, ijn) - A1(g->zc, ijp));
     PUT(ijn, A1(g->xc, ijp) - A1(g->xc, ijn), A1(g->yc, ijp) - A1(g->yc, ijn), A1(g->zc, ijp) - A1(g->zc, ijn));
   }
+  for (int i = 1; i <= g->npro; ++i) { /* src-parallel/grad_lsq_qr.f90: the halo cell as neighbour, owner side only */
+    int ijp = A1(g->owner, g->iProcFacesStart + i), ijn = g->numCells + i;
+    PUT(ijp, A1(g->xc, ijn) - A1(g->xc, ijp), A1(g->yc, ijn) - A1(g->yc, ijp), A1(g->zc, ijn) - A1(g->zc, ijp));
+  }
   int cnt[5], fst[5], sst[5];
   boundary_tables(g, cnt, fst, sst);
   for (int k = 0; k < 5; ++k)
@@ -241,6 +245,10 @@ void fco_grad_lsq_qr(const fco_mesh *g, const double *D, const double *fi, doubl
     int ijp = A1(g->owner, i), ijn = A1(g->neighbour, i);
     PUTB(ijp, A1(fi, ijn) - A1(fi, ijp));
     PUTB(ijn, A1(fi, ijp) - A1(fi, ijn));
+  }
+  for (int i = 1; i <= g->npro; ++i) {
+    int ijp = A1(g->owner, g->iProcFacesStart + i), ijn = g->numCells + i;
+    PUTB(ijp, A1(fi, ijn) - A1(fi, ijp));
   }
   int cnt[5], fst[5], sst[5];
   boundary_tables(g, cnt, fst, sst);
@@ -305,6 +313,63 @@ void fco_slope_limiter(const fco_mesh *g, const fco_csr *m, int which, const dou
     G3(dPhidxi, 1, inp) = slopelimit * G3(dPhidxi, 1, inp);
     G3(dPhidxi, 2, inp) = slopelimit * G3(dPhidxi, 2, inp);
   }
+}
+
+/* Limiters of src-parallel/gradients.f90 on one rank: glomin / glomax arrive already reduced over the ranks
+ * (global_min / global_max).  Barth-Jespersen and Venkatakrishnan are the serial loops (CSR neighbours only, the
+ * unused phi_max / phi_min included); the modified Venkatakrishnan limiter of the parallel build takes the cell's
+ * phimax / phimin from set_phi_min_max -- inner faces and processor faces, true min and max -- instead of the serial
+ * routine's phi_min = min(phi_max, ...). */
+void fco_slope_limiter_par(const fco_mesh *g, const fco_csr *m, int which, const double *phi, double *dPhidxi, double small,
+                           double glomin, double glomax) {
+  const int n = g->numCells;
+  const double epsprim = 0.05;
+  double *phimax = (double *)malloc(sizeof(double) * (size_t)(n + 1)), *phimin = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+  for (int i = 1; i <= n; ++i) { phimax[i] = A1(phi, i); phimin[i] = A1(phi, i); }
+  for (int i = 1; i <= g->numInnerFaces; ++i) {
+    int ijp = A1(g->owner, i), ijn = A1(g->neighbour, i);
+    phimax[ijp] = FCO_MAX2(phimax[ijp], A1(phi, ijn));
+    phimax[ijn] = FCO_MAX2(phimax[ijn], A1(phi, ijp));
+    phimin[ijp] = FCO_MIN2(phimin[ijp], A1(phi, ijn));
+    phimin[ijn] = FCO_MIN2(phimin[ijn], A1(phi, ijp));
+  }
+  for (int i = 1; i <= g->npro; ++i) {
+    int ijp = A1(g->owner, g->iProcFacesStart + i), ijn = n + i;
+    phimax[ijp] = FCO_MAX2(phimax[ijp], A1(phi, ijn));
+    phimin[ijp] = FCO_MIN2(phimin[ijp], A1(phi, ijn));
+  }
+  for (int inp = 1; inp <= n; ++inp) {
+    double phi_p = A1(phi, inp);
+    double deltamax = glomax - A1(phi, inp), deltamin = glomin - A1(phi, inp);
+    double slopelimit = 1.0;
+    for (int k = A1(m->ioffset, inp); k <= A1(m->ioffset, inp + 1) - 1; ++k) {
+      if (k == A1(m->diag, inp)) continue;
+      int ijn = A1(m->ja, k);
+      double gradfiXdr = G3(dPhidxi, 0, inp) * (A1(g->xc, ijn) - A1(g->xc, inp)) +
+                         G3(dPhidxi, 1, inp) * (A1(g->yc, ijn) - A1(g->yc, inp)) +
+                         G3(dPhidxi, 2, inp) * (A1(g->zc, ijn) - A1(g->zc, inp));
+      if (which == 3) {
+        double cell_neighbour_value = phi_p + gradfiXdr;
+        double deltam = cell_neighbour_value - phi_p, deltap;
+        if (deltam > 0.0) deltap = phimax[inp] - phi_p; else deltap = phimin[inp] - phi_p;
+        double epsi = epsprim * (glomax - glomin);
+        double val = 1.0 / (deltam + small) * ((deltap * deltap + epsi * epsi) * deltam + 2 * (deltam * deltam) * deltap) /
+                     (deltap * deltap + 2 * (deltam * deltam) + deltap * deltam + epsi * epsi + small);
+        slopelimit = FCO_MAX2(FCO_MIN2(slopelimit, val), 0.0);
+      } else {
+        double r;
+        if (fabs(gradfiXdr) < (double)1.e-6f) r = 1.0;
+        else if (gradfiXdr > 0.0) r = deltamax / gradfiXdr;
+        else r = deltamin / gradfiXdr;
+        if (which == 1) slopelimit = FCO_MIN2(slopelimit, r);
+        else slopelimit = FCO_MIN2(slopelimit, (r * r + 2.0 * r) / (r * r + r + 2.0));
+      }
+    }
+    G3(dPhidxi, 0, inp) = slopelimit * G3(dPhidxi, 0, inp);
+    G3(dPhidxi, 1, inp) = slopelimit * G3(dPhidxi, 1, inp);
+    G3(dPhidxi, 2, inp) = slopelimit * G3(dPhidxi, 2, inp);
+  }
+  free(phimax); free(phimin);
 }
 
 /* ---- the dispatcher `grad(phi,dPhidxi)` (gradients.f90:95-151) with a process-wide configuration ---- */

@@ -155,6 +155,45 @@ void fco_par_laplacian(fco_rank *R, int nr, double **mu, double **phi) {
   }
 }
 
+/* `grad(phi,dPhidxi)` of src-parallel/gradients.f90:95-160 with the dispatcher's options: exchange(phi); the scheme
+ * (0 gauss with `nigrad` passes, 2 lstsq_qr with the per-rank matrices Dqr[r] of fco_lsq_qr_matrix); the limiter with
+ * glomin / glomax reduced over the ranks; exchange of the three gradient components.  (lstsq / lstsq_dm of the parallel
+ * build are not restated: rc 2.) */
+int fco_par_grad(fco_rank *R, int nr, int method, int limiter, double small, double **Dqr, double **phi, int nigrad,
+                 double **grad) {
+  if (method != 0 && method != 2) return 2;
+  if (method == 0) {
+    fco_par_grad_gauss(R, nr, phi, nigrad, grad);   /* exchanges phi before and the gradient after */
+  } else {
+    fco_par_exchange(R, nr, phi, 1);
+    PAR_RANKS for (int r = 0; r < nr; ++r) {
+      memset(grad[r], 0, sizeof(double) * 3 * (size_t)(R[r].g.numCells + R[r].g.npro));
+      fco_grad_lsq_qr(&R[r].g, Dqr[r], phi[r], grad[r]);
+    }
+  }
+  if (limiter) {
+    double glomin = 0.0, glomax = 0.0;
+    for (int r = 0; r < nr; ++r) {   /* minval / maxval(phi(1:numCells)), then global_min / global_max */
+      const int n = R[r].g.numCells;
+      double lo = phi[r][0], hi = phi[r][0];
+      for (int i = 1; i < n; ++i) { if (phi[r][i] < lo) lo = phi[r][i]; if (phi[r][i] > hi) hi = phi[r][i]; }
+      if (r == 0 || lo < glomin) glomin = lo;
+      if (r == 0 || hi > glomax) glomax = hi;
+    }
+    PAR_RANKS for (int r = 0; r < nr; ++r)
+      fco_slope_limiter_par(&R[r].g, &R[r].m, limiter, phi[r], grad[r], small, glomin, glomax);
+  }
+  if (method != 0 || limiter) {
+    double **comp = (double **)malloc(sizeof(double *) * (size_t)nr);
+    for (int c = 0; c < 3; ++c) {
+      for (int r = 0; r < nr; ++r) comp[r] = grad[r] + c;
+      fco_par_exchange(R, nr, comp, 3);
+    }
+    free(comp);
+  }
+  return 0;
+}
+
 /* ---- Krylov solvers in lock step: src-parallel/dpcg.f90, iccg.f90, bicgstab.f90 ---- */
 typedef struct { double *pk, *zk, *d, *reso, *uk, *vk; fco_strips st; int *pown; } par_scratch;
 
@@ -360,6 +399,31 @@ static void par_outlet(fco_rank *R, int nr, double flomas, double small, int add
   free(part);
 }
 
+/* the `grad` options of the input file for the lock-step routines (fco_par_set_gradient): method 0 gauss / 2 lstsq_qr,
+ * limiter 0..3; the QR matrices are built per rank and kept until the next call */
+static struct { int method, limiter, nr; double small; double **Dqr; } g_par_grad = {0, 0, 0, 0.0, 0};
+int fco_par_grad(fco_rank *R, int nr, int method, int limiter, double small, double **Dqr, double **phi, int nigrad,
+                 double **grad);
+int fco_par_set_gradient(fco_rank *R, int nr, int method, int limiter, double small) {
+  if (g_par_grad.Dqr) {
+    for (int r = 0; r < g_par_grad.nr; ++r) free(g_par_grad.Dqr[r]);
+    free(g_par_grad.Dqr);
+    g_par_grad.Dqr = 0;
+  }
+  g_par_grad.method = method; g_par_grad.limiter = limiter; g_par_grad.small = small; g_par_grad.nr = nr;
+  if (method != 0 && method != 2) return 2;
+  if (method == 2) {
+    g_par_grad.Dqr = (double **)malloc(sizeof(double *) * (size_t)nr);
+    int bad = 0;
+    for (int r = 0; r < nr; ++r) {
+      g_par_grad.Dqr[r] = (double *)malloc(sizeof(double) * 18 * (size_t)R[r].g.numCells);
+      bad += fco_lsq_qr_matrix(&R[r].g, g_par_grad.Dqr[r]);
+    }
+    if (bad) return 3;
+  }
+  return 0;
+}
+
 static void par_grad_field(fco_rank *R, int nr, int which_phi, int which_grad, int nigrad) {
   double **phi = (double **)malloc(sizeof(double *) * (size_t)nr), **gr = (double **)malloc(sizeof(double *) * (size_t)nr);
   FOR_RANKS {
@@ -367,7 +431,9 @@ static void par_grad_field(fco_rank *R, int nr, int which_phi, int which_grad, i
     phi[r] = which_phi == 0 ? f->u : which_phi == 1 ? f->v : which_phi == 2 ? f->w : which_phi == 4 ? f->p : f->pp;
     gr[r] = which_grad == 0 ? f->dUdxi : which_grad == 1 ? f->dVdxi : which_grad == 2 ? f->dWdxi : f->dPdxi;
   }
-  if (nigrad > 0) fco_par_grad_gauss(R, nr, phi, nigrad, gr);
+  if (nigrad > 0 && (g_par_grad.method != 0 || g_par_grad.limiter != 0) && g_par_grad.nr == nr)
+    fco_par_grad(R, nr, g_par_grad.method, g_par_grad.limiter, g_par_grad.small, g_par_grad.Dqr, phi, nigrad, gr);
+  else if (nigrad > 0) fco_par_grad_gauss(R, nr, phi, nigrad, gr);
   else fco_par_grad_gauss_corrected(R, nr, phi, gr);
   free(phi); free(gr);
 }

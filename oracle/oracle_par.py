@@ -140,3 +140,30 @@ class ParCase:
     def get_rAU_x_UEqnH(self, opts: "O.FcoPisoOpts", hs: List[np.ndarray]) -> None:
         """src-parallel/get_rAU_x_UEqnH.f90 on every rank; hs[r] = the backed-up momentum matrix of rank r."""
         O.lib().fco_par_get_rAU_x_UEqnH(self.R, self.nr, self.X, C.byref(opts), self._ptrs(hs))
+
+    # ---- the `grad` dispatcher on several ranks (src-parallel/gradients.f90:95-160) ----
+    def grad(self, phis: List[np.ndarray], method: str = "gauss", limiter: str = "no-limit", nigrad: int = 1,
+             small: float = O.SMALL) -> List[np.ndarray]:
+        """gauss or lstsq_qr (+ optional limiter) of every rank's field; returns the (numCells+npro, 3) gradients with
+        current halos."""
+        mth, lim = O.GRAD_METHODS[method], O.LIMITERS[limiter]
+        Ds = [np.zeros(1) for _ in self.meshes]
+        if mth == 2:
+            Ds = []
+            for m in self.meshes:
+                ms = O.mesh_struct(m)
+                D = np.zeros(18 * m.numCells)
+                bad = O.lib().fco_lsq_qr_matrix(C.byref(ms), O._d(D))
+                assert bad == 0, f"{bad} cells without exactly 6 neighbours"
+                Ds.append(D)
+        out = [np.zeros((m.numCells + m.npro, 3)) for m in self.meshes]
+        rc = O.lib().fco_par_grad(self.R, self.nr, mth, lim, C.c_double(small), self._ptrs(Ds), self._ptrs(phis), nigrad,
+                                  self._ptrs(out))
+        assert rc == 0, rc
+        return out
+
+    def set_gradient(self, method: str = "gauss", limiter: str = "no-limit", small: float = O.SMALL) -> None:
+        """The `grad` options (input file: lstsq_qr / gauss + limiter) used by calcp / piso / calcuvw of this case from
+        now on; call set_gradient() again with the defaults to switch back."""
+        rc = O.lib().fco_par_set_gradient(self.R, self.nr, O.GRAD_METHODS[method], O.LIMITERS[limiter], C.c_double(small))
+        assert rc == 0, rc

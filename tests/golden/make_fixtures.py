@@ -9,6 +9,10 @@ Run in the build container (needs /root/reference; the GPU box never runs this):
   cavity_par.npz  examples/cavity/cavity-setup-parallel.tar.gz: the reference's own 2-rank
                   decomposition (per-rank owner / neighbour / boundary / process files and
                   cell/faceProcAddressing) -- pins the partitioner's array layout.
+  pitzDaily_par_cells.npz  examples/pitzDaily/pitzDaily-setup-parallel.tar.gz: which rank owns every cell of the shipped
+                  2-rank decomposition (cellProcAddressing of both ranks -> cell_rank[12225]); freecappuccino_b200.mesh.
+                  partition(pitzDaily, cell_rank) then rebuilds that decomposition (as tests/test_partition.py proves for
+                  the cavity) -- the multi-rank lstsq_qr / limiter / PISO checks run on it.
 Only mesh INPUT data is stored (points, faces, owner, neighbour, boundary table).
 """
 import glob
@@ -78,6 +82,14 @@ def main():
             proc = [l.split() for l in open(os.path.join(d, "process")) if not l.startswith("#") and l.strip()]
             out[f"p{r}_process"] = np.array([[int(x) for x in row] for row in proc[1:]], dtype=np.int32)
         np.savez_compressed(os.path.join(HERE, "cavity_par.npz"), **out)
+    with tempfile.TemporaryDirectory() as t:
+        tarfile.open(os.path.join(REF, "pitzDaily", "pitzDaily-setup-parallel.tar.gz")).extractall(t)
+        cells = [labels(os.path.join(t, f"processor{r}", "constant", "polyMesh", "cellProcAddressing")) for r in (0, 1)]
+        rank = np.full(sum(c.size for c in cells), -1, dtype=np.int8)
+        for r, c in enumerate(cells):
+            rank[c] = r
+        assert (rank >= 0).all()
+        np.savez_compressed(os.path.join(HERE, "pitzDaily_par_cells.npz"), cell_rank=rank)
     for f in sorted(glob.glob(os.path.join(HERE, "*.npz"))):
         print(os.path.basename(f), os.path.getsize(f), "bytes")
 

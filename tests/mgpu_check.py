@@ -41,7 +41,7 @@ def main():
     failures = []
     # MGPU_SECTIONS: "core" = the pressure-correction path (verified on hardware), "momentum" = the multi-rank momentum
     # predictor (first hardware run pending); tests/test_gpu_multi.py and tests/test_gpu_zz1_multi_momentum.py run one each
-    sections = os.environ.get("MGPU_SECTIONS", "core,momentum").split(",")
+    sections = os.environ.get("MGPU_SECTIONS", "core,momentum,gradients").split(",")
     core_cases = (("hex_mixed", cases.hex_case(12, 9, 4 * world, kinds=("inlet", "outlet", "wall", "symmetry", "wall", "wall"))),
                   ("skew", cases.skew_case(9, 8, 3 * world + 2)),
                   # BASELINE config 5 at test size, cut by recursive coordinate bisection: several
@@ -252,6 +252,87 @@ def main():
                     failures.append(f"{tag}: sumLocalContErr {c0} vs {rp_o.sumLocalContErr}")
                 print(f"[mgpu] {'p2p' if p2p else 'nccl'} {tag}: iters {box[0][tag_p]['iters']} (oracle {its_o}) "
                       f"worst field rel L2 {worst:.2e}", flush=True)
+    # ---- the `grad` dispatcher on several ranks (src-parallel/gradients.f90:95-160): gauss / lstsq_qr with every limiter,
+    #      then calcp with pitzDaily's own settings (lstsq_qr + mVenkatakrishnan, iccg).  Two ranks run the reference's
+    #      SHIPPED pitzDaily decomposition (tests/golden/pitzDaily_par_cells.npz), other rank counts a hexahedral box
+    #      (lstsq_qr is defined for cells with exactly six neighbours) ----
+    if "gradients" in sections:
+        gold = os.path.join(ROOT, "tests", "golden")
+        if world == 2:
+            g = cases.golden_mesh(os.path.join(gold, "pitzDaily.npz"))
+            cell_rank = np.load(os.path.join(gold, "pitzDaily_par_cells.npz"))["cell_rank"].astype(np.int64)
+            mesh_name = "pitzDaily(shipped decomposition)"
+        else:
+            g = cases.hex_case(10, 9, 4 * world, kinds=("inlet", "outlet", "wall", "wall", "symmetry", "symmetry"))
+            cell_rank = M.slab_ranks(g.numCells, world)
+            mesh_name = "hex"
+        parts = M.partition(g, cell_rank, world)
+        part = parts[rank]
+        f = cases.flow_fields(g)
+        fmi, flomas = cases.inlet_fluxes(g, f)
+        gp = O.grad_gauss(g, f["p"], 1)
+        mine = scatter_case(g, part, f, fmi, gp)
+        ctx = lib.Context(local)
+        parallel.init_comm(ctx)
+        ctx.set_mesh(part)
+        ctx.create_csr()
+        p2p = parallel.enable_p2p(ctx)
+        combos = [(m, l) for m in ("gauss", "lstsq_qr") for l in ("no-limit", "Barth-Jespersen", "Venkatakrishnan",
+                                                                    "mVenkatakrishnan")]
+        got = {}
+        for method, limiter in combos:
+            ctx.set_gradient(method, limiter)
+            ctx.upload("USER0", mine["p"])
+            ctx.grad("USER0", "DPDXI", 1)
+            got[(method, limiter)] = ctx.download("DPDXI")
+        # calcp with the input file's options
+        ctx.set_gradient("lstsq_qr", "mVenkatakrishnan")
+        for k, name in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("apu", "APU"), ("apv", "APV"),
+                        ("apw", "APW"), ("dPdxi", "DPDXI")):
+            ctx.upload(name, mine[k])
+        if mine["fmi"].size:
+            ctx.upload("FMI", mine["fmi"])
+        ckw = dict(solver="iccg", flomas=flomas, npcor=1, nigrad=1, sor=1e-12, nsw=2000)
+        rep = ctx.calcp(lib.calcp_opts(parallel=True, **ckw))
+        got["calcp"] = {k: ctx.download(k.upper()) for k in ("u", "v", "w", "p", "pp", "flmass", "su")}
+        got["calcp"]["iters"] = rep.rep[0].iters
+        ctx.close()
+        box = [None] * world
+        dist.all_gather_object(box, got)
+        if rank == 0:
+            pc = OP.ParCase(parts)
+            phis = [scatter_case(g, m, f, fmi, gp)["p"] for m in parts]
+            for method, limiter in combos:
+                ref = pc.grad([p.copy() for p in phis], method, limiter)
+                bad = [r for r in range(world) if not np.array_equal(box[r][(method, limiter)].reshape(-1, 3)[:ref[r].shape[0]], ref[r])]
+                worst = max(cases.rel_l2(box[r][(method, limiter)].reshape(-1, 3)[:ref[r].shape[0]], ref[r]) for r in range(world))
+                if worst > 1e-12:
+                    failures.append(f"{mesh_name}/grad {method}+{limiter}: rel L2 {worst:.2e}")
+                print(f"[mgpu] {'p2p' if p2p else 'nccl'} {mesh_name}/grad {method}+{limiter}: "
+                      f"{'bit-identical' if not bad else 'not bit-identical on ranks ' + str(bad)}, worst rel L2 {worst:.2e}", flush=True)
+            for m, fl in zip(parts, pc.fields):
+                sc = scatter_case(g, m, f, fmi, gp)
+                for k in ("u", "v", "w", "p", "den", "apu", "apv", "apw", "dPdxi"):
+                    getattr(fl, k)[:] = sc[k]
+                fl.fmi[:sc["fmi"].size] = sc["fmi"]
+            pc.set_gradient("lstsq_qr", "mVenkatakrishnan")
+            oo = O.calcp_opts(**ckw)
+            oo.sol.parallel = 1
+            rep_o = pc.calcp(oo)
+            pc.set_gradient()
+            tag = f"{mesh_name}/calcp lstsq_qr+mVenkatakrishnan+iccg"
+            if abs(box[0]["calcp"]["iters"] - rep_o.rep[0].iters) > 1:
+                failures.append(f"{tag}: iterations {box[0]['calcp']['iters']} vs oracle {rep_o.rep[0].iters}")
+            worst = 0.0
+            for r in range(world):
+                for k in ("u", "v", "w", "p", "pp", "flmass", "su"):
+                    ref = getattr(pc.fields[r], k)
+                    e = cases.rel_l2(box[r]["calcp"][k][:ref.size], ref)
+                    worst = max(worst, e)
+                    if e > 1e-10:
+                        failures.append(f"{tag}: rank {r} field {k} rel L2 {e:.2e}")
+            print(f"[mgpu] {'p2p' if p2p else 'nccl'} {tag}: iters {box[0]['calcp']['iters']} (oracle {rep_o.rep[0].iters}) "
+                  f"worst field rel L2 {worst:.2e}", flush=True)
     ok = [not failures]
     dist.broadcast_object_list(ok, src=0)
     if rank == 0:

@@ -138,3 +138,64 @@ def test_simple_loop_with_lsq_qr_gradients_reproduces_ghia():
         oracle.set_gradient("gauss", "no-limit")
     assert err["lstsq_qr"] < 0.025
     assert err["lstsq"] > 0.05
+
+
+# ---- several ranks: the dispatcher of src-parallel/gradients.f90 (fco_par_grad) ----
+def _pitz_two_ranks():
+    import os
+    from freecappuccino_b200 import mesh as M
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    g = cases.golden_mesh(os.path.join(gold, "pitzDaily.npz"))
+    cr = np.load(os.path.join(gold, "pitzDaily_par_cells.npz"))["cell_rank"].astype(np.int64)
+    return g, M.partition(g, cr, 2)
+
+
+def _smooth(g):
+    n = g.numCells
+    x = np.zeros(g.numTotal)
+    from freecappuccino_b200 import mesh as M
+    x[:n] = np.sin(40 * g.xc[:n]) + 30 * g.yc[:n]
+    for k in M.KINDS:
+        fs, sl = g.boundary_faces(k), g.boundary_slots(k)
+        x[sl] = np.sin(40 * g.xf[fs]) + 30 * g.yf[fs]
+    return x
+
+
+def test_two_rank_lstsq_qr_gradient_is_the_serial_one():
+    """The shipped 2-rank pitzDaily decomposition: a cell next to the cut has the same six neighbours as in the serial
+    mesh (the halo cell instead of the remote one), only in another order -- the least-squares gradient is the same
+    up to round-off; the halo copies of the gradient are the neighbour rank's values."""
+    from freecappuccino_b200 import mesh as M
+    from oracle import oracle_par
+    g, parts = _pitz_two_ranks()
+    x = _smooth(g)
+    csr = oracle.create_csr(g)
+    D, bad = oracle.lsq_qr_matrix(g)
+    assert bad == 0
+    ref = oracle.grad_lsq_qr(g, D, x)
+    pc = oracle_par.ParCase(parts)
+    out = pc.grad([M.scatter_total(g, p, x) for p in parts], "lstsq_qr")
+    got = M.gather_cells(g, parts, [o[:p.numCells] for o, p in zip(out, parts)])
+    assert np.allclose(got, ref[:g.numCells], rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    for o, p in zip(out, parts):
+        assert np.allclose(o[p.numCells:], ref[p.halo_global], rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("limiter", ["Barth-Jespersen", "Venkatakrishnan", "mVenkatakrishnan"])
+def test_two_rank_limiters_only_shorten_the_gradient(limiter):
+    from freecappuccino_b200 import mesh as M
+    from oracle import oracle_par
+    g, parts = _pitz_two_ranks()
+    x = _smooth(g)
+    pc = oracle_par.ParCase(parts)
+    phis = [M.scatter_total(g, p, x) for p in parts]
+    free = pc.grad([p.copy() for p in phis], "gauss")
+    lim = pc.grad([p.copy() for p in phis], "gauss", limiter)
+    for a, b, p in zip(free, lim, parts):
+        n = p.numCells
+        na, nb_ = np.linalg.norm(a[:n], axis=1), np.linalg.norm(b[:n], axis=1)
+        assert np.all(nb_ <= na * (1 + 1e-12))
+        cos = np.einsum("ij,ij->i", a[:n], b[:n])
+        assert np.all(cos >= -1e-12 * na * na)          # same direction: a scalar factor in [0, 1]
+        if limiter == "mVenkatakrishnan":   # the other two compare with the GLOBAL extrema and rarely bite on a smooth field
+            assert np.any(nb_ < 0.999 * na)
