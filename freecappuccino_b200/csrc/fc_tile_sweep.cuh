@@ -262,8 +262,10 @@ FCT_UNROLL
 //     [start[l], start[l+1]), one pass of 64 threads on hexahedra, ~25 instructions per row, one CTA barrier per level.
 // Rows with more than PRE entries in their triangle (none on hexahedra with PRE = 4 or BCC polyhedra with PRE = 8) take
 // a slow path through global memory after the staged entries.
-// Shared layout (NS = FC_TILE slots): c[NS][PRE] | c2[NS][PRE] (DIC_PAR, DILU) | z[NS + 1] | di[NS] (FWD/BWD) |
-// dep[NS][PRE] (u16) | row[NS] | s[NS] | e[NS] | lev[NS] (short) | start[NS + 2] (short)
+// Shared layout (NS = FC_TILE slots): c[PRE][NS] | c2[PRE][NS] (DIC_PAR, DILU) | z[NS + 1] | di[NS] (FWD/BWD) |
+// dep[PRE][NS] (u16) | row[NS] | s[NS] | e[NS] | lev[NS] (short) | start[NS + 2] (short).  Entry q of all slots is
+// contiguous: the threads of a level read consecutive 8-byte words (a [slot][q] layout put them 8 PRE bytes apart:
+// 16-way bank conflicts with PRE = 8, measured 670 ns per level on the polyhedral mesh against 163 ns with PRE = 3)
 template <int MODE, int PRE>
 struct fct_walk_layout {
   static constexpr int NS = FC_TILE;
@@ -372,9 +374,9 @@ FCT_UNROLL
         if (MODE == TRI_DIC) c = c * c;
         else if (MODE == TRI_DIC_PAR) c2 = dep == ONE ? 1.0 : c;
         else if (MODE == TRI_DILU) c2 = dep == ONE ? 1.0 : tv[u][q];
-        s_c[slot * PRE + q] = c;
-        if (L::TWO) s_c2[slot * PRE + q] = c2;
-        s_dep[slot * PRE + q] = (unsigned short)dep;
+        s_c[q * NS + slot] = c;
+        if (L::TWO) s_c2[q * NS + slot] = c2;
+        s_dep[q * NS + slot] = (unsigned short)dep;
       }
     }
   }
@@ -422,9 +424,9 @@ FCT_UNROLL
         else if (MODE == TRI_DIC) c = (c * c) * zj;            // iccg.f90:80
         else if (MODE == TRI_DIC_PAR) c = c * zj * c;          // src-parallel/iccg.f90:97
         else c = c * zj * tv[u][q];                            // bicgstab.f90:76
-        s_c[slot * PRE + q] = c;
-        if (L::TWO) s_c2[slot * PRE + q] = 1.0;
-        s_dep[slot * PRE + q] = (unsigned short)ONE;
+        s_c[q * NS + slot] = c;
+        if (L::TWO) s_c2[q * NS + slot] = 1.0;
+        s_dep[q * NS + slot] = (unsigned short)ONE;
       }
     }
   }
@@ -441,8 +443,8 @@ FCT_UNROLL
       double v = s_z[slot];
 FCT_UNROLL
       for (int q = 0; q < PRE; ++q) {
-        double t = s_c[slot * PRE + q] * s_z[s_dep[slot * PRE + q]];
-        if (L::TWO) t = t * s_c2[slot * PRE + q];
+        double t = s_c[q * NS + slot] * s_z[s_dep[q * NS + slot]];
+        if (L::TWO) t = t * s_c2[q * NS + slot];
         v = v - t;
       }
       const int row = s_row[slot];

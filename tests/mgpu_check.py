@@ -63,10 +63,13 @@ def main():
             # (each rank evaluates fluxmc of a shared face from its own side and the formula is not
             # antisymmetric: sum(su) != 0), so its CG solve diverges in the reference algorithm itself.
             # The corrector path is therefore compared with both solves capped at 6 iterations.
-            # Tight solves (rsm < 1e-12; BiCGStab stagnates in round-off below ~1e-11) so that the fields can be held
-            # to the north star's 1e-10 relative L2: GPU and oracle differ only in the order of the inner-product sums.
+            # Tight solves (rsm < 1e-12) so that the fields can be held to the north star's 1e-10 relative L2: GPU and
+            # oracle differ only in the order of the inner-product sums.  BiCGStab stops at 1e-9: below ~1e-11 it stagnates
+            # in round-off for all 2000 sweeps, and 2000 chaotic iterations amplify the summation-order differences (8 ranks:
+            # 1e-8 in the fields with identical iteration counts, profiles/r02_mgpu_n8.log) -- that measures the solver's
+            # conditioning, not parity.
             kw = dict(solver=solver, flomas=flomas, npcor=npcor, lsq_flag=lsq, nigrad=nigrad,
-                      sor=float(os.environ.get("MGPU_SOR", "1e-11" if solver == "bicgstab" else "1e-12")),
+                      sor=float(os.environ.get("MGPU_SOR", "1e-9" if solver == "bicgstab" else "1e-12")),
                       nsw=6 if npcor > 1 else 2000,
                       flux_variant=1 if mesh_name == "poly" else 0)   # see test_config5_polyhedral_path
             ctx = lib.Context(local)

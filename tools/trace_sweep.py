@@ -7,14 +7,15 @@ sys.path.insert(0, ROOT)
 os.environ["FC_SWEEP_TRACE_FILE"] = os.path.join(ROOT, "gpurun_out", "sweep_trace.txt")
 from freecappuccino_b200 import cases, lib
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 216
-m = cases.hex_case(n, n, n)
+poly = len(sys.argv) > 3 and sys.argv[3] == "poly"
+m = cases.poly_case(n) if poly else cases.hex_case(n, n, n)
 f = cases.config4_fields(m)
 ctx = lib.Context(0)
 ctx.set_mesh(m); ctx.create_csr(download=False)
 for k, name in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("apu", "APU"), ("apv", "APV"), ("apw", "APW")):
     ctx.upload(name, f[k])
 ctx.grad_gauss("P", "DPDXI", 1)
-ctx.calcp_assemble(lib.calcp_opts(solver="dpcg", const_mflux=True, sor=1e-8, nsw=100000))
+ctx.calcp_assemble(lib.calcp_opts(solver="dpcg", const_mflux=True, sor=1e-8, nsw=100000, flux_variant=1 if poly else 0))
 mode = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 ctx.set_tuning(lib.TUNE_SWEEP_TILED, mode)
 ctx.fill("PP", 0.0)
