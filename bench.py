@@ -476,8 +476,9 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": "k_dpcg_persist<256,2304,2> (whole DPCG solve, one cooperative launch per step)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8000": achieved / 8000.0,
-                "traffic": (traffic["dram_bytes_per_iteration"] * iters_per_step) if traffic and world == 1 else None,
-                "traffic_source": traffic["source"] if traffic and world == 1 else None,
+                "traffic": (traffic["dram_bytes_per_iteration"] * iters_per_step)
+                if traffic and world == 1 and args.n == traffic.get("n", 216) else None,
+                "traffic_source": traffic["source"] if traffic and world == 1 and args.n == traffic.get("n", 216) else None,
                 "algorithmic_bytes_per_launch": ab["dpcg_iter"] * iters_per_step,
                 "algorithmic_bytes_per_iteration": ab["dpcg_iter"], "iterations_per_launch": iters_per_step,
                 "mean_launch_ms": launch_ms, "launches_timed": args.steps, "grid": persist["grid"],

@@ -440,14 +440,31 @@ FCT_UNROLL
   for (int l = 0; l < nl; ++l) {
     const int s0 = s_start[l], s1 = s_start[l + 1];
     for (int slot = s0 + tid; slot < s1; slot += WT) {
-      double v = s_z[slot];
+      // every shared-memory load of the row first (coefficients and dependency slots, then the values they name),
+      // then the products, then the left-to-right sum: only the PRE subtractions form a dependent chain.  (Written
+      // as one loop the PRE = 8 instantiation kept load -> load -> multiply -> subtract per entry in sequence:
+      // 670 ns per local level on the polyhedral mesh, profiles/r02_sweep_trace_summary.txt.)
+      double cq[PRE], zq[PRE], c2q[PRE];
+      int dq[PRE];
 FCT_UNROLL
       for (int q = 0; q < PRE; ++q) {
-        double t = s_c[q * NS + slot] * s_z[s_dep[q * NS + slot]];
-        if (L::TWO) t = t * s_c2[q * NS + slot];
-        v = v - t;
+        cq[q] = s_c[q * NS + slot];
+        dq[q] = s_dep[q * NS + slot];
+        if (L::TWO) c2q[q] = s_c2[q * NS + slot];
       }
+      double v = s_z[slot];
       const int row = s_row[slot];
+      __asm__ __volatile__("" ::: "memory");   // compiler-only fence: keep the first batch of loads together ...
+FCT_UNROLL
+      for (int q = 0; q < PRE; ++q) zq[q] = s_z[dq[q]];
+      __asm__ __volatile__("" ::: "memory");   // ... and the dependent batch ahead of the arithmetic
+FCT_UNROLL
+      for (int q = 0; q < PRE; ++q) {
+        cq[q] = cq[q] * zq[q];
+        if (L::TWO) cq[q] = cq[q] * c2q[q];
+      }
+FCT_UNROLL
+      for (int q = 0; q < PRE; ++q) v = v - cq[q];
       if (any_long) {                                              // rows longer than PRE (none on hex / BCC meshes)
         const int e = s_e[slot];
         for (int k = s_s[slot] + PRE; k < e; ++k) {

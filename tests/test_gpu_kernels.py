@@ -3,6 +3,8 @@ kernel, the persistent cooperative DPCG kernel vs one launch per vector operatio
 over-long rows, and -- at BASELINE's full 216^3 size -- size-independent properties that need no
 oracle run (symmetry of the assembled operator, the true residual of the converged solve).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -209,4 +211,73 @@ def test_full_size_216_properties(fc):
     r = su - ctx.download("SCRATCH_T")[:nc]
     assert rep.res0 == pytest.approx(np.abs(su).sum(), rel=1e-12)
     assert np.abs(r).sum() / rep.res0 < 1.05e-8
+    ctx.close()
+
+
+@pytest.mark.parametrize("solver", ["dpcg", "iccg"])
+def test_config3_full_size_poisson_against_the_oracle(fc, solver):
+    """BASELINE config 3 at its full size (100^3 Poisson, rsm < 1e-8, nsw = 10000): iteration count within +-1 of the
+    oracle's, solution within the solver tolerance, L-infinity error against sin(2 pi x) sin(2 pi y) second order.
+    (The oracle needs a few seconds per solver.)"""
+    from oracle import oracle
+    mesh = cases.hex_case(100, 100, 100, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry"))
+    n = mesh.numCells
+    csr = oracle.create_csr(mesh)
+    su = cases.poisson_rhs(mesh)
+    su_ref = su.copy()
+    a = oracle.laplacian(mesh, csr, -np.ones(n), np.zeros(mesh.numTotal), su_ref)
+    fi_ref = np.zeros(mesh.numTotal)
+    res0, resl, iters, _ = oracle.solve(solver, csr, a, su_ref, fi_ref, sor=1e-8, nsw=10000)
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    ctx.upload("APU", -np.ones(n))
+    ctx.upload("SU", su)
+    ctx.fill("PP", 0.0)
+    ctx.laplacian("APU", "PP")
+    rep = ctx.solve(solver, "PP", fc.solver_opts(1e-8, 10000))
+    got = ctx.download("PP")[:n]
+    print(f"\n[config 3] {solver}: {rep.iters} iterations (oracle {iters}), {ctx.timings().solve_ms:.1f} ms")
+    assert abs(rep.iters - iters) <= 1, (rep.iters, iters)
+    assert rep.res0 == pytest.approx(res0, rel=1e-11)
+    assert cases.rel_l2(got, fi_ref[:n]) < 1e-6
+    exact = np.sin(2 * np.pi * mesh.xc[:n]) * np.sin(2 * np.pi * mesh.yc[:n])
+    assert np.max(np.abs(got - exact)) < 1e-3
+    ctx.close()
+
+
+def test_config4_at_108_cubed_iteration_parity_with_the_oracle(fc):
+    """BASELINE config 4 at 108^3 (1.26 M cells -- what one rank of the 8-GPU 216^3 run holds): the whole `calcp`
+    (assembly, DPCG to rsm < 1e-8, corrections) against the serial oracle on the same inputs: matrix and right-hand side
+    bit for bit, the same iteration count (north star: within +-1), pp and p to 1e-10.  (bench.py makes the same
+    comparison at 216^3 on every rank count, in its `parity` object.)"""
+    from oracle import oracle, oracle_par
+    n = 108
+    mesh = M.hex_mesh(n, n, n)
+    f = cases.config4_fields(mesh)
+    csr = oracle.create_csr(mesh)
+    of = oracle.Fields(mesh, csr.nnz)
+    for k in ("u", "v", "w", "p", "den", "apu", "apv", "apw"):
+        getattr(of, k)[:] = f[k]
+    of.dPdxi[:] = oracle.grad_gauss(mesh, of.p, 1)
+    kw = dict(solver="dpcg", const_mflux=True, sor=1e-8, nsw=100000, pRefCell=1, urf_p=0.3)
+    oracle_par.set_threads2(1, min(8, len(os.sched_getaffinity(0))))   # row loops only: bit-identical to one thread
+    rep_o = oracle.calcp(mesh, csr, of, oracle.calcp_opts(**kw))
+    oracle_par.set_threads2(1, 1)
+    ctx = fc.Context(0)
+    ctx.set_mesh(mesh)
+    ctx.create_csr(download=False)
+    for k, name in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("den", "DEN"), ("apu", "APU"), ("apv", "APV"),
+                    ("apw", "APW")):
+        ctx.upload(name, f[k])
+    ctx.grad_gauss("P", "DPDXI", 1)
+    rep = ctx.calcp(fc.calcp_opts(**kw))
+    print(f"\n[config 4, 108^3] DPCG {rep.rep[0].iters} iterations (oracle {rep_o.rep[0].iters})")
+    assert np.array_equal(ctx.download("A"), of.a) and np.array_equal(ctx.download("SU"), of.su)
+    assert abs(rep.rep[0].iters - rep_o.rep[0].iters) <= 1, (rep.rep[0].iters, rep_o.rep[0].iters)
+    assert rep.rep[0].res0 == pytest.approx(rep_o.rep[0].res0, rel=1e-12)
+    nc = mesh.numCells
+    assert cases.rel_l2(ctx.download("PP")[:nc], of.pp[:nc]) < 1e-10
+    assert cases.rel_l2(ctx.download("P")[:nc], of.p[:nc]) < 1e-10
+    assert cases.rel_l2(ctx.download("U")[:nc], of.u[:nc]) < 1e-10
     ctx.close()

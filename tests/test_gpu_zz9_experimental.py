@@ -101,35 +101,3 @@ def test_fused_velocity_gradients_are_bit_identical(fc, name, nigrad):
         ctx.close()
     for a, b in zip(*res):
         assert np.array_equal(a, b)
-
-
-@pytest.mark.parametrize("solver", ["dpcg", "iccg"])
-def test_config3_full_size_poisson_against_the_oracle(fc, solver):
-    """BASELINE config 3 at its full size (100^3 Poisson, rsm < 1e-8, nsw = 10000): iteration count within +-1 of the
-    oracle's, solution within the solver tolerance, L-infinity error against sin(2 pi x) sin(2 pi y) second order.
-    (Opt-in until it has run once: the oracle needs about ten seconds per solver.)"""
-    from oracle import oracle
-    mesh = cases.hex_case(100, 100, 100, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry"))
-    n = mesh.numCells
-    csr = oracle.create_csr(mesh)
-    su = cases.poisson_rhs(mesh)
-    su_ref = su.copy()
-    a = oracle.laplacian(mesh, csr, -np.ones(n), np.zeros(mesh.numTotal), su_ref)
-    fi_ref = np.zeros(mesh.numTotal)
-    res0, resl, iters, _ = oracle.solve(solver, csr, a, su_ref, fi_ref, sor=1e-8, nsw=10000)
-    ctx = fc.Context(0)
-    ctx.set_mesh(mesh)
-    ctx.create_csr(download=False)
-    ctx.upload("APU", -np.ones(n))
-    ctx.upload("SU", su)
-    ctx.fill("PP", 0.0)
-    ctx.laplacian("APU", "PP")
-    rep = ctx.solve(solver, "PP", fc.solver_opts(1e-8, 10000))
-    got = ctx.download("PP")[:n]
-    print(f"\n[config 3] {solver}: {rep.iters} iterations (oracle {iters}), {ctx.timings().solve_ms:.1f} ms")
-    assert abs(rep.iters - iters) <= 1, (rep.iters, iters)
-    assert rep.res0 == pytest.approx(res0, rel=1e-11)
-    assert cases.rel_l2(got, fi_ref[:n]) < 1e-6
-    exact = np.sin(2 * np.pi * mesh.xc[:n]) * np.sin(2 * np.pi * mesh.yc[:n])
-    assert np.max(np.abs(got - exact)) < 1e-3
-    ctx.close()
