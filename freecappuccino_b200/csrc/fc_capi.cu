@@ -107,7 +107,7 @@ void free_all(fc_context *ctx) {
                   (void *)ctx->gtmp, (void *)ctx->partials, (void *)ctx->sc, (void *)ctx->bufind,
                   (void *)ctx->sendbuf, (void *)ctx->strip_off, (void *)ctx->strip_idx,
                   (void *)ctx->strip_any32, (void *)ctx->persist, (void *)ctx->uvw_face, (void *)ctx->hcoef, (void *)ctx->dmat, (void *)ctx->tja, (void *)ctx->gtmp3, (void *)ctx->sweep_chk,
-                  (void *)ctx->dmatqr, (void *)ctx->hist})
+                  (void *)ctx->dmatqr, (void *)ctx->hist, (void *)ctx->jcode, (void *)ctx->jdict})
     if (p) cudaFree(p);
   for (int f = 0; f < FC_NUM_FIELDS; ++f)
     if (ctx->field[f]) cudaFree(ctx->field[f]);
@@ -163,6 +163,7 @@ int fc_create(int device, fc_context **out) {
   auto init = [&]() -> int {
     FC_CUDA(cudaSetDevice(device));
     FC_CUDA(cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device));
+    FC_CUDA(cudaDeviceGetAttribute(&ctx->l2_bytes, cudaDevAttrL2CacheSize, device));
     if (ctx->sms < 1) ctx->sms = FC_SMS;
     FC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto &ev : ctx->ev) FC_CUDA(cudaEventCreate(&ev));
@@ -630,12 +631,16 @@ int fc_set_tuning(fc_context *ctx, int key, int value) {
   switch (key) {
     case FC_TUNE_SPMV_KERNEL: if (value < 0 || value > 2) return FC_ERR_ARG; ctx->tune_spmv = value; break;
     case FC_TUNE_DPCG_PERSISTENT: if (value < 0 || value > 1) return FC_ERR_ARG; ctx->tune_persist = value; break;
-    case FC_TUNE_PIPE_GEOMETRY: if (value < 0 || value > 3) return FC_ERR_ARG; ctx->tune_pipe = value; break;
+    case FC_TUNE_PIPE_GEOMETRY: if (value < 0 || value > 4) return FC_ERR_ARG; ctx->tune_pipe = value; break;
     case FC_TUNE_CTAS_PER_SM: if (value < 0 || value > 8) return FC_ERR_ARG; ctx->tune_ctas_per_sm = value; break;
     case FC_TUNE_SWEEP_P2P: if (value < 0 || value > 1) return FC_ERR_ARG; ctx->tune_sweep_p2p = value; break;
     case FC_TUNE_FUSED_GRAD: if (value < 0 || value > 1) return FC_ERR_ARG; ctx->tune_fused_grad = value; break;
     case FC_TUNE_DPCG_FUSED: if (value < 0 || value > 2) return FC_ERR_ARG; ctx->tune_dpcg_fused = value; break;
     case FC_TUNE_FACE_OCC: if (value < 2 || value > 4) return FC_ERR_ARG; ctx->tune_face_occ = value; break;
+    case FC_TUNE_JA_CODED: if (value < 0 || value > 2) return FC_ERR_ARG; ctx->tune_ja_coded = value; break;
+    case FC_TUNE_DPCG_EAGER: if (value < 0 || value > 2) return FC_ERR_ARG; ctx->tune_dpcg_eager = value; break;
+    case FC_TUNE_X_PREFETCH: if (value < 0 || value > 2) return FC_ERR_ARG; ctx->tune_x_prefetch = value; break;
+    case FC_TUNE_MAT_KEEP: if (value < -1 || value > 100) return FC_ERR_ARG; ctx->tune_mat_keep = value; break;
     case FC_TUNE_L2_KEEP: if (value < 0 || value > 2) return FC_ERR_ARG; ctx->tune_l2_keep = value; break;
     case FC_TUNE_SWEEP_CHECK: if (value < 0 || value > 1) return FC_ERR_ARG; ctx->tune_sweep_check = value; break;
     case FC_TUNE_TILE_CTAS: if (value != 2 && value != 3) return FC_ERR_ARG; ctx->tune_tile_ctas = value; break;
@@ -662,6 +667,7 @@ int fc_get_timings(const fc_context *ctx, fc_timings *t) {
   *t = ctx->tm;
   t->launches = ctx->launches;
   t->sweep_tiles = (ctx->tune_sweep_tiled && ctx->tiles_ok) ? ctx->tile_lower.nblocks : 0;
+  t->column_offsets = ctx->coded_ok ? ctx->ndict : 0;
   return FC_OK;
 }
 

@@ -6,6 +6,7 @@
 // linear search (csr_to_k, src/utils.f90:76-100).  The sorted pattern is unique, so
 // here it is produced by count -> scan -> fill -> per-row sort, which gives
 // bit-identical integers without a global sort.
+#include <vector>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_reduce.cuh>
 
@@ -193,6 +194,38 @@ __global__ void k_strip_any32(const int *__restrict__ soff, int n, unsigned char
   any32[g] = soff[r1] > soff[g * 32] ? 1 : 0;
 }
 
+// ---- column indices as one-byte codes (CODED pipelines of fc_spmv_pipe.cuh) ----
+// bit (ja[k] - row + n) of `bits` for every non-zero; the bit is tested before the atomic, so the few distinct
+// offsets of a finite-volume numbering cost a handful of atomics, not one per non-zero
+__global__ void k_delta_mark(const int *__restrict__ ioffset, const int *__restrict__ ja, int n, unsigned *bits) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (int k = ioffset[r]; k < ioffset[r + 1]; ++k) {
+    const unsigned d = (unsigned)(ja[k] - r + n);
+    const unsigned m = 1u << (d & 31u);
+    if (!(__ldcg(bits + (d >> 5)) & m)) atomicOr(bits + (d >> 5), m);
+  }
+}
+// code[k] = position of (ja[k] - row) in the ascending dictionary
+__global__ void k_delta_code(const int *__restrict__ ioffset, const int *__restrict__ ja, int n,
+                             const int *__restrict__ dict, int nd, unsigned char *code) {
+  __shared__ int s_d[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_d[i] = dict[i];
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (int k = ioffset[r]; k < ioffset[r + 1]; ++k) {
+    const int d = ja[k] - r;
+    int lo = 0, hi = nd - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_d[mid] < d) lo = mid + 1;
+      else hi = mid;
+    }
+    code[k] = (unsigned char)lo;
+  }
+}
+
 int exclusive_scan(fc_context *ctx, int *in, int *out, int count) {
   void *tmp = nullptr;
   size_t bytes = 0;
@@ -279,6 +312,47 @@ int fc_csr_post(fc_context *ctx) {
   ctx->launches++;
   ctx->spmv_max_chunk = h;
   ctx->has_csr = true;
+  return fc_codes_build(ctx);
+}
+
+// One-byte column codes of the current pattern: ja[k] = row + jdict[jcode[k]].  Possible when the pattern has at most
+// 256 distinct column offsets (structured and block-structured numberings; 7 on a hexahedral box); otherwise
+// coded_ok stays false and every kernel reads `ja`.
+int fc_codes_build(fc_context *ctx) {
+  const int n = ctx->n, B = 256;
+  ctx->coded_ok = false;
+  if (n < 1 || ctx->nnz < 1) return FC_OK;
+  const size_t words = ((size_t)2 * n + 1 + 31) / 32;
+  unsigned *bits = nullptr;
+  FC_CHECK(fc_dev_alloc(ctx, &bits, words));
+  FC_CUDA(cudaMemsetAsync(bits, 0, words * sizeof(unsigned), ctx->stream));
+  k_delta_mark<<<fc_blocks(n, B), B, 0, ctx->stream>>>(ctx->ioffset, ctx->ja, n, bits);
+  FC_LAUNCH_CHECK();
+  std::vector<unsigned> hb(words);
+  FC_CUDA(cudaMemcpyAsync(hb.data(), bits, words * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  FC_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(bits);
+  std::vector<int> dict;
+  for (size_t w = 0; w < words && dict.size() <= 256; ++w) {
+    unsigned x = hb[w];
+    while (x && dict.size() <= 256) {
+      const int b = __builtin_ctz(x);
+      x &= x - 1;
+      dict.push_back((int)((long long)w * 32 + b - n));
+    }
+  }
+  if (dict.empty() || dict.size() > 256) return FC_OK;
+  const int nd = (int)dict.size();
+  dict.resize(256, dict.back());
+  FC_CHECK(fc_dev_alloc(ctx, &ctx->jdict, 256));
+  FC_CHECK(fc_dev_alloc(ctx, &ctx->jcode, (size_t)ctx->nnz + 64));
+  FC_CUDA(cudaMemcpyAsync(ctx->jdict, dict.data(), 256 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  k_delta_code<<<fc_blocks(n, B), B, 0, ctx->stream>>>(ctx->ioffset, ctx->ja, n, ctx->jdict, nd, ctx->jcode);
+  FC_LAUNCH_CHECK();
+  FC_CUDA(cudaStreamSynchronize(ctx->stream));   // `dict` is a host temporary
+  ctx->launches += 2;
+  ctx->ndict = nd;
+  ctx->coded_ok = true;
   return FC_OK;
 }
 

@@ -43,6 +43,9 @@ struct persist_args {
   unsigned long long red_seq0, halo_seq0;
   double *hist;
   int l2keep;   // the Krylov vectors fit the L2: mark them evict_last (the matrix stream is evict_first)
+  int xprefetch;     // FC_TUNE_X_PREFETCH
+  int eager;         // small partitions: fi += alf*pk runs behind the beta reduction, q = res/a_ii is handed to the p-update
+  int mat_keep256;   // share (of 256) of the matrix chunks that stay in the L2 from one product to the next
   // "fused p" scheme (FUSED kernels): q = res / (a_ii + padd) (in the arena: the neighbours store its halo), the product's
   // result y, and the second direction buffer (pk / pk2 alternate as pold / pnew)
   double *q, *y, *pk2;
@@ -106,10 +109,15 @@ __device__ __forceinline__ void grid_barrier(const persist_args &A, sync_ctx &S,
 // finishes the sum, exchanges it with the other ranks and runs the scalar step `step`.
 // `hseq` != 0 (fused-p scheme): the CTAs stored halo values into the neighbours' memory before this barrier; the last
 // CTA raises the neighbours' halo-arrival flags before it releases its own grid (`sent_remote`: this CTA did store).
-template <int NR>
+struct no_shadow { __device__ __forceinline__ void operator()() const {} };
+
+// `shadow`: work of the whole CTA that does not depend on the reduction's result.  A CTA runs it between its arrival
+// and its wait for the release, i.e. behind the reduction and the exchange with the other ranks; the CTA that arrives
+// last -- and does the reduction -- runs it after it has released the others.
+template <int NR, class Shadow = no_shadow>
 __device__ __forceinline__ void grid_reduce(const persist_args &A, sync_ctx &S, double (&v)[NR], int step, int phase,
                                             unsigned long long seq, unsigned long long hseq = 0ull,
-                                            bool sent_remote = false) {
+                                            bool sent_remote = false, Shadow shadow = Shadow()) {
   const int G = gridDim.x;
   __shared__ unsigned long long s_tarr;
   fc_block_sum<NR>(v, S.s_red);
@@ -123,7 +131,9 @@ __device__ __forceinline__ void grid_reduce(const persist_args &A, sync_ctx &S, 
     if (*S.s_last) s_tarr = fc_globaltimer();
   }
   __syncthreads();
-  if (*S.s_last) {
+  const bool last = *S.s_last;
+  if (!last) shadow();
+  if (last) {
     __threadfence();
     if (hseq && A.p2p && threadIdx.x == 0) {   // every CTA's halo stores are ordered before its arrival
       __threadfence_system();
@@ -187,6 +197,7 @@ __device__ __forceinline__ void grid_reduce(const persist_args &A, sync_ctx &S, 
       if (step == STEP_RES0_SK && sc->nsw <= 0) sc->done = 1;   // `do l=1,ns` with ns = 0: no iteration, fi untouched
       release_barrier(A.ps, S.my_gen, phase, s_tarr);
     }
+    shadow();
   } else if (threadIdx.x == 0) {
     wait_release(A.ps, S.my_gen);
   }
@@ -195,7 +206,7 @@ __device__ __forceinline__ void grid_reduce(const persist_args &A, sync_ctx &S, 
   __syncthreads();
 }
 
-template <int T, int CAP, int S, bool STRIP, bool FUSED>
+template <int T, int CAP, int S, bool STRIP, bool FUSED, bool CODED>
 __global__ void __launch_bounds__(T, 768 / T)   // <= 85 registers: three 256-thread CTAs per SM
 k_dpcg_persist(persist_args A) {
   extern __shared__ __align__(128) unsigned char fc_smem_raw[];
@@ -209,14 +220,17 @@ k_dpcg_persist(persist_args A) {
   fc_scalars *sc = A.sc;
   sync_ctx SY{fc_ld_acquire_gpu(&A.ps->gen), &s_last, s_red};
 
-  fc_spmv_pipe<T, CAP, S> pipe;
-  auto *sm = reinterpret_cast<fc_spmv_smem<T, CAP, S> *>(fc_smem_raw);
+  fc_spmv_pipe<T, CAP, S, CODED> pipe;
+  auto *sm = reinterpret_cast<fc_spmv_smem<T, CAP, S, CODED> *>(fc_smem_raw);
   int rbeg, rend;
   fc_row_range(n, STRIP ? A.st.off : nullptr, &rbeg, &rend);
-  pipe.init(sm, A.M.ioffset, rbeg, rend, STRIP ? A.st.off : nullptr);
+  pipe.init(sm, A.M.ioffset, rbeg, rend, STRIP ? A.st.off : nullptr, A.M.dict);
   // L2 policy of the vector traffic (pk, zk, res, adiag): evict_last when they fit the L2 next to the matrix stream
   const unsigned long long vpol = A.l2keep ? fc_policy_evict_last() : fc_policy_evict_normal();
   pipe.pol_y = vpol;
+  pipe.keep256 = A.mat_keep256;
+  pipe.xprefetch = A.xprefetch;
+  pipe.pol_keep = fc_policy_evict_last();
   pipe.prefetch(A.M);
   const bool p2p = STRIP && A.p2p != nullptr;
   if (p2p) {
@@ -354,10 +368,105 @@ k_dpcg_persist(persist_args A) {
   // ---- res = su - A fi ; res0 = sum|res| ; sk = sum res*res/(a_ii[+small])   (dpcg.f90:51-90) ----
   {
     fc_spmv_vec V{A.fi, A.res, A.su, nullptr, A.diag, A.adiag, A.padd};
+    if (A.eager) V.qout = A.zk;
     double v[2] = {0.0, 0.0};
     pipe.template sweep<FC_MODE_RESID_SK, STRIP>(A.M, V, st, v[0], v[1]);
     pipe.prefetch(A.M);
     grid_reduce<2>(A, SY, v, STEP_RES0_SK, PH_SETUP, ++red_seq);
+  }
+
+  // ================= small partitions (A.eager): the vectors live in the L2 and an iteration is a few tens of
+  // microseconds, a third of it barriers and reductions.  Two changes, both with the operands and the rounding of
+  // dpcg.f90:95-142 (bit-identical iterates):
+  //   * the x/r update leaves q = res/(a_ii[+small]) in zk (it needs that quotient for the next sk anyway), so the
+  //     p-update reads q and pk only -- no division, 24 instead of 48 bytes per row;
+  //   * fi += alf*pk does not ride in the p-update but runs BEHIND the beta reduction: every CTA does its share
+  //     between its arrival at the barrier and its wait for the release, while the last CTA adds the partial sums
+  //     and exchanges them with the other ranks.
+  if (A.eager) {
+    while (!__ldcg(&sc->done)) {
+      {
+        const double bet = __ldcg(&sc->sk) / __ldcg(&sc->s0);
+        int i = rbeg + tid;
+        for (; i + 3 * T < rend; i += 4 * T) {
+          const double q0 = fc_ld_pol(A.zk + i, vpol), q1 = fc_ld_pol(A.zk + i + T, vpol),
+                       q2 = fc_ld_pol(A.zk + i + 2 * T, vpol), q3 = fc_ld_pol(A.zk + i + 3 * T, vpol);
+          const double p0 = fc_ld_pol(A.pk + i, vpol), p1 = fc_ld_pol(A.pk + i + T, vpol),
+                       p2 = fc_ld_pol(A.pk + i + 2 * T, vpol), p3 = fc_ld_pol(A.pk + i + 3 * T, vpol);
+          fc_st_pol(A.pk + i, q0 + bet * p0, vpol);
+          fc_st_pol(A.pk + i + T, q1 + bet * p1, vpol);
+          fc_st_pol(A.pk + i + 2 * T, q2 + bet * p2, vpol);
+          fc_st_pol(A.pk + i + 3 * T, q3 + bet * p3, vpol);
+        }
+        for (; i < rend; i += T) fc_st_pol(A.pk + i, fc_ld_pol(A.zk + i, vpol) + bet * fc_ld_pol(A.pk + i, vpol), vpol);
+        if (p2p && pipe.cta_strip) send_halo(A.pk);
+      }
+      ++halo_seq;
+      grid_barrier(A, SY, PH_PUPDATE, p2p ? halo_seq : 0ull, p2p && pipe.cta_strip);
+      {
+        if (p2p) {
+          st.hseq = halo_seq;
+          pipe.halo_pending = pipe.cta_strip;
+        }
+        fc_spmv_vec V{A.pk, A.zk, nullptr, A.pk, nullptr, nullptr, 0.0};
+        double v[1] = {0.0};
+        double unused = 0.0;
+        pipe.template sweep<FC_MODE_DOT, STRIP>(A.M, V, st, v[0], unused);
+        pipe.prefetch(A.M);
+        grid_reduce<1>(A, SY, v, STEP_PKAPK, PH_SPMV, ++red_seq);
+      }
+      {
+        const double alf = __ldcg(&sc->sk) / __ldcg(&sc->pkapk);
+        double a0 = 0.0, a1 = 0.0;
+        int i = rbeg + tid;
+        for (; i + 3 * T < rend; i += 4 * T) {
+          const double r0 = fc_ld_pol(A.res + i, vpol), r1 = fc_ld_pol(A.res + i + T, vpol),
+                       r2 = fc_ld_pol(A.res + i + 2 * T, vpol), r3 = fc_ld_pol(A.res + i + 3 * T, vpol);
+          const double z0 = fc_ld_pol(A.zk + i, vpol), z1 = fc_ld_pol(A.zk + i + T, vpol),
+                       z2 = fc_ld_pol(A.zk + i + 2 * T, vpol), z3 = fc_ld_pol(A.zk + i + 3 * T, vpol);
+          const double d0 = fc_ld_pol(A.adiag + i, vpol), d1 = fc_ld_pol(A.adiag + i + T, vpol),
+                       d2 = fc_ld_pol(A.adiag + i + 2 * T, vpol), d3 = fc_ld_pol(A.adiag + i + 3 * T, vpol);
+          const double n0 = r0 - alf * z0, n1 = r1 - alf * z1, n2 = r2 - alf * z2, n3 = r3 - alf * z3;
+          const double q0 = n0 / (d0 + A.padd), q1 = n1 / (d1 + A.padd), q2 = n2 / (d2 + A.padd), q3 = n3 / (d3 + A.padd);
+          fc_st_pol(A.res + i, n0, vpol);
+          fc_st_pol(A.res + i + T, n1, vpol);
+          fc_st_pol(A.res + i + 2 * T, n2, vpol);
+          fc_st_pol(A.res + i + 3 * T, n3, vpol);
+          fc_st_pol(A.zk + i, q0, vpol);
+          fc_st_pol(A.zk + i + T, q1, vpol);
+          fc_st_pol(A.zk + i + 2 * T, q2, vpol);
+          fc_st_pol(A.zk + i + 3 * T, q3, vpol);
+          a0 += fabs(n0); a1 += n0 * q0;
+          a0 += fabs(n1); a1 += n1 * q1;
+          a0 += fabs(n2); a1 += n2 * q2;
+          a0 += fabs(n3); a1 += n3 * q3;
+        }
+        for (; i < rend; i += T) {
+          const double n0 = fc_ld_pol(A.res + i, vpol) - alf * fc_ld_pol(A.zk + i, vpol);
+          const double q0 = n0 / (fc_ld_pol(A.adiag + i, vpol) + A.padd);
+          fc_st_pol(A.res + i, n0, vpol);
+          fc_st_pol(A.zk + i, q0, vpol);
+          a0 += fabs(n0); a1 += n0 * q0;
+        }
+        double v[2] = {a0, a1};
+        auto x_update = [&]() {   // fi += alf*pk (dpcg.f90:121-124) behind the reduction
+          int k = rbeg + tid;
+          for (; k + 3 * T < rend; k += 4 * T) {
+            const double p0 = fc_ld_pol(A.pk + k, vpol), p1 = fc_ld_pol(A.pk + k + T, vpol),
+                         p2 = fc_ld_pol(A.pk + k + 2 * T, vpol), p3 = fc_ld_pol(A.pk + k + 3 * T, vpol);
+            const double f0 = A.fi[k], f1 = A.fi[k + T], f2 = A.fi[k + 2 * T], f3 = A.fi[k + 3 * T];
+            A.fi[k] = f0 + alf * p0;
+            A.fi[k + T] = f1 + alf * p1;
+            A.fi[k + 2 * T] = f2 + alf * p2;
+            A.fi[k + 3 * T] = f3 + alf * p3;
+          }
+          for (; k < rend; k += T) A.fi[k] = A.fi[k] + alf * fc_ld_pol(A.pk + k, vpol);
+        };
+        grid_reduce<2>(A, SY, v, STEP_CG_UPDATE_SK, PH_UPDATE, ++red_seq, 0ull, false, x_update);
+      }
+    }
+    pipe.drain();
+    return;
   }
 
   bool first = true;
@@ -482,10 +591,10 @@ k_dpcg_persist(persist_args A) {
   pipe.drain();   // no CTA may exit with bulk copies in flight
 }
 
-template <int T, int CAP, int S, bool STRIP, bool FUSED>
+template <int T, int CAP, int S, bool STRIP, bool FUSED, bool CODED>
 int launch_persist(fc_context *ctx, persist_args &A, bool *ok) {
-  auto kern = k_dpcg_persist<T, CAP, S, STRIP, FUSED>;
-  const size_t smem = sizeof(fc_spmv_smem<T, CAP, S>);
+  auto kern = k_dpcg_persist<T, CAP, S, STRIP, FUSED, CODED>;
+  const size_t smem = sizeof(fc_spmv_smem<T, CAP, S, CODED>);
   // per instantiation and per device (the shared-memory opt-in is a per-device function attribute)
   static int per_sm_dev[FC_MAX_DEVICES];
   static bool per_sm_set[FC_MAX_DEVICES];
@@ -565,26 +674,55 @@ int fc_dpcg_persistent(fc_context *ctx, double *fi, const fc_solver_opts *o, fc_
   A.hist = hist;
   // four vectors of (n + npro) doubles against the 126 MB L2, which the matrix stream shares
   A.l2keep = ctx->tune_l2_keep == 1 || (ctx->tune_l2_keep == 2 && 32.0 * ((double)n + ctx->npro) <= 56e6);
+  {
+    int keep = ctx->tune_mat_keep;
+    if (keep < 0) keep = 0;
+    A.mat_keep256 = keep * 256 / 100;
+    A.xprefetch = ctx->tune_x_prefetch;
+    // measured (profiles/r02_dpcg_eager.jsonl): -4.6 % per iteration at 1.26 M rows, -4.7 % at 2.5 M (the vectors are
+    // mostly L2-resident and the barriers a tenth of the iteration), +1.5 % at 10 M (there the deferred x update saves
+    // a pass over pk that no barrier can hide)
+    A.eager = ctx->tune_dpcg_eager == 1 || (ctx->tune_dpcg_eager == 2 && (double)n + ctx->npro <= 3.2e6);
+  }
 
   // fused-p scheme (FC_TUNE_DPCG_FUSED: 0 never, 1 always, [2] on partitioned meshes, where an iteration is short and
   // the phase / barrier it saves is a fifth of it; on one GPU at 10 M cells the extra gathers cost more than it saves)
   const bool fused = ctx->tune_dpcg_fused == 1 || (ctx->tune_dpcg_fused == 2 && ctx->nranks > 1);
   A.q = ctx->zk; A.y = ctx->uk; A.pk2 = ctx->reso;
+  // one-byte column codes instead of `ja` (FC_TUNE_JA_CODED) when the pattern has them; the fused-p option keeps `ja`
+  // (measured, profiles/r02_ja_coded.jsonl: -2 % per iteration at 10 M rows, -6 % at 2.5 M, +0.7 % at 1.26 M where
+  // the product is bound by the latency of a chunk, not by its bytes)
+  const bool coded = !fused && ctx->coded_ok && A.M.ja == ctx->ja &&
+                     (ctx->tune_ja_coded == 1 || (ctx->tune_ja_coded == 2 && n >= 2000000));
+  if (coded) { A.M.jc = ctx->jcode; A.M.dict = ctx->jdict; }
   FC_CUDA(cudaMemsetAsync(ctx->pk, 0, sizeof(double) * ((size_t)n + ctx->npro), st));
   if (fused) FC_CUDA(cudaMemsetAsync(ctx->reso, 0, sizeof(double) * ((size_t)n + ctx->npro), st));
   k_persist_begin<<<1, 1, 0, st>>>(ctx->persist);
   FC_LAUNCH_CHECK();
   const bool strip = ctx->npro > 0;
   bool ok = false;
-#define FC_PERSIST(T, CAP, S)                                                                 \
-  do {                                                                                        \
-    if (strip && fused) FC_CHECK((launch_persist<T, CAP, S, true, true>(ctx, A, &ok)));       \
-    else if (strip)     FC_CHECK((launch_persist<T, CAP, S, true, false>(ctx, A, &ok)));      \
-    else if (fused)     FC_CHECK((launch_persist<T, CAP, S, false, true>(ctx, A, &ok)));      \
-    else                FC_CHECK((launch_persist<T, CAP, S, false, false>(ctx, A, &ok)));     \
+#define FC_PERSIST(T, CAP, S)                                                                            \
+  do {                                                                                                   \
+    if (strip && fused) FC_CHECK((launch_persist<T, CAP, S, true, true, false>(ctx, A, &ok)));           \
+    else if (fused)     FC_CHECK((launch_persist<T, CAP, S, false, true, false>(ctx, A, &ok)));          \
+    else if (strip && coded) FC_CHECK((launch_persist<T, CAP, S, true, false, true>(ctx, A, &ok)));      \
+    else if (strip)     FC_CHECK((launch_persist<T, CAP, S, true, false, false>(ctx, A, &ok)));          \
+    else if (coded)     FC_CHECK((launch_persist<T, CAP, S, false, false, true>(ctx, A, &ok)));          \
+    else                FC_CHECK((launch_persist<T, CAP, S, false, false, false>(ctx, A, &ok)));         \
   } while (0)
+#define FC_PERSIST_CODED(T, CAP, S)                                                                      \
+  do {                                                                                                   \
+    if (strip) FC_CHECK((launch_persist<T, CAP, S, true, false, true>(ctx, A, &ok)));                    \
+    else       FC_CHECK((launch_persist<T, CAP, S, false, false, true>(ctx, A, &ok)));                   \
+  } while (0)
+  // One-byte codes shrink a 256-row chunk of a hexahedral mesh from 21.5 to 16.1 KB.  The pipeline is bound by the
+  // bytes it keeps in flight (one chunk per CTA with two stages: ~1.5 us of loaded HBM latency), so the coded kernel
+  // takes a third stage -- two chunks in flight per CTA, still three CTAs per SM -- with stages of 1824 non-zeros
+  // (256 rows x 7 + the alignment slack of the copies).
+  const int pipe_sel = (ctx->tune_pipe == 4 && !(coded && ctx->spmv_max_chunk <= 1792)) ? 1 : ctx->tune_pipe;
   if (ctx->spmv_max_chunk <= 2000) {
-    switch (ctx->tune_pipe) {
+    switch (pipe_sel) {
+      case 4: FC_PERSIST_CODED(256, 1824, 3); break;
       case 1: FC_PERSIST(256, 2304, 2); break;
       case 2: FC_PERSIST(256, 2048, 2); break;
       case 3: FC_PERSIST(128, 1024, 2); break;
@@ -594,6 +732,7 @@ int fc_dpcg_persistent(fc_context *ctx, double *fi, const fc_solver_opts *o, fc_
     FC_PERSIST(256, 4096, 2);
   }
 #undef FC_PERSIST
+#undef FC_PERSIST_CODED
   if (!ok) return FC_OK;
   FC_CUDA(cudaMemcpyAsync(ctx->sc_host, ctx->sc, sizeof(fc_scalars), cudaMemcpyDeviceToHost, st));
   FC_CUDA(cudaMemcpyAsync(ctx->persist_host, ctx->persist, sizeof(fc_persist_state), cudaMemcpyDeviceToHost, st));
@@ -611,6 +750,7 @@ int fc_dpcg_persistent(fc_context *ctx, double *fi, const fc_solver_opts *o, fc_
   ctx->tm.persist_update_ms = 1e-6 * (double)ps.t_phase[PH_UPDATE];
   ctx->tm.persist_mail_ms = 1e-6 * (double)ps.t_mail;
   ctx->tm.persist_iters = rep->iters;
+  ctx->tm.persist_index_bytes = coded ? 1 : 4;
   if (rep->iters > 0) {
     ctx->tm.spmv_ms = ctx->tm.persist_spmv_ms / rep->iters;
     ctx->tm.spmv_samples = rep->iters;

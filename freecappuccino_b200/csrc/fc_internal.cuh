@@ -101,6 +101,7 @@ constexpr int FC_TRI_MAXP = 16;
 struct fc_context {
   int device = 0;
   int sms = FC_SMS;                     // SM count of `device` (queried in fc_create)
+  int l2_bytes = 0;                     // L2 size of `device`
   double *hist = nullptr;               // residual history of a solve (fc_solve_csr's `hist`), grown on demand
   size_t hist_cap = 0;
   cudaStream_t stream = nullptr;
@@ -130,6 +131,10 @@ struct fc_context {
   int *ioffset = nullptr, *ja = nullptr, *diag = nullptr, *icj = nullptr, *jci = nullptr;
   int *tpos = nullptr;                  // position of a(j,i) for every lower a(i,j) (bicgstab.f90:72-75)
   int spmv_max_chunk = 0;               // max nnz of a 256-row block
+  unsigned char *jcode = nullptr;       // [nnz] one-byte column codes, ja[k] = row + jdict[jcode[k]] (fc_codes_build)
+  int *jdict = nullptr;                 // [256] ascending column offsets
+  int ndict = 0;
+  bool coded_ok = false;                // the pattern has <= 256 distinct column offsets: jcode / jdict are valid
 
   // ---- fields ----
   double *field[FC_NUM_FIELDS] = {};
@@ -189,6 +194,10 @@ struct fc_context {
   int first_batch[3] = {8, 8, 8};       // per solver: iterations enqueued before the first look at `done`
   int tune_dpcg_fused = 0;              // persistent DPCG: fused-p scheme (0 never [default: measured slower, profiles/r02_fused_p.txt], 1 always, 2 on partitioned meshes)
   int tune_face_occ = 3;                // k_calcp_faces: CTAs per SM its registers must allow (2: 102 registers, 3: 80, 4: 64 + spills)
+  int tune_mat_keep = -1;               // persistent DPCG: percent of the matrix chunks kept in L2 (evict_last); -1 = by size
+  int tune_dpcg_eager = 2;              // persistent DPCG: x update behind the beta reduction + q hand-over (0 off, 1 on, 2 when the vectors fit the L2)
+  int tune_x_prefetch = 0;              // persistent DPCG: prefetch the next chunk's far x gathers (0 off, 1 into L1, 2 into L2)
+  int tune_ja_coded = 2;                // persistent DPCG: one-byte column codes instead of `ja` where the pattern allows (0 off, 1 on, 2 from 2 M rows)
   int tune_l2_keep = 2;                 // persistent DPCG: Krylov vectors evict_last in L2 (0 off, 1 on, 2 when they fit)
   int tune_fused_grad = 1;              // 1: the three velocity gradients of calcuvw / calcp in one kernel per pass
   int tune_sweep_check = 0;             // debugging: every tiled sweep is repeated with the level schedule and compared
@@ -256,6 +265,7 @@ static inline int fc_blocks(size_t n, int bs) { return (int)((n + bs - 1) / bs);
 
 // ---- cross-file entry points ----
 int fc_csr_build(fc_context *ctx);                                   // fc_csr.cu
+int fc_codes_build(fc_context *ctx);                                 // one-byte column codes of the pattern
 int fc_csr_post(fc_context *ctx);                                    // transposed positions, spmv chunking
 int fc_c2f_build(fc_context *ctx);                                   // fc_csr.cu
 int fc_levels_build(fc_context *ctx);                                // fc_trisolve.cu

@@ -264,7 +264,7 @@ int fc_solve_device(fc_context *ctx, int solver, double *fi, const fc_solver_opt
   ctx->pending = {0, 0, 0};
   ctx->halo_wait = 0;
   ctx->tm.persist_ms = ctx->tm.persist_pupdate_ms = ctx->tm.persist_spmv_ms = ctx->tm.persist_update_ms = 0.0;
-  ctx->tm.persist_iters = ctx->tm.persist_grid = 0;
+  ctx->tm.persist_iters = ctx->tm.persist_grid = ctx->tm.persist_index_bytes = 0;
   ctx->tm.persist_mail_ms = 0.0;
   if (solver == FC_DPCG) {   // the whole solve as one persistent kernel (fc_dpcg_persist.cu)
     bool handled = false;

@@ -45,6 +45,11 @@ struct fc_spmv_mat {
   int n;
   const int *ioffset, *ja;
   const double *a;
+  // CODED pipelines: the column indices as one-byte codes, ja[k] = row + dict[jc[k]] (fc_csr.cu, fc_codes_build):
+  // a finite-volume numbering has few distinct column offsets (seven on a structured hexahedral block), so the
+  // index stream shrinks from 4 to 1 byte per non-zero and a product moves 9 instead of 12 bytes per non-zero
+  const unsigned char *jc = nullptr;
+  const int *dict = nullptr;   // [256], ascending offsets
 };
 
 struct fc_spmv_vec {
@@ -89,20 +94,56 @@ __device__ __forceinline__ void fc_row_range(int n, const int *soff, int *rbeg, 
   *rend = blockIdx.x + 1 == gridDim.x ? n : fc_row_cut(n, soff, blockIdx.x + 1, gridDim.x);
 }
 
-template <int T, int CAP, int S>
+template <int T, int CAP, int S, bool CODED = false>
 struct fc_spmv_smem {
   double a[S][CAP];
-  int ja[S][CAP];
+  // column indices of the staged non-zeros: CAP int32, or (CODED) CAP + 32 one-byte codes -- a code copy starts and
+  // ends on a multiple of 16 non-zeros, the copy of `a` on a multiple of 4 (at most 12 + 12 codes more), so the two
+  // stages have different bases
+  alignas(16) unsigned char jraw[S][CODED ? CAP + 32 : CAP * 4];
   int off[S][T + 4];
   unsigned long long full[S];
-  int kb0[FC_KB_MAX], kb1[FC_KB_MAX];   // first / one-past-last non-zero of every chunk this CTA owns
+  int kb[FC_KB_MAX + 1];                // first non-zero of every chunk this CTA owns (kb[j + 1]: one past its last)
   unsigned char cs[FC_KB_MAX];          // chunk contains rows with processor faces
+  int dict[CODED ? 256 : 4];            // CODED: column offset of every code
 };
 
-template <int T, int CAP, int S>
+// N consecutive non-zeros of one row from the staged chunk, v (+|-)= a[c + u] * x[column], left to right
+template <int N, bool RES, bool CODED>
+__device__ __forceinline__ double fc_row_part(const double *pa, const int *pj, const unsigned char *pc, const int *dict,
+                                              int c, int r, const double *x, double v) {
+  int id[N];
+  double av[N], xv[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    id[u] = CODED ? r + dict[pc[c + u]] : pj[c + u];
+    av[u] = pa[c + u];
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) xv[u] = x[id[u]];
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    const double t = av[u] * xv[u];
+    v = RES ? v - t : v + t;
+  }
+  return v;
+}
+
+// the same with x already in registers (gathered one chunk ahead)
+template <int N, bool RES>
+__device__ __forceinline__ double fc_row_part_x(const double *pa, int c, const double (&xq)[8], double v) {
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    const double t = pa[c + u] * xq[u];
+    v = RES ? v - t : v + t;
+  }
+  return v;
+}
+
+template <int T, int CAP, int S, bool CODED = false>
 struct fc_spmv_pipe {
-  static_assert(CAP % 4 == 0 && T % 32 == 0, "staging sizes must keep the bulk copies 16-byte aligned");
-  using smem_t = fc_spmv_smem<T, CAP, S>;
+  static_assert(CAP % 16 == 0 && T % 32 == 0, "staging sizes must keep the bulk copies 16-byte aligned");
+  using smem_t = fc_spmv_smem<T, CAP, S, CODED>;
   smem_t *sm;
   int rbeg, rend, nch;           // rows owned by this CTA, number of chunks
   unsigned issued, consumed;     // running chunk counters over the kernel's life (uniform over the CTA)
@@ -111,13 +152,29 @@ struct fc_spmv_pipe {
   bool cta_strip;                // this CTA owns rows with processor faces
   unsigned long long pol;
   unsigned long long pol_y;      // L2 policy of the result vector's stores (evict_normal unless the caller overrides it)
+  // A Krylov loop walks the same chunks once per iteration.  keep256 / 256 of the CTA's chunks, spread evenly over its
+  // range so that L2 hits and HBM misses alternate through the sweep, carry pol_keep (evict_last) instead of the
+  // streaming policy: as much of the matrix as the L2 can hold next to the vectors stays there from one product to
+  // the next, and only the rest streams from HBM (0 = the whole matrix streams).
+  int keep256;
+  unsigned long long pol_keep;
+  // 1 / 2: while a chunk is computed, the x values the NEXT chunk will gather are prefetched into L1 / L2 (its column
+  // indices are already in shared memory when its copies have landed).  Without it every chunk exposes one full
+  // round trip of its far gathers (the +-nx*ny neighbours come from L2 or, at 10 M cells, from HBM) with only three
+  // chunks per SM to hide it behind.
+  int xprefetch;
+  __device__ __forceinline__ bool kept(int j) const { return (((j + 1) * keep256) >> 8) != ((j * keep256) >> 8); }
 
   __device__ __forceinline__ int row0(int j) const { return rbeg + j * T; }
 
   // Once per kernel.  [rbeg_, rend_) starts on a multiple of 4 rows; `soff` = per-row processor-face
   // offsets (fc_strip::off) or nullptr.  Ends with a block barrier.
-  __device__ __forceinline__ void init(smem_t *s, const int *ioffset, int rbeg_, int rend_, const int *soff) {
+  __device__ __forceinline__ void init(smem_t *s, const int *ioffset, int rbeg_, int rend_, const int *soff,
+                                       const int *dict = nullptr) {
     sm = s;
+    if (CODED) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) sm->dict[i] = dict[i];
+    }
     rbeg = rbeg_;
     rend = rend_ > rbeg_ ? rend_ : rbeg_;
     nch = (rend - rbeg + T - 1) / T;
@@ -126,12 +183,15 @@ struct fc_spmv_pipe {
     halo_pending = false;
     pol = fc_policy_evict_first();
     pol_y = fc_policy_evict_normal();
+    keep256 = 0;
+    xprefetch = 0;
+    pol_keep = pol;
     int any = 0;
     for (int j = threadIdx.x; j < nch; j += blockDim.x) {
       const int r0 = row0(j);
       const int r1 = min(rend, r0 + T);
-      sm->kb0[j] = ioffset[r0];
-      sm->kb1[j] = ioffset[r1];
+      sm->kb[j] = ioffset[r0];
+      if (j + 1 == nch) sm->kb[nch] = ioffset[r1];
       const unsigned char c = (soff && soff[r1] > soff[r0]) ? 1 : 0;
       sm->cs[j] = c;
       any |= c;
@@ -151,15 +211,19 @@ struct fc_spmv_pipe {
     if (threadIdx.x == 0) {
       const int r0 = row0(j);
       const int nr = min(T, rend - r0);
-      const int k0 = sm->kb0[j], k1 = sm->kb1[j];
+      const int k0 = sm->kb[j], k1 = sm->kb[j + 1];
       const int ka = k0 & ~3, cnt = ((k1 + 3) & ~3) - ka;
+      const int kc = k0 & ~15, cntc = ((k1 + 15) & ~15) - kc;   // CODED: the code copy, 16-byte granules
       const unsigned off_bytes = ((unsigned)(nr + 1) * 4u + 15u) & ~15u;
       const bool staged = cnt <= CAP && cnt > 0;
-      fc_mbar_expect_tx(&sm->full[st], off_bytes + (staged ? (unsigned)cnt * 12u : 0u));
+      const unsigned jbytes = CODED ? (unsigned)cntc : (unsigned)cnt * 4u;
+      fc_mbar_expect_tx(&sm->full[st], off_bytes + (staged ? (unsigned)cnt * 8u + jbytes : 0u));
       fc_bulk_g2s(sm->off[st], M.ioffset + r0, off_bytes, &sm->full[st]);
       if (staged) {
-        fc_bulk_g2s(sm->a[st], M.a + ka, (unsigned)cnt * 8u, &sm->full[st], pol);
-        fc_bulk_g2s(sm->ja[st], M.ja + ka, (unsigned)cnt * 4u, &sm->full[st], pol);
+        const unsigned long long pl = kept(j) ? pol_keep : pol;
+        fc_bulk_g2s(sm->a[st], M.a + ka, (unsigned)cnt * 8u, &sm->full[st], pl);
+        if (CODED) fc_bulk_g2s(sm->jraw[st], M.jc + kc, jbytes, &sm->full[st], pl);
+        else       fc_bulk_g2s(sm->jraw[st], M.ja + ka, jbytes, &sm->full[st], pl);
       }
     }
   }
@@ -185,7 +249,29 @@ struct fc_spmv_pipe {
                                         double &acc2) {
     const int tid = threadIdx.x;
     constexpr bool RES = (MODE == FC_MODE_RESID || MODE == FC_MODE_RESID_SK);
-    for (int j = 0; j < nch; ++j) {
+    // Pipelines with three stages gather x one chunk ahead: while chunk j is computed, the x values of the first
+    // eight non-zeros of this thread's row of chunk j+1 (every non-zero of a hexahedral row) are already in flight
+    // into registers -- the column indices of chunk j+1 are in shared memory one stage early.  Without it every
+    // chunk exposes a full round trip of its far gathers (ncu: half of the stall samples of the product are this
+    // scoreboard wait, a quarter the block barrier behind it, 3 % the wait for the matrix).
+    constexpr bool PIPEG = S >= 3 && MODE != FC_MODE_DOT_FUSED;
+    auto gather = [&](int jj, unsigned sgx, double (&xb)[8]) -> int {
+      const int rr0 = row0(jj);
+      const int q0 = sm->kb[jj], q1 = sm->kb[jj + 1];
+      const int qa = q0 & ~3;
+      if (tid >= min(T, rend - rr0) || (((q1 + 3) & ~3) - qa) > CAP) return 0;
+      const int s1 = sm->off[sgx][tid] - qa, e1 = sm->off[sgx][tid + 1] - qa;
+      const int *pj1 = reinterpret_cast<const int *>(sm->jraw[sgx]);
+      const unsigned char *pc1 = sm->jraw[sgx] + (qa - (q0 & ~15));
+      const int n1 = min(e1 - s1, 8);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (u < n1) xb[u] = V.x[CODED ? rr0 + tid + sm->dict[pc1[s1 + u]] : pj1[s1 + u]];
+      return n1;
+    };
+    // one chunk; xc / nc: the x values gathered ahead for it, xn / nn: where the next chunk's go.  The caller
+    // alternates two register buffers (no copies: a copy would wait for the loads it is meant to hide)
+    auto chunk = [&](const int j, double (&xc)[8], int &nc, double (&xn)[8], int &nn) {
       const unsigned sg = consumed % S, par = (consumed / S) & 1u;
       consumed++;
       const int r0 = row0(j);
@@ -226,11 +312,42 @@ struct fc_spmv_pipe {
         }
       }
       fc_mbar_wait(&sm->full[sg], par);
-      const int k0 = sm->kb0[j], k1 = sm->kb1[j];
+      if (PIPEG) {
+        if (j == 0) nc = gather(0, sg, xc);   // the first chunk of a sweep pays its round trip
+        nn = 0;
+        if (j + 1 < nch) {
+          const unsigned sg1 = consumed % S, par1 = (consumed / S) & 1u;
+          fc_mbar_wait(&sm->full[sg1], par1);   // requested two chunks ago
+          nn = gather(j + 1, sg1, xn);
+        }
+      }
+      if (!PIPEG && xprefetch && j + 1 < nch) {
+        // the next chunk's stage: tested once, never waited for
+        const unsigned sg1 = consumed % S, par1 = (consumed / S) & 1u;
+        const int nr1 = min(T, rend - (r0 + T));
+        const int q0 = sm->kb[j + 1], q1 = sm->kb[j + 2];
+        const int qa = q0 & ~3;
+        if (tid < nr1 && (((q1 + 3) & ~3) - qa) <= CAP && fc_mbar_try_wait(&sm->full[sg1], par1)) {
+          const int *pj1 = reinterpret_cast<const int *>(sm->jraw[sg1]);
+          const unsigned char *pc1 = sm->jraw[sg1] + (qa - (q0 & ~15));
+          const int s1 = sm->off[sg1][tid] - qa, e1 = sm->off[sg1][tid + 1] - qa;
+          const int r1 = r + T;
+          for (int c = s1; c < e1; ++c) {
+            const int id = CODED ? r1 + sm->dict[pc1[c]] : pj1[c];
+            const int far = id - r1;
+            if (far > T || far < -T) {   // the near neighbours are this chunk's own gathers
+              if (xprefetch == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(V.x + id));
+              else                asm volatile("prefetch.global.L2 [%0];" ::"l"(V.x + id));
+            }
+          }
+        }
+      }
+      const int k0 = sm->kb[j], k1 = sm->kb[j + 1];
       const int ka = k0 & ~3;
       const bool staged = (((k1 + 3) & ~3) - ka) <= CAP;
       const double *pa = sm->a[sg];
-      const int *pj = sm->ja[sg];
+      const int *pj = reinterpret_cast<const int *>(sm->jraw[sg]);
+      const unsigned char *pc = sm->jraw[sg] + (ka - (k0 & ~15));   // CODED: pc[c] belongs to pa[c]
       const int *po = sm->off[sg];
       if (tid < nr) {
         const int s = po[tid], e = po[tid + 1];
@@ -238,6 +355,40 @@ struct fc_spmv_pipe {
         if (staged) {
           // thread = row: the 32 lanes of a warp read x at 32 consecutive rows' c-th neighbours, which on a
           // finite-volume numbering are (nearly) contiguous -- one or two L1 lines per warp gather
+          if (MODE != FC_MODE_DOT_FUSED && (CODED || PIPEG)) {
+            // Straight-line bodies for every row length (fc_row_part<N>): no predicates, no selects.  Full batches
+            // of eight first, then one body of exactly the remaining length; same operands, same left-to-right
+            // order.  Measured at 216^3 (profiles/r02_spmv_variants.txt): with one-byte codes the product phase of
+            // the persistent kernel takes 162-166 us this way and 172-176 us with the predicated batches below; with
+            // `ja` it is the other way round (185 vs 168 us), so each index format keeps the loop that suits it.
+            int c = s - ka;
+            const int ce = e - ka;
+            if (PIPEG) {
+              switch (nc) {
+                case 1: v = fc_row_part_x<1, RES>(pa, c, xc, v); break;
+                case 2: v = fc_row_part_x<2, RES>(pa, c, xc, v); break;
+                case 3: v = fc_row_part_x<3, RES>(pa, c, xc, v); break;
+                case 4: v = fc_row_part_x<4, RES>(pa, c, xc, v); break;
+                case 5: v = fc_row_part_x<5, RES>(pa, c, xc, v); break;
+                case 6: v = fc_row_part_x<6, RES>(pa, c, xc, v); break;
+                case 7: v = fc_row_part_x<7, RES>(pa, c, xc, v); break;
+                case 8: v = fc_row_part_x<8, RES>(pa, c, xc, v); break;
+                default: break;
+              }
+              c += nc;
+            }
+            for (; ce - c >= 8; c += 8) v = fc_row_part<8, RES, CODED>(pa, pj, pc, sm->dict, c, r, V.x, v);
+            switch (ce - c) {
+              case 1: v = fc_row_part<1, RES, CODED>(pa, pj, pc, sm->dict, c, r, V.x, v); break;
+              case 2: v = fc_row_part<2, RES, CODED>(pa, pj, pc, sm->dict, c, r, V.x, v); break;
+              case 3: v = fc_row_part<3, RES, CODED>(pa, pj, pc, sm->dict, c, r, V.x, v); break;
+              case 4: v = fc_row_part<4, RES, CODED>(pa, pj, pc, sm->dict, c, r, V.x, v); break;
+              case 5: v = fc_row_part<5, RES, CODED>(pa, pj, pc, sm->dict, c, r, V.x, v); break;
+              case 6: v = fc_row_part<6, RES, CODED>(pa, pj, pc, sm->dict, c, r, V.x, v); break;
+              case 7: v = fc_row_part<7, RES, CODED>(pa, pj, pc, sm->dict, c, r, V.x, v); break;
+              default: break;
+            }
+          } else {
           constexpr int U = 8;
           for (int c = s - ka; c < e - ka; c += U) {
             int id[U];
@@ -245,7 +396,7 @@ struct fc_spmv_pipe {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               const bool in = c + u < e - ka;
-              id[u] = in ? pj[c + u] : r;
+              id[u] = in ? (CODED ? r + sm->dict[pc[c + u]] : pj[c + u]) : r;
               av[u] = in ? pa[c + u] : 0.0;
             }
             if (MODE == FC_MODE_DOT_FUSED) {
@@ -265,6 +416,7 @@ struct fc_spmv_pipe {
                 v = RES ? v - t : v + t;
               }
             }
+          }
           }
         } else {  // a chunk too long for the staging buffers: straight from global memory
           for (int k = s; k < e; ++k) {
@@ -318,6 +470,16 @@ struct fc_spmv_pipe {
         if (tid == 0) fc_fence_proxy_async();
         issue_one(M);
       }
+    };
+    double xa[8], xb[8];
+    int na = 0, nb = 0;
+    if (PIPEG) {
+      for (int j = 0; j < nch; j += 2) {
+        chunk(j, xa, na, xb, nb);
+        if (j + 1 < nch) chunk(j + 1, xb, nb, xa, na);
+      }
+    } else {
+      for (int j = 0; j < nch; ++j) chunk(j, xa, na, xb, nb);
     }
     next = 0;
   }

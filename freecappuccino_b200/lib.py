@@ -54,9 +54,13 @@ TUNE_SWEEP_CHECK = 8
 TUNE_L2_KEEP = 9
 TUNE_DPCG_FUSED = 10
 TUNE_FACE_OCC = 11
+TUNE_MAT_KEEP = 12
+TUNE_JA_CODED = 13
+TUNE_X_PREFETCH = 14
+TUNE_DPCG_EAGER = 15
 TUNE_KEYS = {"spmv_kernel": TUNE_SPMV_KERNEL, "dpcg_persistent": TUNE_DPCG_PERSISTENT, "ctas_per_sm": TUNE_CTAS_PER_SM,
              "pipe_geometry": TUNE_PIPE_GEOMETRY, "sweep_p2p": TUNE_SWEEP_P2P, "sweep_tiled": TUNE_SWEEP_TILED,
-             "fused_grad": TUNE_FUSED_GRAD, "tile_ctas": TUNE_TILE_CTAS, "sweep_check": TUNE_SWEEP_CHECK, "l2_keep": TUNE_L2_KEEP, "dpcg_fused": TUNE_DPCG_FUSED, "face_occ": TUNE_FACE_OCC}
+             "fused_grad": TUNE_FUSED_GRAD, "tile_ctas": TUNE_TILE_CTAS, "sweep_check": TUNE_SWEEP_CHECK, "l2_keep": TUNE_L2_KEEP, "dpcg_fused": TUNE_DPCG_FUSED, "face_occ": TUNE_FACE_OCC, "mat_keep": TUNE_MAT_KEEP, "ja_coded": TUNE_JA_CODED, "x_prefetch": TUNE_X_PREFETCH, "dpcg_eager": TUNE_DPCG_EAGER}
 
 
 class MeshDesc(C.Structure):
@@ -96,7 +100,8 @@ class Timings(C.Structure):
                 ("spmv_ms", C.c_double), ("spmv_samples", C.c_int), ("sweep_tiles", C.c_int), ("launches", C.c_longlong),
                 ("persist_ms", C.c_double), ("persist_pupdate_ms", C.c_double), ("persist_spmv_ms", C.c_double),
                 ("persist_update_ms", C.c_double), ("persist_iters", C.c_int), ("persist_grid", C.c_int),
-                ("persist_mail_ms", C.c_double), ("uvw_assemble_ms", C.c_double), ("uvw_solve_ms", C.c_double)]
+                ("persist_mail_ms", C.c_double), ("uvw_assemble_ms", C.c_double), ("uvw_solve_ms", C.c_double),
+                ("persist_index_bytes", C.c_int), ("column_offsets", C.c_int)]
 
 
 # convective schemes of read_input.f90:97-133 -> (face_value branch, limiter) of fc_calcuvw_opts

@@ -340,6 +340,9 @@ typedef struct {
   double persist_mail_ms; /* of the remainder: waiting for the other ranks' partial sums */
   double uvw_assemble_ms; /* last fc_calcuvw: gradients + face + row kernels            */
   double uvw_solve_ms;    /* last fc_calcuvw: the three BiCGStab solves                 */
+  int persist_index_bytes; /* bytes per non-zero the persistent kernel read for the column index:
+                              1 (one-byte codes, FC_TUNE_JA_CODED) or 4 (`ja`); 0 when it did not run */
+  int column_offsets;      /* distinct column offsets ja(k) - row of the pattern, 0 when more than 256  */
 } fc_timings;
 /* Kernel selection, for measurements and A/B tests (defaults in brackets).     */
 enum {
@@ -349,7 +352,10 @@ enum {
                                   as one persistent cooperative kernel            */
   FC_TUNE_CTAS_PER_SM = 2,     /* persistent kernel: CTAs per SM, [0] = all that fit */
   FC_TUNE_PIPE_GEOMETRY = 3,   /* TMA pipeline (threads, non-zeros staged, stages):
-                                  0 256/2304/3, [1] 256/2304/2, 2 256/2048/2, 3 128/1024/2 */
+                                  0 256/2304/3, [1] 256/2304/2, 2 256/2048/2, 3 128/1024/2,
+                                  4 256/1824/3 with one-byte codes (hexahedra only).  Pipelines with three stages
+                                  gather x one chunk ahead into registers; measured slower than two stages
+                                  (profiles/r02_spmv_variants.txt), so they stay options                      */
   FC_TUNE_SWEEP_P2P = 4,       /* triangular sweeps (iccg, bicgstab): [0] one counter per level,
                                   1 point-to-point flags between 128-row blocks (experimental:
                                   same row sums, bit-identical results)                      */
@@ -367,6 +373,22 @@ enum {
                                   calcp assembly at 216^3: 2.72 / 2.45 / 2.84 ms)                               */
   FC_TUNE_L2_KEEP = 9,         /* persistent DPCG kernel: pk, zk, res, a_ii marked L2 evict_last (the matrix
                                   stream is evict_first): 0 never, 1 always, [2] when the four vectors fit  */
+  FC_TUNE_JA_CODED = 13,       /* persistent DPCG kernel: the column indices travel as one-byte codes,
+                                  ja[k] = row + offset[code[k]], when the pattern has at most 256 distinct column
+                                  offsets (7 on a structured hexahedral block): 9 instead of 12 bytes per non-zero
+                                  and product, same columns, bit-identical results: 0 off, 1 on, [2] from 2 M rows
+                                  (below that the product is bound by the latency of a 256-row chunk, not its bytes) */
+  FC_TUNE_DPCG_EAGER = 15,     /* persistent DPCG kernel on small partitions: fi += alf*pk runs behind the beta
+                                  reduction (between a CTA's arrival at the barrier and its release) instead of inside
+                                  the p-update, and the x/r update hands q = res/a_ii to the p-update (24 instead of
+                                  48 bytes per row there, no division); bit-identical iterates: 0 off, 1 on,
+                                  [2] up to 3.2 M rows per rank (measured: -4.6 % at 1.26 M, +1.5 % at 10 M)     */
+  FC_TUNE_X_PREFETCH = 14,     /* persistent DPCG kernel: while a 256-row chunk is computed, the far x gathers of the
+                                  next chunk are prefetched: 0 off, 1 into L1, 2 into L2                       */
+  FC_TUNE_MAT_KEEP = 12,       /* persistent DPCG kernel: percent (0..100) of the matrix chunks whose bulk copies are
+                                  marked L2 evict_last, spread evenly over every CTA's rows, so that this share of
+                                  `a` / `ja` stays in the L2 from one product to the next and only the rest streams
+                                  from HBM; [-1] chosen from the L2 size and the footprint of vectors and matrix  */
   FC_TUNE_TILE_CTAS = 7,       /* tiled sweeps: CTAs per SM the kernel's registers allow, [2] or 3           */
   FC_TUNE_SWEEP_TILED = 5      /* triangular sweeps: 0 one hand-over per dependency level,
                                   1 two-level schedule -- spatial tiles of <= 512 cells walked

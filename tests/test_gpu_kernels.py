@@ -123,6 +123,99 @@ def test_dpcg_persistent_equals_multi_kernel(fc):
     assert cases.rel_l2(out[0][3], out[1][3]) < 1e-10
 
 
+@pytest.mark.parametrize("name", ["hex", "hex_big", "poly", "skew", "shuffled"])
+def test_dpcg_coded_columns_are_bit_identical(fc, name):
+    """FC_TUNE_JA_CODED: the persistent kernel reads one-byte column codes (ja = row + offset[code]) instead of `ja`
+    when the pattern has at most 256 distinct column offsets.  Same columns, same order, same grid: iteration count,
+    residuals, solution and residual vector must not differ by a bit.  A numbering with more than 256 offsets (rows
+    shuffled at random) keeps `ja`."""
+    mesh = {"hex": lambda: cases.hex_case(40, 36, 20, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry")),
+            "hex_big": lambda: cases.hex_case(96, 64, 50),
+            "poly": lambda: cases.poly_case(9), "skew": lambda: cases.skew_case(14, 12, 10),
+            "shuffled": lambda: cases.hex_case(12, 11, 10)}[name]()
+    su = np.random.default_rng(3).standard_normal(mesh.numCells) * mesh.vol[:mesh.numCells]
+    out = {}
+    for coded in (0, 1):
+        ctx = fc.Context(0)
+        ctx.set_tuning(fc.TUNE_JA_CODED, coded)
+        if name == "shuffled":   # explicit CSR of a randomly renumbered Laplacian: ~n distinct offsets
+            n = mesh.numCells
+            ioffset, ja, diag, a = oracle_csr_shuffled(mesh)
+            x = np.zeros(n)
+            rep = ctx.solve_csr("dpcg", ioffset, ja, diag, a, su[:n], x, fc.solver_opts(1e-9, 5000))
+            res = np.zeros(0)
+        else:
+            ctx.set_mesh(mesh)
+            ctx.create_csr(download=False)
+            ctx.upload("APU", -np.ones(mesh.numCells))
+            ctx.upload("SU", su)
+            ctx.upload("PP", 0.01 * np.cos(np.arange(mesh.numTotal)))
+            ctx.laplacian("APU", "PP")
+            rep = ctx.solve("dpcg", "PP", fc.solver_opts(1e-9, 5000))
+            x, res = ctx.download("PP"), ctx.download("RES")
+        t = ctx.timings()
+        assert t.persist_iters == rep.iters, "the persistent kernel did not run"
+        assert rep.iters > 5
+        if name == "shuffled":
+            assert t.column_offsets == 0 and t.persist_index_bytes == 4
+        elif name in ("hex", "hex_big"):
+            assert t.column_offsets == 7 and t.persist_index_bytes == (1 if coded else 4)
+        else:
+            assert t.persist_index_bytes == (1 if coded and t.column_offsets else 4)
+        out[coded] = (rep.iters, rep.res0, rep.resl, x, res)
+        ctx.close()
+    assert out[0][:3] == out[1][:3], (name, out[0][:3], out[1][:3])
+    assert np.array_equal(out[0][3], out[1][3]) and np.array_equal(out[0][4], out[1][4]), name
+
+
+@pytest.mark.parametrize("name", ["hex", "poly", "skew"])
+def test_dpcg_eager_x_update_is_bit_identical(fc, name):
+    """FC_TUNE_DPCG_EAGER: fi += alf*pk behind the beta reduction and q = res/a_ii handed from the x/r update to the
+    p-update.  Same operands and rounding, same grid: iteration count, residuals, solution and final residual vector
+    must not differ by a bit -- also with nsw = 0, one iteration, and a stop after a few iterations."""
+    mesh = {"hex": lambda: cases.hex_case(40, 36, 20, kinds=("wall", "wall", "wall", "wall", "symmetry", "symmetry")),
+            "poly": lambda: cases.poly_case(9), "skew": lambda: cases.skew_case(14, 12, 10)}[name]()
+    su = np.random.default_rng(3).standard_normal(mesh.numCells) * mesh.vol[:mesh.numCells]
+    for sor, nsw in ((1e-9, 5000), (1e-30, 1), (1e-30, 7), (1e-9, 0)):
+        out = {}
+        for eager in (0, 1):
+            ctx = fc.Context(0)
+            ctx.set_mesh(mesh)
+            ctx.create_csr(download=False)
+            ctx.set_tuning(fc.TUNE_DPCG_EAGER, eager)
+            ctx.upload("APU", -np.ones(mesh.numCells))
+            ctx.upload("SU", su)
+            ctx.upload("PP", 0.01 * np.cos(np.arange(mesh.numTotal)))
+            ctx.laplacian("APU", "PP")
+            rep = ctx.solve("dpcg", "PP", fc.solver_opts(sor, nsw))
+            assert ctx.timings().persist_iters == rep.iters
+            out[eager] = (rep.iters, rep.res0, rep.resl, ctx.download("PP"), ctx.download("RES"))
+            ctx.close()
+        assert out[0][:3] == out[1][:3], (name, sor, nsw, out[0][:3], out[1][:3])
+        assert np.array_equal(out[0][3], out[1][3]) and np.array_equal(out[0][4], out[1][4]), (name, sor, nsw)
+
+
+def oracle_csr_shuffled(mesh):
+    """CSR (1-based ioffset / ja / diag + values) of the mesh's unit Laplacian with the rows renumbered at random."""
+    n = mesh.numCells
+    perm = np.random.default_rng(11).permutation(n)
+    own = perm[mesh.owner[:mesh.numInnerFaces] - 1]
+    nei = perm[mesh.neighbour[:mesh.numInnerFaces] - 1]
+    rows = np.concatenate([np.arange(n), own, nei])
+    cols = np.concatenate([np.arange(n), nei, own])
+    vals = np.concatenate([np.zeros(n), -np.ones(own.size), -np.ones(nei.size)])
+    np.add.at(vals, own, 1.0)
+    np.add.at(vals, nei, 1.0)
+    vals[:n] += 0.1
+    order = np.lexsort((cols, rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    ioffset = np.zeros(n + 1, np.int32)
+    np.add.at(ioffset, rows + 1, 1)
+    ioffset = np.cumsum(ioffset).astype(np.int32)
+    diag = np.flatnonzero(rows == cols).astype(np.int32)
+    return ioffset + 1, (cols + 1).astype(np.int32), diag + 1, vals
+
+
 @pytest.mark.parametrize("name", ["hex", "poly", "skew"])
 def test_dpcg_fused_p_scheme_is_bit_identical(fc, name):
     """FC_TUNE_DPCG_FUSED: the persistent kernel without a p-update phase (the product gathers p = q + bet*pold, the

@@ -81,6 +81,36 @@ def l2(n, key=None):
     ctx.close()
 
 
+def knobs(n, specs, iters=400):
+    """Persistent DPCG phase times for a list of knob settings: each spec is "key=value[+key=value...]"
+    (TUNE_KEYS names), e.g.  python tools/sweep_bench.py knobs 108 mat_keep=0 mat_keep=50 mat_keep=50+l2_keep=1"""
+    m, ctx = setup(n)
+    nnz, nc = m.nnz, m.numCells
+    ref = None
+    for spec in specs:
+        kv = dict(item.split("=") for item in spec.split("+"))
+        for k, v in kv.items():
+            ctx.set_tuning(lib.TUNE_KEYS[k], int(v))
+        best = None
+        for _ in range(3):
+            ctx.fill("PP", 0.0)
+            rep = ctx.solve("dpcg", "PP", lib.solver_opts(1e-30, iters))
+            t = ctx.timings()
+            if best is None or t.solve_ms < best[0]:
+                best = (t.solve_ms, t.persist_ms, t.persist_pupdate_ms, t.persist_spmv_ms, t.persist_update_ms, t.persist_iters,
+                        t.persist_grid, t.persist_index_bytes)
+        x = ctx.download("PP")[:nc]
+        if ref is None:
+            ref = x
+        it = max(best[5], 1)
+        print(json.dumps(dict(op="dpcg persistent", n=n, cells=nc, knobs=spec, iters=rep.iters, us_per_iteration=1e3 * best[0] / it,
+                              gbs=(12 * nnz + 116 * nc) / (best[0] / it) / 1e6,
+                              p_update_us=1e3 * best[2] / it, spmv_us=1e3 * best[3] / it, update_us=1e3 * best[4] / it,
+                              sync_us=1e3 * (best[1] - best[2] - best[3] - best[4]) / it, grid=best[6], index_bytes=best[7],
+                              bit_identical_to_first=bool(np.array_equal(x, ref)), resl=rep.resl)), flush=True)
+    ctx.close()
+
+
 def faces(n):
     """Assembly times for every register budget of the face kernels (FC_TUNE_FACE_OCC)."""
     import torch
@@ -121,6 +151,9 @@ def faces(n):
 
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "knobs":
+        knobs(int(sys.argv[2]), sys.argv[3:])
+        sys.exit(0)
     for n in [int(x) for x in sys.argv[2:]]:
         if what == "sweeps":
             sweeps(n)
