@@ -408,6 +408,7 @@ def run_ours(args):
             persist["spmv_ms"] += t.persist_spmv_ms; persist["update_ms"] += t.persist_update_ms
             persist["mail_ms"] += t.persist_mail_ms; persist["iters"] += t.persist_iters
             persist["grid"] = t.persist_grid
+            persist["index_bytes"] = t.persist_index_bytes
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
@@ -473,7 +474,14 @@ def run_ours(args):
         achieved = ab["dpcg_iter"] * iters_per_step / (launch_ms * 1e-3) / 1e9
         it = persist["iters"]
         spmv_us = 1e3 * persist["spmv_ms"] / it
-        roof = {"bound": "hbm", "kernel": "k_dpcg_persist<256,2304,2> (whole DPCG solve, one cooperative launch per step)",
+        ib = persist.get("index_bytes", 4) or 4
+        # what the kernel as written moves per iteration: (8 + index bytes) per non-zero, 100 per row
+        moved = (8 + ib) * mesh.nnz + 100 * mesh.numCells
+        roof = {"bound": "hbm", "kernel": "k_dpcg_persist<256,2304,2> (whole DPCG solve, one cooperative launch per step; column "
+                                          + ("indices as one-byte codes)" if ib == 1 else "indices as int32)"),
+                "index_bytes_per_nonzero": ib, "bytes_moved_per_iteration": moved,
+                "moved_gbs": moved * iters_per_step / (launch_ms * 1e-3) / 1e9,
+                "moved_frac": moved * iters_per_step / (launch_ms * 1e-3) / 1e9 / peak,
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8000": achieved / 8000.0,
                 "traffic": (traffic["dram_bytes_per_iteration"] * iters_per_step)

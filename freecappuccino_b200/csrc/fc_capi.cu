@@ -643,8 +643,8 @@ int fc_set_tuning(fc_context *ctx, int key, int value) {
     case FC_TUNE_MAT_KEEP: if (value < -1 || value > 100) return FC_ERR_ARG; ctx->tune_mat_keep = value; break;
     case FC_TUNE_L2_KEEP: if (value < 0 || value > 2) return FC_ERR_ARG; ctx->tune_l2_keep = value; break;
     case FC_TUNE_SWEEP_CHECK: if (value < 0 || value > 1) return FC_ERR_ARG; ctx->tune_sweep_check = value; break;
-    case FC_TUNE_TILE_CTAS: if (value != 2 && value != 3) return FC_ERR_ARG; ctx->tune_tile_ctas = value; break;
-    case FC_TUNE_SWEEP_TILED: if (value < 0 || value > 4) return FC_ERR_ARG; ctx->tune_sweep_tiled = value; break;
+    case FC_TUNE_TILE_CTAS: if (value < 2 || value > 6) return FC_ERR_ARG; ctx->tune_tile_ctas = value; break;
+    case FC_TUNE_SWEEP_TILED: if (value < 0 || value > 5) return FC_ERR_ARG; ctx->tune_sweep_tiled = value; break;
     default: FC_FAIL(FC_ERR_ARG, "fc_set_tuning: unknown key");
   }
   return FC_OK;

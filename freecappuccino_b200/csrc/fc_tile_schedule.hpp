@@ -368,14 +368,17 @@ inline long long dir_cost(const fc_tile_dir &D) {
 }  // namespace fc_tile_detail
 
 // 0-based CSR (columns ascending inside a row, diag = position of the diagonal) and the cell centres of its rows
+// `min_shrink` > 0 starts from narrower bins (7, 6, 5 ... cells per axis instead of 8): smaller tiles with fewer local
+// levels each, more tile levels -- a measurement knob (FC_TILE_MIN_SHRINK in the library)
 inline fc_tile_schedule fc_build_tile_schedule(int n, const int *ioffset, const int *ja, const int *diag,
-                                               const double *xc, const double *yc, const double *zc) {
+                                               const double *xc, const double *yc, const double *zc,
+                                               int min_shrink = 0) {
   using namespace fc_tile_detail;
   fc_tile_schedule S;
   if (n < 1) { S.why = "empty matrix"; return S; }
   std::vector<int> tile, count;
   int ntiles = 0;
-  for (int shrink = 0; shrink <= 4; ++shrink) {
+  for (int shrink = std::max(0, std::min(min_shrink, 4)); shrink <= 4; ++shrink) {
     int target = 0;
     ntiles = assign_tiles(n, ioffset, ja, diag, xc, yc, zc, shrink, tile, target);
     count.assign(ntiles, 0);

@@ -31,6 +31,12 @@ __device__ __forceinline__ double fct_unset() { return __longlong_as_double(-1ll
 // barrier among the first N threads of the CTA only (the other warps have retired): named barrier 1
 #define FCT_WALK_SYNC(N) asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory")
 #define FCT_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+// k_tile_walk_vf: counters in shared memory between the helper warps (fold a value of another tile, count down) and
+// the walking warps (spin until the level's counter is zero)
+#define FCT_SATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define FCT_LD_SVOL(p) (*(const volatile int *)(p))
+#define FCT_FENCE_BLOCK() __threadfence_block()
+#define FCT_BACKOFF(ns) __nanosleep(ns)
 #endif
 
 // Tiled mode (FC_TUNE_SWEEP_TILED; schedule: fc_tile_schedule.hpp).  A CTA owns one spatial tile of at most FC_TILE
@@ -287,6 +293,9 @@ struct fct_walk_layout {
 #ifndef FCT_TRACE   // measurement aid (-DFC_SWEEP_TRACE builds define it): time stamp number i of tile b
 #define FCT_TRACE(i)
 #endif
+#ifndef FCT_TRACE_AT   // the same, written by thread t
+#define FCT_TRACE_AT(t, i)
+#endif
 struct fct_handover {   // FLAGS: the producers' flags (fc_tile_dir::prod); otherwise the tile-level counters
   const int *blk_level, *lev_blocks_before, *prod, *prod_cnt;
   unsigned int *done, *ready, *flag;
@@ -494,5 +503,239 @@ FCT_UNROLL
       if (old + 1u == H.sweep_no * nb) st_release(H.ready + lev, H.sweep_no);
     }
   }
+  FCT_TRACE(7);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_tile_walk_vf (FC_TUNE_SWEEP_TILED = 5): the staged walk of k_tile_walk with the value-as-flag hand-over of
+// k_tile_sweep_vf, the polls taken off the walk's critical path.
+//
+// With flags a tile starts when its producers have FINISHED: the tile-to-tile critical path of the 216^3 sweep is
+// 79 tile levels x (flag visible 1.8 + fold 1.3 + walk 3.6 + release 0.8 us) = 0.59 ms, three times the time its bytes
+// need.  But the first rows of a tile only need the rows on the near face of its producers, which those produce a
+// third of the way through their own walk.  Here `out` holds the "unset" pattern before the sweep (as in
+// k_tile_sweep_vf; the sweeps re-arm each other's vectors) and the CTA has two kinds of threads after the staging:
+//   * ST staging threads turn into HELPERS: each keeps the (at most SPT x PRE) entries of its slots that name rows of
+//     other tiles in registers, polls their values round-robin -- every round one batch of L2 reads for everything
+//     still missing -- and, when a value has arrived, folds it into the staged coefficient exactly as pass 3 of
+//     k_tile_walk does and counts the slot's local level down in shared memory;
+//   * WT WALKERS (their own two warps: they stage nothing) walk the local levels as before and, before level l, wait
+//     until the level's count of unfolded entries is zero.  They publish every row with a relaxed store the moment it
+//     is computed; no flag, no fence.
+// In the steady state a tile trails its producers by the levels of the face it needs plus one hand-over latency
+// instead of by their whole walk, and the helpers run ahead of the walkers, so no poll sits on a level's critical
+// path.  Tickets are drawn in tile order and a tile only reads rows of tiles with smaller tickets, so every wait is
+// for a CTA that is already running.  Same operands, same left-to-right sums: bit-identical to every other schedule.
+template <int MODE, int PRE, int ST, int WT, int OCC>
+FCT_WALK_KERNEL(ST + WT, OCC)
+k_tile_walk_vf(const int4 *__restrict__ meta_rm, const int *__restrict__ blk_nlev, unsigned int *ticket,
+               unsigned int ticket_base, const int *__restrict__ tja, const int *__restrict__ diag,
+               const int *__restrict__ tpos, const double *__restrict__ a, const double *__restrict__ d,
+               double *in_rw, double *out, double *arm, double small, double padd, const fc_scalars *sc,
+               bool rearm_in, unsigned int backoff_ns) {
+  using L = fct_walk_layout<MODE, PRE>;
+  constexpr int NS = FC_TILE;
+  constexpr int ONE = NS;   // z[ONE] = 1.0
+  constexpr int TT = ST + WT;
+  FCT_DYN_SMEM(fct_raw);
+  FCT_SHARED unsigned int s_b;
+  FCT_SHARED int s_long;
+  double *const s_c = reinterpret_cast<double *>(fct_raw + L::off_c);
+  double *const s_c2 = reinterpret_cast<double *>(fct_raw + L::off_c2);
+  double *const s_z = reinterpret_cast<double *>(fct_raw + L::off_z);
+  double *const s_di = reinterpret_cast<double *>(fct_raw + L::off_di);
+  unsigned short *const s_dep = reinterpret_cast<unsigned short *>(fct_raw + L::off_dep);
+  int *const s_row = reinterpret_cast<int *>(fct_raw + L::off_row);
+  int *const s_s = reinterpret_cast<int *>(fct_raw + L::off_s);
+  int *const s_e = reinterpret_cast<int *>(fct_raw + L::off_e);
+  short *const s_lev = reinterpret_cast<short *>(fct_raw + L::off_lev);
+  short *const s_start = reinterpret_cast<short *>(fct_raw + L::off_start);
+  int *const s_pend = reinterpret_cast<int *>(fct_raw + ((L::bytes + 15) & ~(size_t)15));   // [NS + 2] per local level
+  if (sc && sc->done) return;
+  const int tid = (int)FCT_TID;
+  if (tid == 0) { s_b = FCT_TICKET(ticket) - ticket_base; s_long = 0; s_z[ONE] = 1.0; }
+  for (int i = tid; i < NS + 2; i += TT) s_pend[i] = 0;
+  FCT_SYNC();
+  const unsigned int b = s_b;
+  FCT_TRACE(0);
+  const int nl = blk_nlev[b];
+  const bool walker = tid < WT;
+  const int st = tid - WT;   // staging / helper thread number
+  constexpr int SPT = NS / ST;
+  int rw[SPT], ss[SPT], ee[SPT], sl[SPT], lv[SPT];
+  double av[SPT][PRE], tv[SPT][PRE], vv[SPT], dv[SPT];
+  int jv[SPT][PRE];
+  if (!walker) {
+    // ---- pass 1: descriptors, in ascending row order (see k_tile_walk) ----
+FCT_UNROLL
+    for (int u = 0; u < SPT; ++u) {
+      const int4 mt = meta_rm[(size_t)b * NS + st + u * ST];   // row, slot | level << 16, triangle [s, e)
+      const int slot = mt.x >= 0 ? (mt.y & 0xffff) : st + u * ST;
+      rw[u] = mt.x; ss[u] = mt.z; ee[u] = mt.w; sl[u] = slot;
+      lv[u] = mt.x >= 0 ? (mt.y >> 16) : nl;
+      s_row[slot] = mt.x;
+      s_lev[slot] = (short)lv[u];
+      s_s[slot] = mt.z;
+      s_e[slot] = mt.w;
+      if (mt.x >= 0 && mt.w - mt.z > PRE) s_long = 1;
+    }
+    // ---- pass 2: start value, d, the first PRE coefficients and columns ----
+FCT_UNROLL
+    for (int u = 0; u < SPT; ++u) {
+      const int row = rw[u] >= 0 ? rw[u] : 0;
+      if (MODE == TRI_FWD || MODE == TRI_BWD) { vv[u] = in_rw[row]; dv[u] = d[row]; }
+      else { vv[u] = a[diag[row]]; dv[u] = 0.0; }
+FCT_UNROLL
+      for (int q = 0; q < PRE; ++q) {
+        const bool live = rw[u] >= 0 && ss[u] + q < ee[u];
+        const int k = live ? ss[u] + q : 0;
+        av[u][q] = a[k];
+        jv[u][q] = live ? tja[k] : -(ONE + 1);   // a dead entry depends on "one" with coefficient 0
+        if (MODE == TRI_DILU) tv[u][q] = a[tpos[k]];
+        if (!live) av[u][q] = 0.0;
+      }
+    }
+FCT_UNROLL
+    for (int u = 0; u < SPT; ++u) {
+      const int slot = sl[u];
+      if (rw[u] < 0) continue;
+      // the vectors the next sweeps hand over through: unset again (see k_tile_sweep_vf)
+      if (MODE == TRI_FWD && arm) arm[rw[u]] = fct_unset();
+      if (MODE == TRI_BWD && rearm_in) in_rw[rw[u]] = fct_unset();
+      s_z[slot] = MODE == TRI_BWD ? vv[u] / (dv[u] + small) : vv[u];   // z = z/(d+small), iccg.f90:102
+      if (L::SOLVE) s_di[slot] = dv[u];
+FCT_UNROLL
+      for (int q = 0; q < PRE; ++q) {
+        if (jv[u][q] < 0) {
+          double c = av[u][q], c2 = 1.0;
+          const int dep = -jv[u][q] - 1;   // slot of the same tile, or ONE for a dead entry (c = 0)
+          if (MODE == TRI_DIC) c = c * c;
+          else if (MODE == TRI_DIC_PAR) c2 = dep == ONE ? 1.0 : c;
+          else if (MODE == TRI_DILU) c2 = dep == ONE ? 1.0 : tv[u][q];
+          s_c[q * NS + slot] = c;
+          if (L::TWO) s_c2[q * NS + slot] = c2;
+          s_dep[q * NS + slot] = (unsigned short)dep;
+        } else {
+          FCT_SATOMIC_ADD(s_pend + lv[u], 1);   // a row of another tile: the level waits for it
+        }
+      }
+    }
+  }
+  FCT_SYNC();
+  FCT_TRACE(1);
+  for (int slot = tid; slot < NS; slot += TT) {   // first slot of every local level
+    const int lvl = s_lev[slot];
+    if (slot == 0 || s_lev[slot - 1] != lvl) s_start[lvl] = (short)slot;
+    if (slot == NS - 1 && lvl != nl) s_start[nl] = (short)NS;   // a full tile has no padding slot
+  }
+  FCT_SYNC();
+  if (!walker) {
+    // ---- helpers: poll what other tiles produce, fold it in, count the level down ----
+    unsigned int pend = 0u;
+    double zv[SPT][PRE];
+FCT_UNROLL
+    for (int u = 0; u < SPT; ++u)
+FCT_UNROLL
+      for (int q = 0; q < PRE; ++q)
+        if (rw[u] >= 0 && jv[u][q] >= 0) {
+          pend |= 1u << (u * PRE + q);
+          zv[u][q] = FCT_LD_POLL(out + jv[u][q]);
+        }
+    fc_spin_guard g;
+    while (pend) {
+      bool progress = false;
+FCT_UNROLL
+      for (int u = 0; u < SPT; ++u) {
+FCT_UNROLL
+        for (int q = 0; q < PRE; ++q) {
+          if (pend & (1u << (u * PRE + q))) {
+            const double zj = zv[u][q];
+            if (!fct_is_unset(zj)) {
+              const int slot = sl[u];
+              double c = av[u][q];
+              if (MODE == TRI_FWD || MODE == TRI_BWD) c = c * zj;
+              else if (MODE == TRI_DIC) c = (c * c) * zj;            // iccg.f90:80
+              else if (MODE == TRI_DIC_PAR) c = c * zj * c;          // src-parallel/iccg.f90:97
+              else c = c * zj * tv[u][q];                            // bicgstab.f90:76
+              s_c[q * NS + slot] = c;
+              if (L::TWO) s_c2[q * NS + slot] = 1.0;
+              s_dep[q * NS + slot] = (unsigned short)ONE;
+              FCT_FENCE_BLOCK();   // the folded entry before the count
+              FCT_SATOMIC_ADD(s_pend + lv[u], -1);
+              pend &= ~(1u << (u * PRE + q));
+              progress = true;
+            } else {
+              zv[u][q] = FCT_LD_POLL(out + jv[u][q]);
+            }
+          }
+        }
+      }
+      // a helper that found nothing sleeps: 18 spinning helper warps per SM would take the issue slots of the 6 walking ones
+      if (!progress) { g.tick(); FCT_BACKOFF(backoff_ns); }
+    }
+    FCT_TRACE_AT(WT, 6);
+    return;
+  }
+  FCT_TRACE(2);
+  // ---- walkers: the local levels, branch-free, shared memory only; a level starts when nothing of it is unfolded ----
+  const bool any_long = s_long != 0;
+  for (int l = 0; l < nl; ++l) {
+    {
+      fc_spin_guard g;
+      while (FCT_LD_SVOL(s_pend + l) != 0) g.tick();
+    }
+    FCT_FENCE_BLOCK();
+    if (l == 0) FCT_TRACE(3);
+    if (l == nl / 2) FCT_TRACE(4);
+    const int s0 = s_start[l], s1 = s_start[l + 1];
+    for (int slot = s0 + tid; slot < s1; slot += WT) {
+      double cq[PRE], zq[PRE], c2q[PRE];
+      int dq[PRE];
+FCT_UNROLL
+      for (int q = 0; q < PRE; ++q) {
+        cq[q] = s_c[q * NS + slot];
+        dq[q] = s_dep[q * NS + slot];
+        if (L::TWO) c2q[q] = s_c2[q * NS + slot];
+      }
+      double v = s_z[slot];
+      const int row = s_row[slot];
+      __asm__ __volatile__("" ::: "memory");
+FCT_UNROLL
+      for (int q = 0; q < PRE; ++q) zq[q] = s_z[dq[q]];
+      __asm__ __volatile__("" ::: "memory");
+FCT_UNROLL
+      for (int q = 0; q < PRE; ++q) {
+        cq[q] = cq[q] * zq[q];
+        if (L::TWO) cq[q] = cq[q] * c2q[q];
+      }
+FCT_UNROLL
+      for (int q = 0; q < PRE; ++q) v = v - cq[q];
+      if (any_long) {                                              // rows longer than PRE (none on hex / BCC meshes)
+        const int e = s_e[slot];
+        for (int k = s_s[slot] + PRE; k < e; ++k) {
+          const int j = tja[k];
+          double zj;
+          if (j < 0) {
+            zj = s_z[-j - 1];
+          } else {
+            zj = FCT_LD_POLL(out + j);
+            fc_spin_guard g;
+            while (fct_is_unset(zj)) { g.tick(); zj = FCT_LD_POLL(out + j); }
+          }
+          const double ak = a[k];
+          if (MODE == TRI_FWD || MODE == TRI_BWD) v = v - ak * zj;
+          else if (MODE == TRI_DIC) v = v - (ak * ak) * zj;
+          else if (MODE == TRI_DIC_PAR) v = v - ak * zj * ak;
+          else v = v - ak * zj * a[tpos[k]];
+        }
+      }
+      const double r = L::SOLVE ? v * s_di[slot] : 1.0 / (v + padd);
+      s_z[slot] = r;
+      FCT_ST_PUB(out + row, r);
+    }
+    FCT_WALK_SYNC(WT);
+  }
+  FCT_TRACE(5);
   FCT_TRACE(7);
 }

@@ -333,6 +333,10 @@ __device__ unsigned long long *fct_trace_buf = nullptr;
   do {                                                                                                     \
     if (fct_trace_buf && threadIdx.x == 0 && (b & 15u) == 0u) fct_trace_buf[(size_t)(b >> 4) * 12 + (i)] = fc_globaltimer(); \
   } while (0)
+#define FCT_TRACE_AT(t, i)                                                                                 \
+  do {                                                                                                     \
+    if (fct_trace_buf && threadIdx.x == (t) && (b & 15u) == 0u) fct_trace_buf[(size_t)(b >> 4) * 12 + (i)] = fc_globaltimer(); \
+  } while (0)
 #endif
 static_assert(FC_TILE_MAXP == FC_TRI_MAXP, "one producer-table width");
 #include "fc_tile_sweep.cuh"   // k_tile_sweep<MODE, PRE, P2P>
@@ -443,6 +447,25 @@ int launch_walk(fc_context *ctx, fc_levels &T, unsigned int tbase, const double 
   return FC_OK;
 }
 
+// k_tile_walk_vf: 256 staging / helper threads + 64 walkers, the tile's shared layout plus one counter per local level
+template <int MODE, int PRE, int OCC = 3>
+int launch_walk_vf(fc_context *ctx, fc_levels &T, unsigned int tbase, const double *a, const double *d, double *in_rw,
+                   double *out, double *arm, double small, double padd, bool guarded, bool rearm_in) {
+  auto kern = k_tile_walk_vf<MODE, PRE, FC_STAGE_THREADS, FC_WALK_THREADS, OCC>;
+  static const unsigned int backoff = getenv("FC_SWEEP_BACKOFF_NS") ? (unsigned int)atoi(getenv("FC_SWEEP_BACKOFF_NS")) : 256u;
+  constexpr size_t smem = ((fct_walk_layout<MODE, PRE>::bytes + 15) & ~(size_t)15) + sizeof(int) * (FC_TILE + 2);
+  static bool set[FC_MAX_DEVICES];
+  const int dev = ctx->device >= 0 && ctx->device < FC_MAX_DEVICES ? ctx->device : 0;
+  if (!set[dev] || dev != ctx->device) {
+    FC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set[dev] = true;
+  }
+  kern<<<T.nblocks, FC_STAGE_THREADS + FC_WALK_THREADS, smem, ctx->stream>>>(
+      T.meta_rm, T.blk_nlev, T.ticket, tbase, ctx->tja, ctx->diag, ctx->tpos, a, d, in_rw, out, arm, small, padd,
+      guarded ? ctx->sc : nullptr, rearm_in, backoff);
+  return FC_OK;
+}
+
 // `arm` (forward sweep of the value-as-flag mode): the vector the following backward sweep writes, see fc_tile_sweep.cuh
 template <int MODE>
 int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const double *in, double *out,
@@ -492,6 +515,53 @@ int sweep(fc_context *ctx, fc_levels &L, const double *a, const double *d, const
         }
       }
 #endif
+    } else if (ctx->tune_sweep_tiled == 5) {
+      // staged walk + value-as-flag hand-over (k_tile_walk_vf); the arming of the vectors is that of mode 3 below
+      const bool check = ctx->tune_sweep_check != 0;
+      if (MODE == TRI_FWD || MODE == TRI_BWD) {
+        if (ctx->vf_armed != out) FC_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * (size_t)ctx->n, ctx->stream));
+      } else {
+        FC_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * (size_t)ctx->n, ctx->stream));
+      }
+      ctx->vf_armed = nullptr;
+      double *in_rw = const_cast<double *>(in);
+      double *armv = MODE == TRI_FWD ? arm : nullptr;
+#ifdef FC_SWEEP_TRACE
+      unsigned long long *trbuf = nullptr;
+      const bool tracing = MODE == TRI_FWD && getenv("FC_SWEEP_TRACE_FILE") && T.epoch == 5;
+      const size_t ntr = ((size_t)T.nblocks / 16 + 1) * 12;
+      if (tracing) {
+        FC_CUDA(cudaMalloc((void **)&trbuf, ntr * 8));
+        FC_CUDA(cudaMemsetAsync(trbuf, 0, ntr * 8, ctx->stream));
+        FC_CUDA(cudaMemcpyToSymbolAsync(fct_trace_buf, &trbuf, sizeof(trbuf), 0, cudaMemcpyHostToDevice, ctx->stream));
+      }
+#endif
+      if (ctx->tiles_pre8) FC_CHECK((launch_walk_vf<MODE, 8>(ctx, T, tbase, a, d, in_rw, out, armv, small, padd, guarded, !check)));
+      else if (ctx->tiles_pre3 && ctx->tune_tile_ctas == 4) FC_CHECK((launch_walk_vf<MODE, 3, 4>(ctx, T, tbase, a, d, in_rw, out, armv, small, padd, guarded, !check)));
+      else if (ctx->tiles_pre3 && ctx->tune_tile_ctas == 5) FC_CHECK((launch_walk_vf<MODE, 3, 5>(ctx, T, tbase, a, d, in_rw, out, armv, small, padd, guarded, !check)));
+      else if (ctx->tiles_pre3 && ctx->tune_tile_ctas == 6) FC_CHECK((launch_walk_vf<MODE, 3, 6>(ctx, T, tbase, a, d, in_rw, out, armv, small, padd, guarded, !check)));
+      else if (ctx->tiles_pre3) FC_CHECK((launch_walk_vf<MODE, 3>(ctx, T, tbase, a, d, in_rw, out, armv, small, padd, guarded, !check)));
+      else FC_CHECK((launch_walk_vf<MODE, 4>(ctx, T, tbase, a, d, in_rw, out, armv, small, padd, guarded, !check)));
+      FC_LAUNCH_CHECK();
+#ifdef FC_SWEEP_TRACE
+      if (tracing) {
+        std::vector<unsigned long long> h(ntr);
+        FC_CUDA(cudaMemcpyAsync(h.data(), trbuf, ntr * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        unsigned long long *nullp = nullptr;
+        FC_CUDA(cudaMemcpyToSymbolAsync(fct_trace_buf, &nullp, sizeof(nullp), 0, cudaMemcpyHostToDevice, ctx->stream));
+        FC_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(trbuf);
+        if (FILE *fp = fopen(getenv("FC_SWEEP_TRACE_FILE"), "w")) {
+          for (size_t i = 0; i + 12 <= ntr; i += 12) {
+            for (int c = 0; c < 12; ++c) fprintf(fp, "%llu ", h[i + c]);
+            fprintf(fp, "\n");
+          }
+          fclose(fp);
+        }
+      }
+#endif
+      if (MODE == TRI_FWD && arm) ctx->vf_armed = arm;
+      if (MODE == TRI_BWD && !check) ctx->vf_armed = in_rw;
     } else if (ctx->tune_sweep_tiled == 3) {
       // value-as-flag hand-over: `out` must be all "unset" when the kernel starts.  The factor sweeps and a forward
       // sweep whose target has not been re-armed by the previous backward sweep pay one memset; in the steady state
@@ -662,7 +732,11 @@ int build_tiles(fc_context *ctx) {
   FC_CUDA(cudaMemcpy(yc.data(), ctx->yc, sizeof(double) * n, cudaMemcpyDeviceToHost));
   FC_CUDA(cudaMemcpy(zc.data(), ctx->zc, sizeof(double) * n, cudaMemcpyDeviceToHost));
   const fc_tile_schedule S =
-      fc_build_tile_schedule(ctx->n, ioffset.data(), ja.data(), diag.data(), xc.data(), yc.data(), zc.data());
+      fc_build_tile_schedule(ctx->n, ioffset.data(), ja.data(), diag.data(), xc.data(), yc.data(), zc.data(),
+                             // polyhedral rows (~15 non-zeros) walk 32 local levels in a 7-cell bin; bins of 6 cells per
+                             // axis measured 11 % faster on a 4.2 M-cell BCC-Voronoi mesh (profiles/r02_poly_bins.txt),
+                             // bins of 5 slower again; hexahedra keep 8
+                             getenv("FC_TILE_MIN_SHRINK") ? atoi(getenv("FC_TILE_MIN_SHRINK")) : ((long long)nnz > 10LL * n ? 2 : 0));
   ctx->tiles_why = S.why;
   if (!S.ok) return FC_OK;
   // bins cut into runs of consecutive rows (fc_tile_schedule.hpp repair_tiles) can degenerate into a long chain: keep

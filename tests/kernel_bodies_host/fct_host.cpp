@@ -57,6 +57,10 @@ static inline double fct_unset() { const long long x = -1ll; double v; std::memc
 namespace { std::barrier<> *fct_walk_bar = nullptr; }
 #define FCT_WALK_SYNC(N) fct_walk_bar->arrive_and_wait()
 #define FCT_DYN_SMEM(name) alignas(16) static unsigned char name[160 * 1024]
+#define FCT_SATOMIC_ADD(p, v) __atomic_fetch_add((p), (v), __ATOMIC_ACQ_REL)
+#define FCT_LD_SVOL(p) __atomic_load_n((p), __ATOMIC_ACQUIRE)
+#define FCT_FENCE_BLOCK() __atomic_thread_fence(__ATOMIC_SEQ_CST)
+#define FCT_BACKOFF(ns) std::this_thread::yield()
 static inline unsigned int ld_acquire(const unsigned int *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 static inline void st_release(unsigned int *p, unsigned int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 static inline unsigned int atom_add_acq_rel(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
@@ -316,6 +320,54 @@ int fct_emu_walk(void *h, int mode, int pre8, int flags, int n, const int *ioffs
   fct_bar = nullptr;
   fct_walk_bar = nullptr;
   return 0;
+}
+
+// k_tile_walk_vf (256 staging / helper threads + 64 walkers, value-as-flag hand-over), CTA by CTA in ticket order.
+// Same checks as fct_emu_sweep_vf: the result, and that the forward sweep re-arms `arm`, the backward sweep its input.
+int fct_emu_walk_vf(void *h, int mode, int pre8, int n, const int *ioffset, const int *diag, const int *tpos,
+                    const double *a, const double *d, const double *in, double *out, double small, double padd) {
+  const fc_tile_schedule &S = *(fc_tile_schedule *)h;
+  const fc_tile_dir &D = mode == TRI_BWD ? S.upper : S.lower;
+  unsigned int ticket = 0;
+  constexpr int ST = 256, WT = 64;
+  using kernel_t = void (*)(const int4 *, const int *, unsigned int *, unsigned int, const int *, const int *,
+                            const int *, const double *, const double *, double *, double *, double *, double, double,
+                            const fc_scalars *, bool, unsigned int);
+  kernel_t k = nullptr;
+#define FCT_PICK(M)                                                                                   \
+  case M:                                                                                             \
+    k = pre8 == 2 ? k_tile_walk_vf<M, 3, ST, WT, 2> : pre8 ? k_tile_walk_vf<M, 8, ST, WT, 2>          \
+                                                           : k_tile_walk_vf<M, 4, ST, WT, 2>;         \
+    break;
+  switch (mode) {
+    FCT_PICK(TRI_FWD) FCT_PICK(TRI_BWD) FCT_PICK(TRI_DIC) FCT_PICK(TRI_DIC_PAR) FCT_PICK(TRI_DILU)
+    default: return -1;
+  }
+#undef FCT_PICK
+  std::vector<double> in_copy(in, in + n), arm(n, 0.0);
+  for (int i = 0; i < n; ++i) out[i] = fct_unset();
+  std::barrier<> bar(ST + WT), wbar(WT);
+  fct_bar = &bar;
+  fct_walk_bar = &wbar;
+  std::vector<std::thread> th;
+  th.reserve(ST + WT);
+  for (int t = 0; t < ST + WT; ++t)
+    th.emplace_back([&, t]() {
+      fct_tid = (unsigned)t;
+      for (int b = 0; b < D.nblocks; ++b) {
+        k((const int4 *)D.meta_rm.data(), D.blk_nlev.data(), &ticket, 0u, S.tja.data(), diag, tpos, a, d, in_copy.data(),
+          out, mode == TRI_FWD ? arm.data() : nullptr, small, padd, nullptr, true, 0u);
+        bar.arrive_and_wait();   // next CTA: the static "shared" arrays are reused
+      }
+    });
+  for (auto &x : th) x.join();
+  fct_bar = nullptr;
+  fct_walk_bar = nullptr;
+  int bad = 0;
+  if (mode == TRI_FWD) for (int i = 0; i < n; ++i) bad += fct_is_unset(arm[i]) ? 0 : 1;
+  if (mode == TRI_BWD) for (int i = 0; i < n; ++i) bad += fct_is_unset(in_copy[i]) ? 0 : 1;
+  for (int i = 0; i < n; ++i) bad += fct_is_unset(out[i]) ? 1 : 0;
+  return bad;
 }
 
 }  // extern "C"

@@ -33,11 +33,11 @@ def fc():
 
 @pytest.mark.parametrize("name", list(MESHES))
 @pytest.mark.parametrize("solver", ["iccg", "bicgstab"])
-@pytest.mark.parametrize("mode", ["p2p", "tiled", "tiled-p2p", "tiled-vf", "tiled-walk"])
+@pytest.mark.parametrize("mode", ["p2p", "tiled", "tiled-p2p", "tiled-vf", "tiled-walk", "tiled-walk-vf"])
 def test_sweep_variants_are_bit_identical_to_level_sweeps(fc, name, solver, mode):
     mesh = MESHES[name]()
     key, value = {"p2p": (fc.TUNE_SWEEP_P2P, 1), "tiled": (fc.TUNE_SWEEP_TILED, 1), "tiled-p2p": (fc.TUNE_SWEEP_TILED, 2),
-                  "tiled-vf": (fc.TUNE_SWEEP_TILED, 3), "tiled-walk": (fc.TUNE_SWEEP_TILED, 4)}[mode]
+                  "tiled-vf": (fc.TUNE_SWEEP_TILED, 3), "tiled-walk": (fc.TUNE_SWEEP_TILED, 4), "tiled-walk-vf": (fc.TUNE_SWEEP_TILED, 5)}[mode]
     su = np.random.default_rng(5).standard_normal(mesh.numCells) * mesh.vol[:mesh.numCells]
     res = []
     for p2p in (0, 1):

@@ -296,6 +296,39 @@ def test_value_as_flag_kernel_source_on_host_threads_equals_natural_order_sweeps
         host.fct_free(C.c_void_p(h))
 
 
+@pytest.mark.parametrize("name", EMU_MESHES + ["pitzDaily", "poly-rank-of-4", "hex-24x20x17"])
+def test_tile_walk_vf_kernel_source_on_host_threads_equals_natural_order_sweeps(host, name):
+    """k_tile_walk_vf of fc_tile_sweep.cuh (FC_TUNE_SWEEP_TILED = 5: the staged walk of mode 4 with the value-as-flag
+    hand-over of mode 3 -- 256 helper threads poll and fold the values of other tiles, 64 walkers wait per local level
+    on a shared-memory count): the kernel source on host threads, all five modes, the three staging widths; also that
+    the forward sweep re-arms the backward sweep's target and the backward sweep its own input."""
+    s = System(MESHES[name]())
+    h, info = build(host, s)
+    try:
+        assert host.fct_ok(C.c_void_p(h))
+        zero = np.zeros(s.n)
+
+        def emu(mode, d, src, padd=0.0, pre8=0):
+            ref = np.zeros(s.n)
+            host.fct_reference_sweep(mode, s.n, ip(s.ioffset), ip(s.ja), ip(s.diag), ip(s.tpos), dp(s.a), dp(d), dp(src),
+                                     dp(ref), C.c_double(1e-20), C.c_double(padd))
+            out = np.zeros(s.n)
+            rc = host.fct_emu_walk_vf(C.c_void_p(h), mode, pre8, s.n, ip(s.ioffset), ip(s.diag), ip(s.tpos), dp(s.a),
+                                      dp(d), dp(src), dp(out), C.c_double(1e-20), C.c_double(padd))
+            assert rc == 0, (name, mode, pre8, rc)
+            assert np.array_equal(ref, out), (name, mode, pre8)
+            return out
+
+        for pre8 in (0, 1, 2):   # staged entries per row: 4, 8, 3 (rows longer than that poll inside the walk)
+            emu(DIC, zero, zero, pre8=pre8)
+            emu(DIC_PAR, zero, zero, padd=1e-20, pre8=pre8)
+            d = emu(DILU, zero, zero, pre8=pre8)
+            t = emu(FWD, d, s.r, pre8=pre8)
+            emu(BWD, d, t, pre8=pre8)
+    finally:
+        host.fct_free(C.c_void_p(h))
+
+
 def renumbered(s, perm):
     """The same matrix with rows / columns renumbered: new row perm[i] = old row i; columns ascending again."""
     n = s.n

@@ -20,7 +20,8 @@ from freecappuccino_b200 import cases, lib  # noqa: E402
 
 
 def setup(n):
-    m = cases.hex_case(n, n, n)
+    poly = os.environ.get("MESH") == "poly"   # BCC-Voronoi cells (config 5's cell type), 2 n^3 of them
+    m = cases.poly_case(n) if poly else cases.hex_case(n, n, n)
     f = cases.config4_fields(m)
     ctx = lib.Context(0)
     ctx.set_mesh(m)
@@ -29,7 +30,7 @@ def setup(n):
                     ("apw", "APW")):
         ctx.upload(name, f[k])
     ctx.grad_gauss("P", "DPDXI", 1)
-    ctx.calcp_assemble(lib.calcp_opts(solver="dpcg", const_mflux=True, sor=1e-8, nsw=100000))
+    ctx.calcp_assemble(lib.calcp_opts(solver="dpcg", const_mflux=True, sor=1e-8, nsw=100000, flux_variant=1 if poly else 0))
     return m, ctx
 
 
@@ -37,7 +38,7 @@ def sweeps(n):
     m, ctx = setup(n)
     nnz, nc = m.nnz, m.numCells
     ref = {}
-    for tiled, occ in ((0, 2), (2, 2), (4, 2), (4, 3)):
+    for tiled, occ in [(int(t.split(":")[0]), int(t.split(":")[1]) if ":" in t else 2) for t in os.environ.get("SWEEP_MODES", "0,2,4,5").split(",")]:
         ctx.set_tuning(lib.TUNE_SWEEP_TILED, tiled)
         ctx.set_tuning(lib.TUNE_TILE_CTAS, occ)
         for solver, nbytes, its in (("iccg", 24 * nnz + 164 * nc, 20), ("bicgstab", 2 * (24 * nnz + 164 * nc), 10)):
@@ -54,7 +55,7 @@ def sweeps(n):
                 ms_it = best / max(rep.iters, 1)
                 print(json.dumps(dict(op=f"{solver} iteration", n=n, sweep_tiled=tiled, tile_ctas=occ, ms_per_iteration=ms_it,
                                       gbs=nbytes / ms_it / 1e6, iters=rep.iters, resl=rep.resl,
-                                      bit_identical_to_level_schedule=bool(np.array_equal(x, ref[solver])),
+                                      bit_identical_to_level_schedule=bool(np.array_equal(x, ref[solver])) if solver in ref else None,
                                       schedule=ctx.sweep_schedule_info()[:160])), flush=True)
             except lib.FcError as e:
                 print(json.dumps(dict(op=f"{solver} iteration", sweep_tiled=tiled, tile_ctas=occ, error=str(e))), flush=True)

@@ -6,6 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["FC_SWEEP_TRACE_FILE"] = os.path.join(ROOT, "gpurun_out", "sweep_trace.txt")
 from freecappuccino_b200 import cases, lib
+lib.LIB_PATH = os.environ.get("FCAPP_LIB", os.path.join(ROOT, "freecappuccino_b200", "libfcapp_cuda_trace.so"))   # the -DFC_SWEEP_TRACE build
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 216
 poly = len(sys.argv) > 3 and sys.argv[3] == "poly"
 m = cases.poly_case(n) if poly else cases.hex_case(n, n, n)
@@ -27,6 +28,22 @@ t0 = t[:, 0].min()
 names = ["start->ticket", "ticket->meta", "meta->loaded", "loaded->flags", "flags->ldcg", "ldcg->walk_done", "walk_done->released"]
 if mode == 4:
     names = ["ticket->metas", "metas->pass2", "pass2->flags", "flags->pass3", "pass3->levstart", "levstart->walk_done", "walk_done->released"]
+if mode == 5:
+    # stamps: 0 ticket, 1 staged, 2 level table, 3 level 0 starts, 4 middle level starts, 5 walk done, 6 helper of thread 64 done
+    t = t[t[:, 5] > 0]
+    t0 = t[:, 0].min()
+    print("tiles traced", len(t), "sweep span us", (t[:, 5].max() - t0) / 1e3)
+    for nm, a, b in (("ticket->staged", 0, 1), ("staged->level table", 1, 2), ("table->level 0 starts (wait)", 2, 3),
+                     ("level 0->middle level", 3, 4), ("middle level->walk done", 4, 5), ("whole tile", 0, 5),
+                     ("staged->first helper done", 1, 6)):
+        x = t[:, b] - t[:, a]
+        x = x[(t[:, b] > 0) & (t[:, a] > 0)]
+        print(f"{nm:32s} median {np.median(x):8.0f} ns  mean {x.mean():8.0f}  p90 {np.percentile(x, 90):8.0f}")
+    ev = np.concatenate([np.stack([t[:, 0], np.ones(len(t))], 1), np.stack([t[:, 5], -np.ones(len(t))], 1)])
+    ev = ev[np.argsort(ev[:, 0])]
+    print("alive tiles (x16): mean", 16 * np.cumsum(ev[:, 1]).mean(), "max", 16 * np.cumsum(ev[:, 1]).max())
+    ctx.close()
+    sys.exit(0)
 d = np.diff(t[:, :8], axis=1)
 print("tiles traced", len(t), "sweep span us", (t[:, 7].max() - t0) / 1e3)
 for i, nm in enumerate(names):
