@@ -32,6 +32,32 @@ def scatter_case(g, part, f, fmi, gp):
     return out
 
 
+def noise_bars(parts, g, f, fmi, gp, oo, pc, seeds=6, factor=4.0, floor=1e-10):
+    """Per-field bar for a solver whose result the reference algorithm itself cannot hold to 1e-10: `factor` x the
+    largest change of the field over `seeds` runs of the lock-step oracle with one-ulp noise on the input velocities
+    (`pc` = the unperturbed oracle run), never below `floor`."""
+    from oracle import oracle_par as OP   # test infrastructure: the checker, never on the product path
+    world = len(parts)
+    bar = {k: floor for k in ("u", "v", "w", "p", "pp", "flmass")}
+    for seed in range(1, seeds + 1):
+        rng = np.random.default_rng(seed)
+        pq = OP.ParCase(parts)
+        for m, fl in zip(parts, pq.fields):
+            sc = scatter_case(g, m, f, fmi, gp)
+            for k in ("u", "v", "w", "p", "den", "apu", "apv", "apw", "dPdxi"):
+                getattr(fl, k)[:] = sc[k]
+            for k in ("u", "v", "w"):
+                arr = getattr(fl, k)
+                arr[:] = arr * (1.0 + 2.2e-16 * rng.integers(-1, 2, arr.size))
+            fl.fmi[:sc["fmi"].size] = sc["fmi"]
+        pq.calcp(oo)
+        for k in bar:
+            sens = max(cases.rel_l2(np.array(getattr(pq.fields[r], k)), np.array(getattr(pc.fields[r], k)))
+                       for r in range(world))
+            bar[k] = max(bar[k], factor * sens)
+    return bar
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -118,22 +144,7 @@ def main():
                 # the oracle's own input); DPCG and ICCG keep 1e-10 (their change under the same noise is 1e-13).
                 bar = {k: 1e-10 for k in ("u", "v", "w", "p", "pp", "flmass")}
                 if solver == "bicgstab":
-                    for seed in range(1, 7):
-                        rng = np.random.default_rng(seed)
-                        pq = OP.ParCase(parts)
-                        for m, fl in zip(parts, pq.fields):
-                            sc = scatter_case(g, m, f, fmi, gp)
-                            for k in ("u", "v", "w", "p", "den", "apu", "apv", "apw", "dPdxi"):
-                                getattr(fl, k)[:] = sc[k]
-                            for k in ("u", "v", "w"):
-                                arr = getattr(fl, k)
-                                arr[:] = arr * (1.0 + 2.2e-16 * rng.integers(-1, 2, arr.size))
-                            fl.fmi[:sc["fmi"].size] = sc["fmi"]
-                        pq.calcp(oo)
-                        for k in bar:
-                            sens = max(cases.rel_l2(np.array(getattr(pq.fields[r], k)), np.array(getattr(pc.fields[r], k)))
-                                       for r in range(world))
-                            bar[k] = max(bar[k], 4.0 * sens)
+                    bar = noise_bars(parts, g, f, fmi, gp, oo, pc)
                 worst = 0.0
                 for r in range(world):
                     for k in ("u", "v", "w", "p", "pp", "flmass"):

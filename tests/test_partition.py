@@ -140,3 +140,37 @@ def test_gloo_two_rank_distributed_dpcg():
     env = dict(os.environ, OMP_NUM_THREADS="1")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and "GLOO DPCG OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_noise_bars_of_the_multi_rank_check():
+    """tests/mgpu_check.py holds BiCGStab to a bar measured with the oracle itself (one-ulp noise on the input
+    velocities): on 2 ranks the reference algorithm is stable (bar = the north star's 1e-10), on the 8-rank partition
+    of the same kind of mesh one-ulp noise moves its result by more than 1e-9 -- with unchanged iteration counts."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mgpu_check_helpers", os.path.join(ROOT, "tests", "mgpu_check.py"))
+    src = open(spec.origin).read().split("def main")[0]
+    ns = {"__file__": spec.origin, "__name__": "mgpu_check_helpers"}
+    exec(compile(src, spec.origin, "exec"), ns)
+    from oracle import oracle as O, oracle_par as OP
+    for world, stable in ((2, True), (8, False)):
+        g = cases.hex_case(12, 9, 4 * world, kinds=("inlet", "outlet", "wall", "symmetry", "wall", "wall"))
+        f = cases.flow_fields(g)
+        fmi, flomas = cases.inlet_fluxes(g, f)
+        gp = O.grad_gauss(g, f["p"], 1)
+        parts = M.partition(g, M.slab_ranks(g.numCells, world), world)
+        oo = O.calcp_opts(solver="bicgstab", flomas=flomas, npcor=1, lsq_flag=False, nigrad=1, sor=1e-7, nsw=2000)
+        oo.sol.parallel = 1
+        pc = OP.ParCase(parts)
+        for m, fl in zip(parts, pc.fields):
+            sc = ns["scatter_case"](g, m, f, fmi, gp)
+            for k in ("u", "v", "w", "p", "den", "apu", "apv", "apw", "dPdxi"):
+                getattr(fl, k)[:] = sc[k]
+            fl.fmi[:sc["fmi"].size] = sc["fmi"]
+        rep = pc.calcp(oo)
+        assert rep.rep[0].iters < 200
+        bars = ns["noise_bars"](parts, g, f, fmi, gp, oo, pc, seeds=3)
+        assert set(bars) == {"u", "v", "w", "p", "pp", "flmass"} and min(bars.values()) >= 1e-10
+        if stable:
+            assert max(bars.values()) == 1e-10, bars
+        else:
+            assert max(bars.values()) > 1e-9, bars
