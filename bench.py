@@ -480,6 +480,10 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": "k_dpcg_persist<256,2304,2> (whole DPCG solve, one cooperative launch per step; column "
                                           + ("indices as one-byte codes)" if ib == 1 else "indices as int32)"),
                 "index_bytes_per_nonzero": ib, "bytes_moved_per_iteration": moved,
+                "note": ("achieved / frac use SURVEY 8(d)'s unit 12 nnz + 116 n per iteration; with one-byte column codes "
+                         "the kernel moves (8 + 1) nnz + 100 n (ncu: profiles/ncu_traffic.json), so frac can exceed 1 -- "
+                         "moved_gbs / moved_frac are the same launch time on the bytes actually moved") if ib == 1 else
+                        "achieved / frac use SURVEY 8(d)'s unit 12 nnz + 116 n per iteration; the kernel moves 12 nnz + 100 n",
                 "moved_gbs": moved * iters_per_step / (launch_ms * 1e-3) / 1e9,
                 "moved_frac": moved * iters_per_step / (launch_ms * 1e-3) / 1e9 / peak,
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
