@@ -1,9 +1,12 @@
-"""Opt-in checks of experimental kernel variants that are OFF by default (fc_set_tuning).  They have not run on
-hardware yet, so the default `pytest -m gpu` skips them; enable with FCAPP_EXPERIMENTAL=1.
+"""Opt-in checks of the kernel variants behind fc_set_tuning (the default ones included: every sweep schedule is compared
+with the level schedule).  They take a minute and repeat what the default suite checks for the default kernels, so the
+default `pytest -m gpu` skips them; enable with FCAPP_EXPERIMENTAL=1 (profiles/r02_pytest_experimental_final.log: 54 passed
+on B200).
 
 FC_TUNE_SWEEP_P2P: point-to-point block flags instead of one counter per level in the DIC / DILU triangular sweeps
 (fc_trisolve.cu).  FC_TUNE_SWEEP_TILED: two-level schedule, spatial tiles walked inside one CTA (fc_tile_schedule.hpp;
-its schedule is checked on the CPU by tests/test_tile_schedule.py).  The row sums are unchanged in both, so every
+its schedule and the kernel sources are checked on the CPU by tests/test_tile_schedule.py), hand-over by level counters,
+producer flags (modes 1, 2, 4) or the values themselves (modes 3, 5).  The row sums are unchanged in both, so every
 iterate must be bit-identical to the default mode."""
 import os
 import time
