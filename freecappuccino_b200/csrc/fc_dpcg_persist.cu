@@ -693,7 +693,9 @@ int fc_dpcg_persistent(fc_context *ctx, double *fi, const fc_solver_opts *o, fc_
   // (measured, profiles/r02_ja_coded.jsonl: -2 % per iteration at 10 M rows, -6 % at 2.5 M, +0.7 % at 1.26 M where
   // the product is bound by the latency of a chunk, not by its bytes)
   const bool coded = !fused && ctx->coded_ok && A.M.ja == ctx->ja &&
-                     (ctx->tune_ja_coded == 1 || (ctx->tune_ja_coded == 2 && n >= 2000000));
+                     (ctx->tune_ja_coded == 1 || (ctx->tune_ja_coded == 2 && n >= 2000000 && ctx->nranks == 1));
+  // (by default on one rank only: the coded kernel with processor strips compiles from the same template and is
+  // selectable with FC_TUNE_JA_CODED = 1, but the round's GPU time ended before it had run on several GPUs)
   if (coded) { A.M.jc = ctx->jcode; A.M.dict = ctx->jdict; }
   FC_CUDA(cudaMemsetAsync(ctx->pk, 0, sizeof(double) * ((size_t)n + ctx->npro), st));
   if (fused) FC_CUDA(cudaMemsetAsync(ctx->reso, 0, sizeof(double) * ((size_t)n + ctx->npro), st));

@@ -376,7 +376,7 @@ enum {
   FC_TUNE_JA_CODED = 13,       /* persistent DPCG kernel: the column indices travel as one-byte codes,
                                   ja[k] = row + offset[code[k]], when the pattern has at most 256 distinct column
                                   offsets (7 on a structured hexahedral block): 9 instead of 12 bytes per non-zero
-                                  and product, same columns, bit-identical results: 0 off, 1 on, [2] from 2 M rows
+                                  and product, same columns, bit-identical results: 0 off, 1 on, [2] from 2 M rows on one rank
                                   (below that the product is bound by the latency of a 256-row chunk, not its bytes) */
   FC_TUNE_DPCG_EAGER = 15,     /* persistent DPCG kernel on small partitions: fi += alf*pk runs behind the beta
                                   reduction (between a CTA's arrival at the barrier and its release) instead of inside
