@@ -93,6 +93,11 @@ void *fct_build(int n, const int *ioffset, const int *ja, const int *diag, const
                 const double *zc) {
   return new fc_tile_schedule(fc_build_tile_schedule(n, ioffset, ja, diag, xc, yc, zc));
 }
+// the same with narrower starting bins (the library starts polyhedral meshes at min_shrink = 2: 6 cells per axis)
+void *fct_build_shrunk(int n, const int *ioffset, const int *ja, const int *diag, const double *xc, const double *yc,
+                       const double *zc, int min_shrink) {
+  return new fc_tile_schedule(fc_build_tile_schedule(n, ioffset, ja, diag, xc, yc, zc, min_shrink));
+}
 void fct_free(void *h) { delete (fc_tile_schedule *)h; }
 int fct_ok(void *h) { return ((fc_tile_schedule *)h)->ok ? 1 : 0; }
 const char *fct_why(void *h) { return ((fc_tile_schedule *)h)->why.c_str(); }

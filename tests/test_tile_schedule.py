@@ -29,6 +29,7 @@ def host():
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++20", "-pthread", "-o", so, src])
     lib = C.CDLL(so)
     lib.fct_build.restype = C.c_void_p
+    lib.fct_build_shrunk.restype = C.c_void_p
     lib.fct_why.restype = C.c_char_p
     return lib
 
@@ -325,6 +326,34 @@ def test_tile_walk_vf_kernel_source_on_host_threads_equals_natural_order_sweeps(
             d = emu(DILU, zero, zero, pre8=pre8)
             t = emu(FWD, d, s.r, pre8=pre8)
             emu(BWD, d, t, pre8=pre8)
+    finally:
+        host.fct_free(C.c_void_p(h))
+
+
+@pytest.mark.parametrize("name", ["poly-6", "poly-rank-of-4", "poly-12", "hex-24x20x17", "pitzDaily"])
+@pytest.mark.parametrize("shrink", [1, 2, 3])
+def test_narrower_bins_give_valid_and_exact_schedules(host, name, shrink):
+    """fc_build_tile_schedule(min_shrink): the library starts meshes with more than 10 non-zeros per row (polyhedra) at
+    6-cell bins (min_shrink = 2; profiles/r02_poly_bins.txt).  Every bin width must give an acyclic tile graph, no row
+    visited before its dependencies, values through global memory only from lower tile levels / named producers, and
+    sweeps bit-identical to the natural-order ones -- also on a rank-local mesh of a partition."""
+    mesh = cases.poly_case(12) if name == "poly-12" else MESHES[name]()
+    s = System(mesh)
+    h = host.fct_build_shrunk(s.n, ip(s.ioffset), ip(s.ja), ip(s.diag), dp(s.xc), dp(s.yc), dp(s.zc), shrink)
+    try:
+        assert host.fct_ok(C.c_void_p(h)), host.fct_why(C.c_void_p(h)).decode()
+        info = np.zeros(11, np.int32)
+        host.fct_info(C.c_void_p(h), ip(info))
+        assert info[2] <= 512   # rows of the largest tile
+        zero = np.zeros(s.n)
+        for mode, padd in ((DIC, 0.0), (DIC_PAR, 1e-20), (DILU, 0.0)):
+            ref, out, bad = run(host, h, s, mode, zero, zero, padd=padd)
+            assert bad == 0 and np.array_equal(ref, out), (name, shrink, mode, bad)
+        d = out
+        ref, t, bad = run(host, h, s, FWD, d, s.r)
+        assert bad == 0 and np.array_equal(ref, t), (name, shrink, "fwd", bad)
+        ref, z, bad = run(host, h, s, BWD, d, t)
+        assert bad == 0 and np.array_equal(ref, z), (name, shrink, "bwd", bad)
     finally:
         host.fct_free(C.c_void_p(h))
 
