@@ -733,10 +733,11 @@ int build_tiles(fc_context *ctx) {
   FC_CUDA(cudaMemcpy(zc.data(), ctx->zc, sizeof(double) * n, cudaMemcpyDeviceToHost));
   const fc_tile_schedule S =
       fc_build_tile_schedule(ctx->n, ioffset.data(), ja.data(), diag.data(), xc.data(), yc.data(), zc.data(),
-                             // polyhedral rows (~15 non-zeros) walk 32 local levels in a 7-cell bin; bins of 6 cells per
-                             // axis measured 11 % faster on a 4.2 M-cell BCC-Voronoi mesh (profiles/r02_poly_bins.txt),
-                             // bins of 5 slower again; hexahedra keep 8
-                             getenv("FC_TILE_MIN_SHRINK") ? atoi(getenv("FC_TILE_MIN_SHRINK")) : ((long long)nnz > 10LL * n ? 2 : 0));
+                             // FC_TILE_MIN_SHRINK: narrower bins, a measurement knob.  On polyhedral meshes 6-cell bins
+                             // measured 11 % faster at 4.2 M cells (profiles/r02_poly_bins.txt) but 12 % slower at the
+                             // 20 M cells of config 5 (13.2 against 11.8 ms per ICCG iteration in the bench line), so the
+                             // default stays at the widest bins that fit a tile
+                             getenv("FC_TILE_MIN_SHRINK") ? atoi(getenv("FC_TILE_MIN_SHRINK")) : 0);
   ctx->tiles_why = S.why;
   if (!S.ok) return FC_OK;
   // bins cut into runs of consecutive rows (fc_tile_schedule.hpp repair_tiles) can degenerate into a long chain: keep

@@ -333,8 +333,8 @@ def test_tile_walk_vf_kernel_source_on_host_threads_equals_natural_order_sweeps(
 @pytest.mark.parametrize("name", ["poly-6", "poly-rank-of-4", "poly-12", "hex-24x20x17", "pitzDaily"])
 @pytest.mark.parametrize("shrink", [1, 2, 3])
 def test_narrower_bins_give_valid_and_exact_schedules(host, name, shrink):
-    """fc_build_tile_schedule(min_shrink): the library starts meshes with more than 10 non-zeros per row (polyhedra) at
-    6-cell bins (min_shrink = 2; profiles/r02_poly_bins.txt).  Every bin width must give an acyclic tile graph, no row
+    """fc_build_tile_schedule(min_shrink): narrower starting bins (FC_TILE_MIN_SHRINK in the library, a measurement
+    knob: profiles/r02_poly_bins.txt).  Every bin width must give an acyclic tile graph, no row
     visited before its dependencies, values through global memory only from lower tile levels / named producers, and
     sweeps bit-identical to the natural-order ones -- also on a rank-local mesh of a partition."""
     mesh = cases.poly_case(12) if name == "poly-12" else MESHES[name]()
